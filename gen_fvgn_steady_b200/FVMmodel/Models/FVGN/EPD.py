@@ -1,0 +1,105 @@
+"""Encoder / GnBlock / Decoder / EncoderProcesserDecoder with the reference's module API and state_dict
+keys (src/FVMmodel/Models/FVGN/EPD.py:10-270).  The nn.Linear / nn.LayerNorm children only hold the
+parameters; every forward is a fused sm_100a kernel behind a torch.autograd.Function (ops.py)."""
+import torch
+from torch import nn
+
+from ....data import Data
+from .... import ops
+from ....plan import GraphPlan
+from .blocks import EdgeBlock, NodeBlock, mlp_params, _precision
+
+
+def build_mlp(in_size, hidden_size, out_size, drop_out=True, lay_norm=True, dropout_prob=0.2):
+    """Linear-GELU-Linear-GELU-Linear [+LayerNorm] parameter container (EPD.py:10-33)."""
+    if drop_out:
+        raise NotImplementedError("drop_out=True is never used on the live path (EPD.py:98-103,163-175)")
+    if hidden_size != 128 or out_size != 128:
+        raise NotImplementedError("fvgn_b200 kernels are built for hidden_size=128")
+    module = nn.Sequential(nn.Linear(in_size, hidden_size), nn.GELU(), nn.Linear(hidden_size, hidden_size), nn.GELU(),
+                           nn.Linear(hidden_size, out_size))
+    if lay_norm:
+        return nn.Sequential(module, nn.LayerNorm(normalized_shape=out_size))
+    return module
+
+
+def build_mlp_from_num_layer(in_size, hidden_size, out_size, drop_out=False, lay_norm=True, dropout_prob=0.2, num_layer=2):
+    """EPD.py:36-63; the live path uses num_layer=2, lay_norm=False (the decoder)."""
+    if drop_out or num_layer != 2 or lay_norm:
+        raise NotImplementedError("only the decoder configuration (num_layer=2, no LayerNorm, no dropout) is on the path")
+    return nn.Sequential(nn.Linear(in_size, hidden_size), nn.GELU(), nn.Linear(hidden_size, hidden_size), nn.GELU(),
+                         nn.Linear(hidden_size, out_size))
+
+
+def _carry(graph, **updates):
+    out = Data(x=graph.x, edge_attr=getattr(graph, "edge_attr", None), edge_index=graph.edge_index,
+               face=getattr(graph, "face", None), num_graphs=getattr(graph, "num_graphs", None),
+               batch=getattr(graph, "batch", None))
+    for k in ("pos", "_fvgn_plan"):
+        if hasattr(graph, k):
+            setattr(out, k, getattr(graph, k))
+    for k, v in updates.items():
+        setattr(out, k, v)
+    return out
+
+
+class Encoder(nn.Module):
+    def __init__(self, node_input_size=128, edge_input_size=128, hidden_size=128):
+        super().__init__()
+        if node_input_size != 12 or edge_input_size != 15:
+            raise NotImplementedError("encoder kernels are built for node_input_size=12, edge_input_size=15 (importer.py:22-30)")
+        self.eb_encoder = build_mlp(edge_input_size, hidden_size, int(hidden_size), drop_out=False)
+        self.nb_encoder = build_mlp(node_input_size, hidden_size, int(hidden_size), drop_out=False)
+
+    def forward(self, graph_node, graph_cell=None):
+        """graph_node.x is the normalised [N,12] feature; the [E,15] relative edge feature of
+        importer.py:54-78 is computed inside the edge-encoder kernel from x and pos."""
+        plan = GraphPlan.of(graph_node)
+        node_, edge_ = ops.EncoderFn.apply(graph_node.x.contiguous(), graph_node.pos.float().contiguous(), plan,
+                                           _precision(self), *mlp_params(self.nb_encoder), *mlp_params(self.eb_encoder))
+        return _carry(graph_node, x=node_, edge_attr=edge_, _fvgn_plan=plan), node_
+
+
+class GnBlock(nn.Module):
+    def __init__(self, hidden_size=128, drop_out=False):
+        super().__init__()
+        eb_input_dim = int(3 * hidden_size)
+        nb_input_dim = int(hidden_size + (hidden_size // 2.0))
+        self.nb_module = NodeBlock(hidden_size, custom_func=build_mlp(nb_input_dim, hidden_size, int(hidden_size), drop_out=drop_out))
+        self.eb_module = EdgeBlock(input_size=hidden_size, custom_func=build_mlp(eb_input_dim, hidden_size, int(hidden_size), drop_out=drop_out))
+
+    def forward(self, graph_node):
+        plan = GraphPlan.of(graph_node)
+        x, e = ops.GnBlockFn.apply(graph_node.x, graph_node.edge_attr, plan, _precision(self),
+                                   *mlp_params(self.eb_module.net), *mlp_params(self.nb_module.net))
+        return _carry(graph_node, x=x, edge_attr=e, _fvgn_plan=plan)
+
+
+class Decoder(nn.Module):
+    def __init__(self, hidden_sze=128, node_output_size=3):
+        super().__init__()
+        if node_output_size != 3:
+            raise NotImplementedError("decoder kernel is built for node_output_size=3")
+        self.node_decode_module = build_mlp_from_num_layer(hidden_sze, hidden_sze, node_output_size, drop_out=False,
+                                                           lay_norm=False, num_layer=2)
+
+    def forward(self, latent_graph_node=None):
+        return ops.DecoderFn.apply(latent_graph_node.x, _precision(self), *mlp_params(self.node_decode_module))
+
+
+class EncoderProcesserDecoder(nn.Module):
+    """Pure GN composition (EPD.py:222-270)."""
+
+    def __init__(self, message_passing_num, edge_input_size, node_input_size, node_output_size, drop_out=False,
+                 hidden_size=128, params=None):
+        super().__init__()
+        self.encoder = Encoder(node_input_size=node_input_size, edge_input_size=edge_input_size, hidden_size=hidden_size)
+        self.GN_block_list = nn.ModuleList([GnBlock(hidden_size=hidden_size, drop_out=drop_out)
+                                            for _ in range(message_passing_num)])
+        self.decoder = Decoder(hidden_sze=hidden_size, node_output_size=node_output_size)
+
+    def forward(self, graph_node=None, graph_edge=None, graph_cell=None):
+        latent, _ = self.encoder(graph_node)
+        for model in self.GN_block_list:
+            latent = model(latent)
+        return self.decoder(latent)

@@ -1,0 +1,23 @@
+"""TransFVGN_v1 Simulator (src/FVMmodel/Models/TransFVGN/TransFVGN_v1.py:10-73): Encoder -> GnBlock x mp -> Transolver -> Decoder."""
+from torch import nn
+
+from ..FVGN.EPD import Encoder, Decoder, GnBlock
+from ..GraphTransolver.GraphTransolver import Transolver_block
+
+
+class Simulator(nn.Module):
+    def __init__(self, message_passing_num, edge_input_size, node_input_size, node_output_size, drop_out=False,
+                 hidden_size=128, params=None):
+        super().__init__()
+        self.encoder = Encoder(node_input_size=node_input_size, edge_input_size=edge_input_size, hidden_size=hidden_size)
+        self.GN_block_list = nn.ModuleList([GnBlock(hidden_size=hidden_size, drop_out=drop_out)
+                                            for _ in range(message_passing_num)])
+        self.TransBlock = Transolver_block(num_heads=8, hidden_dim=hidden_size, dropout=0, act="gelu", mlp_ratio=2, slice_num=32)
+        self.decoder = Decoder(hidden_sze=hidden_size, node_output_size=node_output_size)
+
+    def forward(self, graph_node=None, graph_edge=None, graph_cell=None):
+        latent, node_embedding = self.encoder(graph_node)
+        for model in self.GN_block_list:
+            latent = model(latent)
+        latent.x = self.TransBlock(latent.x + node_embedding, graph_node.batch)
+        return self.decoder(latent)

@@ -1,0 +1,39 @@
+"""TransFVGN_v2 Simulator (src/FVMmodel/Models/TransFVGN/TransFVGN_v2.py:12-104): Encoder -> 2 x (GnBlock x mp -> Transolver) -> Decoder."""
+from torch import nn
+
+from ..FVGN.EPD import Encoder, Decoder, GnBlock
+from ..GraphTransolver.GraphTransolver import Transolver_block
+
+
+class AttnProcessor(nn.Module):
+    def __init__(self, message_passing_num=0, hidden_size=128, drop_out=False):
+        super().__init__()
+        if message_passing_num < 1:
+            raise ValueError("message_passing_num must be greater than 0")
+        self.GN_block_list = nn.ModuleList([GnBlock(hidden_size=hidden_size, drop_out=drop_out)
+                                            for _ in range(message_passing_num)])
+        self.TransBlock = Transolver_block(num_heads=8, hidden_dim=hidden_size, dropout=0, act="gelu", mlp_ratio=2, slice_num=32)
+
+    def forward(self, latent_graph_node, graph_edge):
+        node_embedding = latent_graph_node.x
+        latent = latent_graph_node
+        for model in self.GN_block_list:
+            latent = model(latent)
+        latent.x = self.TransBlock(latent.x + node_embedding, latent.batch)
+        return latent
+
+
+class Simulator(nn.Module):
+    def __init__(self, message_passing_num, edge_input_size, node_input_size, node_output_size, drop_out=False,
+                 hidden_size=128, params=None):
+        super().__init__()
+        self.encoder = Encoder(node_input_size=node_input_size, edge_input_size=edge_input_size, hidden_size=hidden_size)
+        self.processpr_list = nn.ModuleList([AttnProcessor(message_passing_num=message_passing_num, hidden_size=hidden_size,
+                                                           drop_out=False) for _ in range(2)])
+        self.decoder = Decoder(hidden_sze=hidden_size, node_output_size=node_output_size)
+
+    def forward(self, graph_node=None, graph_edge=None, graph_cell=None):
+        latent, _ = self.encoder(graph_node)
+        for model in self.processpr_list:
+            latent = model(latent, graph_edge)
+        return self.decoder(latent)

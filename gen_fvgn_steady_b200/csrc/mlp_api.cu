@@ -1,0 +1,96 @@
+// C-ABI entry points of the fused MLP blocks: validation + dispatch to the fp32 SIMT kernels
+// (mlp_simt.cu) or the bf16 tcgen05 kernels (mlp_tc.cu).
+#include "common.cuh"
+
+int fvgn_mlp_forward_simt(const fvgn_mlp_desc* d, void* stream);
+int fvgn_mlp_backward_simt(const fvgn_mlp_desc* d, void* stream);
+int fvgn_mlp_simt_partials(int64_t rows);
+int64_t fvgn_mlp_param_count_impl(int32_t mode);
+#ifndef FVGN_EMU
+int fvgn_mlp_forward_tc(const fvgn_mlp_desc* d, void* stream);
+int fvgn_mlp_backward_tc(const fvgn_mlp_desc* d, void* stream);
+int fvgn_mlp_tc_partials(int32_t mode, int64_t rows);
+int64_t fvgn_mlp_tc_packed_bytes(int32_t mode);
+int fvgn_mlp_tc_pack(int32_t mode, const float* w1, const float* w2, const float* w3, void* packed, void* stream);
+#endif
+
+extern "C" int fvgn_version(void) {
+#ifdef FVGN_EMU
+  return 0x0100 << 8;  // emulated build: neither sm_100a nor tcgen05
+#else
+  return (0x0100 << 8) | 1 | 2;
+#endif
+}
+
+extern "C" int64_t fvgn_mlp_param_count(int32_t mode) { return fvgn_mlp_param_count_impl(mode); }
+
+extern "C" int32_t fvgn_mlp_bwd_partials(int32_t mode, int32_t precision, int64_t rows) {
+#ifndef FVGN_EMU
+  if (precision == FVGN_PREC_BF16) return fvgn_mlp_tc_partials(mode, rows);
+#endif
+  (void)mode;
+  (void)precision;
+  return fvgn_mlp_simt_partials(rows);
+}
+
+extern "C" int64_t fvgn_mlp_packed_bytes(int32_t mode) {
+#ifndef FVGN_EMU
+  return fvgn_mlp_tc_packed_bytes(mode);
+#else
+  (void)mode;
+  return 0;
+#endif
+}
+
+extern "C" int fvgn_mlp_pack_weights(int32_t mode, const float* w1, const float* w2, const float* w3, void* packed,
+                                     void* stream) {
+#ifndef FVGN_EMU
+  return fvgn_mlp_tc_pack(mode, w1, w2, w3, packed, stream);
+#else
+  (void)mode; (void)w1; (void)w2; (void)w3; (void)packed; (void)stream;
+  return FVGN_ERR_UNSUPPORTED;
+#endif
+}
+
+static int check_common(const fvgn_mlp_desc* d) {
+  if (!d) return FVGN_ERR_NULL;
+  if (d->mode < FVGN_MLP_EDGE || d->mode > FVGN_MLP_DEC) return FVGN_ERR_UNSUPPORTED;
+  if (d->rows < 0) return FVGN_ERR_SHAPE;
+  if (!d->in0 || !d->w1 || !d->b1 || !d->w2 || !d->b2 || !d->w3 || !d->b3) return FVGN_ERR_NULL;
+  if (d->mode != FVGN_MLP_DEC && (!d->ln_g || !d->ln_b)) return FVGN_ERR_NULL;
+  if ((d->mode == FVGN_MLP_EDGE || d->mode == FVGN_MLP_ENC_EDGE) && (!d->idx_s || !d->idx_r || !d->in1)) return FVGN_ERR_NULL;
+  if (d->mode == FVGN_MLP_NODE && !d->in1) return FVGN_ERR_NULL;
+  if (!fvgn_aligned16(d->in0) || !fvgn_aligned16(d->in1) || !fvgn_aligned16(d->out) || !fvgn_aligned16(d->out_res) ||
+      !fvgn_aligned16(d->d_out) || !fvgn_aligned16(d->d_gather) || !fvgn_aligned16(d->d_in0) ||
+      !fvgn_aligned16(d->d_in1) || !fvgn_aligned16(d->ln_g) || !fvgn_aligned16(d->ln_b))
+    return FVGN_ERR_ALIGN;
+  return FVGN_OK;
+}
+
+extern "C" int fvgn_mlp_forward(const fvgn_mlp_desc* d, void* stream) {
+  int rc = check_common(d);
+  if (rc) return rc;
+  if ((d->mode == FVGN_MLP_EDGE || d->mode == FVGN_MLP_NODE) ? (!d->out_res && !d->out) : !d->out) return FVGN_ERR_NULL;
+  if (d->rows == 0) return FVGN_OK;
+  if (d->precision == FVGN_PREC_FP32) return fvgn_mlp_forward_simt(d, stream);
+#ifndef FVGN_EMU
+  if (d->precision == FVGN_PREC_BF16) return fvgn_mlp_forward_tc(d, stream);
+#endif
+  return FVGN_ERR_UNSUPPORTED;
+}
+
+extern "C" int fvgn_mlp_backward(const fvgn_mlp_desc* d, void* stream) {
+  int rc = check_common(d);
+  if (rc) return rc;
+  if (!d->d_out || !d->partials || !d->d_params || d->n_partials < 1) return FVGN_ERR_NULL;
+  if ((d->mode == FVGN_MLP_EDGE || d->mode == FVGN_MLP_NODE) && (!d->d_in0 || !d->d_in1)) return FVGN_ERR_NULL;
+  if (d->mode == FVGN_MLP_DEC && !d->d_in0) return FVGN_ERR_NULL;
+  if (d->precision == FVGN_PREC_FP32) {
+    if (d->n_partials != fvgn_mlp_simt_partials(d->rows)) return FVGN_ERR_SHAPE;
+    return fvgn_mlp_backward_simt(d, stream);
+  }
+#ifndef FVGN_EMU
+  if (d->precision == FVGN_PREC_BF16) return fvgn_mlp_backward_tc(d, stream);
+#endif
+  return FVGN_ERR_UNSUPPORTED;
+}

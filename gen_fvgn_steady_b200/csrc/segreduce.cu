@@ -1,0 +1,127 @@
+// Deterministic CSR segmented reductions over the mesh graph (replace torch_scatter atomics).
+//
+// Reference semantics:
+//   agg_i = sum_{j in Adj(i)} x_j                     blocks.py:92-99   (scatter_add of x[cat(r,s)] by cat(s,r))
+//   a1_i  = sum_{f: s_f=i} e'_f[0:H/2] + sum_{f: r_f=i} e'_f[H/2:H]   blocks.py:24-42
+//   a2_i  = (1/deg_i) sum_{j in Adj(i)} a1_j          blocks.py:44-51   (scatter_mean, deg clamped >= 1)
+// The CSR lists are the *stable* grouping of the reference's scatter entry order by destination,
+// so every row is summed in exactly the order a sequential index_add_ would use: results are
+// bit-reproducible and equal to the CPU reference's fp32 sums.
+// Backward of each is the same kernel (Adj is symmetric; the incidence transpose is a gather that
+// the MLP backward prologue performs).
+//
+// Mapping: W/4 lanes per row, one float4 per lane (a 512-B row is one fully coalesced warp access).
+#include "common.cuh"
+
+template <int W>
+__global__ void __launch_bounds__(256) adj_reduce_kernel(const float* __restrict__ src, const int32_t* __restrict__ ptr,
+                                                         const int32_t* __restrict__ nbr, float* __restrict__ dst,
+                                                         int64_t n, int flags) {
+  constexpr int LPR = W / 4;
+  constexpr int RPB = 256 / LPR;
+  const int64_t row = (int64_t)blockIdx.x * RPB + threadIdx.x / LPR;
+  const int lane = threadIdx.x % LPR;
+  if (row >= n) return;
+  const int beg = ptr[row], end = ptr[row + 1];
+  const bool div_src = flags & FVGN_ADJ_DIV_SRC_BY_DEG;
+  float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+  int t = beg;
+  for (; t + 4 <= end; t += 4) {
+    int j[4];
+    float4 v[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) j[u] = nbr[t + u];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) v[u] = ld4(src + (size_t)j[u] * W + lane * 4);
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      if (div_src) {
+        const float d = (float)max(ptr[j[u] + 1] - ptr[j[u]], 1);
+        v[u].x /= d; v[u].y /= d; v[u].z /= d; v[u].w /= d;
+      }
+      acc = add4(acc, v[u]);
+    }
+  }
+  for (; t < end; ++t) {
+    const int j = nbr[t];
+    float4 v = ld4(src + (size_t)j * W + lane * 4);
+    if (div_src) {
+      const float d = (float)max(ptr[j + 1] - ptr[j], 1);
+      v.x /= d; v.y /= d; v.z /= d; v.w /= d;
+    }
+    acc = add4(acc, v);
+  }
+  if (flags & FVGN_ADJ_DIV_DST_BY_DEG) {
+    const float d = (float)max(end - beg, 1);
+    acc.x /= d; acc.y /= d; acc.z /= d; acc.w /= d;
+  }
+  float* o = dst + (size_t)row * W + lane * 4;
+  if (flags & FVGN_ADJ_ACCUMULATE) acc = add4(ld4(o), acc);
+  st4(o, acc);
+}
+
+// dst[i, 0:W] = sum over incidence entries (edge f, role) of src[f, role*W : role*W + W]
+template <int W>
+__global__ void __launch_bounds__(256) inc_reduce_kernel(const float* __restrict__ src, const int32_t* __restrict__ ptr,
+                                                         const int32_t* __restrict__ code, float* __restrict__ dst,
+                                                         int64_t n) {
+  constexpr int LPR = W / 4;
+  constexpr int RPB = 256 / LPR;
+  const int64_t row = (int64_t)blockIdx.x * RPB + threadIdx.x / LPR;
+  const int lane = threadIdx.x % LPR;
+  if (row >= n) return;
+  const int beg = ptr[row], end = ptr[row + 1];
+  float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+  int t = beg;
+  for (; t + 4 <= end; t += 4) {
+    int c[4];
+    float4 v[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) c[u] = code[t + u];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) v[u] = ld4(src + (size_t)(c[u] >> 1) * (2 * W) + (c[u] & 1) * W + lane * 4);
+#pragma unroll
+    for (int u = 0; u < 4; ++u) acc = add4(acc, v[u]);
+  }
+  for (; t < end; ++t) {
+    const int c = code[t];
+    acc = add4(acc, ld4(src + (size_t)(c >> 1) * (2 * W) + (c & 1) * W + lane * 4));
+  }
+  st4(dst + (size_t)row * W + lane * 4, acc);
+}
+
+extern "C" int fvgn_adj_reduce(const float* src, const int32_t* ptr, const int32_t* nbr, float* dst, int64_t n_rows,
+                               int32_t width, int32_t flags, void* stream) {
+  if (n_rows < 0) return FVGN_ERR_SHAPE;
+  if (n_rows == 0) return FVGN_OK;
+  if (!fvgn_aligned16(src) || !fvgn_aligned16(dst)) return FVGN_ERR_ALIGN;
+  if (width == 128) {
+    const unsigned grid = (unsigned)((n_rows + 7) / 8);
+    FVGN_LAUNCH_SEQ(adj_reduce_kernel<128>, grid, 256, 0, stream, src, ptr, nbr, dst, n_rows, flags);
+  } else if (width == 64) {
+    const unsigned grid = (unsigned)((n_rows + 15) / 16);
+    FVGN_LAUNCH_SEQ(adj_reduce_kernel<64>, grid, 256, 0, stream, src, ptr, nbr, dst, n_rows, flags);
+  } else {
+    return FVGN_ERR_UNSUPPORTED;
+  }
+  FVGN_CHECK_LAUNCH();
+  return FVGN_OK;
+}
+
+extern "C" int fvgn_inc_reduce(const float* src, const int32_t* ptr, const int32_t* code, float* dst, int64_t n_rows,
+                               int32_t width, void* stream) {
+  if (n_rows < 0) return FVGN_ERR_SHAPE;
+  if (n_rows == 0) return FVGN_OK;
+  if (!fvgn_aligned16(src) || !fvgn_aligned16(dst)) return FVGN_ERR_ALIGN;
+  if (width == 128) {
+    const unsigned grid = (unsigned)((n_rows + 7) / 8);
+    FVGN_LAUNCH_SEQ(inc_reduce_kernel<128>, grid, 256, 0, stream, src, ptr, code, dst, n_rows);
+  } else if (width == 64) {
+    const unsigned grid = (unsigned)((n_rows + 15) / 16);
+    FVGN_LAUNCH_SEQ(inc_reduce_kernel<64>, grid, 256, 0, stream, src, ptr, code, dst, n_rows);
+  } else {
+    return FVGN_ERR_UNSUPPORTED;
+  }
+  FVGN_CHECK_LAUNCH();
+  return FVGN_OK;
+}

@@ -1,0 +1,402 @@
+"""torch.autograd.Function wrappers over the C-ABI kernels, each with a hand-written backward.
+
+No torch_scatter / PyG / Triton / torch.compile anywhere; PyTorch only owns memory, streams and the
+autograd graph between these ops.
+"""
+import ctypes
+import os
+
+import torch
+
+from . import _lib
+from ._lib import fptr, iptr
+
+PREC = {"fp32": _lib.FVGN_PREC_FP32, "bf16": _lib.FVGN_PREC_BF16}
+
+
+def default_precision():
+    return os.environ.get("FVGN_PRECISION", "fp32")
+
+
+def _empty(shape, like):
+    return torch.empty(shape, dtype=torch.float32, device=like.device)
+
+
+def _c(t):
+    return t if t.is_contiguous() else t.contiguous()
+
+
+# ------------------------------------------------------------------ raw kernel calls
+def adj_reduce(src, plan, width, flags=0, out=None):
+    """out[i] = sum_{j in Adj(i)} src[j]  (blocks.py:92-99 / :44-51)."""
+    if out is None:
+        out = _empty((plan.N, width), src)
+    _lib.call("fvgn_adj_reduce", fptr(src), iptr(plan.inc_ptr), iptr(plan.inc_nbr), fptr(out), plan.N, width, flags,
+              _lib.stream_ptr(src.device))
+    return out
+
+
+def inc_reduce(src, plan, width):
+    """out[i] = sum over incident (edge, role) of src[edge, role*width:(role+1)*width]  (blocks.py:24-42)."""
+    out = _empty((plan.N, width), src)
+    _lib.call("fvgn_inc_reduce", fptr(src), iptr(plan.inc_ptr), iptr(plan.inc_code), fptr(out), plan.N, width,
+              _lib.stream_ptr(src.device))
+    return out
+
+
+_MLP_K1 = {_lib.FVGN_MLP_EDGE: 384, _lib.FVGN_MLP_NODE: 192, _lib.FVGN_MLP_ENC_NODE: 12, _lib.FVGN_MLP_ENC_EDGE: 15,
+           _lib.FVGN_MLP_DEC: 128}
+
+
+class PackedWeights:
+    """bf16 UMMA operand images of the MLP weights, rebuilt whenever a parameter's version counter moves."""
+    _cache = {}
+
+    @classmethod
+    def get(cls, mode, params):
+        w1, w2, w3 = params[0], params[2], params[4]
+        key = (w1.data_ptr(), w2.data_ptr(), w3.data_ptr())
+        ver = (w1._version, w2._version, w3._version)
+        hit = cls._cache.get(key)
+        if hit is not None and hit[0] == ver:
+            return hit[1]
+        nbytes = int(_lib.load().fvgn_mlp_packed_bytes(mode))
+        buf = torch.empty(max(nbytes, 16), dtype=torch.uint8, device=w1.device)
+        _lib.call("fvgn_mlp_pack_weights", mode, fptr(_c(w1.detach())), fptr(_c(w2.detach())), fptr(_c(w3.detach())),
+                  _lib.ptr(buf), _lib.stream_ptr(w1.device))
+        cls._cache[key] = (ver, buf)
+        return buf
+
+
+def _mlp_desc(mode, precision, rows, params, in0, in1=None, idx_s=None, idx_r=None, flags=0):
+    d = _lib.MlpDesc()
+    d.mode, d.precision, d.rows, d.flags = mode, PREC[precision], rows, flags
+    d.in0, d.in1 = fptr(in0), fptr(in1, True)
+    d.idx_s, d.idx_r = iptr(idx_s, True), iptr(idx_r, True)
+    ps = [_c(p.detach()) for p in params]
+    d._keep = ps  # keep contiguous copies alive for the duration of the call
+    d.w1, d.b1, d.w2, d.b2, d.w3, d.b3 = (fptr(p) for p in ps[:6])
+    if len(ps) == 8:
+        d.ln_g, d.ln_b = fptr(ps[6]), fptr(ps[7])
+    if precision == "bf16":
+        d._packed = PackedWeights.get(mode, params)
+        d.w_bf16 = _lib.ptr(d._packed)
+    return d
+
+
+def mlp_forward(mode, precision, rows, params, in0, in1=None, idx_s=None, idx_r=None, want_out=True, want_res=False,
+                flags=0):
+    d = _mlp_desc(mode, precision, rows, params, in0, in1, idx_s, idx_r, flags)
+    nout = 3 if mode == _lib.FVGN_MLP_DEC else 128
+    out = _empty((rows, nout), in0) if want_out else None
+    res = _empty((rows, 128), in0) if want_res else None
+    d.out, d.out_res = fptr(out, True), fptr(res, True)
+    _lib.call("fvgn_mlp_forward", ctypes.byref(d), _lib.stream_ptr(in0.device))
+    return out, res
+
+
+def mlp_backward(mode, precision, rows, params, in0, in1, idx_s, idx_r, d_out, d_gather=None, d_in0=None, d_in1=None,
+                 flags=0):
+    """Runs the fused backward; returns the list of parameter gradients (views of one flat buffer)."""
+    d = _mlp_desc(mode, precision, rows, params, in0, in1, idx_s, idx_r, flags)
+    lib = _lib.load()
+    pc = int(lib.fvgn_mlp_param_count(mode))
+    npart = int(lib.fvgn_mlp_bwd_partials(mode, PREC[precision], rows))
+    partials = _empty((npart, pc), in0)
+    flat = _empty((pc,), in0)
+    d.d_out, d.d_gather = fptr(d_out), fptr(d_gather, True)
+    d.d_in0, d.d_in1 = fptr(d_in0, True), fptr(d_in1, True)
+    d.partials, d.n_partials, d.d_params = fptr(partials), npart, fptr(flat)
+    _lib.call("fvgn_mlp_backward", ctypes.byref(d), _lib.stream_ptr(in0.device))
+    k1 = _MLP_K1[mode]
+    nout = 3 if mode == _lib.FVGN_MLP_DEC else 128
+    sizes = [(128, k1), (128,), (128, 128), (128,), (nout, 128), (nout,)]
+    if len(params) == 8:
+        sizes += [(128,), (128,)]
+    grads, off = [], 0
+    for shp in sizes:
+        n = 1
+        for s in shp:
+            n *= s
+        grads.append(flat[off:off + n].view(shp))
+        off += n
+    return grads
+
+
+# ------------------------------------------------------------------ Encoder
+class EncoderFn(torch.autograd.Function):
+    """Encoder.forward (EPD.py:116-153) with the relative edge features of importer.py:54-78 fused in."""
+
+    @staticmethod
+    def forward(ctx, xn, pos, plan, precision, *params):
+        nb, eb = params[:8], params[8:]
+        node, _ = mlp_forward(_lib.FVGN_MLP_ENC_NODE, precision, plan.N, nb, xn)
+        edge, _ = mlp_forward(_lib.FVGN_MLP_ENC_EDGE, precision, plan.E, eb, xn, pos, plan.edge_s, plan.edge_r)
+        ctx.plan, ctx.precision = plan, precision
+        ctx.save_for_backward(xn, pos, *params)
+        return node, edge
+
+    @staticmethod
+    def backward(ctx, d_node, d_edge):
+        xn, pos, *params = ctx.saved_tensors
+        plan, precision = ctx.plan, ctx.precision
+        gn = mlp_backward(_lib.FVGN_MLP_ENC_NODE, precision, plan.N, params[:8], xn, None, None, None, _c(d_node))
+        ge = mlp_backward(_lib.FVGN_MLP_ENC_EDGE, precision, plan.E, params[8:], xn, pos, plan.edge_s, plan.edge_r,
+                          _c(d_edge))
+        return (None, None, None, None, *gn, *ge)
+
+
+# ------------------------------------------------------------------ GnBlock
+class GnBlockFn(torch.autograd.Function):
+    """GnBlock.forward (EPD.py:177-195) = EdgeBlock (blocks.py:71-120) -> NodeBlock (blocks.py:13-63) -> residuals.
+
+    forward : agg = Adj x ; e' = MLP_e([agg[s]|agg[r]|e]) ; a1 = incidence-sum(e' halves) ; a2 = D^-1 Adj a1 ;
+              x' = MLP_n([a2|x]) ; returns (x + x', e + e')
+    backward: the transposes of the three reductions are the same CSR kernels; the MLPs recompute their hidden
+              activations from the saved block inputs (x, agg, a2, e)."""
+
+    @staticmethod
+    def forward(ctx, x, e, plan, precision, *params):
+        eb, nb = params[:8], params[8:]
+        x, e = _c(x), _c(e)
+        agg = adj_reduce(x, plan, 128)
+        e_new, e_out = mlp_forward(_lib.FVGN_MLP_EDGE, precision, plan.E, eb, agg, e, plan.edge_s, plan.edge_r,
+                                   want_out=True, want_res=True)
+        a1 = inc_reduce(e_new, plan, 64)
+        del e_new
+        a2 = adj_reduce(a1, plan, 64, _lib.FVGN_ADJ_DIV_DST_BY_DEG)
+        del a1
+        _, x_out = mlp_forward(_lib.FVGN_MLP_NODE, precision, plan.N, nb, a2, x, want_out=False, want_res=True)
+        ctx.plan, ctx.precision = plan, precision
+        ctx.save_for_backward(x, e, agg, a2, *params)
+        return x_out, e_out
+
+    @staticmethod
+    def backward(ctx, d_x_out, d_e_out):
+        x, e, agg, a2, *params = ctx.saved_tensors
+        plan, precision = ctx.plan, ctx.precision
+        eb, nb = params[:8], params[8:]
+        d_x_out = _c(d_x_out) if d_x_out is not None else torch.zeros_like(x)
+        d_e_out = _c(d_e_out) if d_e_out is not None else torch.zeros_like(e)
+        d_a2 = _empty((plan.N, 64), x)
+        d_x = _empty((plan.N, 128), x)
+        g_nb = mlp_backward(_lib.FVGN_MLP_NODE, precision, plan.N, nb, a2, x, None, None, d_x_out, None, d_a2, d_x)
+        d_a1 = adj_reduce(d_a2, plan, 64, _lib.FVGN_ADJ_DIV_SRC_BY_DEG)
+        del d_a2
+        d_sr = _empty((plan.E, 256), x)
+        d_e = _empty((plan.E, 128), x)
+        g_eb = mlp_backward(_lib.FVGN_MLP_EDGE, precision, plan.E, eb, agg, e, plan.edge_s, plan.edge_r, d_e_out, d_a1,
+                            d_sr, d_e)
+        d_agg = inc_reduce(d_sr, plan, 128)
+        del d_sr
+        adj_reduce(d_agg, plan, 128, _lib.FVGN_ADJ_ACCUMULATE, out=d_x)
+        return (d_x, d_e, None, None, *g_eb, *g_nb)
+
+
+class EdgeBlockFn(torch.autograd.Function):
+    """Stand-alone EdgeBlock.forward (blocks.py:71-120): e' = MLP_e([agg[s]|agg[r]|e]), no residual."""
+
+    @staticmethod
+    def forward(ctx, x, e, plan, precision, *params):
+        x, e = _c(x), _c(e)
+        agg = adj_reduce(x, plan, 128)
+        e_new, _ = mlp_forward(_lib.FVGN_MLP_EDGE, precision, plan.E, params, agg, e, plan.edge_s, plan.edge_r,
+                               flags=_lib.FVGN_MLP_NO_RESIDUAL)
+        ctx.plan, ctx.precision = plan, precision
+        ctx.save_for_backward(agg, e, *params)
+        return e_new
+
+    @staticmethod
+    def backward(ctx, d_e_new):
+        agg, e, *params = ctx.saved_tensors
+        plan, precision = ctx.plan, ctx.precision
+        d_sr = _empty((plan.E, 256), e)
+        d_e = _empty((plan.E, 128), e)
+        g = mlp_backward(_lib.FVGN_MLP_EDGE, precision, plan.E, params, agg, e, plan.edge_s, plan.edge_r, _c(d_e_new), None,
+                         d_sr, d_e, flags=_lib.FVGN_MLP_NO_RESIDUAL)
+        d_agg = inc_reduce(d_sr, plan, 128)
+        d_x = adj_reduce(d_agg, plan, 128)
+        return (d_x, d_e, None, None, *g)
+
+
+class NodeBlockFn(torch.autograd.Function):
+    """Stand-alone NodeBlock.forward (blocks.py:13-63): x' = MLP_n([a2|x]) from the edge latents, no residual."""
+
+    @staticmethod
+    def forward(ctx, x, e, plan, precision, *params):
+        x, e = _c(x), _c(e)
+        a1 = inc_reduce(e, plan, 64)
+        a2 = adj_reduce(a1, plan, 64, _lib.FVGN_ADJ_DIV_DST_BY_DEG)
+        x_new, _ = mlp_forward(_lib.FVGN_MLP_NODE, precision, plan.N, params, a2, x, flags=_lib.FVGN_MLP_NO_RESIDUAL)
+        ctx.plan, ctx.precision = plan, precision
+        ctx.save_for_backward(a2, x, *params)
+        return x_new
+
+    @staticmethod
+    def backward(ctx, d_x_new):
+        a2, x, *params = ctx.saved_tensors
+        plan, precision = ctx.plan, ctx.precision
+        d_a2 = _empty((plan.N, 64), x)
+        d_x = _empty((plan.N, 128), x)
+        g = mlp_backward(_lib.FVGN_MLP_NODE, precision, plan.N, params, a2, x, None, None, _c(d_x_new), None, d_a2, d_x,
+                         flags=_lib.FVGN_MLP_NO_RESIDUAL)
+        d_a1 = adj_reduce(d_a2, plan, 64, _lib.FVGN_ADJ_DIV_SRC_BY_DEG)
+        # transpose of the incidence sum: d_e[f] = [d_a1[s_f] | d_a1[r_f]]
+        d_e = torch.cat([d_a1[plan.edge_s.long()], d_a1[plan.edge_r.long()]], 1)
+        return (d_x, d_e, None, None, *g)
+
+
+# ------------------------------------------------------------------ Decoder + head
+class DecoderFn(torch.autograd.Function):
+    """Decoder.forward (EPD.py:215-219): Linear-GELU-Linear-GELU-Linear(128->3), no LayerNorm."""
+
+    @staticmethod
+    def forward(ctx, x, precision, *params):
+        x = _c(x)
+        out, _ = mlp_forward(_lib.FVGN_MLP_DEC, precision, x.shape[0], params, x)
+        ctx.precision = precision
+        ctx.save_for_backward(x, *params)
+        return out
+
+    @staticmethod
+    def backward(ctx, d_out):
+        x, *params = ctx.saved_tensors
+        d_x = _empty(tuple(x.shape), x)
+        g = mlp_backward(_lib.FVGN_MLP_DEC, ctx.precision, x.shape[0], params, x, None, None, None, _c(d_out), None, d_x)
+        return (d_x, None, *g)
+
+
+INTEGRATORS = {"explicit": 0, "implicit": 1, "imex": 2}
+
+
+class HeadFn(torch.autograd.Function):
+    """importer.py:187-201: uvp = 10 tanh(raw/10), Dirichlet BC, uv_hat; returns phi[N,7] = [uvp | uv_hat | uv_old]."""
+
+    @staticmethod
+    def forward(ctx, raw, uv_old, y, node_type, integrator):
+        raw = _c(raw)
+        n = raw.shape[0]
+        phi = _empty((n, 7), raw)
+        _lib.call("fvgn_head_forward", fptr(raw), fptr(uv_old), fptr(y), iptr(node_type), integrator, fptr(phi), n,
+                  _lib.stream_ptr(raw.device))
+        ctx.integrator = integrator
+        ctx.save_for_backward(raw, node_type)
+        return phi
+
+    @staticmethod
+    def backward(ctx, d_phi):
+        raw, node_type = ctx.saved_tensors
+        d_raw = torch.empty_like(raw)
+        _lib.call("fvgn_head_backward", fptr(raw), iptr(node_type), ctx.integrator, fptr(_c(d_phi)), fptr(d_raw),
+                  raw.shape[0], _lib.stream_ptr(raw.device))
+        return d_raw, None, None, None, None
+
+
+# ------------------------------------------------------------------ per-graph column sums
+def segment_colsum(x, width, ld, chunks, chunk_ptr, nchunks, nseg, center=None, power=1, col_offset=0):
+    """[nseg, width] = per-graph sums of (x[:, off:off+width] - center[seg])**power, deterministic two-level tree."""
+    part = _empty((max(nchunks, 1), width), x)
+    out = _empty((nseg, width), x)
+    st = _lib.stream_ptr(x.device)
+    _lib.call("fvgn_chunk_colsum", fptr(x) + 4 * col_offset, width, ld, fptr(center, True), 0 if center is None else center.shape[1], power,
+              iptr(chunks), nchunks, fptr(part), st)
+    _lib.call("fvgn_chunk_combine", fptr(part), width, iptr(chunk_ptr), nseg, fptr(out), st)
+    return out
+
+
+# ------------------------------------------------------------------ WLSQ
+class WlsqFn(torch.autograd.Function):
+    """node_based_WLSQ (FVgrad.py:235-367, precomputed-moments branch) -> [N, C, nq]."""
+
+    @staticmethod
+    def forward(ctx, phi, plan, nq):
+        phi = _c(phi)
+        nc = phi.shape[1]
+        q, qsum, qt = plan.wlsq_weights(nq)
+        grad = _empty((plan.N, nc, nq), phi)
+        _lib.call("fvgn_wlsq_forward", fptr(phi), nc, iptr(plan.w_ptr), iptr(plan.w_col), fptr(q), nq, fptr(grad), plan.N,
+                  _lib.stream_ptr(phi.device))
+        ctx.plan, ctx.nq, ctx.nc = plan, nq, nc
+        return grad
+
+    @staticmethod
+    def backward(ctx, g):
+        plan, nq, nc = ctx.plan, ctx.nq, ctx.nc
+        q, qsum, qt = plan.wlsq_weights(nq)
+        g = _c(g)
+        d_phi = _empty((plan.N, nc), g)
+        _lib.call("fvgn_wlsq_backward", fptr(g), nc, iptr(plan.w_tptr), iptr(plan.w_trow), fptr(qt), fptr(qsum), nq,
+                  fptr(d_phi), 0, plan.N, _lib.stream_ptr(g.device))
+        return d_phi, None, None
+
+
+# ------------------------------------------------------------------ fused FV loss
+def _fv_desc(plan, phi, grad, theta, dt):
+    d = _lib.FvDesc()
+    d.n_nodes, d.n_faces, d.n_cells, d.n_slots, d.n_graphs = plan.N, plan.E, plan.C, plan.K, plan.B
+    d.phi, d.grad = fptr(phi), fptr(grad)
+    d.pos, d.y, d.node_type = fptr(plan.pos), fptr(plan.y), iptr(plan.node_type)
+    d.edge_s, d.edge_r = iptr(plan.edge_s), iptr(plan.edge_r)
+    d.face_pos, d.face_area, d.face_type = fptr(plan.face_pos), fptr(plan.face_area), iptr(plan.face_type)
+    d.centroid, d.cells_area, d.batch_cell = fptr(plan.centroid), fptr(plan.cells_area), iptr(plan.batch_cell)
+    d.cell_ptr, d.slot_node, d.slot_face = iptr(plan.cell_ptr), iptr(plan.slot_node), iptr(plan.slot_face)
+    d.slot_unv, d.slot_cell = fptr(plan.slot_unv), iptr(plan.slot_cell)
+    d.face_slot_ptr, d.face_slot = iptr(plan.face_slot_ptr), iptr(plan.face_slot)
+    d.node_slot_ptr, d.node_slot = iptr(plan.node_slot_ptr), iptr(plan.node_slot)
+    d.inc_ptr, d.inc_code = iptr(plan.inc_ptr), iptr(plan.inc_code)
+    d.theta, d.dt = fptr(theta), fptr(dt)
+    return d
+
+
+class FVLossFn(torch.autograd.Function):
+    """Intergrator.forward (FVscheme.py:618-724) with conserved_form (:50-274): phi[N,7] -> losses[B,4]
+    = (continuity, momentum-x, momentum-y, pressure-outlet) + non-differentiable uvp_node[N,3], uvp_cell[C,3]."""
+
+    @staticmethod
+    def forward(ctx, phi, plan, theta, sigma, dt, out_scale, ncn_smooth):
+        phi = _c(phi)
+        st = _lib.stream_ptr(phi.device)
+        q, qsum, qt = plan.wlsq_weights(2)
+        grad = _empty((plan.N, 7, 2), phi)
+        _lib.call("fvgn_wlsq_forward", fptr(phi), 7, iptr(plan.w_ptr), iptr(plan.w_col), fptr(q), 2, fptr(grad), plan.N, st)
+        res = _empty((plan.C, 4), phi)
+        phic = _empty((plan.C, 5), phi)
+        theta, dt = _c(theta.float()), _c(dt.reshape(-1).float())
+        d = _fv_desc(plan, phi, grad, theta, dt)
+        d.res, d.phic = fptr(res), fptr(phic)
+        _lib.call("fvgn_fv_forward", ctypes.byref(d), st)
+        sq = segment_colsum(res, 3, 4, plan.cell_chunks, plan.cell_chunk_ptr, plan.n_cell_chunks, plan.B, power=2)
+        ps = segment_colsum(res, 1, 4, plan.cell_chunks, plan.cell_chunk_ptr, plan.n_cell_chunks, plan.B, power=1,
+                            col_offset=3)
+        S = torch.cat([sq, ps], 1)                                           # [B,4]
+        scale = torch.cat([theta[:, 1:2], sigma[:, 0:2].float(), torch.ones_like(theta[:, 0:1])], 1)
+        root = torch.sqrt(S)
+        losses = root * scale
+        uvp_node = _empty((plan.N, 3), phi)
+        uvp_cell = _empty((plan.C, 3), phi)
+        _lib.call("fvgn_fv_outputs", ctypes.byref(d), iptr(plan.batch_node), fptr(_c(out_scale.float())), int(ncn_smooth),
+                  fptr(uvp_node), fptr(uvp_cell), st)
+        ctx.plan = plan
+        ctx.save_for_backward(phi, grad, res, root, scale, theta, dt)
+        ctx.mark_non_differentiable(uvp_node, uvp_cell, grad)
+        return losses, uvp_node, uvp_cell, grad
+
+    @staticmethod
+    def backward(ctx, g_losses, _gn, _gc, _gg):
+        phi, grad, res, root, scale, theta, dt = ctx.saved_tensors
+        plan = ctx.plan
+        st = _lib.stream_ptr(phi.device)
+        safe = torch.where(root > 0, root, torch.ones_like(root))
+        coef = torch.where(root > 0, g_losses * scale / safe, torch.zeros_like(root))
+        coef = torch.cat([coef[:, 0:3], coef[:, 3:4] * 0.5], 1).contiguous()
+        d = _fv_desc(plan, phi, grad, theta, dt)
+        d_face = _empty((plan.E, 13), phi)
+        d_phi = _empty((plan.N, 7), phi)
+        d_grad = _empty((plan.N, 7, 2), phi)
+        d.res, d.coef = fptr(res), fptr(coef)
+        d.d_face, d.d_phi, d.d_grad = fptr(d_face), fptr(d_phi), fptr(d_grad)
+        _lib.call("fvgn_fv_backward", ctypes.byref(d), st)
+        q, qsum, qt = plan.wlsq_weights(2)
+        _lib.call("fvgn_wlsq_backward", fptr(d_grad), 7, iptr(plan.w_tptr), iptr(plan.w_trow), fptr(qt), fptr(qsum), 2,
+                  fptr(d_phi), 1, plan.N, st)
+        return d_phi, None, None, None, None, None, None

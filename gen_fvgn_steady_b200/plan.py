@@ -1,0 +1,158 @@
+"""GraphPlan: the int32 CSR structures built once per batch topology from the Load_mesh batch layout.
+
+Every list is the *stable* grouping of the reference's scatter entry order by destination, so the
+deterministic CSR reductions sum in exactly the order a sequential index_add_ would
+(oracle/fvgn_oracle.py: csr_stable / node_incidence_plan / wlsq_entry_plan are the bit-exact targets).
+
+Inputs are the five batched graphs of src/Load_mesh/Graph_loader.py:503-784:
+  graph_node  : x, edge_index[2,E], face=cells_node[K], pos, node_type, y, batch
+  graph_node_x: face_node_x[2,X], support_edge[2,2B], A_node_to_node, single_B_node_to_node, extra_B_node_to_node
+  graph_edge  : face_type, face_area, face=cells_face[K], pos (face centres), batch
+  graph_cell  : cells_face_unv[K,2], cells_area, pos (centroids), face=cells_index[K], batch
+"""
+import torch
+
+from . import _lib
+
+CHUNK_ROWS = 4096
+
+
+def _i32(t):
+    return t.to(torch.int32).contiguous()
+
+
+def csr_stable(dest, n):
+    """rowptr[n+1] (int32), perm (int64): entries grouped by destination row, original order kept inside a row."""
+    dest = dest.reshape(-1).to(torch.int64)
+    perm = torch.sort(dest, stable=True).indices
+    counts = torch.bincount(dest, minlength=n)
+    rowptr = torch.zeros(n + 1, dtype=torch.int64, device=dest.device)
+    torch.cumsum(counts, 0, out=rowptr[1:])
+    return rowptr.to(torch.int32), perm
+
+
+def _chunks(batch, nseg):
+    """Row chunks of <= CHUNK_ROWS rows that never straddle a graph: (chunks[nchunks,3], chunk_ptr[nseg+1])."""
+    counts = torch.bincount(batch.to(torch.int64), minlength=nseg).cpu().tolist()
+    rows, ptr, start = [], [0], 0
+    for seg, cnt in enumerate(counts):
+        r = start
+        while r < start + cnt:
+            e = min(r + CHUNK_ROWS, start + cnt)
+            rows.append((seg, r, e))
+            r = e
+        start += cnt
+        ptr.append(len(rows))
+    dev = batch.device
+    chunks = torch.tensor(rows if rows else [(0, 0, 0)], dtype=torch.int32, device=dev).reshape(-1, 3)
+    return chunks.contiguous(), torch.tensor(ptr, dtype=torch.int32, device=dev), len(rows)
+
+
+class GraphPlan:
+    """Device-resident topology plan of one batch.  Build with GraphPlan.build(...) or GraphPlan.of(...) (cached)."""
+
+    @staticmethod
+    def of(graph_node, graph_node_x=None, graph_edge=None, graph_cell=None, order="2nd"):
+        key = (graph_node.edge_index.data_ptr(), tuple(graph_node.edge_index.shape))
+        key_fv = None if graph_node_x is None else (graph_node_x.face_node_x.data_ptr(), graph_cell.face.data_ptr(), order)
+        plan = getattr(graph_node, "_fvgn_plan", None)
+        if plan is not None and plan.key == key and (key_fv is None or plan.key_fv == key_fv):
+            return plan
+        plan = GraphPlan.build(graph_node, graph_node_x, graph_edge, graph_cell, order)
+        plan.key, plan.key_fv = key, key_fv
+        graph_node._fvgn_plan = plan
+        return plan
+
+    @staticmethod
+    def build(graph_node, graph_node_x=None, graph_edge=None, graph_cell=None, order="2nd"):
+        p = GraphPlan()
+        ei = graph_node.edge_index
+        dev = ei.device
+        p.device = dev
+        N = int(graph_node.pos.shape[0]) if getattr(graph_node, "pos", None) is not None else int(graph_node.x.shape[0])
+        E = int(ei.shape[1])
+        p.N, p.E = N, E
+        s, r = ei[0].to(torch.int64), ei[1].to(torch.int64)
+        p.edge_s, p.edge_r = _i32(s), _i32(r)
+        # node incidence, entry order = cat(senders, receivers)  (blocks.py:24-42,84-99)
+        p.inc_ptr, perm = csr_stable(torch.cat([s, r]), N)
+        edge = perm % max(E, 1)
+        role = perm // max(E, 1)
+        p.inc_code = _i32(edge * 2 + role)
+        p.inc_nbr = _i32(torch.where(role == 0, r[edge], s[edge])) if E > 0 else _i32(edge)
+        batch = getattr(graph_node, "batch", None)
+        if batch is None:
+            batch = torch.zeros(N, dtype=torch.int64, device=dev)
+        p.batch_node = _i32(batch)
+        p.B = int(batch.max().item()) + 1 if N > 0 else 1
+        p.node_chunks, p.node_chunk_ptr, p.n_node_chunks = _chunks(batch, p.B)
+        p.has_fv = False
+        if graph_node_x is not None:
+            p._build_fv(graph_node, graph_node_x, graph_edge, graph_cell, order)
+        return p
+
+    # ------------------------------------------------------------------ finite-volume part
+    def _build_fv(self, graph_node, graph_node_x, graph_edge, graph_cell, order):
+        dev, N, E = self.device, self.N, self.E
+        f32 = torch.float32
+        cells_node = graph_node.face.reshape(-1).to(torch.int64)
+        cells_face = graph_edge.face.reshape(-1).to(torch.int64)
+        cells_index = graph_cell.face.reshape(-1).to(torch.int64)
+        C = int(graph_cell.pos.shape[0])
+        K = int(cells_index.shape[0])
+        self.C, self.K = C, K
+        # slots sorted by cell (stable); identity for the reference's layouts (cells_index non-decreasing)
+        self.cell_ptr, sperm = csr_stable(cells_index, C)
+        self.slot_cell = _i32(cells_index[sperm])
+        self.slot_node = _i32(cells_node[sperm])
+        self.slot_face = _i32(cells_face[sperm])
+        self.slot_unv = graph_cell.cells_face_unv.reshape(-1, 2)[sperm].to(f32).contiguous()
+        self.face_slot_ptr, fperm = csr_stable(cells_face[sperm], E)
+        self.face_slot = _i32(fperm)
+        self.node_slot_ptr, nperm = csr_stable(cells_node[sperm], N)
+        self.node_slot = _i32(nperm)
+        self.batch_cell = _i32(graph_cell.batch)
+        self.cell_chunks, self.cell_chunk_ptr, self.n_cell_chunks = _chunks(graph_cell.batch, self.B)
+        # geometry (fp32 copies in the layout the kernels read)
+        self.pos = graph_node.pos.to(f32).contiguous()
+        self.y = graph_node.y.to(f32).contiguous()
+        self.node_type = _i32(graph_node.node_type.reshape(-1))
+        self.face_pos = graph_edge.pos.to(f32).contiguous()
+        self.face_area = graph_edge.face_area.reshape(-1).to(f32).contiguous()
+        self.face_type = _i32(graph_edge.face_type.reshape(-1))
+        self.centroid = graph_cell.pos.to(f32).contiguous()
+        self.cells_area = graph_cell.cells_area.reshape(-1).to(f32).contiguous()
+        # WLSQ stencil: directed entries cat(fx, flip(fx), support_edge), (out -> in), grouped by 'in'  (FVgrad.py:264-273)
+        fx = graph_node_x.face_node_x.to(torch.int64)
+        se = graph_node_x.support_edge.to(torch.int64)
+        out_i = torch.cat([fx[0], fx[1], se[0]])
+        in_i = torch.cat([fx[1], fx[0], se[1]])
+        self.w_ptr, wperm = csr_stable(in_i, N)
+        self.w_col = _i32(out_i[wperm])
+        A = graph_node_x.A_node_to_node.to(f32).contiguous()
+        nm = int(A.shape[-1])
+        B1 = graph_node_x.single_B_node_to_node.reshape(-1, nm).to(f32)
+        Bx = graph_node_x.extra_B_node_to_node.reshape(-1, nm).to(f32)
+        flip = B1.clone()
+        flip[:, 0:2] *= -1  # FVgrad.py:301-306
+        moments = torch.cat([B1, flip, Bx], 0)[wperm].contiguous()
+        del flip
+        self.w_nm = nm
+        self.w_moments, self.w_A = moments, A
+        self.w_row = _i32(in_i[wperm])
+        self.w_tptr, self.w_tperm = csr_stable(self.w_col, N)
+        self.w_trow = _i32(self.w_row[self.w_tperm].to(torch.int64))
+        self._wq = {}
+        self.wlsq_weights(2)
+        self.has_fv = True
+
+    def wlsq_weights(self, nq):
+        """(q[nnz,nq], qsum[N,nq], qT[nnz,nq]) with the fp64 inverse moment matrix folded in (cached per nq)."""
+        if nq not in self._wq:
+            nnz = int(self.w_col.shape[0])
+            q = torch.empty((nnz, nq), dtype=torch.float32, device=self.device)
+            qsum = torch.empty((self.N, nq), dtype=torch.float32, device=self.device)
+            _lib.call("fvgn_wlsq_weights", _lib.fptr(self.w_A), self.w_nm, _lib.iptr(self.w_ptr), _lib.fptr(self.w_moments),
+                      nq, _lib.fptr(q), _lib.fptr(qsum), self.N, _lib.stream_ptr(self.device))
+            self._wq[nq] = (q, qsum, q[self.w_tperm].contiguous())
+        return self._wq[nq]

@@ -1,0 +1,166 @@
+/* fvgn_b200 -- C-ABI of the B200-native Gen-FVGN hot path (libfvgn_b200.so).
+ *
+ * The reference (Litianyu141/Gen-FVGN-steady) is pure Python and has no FFI seam; the seam is the
+ * Python module API of src/FVMmodel, which gen_fvgn_steady_b200/FVMmodel mirrors.  This header is
+ * the layer directly below that mirror: every entry point replaces the group of torch /
+ * torch_scatter / PyG calls cited beside it (paths relative to the reference repo root).
+ *
+ * Conventions
+ *   - plain pointers and sizes only; all pointers are DEVICE pointers; the caller (PyTorch) owns
+ *     every buffer including workspaces; functions enqueue on `stream` (a cudaStream_t passed as
+ *     void*) and never allocate, synchronise or touch global state.
+ *   - float tensors are fp32 row-major; index tensors are int32.
+ *   - return value: FVGN_OK or a negative FVGN_ERR_* code (the Python wrapper raises RuntimeError).
+ */
+#ifndef FVGN_B200_H
+#define FVGN_B200_H
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define FVGN_OK 0
+#define FVGN_ERR_SHAPE (-1)
+#define FVGN_ERR_ALIGN (-2)
+#define FVGN_ERR_UNSUPPORTED (-3)
+#define FVGN_ERR_LAUNCH (-4)
+#define FVGN_ERR_NULL (-5)
+
+/* library / build identification; bit0 of the return = built for sm_100a, bit1 = tcgen05 kernels present */
+int fvgn_version(void);
+
+/* ------------------------------------------------------------------ CSR segmented reductions */
+#define FVGN_ADJ_ACCUMULATE 1      /* dst += result                               */
+#define FVGN_ADJ_DIV_DST_BY_DEG 2  /* result /= max(deg(row),1)   (scatter_mean)   */
+#define FVGN_ADJ_DIV_SRC_BY_DEG 4  /* each term /= max(deg(src),1) (its transpose) */
+/* dst[i,:] = sum_{t in [ptr[i],ptr[i+1])} src[nbr[t],:], width in {64,128}.
+ * Replaces src/FVMmodel/Models/FVGN/blocks.py:92-99 (x[senders/receivers] + scatter_add) and
+ * blocks.py:44-51 (scatter_mean); backward of both is the same call (Adj symmetric). */
+int fvgn_adj_reduce(const float* src, const int32_t* ptr, const int32_t* nbr, float* dst, int64_t n_rows,
+                    int32_t width, int32_t flags, void* stream);
+/* dst[i,0:W] = sum over incidence entries code=(edge*2+role) of src[edge, role*W:(role+1)*W], src is [E,2W].
+ * Replaces blocks.py:24-42 (chunk + cat + scatter_add); also the deterministic transpose of the
+ * agg[senders]/agg[receivers] gathers of blocks.py:101-107 in backward. */
+int fvgn_inc_reduce(const float* src, const int32_t* ptr, const int32_t* code, float* dst, int64_t n_rows,
+                    int32_t width, void* stream);
+
+/* ------------------------------------------------------------------ fused MLP blocks */
+#define FVGN_MLP_EDGE 0     /* EdgeBlock  blocks.py:101-111 + EPD.py:170-175,186 : in=[agg[s]|agg[r]|e], K1=384, LN, +e   */
+#define FVGN_MLP_NODE 1     /* NodeBlock  blocks.py:54 + EPD.py:163-168,185      : in=[a2|x],           K1=192, LN, +x   */
+#define FVGN_MLP_ENC_NODE 2 /* Encoder.nb_encoder EPD.py:118                      : in=x[N,12],          K1=12,  LN       */
+#define FVGN_MLP_ENC_EDGE 3 /* importer.py:54-78 + Encoder.eb_encoder EPD.py:119  : in=[xn[s]-xn[r]|dpos|norm], K1=15, LN */
+#define FVGN_MLP_DEC 4      /* Decoder EPD.py:215-219                             : in=x[N,128], K1=128, out=3, no LN    */
+#define FVGN_PREC_FP32 0    /* SIMT fp32 FMA (parity mode, rel 1e-5 vs the reference's CPU fp32)   */
+#define FVGN_MLP_NO_RESIDUAL 1
+#define FVGN_PREC_BF16 1    /* tcgen05.mma kind::f16 bf16 operands, fp32 accumulate in TMEM (throughput mode) */
+
+typedef struct fvgn_mlp_desc {
+  int32_t mode;      /* FVGN_MLP_*  */
+  int32_t precision; /* FVGN_PREC_* */
+  int64_t rows;      /* edges (EDGE, ENC_EDGE) or nodes */
+  const float* in0;  /* EDGE: agg[N,128]  NODE: a2[N,64]  ENC_NODE: xn[N,12]  ENC_EDGE: xn[N,12]  DEC: x[N,128] */
+  const float* in1;  /* EDGE: e[E,128]    NODE: x[N,128]  ENC_EDGE: pos[N,2]  else NULL */
+  const int32_t* idx_s; /* EDGE / ENC_EDGE: senders   [rows] */
+  const int32_t* idx_r; /* EDGE / ENC_EDGE: receivers [rows] */
+  /* parameters, reference state_dict layout: net.0.{0,2,4}.{weight,bias}, net.1.{weight,bias} */
+  const float* w1; const float* b1; const float* w2; const float* b2; const float* w3; const float* b3;
+  const float* ln_g; const float* ln_b; /* NULL for DEC */
+  const void* w_bf16; /* FVGN_PREC_BF16 only: packed bf16 operand image made by fvgn_mlp_pack_weights */
+  int32_t flags;      /* FVGN_MLP_NO_RESIDUAL: stand-alone EdgeBlock/NodeBlock (no "+ e" / "+ x" in fwd and bwd) */
+  int32_t reserved0;
+  /* forward outputs */
+  float* out;     /* y = MLP(in)  [rows,128] ([rows,3] for DEC); may be NULL for EDGE/NODE if only out_res is wanted */
+  float* out_res; /* EDGE: e + y, NODE: x + y; NULL otherwise */
+  /* backward inputs */
+  const float* d_out;    /* grad wrt out_res (EDGE/NODE) or out (ENC_*, DEC) */
+  const float* d_gather; /* EDGE: d_a1[N,64]; [d_a1[s]|d_a1[r]] is added to d_out (transpose of blocks.py:24-42) */
+  /* backward outputs */
+  float* d_in0; /* EDGE: [E,256] = d(agg[s]) | d(agg[r]);  NODE: d_a2[N,64];  DEC: d_x[N,128];  ENC_*: NULL */
+  float* d_in1; /* EDGE: d_e[E,128] = d_out + dX[:,256:384];  NODE: d_x[N,128] = d_out + dX[:,64:192] */
+  float* partials;     /* [n_partials, fvgn_mlp_param_count(mode)] per-CTA weight-gradient partial sums */
+  int32_t n_partials;  /* = grid size of the backward kernel, from fvgn_mlp_bwd_partials() */
+  float* d_params;     /* [param_count] flat: w1,b1,w2,b2,w3,b3,ln_g,ln_b (deterministic reduction of partials) */
+} fvgn_mlp_desc;
+
+int64_t fvgn_mlp_param_count(int32_t mode);
+int32_t fvgn_mlp_bwd_partials(int32_t mode, int32_t precision, int64_t rows); /* number of per-CTA partial buffers to allocate */
+int64_t fvgn_mlp_packed_bytes(int32_t mode);
+/* fp32 parameters -> bf16 UMMA operand image (weights change every optimiser step; call once per step) */
+int fvgn_mlp_pack_weights(int32_t mode, const float* w1, const float* w2, const float* w3, void* packed, void* stream);
+int fvgn_mlp_forward(const fvgn_mlp_desc* d, void* stream);
+int fvgn_mlp_backward(const fvgn_mlp_desc* d, void* stream);
+
+/* ------------------------------------------------------------------ importer prologue / head */
+/* Column sums of (x - center[seg])^p over row chunks: chunks[nchunks,3] = (segment, row_begin, row_end);
+ * out_partial[nchunks, width].  center may be NULL.  p in {1,2}.  Deterministic replacement of the
+ * scatter_mean of importer.py:86-90, Normalizer sums (utils/normalization.py:55-66) and
+ * global_add_pool (FVscheme.py:184-188,243-247). */
+int fvgn_chunk_colsum(const float* x, int32_t width, int32_t ld, const float* center, int32_t center_ld, int32_t power,
+                      const int32_t* chunks, int32_t nchunks, float* out_partial, void* stream);
+/* out[seg, :] = sum of out_partial over the chunks of seg (chunk_ptr[nseg+1]) */
+int fvgn_chunk_combine(const float* partial, int32_t width, const int32_t* chunk_ptr, int32_t nseg, float* out,
+                       void* stream);
+/* importer.py:168-176 : uv_old = x[:,0:2]/uvp_dim[batch]; xn[:,0:3]=(x-mean_g)/(std_g+1e-8); xn[:,3:12]=(x-mean)/std */
+int fvgn_prologue(const float* x, const int32_t* batch, const float* uvp_dim, const float* gmean, const float* gstd,
+                  const float* nmean, const float* nstd, int32_t norm_uvp, float* xn, float* uv_old, int64_t n,
+                  void* stream);
+/* importer.py:187-201 : uvp = 10 tanh(raw/10); Dirichlet rows <- y, p=0 at PRESS_POINT; uv_hat by integrator
+ * (0 explicit, 1 implicit, 2 imex); phi[N,7] = [uvp | uv_hat | uv_old]  (FVscheme.py:643-646) */
+int fvgn_head_forward(const float* raw, const float* uv_old, const float* y, const int32_t* node_type, int32_t integrator,
+                      float* phi, int64_t n, void* stream);
+int fvgn_head_backward(const float* raw, const int32_t* node_type, int32_t integrator, const float* d_phi, float* d_raw,
+                       int64_t n, void* stream);
+
+/* ------------------------------------------------------------------ finite-volume loss */
+/* Plan-time: fold the fp64 inverse of the per-node 5x5 (2x2 for order 1) moment matrix into per-entry
+ * weights q(e) = (A_i^-1 w m(e))[0:nq]; entries are CSR-ordered (row = 'in' node).  moments[nnz,nm].
+ * Replaces the run-time row-normalise + torch.linalg.solve of FVgrad.py:335-359. */
+int fvgn_wlsq_weights(const float* A, int32_t nm, const int32_t* ptr, const float* moments, int32_t nq, float* q,
+                      float* qsum, int64_t n, void* stream);
+/* grad[i,c,d] = sum_e q[e,d] (phi[col[e],c] - phi[i,c])   (FVgrad.py:295-325 + :335-359), nc channels, nq in {2,5} */
+int fvgn_wlsq_forward(const float* phi, int32_t nc, const int32_t* ptr, const int32_t* col, const float* q, int32_t nq,
+                      float* grad, int64_t n, void* stream);
+/* d_phi[j,c] (+)= sum_{e in T(j)} sum_d qT[e,d] g[rowT[e],c,d] - sum_d qsum[j,d] g[j,c,d] */
+int fvgn_wlsq_backward(const float* g, int32_t nc, const int32_t* tptr, const int32_t* trow, const float* tq,
+                       const float* qsum, int32_t nq, float* d_phi, int32_t accumulate, int64_t n, void* stream);
+
+typedef struct fvgn_fv_desc {
+  int64_t n_nodes, n_faces, n_cells, n_slots;
+  int32_t n_graphs;
+  /* fields */
+  const float* phi;   /* [N,7]  u,v,p,u_hat,v_hat,u_old,v_old */
+  const float* grad;  /* [N,7,2] WLSQ gradient */
+  /* geometry / topology (Load_mesh batch layout, int32, slots sorted by cell) */
+  const float* pos; const float* y; const int32_t* node_type;
+  const int32_t* edge_s; const int32_t* edge_r;
+  const float* face_pos; const float* face_area; const int32_t* face_type;
+  const float* centroid; const float* cells_area; const int32_t* batch_cell;
+  const int32_t* cell_ptr; const int32_t* slot_node; const int32_t* slot_face; const float* slot_unv;
+  const int32_t* slot_cell;
+  const int32_t* face_slot_ptr; const int32_t* face_slot;   /* face -> slots */
+  const int32_t* node_slot_ptr; const int32_t* node_slot;   /* node -> slots */
+  const int32_t* inc_ptr; const int32_t* inc_code;          /* node -> (face*2+role) */
+  const float* theta; /* [B,9] */ const float* dt; /* [B] */
+  /* forward outputs */
+  float* res;   /* [C,4] continuity, mom_x, mom_y, sum of squared outlet residuals */
+  float* phic;  /* [C,5] cell values of u,v,p,u_old,v_old */
+  /* backward */
+  const float* coef;  /* [B,4] dL/dres scale: dL/dres[c,k] = coef[b,k]*res[c,k] (k<3), dL/dres[c,3] = coef[b,3] */
+  float* d_face;      /* [E,13] scratch: d phi_f[5], d gradphi_f[(0,1,3,4),2] */
+  float* d_phi;       /* [N,7]  */
+  float* d_grad;      /* [N,7,2] */
+} fvgn_fv_desc;
+/* Intergrator.conserved_form FVscheme.py:50-250 with node_to_cell/node_to_face (FVInterpolation.py:36-185) and
+ * _fix_face_flux_BC (FVscheme.py:32-48) fused: one pass over cells. */
+int fvgn_fv_forward(const fvgn_fv_desc* d, void* stream);
+int fvgn_fv_backward(const fvgn_fv_desc* d, void* stream);
+/* cell_to_node_2nd_order (FVInterpolation.py:218-265) + BC re-enforcement and re-dimensionalisation
+ * (importer.py:223-231): uvp_node[N,3], uvp_cell[C,3] */
+int fvgn_fv_outputs(const fvgn_fv_desc* d, const int32_t* batch_node, const float* scale /*[B,3] uvp_dim*sigma*/,
+                    int32_t ncn_smooth, float* uvp_node, float* uvp_cell, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* FVGN_B200_H */
