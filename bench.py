@@ -1,0 +1,311 @@
+#!/usr/bin/env python
+"""bench.py -- cells*steps/sec of one Gen-FVGN training step (NNmodel.forward + loss.backward + Adam) on B200.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--cells C] [--net EPD|TransFVGN_v1|TransFVGN_v2]
+                    [--mp G] [--precision fp32|bf16]
+
+Workload (BASELINE.json config 5): one synthetic jittered quad mesh of `--cells` cells (default 4M) per GPU, cavity BCs,
+Navier-Stokes theta, net = Encoder -> GnBlock x G -> Decoder + finite-volume PDE loss, resident batch
+(the solve_with_grad_GPU.py regime).  N > 1: data parallel, one mesh per rank (weak scaling), one NCCL all-reduce of the
+flat gradient per step.  Prints ONE JSON line (rank 0).
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+import torch  # noqa: E402
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--cells", type=int, default=int(os.environ.get("FVGN_BENCH_CELLS", 4_000_000)))
+    ap.add_argument("--net", default=os.environ.get("FVGN_BENCH_NET", "EPD"))
+    ap.add_argument("--mp", type=int, default=int(os.environ.get("FVGN_BENCH_MP", 6)))
+    ap.add_argument("--precision", default=os.environ.get("FVGN_PRECISION", "fp32"))
+    ap.add_argument("--cpu-cells", type=int, default=40_000, help="cell count of the bounded CPU-baseline sample")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    return ap.parse_args()
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return float(d["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def alg_bytes_step(N, E, C, K, X, G):
+    """ALG_BYTES(step)."""
+    return G * (16.5 * N + 9 * E) * 512 + (5 * N + 2 * E) * 512 + 2.5 * (28 * X + 250 * N + 24 * K + 40 * E + 50 * C)
+
+
+def make_mesh(cells, seed, device):
+    """One synthetic quad mesh with ~cells cells -> the converter/loader dict (numpy) + initial field."""
+    from gen_fvgn_steady_b200.mesh import synthetic as S
+    n = max(int(round(cells ** 0.5)), 4)
+    if device is not None and n * n > 300_000:
+        from gen_fvgn_steady_b200.mesh import synthetic_torch as ST
+        return ST.make_case(n, kind="quad", bc="cavity", seed=seed, device=device)
+    return S.make_case(n, kind="quad", bc="cavity", seed=seed)
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled during the timed region (B200_PROFILING.md recipe)."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "100"], stdout=subprocess.PIPE, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        sm = [float(r[0]) for r in self.rows if r and r[0].replace(".", "").isdigit()]
+        mx = [float(r[1]) for r in self.rows if len(r) > 1 and r[1].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [n for i, n in enumerate(names) if any(len(r) > 3 + i and r[3 + i].lower().startswith("active") for r in self.rows)]
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": reasons,
+                "samples": len(sm)}
+
+
+# ----------------------------------------------------------------------------------------------- CPU reference arm
+def cpu_reference_step_time(cells, net, mp, steps, warmup, threads):
+    """The reference's algorithm on the host cores: oracle/fvgn_oracle.py (a CPU restatement pinned to the unmodified
+    reference's golden vectors; the reference itself needs torch_scatter/PyG and /root/reference, neither exists on the
+    GPU box).  fwd + backward + Adam on one synthetic quad mesh of `cells` cells.  Returns (sec/step, cells, N, E)."""
+    from oracle import fvgn_oracle as O
+    from gen_fvgn_steady_b200.FVMmodel.importer import NNmodel
+    from gen_fvgn_steady_b200.utils.get_param import params as default_params
+    torch.set_num_threads(threads)
+    mesh, uvp = make_mesh(cells, 0, None)
+    g = O.graphs_from_meshes([mesh], [uvp], torch.float32)
+    torch.manual_seed(0)
+    model = NNmodel(default_params(net=net, message_passing_num=mp))
+    sd = {k: v.detach().clone() for k, v in model.state_dict().items()}
+    leaves = {k: v.requires_grad_(True) for k, v in sd.items() if not k.startswith("node_norm.")}
+    opt = torch.optim.Adam(list(leaves.values()), lr=5e-5)
+    times = []
+    for it in range(warmup + steps):
+        t0 = time.perf_counter()
+        opt.zero_grad(set_to_none=True)
+        res = O.nnmodel_forward(sd, g, net=net, mp_num=mp)
+        loss = O.script_loss(res)
+        loss.backward()
+        opt.step()
+        if it >= warmup:
+            times.append(time.perf_counter() - t0)
+    C = int(g["centroid"].shape[0])
+    return float(np.mean(times)), C
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    threads = os.cpu_count() or 1
+    sec, C = cpu_reference_step_time(args.cpu_cells, args.net, args.mp, max(args.steps, 1), max(min(args.warmup, 1), 0), threads)
+    val = C / sec
+    sample = f"{C}-cell synthetic quad mesh (same generator, net, G, loss as the GPU arm), fwd+bwd+Adam, fp32, {threads} threads"
+    line = {"impl": "reference", "metric": "cells*steps/sec (fwd+bwd train step)", "value": val, "unit": "cells*steps/s",
+            "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": sec * 1e3,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": workload_config(args, C_bench=C),
+            "cpu_baseline": {"value": val, "unit": "cells*steps/s", "cores": threads, "kind": "port", "sample": sample},
+            "e2e": {"value": val, "unit": "cells*steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line))
+
+
+def workload_config(args, C_bench=None):
+    return {"workload": f"synthetic jittered quad mesh, {args.cells} cells/GPU, cavity BC, NS theta; "
+                        f"{args.net} G={args.mp} + FV PDE loss; resident batch (solve_with_grad regime)",
+            "net": args.net, "gn_blocks": args.mp, "cells_per_gpu": args.cells if C_bench is None else C_bench,
+            "precision": args.precision, "l2": "inputs/activations (GBs) far exceed the 126 MB L2; no explicit flush"}
+
+
+# ----------------------------------------------------------------------------------------------- our arm
+def run_ours(args):
+    import torch.distributed as dist
+    from gen_fvgn_steady_b200 import _lib, ops
+    from gen_fvgn_steady_b200.FVMmodel.importer import NNmodel
+    from gen_fvgn_steady_b200.mesh.batching import graphs_from_meshes
+    from gen_fvgn_steady_b200.plan import GraphPlan
+    from gen_fvgn_steady_b200.utils.get_param import params as default_params
+    from gen_fvgn_steady_b200 import parallel
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise RuntimeError("bench.py --impl ours needs a CUDA device: this package has no CPU path")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    mesh, uvp = make_mesh(args.cells, rank, dev)
+    graphs = graphs_from_meshes([mesh], [uvp], dev)
+    del mesh
+    gn, gx, ge, gc, gi = graphs
+    p = default_params(net=args.net, message_passing_num=args.mp, precision=args.precision)
+    torch.manual_seed(0)
+    model = NNmodel(p).to(dev)
+    flat_grad = parallel.flatten_gradients(model)
+    opt = torch.optim.Adam(model.parameters(), lr=p.lr, fused=True)
+    plan = GraphPlan.of(gn, gx, ge, gc, p.order)
+    N, E, C, K, X = plan.N, plan.E, plan.C, plan.K, int(gx.face_node_x.shape[1])
+    x_host = gn.x.detach().cpu().pin_memory()
+    x_dev0 = gn.x.clone()
+    uvp_host = torch.empty((N, 3), dtype=torch.float32).pin_memory()
+    loss_host = torch.empty((), dtype=torch.float32).pin_memory()
+
+    def step(e2e):
+        if e2e:
+            gn.x = x_host.to(dev, non_blocking=True)
+        else:
+            gn.x = x_dev0
+        gn.norm_uvp, gn.norm_global = True, True
+        flat_grad.zero_()
+        out = model(gn, gx, ge, gc, gi, is_training=True)
+        lb = p.loss_press * out[3] + p.loss_cont * out[0] + p.loss_mom * out[1] + p.loss_mom * out[2]
+        loss = torch.mean(torch.log(lb))
+        loss.backward()
+        if world > 1:
+            parallel.allreduce_gradients(flat_grad, world)
+        opt.step()
+        if e2e:
+            uvp_host.copy_(out[4], non_blocking=True)
+            loss_host.copy_(loss.detach(), non_blocking=True)
+        return loss
+
+    def timed(nsteps, e2e):
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        ev0.record()
+        for _ in range(nsteps):
+            step(e2e)
+        ev1.record()
+        torch.cuda.synchronize()
+        ms = torch.tensor([ev0.elapsed_time(ev1)], device=dev)
+        if world > 1:
+            dist.barrier()
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return float(ms.item())
+
+    for _ in range(max(args.warmup, 3)):
+        step(False)
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    l0 = _lib.launch_count
+    ms = timed(args.steps, False)
+    launches = _lib.launch_count - l0
+    step(True)
+    ms_e2e = timed(args.steps, True)
+    clocks = sampler.stop() if rank == 0 else None
+    last_loss = float(loss_host)
+
+    # dominant kernel: timed alone with CUDA events on the launching stream
+    roof = dominant_kernel_roofline(model, plan, dev, args, p)
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+    hbm, how = peaks()
+    sec = ms / 1e3 / args.steps
+    value = world * C / sec
+    ab = alg_bytes_step(N, E, C, K, X, args.mp)
+    line = {"metric": "cells*steps/sec (fwd+bwd train step)", "value": value, "unit": "cells*steps/s", "n_gpus": world,
+            "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f32" if args.precision == "fp32" else "bf16 (fp32 accumulate/storage)",
+            "data": "synthetic", "config": dict(workload_config(args, C_bench=C), N=N, E=E, C=C, K=K, X=X,
+                                                parallelism=f"dp{world}", loss=last_loss),
+            "clocks": clocks, "gpu_launches": launches,
+            "e2e": {"value": world * C / (ms_e2e / 1e3 / args.steps), "unit": "cells*steps/s", "h2d_bytes_per_step": N * 12 * 4,
+                    "d2h_bytes_per_step": N * 3 * 4 + 4, "ms_per_step": ms_e2e / args.steps},
+            "roofline": dict(roof, peak=hbm, frac=roof["achieved"] / hbm, peak_source=how),
+            "step_roofline": {"alg_bytes_per_step": ab, "achieved_gbs": ab / sec / 1e9, "frac": ab / sec / 1e9 / hbm,
+                              "alg_kb_per_cell": ab / C / 1e3}}
+    if not args.no_cpu_baseline:
+        threads = os.cpu_count() or 1
+        sec_cpu, C_cpu = cpu_reference_step_time(args.cpu_cells, args.net, args.mp, 2, 1, threads)
+        line["cpu_baseline"] = {"value": C_cpu / sec_cpu, "unit": "cells*steps/s", "cores": threads, "kind": "port",
+                                "sample": f"{C_cpu}-cell synthetic quad mesh, same net/loss, fwd+bwd+Adam fp32, 2 steps after 1 warm-up "
+                                          f"(oracle/fvgn_oracle.py on the host cores)"}
+    print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def dominant_kernel_roofline(model, plan, dev, args, p):
+    """Times the dominant kernel of the step (fused edge-MLP backward of one GnBlock) alone, CUDA events on its stream.
+    Algorithmic bytes per edge: e, d_e_out read, d_e written (3 x 512 B), d(agg[s])|d(agg[r]) written
+    (1024 B), agg / d_a1 gathers at unique-row volume ((512 + 256) * N/E B)."""
+    from gen_fvgn_steady_b200 import _lib, ops
+    from gen_fvgn_steady_b200.FVMmodel.Models.FVGN.blocks import mlp_params
+    blk = None
+    for m in model.modules():
+        if m.__class__.__name__ == "GnBlock":
+            blk = m
+            break
+    N, E = plan.N, plan.E
+    gen = torch.Generator(device=dev).manual_seed(1)
+    agg = torch.randn((N, 128), device=dev, generator=gen)
+    e = torch.randn((E, 128), device=dev, generator=gen)
+    d_out = torch.randn((E, 128), device=dev, generator=gen)
+    d_a1 = torch.randn((N, 64), device=dev, generator=gen)
+    d_sr = torch.empty((E, 256), device=dev)
+    d_e = torch.empty((E, 128), device=dev)
+    params = [q.detach() for q in mlp_params(blk.eb_module.net)]
+    reps = 3
+    times = []
+    for i in range(reps + 1):
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        ev0.record()
+        ops.mlp_backward(_lib.FVGN_MLP_EDGE, args.precision, E, params, agg, e, plan.edge_s, plan.edge_r, d_out, d_a1, d_sr, d_e)
+        ev1.record()
+        torch.cuda.synchronize()
+        if i > 0:
+            times.append(ev0.elapsed_time(ev1))
+    ms = float(np.mean(times))
+    alg = E * (3 * 512 + 1024) + N * (512 + 256)
+    return {"kernel": "mlp_bwd_kernel<EDGE> (fused edge-MLP backward: recompute + dgrad + wgrad)" if args.precision == "fp32"
+            else "mlp_tc_bwd<EDGE>", "bound": "hbm", "achieved": alg / (ms / 1e3) / 1e9, "unit": "GB/s", "ms_per_launch": ms,
+            "alg_bytes_per_launch": alg, "traffic": None}
+
+
+if __name__ == "__main__":
+    a = parse_args()
+    if a.impl == "reference":
+        run_reference(a)
+    else:
+        run_ours(a)

@@ -143,6 +143,13 @@ def check(rc, what):
         raise RuntimeError(f"fvgn_b200: {what} failed with {_ERRORS.get(rc, rc)}")
 
 
+# kernels launched per C-ABI call (for bench.py's gpu_launches claim)
+LAUNCHES_PER_CALL = {"fvgn_mlp_backward": 2, "fvgn_fv_backward": 2, "fvgn_fv_outputs": 2}
+launch_count = 0
+
+
 def call(name, *args):
+    global launch_count
     rc = getattr(load(), name)(*args)
     check(rc, name)
+    launch_count += LAUNCHES_PER_CALL.get(name, 1)
