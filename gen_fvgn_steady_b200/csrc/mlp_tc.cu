@@ -1,7 +1,564 @@
-// placeholder until the tcgen05 kernels land
+// Fused 3-layer MLP blocks on 5th-gen tensor cores (FVGN_PREC_BF16): tcgen05.mma kind::f16, bf16 operands,
+// fp32 accumulators in TMEM, fp32 bias / GELU / LayerNorm / residual, fp32 activations in HBM.
+//
+// Persistent kernel, one CTA per SM, tile = 128 rows (UMMA M=128, N=128, K=16):
+//   warps 4-7  producers : gather the input rows (edge endpoints / concatenations / relative edge features),
+//                          convert to bf16 and write 64-wide K chunks into a shared-memory ring in the canonical
+//                          K-major SWIZZLE_128B UMMA layout
+//   warp  8    MMA issuer: one elected thread issues tcgen05.mma; layer 1 reads A from the ring (SS), layers 2/3
+//                          read A straight from TMEM (TS) where the epilogue left the GELU output as bf16
+//   warps 0-3  epilogue  : tcgen05.ld accumulator -> +bias -> GELU -> bf16 -> tcgen05.st (next layer's A operand);
+//                          last layer: LayerNorm (one thread owns one row: no cross-lane reduction) + residual,
+//                          transposed through a small smem stage for coalesced stores
+// All three weight matrices stay resident in shared memory as a pre-swizzled bf16 image (<= 160 KB), loaded once
+// per CTA with cp.async.bulk; HBM traffic is the activation rows only.
 #include "common.cuh"
-int fvgn_mlp_forward_tc(const fvgn_mlp_desc*, void*) { return FVGN_ERR_UNSUPPORTED; }
-int fvgn_mlp_backward_tc(const fvgn_mlp_desc*, void*) { return FVGN_ERR_UNSUPPORTED; }
-int fvgn_mlp_tc_partials(int32_t, int64_t) { return 1; }
-int64_t fvgn_mlp_tc_packed_bytes(int32_t) { return 0; }
-int fvgn_mlp_tc_pack(int32_t, const float*, const float*, const float*, void*, void*) { return FVGN_ERR_UNSUPPORTED; }
+#include <cuda_bf16.h>
+
+namespace {
+
+constexpr int TILE_M = 128;
+constexpr int KB_BYTES = 128 * 128;  // one K-block: 128 rows x 64 bf16 (128 B per row), SWIZZLE_128B
+constexpr int NTHREADS = 288;
+
+template <int MODE> struct TCfg;
+template <> struct TCfg<FVGN_MLP_EDGE> { static constexpr int K1 = 384, K1P = 384, NOUT = 128, NSTAGE = 3; static constexpr bool LN = true; };
+template <> struct TCfg<FVGN_MLP_NODE> { static constexpr int K1 = 192, K1P = 192, NOUT = 128, NSTAGE = 6; static constexpr bool LN = true; };
+template <> struct TCfg<FVGN_MLP_ENC_NODE> { static constexpr int K1 = 12, K1P = 16, NOUT = 128, NSTAGE = 4; static constexpr bool LN = true; };
+template <> struct TCfg<FVGN_MLP_ENC_EDGE> { static constexpr int K1 = 15, K1P = 16, NOUT = 128, NSTAGE = 4; static constexpr bool LN = true; };
+template <> struct TCfg<FVGN_MLP_DEC> { static constexpr int K1 = 128, K1P = 128, NOUT = 3, NSTAGE = 4; static constexpr bool LN = false; };
+
+__host__ __device__ constexpr int nkb1(int k1p) { return (k1p + 63) / 64; }
+__host__ __device__ constexpr int image_bytes(int k1p) { return (nkb1(k1p) + 4) * KB_BYTES; }
+
+constexpr int STG_COLS = 16;                       // columns per staged store pass
+constexpr int STG_LD = STG_COLS + 4;               // padded row (floats)
+constexpr int STG_BYTES = 4 * 32 * STG_LD * 4;     // 4 epilogue warps x 32 rows
+
+template <int MODE> constexpr int smem_bytes() {
+  return image_bytes(TCfg<MODE>::K1P) + TCfg<MODE>::NSTAGE * KB_BYTES + STG_BYTES + 5 * 512 + 256;
+}
+
+// ------------------------------------------------------------------------------------------ PTX helpers
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  uint32_t done = 0;
+  for (uint32_t spin = 0; !done; ++spin) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(done)
+        : "r"(bar), "r"(parity)
+        : "memory");
+    if (spin > (1u << 24)) __trap();  // watchdog: a protocol bug must not hang the GPU
+  }
+}
+__device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
+               "l"(src), "r"(bytes), "r"(bar)
+               : "memory");
+}
+
+__device__ __forceinline__ void tmem_alloc(uint32_t slot_smem, uint32_t ncols) {
+  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(slot_smem), "r"(ncols) : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
+  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+// D[tmem] (+)= A[smem] * B[smem]^T
+__device__ __forceinline__ void umma_ss(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t acc) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(d_tmem),
+      "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(acc)
+      : "memory");
+}
+// D[tmem] (+)= A[tmem] * B[smem]^T
+__device__ __forceinline__ void umma_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc, uint32_t idesc, uint32_t acc) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}" ::"r"(d_tmem),
+      "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(acc)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_st8(uint32_t taddr, const uint32_t (&r)[8]) {
+  asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"r"(taddr), "r"(r[0]), "r"(r[1]),
+               "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7])
+               : "memory");
+}
+__device__ __forceinline__ void tmem_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ void tmem_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+
+// K-major SWIZZLE_128B shared-memory matrix descriptor (cute::UMMA::SmemDescriptor): 8-row groups 1024 B apart
+__device__ __forceinline__ uint64_t make_desc_k128(uint32_t saddr) {
+  return (uint64_t)((saddr >> 4) & 0x3FFF) | (1ull << 16) | (64ull << 32) | (1ull << 46) | (2ull << 61);
+}
+// instruction descriptor: D=f32, A=B=bf16, both K-major, M=128, N=128 (cute::UMMA::InstrDescriptor)
+constexpr uint32_t IDESC = (1u << 4) | (1u << 7) | (1u << 10) | ((128u >> 3) << 17) | ((128u >> 4) << 24);
+
+// erf via Abramowitz-Stegun 7.1.26 (|err| < 1.5e-7): MUFU ex2 + rcp, ~14 instructions
+__device__ __forceinline__ float gelu_fast(float x) {
+  const float z = fabsf(x) * 0.70710678118654752f;
+  const float t = __fdividef(1.0f, fmaf(0.3275911f, z, 1.0f));
+  float p = fmaf(1.061405429f, t, -1.453152027f);
+  p = fmaf(p, t, 1.421413741f);
+  p = fmaf(p, t, -0.284496736f);
+  p = fmaf(p, t, 0.254829592f);
+  const float e = 1.0f - p * t * __expf(-z * z);
+  return 0.5f * x * (1.0f + copysignf(e, x));
+}
+
+__device__ __forceinline__ uint32_t pack_bf16(float lo, float hi) {
+  __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);
+  return *reinterpret_cast<uint32_t*>(&v);
+}
+
+// byte offset of (row, 16-byte chunk) inside one K-block in the SWIZZLE_128B K-major layout
+__device__ __host__ __forceinline__ uint32_t sw128_off(int row, int chunk) {
+  return (uint32_t)((row >> 3) * 1024 + (row & 7) * 128 + ((chunk ^ (row & 7)) << 4));
+}
+
+// ------------------------------------------------------------------------------------------ weight image
+// image = [W1 K-blocks][W2: 2 K-blocks][W3: 2 K-blocks], each K-block 128 rows x 64 k, bf16, pre-swizzled
+__global__ void pack_weights_kernel(const float* __restrict__ w1, const float* __restrict__ w2, const float* __restrict__ w3,
+                                    int k1, int k1p, int nout, uint8_t* __restrict__ img) {
+  const int nkb = nkb1(k1p);
+  const int total = (nkb + 4) * 128 * 8;  // 16-byte chunks
+  for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += gridDim.x * blockDim.x) {
+    const int kb = idx / (128 * 8), row = (idx / 8) % 128, chunk = idx % 8;
+    uint32_t packed[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      float v[2];
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        const int kk = chunk * 8 + j * 2 + h;
+        float x = 0.f;
+        if (kb < nkb) {
+          const int k = kb * 64 + kk;
+          if (k < k1) x = w1[(size_t)row * k1 + k];
+        } else if (kb < nkb + 2) {
+          x = w2[(size_t)row * 128 + (kb - nkb) * 64 + kk];
+        } else {
+          if (row < nout) x = w3[(size_t)row * 128 + (kb - nkb - 2) * 64 + kk];
+        }
+        v[h] = x;
+      }
+      packed[j] = pack_bf16(v[0], v[1]);
+    }
+    *reinterpret_cast<uint4*>(img + (size_t)kb * KB_BYTES + sw128_off(row, chunk)) =
+        make_uint4(packed[0], packed[1], packed[2], packed[3]);
+  }
+}
+
+// ------------------------------------------------------------------------------------------ producers
+// pointer to the 64 fp32 source values of (tile row, K-block kb), or nullptr for an all-zero row
+template <int MODE>
+__device__ __forceinline__ const float* chunk_src(const fvgn_mlp_desc& d, int64_t row, int kb, int s, int r) {
+  if (row >= d.rows) return nullptr;
+  if (MODE == FVGN_MLP_EDGE) {
+    if (kb < 2) return d.in0 + (size_t)s * 128 + kb * 64;
+    if (kb < 4) return d.in0 + (size_t)r * 128 + (kb - 2) * 64;
+    return d.in1 + (size_t)row * 128 + (kb - 4) * 64;
+  } else if (MODE == FVGN_MLP_NODE) {
+    if (kb == 0) return d.in0 + (size_t)row * 64;
+    return d.in1 + (size_t)row * 128 + (kb - 1) * 64;
+  } else {
+    return d.in0 + (size_t)row * 128 + kb * 64;
+  }
+}
+
+template <int MODE>
+__device__ __forceinline__ void produce_chunk(const fvgn_mlp_desc& d, int64_t row0, int kb, uint8_t* stage, int pw, int lane) {
+  if (MODE == FVGN_MLP_ENC_NODE || MODE == FVGN_MLP_ENC_EDGE) {
+    // one thread per row: 16 bf16 (K padded to 16) = chunks 0 and 1 of the row
+    const int rloc = pw * 32 + lane;
+    const int64_t row = row0 + rloc;
+    float v[16];
+#pragma unroll
+    for (int j = 0; j < 16; ++j) v[j] = 0.f;
+    if (row < d.rows) {
+      if (MODE == FVGN_MLP_ENC_NODE) {
+        const float4* p = reinterpret_cast<const float4*>(d.in0 + (size_t)row * 12);
+        const float4 a = p[0], b = p[1], c = p[2];
+        v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+        v[8] = c.x; v[9] = c.y; v[10] = c.z; v[11] = c.w;
+      } else {  // importer.py:54-78
+        const int s = d.idx_s[row], r = d.idx_r[row];
+        const float4* ps = reinterpret_cast<const float4*>(d.in0 + (size_t)s * 12);
+        const float4* pr = reinterpret_cast<const float4*>(d.in0 + (size_t)r * 12);
+        const float4 a = ps[0], b = ps[1], c = ps[2], e = pr[0], f = pr[1], g = pr[2];
+        v[0] = a.x - e.x; v[1] = a.y - e.y; v[2] = a.z - e.z; v[3] = a.w - e.w;
+        v[4] = b.x - f.x; v[5] = b.y - f.y; v[6] = b.z - f.z; v[7] = b.w - f.w;
+        v[8] = c.x - g.x; v[9] = c.y - g.y; v[10] = c.z - g.z; v[11] = c.w - g.w;
+        const float2 qs = *reinterpret_cast<const float2*>(d.in1 + (size_t)s * 2);
+        const float2 qr = *reinterpret_cast<const float2*>(d.in1 + (size_t)r * 2);
+        const float dx = qs.x - qr.x, dy = qs.y - qr.y;
+        v[12] = dx; v[13] = dy; v[14] = sqrtf(dx * dx + dy * dy);
+      }
+    }
+#pragma unroll
+    for (int c = 0; c < 2; ++c)
+      *reinterpret_cast<uint4*>(stage + sw128_off(rloc, c)) =
+          make_uint4(pack_bf16(v[c * 8 + 0], v[c * 8 + 1]), pack_bf16(v[c * 8 + 2], v[c * 8 + 3]),
+                     pack_bf16(v[c * 8 + 4], v[c * 8 + 5]), pack_bf16(v[c * 8 + 6], v[c * 8 + 7]));
+    return;
+  }
+  // generic: 8 lanes per row (32 B of fp32 -> one 16-B bf16 chunk each), 4 rows per warp-instruction, 8 passes
+  const int seg = lane & 7;
+  float4 lo[8], hi[8];
+  const float* src[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const int rloc = i * 16 + pw * 4 + (lane >> 3);
+    const int64_t row = row0 + rloc;
+    int s = 0, r = 0;
+    if (MODE == FVGN_MLP_EDGE && kb < 4 && row < d.rows) {
+      if (kb < 2) s = d.idx_s[row]; else r = d.idx_r[row];
+    }
+    src[i] = chunk_src<MODE>(d, row, kb, s, r);
+  }
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    if (src[i]) {
+      lo[i] = __ldg(reinterpret_cast<const float4*>(src[i] + seg * 8));
+      hi[i] = __ldg(reinterpret_cast<const float4*>(src[i] + seg * 8 + 4));
+    } else {
+      lo[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+      hi[i] = lo[i];
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const int rloc = i * 16 + pw * 4 + (lane >> 3);
+    *reinterpret_cast<uint4*>(stage + sw128_off(rloc, seg)) =
+        make_uint4(pack_bf16(lo[i].x, lo[i].y), pack_bf16(lo[i].z, lo[i].w), pack_bf16(hi[i].x, hi[i].y),
+                   pack_bf16(hi[i].z, hi[i].w));
+  }
+}
+
+// ------------------------------------------------------------------------------------------ forward kernel
+template <int MODE>
+__global__ void __launch_bounds__(NTHREADS, 1) mlp_tc_fwd_kernel(const fvgn_mlp_desc d) {
+  using C = TCfg<MODE>;
+  constexpr int NKB1 = nkb1(C::K1P);
+  constexpr int LASTK = (C::K1P - 64 * (NKB1 - 1)) / 16;  // MMAs (K=16) in the last K-block of layer 1
+  constexpr int NSTAGE = C::NSTAGE;
+  constexpr uint32_t ACC0 = 0, ACC1 = 128, ACOL = 256;   // TMEM columns: two fp32 accumulators + bf16 A operand (64 cols)
+  FVGN_DYN_SMEM(smem);
+  uint8_t* w_img = smem;
+  uint8_t* ring = w_img + image_bytes(C::K1P);
+  float* stg = reinterpret_cast<float*>(ring + NSTAGE * KB_BYTES);
+  float* sb1 = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(stg) + STG_BYTES);
+  float* sb2 = sb1 + 128;
+  float* sb3 = sb2 + 128;
+  float* sg = sb3 + 128;
+  float* sbeta = sg + 128;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sbeta + 128);
+  // barrier map: [0] weights, [1..NSTAGE] ring full, [1+NSTAGE..2NSTAGE] ring empty, then l1, l2, l3, a_ready
+  const uint32_t bar0 = smem_u32(bars);
+  auto BAR = [&](int i) { return bar0 + 8u * (uint32_t)i; };
+  constexpr int B_W = 0, B_FULL = 1, B_EMPTY = 1 + NSTAGE, B_L1 = 1 + 2 * NSTAGE, B_L2 = B_L1 + 1, B_L3 = B_L1 + 2,
+                B_A = B_L1 + 3;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 24);
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int64_t ntiles = (d.rows + TILE_M - 1) / TILE_M;
+
+  if (tid == 0) {
+    mbar_init(BAR(B_W), 1);
+    for (int s = 0; s < NSTAGE; ++s) {
+      mbar_init(BAR(B_FULL + s), 4);   // one elected lane per producer warp
+      mbar_init(BAR(B_EMPTY + s), 1);  // tcgen05.commit
+    }
+    mbar_init(BAR(B_L1), 1);
+    mbar_init(BAR(B_L2), 1);
+    mbar_init(BAR(B_L3), 1);
+    mbar_init(BAR(B_A), 128);
+    fence_barrier_init();
+  }
+  for (int i = tid; i < 128; i += NTHREADS) {
+    sb1[i] = d.b1[i];
+    sb2[i] = d.b2[i];
+    sb3[i] = (i < C::NOUT) ? d.b3[i] : 0.f;
+    sg[i] = C::LN ? d.ln_g[i] : 1.f;
+    sbeta[i] = C::LN ? d.ln_b[i] : 0.f;
+  }
+  if (warp == 8) tmem_alloc(smem_u32(tmem_slot), 512);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *tmem_slot;
+
+  if (warp == 8) {
+    // =============================================================== MMA issuer (+ weight loader)
+    if (lane == 0) {
+      constexpr uint32_t img_bytes = (uint32_t)image_bytes(C::K1P);
+      mbar_expect_tx(BAR(B_W), img_bytes);
+      for (uint32_t off = 0; off < img_bytes; off += KB_BYTES)
+        bulk_g2s(smem_u32(w_img + off), reinterpret_cast<const uint8_t*>(d.w_bf16) + off, KB_BYTES, BAR(B_W));
+      mbar_wait(BAR(B_W), 0);
+      const uint32_t w1s = smem_u32(w_img), w2s = w1s + NKB1 * KB_BYTES, w3s = w2s + 2 * KB_BYTES;
+      uint32_t it = 0, pa = 0;
+      for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+        // ---- layer 1: A from the smem ring
+        for (int kb = 0; kb < NKB1; ++kb, ++it) {
+          const int s = it % NSTAGE;
+          mbar_wait(BAR(B_FULL + s), (it / NSTAGE) & 1);
+          tc_fence_after();
+          const uint64_t ad = make_desc_k128(smem_u32(ring + s * KB_BYTES));
+          const uint64_t bd = make_desc_k128(w1s + kb * KB_BYTES);
+          const int nk = (kb == NKB1 - 1) ? LASTK : 4;
+          for (int k = 0; k < nk; ++k) umma_ss(tmem + ACC0, ad + 2 * k, bd + 2 * k, IDESC, (kb | k) != 0);
+          umma_commit(BAR(B_EMPTY + s));
+        }
+        umma_commit(BAR(B_L1));
+        // ---- layer 2: A = gelu(layer 1) as bf16 in TMEM
+        mbar_wait(BAR(B_A), pa);
+        pa ^= 1;
+        tc_fence_after();
+        for (int k = 0; k < 8; ++k)
+          umma_ts(tmem + ACC1, tmem + ACOL + 8 * k, make_desc_k128(w2s + (k >> 2) * KB_BYTES) + 2 * (k & 3), IDESC, k != 0);
+        umma_commit(BAR(B_L2));
+        // ---- layer 3
+        mbar_wait(BAR(B_A), pa);
+        pa ^= 1;
+        tc_fence_after();
+        for (int k = 0; k < 8; ++k)
+          umma_ts(tmem + ACC1, tmem + ACOL + 8 * k, make_desc_k128(w3s + (k >> 2) * KB_BYTES) + 2 * (k & 3), IDESC, k != 0);
+        umma_commit(BAR(B_L3));
+      }
+    }
+    __syncwarp();
+  } else if (warp >= 4) {
+    // =============================================================== producers
+    const int pw = warp - 4;
+    uint32_t it = 0;
+    for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+      const int64_t row0 = tile * TILE_M;
+      for (int kb = 0; kb < NKB1; ++kb, ++it) {
+        const int s = it % NSTAGE;
+        mbar_wait(BAR(B_EMPTY + s), ((it / NSTAGE) & 1) ^ 1);
+        produce_chunk<MODE>(d, row0, kb, ring + s * KB_BYTES, pw, lane);
+        fence_proxy_async();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(BAR(B_FULL + s));
+      }
+    }
+  } else {
+    // =============================================================== epilogue (thread <-> row)
+    const uint32_t lane_base = (uint32_t)(warp * 32) << 16;
+    const int rloc = warp * 32 + lane;
+    float* mystg = stg + warp * 32 * STG_LD;
+    uint32_t ph = 0;
+    for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ph ^= 1) {
+      const int64_t row0 = tile * TILE_M;
+      // ---- hidden layers: +bias, GELU, bf16 -> TMEM A operand
+#pragma unroll 1
+      for (int layer = 0; layer < 2; ++layer) {
+        mbar_wait(BAR(layer == 0 ? B_L1 : B_L2), ph);
+        tc_fence_after();
+        const uint32_t acc = tmem + lane_base + (layer == 0 ? ACC0 : ACC1);
+        const float* bias = layer == 0 ? sb1 : sb2;
+#pragma unroll 1
+        for (int c0 = 0; c0 < 128; c0 += 16) {
+          uint32_t r[16], p[8];
+          tmem_ld16(acc + c0, r);
+          tmem_wait_ld();
+#pragma unroll
+          for (int j = 0; j < 8; ++j)
+            p[j] = pack_bf16(gelu_fast(__uint_as_float(r[2 * j]) + bias[c0 + 2 * j]),
+                             gelu_fast(__uint_as_float(r[2 * j + 1]) + bias[c0 + 2 * j + 1]));
+          tmem_st8(tmem + lane_base + ACOL + c0 / 2, p);
+        }
+        tmem_wait_st();
+        tc_fence_before();
+        mbar_arrive(BAR(B_A));
+      }
+      // ---- output layer
+      mbar_wait(BAR(B_L3), ph);
+      tc_fence_after();
+      const uint32_t acc = tmem + lane_base + ACC1;
+      if (C::LN) {
+        float sum = 0.f;
+#pragma unroll 1
+        for (int c0 = 0; c0 < 128; c0 += 16) {
+          uint32_t r[16];
+          tmem_ld16(acc + c0, r);
+          tmem_wait_ld();
+#pragma unroll
+          for (int j = 0; j < 16; ++j) sum += __uint_as_float(r[j]) + sb3[c0 + j];
+        }
+        const float mean = sum * (1.0f / 128.0f);
+        float sq = 0.f;
+#pragma unroll 1
+        for (int c0 = 0; c0 < 128; c0 += 16) {
+          uint32_t r[16];
+          tmem_ld16(acc + c0, r);
+          tmem_wait_ld();
+#pragma unroll
+          for (int j = 0; j < 16; ++j) {
+            const float dv = __uint_as_float(r[j]) + sb3[c0 + j] - mean;
+            sq = fmaf(dv, dv, sq);
+          }
+        }
+        const float rstd = rsqrtf(sq * (1.0f / 128.0f) + 1e-5f);
+        const float* resid = (MODE == FVGN_MLP_EDGE || MODE == FVGN_MLP_NODE) ? d.in1 : nullptr;
+#pragma unroll 1
+        for (int c0 = 0; c0 < 128; c0 += STG_COLS) {
+          uint32_t r[16];
+          tmem_ld16(acc + c0, r);
+          tmem_wait_ld();
+#pragma unroll
+          for (int j = 0; j < 16; j += 4) {
+            float4 y;
+            y.x = (__uint_as_float(r[j + 0]) + sb3[c0 + j + 0] - mean) * rstd * sg[c0 + j + 0] + sbeta[c0 + j + 0];
+            y.y = (__uint_as_float(r[j + 1]) + sb3[c0 + j + 1] - mean) * rstd * sg[c0 + j + 1] + sbeta[c0 + j + 1];
+            y.z = (__uint_as_float(r[j + 2]) + sb3[c0 + j + 2] - mean) * rstd * sg[c0 + j + 2] + sbeta[c0 + j + 2];
+            y.w = (__uint_as_float(r[j + 3]) + sb3[c0 + j + 3] - mean) * rstd * sg[c0 + j + 3] + sbeta[c0 + j + 3];
+            *reinterpret_cast<float4*>(mystg + lane * STG_LD + j) = y;
+          }
+          __syncwarp();
+          // coalesced write-out: 4 lanes cover the 64 B of one row, 8 rows per instruction
+#pragma unroll
+          for (int pass = 0; pass < 4; ++pass) {
+            const int rr = pass * 8 + (lane >> 2), cc = (lane & 3) * 4;
+            const int64_t row = row0 + warp * 32 + rr;
+            if (row < d.rows) {
+              const float4 y = *reinterpret_cast<const float4*>(mystg + rr * STG_LD + cc);
+              const size_t o = (size_t)row * 128 + c0 + cc;
+              if (d.out) *reinterpret_cast<float4*>(d.out + o) = y;
+              if (resid && d.out_res) {
+                const float4 x = __ldg(reinterpret_cast<const float4*>(resid + o));
+                *reinterpret_cast<float4*>(d.out_res + o) = make_float4(x.x + y.x, x.y + y.y, x.z + y.z, x.w + y.w);
+              }
+            }
+          }
+          __syncwarp();
+        }
+      } else {
+        // decoder: 3 outputs per row, no LayerNorm
+        uint32_t r[16];
+        tmem_ld16(acc, r);
+        tmem_wait_ld();
+        const int64_t row = row0 + rloc;
+        if (row < d.rows) {
+#pragma unroll
+          for (int j = 0; j < 3; ++j) d.out[(size_t)row * 3 + j] = __uint_as_float(r[j]) + sb3[j];
+        }
+      }
+      tc_fence_before();
+    }
+  }
+  __syncthreads();
+  if (warp == 8) {
+    tc_fence_after();
+    tmem_dealloc(tmem, 512);
+  }
+}
+
+template <int MODE>
+int launch_tc_fwd(const fvgn_mlp_desc& d, void* stream) {
+  auto kern = mlp_tc_fwd_kernel<MODE>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes<MODE>()) != cudaSuccess)
+      return FVGN_ERR_LAUNCH;
+    attr_set = true;
+  }
+  static int num_sms = 0;
+  if (num_sms == 0) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev);
+    if (num_sms <= 0) num_sms = 148;
+  }
+  const int64_t ntiles = (d.rows + TILE_M - 1) / TILE_M;
+  const unsigned grid = (unsigned)(ntiles < num_sms ? ntiles : num_sms);
+  kern<<<grid, NTHREADS, smem_bytes<MODE>(), (cudaStream_t)stream>>>(d);
+  FVGN_CHECK_LAUNCH();
+  return FVGN_OK;
+}
+
+}  // namespace
+
+int fvgn_mlp_backward_simt(const fvgn_mlp_desc* d, void* stream);
+int fvgn_mlp_simt_partials(int64_t rows);
+
+int fvgn_mlp_forward_tc(const fvgn_mlp_desc* d, void* stream) {
+  if (!d->w_bf16) return FVGN_ERR_NULL;
+  if ((((uintptr_t)d->w_bf16) & 15) != 0) return FVGN_ERR_ALIGN;
+  switch (d->mode) {
+    case FVGN_MLP_EDGE: return launch_tc_fwd<FVGN_MLP_EDGE>(*d, stream);
+    case FVGN_MLP_NODE: return launch_tc_fwd<FVGN_MLP_NODE>(*d, stream);
+    case FVGN_MLP_ENC_NODE: return launch_tc_fwd<FVGN_MLP_ENC_NODE>(*d, stream);
+    case FVGN_MLP_ENC_EDGE: return launch_tc_fwd<FVGN_MLP_ENC_EDGE>(*d, stream);
+    case FVGN_MLP_DEC: return launch_tc_fwd<FVGN_MLP_DEC>(*d, stream);
+  }
+  return FVGN_ERR_UNSUPPORTED;
+}
+
+// Backward of the bf16 mode: until the tcgen05 backward lands this runs the fp32 SIMT backward (it recomputes the
+// forward in fp32, so the gradient is that of the fp32 function evaluated at the same weights).
+int fvgn_mlp_backward_tc(const fvgn_mlp_desc* d, void* stream) {
+  if (d->n_partials != fvgn_mlp_simt_partials(d->rows)) return FVGN_ERR_SHAPE;
+  return fvgn_mlp_backward_simt(d, stream);
+}
+int fvgn_mlp_tc_partials(int32_t, int64_t rows) { return fvgn_mlp_simt_partials(rows); }
+
+int64_t fvgn_mlp_tc_packed_bytes(int32_t mode) {
+  switch (mode) {
+    case FVGN_MLP_EDGE: return image_bytes(384);
+    case FVGN_MLP_NODE: return image_bytes(192);
+    case FVGN_MLP_ENC_NODE: return image_bytes(16);
+    case FVGN_MLP_ENC_EDGE: return image_bytes(16);
+    case FVGN_MLP_DEC: return image_bytes(128);
+  }
+  return -1;
+}
+
+int fvgn_mlp_tc_pack(int32_t mode, const float* w1, const float* w2, const float* w3, void* packed, void* stream) {
+  int k1, k1p, nout = 128;
+  switch (mode) {
+    case FVGN_MLP_EDGE: k1 = 384; k1p = 384; break;
+    case FVGN_MLP_NODE: k1 = 192; k1p = 192; break;
+    case FVGN_MLP_ENC_NODE: k1 = 12; k1p = 16; break;
+    case FVGN_MLP_ENC_EDGE: k1 = 15; k1p = 16; break;
+    case FVGN_MLP_DEC: k1 = 128; k1p = 128; nout = 3; break;
+    default: return FVGN_ERR_UNSUPPORTED;
+  }
+  if (!w1 || !w2 || !w3 || !packed) return FVGN_ERR_NULL;
+  pack_weights_kernel<<<64, 256, 0, (cudaStream_t)stream>>>(w1, w2, w3, k1, k1p, nout, reinterpret_cast<uint8_t*>(packed));
+  FVGN_CHECK_LAUNCH();
+  return FVGN_OK;
+}
