@@ -66,3 +66,16 @@ def test_missing_library_fails_loudly(monkeypatch):
     from gen_fvgn_steady_b200 import _lib
     with pytest.raises(RuntimeError):
         _lib.fptr(torch.zeros(4))  # host tensor: no CPU path
+
+
+@pytest.mark.parametrize("name", ["synth_ns_batch2_v1", "poisson_quad_tri_v2"])
+def test_product_bf16_within_stated_tolerance(name):
+    """Throughput mode (tcgen05, bf16 operands, fp32 accumulate): latents / losses within the stated 1e-2."""
+    PU.use_real_kernels()
+    model, out, loss, z = PU.run_product(name, "cuda", "bf16")
+    rep = {}
+    PU.compare_with_golden(model, out, loss, z, "f64", tol=1e9, gtol=1e9, report=rep)
+    with open(f"gpurun_out/parity_bf16_{name}.json", "w") as f:
+        json.dump({k: float(v) for k, v in rep.items() if k != "param_grad_worst_key"}, f, indent=1)
+    for k in ("loss_cont", "loss_mom_x", "loss_mom_y", "loss_press", "decoder_out", "uvp_node", "uvp_cell", "loss"):
+        assert rep[k] < 1e-2, (k, rep[k])
