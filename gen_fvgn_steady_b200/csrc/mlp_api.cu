@@ -11,6 +11,7 @@ int fvgn_mlp_forward_tc(const fvgn_mlp_desc* d, void* stream);
 int fvgn_mlp_backward_tc(const fvgn_mlp_desc* d, void* stream);
 int fvgn_mlp_tc_partials(int32_t mode, int64_t rows);
 int64_t fvgn_mlp_tc_packed_bytes(int32_t mode);
+int64_t fvgn_mlp_tc_workspace_bytes(int32_t mode, int64_t rows);
 int fvgn_mlp_tc_pack(int32_t mode, const float* w1, const float* w2, const float* w3, void* packed, void* stream);
 #endif
 
@@ -31,6 +32,14 @@ extern "C" int32_t fvgn_mlp_bwd_partials(int32_t mode, int32_t precision, int64_
   (void)mode;
   (void)precision;
   return fvgn_mlp_simt_partials(rows);
+}
+
+extern "C" int64_t fvgn_mlp_bwd_workspace_bytes(int32_t mode, int32_t precision, int64_t rows) {
+#ifndef FVGN_EMU
+  if (precision == FVGN_PREC_BF16) return fvgn_mlp_tc_workspace_bytes(mode, rows);
+#endif
+  (void)mode; (void)precision; (void)rows;
+  return 0;
 }
 
 extern "C" int64_t fvgn_mlp_packed_bytes(int32_t mode) {

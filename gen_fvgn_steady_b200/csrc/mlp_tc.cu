@@ -69,92 +69,6 @@ __global__ void pack_weights_kernel(const float* __restrict__ w1, const float* _
   }
 }
 
-// ------------------------------------------------------------------------------------------ producers
-// pointer to the 64 fp32 source values of (tile row, K-block kb), or nullptr for an all-zero row
-template <int MODE>
-__device__ __forceinline__ const float* chunk_src(const fvgn_mlp_desc& d, int64_t row, int kb, int s, int r) {
-  if (row >= d.rows) return nullptr;
-  if (MODE == FVGN_MLP_EDGE) {
-    if (kb < 2) return d.in0 + (size_t)s * 128 + kb * 64;
-    if (kb < 4) return d.in0 + (size_t)r * 128 + (kb - 2) * 64;
-    return d.in1 + (size_t)row * 128 + (kb - 4) * 64;
-  } else if (MODE == FVGN_MLP_NODE) {
-    if (kb == 0) return d.in0 + (size_t)row * 64;
-    return d.in1 + (size_t)row * 128 + (kb - 1) * 64;
-  } else {
-    return d.in0 + (size_t)row * 128 + kb * 64;
-  }
-}
-
-template <int MODE>
-__device__ __forceinline__ void produce_chunk(const fvgn_mlp_desc& d, int64_t row0, int kb, uint8_t* stage, int pw, int lane) {
-  if (MODE == FVGN_MLP_ENC_NODE || MODE == FVGN_MLP_ENC_EDGE) {
-    // one thread per row: 16 bf16 (K padded to 16) = chunks 0 and 1 of the row
-    const int rloc = pw * 32 + lane;
-    const int64_t row = row0 + rloc;
-    float v[16];
-#pragma unroll
-    for (int j = 0; j < 16; ++j) v[j] = 0.f;
-    if (row < d.rows) {
-      if (MODE == FVGN_MLP_ENC_NODE) {
-        const float4* p = reinterpret_cast<const float4*>(d.in0 + (size_t)row * 12);
-        const float4 a = p[0], b = p[1], c = p[2];
-        v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
-        v[8] = c.x; v[9] = c.y; v[10] = c.z; v[11] = c.w;
-      } else {  // importer.py:54-78
-        const int s = d.idx_s[row], r = d.idx_r[row];
-        const float4* ps = reinterpret_cast<const float4*>(d.in0 + (size_t)s * 12);
-        const float4* pr = reinterpret_cast<const float4*>(d.in0 + (size_t)r * 12);
-        const float4 a = ps[0], b = ps[1], c = ps[2], e = pr[0], f = pr[1], g = pr[2];
-        v[0] = a.x - e.x; v[1] = a.y - e.y; v[2] = a.z - e.z; v[3] = a.w - e.w;
-        v[4] = b.x - f.x; v[5] = b.y - f.y; v[6] = b.z - f.z; v[7] = b.w - f.w;
-        v[8] = c.x - g.x; v[9] = c.y - g.y; v[10] = c.z - g.z; v[11] = c.w - g.w;
-        const float2 qs = *reinterpret_cast<const float2*>(d.in1 + (size_t)s * 2);
-        const float2 qr = *reinterpret_cast<const float2*>(d.in1 + (size_t)r * 2);
-        const float dx = qs.x - qr.x, dy = qs.y - qr.y;
-        v[12] = dx; v[13] = dy; v[14] = sqrtf(dx * dx + dy * dy);
-      }
-    }
-#pragma unroll
-    for (int c = 0; c < 2; ++c)
-      *reinterpret_cast<uint4*>(stage + sw128_off(rloc, c)) =
-          make_uint4(pack_bf16(v[c * 8 + 0], v[c * 8 + 1]), pack_bf16(v[c * 8 + 2], v[c * 8 + 3]),
-                     pack_bf16(v[c * 8 + 4], v[c * 8 + 5]), pack_bf16(v[c * 8 + 6], v[c * 8 + 7]));
-    return;
-  }
-  // generic: 8 lanes per row (32 B of fp32 -> one 16-B bf16 chunk each), 4 rows per warp-instruction, 8 passes
-  const int seg = lane & 7;
-  float4 lo[8], hi[8];
-  const float* src[8];
-#pragma unroll
-  for (int i = 0; i < 8; ++i) {
-    const int rloc = i * 16 + pw * 4 + (lane >> 3);
-    const int64_t row = row0 + rloc;
-    int s = 0, r = 0;
-    if (MODE == FVGN_MLP_EDGE && kb < 4 && row < d.rows) {
-      if (kb < 2) s = d.idx_s[row]; else r = d.idx_r[row];
-    }
-    src[i] = chunk_src<MODE>(d, row, kb, s, r);
-  }
-#pragma unroll
-  for (int i = 0; i < 8; ++i) {
-    if (src[i]) {
-      lo[i] = __ldg(reinterpret_cast<const float4*>(src[i] + seg * 8));
-      hi[i] = __ldg(reinterpret_cast<const float4*>(src[i] + seg * 8 + 4));
-    } else {
-      lo[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-      hi[i] = lo[i];
-    }
-  }
-#pragma unroll
-  for (int i = 0; i < 8; ++i) {
-    const int rloc = i * 16 + pw * 4 + (lane >> 3);
-    *reinterpret_cast<uint4*>(stage + sw128_off(rloc, seg)) =
-        make_uint4(pack_bf16(lo[i].x, lo[i].y), pack_bf16(lo[i].z, lo[i].w), pack_bf16(hi[i].x, hi[i].y),
-                   pack_bf16(hi[i].z, hi[i].w));
-  }
-}
-
 // ------------------------------------------------------------------------------------------ forward kernel
 template <int MODE>
 __global__ void __launch_bounds__(NTHREADS, 1) mlp_tc_fwd_kernel(const fvgn_mlp_desc d) {
@@ -400,9 +314,6 @@ int launch_tc_fwd(const fvgn_mlp_desc& d, void* stream) {
 
 }  // namespace
 
-int fvgn_mlp_backward_simt(const fvgn_mlp_desc* d, void* stream);
-int fvgn_mlp_simt_partials(int64_t rows);
-
 int fvgn_mlp_forward_tc(const fvgn_mlp_desc* d, void* stream) {
   if (!d->w_bf16) return FVGN_ERR_NULL;
   if ((((uintptr_t)d->w_bf16) & 15) != 0) return FVGN_ERR_ALIGN;
@@ -415,14 +326,6 @@ int fvgn_mlp_forward_tc(const fvgn_mlp_desc* d, void* stream) {
   }
   return FVGN_ERR_UNSUPPORTED;
 }
-
-// Backward of the bf16 mode: until the tcgen05 backward lands this runs the fp32 SIMT backward (it recomputes the
-// forward in fp32, so the gradient is that of the fp32 function evaluated at the same weights).
-int fvgn_mlp_backward_tc(const fvgn_mlp_desc* d, void* stream) {
-  if (d->n_partials != fvgn_mlp_simt_partials(d->rows)) return FVGN_ERR_SHAPE;
-  return fvgn_mlp_backward_simt(d, stream);
-}
-int fvgn_mlp_tc_partials(int32_t, int64_t rows) { return fvgn_mlp_simt_partials(rows); }
 
 int64_t fvgn_mlp_tc_packed_bytes(int32_t mode) {
   switch (mode) {

@@ -135,4 +135,169 @@ __host__ __device__ constexpr uint32_t make_idesc(int n, int a_mn_major, int b_m
          ((uint32_t)(n >> 3) << 17) | ((128u >> 4) << 24);
 }
 
+// ------------------------------------------------------------------------------------------ producers
+// pointer to the 64 fp32 source values of (tile row, K-block kb), or nullptr for an all-zero row
+template <int MODE>
+__device__ __forceinline__ const float* chunk_src(const fvgn_mlp_desc& d, int64_t row, int kb, int s, int r) {
+  if (row >= d.rows) return nullptr;
+  if (MODE == FVGN_MLP_EDGE) {
+    if (kb < 2) return d.in0 + (size_t)s * 128 + kb * 64;
+    if (kb < 4) return d.in0 + (size_t)r * 128 + (kb - 2) * 64;
+    return d.in1 + (size_t)row * 128 + (kb - 4) * 64;
+  } else if (MODE == FVGN_MLP_NODE) {
+    if (kb == 0) return d.in0 + (size_t)row * 64;
+    return d.in1 + (size_t)row * 128 + (kb - 1) * 64;
+  } else {
+    return d.in0 + (size_t)row * 128 + kb * 64;
+  }
+}
+
+template <int MODE>
+__device__ __forceinline__ void produce_chunk(const fvgn_mlp_desc& d, int64_t row0, int kb, uint8_t* stage, int pw, int lane) {
+  if (MODE == FVGN_MLP_ENC_NODE || MODE == FVGN_MLP_ENC_EDGE) {
+    // one thread per row: 16 bf16 (K padded to 16) = chunks 0 and 1 of the row
+    const int rloc = pw * 32 + lane;
+    const int64_t row = row0 + rloc;
+    float v[16];
+#pragma unroll
+    for (int j = 0; j < 16; ++j) v[j] = 0.f;
+    if (row < d.rows) {
+      if (MODE == FVGN_MLP_ENC_NODE) {
+        const float4* p = reinterpret_cast<const float4*>(d.in0 + (size_t)row * 12);
+        const float4 a = p[0], b = p[1], c = p[2];
+        v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+        v[8] = c.x; v[9] = c.y; v[10] = c.z; v[11] = c.w;
+      } else {  // importer.py:54-78
+        const int s = d.idx_s[row], r = d.idx_r[row];
+        const float4* ps = reinterpret_cast<const float4*>(d.in0 + (size_t)s * 12);
+        const float4* pr = reinterpret_cast<const float4*>(d.in0 + (size_t)r * 12);
+        const float4 a = ps[0], b = ps[1], c = ps[2], e = pr[0], f = pr[1], g = pr[2];
+        v[0] = a.x - e.x; v[1] = a.y - e.y; v[2] = a.z - e.z; v[3] = a.w - e.w;
+        v[4] = b.x - f.x; v[5] = b.y - f.y; v[6] = b.z - f.z; v[7] = b.w - f.w;
+        v[8] = c.x - g.x; v[9] = c.y - g.y; v[10] = c.z - g.z; v[11] = c.w - g.w;
+        const float2 qs = *reinterpret_cast<const float2*>(d.in1 + (size_t)s * 2);
+        const float2 qr = *reinterpret_cast<const float2*>(d.in1 + (size_t)r * 2);
+        const float dx = qs.x - qr.x, dy = qs.y - qr.y;
+        v[12] = dx; v[13] = dy; v[14] = sqrtf(dx * dx + dy * dy);
+      }
+    }
+#pragma unroll
+    for (int c = 0; c < 2; ++c)
+      *reinterpret_cast<uint4*>(stage + sw128_off(rloc, c)) =
+          make_uint4(pack_bf16(v[c * 8 + 0], v[c * 8 + 1]), pack_bf16(v[c * 8 + 2], v[c * 8 + 3]),
+                     pack_bf16(v[c * 8 + 4], v[c * 8 + 5]), pack_bf16(v[c * 8 + 6], v[c * 8 + 7]));
+#pragma unroll
+    for (int c = 2; c < 8; ++c)  // the rest of the 64-wide block must be zero (it is an MMA operand in the wgrad pass)
+      *reinterpret_cast<uint4*>(stage + sw128_off(rloc, c)) = make_uint4(0u, 0u, 0u, 0u);
+    return;
+  }
+  // generic: 8 lanes per row (32 B of fp32 -> one 16-B bf16 chunk each), 4 rows per warp-instruction, 8 passes
+  const int seg = lane & 7;
+  float4 lo[8], hi[8];
+  const float* src[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const int rloc = i * 16 + pw * 4 + (lane >> 3);
+    const int64_t row = row0 + rloc;
+    int s = 0, r = 0;
+    if (MODE == FVGN_MLP_EDGE && kb < 4 && row < d.rows) {
+      if (kb < 2) s = d.idx_s[row]; else r = d.idx_r[row];
+    }
+    src[i] = chunk_src<MODE>(d, row, kb, s, r);
+  }
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    if (src[i]) {
+      lo[i] = __ldg(reinterpret_cast<const float4*>(src[i] + seg * 8));
+      hi[i] = __ldg(reinterpret_cast<const float4*>(src[i] + seg * 8 + 4));
+    } else {
+      lo[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+      hi[i] = lo[i];
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const int rloc = i * 16 + pw * 4 + (lane >> 3);
+    *reinterpret_cast<uint4*>(stage + sw128_off(rloc, seg)) =
+        make_uint4(pack_bf16(lo[i].x, lo[i].y), pack_bf16(lo[i].z, lo[i].w), pack_bf16(hi[i].x, hi[i].y),
+                   pack_bf16(hi[i].z, hi[i].w));
+  }
+}
+
+
+// ------------------------------------------------------------------------------------------ extra helpers (backward)
+__device__ __forceinline__ void tmem_ld8(uint32_t taddr, uint32_t (&r)[8]) {
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+               : "r"(taddr)
+               : "memory");
+}
+// linear shared -> global bulk store (TMA engine), bulk-group completion
+__device__ __forceinline__ void bulk_s2g(void* dst, uint32_t src_smem, uint32_t bytes) {
+  asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst), "r"(src_smem), "r"(bytes) : "memory");
+  asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+}
+__device__ __forceinline__ void bulk_wait_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait0() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+// named barrier among the 128 epilogue threads (barrier 0 is __syncthreads)
+__device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, 128;" ::: "memory"); }
+
+// gelu(x) and gelu'(x) from one erf/exp evaluation (A&S 7.1.26)
+__device__ __forceinline__ void gelu_pair(float x, float& h, float& g) {
+  const float z = fabsf(x) * 0.70710678118654752f;
+  const float t = __fdividef(1.0f, fmaf(0.3275911f, z, 1.0f));
+  float p = fmaf(1.061405429f, t, -1.453152027f);
+  p = fmaf(p, t, 1.421413741f);
+  p = fmaf(p, t, -0.284496736f);
+  p = fmaf(p, t, 0.254829592f);
+  const float ex = __expf(-z * z);  // = exp(-x^2/2)
+  const float cdf = 0.5f * (1.0f + copysignf(1.0f - p * t * ex, x));
+  h = x * cdf;
+  g = fmaf(x * 0.39894228040143268f, ex, cdf);
+}
+
+__device__ __forceinline__ float bf16_lo(uint32_t w) { return __uint_as_float(w << 16); }
+__device__ __forceinline__ float bf16_hi(uint32_t w) { return __uint_as_float(w & 0xFFFF0000u); }
+
+// Column sums over the 32 lanes (rows) of a warp for 16 columns held per lane: returns, in lane L, the total of
+// column (L & 15).  16 + 8 + 4 + 2 + 1 = 31 shuffles.
+__device__ __forceinline__ float warp_colsum16(float (&v)[16], int lane) {
+#pragma unroll
+  for (int j = 0; j < 16; ++j) v[j] += __shfl_xor_sync(0xffffffffu, v[j], 16);
+  float a[8];
+  {
+    const bool up = (lane >> 3) & 1;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const float send = up ? v[j] : v[j + 8];
+      const float recv = __shfl_xor_sync(0xffffffffu, send, 8);
+      a[j] = (up ? v[j + 8] : v[j]) + recv;
+    }
+  }
+  float b[4];
+  {
+    const bool up = (lane >> 2) & 1;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const float send = up ? a[j] : a[j + 4];
+      const float recv = __shfl_xor_sync(0xffffffffu, send, 4);
+      b[j] = (up ? a[j + 4] : a[j]) + recv;
+    }
+  }
+  float c[2];
+  {
+    const bool up = (lane >> 1) & 1;
+#pragma unroll
+    for (int j = 0; j < 2; ++j) {
+      const float send = up ? b[j] : b[j + 2];
+      const float recv = __shfl_xor_sync(0xffffffffu, send, 2);
+      c[j] = (up ? b[j + 2] : b[j]) + recv;
+    }
+  }
+  const bool up = lane & 1;
+  const float send = up ? c[0] : c[1];
+  const float recv = __shfl_xor_sync(0xffffffffu, send, 1);
+  return (up ? c[1] : c[0]) + recv;
+}
+
 }  // namespace tc

@@ -107,6 +107,11 @@ def mlp_backward(mode, precision, rows, params, in0, in1, idx_s, idx_r, d_out, d
     d.d_out, d.d_gather = fptr(d_out), fptr(d_gather, True)
     d.d_in0, d.d_in1 = fptr(d_in0, True), fptr(d_in1, True)
     d.partials, d.n_partials, d.d_params = fptr(partials), npart, fptr(flat)
+    ws_bytes = int(lib.fvgn_mlp_bwd_workspace_bytes(mode, PREC[precision], rows))
+    if ws_bytes > 0:
+        ws = torch.empty(ws_bytes + 1024, dtype=torch.uint8, device=in0.device)
+        d._ws = ws
+        d.workspace = (ws.data_ptr() + 1023) // 1024 * 1024
     _lib.call("fvgn_mlp_backward", ctypes.byref(d), _lib.stream_ptr(in0.device))
     k1 = _MLP_K1[mode]
     nout = 3 if mode == _lib.FVGN_MLP_DEC else 128

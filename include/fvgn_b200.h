@@ -51,8 +51,8 @@ int fvgn_inc_reduce(const float* src, const int32_t* ptr, const int32_t* code, f
 #define FVGN_MLP_ENC_NODE 2 /* Encoder.nb_encoder EPD.py:118                      : in=x[N,12],          K1=12,  LN       */
 #define FVGN_MLP_ENC_EDGE 3 /* importer.py:54-78 + Encoder.eb_encoder EPD.py:119  : in=[xn[s]-xn[r]|dpos|norm], K1=15, LN */
 #define FVGN_MLP_DEC 4      /* Decoder EPD.py:215-219                             : in=x[N,128], K1=128, out=3, no LN    */
+#define FVGN_MLP_NO_RESIDUAL 1 /* desc.flags */
 #define FVGN_PREC_FP32 0    /* SIMT fp32 FMA (parity mode, rel 1e-5 vs the reference's CPU fp32)   */
-#define FVGN_MLP_NO_RESIDUAL 1
 #define FVGN_PREC_BF16 1    /* tcgen05.mma kind::f16 bf16 operands, fp32 accumulate in TMEM (throughput mode) */
 
 typedef struct fvgn_mlp_desc {
@@ -81,10 +81,12 @@ typedef struct fvgn_mlp_desc {
   float* partials;     /* [n_partials, fvgn_mlp_param_count(mode)] per-CTA weight-gradient partial sums */
   int32_t n_partials;  /* = grid size of the backward kernel, from fvgn_mlp_bwd_partials() */
   float* d_params;     /* [param_count] flat: w1,b1,w2,b2,w3,b3,ln_g,ln_b (deterministic reduction of partials) */
+  void* workspace;     /* backward scratch of fvgn_mlp_bwd_workspace_bytes() bytes (bf16 dZ1 tile images), 1024-B aligned */
 } fvgn_mlp_desc;
 
 int64_t fvgn_mlp_param_count(int32_t mode);
 int32_t fvgn_mlp_bwd_partials(int32_t mode, int32_t precision, int64_t rows); /* number of per-CTA partial buffers to allocate */
+int64_t fvgn_mlp_bwd_workspace_bytes(int32_t mode, int32_t precision, int64_t rows);
 int64_t fvgn_mlp_packed_bytes(int32_t mode);
 /* fp32 parameters -> bf16 UMMA operand image (weights change every optimiser step; call once per step) */
 int fvgn_mlp_pack_weights(int32_t mode, const float* w1, const float* w2, const float* w3, void* packed, void* stream);

@@ -93,3 +93,45 @@ def test_tc_forward_is_deterministic():
     a, _ = ops.mlp_forward(code, "bf16", 50000, params, in0, in1, s, r)
     b, _ = ops.mlp_forward(code, "bf16", 50000, params, in0, in1, s, r)
     assert torch.equal(a, b)
+
+
+def _bwd_run(code, mode, precision, rows, nodes, params, in0, in1, s, r, d_out, d_gather, flags=0):
+    from gen_fvgn_steady_b200 import ops
+    dev = in0.device
+    d_in0 = d_in1 = None
+    if mode == "EDGE":
+        d_in0, d_in1 = torch.zeros((rows, 256), device=dev), torch.zeros((rows, 128), device=dev)
+    elif mode == "NODE":
+        d_in0, d_in1 = torch.zeros((rows, 64), device=dev), torch.zeros((rows, 128), device=dev)
+    elif mode == "DEC":
+        d_in0 = torch.zeros((rows, 128), device=dev)
+    grads = ops.mlp_backward(code, precision, rows, params, in0, in1, s, r, d_out, d_gather, d_in0, d_in1, flags=flags)
+    torch.cuda.synchronize()
+    return [g.clone() for g in grads], d_in0, d_in1
+
+
+@pytest.mark.parametrize("mode", MODES)
+@pytest.mark.parametrize("rows", [1000, 128 * 148 + 300])
+def test_tc_backward_matches_fp32(mode, rows):
+    """tcgen05 backward (bf16 operands) vs the fp32 SIMT backward on the same inputs: relative L2 within 3e-2."""
+    dev = torch.device("cuda")
+    nodes = 3000
+    code, params, in0, in1, s, r, X, res = _inputs(mode, rows, nodes, dev, seed=3)
+    g = torch.Generator(device=dev).manual_seed(11)
+    nout = 3 if mode == "DEC" else 128
+    d_out = torch.randn((rows, nout), device=dev, generator=g)
+    d_gather = torch.randn((nodes, 64), device=dev, generator=g) if mode == "EDGE" else None
+    ref = _bwd_run(code, mode, "fp32", rows, nodes, params, in0, in1, s, r, d_out, d_gather)
+    got = _bwd_run(code, mode, "bf16", rows, nodes, params, in0, in1, s, r, d_out, d_gather)
+    names = ["w1", "b1", "w2", "b2", "w3", "b3", "ln_g", "ln_b"]
+    rep = {}
+    for n, a, b in zip(names, got[0], ref[0]):
+        rep[n] = float((a - b).norm() / b.norm().clamp(min=1e-20))
+    for n, a, b in (("d_in0", got[1], ref[1]), ("d_in1", got[2], ref[2])):
+        if a is not None:
+            rep[n] = float((a - b).norm() / b.norm().clamp(min=1e-20))
+    os.makedirs("gpurun_out", exist_ok=True)
+    with open(f"gpurun_out/tc_bwd_{mode}_{rows}.json", "w") as f:
+        json.dump(rep, f, indent=1)
+    bad = {k: v for k, v in rep.items() if not (v < 3e-2)}
+    assert not bad, rep
