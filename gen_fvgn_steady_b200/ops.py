@@ -49,26 +49,30 @@ _MLP_K1 = {_lib.FVGN_MLP_EDGE: 384, _lib.FVGN_MLP_NODE: 192, _lib.FVGN_MLP_ENC_N
 
 
 class PackedWeights:
-    """bf16 UMMA operand images of the MLP weights, rebuilt whenever a parameter's version counter moves."""
+    """bf16 UMMA operand images of the MLP weights.  Cached per (w1, w2, w3) tensor objects (weak references) and
+    rebuilt whenever a parameter's version counter moves (optimizer step, load_state_dict, ...)."""
     _cache = {}
 
     @classmethod
     def get(cls, mode, params):
+        import weakref
         w1, w2, w3 = params[0], params[2], params[4]
-        key = (w1.data_ptr(), w2.data_ptr(), w3.data_ptr())
-        ver = (w1._version, w2._version, w3._version)
+        key = (id(w1), id(w2), id(w3), mode)
+        ver = (w1._version, w2._version, w3._version, w1.data_ptr(), w2.data_ptr(), w3.data_ptr())
         hit = cls._cache.get(key)
-        if hit is not None and hit[0] == ver:
+        if hit is not None and hit[0] == ver and all(r() is t for r, t in zip(hit[2], (w1, w2, w3))):
             return hit[1]
         nbytes = int(_lib.load().fvgn_mlp_packed_bytes(mode))
         buf = torch.empty(max(nbytes, 16), dtype=torch.uint8, device=w1.device)
         _lib.call("fvgn_mlp_pack_weights", mode, fptr(_c(w1.detach())), fptr(_c(w2.detach())), fptr(_c(w3.detach())),
                   _lib.ptr(buf), _lib.stream_ptr(w1.device))
-        cls._cache[key] = (ver, buf)
+        if len(cls._cache) > 256:
+            cls._cache = {k: v for k, v in cls._cache.items() if all(r() is not None for r in v[2])}
+        cls._cache[key] = (ver, buf, tuple(weakref.ref(t) for t in (w1, w2, w3)))
         return buf
 
 
-def _mlp_desc(mode, precision, rows, params, in0, in1=None, idx_s=None, idx_r=None, flags=0):
+def _mlp_desc(mode, precision, rows, params, in0, in1=None, idx_s=None, idx_r=None, flags=0, packed=None):
     d = _lib.MlpDesc()
     d.mode, d.precision, d.rows, d.flags = mode, PREC[precision], rows, flags
     d.in0, d.in1 = fptr(in0), fptr(in1, True)
@@ -79,14 +83,14 @@ def _mlp_desc(mode, precision, rows, params, in0, in1=None, idx_s=None, idx_r=No
     if len(ps) == 8:
         d.ln_g, d.ln_b = fptr(ps[6]), fptr(ps[7])
     if precision == "bf16":
-        d._packed = PackedWeights.get(mode, params)
+        d._packed = packed if packed is not None else PackedWeights.get(mode, params)
         d.w_bf16 = _lib.ptr(d._packed)
     return d
 
 
 def mlp_forward(mode, precision, rows, params, in0, in1=None, idx_s=None, idx_r=None, want_out=True, want_res=False,
-                flags=0):
-    d = _mlp_desc(mode, precision, rows, params, in0, in1, idx_s, idx_r, flags)
+                flags=0, packed=None):
+    d = _mlp_desc(mode, precision, rows, params, in0, in1, idx_s, idx_r, flags, packed)
     nout = 3 if mode == _lib.FVGN_MLP_DEC else 128
     out = _empty((rows, nout), in0) if want_out else None
     res = _empty((rows, 128), in0) if want_res else None
@@ -96,9 +100,10 @@ def mlp_forward(mode, precision, rows, params, in0, in1=None, idx_s=None, idx_r=
 
 
 def mlp_backward(mode, precision, rows, params, in0, in1, idx_s, idx_r, d_out, d_gather=None, d_in0=None, d_in1=None,
-                 flags=0):
-    """Runs the fused backward; returns the list of parameter gradients (views of one flat buffer)."""
-    d = _mlp_desc(mode, precision, rows, params, in0, in1, idx_s, idx_r, flags)
+                 flags=0, packed=None):
+    """Runs the fused backward; returns the list of parameter gradients (views of one flat buffer).
+    packed: the bf16 weight image used by the matching forward (bf16 mode); repacked from `params` when None."""
+    d = _mlp_desc(mode, precision, rows, params, in0, in1, idx_s, idx_r, flags, packed)
     lib = _lib.load()
     pc = int(lib.fvgn_mlp_param_count(mode))
     npart = int(lib.fvgn_mlp_bwd_partials(mode, PREC[precision], rows))
@@ -128,6 +133,10 @@ def mlp_backward(mode, precision, rows, params, in0, in1, idx_s, idx_r, d_out, d
     return grads
 
 
+def _packed(mode, precision, params):
+    return PackedWeights.get(mode, params) if precision == "bf16" else None
+
+
 # ------------------------------------------------------------------ Encoder
 class EncoderFn(torch.autograd.Function):
     """Encoder.forward (EPD.py:116-153) with the relative edge features of importer.py:54-78 fused in."""
@@ -135,8 +144,9 @@ class EncoderFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, xn, pos, plan, precision, *params):
         nb, eb = params[:8], params[8:]
-        node, _ = mlp_forward(_lib.FVGN_MLP_ENC_NODE, precision, plan.N, nb, xn)
-        edge, _ = mlp_forward(_lib.FVGN_MLP_ENC_EDGE, precision, plan.E, eb, xn, pos, plan.edge_s, plan.edge_r)
+        ctx.pk = (_packed(_lib.FVGN_MLP_ENC_NODE, precision, nb), _packed(_lib.FVGN_MLP_ENC_EDGE, precision, eb))
+        node, _ = mlp_forward(_lib.FVGN_MLP_ENC_NODE, precision, plan.N, nb, xn, packed=ctx.pk[0])
+        edge, _ = mlp_forward(_lib.FVGN_MLP_ENC_EDGE, precision, plan.E, eb, xn, pos, plan.edge_s, plan.edge_r, packed=ctx.pk[1])
         ctx.plan, ctx.precision = plan, precision
         ctx.save_for_backward(xn, pos, *params)
         return node, edge
@@ -145,9 +155,10 @@ class EncoderFn(torch.autograd.Function):
     def backward(ctx, d_node, d_edge):
         xn, pos, *params = ctx.saved_tensors
         plan, precision = ctx.plan, ctx.precision
-        gn = mlp_backward(_lib.FVGN_MLP_ENC_NODE, precision, plan.N, params[:8], xn, None, None, None, _c(d_node))
+        gn = mlp_backward(_lib.FVGN_MLP_ENC_NODE, precision, plan.N, params[:8], xn, None, None, None, _c(d_node),
+                          packed=ctx.pk[0])
         ge = mlp_backward(_lib.FVGN_MLP_ENC_EDGE, precision, plan.E, params[8:], xn, pos, plan.edge_s, plan.edge_r,
-                          _c(d_edge))
+                          _c(d_edge), packed=ctx.pk[1])
         return (None, None, None, None, *gn, *ge)
 
 
@@ -164,14 +175,16 @@ class GnBlockFn(torch.autograd.Function):
     def forward(ctx, x, e, plan, precision, *params):
         eb, nb = params[:8], params[8:]
         x, e = _c(x), _c(e)
+        ctx.pk = (_packed(_lib.FVGN_MLP_EDGE, precision, eb), _packed(_lib.FVGN_MLP_NODE, precision, nb))
         agg = adj_reduce(x, plan, 128)
         e_new, e_out = mlp_forward(_lib.FVGN_MLP_EDGE, precision, plan.E, eb, agg, e, plan.edge_s, plan.edge_r,
-                                   want_out=True, want_res=True)
+                                   want_out=True, want_res=True, packed=ctx.pk[0])
         a1 = inc_reduce(e_new, plan, 64)
         del e_new
         a2 = adj_reduce(a1, plan, 64, _lib.FVGN_ADJ_DIV_DST_BY_DEG)
         del a1
-        _, x_out = mlp_forward(_lib.FVGN_MLP_NODE, precision, plan.N, nb, a2, x, want_out=False, want_res=True)
+        _, x_out = mlp_forward(_lib.FVGN_MLP_NODE, precision, plan.N, nb, a2, x, want_out=False, want_res=True,
+                               packed=ctx.pk[1])
         ctx.plan, ctx.precision = plan, precision
         ctx.save_for_backward(x, e, agg, a2, *params)
         return x_out, e_out
@@ -185,13 +198,14 @@ class GnBlockFn(torch.autograd.Function):
         d_e_out = _c(d_e_out) if d_e_out is not None else torch.zeros_like(e)
         d_a2 = _empty((plan.N, 64), x)
         d_x = _empty((plan.N, 128), x)
-        g_nb = mlp_backward(_lib.FVGN_MLP_NODE, precision, plan.N, nb, a2, x, None, None, d_x_out, None, d_a2, d_x)
+        g_nb = mlp_backward(_lib.FVGN_MLP_NODE, precision, plan.N, nb, a2, x, None, None, d_x_out, None, d_a2, d_x,
+                            packed=ctx.pk[1])
         d_a1 = adj_reduce(d_a2, plan, 64, _lib.FVGN_ADJ_DIV_SRC_BY_DEG)
         del d_a2
         d_sr = _empty((plan.E, 256), x)
         d_e = _empty((plan.E, 128), x)
         g_eb = mlp_backward(_lib.FVGN_MLP_EDGE, precision, plan.E, eb, agg, e, plan.edge_s, plan.edge_r, d_e_out, d_a1,
-                            d_sr, d_e)
+                            d_sr, d_e, packed=ctx.pk[0])
         d_agg = inc_reduce(d_sr, plan, 128)
         del d_sr
         adj_reduce(d_agg, plan, 128, _lib.FVGN_ADJ_ACCUMULATE, out=d_x)
@@ -205,8 +219,9 @@ class EdgeBlockFn(torch.autograd.Function):
     def forward(ctx, x, e, plan, precision, *params):
         x, e = _c(x), _c(e)
         agg = adj_reduce(x, plan, 128)
+        ctx.pk = _packed(_lib.FVGN_MLP_EDGE, precision, params)
         e_new, _ = mlp_forward(_lib.FVGN_MLP_EDGE, precision, plan.E, params, agg, e, plan.edge_s, plan.edge_r,
-                               flags=_lib.FVGN_MLP_NO_RESIDUAL)
+                               flags=_lib.FVGN_MLP_NO_RESIDUAL, packed=ctx.pk)
         ctx.plan, ctx.precision = plan, precision
         ctx.save_for_backward(agg, e, *params)
         return e_new
@@ -218,7 +233,7 @@ class EdgeBlockFn(torch.autograd.Function):
         d_sr = _empty((plan.E, 256), e)
         d_e = _empty((plan.E, 128), e)
         g = mlp_backward(_lib.FVGN_MLP_EDGE, precision, plan.E, params, agg, e, plan.edge_s, plan.edge_r, _c(d_e_new), None,
-                         d_sr, d_e, flags=_lib.FVGN_MLP_NO_RESIDUAL)
+                         d_sr, d_e, flags=_lib.FVGN_MLP_NO_RESIDUAL, packed=ctx.pk)
         d_agg = inc_reduce(d_sr, plan, 128)
         d_x = adj_reduce(d_agg, plan, 128)
         return (d_x, d_e, None, None, *g)
@@ -232,7 +247,9 @@ class NodeBlockFn(torch.autograd.Function):
         x, e = _c(x), _c(e)
         a1 = inc_reduce(e, plan, 64)
         a2 = adj_reduce(a1, plan, 64, _lib.FVGN_ADJ_DIV_DST_BY_DEG)
-        x_new, _ = mlp_forward(_lib.FVGN_MLP_NODE, precision, plan.N, params, a2, x, flags=_lib.FVGN_MLP_NO_RESIDUAL)
+        ctx.pk = _packed(_lib.FVGN_MLP_NODE, precision, params)
+        x_new, _ = mlp_forward(_lib.FVGN_MLP_NODE, precision, plan.N, params, a2, x, flags=_lib.FVGN_MLP_NO_RESIDUAL,
+                               packed=ctx.pk)
         ctx.plan, ctx.precision = plan, precision
         ctx.save_for_backward(a2, x, *params)
         return x_new
@@ -244,7 +261,7 @@ class NodeBlockFn(torch.autograd.Function):
         d_a2 = _empty((plan.N, 64), x)
         d_x = _empty((plan.N, 128), x)
         g = mlp_backward(_lib.FVGN_MLP_NODE, precision, plan.N, params, a2, x, None, None, _c(d_x_new), None, d_a2, d_x,
-                         flags=_lib.FVGN_MLP_NO_RESIDUAL)
+                         flags=_lib.FVGN_MLP_NO_RESIDUAL, packed=ctx.pk)
         d_a1 = adj_reduce(d_a2, plan, 64, _lib.FVGN_ADJ_DIV_SRC_BY_DEG)
         # transpose of the incidence sum: d_e[f] = [d_a1[s_f] | d_a1[r_f]]
         d_e = torch.cat([d_a1[plan.edge_s.long()], d_a1[plan.edge_r.long()]], 1)
@@ -258,7 +275,8 @@ class DecoderFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, x, precision, *params):
         x = _c(x)
-        out, _ = mlp_forward(_lib.FVGN_MLP_DEC, precision, x.shape[0], params, x)
+        ctx.pk = _packed(_lib.FVGN_MLP_DEC, precision, params)
+        out, _ = mlp_forward(_lib.FVGN_MLP_DEC, precision, x.shape[0], params, x, packed=ctx.pk)
         ctx.precision = precision
         ctx.save_for_backward(x, *params)
         return out
@@ -267,7 +285,8 @@ class DecoderFn(torch.autograd.Function):
     def backward(ctx, d_out):
         x, *params = ctx.saved_tensors
         d_x = _empty(tuple(x.shape), x)
-        g = mlp_backward(_lib.FVGN_MLP_DEC, ctx.precision, x.shape[0], params, x, None, None, None, _c(d_out), None, d_x)
+        g = mlp_backward(_lib.FVGN_MLP_DEC, ctx.precision, x.shape[0], params, x, None, None, None, _c(d_out), None, d_x,
+                         packed=ctx.pk)
         return (d_x, None, *g)
 
 

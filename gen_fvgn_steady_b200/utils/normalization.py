@@ -35,7 +35,9 @@ class Normalizer(nn.Module):
 
     def std(self):
         safe = torch.clamp(self.acc_count, min=1.0)
-        std = torch.sqrt(self.acc_sum_squared / safe - self.mean() ** 2)
+        # the reference takes sqrt(E[x^2] - mean^2) directly (normalization.py:80-83); for a constant feature fp32
+        # rounding can push that a few ulp below zero and the reference then propagates NaN -- clamp at 0 instead.
+        std = torch.sqrt(torch.clamp(self.acc_sum_squared / safe - self.mean() ** 2, min=0.0))
         return torch.where(std < self.epsilon, torch.ones_like(std), std)
 
     def _load_from_state_dict(self, *args, **kwargs):
