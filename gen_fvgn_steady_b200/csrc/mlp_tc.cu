@@ -18,7 +18,7 @@ using namespace tc;
 
 namespace {
 
-constexpr int NTHREADS = 288;
+constexpr int NTHREADS = 416;  // 8 epilogue warps (two tile pipelines) + 4 producer warps + 1 MMA warp
 
 template <int MODE> struct TCfg;
 template <> struct TCfg<FVGN_MLP_EDGE> { static constexpr int K1 = 384, K1P = 384, NOUT = 128, NSTAGE = 3; static constexpr bool LN = true; };
@@ -27,10 +27,9 @@ template <> struct TCfg<FVGN_MLP_ENC_NODE> { static constexpr int K1 = 12, K1P =
 template <> struct TCfg<FVGN_MLP_ENC_EDGE> { static constexpr int K1 = 15, K1P = 16, NOUT = 128, NSTAGE = 4; static constexpr bool LN = true; };
 template <> struct TCfg<FVGN_MLP_DEC> { static constexpr int K1 = 128, K1P = 128, NOUT = 3, NSTAGE = 4; static constexpr bool LN = false; };
 
-
-constexpr int STG_COLS = 16;                       // columns per staged store pass
+constexpr int STG_COLS = 8;                        // columns per staged store pass
 constexpr int STG_LD = STG_COLS + 4;               // padded row (floats)
-constexpr int STG_BYTES = 4 * 32 * STG_LD * 4;     // 4 epilogue warps x 32 rows
+constexpr int STG_BYTES = 8 * 32 * STG_LD * 4;     // 8 epilogue warps x 32 rows
 
 template <int MODE> constexpr int smem_bytes() {
   return image_bytes(TCfg<MODE>::K1P) + TCfg<MODE>::NSTAGE * KB_BYTES + STG_BYTES + 5 * 512 + 256;
@@ -70,13 +69,16 @@ __global__ void pack_weights_kernel(const float* __restrict__ w1, const float* _
 }
 
 // ------------------------------------------------------------------------------------------ forward kernel
+// Two tiles are in flight per CTA (pipelines P0 / P1, one epilogue warpgroup and 192 TMEM columns each); the single MMA
+// thread issues their layers interleaved  L1(P0) L1(P1) L2(P0) L2(P1) L3(P0) L3(P1)  so that the tensor core and the
+// loads of one tile run under the epilogue of the other.
 template <int MODE>
 __global__ void __launch_bounds__(NTHREADS, 1) mlp_tc_fwd_kernel(const fvgn_mlp_desc d) {
   using C = TCfg<MODE>;
   constexpr int NKB1 = nkb1(C::K1P);
   constexpr int LASTK = (C::K1P - 64 * (NKB1 - 1)) / 16;  // MMAs (K=16) in the last K-block of layer 1
   constexpr int NSTAGE = C::NSTAGE;
-  constexpr uint32_t ACC0 = 0, ACC1 = 128, ACOL = 256;   // TMEM columns: two fp32 accumulators + bf16 A operand (64 cols)
+  // TMEM columns per pipeline p: accumulator [192 p, +128), bf16 A operand [192 p + 128, +64)
   FVGN_DYN_SMEM(smem);
   uint8_t* w_img = smem;
   uint8_t* ring = w_img + image_bytes(C::K1P);
@@ -87,11 +89,10 @@ __global__ void __launch_bounds__(NTHREADS, 1) mlp_tc_fwd_kernel(const fvgn_mlp_
   float* sg = sb3 + 128;
   float* sbeta = sg + 128;
   uint64_t* bars = reinterpret_cast<uint64_t*>(sbeta + 128);
-  // barrier map: [0] weights, [1..NSTAGE] ring full, [1+NSTAGE..2NSTAGE] ring empty, then l1, l2, l3, a_ready
   const uint32_t bar0 = smem_u32(bars);
   auto BAR = [&](int i) { return bar0 + 8u * (uint32_t)i; };
-  constexpr int B_W = 0, B_FULL = 1, B_EMPTY = 1 + NSTAGE, B_L1 = 1 + 2 * NSTAGE, B_L2 = B_L1 + 1, B_L3 = B_L1 + 2,
-                B_A = B_L1 + 3;
+  // barrier map: weights | ring full | ring empty | per pipeline: layer done, A operand ready, accumulator free
+  constexpr int B_W = 0, B_FULL = 1, B_EMPTY = 1 + NSTAGE, B_L = 1 + 2 * NSTAGE, B_A = B_L + 2, B_FREE = B_L + 4;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 24);
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -103,10 +104,11 @@ __global__ void __launch_bounds__(NTHREADS, 1) mlp_tc_fwd_kernel(const fvgn_mlp_
       mbar_init(BAR(B_FULL + s), 4);   // one elected lane per producer warp
       mbar_init(BAR(B_EMPTY + s), 1);  // tcgen05.commit
     }
-    mbar_init(BAR(B_L1), 1);
-    mbar_init(BAR(B_L2), 1);
-    mbar_init(BAR(B_L3), 1);
-    mbar_init(BAR(B_A), 128);
+    for (int p = 0; p < 2; ++p) {
+      mbar_init(BAR(B_L + p), 1);
+      mbar_init(BAR(B_A + p), 128);
+      mbar_init(BAR(B_FREE + p), 128);
+    }
     fence_barrier_init();
   }
   for (int i = tid; i < 128; i += NTHREADS) {
@@ -116,13 +118,13 @@ __global__ void __launch_bounds__(NTHREADS, 1) mlp_tc_fwd_kernel(const fvgn_mlp_
     sg[i] = C::LN ? d.ln_g[i] : 1.f;
     sbeta[i] = C::LN ? d.ln_b[i] : 0.f;
   }
-  if (warp == 8) tmem_alloc(smem_u32(tmem_slot), 512);
+  if (warp == 12) tmem_alloc(smem_u32(tmem_slot), 512);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = *tmem_slot;
 
-  if (warp == 8) {
+  if (warp == 12) {
     // =============================================================== MMA issuer (+ weight loader)
     if (lane == 0) {
       constexpr uint32_t img_bytes = (uint32_t)image_bytes(C::K1P);
@@ -131,40 +133,47 @@ __global__ void __launch_bounds__(NTHREADS, 1) mlp_tc_fwd_kernel(const fvgn_mlp_
         bulk_g2s(smem_u32(w_img + off), reinterpret_cast<const uint8_t*>(d.w_bf16) + off, KB_BYTES, BAR(B_W));
       mbar_wait(BAR(B_W), 0);
       const uint32_t w1s = smem_u32(w_img), w2s = w1s + NKB1 * KB_BYTES, w3s = w2s + 2 * KB_BYTES;
-      uint32_t it = 0, pa = 0;
-      for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
-        // ---- layer 1: A from the smem ring
-        for (int kb = 0; kb < NKB1; ++kb, ++it) {
-          const int s = it % NSTAGE;
-          mbar_wait(BAR(B_FULL + s), (it / NSTAGE) & 1);
+      uint32_t it = 0;
+      uint32_t pa[2] = {0, 0}, pf[2] = {0, 0};  // parities: A-ready waits, accumulator-free waits
+      for (int64_t tile0 = blockIdx.x; tile0 < ntiles; tile0 += 2 * (int64_t)gridDim.x) {
+        const int np = (tile0 + gridDim.x < ntiles) ? 2 : 1;
+        // ---- layer 1 of both tiles: A from the smem ring
+        for (int p = 0; p < np; ++p) {
+          const uint32_t acc = tmem + 192 * p;
+          mbar_wait(BAR(B_FREE + p), pf[p] ^ 1);  // epilogue of this pipeline's previous tile has drained the accumulator
+          pf[p] ^= 1;
           tc_fence_after();
-          const uint64_t ad = make_desc_k128(smem_u32(ring + s * KB_BYTES));
-          const uint64_t bd = make_desc_k128(w1s + kb * KB_BYTES);
-          const int nk = (kb == NKB1 - 1) ? LASTK : 4;
-          for (int k = 0; k < nk; ++k) umma_ss(tmem + ACC0, ad + 2 * k, bd + 2 * k, IDESC, (kb | k) != 0);
-          umma_commit(BAR(B_EMPTY + s));
+          for (int kb = 0; kb < NKB1; ++kb, ++it) {
+            const int s = it % NSTAGE;
+            mbar_wait(BAR(B_FULL + s), (it / NSTAGE) & 1);
+            tc_fence_after();
+            const uint64_t ad = make_desc_k128(smem_u32(ring + s * KB_BYTES));
+            const uint64_t bd = make_desc_k128(w1s + kb * KB_BYTES);
+            const int nk = (kb == NKB1 - 1) ? LASTK : 4;
+            for (int k = 0; k < nk; ++k) umma_ss(acc, ad + 2 * k, bd + 2 * k, IDESC, (kb | k) != 0);
+            umma_commit(BAR(B_EMPTY + s));
+          }
+          umma_commit(BAR(B_L + p));
         }
-        umma_commit(BAR(B_L1));
-        // ---- layer 2: A = gelu(layer 1) as bf16 in TMEM
-        mbar_wait(BAR(B_A), pa);
-        pa ^= 1;
-        tc_fence_after();
-        for (int k = 0; k < 8; ++k)
-          umma_ts(tmem + ACC1, tmem + ACOL + 8 * k, make_desc_k128(w2s + (k >> 2) * KB_BYTES) + 2 * (k & 3), IDESC, k != 0);
-        umma_commit(BAR(B_L2));
-        // ---- layer 3
-        mbar_wait(BAR(B_A), pa);
-        pa ^= 1;
-        tc_fence_after();
-        for (int k = 0; k < 8; ++k)
-          umma_ts(tmem + ACC1, tmem + ACOL + 8 * k, make_desc_k128(w3s + (k >> 2) * KB_BYTES) + 2 * (k & 3), IDESC, k != 0);
-        umma_commit(BAR(B_L3));
+        // ---- layers 2 and 3: A = gelu(previous layer) as bf16 in TMEM
+        for (int layer = 0; layer < 2; ++layer) {
+          const uint32_t ws = layer == 0 ? w2s : w3s;
+          for (int p = 0; p < np; ++p) {
+            const uint32_t acc = tmem + 192 * p, acol = acc + 128;
+            mbar_wait(BAR(B_A + p), pa[p]);
+            pa[p] ^= 1;
+            tc_fence_after();
+            for (int k = 0; k < 8; ++k)
+              umma_ts(acc, acol + 8 * k, make_desc_k128(ws + (k >> 2) * KB_BYTES) + 2 * (k & 3), IDESC, k != 0);
+            umma_commit(BAR(B_L + p));
+          }
+        }
       }
     }
     __syncwarp();
-  } else if (warp >= 4) {
+  } else if (warp >= 8) {
     // =============================================================== producers
-    const int pw = warp - 4;
+    const int pw = warp - 8;
     uint32_t it = 0;
     for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
       const int64_t row0 = tile * TILE_M;
@@ -178,51 +187,44 @@ __global__ void __launch_bounds__(NTHREADS, 1) mlp_tc_fwd_kernel(const fvgn_mlp_
       }
     }
   } else {
-    // =============================================================== epilogue (thread <-> row)
-    const uint32_t lane_base = (uint32_t)(warp * 32) << 16;
-    const int rloc = warp * 32 + lane;
+    // =============================================================== epilogue: pipeline p = warp / 4, thread <-> row
+    const int p = warp >> 2, q = warp & 3;
+    const uint32_t lane_base = (uint32_t)(q * 32) << 16;
+    const uint32_t acc = tmem + lane_base + 192 * p, acol = acc + 128;
+    const int rloc = q * 32 + lane;
     float* mystg = stg + warp * 32 * STG_LD;
     uint32_t ph = 0;
-    for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ph ^= 1) {
+    for (int64_t tile = blockIdx.x + (int64_t)p * gridDim.x; tile < ntiles; tile += 2 * (int64_t)gridDim.x) {
       const int64_t row0 = tile * TILE_M;
       // ---- hidden layers: +bias, GELU, bf16 -> TMEM A operand
 #pragma unroll 1
       for (int layer = 0; layer < 2; ++layer) {
-        mbar_wait(BAR(layer == 0 ? B_L1 : B_L2), ph);
+        mbar_wait(BAR(B_L + p), ph);
+        ph ^= 1;
         tc_fence_after();
-        const uint32_t acc = tmem + lane_base + (layer == 0 ? ACC0 : ACC1);
         const float* bias = layer == 0 ? sb1 : sb2;
 #pragma unroll 1
         for (int c0 = 0; c0 < 128; c0 += 16) {
-          uint32_t r[16], p[8];
+          uint32_t r[16], w[8];
           tmem_ld16(acc + c0, r);
           tmem_wait_ld();
 #pragma unroll
           for (int j = 0; j < 8; ++j)
-            p[j] = pack_bf16(gelu_fast(__uint_as_float(r[2 * j]) + bias[c0 + 2 * j]),
-                             gelu_fast(__uint_as_float(r[2 * j + 1]) + bias[c0 + 2 * j + 1]));
-          tmem_st8(tmem + lane_base + ACOL + c0 / 2, p);
+            w[j] = pack_bf16(gelu_tanh(__uint_as_float(r[2 * j]) + bias[c0 + 2 * j]),
+                             gelu_tanh(__uint_as_float(r[2 * j + 1]) + bias[c0 + 2 * j + 1]));
+          tmem_st8(acol + c0 / 2, w);
         }
         tmem_wait_st();
         tc_fence_before();
-        mbar_arrive(BAR(B_A));
+        mbar_arrive(BAR(B_A + p));
       }
       // ---- output layer
-      mbar_wait(BAR(B_L3), ph);
+      mbar_wait(BAR(B_L + p), ph);
+      ph ^= 1;
       tc_fence_after();
-      const uint32_t acc = tmem + lane_base + ACC1;
       if (C::LN) {
-        float sum = 0.f;
-#pragma unroll 1
-        for (int c0 = 0; c0 < 128; c0 += 16) {
-          uint32_t r[16];
-          tmem_ld16(acc + c0, r);
-          tmem_wait_ld();
-#pragma unroll
-          for (int j = 0; j < 16; ++j) sum += __uint_as_float(r[j]) + sb3[c0 + j];
-        }
-        const float mean = sum * (1.0f / 128.0f);
-        float sq = 0.f;
+        // LayerNorm statistics in one pass over the accumulator (sum / sum of squares in fp32)
+        float sum = 0.f, sq = 0.f;
 #pragma unroll 1
         for (int c0 = 0; c0 < 128; c0 += 16) {
           uint32_t r[16];
@@ -230,43 +232,49 @@ __global__ void __launch_bounds__(NTHREADS, 1) mlp_tc_fwd_kernel(const fvgn_mlp_
           tmem_wait_ld();
 #pragma unroll
           for (int j = 0; j < 16; ++j) {
-            const float dv = __uint_as_float(r[j]) + sb3[c0 + j] - mean;
-            sq = fmaf(dv, dv, sq);
+            const float y = __uint_as_float(r[j]) + sb3[c0 + j];
+            sum += y;
+            sq = fmaf(y, y, sq);
           }
         }
-        const float rstd = rsqrtf(sq * (1.0f / 128.0f) + 1e-5f);
+        const float mean = sum * (1.0f / 128.0f);
+        const float rstd = rsqrtf(fmaxf(sq * (1.0f / 128.0f) - mean * mean, 0.f) + 1e-5f);
         const float* resid = (MODE == FVGN_MLP_EDGE || MODE == FVGN_MLP_NODE) ? d.in1 : nullptr;
 #pragma unroll 1
-        for (int c0 = 0; c0 < 128; c0 += STG_COLS) {
+        for (int c0 = 0; c0 < 128; c0 += 16) {
           uint32_t r[16];
           tmem_ld16(acc + c0, r);
           tmem_wait_ld();
 #pragma unroll
-          for (int j = 0; j < 16; j += 4) {
-            float4 y;
-            y.x = (__uint_as_float(r[j + 0]) + sb3[c0 + j + 0] - mean) * rstd * sg[c0 + j + 0] + sbeta[c0 + j + 0];
-            y.y = (__uint_as_float(r[j + 1]) + sb3[c0 + j + 1] - mean) * rstd * sg[c0 + j + 1] + sbeta[c0 + j + 1];
-            y.z = (__uint_as_float(r[j + 2]) + sb3[c0 + j + 2] - mean) * rstd * sg[c0 + j + 2] + sbeta[c0 + j + 2];
-            y.w = (__uint_as_float(r[j + 3]) + sb3[c0 + j + 3] - mean) * rstd * sg[c0 + j + 3] + sbeta[c0 + j + 3];
-            *reinterpret_cast<float4*>(mystg + lane * STG_LD + j) = y;
-          }
-          __syncwarp();
-          // coalesced write-out: 4 lanes cover the 64 B of one row, 8 rows per instruction
+          for (int half = 0; half < 2; ++half) {
+            const int cb = c0 + half * STG_COLS;
 #pragma unroll
-          for (int pass = 0; pass < 4; ++pass) {
-            const int rr = pass * 8 + (lane >> 2), cc = (lane & 3) * 4;
-            const int64_t row = row0 + warp * 32 + rr;
-            if (row < d.rows) {
-              const float4 y = *reinterpret_cast<const float4*>(mystg + rr * STG_LD + cc);
-              const size_t o = (size_t)row * 128 + c0 + cc;
-              if (d.out) *reinterpret_cast<float4*>(d.out + o) = y;
-              if (resid && d.out_res) {
-                const float4 x = __ldg(reinterpret_cast<const float4*>(resid + o));
-                *reinterpret_cast<float4*>(d.out_res + o) = make_float4(x.x + y.x, x.y + y.y, x.z + y.z, x.w + y.w);
+            for (int j = 0; j < STG_COLS; j += 4) {
+              float4 y;
+              y.x = (__uint_as_float(r[half * 8 + j + 0]) + sb3[cb + j + 0] - mean) * rstd * sg[cb + j + 0] + sbeta[cb + j + 0];
+              y.y = (__uint_as_float(r[half * 8 + j + 1]) + sb3[cb + j + 1] - mean) * rstd * sg[cb + j + 1] + sbeta[cb + j + 1];
+              y.z = (__uint_as_float(r[half * 8 + j + 2]) + sb3[cb + j + 2] - mean) * rstd * sg[cb + j + 2] + sbeta[cb + j + 2];
+              y.w = (__uint_as_float(r[half * 8 + j + 3]) + sb3[cb + j + 3] - mean) * rstd * sg[cb + j + 3] + sbeta[cb + j + 3];
+              *reinterpret_cast<float4*>(mystg + lane * STG_LD + j) = y;
+            }
+            __syncwarp();
+            // coalesced write-out: 2 lanes cover the 32 B of one row, 16 rows per instruction
+#pragma unroll
+            for (int pass = 0; pass < 2; ++pass) {
+              const int rr = pass * 16 + (lane >> 1), cc = (lane & 1) * 4;
+              const int64_t row = row0 + q * 32 + rr;
+              if (row < d.rows) {
+                const float4 y = *reinterpret_cast<const float4*>(mystg + rr * STG_LD + cc);
+                const size_t o = (size_t)row * 128 + cb + cc;
+                if (d.out) *reinterpret_cast<float4*>(d.out + o) = y;
+                if (resid && d.out_res) {
+                  const float4 x = __ldg(reinterpret_cast<const float4*>(resid + o));
+                  *reinterpret_cast<float4*>(d.out_res + o) = make_float4(x.x + y.x, x.y + y.y, x.z + y.z, x.w + y.w);
+                }
               }
             }
+            __syncwarp();
           }
-          __syncwarp();
         }
       } else {
         // decoder: 3 outputs per row, no LayerNorm
@@ -280,10 +288,11 @@ __global__ void __launch_bounds__(NTHREADS, 1) mlp_tc_fwd_kernel(const fvgn_mlp_
         }
       }
       tc_fence_before();
+      mbar_arrive(BAR(B_FREE + p));  // accumulator drained: this pipeline's next tile may start layer 1
     }
   }
   __syncthreads();
-  if (warp == 8) {
+  if (warp == 12) {
     tc_fence_after();
     tmem_dealloc(tmem, 512);
   }

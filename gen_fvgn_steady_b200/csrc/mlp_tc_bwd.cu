@@ -258,8 +258,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) mlp_tc_bwd_a_kernel(const fvgn_ml
 #pragma unroll
           for (int j = 0; j < 8; ++j) {
             float h0, g0, h1, g1;
-            gelu_pair(__uint_as_float(r[2 * j]) + bias[c0 + 2 * j], h0, g0);
-            gelu_pair(__uint_as_float(r[2 * j + 1]) + bias[c0 + 2 * j + 1], h1, g1);
+            gelu_tanh_pair(__uint_as_float(r[2 * j]) + bias[c0 + 2 * j], h0, g0);
+            gelu_tanh_pair(__uint_as_float(r[2 * j + 1]) + bias[c0 + 2 * j + 1], h1, g1);
             hw[j] = pack_bf16(h0, h1);
             gw[j] = pack_bf16(g0, g1);
           }

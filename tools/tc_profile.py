@@ -1,0 +1,46 @@
+"""Profiling driver: one forward + one backward of the fused edge / node MLP blocks at a given row count
+(used under ncu; see profiles/)."""
+import sys
+import os
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch
+from gen_fvgn_steady_b200 import _lib, ops
+
+rows = int(sys.argv[1]) if len(sys.argv) > 1 else 2_000_000
+mode = sys.argv[2] if len(sys.argv) > 2 else "EDGE"
+prec = sys.argv[3] if len(sys.argv) > 3 else "bf16"
+dev = torch.device("cuda")
+nodes = rows // 2
+g = torch.Generator(device=dev).manual_seed(0)
+rn = lambda *s: torch.randn(*s, device=dev, generator=g)
+k1 = {"EDGE": 384, "NODE": 192}[mode]
+params = [rn(128, k1) / k1 ** 0.5, 0.1 * rn(128), rn(128, 128) / 128 ** 0.5, 0.1 * rn(128), rn(128, 128) / 128 ** 0.5, 0.1 * rn(128),
+          1 + 0.1 * rn(128), 0.1 * rn(128)]
+# mesh-like locality: senders sorted, receivers nearby
+if mode == "EDGE":
+    s = torch.arange(rows, device=dev) // 2
+    r = torch.clamp(s + torch.randint(1, 2000, (rows,), device=dev, generator=g), max=nodes - 1)
+    s, r = s.to(torch.int32), r.to(torch.int32)
+    in0, in1 = rn(nodes, 128), rn(rows, 128)
+    d_in0, d_in1 = torch.empty((rows, 256), device=dev), torch.empty((rows, 128), device=dev)
+    d_gather = rn(nodes, 64)
+    code = _lib.FVGN_MLP_EDGE
+else:
+    s = r = None
+    in0, in1 = rn(rows, 64), rn(rows, 128)
+    d_in0, d_in1 = torch.empty((rows, 64), device=dev), torch.empty((rows, 128), device=dev)
+    d_gather = None
+    code = _lib.FVGN_MLP_NODE
+d_out = rn(rows, 128)
+for _ in range(2):
+    ops.mlp_forward(code, prec, rows, params, in0, in1, s, r, want_out=True, want_res=True)
+    ops.mlp_backward(code, prec, rows, params, in0, in1, s, r, d_out, d_gather, d_in0, d_in1)
+torch.cuda.synchronize()
+ev = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
+ev[0].record()
+ops.mlp_forward(code, prec, rows, params, in0, in1, s, r, want_out=True, want_res=True)
+ev[1].record()
+ops.mlp_backward(code, prec, rows, params, in0, in1, s, r, d_out, d_gather, d_in0, d_in1)
+ev[2].record()
+torch.cuda.synchronize()
+print(f"{mode} rows={rows} {prec}: fwd {ev[0].elapsed_time(ev[1]):.3f} ms, bwd {ev[1].elapsed_time(ev[2]):.3f} ms")
