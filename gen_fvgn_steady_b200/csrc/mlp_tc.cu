@@ -18,7 +18,7 @@ using namespace tc;
 
 namespace {
 
-constexpr int NTHREADS = 416;  // 8 epilogue warps (two tile pipelines) + 4 producer warps + 1 MMA warp
+constexpr int NTHREADS = 544;  // 8 epilogue warps (two tile pipelines) + 8 producer warps (two chunk teams) + 1 MMA warp
 
 template <int MODE> struct TCfg;
 template <> struct TCfg<FVGN_MLP_EDGE> { static constexpr int K1 = 384, K1P = 384, NOUT = 128, NSTAGE = 3; static constexpr bool LN = true; };
@@ -118,13 +118,13 @@ __global__ void __launch_bounds__(NTHREADS, 1) mlp_tc_fwd_kernel(const fvgn_mlp_
     sg[i] = C::LN ? d.ln_g[i] : 1.f;
     sbeta[i] = C::LN ? d.ln_b[i] : 0.f;
   }
-  if (warp == 12) tmem_alloc(smem_u32(tmem_slot), 512);
+  if (warp == 16) tmem_alloc(smem_u32(tmem_slot), 512);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = *tmem_slot;
 
-  if (warp == 12) {
+  if (warp == 16) {
     // =============================================================== MMA issuer (+ weight loader)
     if (lane == 0) {
       constexpr uint32_t img_bytes = (uint32_t)image_bytes(C::K1P);
@@ -172,19 +172,24 @@ __global__ void __launch_bounds__(NTHREADS, 1) mlp_tc_fwd_kernel(const fvgn_mlp_
     }
     __syncwarp();
   } else if (warp >= 8) {
-    // =============================================================== producers
-    const int pw = warp - 8;
+    // =============================================================== producers: team (warp-8)/4 fills every other chunk
+    const int team = (warp - 8) >> 2, pw = (warp - 8) & 3;
     uint32_t it = 0;
+    TileIdx idx, idx_next;
+    load_tile_idx<MODE>(d, (int64_t)blockIdx.x * TILE_M, pw, lane, idx);
     for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
       const int64_t row0 = tile * TILE_M;
+      load_tile_idx<MODE>(d, (tile + gridDim.x) * TILE_M, pw, lane, idx_next);  // rows past the end load nothing
       for (int kb = 0; kb < NKB1; ++kb, ++it) {
+        if ((int)(it & 1) != team) continue;
         const int s = it % NSTAGE;
         mbar_wait(BAR(B_EMPTY + s), ((it / NSTAGE) & 1) ^ 1);
-        produce_chunk<MODE>(d, row0, kb, ring + s * KB_BYTES, pw, lane);
+        produce_chunk<MODE>(d, row0, kb, ring + s * KB_BYTES, pw, lane, idx);
         fence_proxy_async();
         __syncwarp();
         if (lane == 0) mbar_arrive(BAR(B_FULL + s));
       }
+      idx = idx_next;
     }
   } else {
     // =============================================================== epilogue: pipeline p = warp / 4, thread <-> row
@@ -292,7 +297,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) mlp_tc_fwd_kernel(const fvgn_mlp_
     }
   }
   __syncthreads();
-  if (warp == 12) {
+  if (warp == 16) {
     tc_fence_after();
     tmem_dealloc(tmem, 512);
   }

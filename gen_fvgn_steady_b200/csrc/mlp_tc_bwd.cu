@@ -199,8 +199,10 @@ __global__ void __launch_bounds__(NTHREADS, 1) mlp_tc_bwd_a_kernel(const fvgn_ml
     // ============================================================ producers: X chunk (gather + bf16) and W1 K-block (bulk copy)
     const int pw = warp - 4;
     uint32_t it = 0;
+    TileIdx idx;
     for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
       const int64_t row0 = tile * TILE_M;
+      load_tile_idx<MODE>(d, row0, pw, lane, idx);
       for (int kb = 0; kb < NKB1; ++kb, ++it) {
         const int s = it % NSTAGE;
         uint8_t* stage = ring + s * 2 * KB_BYTES;
@@ -209,7 +211,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) mlp_tc_bwd_a_kernel(const fvgn_ml
           mbar_expect_tx(BAR(B_FULL + s), KB_BYTES);
           bulk_g2s(smem_u32(stage + KB_BYTES), w_img + (size_t)kb * KB_BYTES, KB_BYTES, BAR(B_FULL + s));
         }
-        produce_chunk<MODE>(d, row0, kb, stage, pw, lane);
+        produce_chunk<MODE>(d, row0, kb, stage, pw, lane, idx);
         fence_proxy_async();
         __syncwarp();
         if (lane == 0) mbar_arrive(BAR(B_FULL + s));
@@ -573,8 +575,10 @@ __global__ void __launch_bounds__(NTHREADS, 1) mlp_tc_bwd_b_kernel(const fvgn_ml
     // ============================================================ producers: dZ1 tile (bulk copy) + X chunks (gather)
     const int pw = warp - 4;
     uint32_t it = 0, tcount = 0;
+    TileIdx idx;
     for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++tcount) {
       const int64_t row0 = tile * TILE_M;
+      load_tile_idx<MODE>(d, row0, pw, lane, idx);
       if (pw == 0 && lane == 0) {
         const int zb = tcount & 1;
         mbar_wait(BAR(B_DZEMPTY + zb), ((tcount >> 1) & 1) ^ 1);
@@ -584,7 +588,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) mlp_tc_bwd_b_kernel(const fvgn_ml
       for (int kb = 0; kb < NKB1; ++kb, ++it) {
         const int s = it % NSTAGE;
         mbar_wait(BAR(B_XEMPTY + s), ((it / NSTAGE) & 1) ^ 1);
-        produce_chunk<MODE>(d, row0, kb, ring + s * KB_BYTES, pw, lane);
+        produce_chunk<MODE>(d, row0, kb, ring + s * KB_BYTES, pw, lane, idx);
         fence_proxy_async();
         __syncwarp();
         if (lane == 0) mbar_arrive(BAR(B_XFULL + s));

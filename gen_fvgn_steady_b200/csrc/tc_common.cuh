@@ -174,8 +174,30 @@ __device__ __forceinline__ const float* chunk_src(const fvgn_mlp_desc& d, int64_
   }
 }
 
+// endpoint indices of the 8 tile rows a producer lane handles (rows i*16 + pw*4 + lane/8), fetched once per tile so
+// that the gathers of every chunk do not wait on a dependent index load
+struct TileIdx {
+  int s[8], r[8];
+};
 template <int MODE>
-__device__ __forceinline__ void produce_chunk(const fvgn_mlp_desc& d, int64_t row0, int kb, uint8_t* stage, int pw, int lane) {
+__device__ __forceinline__ void load_tile_idx(const fvgn_mlp_desc& d, int64_t row0, int pw, int lane, TileIdx& idx) {
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    idx.s[i] = 0;
+    idx.r[i] = 0;
+    if (MODE == FVGN_MLP_EDGE) {
+      const int64_t row = row0 + i * 16 + pw * 4 + (lane >> 3);
+      if (row < d.rows) {
+        idx.s[i] = __ldg(d.idx_s + row);
+        idx.r[i] = __ldg(d.idx_r + row);
+      }
+    }
+  }
+}
+
+template <int MODE>
+__device__ __forceinline__ void produce_chunk(const fvgn_mlp_desc& d, int64_t row0, int kb, uint8_t* stage, int pw, int lane,
+                                              const TileIdx& idx) {
   if (MODE == FVGN_MLP_ENC_NODE || MODE == FVGN_MLP_ENC_EDGE) {
     // one thread per row: 16 bf16 (K padded to 16) = chunks 0 and 1 of the row
     const int rloc = pw * 32 + lane;
@@ -221,11 +243,7 @@ __device__ __forceinline__ void produce_chunk(const fvgn_mlp_desc& d, int64_t ro
   for (int i = 0; i < 8; ++i) {
     const int rloc = i * 16 + pw * 4 + (lane >> 3);
     const int64_t row = row0 + rloc;
-    int s = 0, r = 0;
-    if (MODE == FVGN_MLP_EDGE && kb < 4 && row < d.rows) {
-      if (kb < 2) s = d.idx_s[row]; else r = d.idx_r[row];
-    }
-    src[i] = chunk_src<MODE>(d, row, kb, s, r);
+    src[i] = chunk_src<MODE>(d, row, kb, idx.s[i], idx.r[i]);
   }
 #pragma unroll
   for (int i = 0; i < 8; ++i) {
@@ -245,7 +263,6 @@ __device__ __forceinline__ void produce_chunk(const fvgn_mlp_desc& d, int64_t ro
                    pack_bf16(hi[i].z, hi[i].w));
   }
 }
-
 
 // ------------------------------------------------------------------------------------------ extra helpers (backward)
 __device__ __forceinline__ void tmem_ld8(uint32_t taddr, uint32_t (&r)[8]) {
