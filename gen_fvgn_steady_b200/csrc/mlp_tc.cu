@@ -69,16 +69,18 @@ __global__ void pack_weights_kernel(const float* __restrict__ w1, const float* _
 }
 
 // ------------------------------------------------------------------------------------------ forward kernel
-// Two tiles are in flight per CTA (pipelines P0 / P1, one epilogue warpgroup and 192 TMEM columns each); the single MMA
-// thread issues their layers interleaved  L1(P0) L1(P1) L2(P0) L2(P1) L3(P0) L3(P1)  so that the tensor core and the
-// loads of one tile run under the epilogue of the other.
+// Two tiles are in flight per CTA (pipelines P0 / P1: one epilogue warpgroup and two 128-column TMEM accumulators each).
+// The bf16 A operand of layers 2/3 is written IN PLACE over the lower 64 columns of the accumulator it was computed
+// from (column pair (2j,2j+1) -> column j, always behind the read front), so per tile  L1 -> T1, L2: T1[0:64] -> T2,
+// L3: T2[0:64] -> T1, and the NEXT tile of the pipeline runs its layer 1 into T2 while the epilogue still drains T1.
+// MMA issue order per tile pair:  L2(P0) L2(P1) L3(P0) L1'(P0) L3(P1) L1'(P1)   (L1' = layer 1 of the following pair),
+// so loads, tensor work and the three epilogues of different tiles overlap.
 template <int MODE>
 __global__ void __launch_bounds__(NTHREADS, 1) mlp_tc_fwd_kernel(const fvgn_mlp_desc d) {
   using C = TCfg<MODE>;
   constexpr int NKB1 = nkb1(C::K1P);
   constexpr int LASTK = (C::K1P - 64 * (NKB1 - 1)) / 16;  // MMAs (K=16) in the last K-block of layer 1
   constexpr int NSTAGE = C::NSTAGE;
-  // TMEM columns per pipeline p: accumulator [192 p, +128), bf16 A operand [192 p + 128, +64)
   FVGN_DYN_SMEM(smem);
   uint8_t* w_img = smem;
   uint8_t* ring = w_img + image_bytes(C::K1P);
@@ -91,23 +93,25 @@ __global__ void __launch_bounds__(NTHREADS, 1) mlp_tc_fwd_kernel(const fvgn_mlp_
   uint64_t* bars = reinterpret_cast<uint64_t*>(sbeta + 128);
   const uint32_t bar0 = smem_u32(bars);
   auto BAR = [&](int i) { return bar0 + 8u * (uint32_t)i; };
-  // barrier map: weights | ring full | ring empty | per pipeline: layer done, A operand ready, accumulator free
-  constexpr int B_W = 0, B_FULL = 1, B_EMPTY = 1 + NSTAGE, B_L = 1 + 2 * NSTAGE, B_A = B_L + 2, B_FREE = B_L + 4;
+  // barrier map: weights | ring full | ring empty | per pipeline: layer-1 done, layer-2/3 done, A operand ready
+  constexpr int B_W = 0, B_FULL = 1, B_EMPTY = 1 + NSTAGE, B_L1 = 1 + 2 * NSTAGE, B_L23 = B_L1 + 2, B_A = B_L1 + 4;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 24);
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int64_t ntiles = (d.rows + TILE_M - 1) / TILE_M;
+  // tiles of this CTA: blockIdx.x + i * gridDim.x, i = 0 .. ntl-1; tile i belongs to pipeline i & 1
+  const int64_t ntl = (ntiles - blockIdx.x + gridDim.x - 1) / gridDim.x;
 
   if (tid == 0) {
     mbar_init(BAR(B_W), 1);
     for (int s = 0; s < NSTAGE; ++s) {
-      mbar_init(BAR(B_FULL + s), 4);   // one elected lane per producer warp
+      mbar_init(BAR(B_FULL + s), 4);   // one elected lane per producer warp of the team that fills the stage
       mbar_init(BAR(B_EMPTY + s), 1);  // tcgen05.commit
     }
     for (int p = 0; p < 2; ++p) {
-      mbar_init(BAR(B_L + p), 1);
+      mbar_init(BAR(B_L1 + p), 1);
+      mbar_init(BAR(B_L23 + p), 1);
       mbar_init(BAR(B_A + p), 128);
-      mbar_init(BAR(B_FREE + p), 128);
     }
     fence_barrier_init();
   }
@@ -134,38 +138,46 @@ __global__ void __launch_bounds__(NTHREADS, 1) mlp_tc_fwd_kernel(const fvgn_mlp_
       mbar_wait(BAR(B_W), 0);
       const uint32_t w1s = smem_u32(w_img), w2s = w1s + NKB1 * KB_BYTES, w3s = w2s + 2 * KB_BYTES;
       uint32_t it = 0;
-      uint32_t pa[2] = {0, 0}, pf[2] = {0, 0};  // parities: A-ready waits, accumulator-free waits
-      for (int64_t tile0 = blockIdx.x; tile0 < ntiles; tile0 += 2 * (int64_t)gridDim.x) {
-        const int np = (tile0 + gridDim.x < ntiles) ? 2 : 1;
-        // ---- layer 1 of both tiles: A from the smem ring
-        for (int p = 0; p < np; ++p) {
-          const uint32_t acc = tmem + 192 * p;
-          mbar_wait(BAR(B_FREE + p), pf[p] ^ 1);  // epilogue of this pipeline's previous tile has drained the accumulator
-          pf[p] ^= 1;
+      uint32_t pa[2] = {0, 0}, pl[2] = {0, 0};
+      // layer 1 of tile i into accumulator `acc`: consumes NKB1 ring chunks in production order
+      auto layer1 = [&](uint32_t acc, int p) {
+        for (int kb = 0; kb < NKB1; ++kb, ++it) {
+          const int s = it % NSTAGE;
+          mbar_wait(BAR(B_FULL + s), (it / NSTAGE) & 1);
           tc_fence_after();
-          for (int kb = 0; kb < NKB1; ++kb, ++it) {
-            const int s = it % NSTAGE;
-            mbar_wait(BAR(B_FULL + s), (it / NSTAGE) & 1);
-            tc_fence_after();
-            const uint64_t ad = make_desc_k128(smem_u32(ring + s * KB_BYTES));
-            const uint64_t bd = make_desc_k128(w1s + kb * KB_BYTES);
-            const int nk = (kb == NKB1 - 1) ? LASTK : 4;
-            for (int k = 0; k < nk; ++k) umma_ss(acc, ad + 2 * k, bd + 2 * k, IDESC, (kb | k) != 0);
-            umma_commit(BAR(B_EMPTY + s));
-          }
-          umma_commit(BAR(B_L + p));
+          const uint64_t ad = make_desc_k128(smem_u32(ring + s * KB_BYTES));
+          const uint64_t bd = make_desc_k128(w1s + kb * KB_BYTES);
+          const int nk = (kb == NKB1 - 1) ? LASTK : 4;
+          for (int k = 0; k < nk; ++k) umma_ss(acc, ad + 2 * k, bd + 2 * k, IDESC, (kb | k) != 0);
+          umma_commit(BAR(B_EMPTY + s));
         }
-        // ---- layers 2 and 3: A = gelu(previous layer) as bf16 in TMEM
-        for (int layer = 0; layer < 2; ++layer) {
-          const uint32_t ws = layer == 0 ? w2s : w3s;
-          for (int p = 0; p < np; ++p) {
-            const uint32_t acc = tmem + 192 * p, acol = acc + 128;
-            mbar_wait(BAR(B_A + p), pa[p]);
-            pa[p] ^= 1;
+        umma_commit(BAR(B_L1 + p));
+      };
+      // layers 2/3: A = bf16 image in the lower 64 columns of `src`, D = `dst`
+      auto layer23 = [&](uint32_t dst, uint32_t src, uint32_t ws, int p) {
+        mbar_wait(BAR(B_A + p), pa[p]);
+        pa[p] ^= 1;
+        tc_fence_after();
+        for (int k = 0; k < 8; ++k)
+          umma_ts(dst, src + 8 * k, make_desc_k128(ws + (k >> 2) * KB_BYTES) + 2 * (k & 3), IDESC, k != 0);
+        umma_commit(BAR(B_L23 + p));
+        pl[p] ^= 1;
+      };
+      // accumulators of tile i: T1 = first target (layer 1, layer 3), T2 = layer 2 target; they swap every tile
+      auto T1 = [&](int64_t i) { return tmem + 256 * (uint32_t)(i & 1) + 128 * (uint32_t)((i >> 1) & 1); };
+      auto T2 = [&](int64_t i) { return tmem + 256 * (uint32_t)(i & 1) + 128 * (uint32_t)(((i >> 1) & 1) ^ 1); };
+      for (int64_t i = 0; i < 2 && i < ntl; ++i) layer1(T1(i), (int)(i & 1));
+      for (int64_t i0 = 0; i0 < ntl; i0 += 2) {
+        const int np = (i0 + 1 < ntl) ? 2 : 1;
+        for (int p = 0; p < np; ++p) layer23(T2(i0 + p), T1(i0 + p), w2s, p);
+        for (int p = 0; p < np; ++p) {
+          layer23(T1(i0 + p), T2(i0 + p), w3s, p);
+          if (i0 + p + 2 < ntl) {
+            // the next tile's layer 1 targets T2 of this tile, whose lower half is the A operand of the layer 3 just
+            // issued: wait until that MMA group has retired before overwriting it
+            mbar_wait(BAR(B_L23 + p), pl[p] ^ 1);
             tc_fence_after();
-            for (int k = 0; k < 8; ++k)
-              umma_ts(acc, acol + 8 * k, make_desc_k128(ws + (k >> 2) * KB_BYTES) + 2 * (k & 3), IDESC, k != 0);
-            umma_commit(BAR(B_L + p));
+            layer1(T1(i0 + p + 2), p);
           }
         }
       }
@@ -195,18 +207,25 @@ __global__ void __launch_bounds__(NTHREADS, 1) mlp_tc_fwd_kernel(const fvgn_mlp_
     // =============================================================== epilogue: pipeline p = warp / 4, thread <-> row
     const int p = warp >> 2, q = warp & 3;
     const uint32_t lane_base = (uint32_t)(q * 32) << 16;
-    const uint32_t acc = tmem + lane_base + 192 * p, acol = acc + 128;
     const int rloc = q * 32 + lane;
     float* mystg = stg + warp * 32 * STG_LD;
-    uint32_t ph = 0;
-    for (int64_t tile = blockIdx.x + (int64_t)p * gridDim.x; tile < ntiles; tile += 2 * (int64_t)gridDim.x) {
-      const int64_t row0 = tile * TILE_M;
-      // ---- hidden layers: +bias, GELU, bf16 -> TMEM A operand
+    uint32_t ph1 = 0, ph23 = 0;
+    for (int64_t i = p; i < ntl; i += 2) {
+      const int64_t row0 = (blockIdx.x + i * gridDim.x) * TILE_M;
+      const uint32_t t1 = tmem + lane_base + 256 * (uint32_t)p + 128 * (uint32_t)((i >> 1) & 1);
+      const uint32_t t2 = tmem + lane_base + 256 * (uint32_t)p + 128 * (uint32_t)(((i >> 1) & 1) ^ 1);
+      // ---- hidden layers: +bias, GELU, bf16 written in place over the accumulator's lower 64 columns
 #pragma unroll 1
       for (int layer = 0; layer < 2; ++layer) {
-        mbar_wait(BAR(B_L + p), ph);
-        ph ^= 1;
+        if (layer == 0) {
+          mbar_wait(BAR(B_L1 + p), ph1);
+          ph1 ^= 1;
+        } else {
+          mbar_wait(BAR(B_L23 + p), ph23);
+          ph23 ^= 1;
+        }
         tc_fence_after();
+        const uint32_t acc = layer == 0 ? t1 : t2;
         const float* bias = layer == 0 ? sb1 : sb2;
 #pragma unroll 1
         for (int c0 = 0; c0 < 128; c0 += 16) {
@@ -217,16 +236,17 @@ __global__ void __launch_bounds__(NTHREADS, 1) mlp_tc_fwd_kernel(const fvgn_mlp_
           for (int j = 0; j < 8; ++j)
             w[j] = pack_bf16(gelu_tanh(__uint_as_float(r[2 * j]) + bias[c0 + 2 * j]),
                              gelu_tanh(__uint_as_float(r[2 * j + 1]) + bias[c0 + 2 * j + 1]));
-          tmem_st8(acol + c0 / 2, w);
+          tmem_st8(acc + c0 / 2, w);
         }
         tmem_wait_st();
         tc_fence_before();
         mbar_arrive(BAR(B_A + p));
       }
-      // ---- output layer
-      mbar_wait(BAR(B_L + p), ph);
-      ph ^= 1;
+      // ---- output layer (accumulated into T1)
+      mbar_wait(BAR(B_L23 + p), ph23);
+      ph23 ^= 1;
       tc_fence_after();
+      const uint32_t acc = t1;
       if (C::LN) {
         // LayerNorm statistics in one pass over the accumulator (sum / sum of squares in fp32)
         float sum = 0.f, sq = 0.f;
@@ -245,10 +265,22 @@ __global__ void __launch_bounds__(NTHREADS, 1) mlp_tc_fwd_kernel(const fvgn_mlp_
         const float mean = sum * (1.0f / 128.0f);
         const float rstd = rsqrtf(fmaxf(sq * (1.0f / 128.0f) - mean * mean, 0.f) + 1e-5f);
         const float* resid = (MODE == FVGN_MLP_EDGE || MODE == FVGN_MLP_NODE) ? d.in1 : nullptr;
+        const bool do_res = resid && d.out_res;
 #pragma unroll 1
         for (int c0 = 0; c0 < 128; c0 += 16) {
           uint32_t r[16];
           tmem_ld16(acc + c0, r);
+          // residual rows for this 16-column group: issue the loads before they are needed
+          float4 xr[2][2];
+#pragma unroll
+          for (int half = 0; half < 2; ++half)
+#pragma unroll
+            for (int pass = 0; pass < 2; ++pass) {
+              const int64_t row = row0 + q * 32 + pass * 16 + (lane >> 1);
+              xr[half][pass] = make_float4(0.f, 0.f, 0.f, 0.f);
+              if (do_res && row < d.rows)
+                xr[half][pass] = __ldg(reinterpret_cast<const float4*>(resid + (size_t)row * 128 + c0 + half * STG_COLS + (lane & 1) * 4));
+            }
           tmem_wait_ld();
 #pragma unroll
           for (int half = 0; half < 2; ++half) {
@@ -272,8 +304,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) mlp_tc_fwd_kernel(const fvgn_mlp_
                 const float4 y = *reinterpret_cast<const float4*>(mystg + rr * STG_LD + cc);
                 const size_t o = (size_t)row * 128 + cb + cc;
                 if (d.out) *reinterpret_cast<float4*>(d.out + o) = y;
-                if (resid && d.out_res) {
-                  const float4 x = __ldg(reinterpret_cast<const float4*>(resid + o));
+                if (do_res) {
+                  const float4 x = xr[half][pass];
                   *reinterpret_cast<float4*>(d.out_res + o) = make_float4(x.x + y.x, x.y + y.y, x.z + y.z, x.w + y.w);
                 }
               }
@@ -293,7 +325,6 @@ __global__ void __launch_bounds__(NTHREADS, 1) mlp_tc_fwd_kernel(const fvgn_mlp_
         }
       }
       tc_fence_before();
-      mbar_arrive(BAR(B_FREE + p));  // accumulator drained: this pipeline's next tile may start layer 1
     }
   }
   __syncthreads();
