@@ -227,17 +227,14 @@ __global__ void __launch_bounds__(NTHREADS, 1) mlp_tc_fwd_kernel(const fvgn_mlp_
         tc_fence_after();
         const uint32_t acc = layer == 0 ? t1 : t2;
         const float* bias = layer == 0 ? sb1 : sb2;
-#pragma unroll 1
-        for (int c0 = 0; c0 < 128; c0 += 16) {
-          uint32_t r[16], w[8];
-          tmem_ld16(acc + c0, r);
-          tmem_wait_ld();
+        for_each_chunk16(acc, [&](int c0, uint32_t (&r)[16]) {
+          uint32_t w[8];
 #pragma unroll
           for (int j = 0; j < 8; ++j)
             w[j] = pack_bf16(gelu_tanh(__uint_as_float(r[2 * j]) + bias[c0 + 2 * j]),
                              gelu_tanh(__uint_as_float(r[2 * j + 1]) + bias[c0 + 2 * j + 1]));
-          tmem_st8(acc + c0 / 2, w);
-        }
+          tmem_st8(acc + c0 / 2, w);  // in place: always behind the columns still to be read (and the one in flight)
+        });
         tmem_wait_st();
         tc_fence_before();
         mbar_arrive(BAR(B_A + p));
@@ -250,18 +247,14 @@ __global__ void __launch_bounds__(NTHREADS, 1) mlp_tc_fwd_kernel(const fvgn_mlp_
       if (C::LN) {
         // LayerNorm statistics in one pass over the accumulator (sum / sum of squares in fp32)
         float sum = 0.f, sq = 0.f;
-#pragma unroll 1
-        for (int c0 = 0; c0 < 128; c0 += 16) {
-          uint32_t r[16];
-          tmem_ld16(acc + c0, r);
-          tmem_wait_ld();
+        for_each_chunk16(acc, [&](int c0, uint32_t (&r)[16]) {
 #pragma unroll
           for (int j = 0; j < 16; ++j) {
             const float y = __uint_as_float(r[j]) + sb3[c0 + j];
             sum += y;
             sq = fmaf(y, y, sq);
           }
-        }
+        });
         const float mean = sum * (1.0f / 128.0f);
         const float rstd = rsqrtf(fmaxf(sq * (1.0f / 128.0f) - mean * mean, 0.f) + 1e-5f);
         const float* resid = (MODE == FVGN_MLP_EDGE || MODE == FVGN_MLP_NODE) ? d.in1 : nullptr;

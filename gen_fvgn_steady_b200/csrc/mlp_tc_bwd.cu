@@ -90,8 +90,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) mlp_tc_bwd_a_kernel(const fvgn_ml
   uint64_t* bars = reinterpret_cast<uint64_t*>(sg + 128);
   const uint32_t bar0 = smem_u32(bars);
   auto BAR = [&](int i) { return bar0 + 8u * (uint32_t)i; };
-  constexpr int B_W = 0, B_FULL = 1, B_EMPTY = 3, B_MMA = 5, B_EPI = 6;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 8);
+  constexpr int B_W = 0, B_FULL = 1, B_EMPTY = 3, B_MMA = 5, B_EPI = 6, B_DO = 7, B_CFREE = 8;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 10);
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int64_t ntiles = (d.rows + TILE_M - 1) / TILE_M;
@@ -115,6 +115,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) mlp_tc_bwd_a_kernel(const fvgn_ml
     }
     mbar_init(BAR(B_MMA), 1);
     mbar_init(BAR(B_EPI), 128);
+    mbar_init(BAR(B_DO), 4);     // producers: upstream-gradient tile parked in bufC
+    mbar_init(BAR(B_CFREE), 1);  // tcgen05.commit: bufC no longer read by the previous tile's MMAs
     fence_barrier_init();
   }
   for (int i = tid; i < 128; i += NTHREADS) {
@@ -185,6 +187,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) mlp_tc_bwd_a_kernel(const fvgn_ml
         wait_epi();                       // E3: dY in bufC
         gemm_wgrad(DW3, cs, h2s, first);  // dW3 += dY^T H2
         gemm_dgrad(WACC, cs, w3s);        // dH2 = dY W3
+        umma_commit(BAR(B_CFREE));
         umma_commit(BAR(B_MMA));
         wait_epi();                       // E4: dZ2 in bufH2
         gemm_wgrad(DW2, h2s, h1s, first); // dW2 += dZ2^T H1
@@ -196,11 +199,12 @@ __global__ void __launch_bounds__(NTHREADS, 1) mlp_tc_bwd_a_kernel(const fvgn_ml
     }
     __syncwarp();
   } else if (warp >= 4) {
-    // ============================================================ producers: X chunk (gather + bf16) and W1 K-block (bulk copy)
+    // ============================================================ producers: X chunk (gather + bf16), W1 K-block (bulk copy)
+    // and the tile of upstream gradients dO = d_out (+ gathered d_a1) as bf16 into bufC
     const int pw = warp - 4;
-    uint32_t it = 0;
+    uint32_t it = 0, tcount = 0;
     TileIdx idx;
-    for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+    for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++tcount) {
       const int64_t row0 = tile * TILE_M;
       load_tile_idx<MODE>(d, row0, pw, lane, idx);
       for (int kb = 0; kb < NKB1; ++kb, ++it) {
@@ -216,6 +220,57 @@ __global__ void __launch_bounds__(NTHREADS, 1) mlp_tc_bwd_a_kernel(const fvgn_ml
         __syncwarp();
         if (lane == 0) mbar_arrive(BAR(B_FULL + s));
       }
+      mbar_wait(BAR(B_CFREE), (tcount & 1) ^ 1);  // previous tile's dW3 / dH2 MMAs have retired
+      if (C::LN) {
+        const int seg = lane & 7;
+#pragma unroll 1
+        for (int kb = 0; kb < 2; ++kb) {
+          float4 lo[8], hi[8];
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            const int64_t row = row0 + i * 16 + pw * 4 + (lane >> 3);
+            lo[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+            hi[i] = lo[i];
+            if (row < d.rows) {
+              const float* p = d.d_out + (size_t)row * 128 + kb * 64 + seg * 8;
+              lo[i] = __ldg(reinterpret_cast<const float4*>(p));
+              hi[i] = __ldg(reinterpret_cast<const float4*>(p + 4));
+              if (MODE == FVGN_MLP_EDGE && d.d_gather) {
+                const float* g = d.d_gather + (size_t)(kb == 0 ? idx.s[i] : idx.r[i]) * 64 + seg * 8;
+                const float4 a = __ldg(reinterpret_cast<const float4*>(g)), b = __ldg(reinterpret_cast<const float4*>(g + 4));
+                lo[i] = make_float4(lo[i].x + a.x, lo[i].y + a.y, lo[i].z + a.z, lo[i].w + a.w);
+                hi[i] = make_float4(hi[i].x + b.x, hi[i].y + b.y, hi[i].z + b.z, hi[i].w + b.w);
+              }
+            }
+          }
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            const int rloc = i * 16 + pw * 4 + (lane >> 3);
+            *reinterpret_cast<uint4*>(bufC + kb * KB_BYTES + sw128_off(rloc, seg)) =
+                make_uint4(pack_bf16(lo[i].x, lo[i].y), pack_bf16(lo[i].z, lo[i].w), pack_bf16(hi[i].x, hi[i].y),
+                           pack_bf16(hi[i].z, hi[i].w));
+          }
+        }
+      } else {
+        // decoder: dY = d_out[row, 0:3] zero-padded to 128 columns (one thread per row)
+        const int rloc = pw * 32 + lane;
+        const int64_t row = row0 + rloc;
+        float a = 0.f, b = 0.f, c = 0.f;
+        if (row < d.rows) {
+          a = d.d_out[(size_t)row * 3];
+          b = d.d_out[(size_t)row * 3 + 1];
+          c = d.d_out[(size_t)row * 3 + 2];
+        }
+#pragma unroll
+        for (int kb = 0; kb < 2; ++kb)
+#pragma unroll
+          for (int ch = 0; ch < 8; ++ch)
+            *reinterpret_cast<uint4*>(bufC + kb * KB_BYTES + sw128_off(rloc, ch)) =
+                (kb == 0 && ch == 0) ? make_uint4(pack_bf16(a, b), pack_bf16(c, 0.f), 0u, 0u) : make_uint4(0u, 0u, 0u, 0u);
+      }
+      fence_proxy_async();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(BAR(B_DO));
     }
   } else {
     // ============================================================ epilogue: thread <-> row of the tile
@@ -231,16 +286,15 @@ __global__ void __launch_bounds__(NTHREADS, 1) mlp_tc_bwd_a_kernel(const fvgn_ml
       tc_fence_before();
       mbar_arrive(BAR(B_EPI));
     };
-    float db1a = 0.f, db1b = 0.f, db2a = 0.f, db2b = 0.f, db3a = 0.f, db3b = 0.f;
-    float dgam[8], dbet[8];
+    float db1a = 0.f, db1b = 0.f, db2a = 0.f, db2b = 0.f, db3a = 0.f, db3b = 0.f, dbta = 0.f, dbtb = 0.f;
+    float dgam[8];
 #pragma unroll
-    for (int i = 0; i < 8; ++i) dgam[i] = dbet[i] = 0.f;
+    for (int i = 0; i < 8; ++i) dgam[i] = 0.f;
     bool store_pending = false;
+    uint32_t pdo = 0;
+    const uint32_t wacc = tmem + lane_base + WACC;
 
     for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
-      const int64_t row0 = tile * TILE_M;
-      const int64_t row = row0 + rloc;
-      const bool valid = row < d.rows;
       // ---------------- E1 / E2: hidden activations (bf16, shared memory) + gelu' (bf16, TMEM)
 #pragma unroll 1
       for (int layer = 0; layer < 2; ++layer) {
@@ -251,12 +305,9 @@ __global__ void __launch_bounds__(NTHREADS, 1) mlp_tc_bwd_a_kernel(const fvgn_ml
         }
         uint8_t* hb = layer == 0 ? bufH1 : bufH2;
         const float* bias = layer == 0 ? sb1 : sb2;
-        const uint32_t gcol = layer == 0 ? G1 : G2;
-#pragma unroll 1
-        for (int c0 = 0; c0 < 128; c0 += 16) {
-          uint32_t r[16], hw[8], gw[8];
-          tmem_ld16(tmem + lane_base + WACC + c0, r);
-          tmem_wait_ld();
+        const uint32_t gcol = tmem + lane_base + (layer == 0 ? G1 : G2);
+        for_each_chunk16(wacc, [&](int c0, uint32_t (&r)[16]) {
+          uint32_t hw[8], gw[8];
 #pragma unroll
           for (int j = 0; j < 8; ++j) {
             float h0, g0, h1, g1;
@@ -266,97 +317,57 @@ __global__ void __launch_bounds__(NTHREADS, 1) mlp_tc_bwd_a_kernel(const fvgn_ml
             gw[j] = pack_bf16(g0, g1);
           }
           store_tile16(hb, rloc, c0, hw);
-          tmem_st8(tmem + lane_base + gcol + c0 / 2, gw);
-        }
+          tmem_st8(gcol + c0 / 2, gw);
+        });
         tmem_wait_st();
         fence_proxy_async();
         done();
       }
-      // ---------------- E3: upstream gradient, LayerNorm backward -> dY (bf16) in bufC
+      // ---------------- E3: LayerNorm backward -> dY (bf16) in bufC (the producers parked dO there)
       wait_mma();
-      int gs = 0, gr = 0;
-      if (MODE == FVGN_MLP_EDGE && d.d_gather && valid) {
-        gs = d.idx_s[row];
-        gr = d.idx_r[row];
-      }
+      mbar_wait(BAR(B_DO), pdo);
+      pdo ^= 1;
       if (C::LN) {
-        float sum = 0.f;
-#pragma unroll 1
-        for (int c0 = 0; c0 < 128; c0 += 16) {
-          uint32_t r[16];
-          tmem_ld16(tmem + lane_base + WACC + c0, r);
-          tmem_wait_ld();
+        tile_colsum(bufC, tid, dbta, dbtb);  // d beta = column sums of dO
+        float sum = 0.f, sq = 0.f;
+        for_each_chunk16(wacc, [&](int c0, uint32_t (&r)[16]) {
 #pragma unroll
-          for (int j = 0; j < 16; ++j) sum += __uint_as_float(r[j]) + sb3[c0 + j];
-        }
+          for (int j = 0; j < 16; ++j) {
+            const float y = __uint_as_float(r[j]) + sb3[c0 + j];
+            sum += y;
+            sq = fmaf(y, y, sq);
+          }
+        });
         const float mean = sum * (1.0f / 128.0f);
-        float sq = 0.f;
-#pragma unroll 1
-        for (int c0 = 0; c0 < 128; c0 += 16) {
-          uint32_t r[16];
-          tmem_ld16(tmem + lane_base + WACC + c0, r);
-          tmem_wait_ld();
-#pragma unroll
-          for (int j = 0; j < 16; ++j) {
-            const float dv = __uint_as_float(r[j]) + sb3[c0 + j] - mean;
-            sq = fmaf(dv, dv, sq);
-          }
-        }
-        const float rstd = rsqrtf(sq * (1.0f / 128.0f) + 1e-5f);
+        const float rstd = rsqrtf(fmaxf(sq * (1.0f / 128.0f) - mean * mean, 0.f) + 1e-5f);
         float m1 = 0.f, m2 = 0.f;
-        // sweep A: dO (fp32 from HBM), LN parameter gradients, row moments; park dO as bf16 in bufC
-#pragma unroll 1
-        for (int c0 = 0; c0 < 128; c0 += 16) {
-          uint32_t r[16], ow[8];
-          float go[16], gx[16];
-          tmem_ld16(tmem + lane_base + WACC + c0, r);
-          if (valid) {
-            const float4* p = reinterpret_cast<const float4*>(d.d_out + (size_t)row * 128 + c0);
+        // sweep A: row moments and d gamma
+        for_each_chunk16(wacc, [&](int c0, uint32_t (&r)[16]) {
+          uint32_t ow[8];
+          float gx[16];
+          load_tile16(bufC, rloc, c0, ow);
 #pragma unroll
-            for (int q = 0; q < 4; ++q) {
-              const float4 v = __ldg(p + q);
-              go[4 * q] = v.x; go[4 * q + 1] = v.y; go[4 * q + 2] = v.z; go[4 * q + 3] = v.w;
-            }
-            if (MODE == FVGN_MLP_EDGE && d.d_gather) {
-              const float4* g = reinterpret_cast<const float4*>(d.d_gather + (size_t)(c0 < 64 ? gs : gr) * 64 + (c0 & 63));
-#pragma unroll
-              for (int q = 0; q < 4; ++q) {
-                const float4 v = __ldg(g + q);
-                go[4 * q] += v.x; go[4 * q + 1] += v.y; go[4 * q + 2] += v.z; go[4 * q + 3] += v.w;
-              }
-            }
-          } else {
-#pragma unroll
-            for (int j = 0; j < 16; ++j) go[j] = 0.f;
+          for (int j = 0; j < 8; ++j) {
+            const float xh0 = (__uint_as_float(r[2 * j]) + sb3[c0 + 2 * j] - mean) * rstd;
+            const float xh1 = (__uint_as_float(r[2 * j + 1]) + sb3[c0 + 2 * j + 1] - mean) * rstd;
+            const float o0 = bf16_lo(ow[j]), o1 = bf16_hi(ow[j]);
+            const float dx0 = o0 * sg[c0 + 2 * j], dx1 = o1 * sg[c0 + 2 * j + 1];
+            m1 += dx0 + dx1;
+            m2 = fmaf(dx0, xh0, fmaf(dx1, xh1, m2));
+            gx[2 * j] = o0 * xh0;
+            gx[2 * j + 1] = o1 * xh1;
           }
-          tmem_wait_ld();
+          const float cg = warp_colsum16(gx, lane);
 #pragma unroll
-          for (int j = 0; j < 16; ++j) {
-            const float xh = (__uint_as_float(r[j]) + sb3[c0 + j] - mean) * rstd;
-            const float dx = go[j] * sg[c0 + j];
-            m1 += dx;
-            m2 = fmaf(dx, xh, m2);
-            gx[j] = go[j] * xh;
-          }
-#pragma unroll
-          for (int j = 0; j < 8; ++j) ow[j] = pack_bf16(go[2 * j], go[2 * j + 1]);
-          store_tile16(bufC, rloc, c0, ow);
-          const float cb = warp_colsum16(go, lane), cg = warp_colsum16(gx, lane);
-#pragma unroll
-          for (int i = 0; i < 8; ++i) {  // static register indexing (no local-memory array)
-            dbet[i] += (i == (c0 >> 4)) ? cb : 0.f;
-            dgam[i] += (i == (c0 >> 4)) ? cg : 0.f;
-          }
-        }
+          for (int i = 0; i < 8; ++i) dgam[i] += (i == (c0 >> 4)) ? cg : 0.f;  // static register indexing
+        });
         m1 *= (1.0f / 128.0f);
         m2 *= (1.0f / 128.0f);
+        epi_bar_sync();  // every thread has finished reading the whole dO tile (d beta) before rows are overwritten
         // sweep B: dY = rstd * (dO*gamma - m1 - xhat*m2)
-#pragma unroll 1
-        for (int c0 = 0; c0 < 128; c0 += 16) {
-          uint32_t r[16], ow[8];
-          tmem_ld16(tmem + lane_base + WACC + c0, r);
+        for_each_chunk16(wacc, [&](int c0, uint32_t (&r)[16]) {
+          uint32_t ow[8];
           load_tile16(bufC, rloc, c0, ow);
-          tmem_wait_ld();
 #pragma unroll
           for (int j = 0; j < 8; ++j) {
             const float xh0 = (__uint_as_float(r[2 * j]) + sb3[c0 + 2 * j] - mean) * rstd;
@@ -366,56 +377,38 @@ __global__ void __launch_bounds__(NTHREADS, 1) mlp_tc_bwd_a_kernel(const fvgn_ml
             ow[j] = pack_bf16(y0, y1);
           }
           store_tile16(bufC, rloc, c0, ow);
-        }
-      } else {
-        // decoder: dY = d_out[row, 0:3], zero-padded to 128 columns
-#pragma unroll 1
-        for (int c0 = 0; c0 < 128; c0 += 16) {
-          uint32_t ow[8];
-#pragma unroll
-          for (int j = 0; j < 8; ++j) ow[j] = 0u;
-          if (c0 == 0 && valid) {
-            const float a = d.d_out[(size_t)row * 3], b = d.d_out[(size_t)row * 3 + 1], c = d.d_out[(size_t)row * 3 + 2];
-            ow[0] = pack_bf16(a, b);
-            ow[1] = pack_bf16(c, 0.f);
-          }
-          store_tile16(bufC, rloc, c0, ow);
-        }
+        });
+        fence_proxy_async();
+        epi_bar_sync();
       }
-      fence_proxy_async();
-      epi_bar_sync();
       tile_colsum(bufC, tid, db3a, db3b);
       done();
       // ---------------- E4: dZ2 = dH2 * gelu'(Z2) -> bufH2
       wait_mma();
-#pragma unroll 1
-      for (int c0 = 0; c0 < 128; c0 += 16) {
-        uint32_t r[16], g[8], ow[8];
-        tmem_ld16(tmem + lane_base + WACC + c0, r);
+      for_each_chunk16(wacc, [&](int c0, uint32_t (&r)[16]) {
+        uint32_t g[8], ow[8];
         tmem_ld8(tmem + lane_base + G2 + c0 / 2, g);
         tmem_wait_ld();
 #pragma unroll
         for (int j = 0; j < 8; ++j)
           ow[j] = pack_bf16(__uint_as_float(r[2 * j]) * bf16_lo(g[j]), __uint_as_float(r[2 * j + 1]) * bf16_hi(g[j]));
         store_tile16(bufH2, rloc, c0, ow);
-      }
+      });
       fence_proxy_async();
       epi_bar_sync();
       tile_colsum(bufH2, tid, db2a, db2b);
       done();
       // ---------------- E5: dZ1 = dH1 * gelu'(Z1) -> bufH1 -> HBM tile image
       wait_mma();
-#pragma unroll 1
-      for (int c0 = 0; c0 < 128; c0 += 16) {
-        uint32_t r[16], g[8], ow[8];
-        tmem_ld16(tmem + lane_base + WACC + c0, r);
+      for_each_chunk16(wacc, [&](int c0, uint32_t (&r)[16]) {
+        uint32_t g[8], ow[8];
         tmem_ld8(tmem + lane_base + G1 + c0 / 2, g);
         tmem_wait_ld();
 #pragma unroll
         for (int j = 0; j < 8; ++j)
           ow[j] = pack_bf16(__uint_as_float(r[2 * j]) * bf16_lo(g[j]), __uint_as_float(r[2 * j + 1]) * bf16_hi(g[j]));
         store_tile16(bufH1, rloc, c0, ow);
-      }
+      });
       fence_proxy_async();
       epi_bar_sync();
       if (tid == 0) bulk_s2g(dz_img + (size_t)tile * BUF_BYTES, smem_u32(bufH1), BUF_BYTES);
@@ -451,12 +444,10 @@ __global__ void __launch_bounds__(NTHREADS, 1) mlp_tc_bwd_a_kernel(const fvgn_ml
       scr[half * 128 + 2 * p] = db1a; scr[half * 128 + 2 * p + 1] = db1b;
       scr[256 + half * 128 + 2 * p] = db2a; scr[256 + half * 128 + 2 * p + 1] = db2b;
       scr[512 + half * 128 + 2 * p] = db3a; scr[512 + half * 128 + 2 * p + 1] = db3b;
+      scr[1280 + half * 128 + 2 * p] = dbta; scr[1280 + half * 128 + 2 * p + 1] = dbtb;
       if (C::LN && lane < 16) {
 #pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          scr[768 + warp * 128 + i * 16 + lane] = dgam[i];
-          scr[1280 + warp * 128 + i * 16 + lane] = dbet[i];
-        }
+        for (int i = 0; i < 8; ++i) scr[768 + warp * 128 + i * 16 + lane] = dgam[i];
       }
     }
     epi_bar_sync();
@@ -466,7 +457,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) mlp_tc_bwd_a_kernel(const fvgn_ml
       if (tid < C::NOUT) Pb3[tid] = scr[512 + tid] + scr[640 + tid];
       if (C::LN) {
         Pg[tid] = scr[768 + tid] + scr[896 + tid] + scr[1024 + tid] + scr[1152 + tid];
-        Pbeta[tid] = scr[1280 + tid] + scr[1408 + tid] + scr[1536 + tid] + scr[1664 + tid];
+        Pbeta[tid] = scr[1280 + tid] + scr[1408 + tid];
       }
     }
     tc_fence_before();
@@ -607,54 +598,48 @@ __global__ void __launch_bounds__(NTHREADS, 1) mlp_tc_bwd_b_kernel(const fvgn_ml
           const int ab = blk & 1;
           mbar_wait(BAR(B_AFULL + ab), (blk >> 1) & 1);
           tc_fence_after();
-#pragma unroll 1
-          for (int c0 = 0; c0 < 64; c0 += 16) {
-            uint32_t r[16];
-            tmem_ld16(tmem + lane_base + WACC + 64 * ab + c0, r);
-            tmem_wait_ld();
+          for_each_chunk16<64>(tmem + lane_base + WACC + 64 * ab, [&](int c0, uint32_t (&r)[16]) {
+            const int col0 = 64 * j + c0;  // first input column of this 16-column group
+            // which destination does this group go to (uniform over the group: boundaries are multiples of 64)
+            float* dst;
+            int ld, colo;
+            bool add_res = false;
+            if (MODE == FVGN_MLP_EDGE) {
+              if (col0 < 256) { dst = d.d_in0; ld = 256; colo = col0; }
+              else { dst = d.d_in1; ld = 128; colo = col0 - 256; add_res = resid; }
+            } else if (MODE == FVGN_MLP_NODE) {
+              if (col0 < 64) { dst = d.d_in0; ld = 64; colo = col0; }
+              else { dst = d.d_in1; ld = 128; colo = col0 - 64; add_res = resid; }
+            } else {
+              dst = d.d_in0; ld = 128; colo = col0;
+            }
+            // residual gradient rows: issue the loads before the staging round trip
+            float4 g[4];
+#pragma unroll
+            for (int pass = 0; pass < 4; ++pass) {
+              const int64_t row = row0 + warp * 32 + pass * 8 + (lane >> 2);
+              g[pass] = make_float4(0.f, 0.f, 0.f, 0.f);
+              if (add_res && row < d.rows)
+                g[pass] = __ldg(reinterpret_cast<const float4*>(d.d_out + (size_t)row * 128 + colo + (lane & 3) * 4));
+            }
 #pragma unroll
             for (int q = 0; q < 4; ++q)
               *reinterpret_cast<float4*>(mystg + lane * STG_LD + 4 * q) =
                   make_float4(__uint_as_float(r[4 * q]), __uint_as_float(r[4 * q + 1]), __uint_as_float(r[4 * q + 2]),
                               __uint_as_float(r[4 * q + 3]));
             __syncwarp();
-            const int col0 = 64 * j + c0;  // first input column of this 16-column group
 #pragma unroll
             for (int pass = 0; pass < 4; ++pass) {
               const int rr = pass * 8 + (lane >> 2), cc = (lane & 3) * 4;
               const int64_t row = row0 + warp * 32 + rr;
               if (row < d.rows) {
                 float4 v = *reinterpret_cast<const float4*>(mystg + rr * STG_LD + cc);
-                const int col = col0 + cc;
-                if (MODE == FVGN_MLP_EDGE) {
-                  if (col < 256) {
-                    *reinterpret_cast<float4*>(d.d_in0 + (size_t)row * 256 + col) = v;
-                  } else {
-                    const size_t o = (size_t)row * 128 + (col - 256);
-                    if (resid) {
-                      const float4 g = __ldg(reinterpret_cast<const float4*>(d.d_out + o));
-                      v = make_float4(v.x + g.x, v.y + g.y, v.z + g.z, v.w + g.w);
-                    }
-                    *reinterpret_cast<float4*>(d.d_in1 + o) = v;
-                  }
-                } else if (MODE == FVGN_MLP_NODE) {
-                  if (col < 64) {
-                    *reinterpret_cast<float4*>(d.d_in0 + (size_t)row * 64 + col) = v;
-                  } else {
-                    const size_t o = (size_t)row * 128 + (col - 64);
-                    if (resid) {
-                      const float4 g = __ldg(reinterpret_cast<const float4*>(d.d_out + o));
-                      v = make_float4(v.x + g.x, v.y + g.y, v.z + g.z, v.w + g.w);
-                    }
-                    *reinterpret_cast<float4*>(d.d_in1 + o) = v;
-                  }
-                } else {
-                  *reinterpret_cast<float4*>(d.d_in0 + (size_t)row * 128 + col) = v;
-                }
+                v = make_float4(v.x + g[pass].x, v.y + g[pass].y, v.z + g[pass].z, v.w + g[pass].w);
+                *reinterpret_cast<float4*>(dst + (size_t)row * ld + colo + cc) = v;
               }
             }
             __syncwarp();
-          }
+          });
           tc_fence_before();
           mbar_arrive(BAR(B_AFREE + ab));
         }

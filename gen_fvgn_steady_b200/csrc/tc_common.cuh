@@ -281,6 +281,24 @@ __device__ __forceinline__ void bulk_wait0() { asm volatile("cp.async.bulk.wait_
 // named barrier among the 128 epilogue threads (barrier 0 is __syncthreads)
 __device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, 128;" ::: "memory"); }
 
+// Visit the eight 16-column chunks of a 128-column fp32 accumulator: f(c0, r[16]).  The tcgen05.ld of the next chunk
+// is in flight while the current one is processed (tcgen05.wait::ld only waits once the work is done).
+template <int NCOLS = 128, class F>
+__device__ __forceinline__ void for_each_chunk16(uint32_t taddr, F&& f) {
+  uint32_t ra[16], rb[16];
+  tmem_ld16(taddr, ra);
+  tmem_wait_ld();
+#pragma unroll 1
+  for (int c0 = 0; c0 < NCOLS; c0 += 32) {
+    tmem_ld16(taddr + c0 + 16, rb);
+    f(c0, ra);
+    tmem_wait_ld();
+    if (c0 + 32 < NCOLS) tmem_ld16(taddr + c0 + 32, ra);
+    f(c0 + 16, rb);
+    tmem_wait_ld();
+  }
+}
+
 // gelu(x) and gelu'(x) from one erf/exp evaluation (A&S 7.1.26)
 __device__ __forceinline__ void gelu_pair(float x, float& h, float& g) {
   const float z = fabsf(x) * 0.70710678118654752f;
