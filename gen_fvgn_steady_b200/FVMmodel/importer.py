@@ -40,7 +40,14 @@ class NNmodel(nn.Module):
         if self.node_phi_size != 3 or params.node_input_size != 12:
             raise NotImplementedError("kernels are built for node_phi_size=3, node_input_size=12 (get_param.py:69-70)")
         self.set_precision(getattr(params, "precision", None))
+        self.dp_group = None
         self.initialize_weights()
+
+    def enable_data_parallel(self, group=True):
+        """Data-parallel mode: this rank holds a shard of the batch's graphs; the Normalizer
+        increments are summed over ranks so that every rank keeps the statistics of the global batch.  The gradient
+        all-reduce itself is done by the caller (gen_fvgn_steady_b200.parallel)."""
+        self.dp_group = group
 
     def set_precision(self, precision):
         """'fp32' (SIMT, parity) or 'bf16' (tcgen05, throughput).  None -> $FVGN_PRECISION or fp32."""
@@ -85,7 +92,12 @@ class NNmodel(nn.Module):
             if self.node_norm.wants_accumulation():
                 sq = ops.segment_colsum(x, 9, 12, plan.node_chunks, plan.node_chunk_ptr, plan.n_node_chunks, B, power=2,
                                         col_offset=3)
-                self.node_norm.accumulate(sums[:, 3:12].sum(0), sq.sum(0), N)
+                s1, s2, cnt = sums[:, 3:12].sum(0), sq.sum(0), N
+                if self.dp_group is not None:
+                    from ..parallel import allreduce_normalizer
+                    s1, s2, cnt = allreduce_normalizer(self.node_norm, (s1, s2, cnt),
+                                                       None if self.dp_group is True else self.dp_group)
+                self.node_norm.accumulate(s1, s2, cnt)
             nmean, nstd = self.node_norm.mean().float().contiguous(), self.node_norm.std().float().contiguous()
         xn = torch.empty_like(x)
         uv_old = torch.empty((N, 2), dtype=torch.float32, device=x.device)

@@ -21,8 +21,8 @@ def flatten_gradients(model):
     return flat
 
 
-def allreduce_gradients(flat, world_size):
-    dist.all_reduce(flat, op=dist.ReduceOp.SUM)
+def allreduce_gradients(flat, world_size, group=None):
+    dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=group)
     flat.div_(world_size)
 
 
@@ -31,11 +31,11 @@ def shard_graphs(num_graphs, rank, world_size):
     return list(range(rank, num_graphs, world_size))
 
 
-def allreduce_normalizer(normalizer, pending):
+def allreduce_normalizer(normalizer, pending, group=None):
     """Sum the Normalizer increments of this step over ranks so every rank holds the global-batch statistics.
     pending = (data_sum, squared_sum, count) as produced by NNmodel.update_x_attr on the local shard."""
     s, ss, cnt = pending
     buf = torch.cat([s.reshape(-1), ss.reshape(-1), torch.tensor([float(cnt)], device=s.device)])
-    dist.all_reduce(buf, op=dist.ReduceOp.SUM)
+    dist.all_reduce(buf, op=dist.ReduceOp.SUM, group=group)
     n = s.numel()
     return buf[:n], buf[n:2 * n], float(buf[-1])
