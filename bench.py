@@ -34,7 +34,8 @@ def parse_args():
     ap.add_argument("--cells", type=int, default=int(os.environ.get("FVGN_BENCH_CELLS", 4_000_000)))
     ap.add_argument("--net", default=os.environ.get("FVGN_BENCH_NET", "EPD"))
     ap.add_argument("--mp", type=int, default=int(os.environ.get("FVGN_BENCH_MP", 6)))
-    ap.add_argument("--precision", default=os.environ.get("FVGN_PRECISION", "fp32"))
+    ap.add_argument("--precision", default=os.environ.get("FVGN_PRECISION", "bf16"), choices=["bf16", "fp32"],
+                    help="bf16: tcgen05 throughput mode (default); fp32: SIMT parity mode")
     ap.add_argument("--cpu-cells", type=int, default=40_000, help="cell count of the bounded CPU-baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     return ap.parse_args()
@@ -176,6 +177,8 @@ def run_ours(args):
     p = default_params(net=args.net, message_passing_num=args.mp, precision=args.precision)
     torch.manual_seed(0)
     model = NNmodel(p).to(dev)
+    if world > 1:
+        model.enable_data_parallel(True)
     flat_grad = parallel.flatten_gradients(model)
     opt = torch.optim.Adam(model.parameters(), lr=p.lr, fused=True)
     plan = GraphPlan.of(gn, gx, ge, gc, p.order)
