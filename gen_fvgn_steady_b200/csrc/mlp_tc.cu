@@ -227,12 +227,36 @@ __global__ void __launch_bounds__(NTHREADS, 1) mlp_tc_fwd_kernel(const fvgn_mlp_
         tc_fence_after();
         const uint32_t acc = layer == 0 ? t1 : t2;
         const float* bias = layer == 0 ? sb1 : sb2;
+        // layer 1 only: Z1 is rounded to bf16 (what the backward reads back) and stored as a pre-swizzled tile image
+        uint8_t* zimg = (layer == 0 && d.z1_img)
+                            ? reinterpret_cast<uint8_t*>(d.z1_img) + (size_t)(row0 / TILE_M) * (2 * KB_BYTES) : nullptr;
         for_each_chunk16(acc, [&](int c0, uint32_t (&r)[16]) {
           uint32_t w[8];
+          float z[16];
 #pragma unroll
-          for (int j = 0; j < 8; ++j)
-            w[j] = pack_bf16(gelu_tanh(__uint_as_float(r[2 * j]) + bias[c0 + 2 * j]),
-                             gelu_tanh(__uint_as_float(r[2 * j + 1]) + bias[c0 + 2 * j + 1]));
+          for (int j = 0; j < 16; j += 4) {
+            const float4 b = *reinterpret_cast<const float4*>(bias + c0 + j);
+            z[j] = __uint_as_float(r[j]) + b.x;
+            z[j + 1] = __uint_as_float(r[j + 1]) + b.y;
+            z[j + 2] = __uint_as_float(r[j + 2]) + b.z;
+            z[j + 3] = __uint_as_float(r[j + 3]) + b.w;
+          }
+          if (layer == 0) {
+            uint32_t zw[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              zw[j] = pack_bf16(z[2 * j], z[2 * j + 1]);
+              z[2 * j] = bf16_lo(zw[j]);
+              z[2 * j + 1] = bf16_hi(zw[j]);
+            }
+            if (zimg) {
+              const int kb = c0 >> 6, chunk = (c0 & 63) >> 3;
+              *reinterpret_cast<uint4*>(zimg + kb * KB_BYTES + sw128_off(rloc, chunk)) = make_uint4(zw[0], zw[1], zw[2], zw[3]);
+              *reinterpret_cast<uint4*>(zimg + kb * KB_BYTES + sw128_off(rloc, chunk + 1)) = make_uint4(zw[4], zw[5], zw[6], zw[7]);
+            }
+          }
+#pragma unroll
+          for (int j = 0; j < 8; ++j) w[j] = pack_bf16(gelu_tanh(z[2 * j]), gelu_tanh(z[2 * j + 1]));
           tmem_st8(acc + c0 / 2, w);  // in place: always behind the columns still to be read (and the one in flight)
         });
         tmem_wait_st();
@@ -249,10 +273,12 @@ __global__ void __launch_bounds__(NTHREADS, 1) mlp_tc_fwd_kernel(const fvgn_mlp_
         float sum = 0.f, sq = 0.f;
         for_each_chunk16(acc, [&](int c0, uint32_t (&r)[16]) {
 #pragma unroll
-          for (int j = 0; j < 16; ++j) {
-            const float y = __uint_as_float(r[j]) + sb3[c0 + j];
-            sum += y;
-            sq = fmaf(y, y, sq);
+          for (int j = 0; j < 16; j += 4) {
+            const float4 b = *reinterpret_cast<const float4*>(sb3 + c0 + j);
+            const float y0 = __uint_as_float(r[j]) + b.x, y1 = __uint_as_float(r[j + 1]) + b.y;
+            const float y2 = __uint_as_float(r[j + 2]) + b.z, y3 = __uint_as_float(r[j + 3]) + b.w;
+            sum += (y0 + y1) + (y2 + y3);
+            sq = fmaf(y0, y0, fmaf(y1, y1, fmaf(y2, y2, fmaf(y3, y3, sq))));
           }
         });
         const float mean = sum * (1.0f / 128.0f);
@@ -280,11 +306,14 @@ __global__ void __launch_bounds__(NTHREADS, 1) mlp_tc_fwd_kernel(const fvgn_mlp_
             const int cb = c0 + half * STG_COLS;
 #pragma unroll
             for (int j = 0; j < STG_COLS; j += 4) {
+              const float4 b = *reinterpret_cast<const float4*>(sb3 + cb + j);
+              const float4 gm = *reinterpret_cast<const float4*>(sg + cb + j);
+              const float4 bt = *reinterpret_cast<const float4*>(sbeta + cb + j);
               float4 y;
-              y.x = (__uint_as_float(r[half * 8 + j + 0]) + sb3[cb + j + 0] - mean) * rstd * sg[cb + j + 0] + sbeta[cb + j + 0];
-              y.y = (__uint_as_float(r[half * 8 + j + 1]) + sb3[cb + j + 1] - mean) * rstd * sg[cb + j + 1] + sbeta[cb + j + 1];
-              y.z = (__uint_as_float(r[half * 8 + j + 2]) + sb3[cb + j + 2] - mean) * rstd * sg[cb + j + 2] + sbeta[cb + j + 2];
-              y.w = (__uint_as_float(r[half * 8 + j + 3]) + sb3[cb + j + 3] - mean) * rstd * sg[cb + j + 3] + sbeta[cb + j + 3];
+              y.x = (__uint_as_float(r[half * 8 + j + 0]) + b.x - mean) * rstd * gm.x + bt.x;
+              y.y = (__uint_as_float(r[half * 8 + j + 1]) + b.y - mean) * rstd * gm.y + bt.y;
+              y.z = (__uint_as_float(r[half * 8 + j + 2]) + b.z - mean) * rstd * gm.z + bt.z;
+              y.w = (__uint_as_float(r[half * 8 + j + 3]) + b.w - mean) * rstd * gm.w + bt.w;
               *reinterpret_cast<float4*>(mystg + lane * STG_LD + j) = y;
             }
             __syncwarp();

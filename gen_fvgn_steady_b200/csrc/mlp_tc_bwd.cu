@@ -70,27 +70,49 @@ __device__ __forceinline__ void tile_colsum(const uint8_t* buf, int t, float& s0
 }
 
 // =============================================================================================== kernel A
+// Roles (448 threads): warps 0-7 epilogue (thread <-> (row, column half): warps w and w+4 share a TMEM lane quarter and
+// split the 128 columns), warps 8-11 stage the upstream-gradient tile dO as bf16, warp 12 issues the MMAs, warp 13 is the
+// bulk-copy loader (W2/W3 image once, then one 32 KB Z1 tile image per tile, double buffered).
+// Layer 1 is NOT recomputed: the forward left Z1 (bf16) in HBM; E1 turns the tile into H1 (in place, shared memory) and
+// gelu'(Z1) (TMEM).  Per tile:  E1 -> R2 -> E2 -> R3 -> E3 (LayerNorm backward) -> dW3/dH2 -> E4 -> dW2/dH1 -> E5.
+constexpr int A_THREADS = 448;
+constexpr int A_EPI = 256;  // epilogue threads
+__device__ __forceinline__ void epi_bar_sync256() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
+
+// column sums of a bf16 tile by the 256 epilogue threads: thread t owns column pair (2p, 2p+1), p = t & 63, rows [32*(t>>6), +32)
+__device__ __forceinline__ void tile_colsum256(const uint8_t* buf, int t, float& s0, float& s1) {
+  const int p = t & 63, r0 = (t >> 6) * 32;
+  const int kb = (2 * p) >> 6, chunk = ((2 * p) & 63) >> 3, word = p & 3;
+  const uint8_t* base = buf + kb * KB_BYTES + word * 4;
+  float a = 0.f, b = 0.f;
+#pragma unroll 8
+  for (int r = r0; r < r0 + 32; ++r) {
+    const uint32_t w = *reinterpret_cast<const uint32_t*>(base + sw128_off(r, chunk));
+    a += bf16_lo(w);
+    b += bf16_hi(w);
+  }
+  s0 += a;
+  s1 += b;
+}
+
 template <int MODE>
-__global__ void __launch_bounds__(NTHREADS, 1) mlp_tc_bwd_a_kernel(const fvgn_mlp_desc d) {
+__global__ void __launch_bounds__(A_THREADS, 1) mlp_tc_bwd_a_kernel(const fvgn_mlp_desc d) {
   using C = BCfg<MODE>;
-  constexpr int NKB1 = nkb1(C::K1P);
-  constexpr int LASTK = (C::K1P - 64 * (NKB1 - 1)) / 16;
-  constexpr int NSTAGE = 2;
   constexpr uint32_t DW2 = 0, DW3 = 128, WACC = 256, G1 = 384, G2 = 448;
   FVGN_DYN_SMEM(smem);
   uint8_t* w23 = smem;                              // W2 image | W3 image (64 KB)
-  uint8_t* ring = w23 + 4 * KB_BYTES;               // NSTAGE x [X chunk | W1 K-block]
-  uint8_t* bufH1 = ring + NSTAGE * 2 * KB_BYTES;
-  uint8_t* bufH2 = bufH1 + BUF_BYTES;
-  uint8_t* bufC = bufH2 + BUF_BYTES;
-  float* sb1 = reinterpret_cast<float*>(bufC + BUF_BYTES);
-  float* sb2 = sb1 + 128;
+  uint8_t* bufZ = w23 + 4 * KB_BYTES;               // 2 x [Z1 -> H1 -> dZ1] tile
+  uint8_t* bufH2 = bufZ + 2 * BUF_BYTES;            // H2 -> dZ2
+  uint8_t* bufC = bufH2 + BUF_BYTES;                // dO -> dY
+  float* sb2 = reinterpret_cast<float*>(bufC + BUF_BYTES);
   float* sb3 = sb2 + 128;
   float* sg = sb3 + 128;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(sg + 128);
+  float2* xchA = reinterpret_cast<float2*>(sg + 128);  // [2 halves][128 rows] LayerNorm statistics exchange
+  float2* xchB = xchA + 256;                           // [2][128] LayerNorm-backward row moments exchange
+  uint64_t* bars = reinterpret_cast<uint64_t*>(xchB + 256);
   const uint32_t bar0 = smem_u32(bars);
   auto BAR = [&](int i) { return bar0 + 8u * (uint32_t)i; };
-  constexpr int B_W = 0, B_FULL = 1, B_EMPTY = 3, B_MMA = 5, B_EPI = 6, B_DO = 7, B_CFREE = 8;
+  constexpr int B_W = 0, B_ZFULL = 1, B_ZEMPTY = 3, B_MMA = 5, B_EPI = 6, B_DO = 7, B_CFREE = 8;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 10);
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -105,42 +127,55 @@ __global__ void __launch_bounds__(NTHREADS, 1) mlp_tc_bwd_a_kernel(const fvgn_ml
   float* Pg = Pb3 + C::NOUT;
   float* Pbeta = Pg + 128;
   uint8_t* dz_img = reinterpret_cast<uint8_t*>(d.workspace);
+  const uint8_t* z_img = reinterpret_cast<const uint8_t*>(d.z1_img);
   const uint8_t* w_img = reinterpret_cast<const uint8_t*>(d.w_bf16);
+  constexpr int NKB1 = nkb1(C::K1P);
 
   if (tid == 0) {
     mbar_init(BAR(B_W), 1);
-    for (int s = 0; s < NSTAGE; ++s) {
-      mbar_init(BAR(B_FULL + s), 5);  // 4 producer warps + the expect_tx arrival of the W1 K-block copy
-      mbar_init(BAR(B_EMPTY + s), 1);
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(BAR(B_ZFULL + s), 1);          // expect_tx arrival + the bytes of the bulk copy
+      mbar_init(BAR(B_ZEMPTY + s), A_EPI + 1); // every epilogue thread (done reading) + thread 0 (bulk store has read it)
     }
     mbar_init(BAR(B_MMA), 1);
-    mbar_init(BAR(B_EPI), 128);
-    mbar_init(BAR(B_DO), 4);     // producers: upstream-gradient tile parked in bufC
-    mbar_init(BAR(B_CFREE), 1);  // tcgen05.commit: bufC no longer read by the previous tile's MMAs
+    mbar_init(BAR(B_EPI), A_EPI);
+    mbar_init(BAR(B_DO), 4);     // producer warps: upstream-gradient tile parked in bufC
+    mbar_init(BAR(B_CFREE), 2);  // tcgen05.commit (dW3 / dH2 MMAs retired) + epilogue (db3 column sums done)
     fence_barrier_init();
   }
-  for (int i = tid; i < 128; i += NTHREADS) {
-    sb1[i] = d.b1[i];
+  for (int i = tid; i < 128; i += A_THREADS) {
     sb2[i] = d.b2[i];
     sb3[i] = (i < C::NOUT) ? d.b3[i] : 0.f;
     sg[i] = C::LN ? d.ln_g[i] : 1.f;
   }
-  if (warp == 8) tmem_alloc(smem_u32(tmem_slot), 512);
+  if (warp == 12) tmem_alloc(smem_u32(tmem_slot), 512);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = *tmem_slot;
 
-  if (warp == 8) {
-    // ============================================================ MMA issuer
+  if (warp == 13) {
+    // ============================================================ loader
     if (lane == 0) {
       mbar_expect_tx(BAR(B_W), 4 * KB_BYTES);
       for (int i = 0; i < 4; ++i)
         bulk_g2s(smem_u32(w23 + i * KB_BYTES), w_img + (size_t)(NKB1 + i) * KB_BYTES, KB_BYTES, BAR(B_W));
+      uint32_t i = 0;
+      for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++i) {
+        const int zb = i & 1;
+        mbar_wait(BAR(B_ZEMPTY + zb), ((i >> 1) & 1) ^ 1);
+        mbar_expect_tx(BAR(B_ZFULL + zb), BUF_BYTES);
+        bulk_g2s(smem_u32(bufZ + zb * BUF_BYTES), z_img + (size_t)tile * BUF_BYTES, BUF_BYTES, BAR(B_ZFULL + zb));
+      }
+    }
+    __syncwarp();
+  } else if (warp == 12) {
+    // ============================================================ MMA issuer
+    if (lane == 0) {
       mbar_wait(BAR(B_W), 0);
       const uint32_t w2s = smem_u32(w23), w3s = w2s + 2 * KB_BYTES;
-      const uint32_t h1s = smem_u32(bufH1), h2s = smem_u32(bufH2), cs = smem_u32(bufC);
-      uint32_t it = 0, pe = 0;
+      const uint32_t h2s = smem_u32(bufH2), cs = smem_u32(bufC);
+      uint32_t pe = 0, i = 0;
       bool first = true;
       auto wait_epi = [&]() {
         mbar_wait(BAR(B_EPI), pe);
@@ -165,20 +200,9 @@ __global__ void __launch_bounds__(NTHREADS, 1) mlp_tc_bwd_a_kernel(const fvgn_ml
           umma_ss(tmem + acc, make_desc_k128(a_s + (k >> 2) * KB_BYTES) + 2 * (k & 3), make_desc_mn128(w_s, KB_BYTES) + 128 * k,
                   IDESC_KM, k != 0);
       };
-      for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
-        // R1: Z1 = X W1^T  (X chunk and W1 K-block arrive together in a ring stage)
-        for (int kb = 0; kb < NKB1; ++kb, ++it) {
-          const int s = it % NSTAGE;
-          mbar_wait(BAR(B_FULL + s), (it / NSTAGE) & 1);
-          tc_fence_after();
-          const uint64_t ad = make_desc_k128(smem_u32(ring + s * 2 * KB_BYTES));
-          const uint64_t bd = make_desc_k128(smem_u32(ring + s * 2 * KB_BYTES + KB_BYTES));
-          const int nk = (kb == NKB1 - 1) ? LASTK : 4;
-          for (int k = 0; k < nk; ++k) umma_ss(tmem + WACC, ad + 2 * k, bd + 2 * k, IDESC_KK, (kb | k) != 0);
-          umma_commit(BAR(B_EMPTY + s));
-        }
-        umma_commit(BAR(B_MMA));
-        wait_epi();                       // E1: H1 in bufH1, gelu'(Z1) in TMEM
+      for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++i) {
+        const uint32_t h1s = smem_u32(bufZ + (i & 1) * BUF_BYTES);
+        wait_epi();                       // E1: H1 in bufZ, gelu'(Z1) in TMEM
         gemm_kk(WACC, h1s, w2s);          // R2
         umma_commit(BAR(B_MMA));
         wait_epi();                       // E2: H2 in bufH2
@@ -193,37 +217,24 @@ __global__ void __launch_bounds__(NTHREADS, 1) mlp_tc_bwd_a_kernel(const fvgn_ml
         gemm_wgrad(DW2, h2s, h1s, first); // dW2 += dZ2^T H1
         gemm_dgrad(WACC, h2s, w2s);       // dH1 = dZ2 W2
         umma_commit(BAR(B_MMA));
-        wait_epi();                       // E5: dZ1 written, WACC drained
         first = false;
       }
     }
     __syncwarp();
-  } else if (warp >= 4) {
-    // ============================================================ producers: X chunk (gather + bf16), W1 K-block (bulk copy)
-    // and the tile of upstream gradients dO = d_out (+ gathered d_a1) as bf16 into bufC
-    const int pw = warp - 4;
-    uint32_t it = 0, tcount = 0;
+  } else if (warp >= 8) {
+    // ============================================================ producers: the tile of upstream gradients
+    // dO = d_out (+ gathered d_a1) as bf16 into bufC.  The loads of the next tile are issued (and packed) before waiting
+    // for bufC to be released, so their latency is hidden behind the current tile.
+    const int pw = warp - 8;
+    uint32_t tcount = 0;
     TileIdx idx;
     for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++tcount) {
       const int64_t row0 = tile * TILE_M;
-      load_tile_idx<MODE>(d, row0, pw, lane, idx);
-      for (int kb = 0; kb < NKB1; ++kb, ++it) {
-        const int s = it % NSTAGE;
-        uint8_t* stage = ring + s * 2 * KB_BYTES;
-        mbar_wait(BAR(B_EMPTY + s), ((it / NSTAGE) & 1) ^ 1);
-        if (pw == 0 && lane == 0) {
-          mbar_expect_tx(BAR(B_FULL + s), KB_BYTES);
-          bulk_g2s(smem_u32(stage + KB_BYTES), w_img + (size_t)kb * KB_BYTES, KB_BYTES, BAR(B_FULL + s));
-        }
-        produce_chunk<MODE>(d, row0, kb, stage, pw, lane, idx);
-        fence_proxy_async();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(BAR(B_FULL + s));
-      }
-      mbar_wait(BAR(B_CFREE), (tcount & 1) ^ 1);  // previous tile's dW3 / dH2 MMAs have retired
       if (C::LN) {
+        if (MODE == FVGN_MLP_EDGE && d.d_gather) load_tile_idx<MODE>(d, row0, pw, lane, idx);
         const int seg = lane & 7;
-#pragma unroll 1
+        uint4 pk[2][8];
+#pragma unroll
         for (int kb = 0; kb < 2; ++kb) {
           float4 lo[8], hi[8];
 #pragma unroll
@@ -235,7 +246,13 @@ __global__ void __launch_bounds__(NTHREADS, 1) mlp_tc_bwd_a_kernel(const fvgn_ml
               const float* p = d.d_out + (size_t)row * 128 + kb * 64 + seg * 8;
               lo[i] = __ldg(reinterpret_cast<const float4*>(p));
               hi[i] = __ldg(reinterpret_cast<const float4*>(p + 4));
-              if (MODE == FVGN_MLP_EDGE && d.d_gather) {
+            }
+          }
+          if (MODE == FVGN_MLP_EDGE && d.d_gather) {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              const int64_t row = row0 + i * 16 + pw * 4 + (lane >> 3);
+              if (row < d.rows) {
                 const float* g = d.d_gather + (size_t)(kb == 0 ? idx.s[i] : idx.r[i]) * 64 + seg * 8;
                 const float4 a = __ldg(reinterpret_cast<const float4*>(g)), b = __ldg(reinterpret_cast<const float4*>(g + 4));
                 lo[i] = make_float4(lo[i].x + a.x, lo[i].y + a.y, lo[i].z + a.z, lo[i].w + a.w);
@@ -244,13 +261,18 @@ __global__ void __launch_bounds__(NTHREADS, 1) mlp_tc_bwd_a_kernel(const fvgn_ml
             }
           }
 #pragma unroll
+          for (int i = 0; i < 8; ++i)
+            pk[kb][i] = make_uint4(pack_bf16(lo[i].x, lo[i].y), pack_bf16(lo[i].z, lo[i].w), pack_bf16(hi[i].x, hi[i].y),
+                                   pack_bf16(hi[i].z, hi[i].w));
+        }
+        mbar_wait(BAR(B_CFREE), (tcount & 1) ^ 1);  // previous tile's dW3 / dH2 MMAs and db3 column sums are done
+#pragma unroll
+        for (int kb = 0; kb < 2; ++kb)
+#pragma unroll
           for (int i = 0; i < 8; ++i) {
             const int rloc = i * 16 + pw * 4 + (lane >> 3);
-            *reinterpret_cast<uint4*>(bufC + kb * KB_BYTES + sw128_off(rloc, seg)) =
-                make_uint4(pack_bf16(lo[i].x, lo[i].y), pack_bf16(lo[i].z, lo[i].w), pack_bf16(hi[i].x, hi[i].y),
-                           pack_bf16(hi[i].z, hi[i].w));
+            *reinterpret_cast<uint4*>(bufC + kb * KB_BYTES + sw128_off(rloc, seg)) = pk[kb][i];
           }
-        }
       } else {
         // decoder: dY = d_out[row, 0:3] zero-padded to 128 columns (one thread per row)
         const int rloc = pw * 32 + lane;
@@ -261,6 +283,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) mlp_tc_bwd_a_kernel(const fvgn_ml
           b = d.d_out[(size_t)row * 3 + 1];
           c = d.d_out[(size_t)row * 3 + 2];
         }
+        mbar_wait(BAR(B_CFREE), (tcount & 1) ^ 1);
 #pragma unroll
         for (int kb = 0; kb < 2; ++kb)
 #pragma unroll
@@ -273,9 +296,11 @@ __global__ void __launch_bounds__(NTHREADS, 1) mlp_tc_bwd_a_kernel(const fvgn_ml
       if (lane == 0) mbar_arrive(BAR(B_DO));
     }
   } else {
-    // ============================================================ epilogue: thread <-> row of the tile
-    const uint32_t lane_base = (uint32_t)(warp * 32) << 16;
-    const int rloc = warp * 32 + lane;
+    // ============================================================ epilogue: thread <-> (row, column half)
+    const int q = warp & 3, half = warp >> 2;
+    const uint32_t lane_base = (uint32_t)(q * 32) << 16;
+    const int rloc = q * 32 + lane;
+    const int cbase = 64 * half;  // first column of this thread's half
     uint32_t pm = 0;
     auto wait_mma = [&]() {
       mbar_wait(BAR(B_MMA), pm);
@@ -287,71 +312,97 @@ __global__ void __launch_bounds__(NTHREADS, 1) mlp_tc_bwd_a_kernel(const fvgn_ml
       mbar_arrive(BAR(B_EPI));
     };
     float db1a = 0.f, db1b = 0.f, db2a = 0.f, db2b = 0.f, db3a = 0.f, db3b = 0.f, dbta = 0.f, dbtb = 0.f;
-    float dgam[8];
+    float dgam[4];
 #pragma unroll
-    for (int i = 0; i < 8; ++i) dgam[i] = 0.f;
-    bool store_pending = false;
-    uint32_t pdo = 0;
-    const uint32_t wacc = tmem + lane_base + WACC;
+    for (int i = 0; i < 4; ++i) dgam[i] = 0.f;
+    uint32_t pdo = 0, i = 0;
+    const uint32_t wacc = tmem + lane_base + WACC + cbase;
+    const uint32_t g1c = tmem + lane_base + G1 + cbase / 2, g2c = tmem + lane_base + G2 + cbase / 2;
 
-    for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
-      // ---------------- E1 / E2: hidden activations (bf16, shared memory) + gelu' (bf16, TMEM)
+    for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++i) {
+      const int zb = i & 1;
+      uint8_t* bz = bufZ + zb * BUF_BYTES;
+      // ---------------- E1: Z1 (bf16, from the forward) -> H1 in place + gelu'(Z1) into TMEM
+      mbar_wait(BAR(B_ZFULL + zb), (i >> 1) & 1);
 #pragma unroll 1
-      for (int layer = 0; layer < 2; ++layer) {
-        wait_mma();
-        if (layer == 0 && store_pending) {  // bufH1 still feeds the previous tile's dZ1 bulk store
-          if (tid == 0) bulk_wait_read0();
-          epi_bar_sync();
-        }
-        uint8_t* hb = layer == 0 ? bufH1 : bufH2;
-        const float* bias = layer == 0 ? sb1 : sb2;
-        const uint32_t gcol = tmem + lane_base + (layer == 0 ? G1 : G2);
-        for_each_chunk16(wacc, [&](int c0, uint32_t (&r)[16]) {
-          uint32_t hw[8], gw[8];
+      for (int c0 = 0; c0 < 64; c0 += 16) {
+        uint32_t zw[8], hw[8], gw[8];
+        load_tile16(bz, rloc, cbase + c0, zw);
 #pragma unroll
-          for (int j = 0; j < 8; ++j) {
-            float h0, g0, h1, g1;
-            gelu_tanh_pair(__uint_as_float(r[2 * j]) + bias[c0 + 2 * j], h0, g0);
-            gelu_tanh_pair(__uint_as_float(r[2 * j + 1]) + bias[c0 + 2 * j + 1], h1, g1);
-            hw[j] = pack_bf16(h0, h1);
-            gw[j] = pack_bf16(g0, g1);
-          }
-          store_tile16(hb, rloc, c0, hw);
-          tmem_st8(gcol + c0 / 2, gw);
-        });
-        tmem_wait_st();
-        fence_proxy_async();
-        done();
+        for (int j = 0; j < 8; ++j) {
+          float h0, g0, h1, g1;
+          gelu_tanh_pair(bf16_lo(zw[j]), h0, g0);
+          gelu_tanh_pair(bf16_hi(zw[j]), h1, g1);
+          hw[j] = pack_bf16(h0, h1);
+          gw[j] = pack_bf16(g0, g1);
+        }
+        store_tile16(bz, rloc, cbase + c0, hw);
+        tmem_st8(g1c + c0 / 2, gw);
       }
+      tmem_wait_st();
+      fence_proxy_async();
+      done();
+      if (i > 0 && tid == 0) {
+        // the previous tile's dZ1 bulk store has finished reading its buffer: hand it back to the loader
+        bulk_wait_read0();
+        mbar_arrive(BAR(B_ZEMPTY + (zb ^ 1)));
+      }
+      // ---------------- E2: H2 (bf16, shared memory) + gelu'(Z2) (bf16, TMEM)
+      wait_mma();
+      for_each_chunk16<64>(wacc, [&](int c0, uint32_t (&r)[16]) {
+        uint32_t hw[8], gw[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const float2 b = *reinterpret_cast<const float2*>(sb2 + cbase + c0 + 2 * j);
+          float h0, g0, h1, g1;
+          gelu_tanh_pair(__uint_as_float(r[2 * j]) + b.x, h0, g0);
+          gelu_tanh_pair(__uint_as_float(r[2 * j + 1]) + b.y, h1, g1);
+          hw[j] = pack_bf16(h0, h1);
+          gw[j] = pack_bf16(g0, g1);
+        }
+        store_tile16(bufH2, rloc, cbase + c0, hw);
+        tmem_st8(g2c + c0 / 2, gw);
+      });
+      tmem_wait_st();
+      fence_proxy_async();
+      done();
       // ---------------- E3: LayerNorm backward -> dY (bf16) in bufC (the producers parked dO there)
       wait_mma();
       mbar_wait(BAR(B_DO), pdo);
       pdo ^= 1;
       if (C::LN) {
-        tile_colsum(bufC, tid, dbta, dbtb);  // d beta = column sums of dO
+        tile_colsum256(bufC, tid, dbta, dbtb);  // d beta = column sums of dO
         float sum = 0.f, sq = 0.f;
-        for_each_chunk16(wacc, [&](int c0, uint32_t (&r)[16]) {
+        for_each_chunk16<64>(wacc, [&](int c0, uint32_t (&r)[16]) {
 #pragma unroll
           for (int j = 0; j < 16; ++j) {
-            const float y = __uint_as_float(r[j]) + sb3[c0 + j];
+            const float y = __uint_as_float(r[j]) + sb3[cbase + c0 + j];
             sum += y;
             sq = fmaf(y, y, sq);
           }
         });
+        xchA[half * 128 + rloc] = make_float2(sum, sq);
+        epi_bar_sync256();
+        {
+          const float2 o = xchA[(half ^ 1) * 128 + rloc];
+          sum += o.x;
+          sq += o.y;
+        }
         const float mean = sum * (1.0f / 128.0f);
         const float rstd = rsqrtf(fmaxf(sq * (1.0f / 128.0f) - mean * mean, 0.f) + 1e-5f);
         float m1 = 0.f, m2 = 0.f;
         // sweep A: row moments and d gamma
-        for_each_chunk16(wacc, [&](int c0, uint32_t (&r)[16]) {
+        for_each_chunk16<64>(wacc, [&](int c0, uint32_t (&r)[16]) {
           uint32_t ow[8];
           float gx[16];
-          load_tile16(bufC, rloc, c0, ow);
+          load_tile16(bufC, rloc, cbase + c0, ow);
 #pragma unroll
           for (int j = 0; j < 8; ++j) {
-            const float xh0 = (__uint_as_float(r[2 * j]) + sb3[c0 + 2 * j] - mean) * rstd;
-            const float xh1 = (__uint_as_float(r[2 * j + 1]) + sb3[c0 + 2 * j + 1] - mean) * rstd;
+            const int c = cbase + c0 + 2 * j;
+            const float xh0 = (__uint_as_float(r[2 * j]) + sb3[c] - mean) * rstd;
+            const float xh1 = (__uint_as_float(r[2 * j + 1]) + sb3[c + 1] - mean) * rstd;
             const float o0 = bf16_lo(ow[j]), o1 = bf16_hi(ow[j]);
-            const float dx0 = o0 * sg[c0 + 2 * j], dx1 = o1 * sg[c0 + 2 * j + 1];
+            const float dx0 = o0 * sg[c], dx1 = o1 * sg[c + 1];
             m1 += dx0 + dx1;
             m2 = fmaf(dx0, xh0, fmaf(dx1, xh1, m2));
             gx[2 * j] = o0 * xh0;
@@ -359,111 +410,118 @@ __global__ void __launch_bounds__(NTHREADS, 1) mlp_tc_bwd_a_kernel(const fvgn_ml
           }
           const float cg = warp_colsum16(gx, lane);
 #pragma unroll
-          for (int i = 0; i < 8; ++i) dgam[i] += (i == (c0 >> 4)) ? cg : 0.f;  // static register indexing
+          for (int k = 0; k < 4; ++k) dgam[k] += (k == (c0 >> 4)) ? cg : 0.f;  // static register indexing
         });
-        m1 *= (1.0f / 128.0f);
-        m2 *= (1.0f / 128.0f);
-        epi_bar_sync();  // every thread has finished reading the whole dO tile (d beta) before rows are overwritten
+        xchB[half * 128 + rloc] = make_float2(m1, m2);
+        epi_bar_sync256();  // also: every thread has finished reading the dO tile (d beta) before rows are overwritten
+        {
+          const float2 o = xchB[(half ^ 1) * 128 + rloc];
+          m1 = (m1 + o.x) * (1.0f / 128.0f);
+          m2 = (m2 + o.y) * (1.0f / 128.0f);
+        }
         // sweep B: dY = rstd * (dO*gamma - m1 - xhat*m2)
-        for_each_chunk16(wacc, [&](int c0, uint32_t (&r)[16]) {
+        for_each_chunk16<64>(wacc, [&](int c0, uint32_t (&r)[16]) {
           uint32_t ow[8];
-          load_tile16(bufC, rloc, c0, ow);
+          load_tile16(bufC, rloc, cbase + c0, ow);
 #pragma unroll
           for (int j = 0; j < 8; ++j) {
-            const float xh0 = (__uint_as_float(r[2 * j]) + sb3[c0 + 2 * j] - mean) * rstd;
-            const float xh1 = (__uint_as_float(r[2 * j + 1]) + sb3[c0 + 2 * j + 1] - mean) * rstd;
-            const float y0 = rstd * (bf16_lo(ow[j]) * sg[c0 + 2 * j] - m1 - xh0 * m2);
-            const float y1 = rstd * (bf16_hi(ow[j]) * sg[c0 + 2 * j + 1] - m1 - xh1 * m2);
+            const int c = cbase + c0 + 2 * j;
+            const float xh0 = (__uint_as_float(r[2 * j]) + sb3[c] - mean) * rstd;
+            const float xh1 = (__uint_as_float(r[2 * j + 1]) + sb3[c + 1] - mean) * rstd;
+            const float y0 = rstd * (bf16_lo(ow[j]) * sg[c] - m1 - xh0 * m2);
+            const float y1 = rstd * (bf16_hi(ow[j]) * sg[c + 1] - m1 - xh1 * m2);
             ow[j] = pack_bf16(y0, y1);
           }
-          store_tile16(bufC, rloc, c0, ow);
+          store_tile16(bufC, rloc, cbase + c0, ow);
         });
         fence_proxy_async();
-        epi_bar_sync();
       }
-      tile_colsum(bufC, tid, db3a, db3b);
       done();
+      epi_bar_sync256();                        // the whole dY tile is written
+      tile_colsum256(bufC, tid, db3a, db3b);    // overlaps the dW3 / dH2 MMAs
       // ---------------- E4: dZ2 = dH2 * gelu'(Z2) -> bufH2
       wait_mma();
-      for_each_chunk16(wacc, [&](int c0, uint32_t (&r)[16]) {
+      for_each_chunk16<64>(wacc, [&](int c0, uint32_t (&r)[16]) {
         uint32_t g[8], ow[8];
-        tmem_ld8(tmem + lane_base + G2 + c0 / 2, g);
+        tmem_ld8(g2c + c0 / 2, g);
         tmem_wait_ld();
 #pragma unroll
         for (int j = 0; j < 8; ++j)
           ow[j] = pack_bf16(__uint_as_float(r[2 * j]) * bf16_lo(g[j]), __uint_as_float(r[2 * j + 1]) * bf16_hi(g[j]));
-        store_tile16(bufH2, rloc, c0, ow);
+        store_tile16(bufH2, rloc, cbase + c0, ow);
       });
       fence_proxy_async();
-      epi_bar_sync();
-      tile_colsum(bufH2, tid, db2a, db2b);
       done();
-      // ---------------- E5: dZ1 = dH1 * gelu'(Z1) -> bufH1 -> HBM tile image
+      epi_bar_sync256();                         // every thread is past its db3 column sums; the dZ2 tile is complete
+      if (tid == 0) mbar_arrive(BAR(B_CFREE));
+      tile_colsum256(bufH2, tid, db2a, db2b);    // overlaps the dW2 / dH1 MMAs
+      // ---------------- E5: dZ1 = dH1 * gelu'(Z1) -> bufZ (in place over H1) -> HBM tile image
       wait_mma();
-      for_each_chunk16(wacc, [&](int c0, uint32_t (&r)[16]) {
+      for_each_chunk16<64>(wacc, [&](int c0, uint32_t (&r)[16]) {
         uint32_t g[8], ow[8];
-        tmem_ld8(tmem + lane_base + G1 + c0 / 2, g);
+        tmem_ld8(g1c + c0 / 2, g);
         tmem_wait_ld();
 #pragma unroll
         for (int j = 0; j < 8; ++j)
           ow[j] = pack_bf16(__uint_as_float(r[2 * j]) * bf16_lo(g[j]), __uint_as_float(r[2 * j + 1]) * bf16_hi(g[j]));
-        store_tile16(bufH1, rloc, c0, ow);
+        store_tile16(bz, rloc, cbase + c0, ow);
       });
       fence_proxy_async();
-      epi_bar_sync();
-      if (tid == 0) bulk_s2g(dz_img + (size_t)tile * BUF_BYTES, smem_u32(bufH1), BUF_BYTES);
-      store_pending = true;
-      tile_colsum(bufH1, tid, db1a, db1b);
-      done();
+      tc_fence_before();
+      epi_bar_sync256();
+      if (tid == 0) bulk_s2g(dz_img + (size_t)tile * BUF_BYTES, smem_u32(bz), BUF_BYTES);
+      tile_colsum256(bz, tid, db1a, db1b);
+      mbar_arrive(BAR(B_ZEMPTY + zb));  // this thread no longer reads the buffer (thread 0 adds the bulk store's release)
     }
     // ---------------- flush: weight-gradient accumulators (TMEM) and the column sums -> this CTA's partial buffer
     if (tid == 0) bulk_wait0();
-    epi_bar_sync();
+    epi_bar_sync256();
     tc_fence_after();
     {
       const int o = rloc;  // TMEM lane = output feature
 #pragma unroll 1
-      for (int c0 = 0; c0 < 128; c0 += 16) {
+      for (int c0 = 0; c0 < 64; c0 += 16) {
         uint32_t r[16];
-        tmem_ld16(tmem + lane_base + DW2 + c0, r);
+        tmem_ld16(tmem + lane_base + DW2 + cbase + c0, r);
         tmem_wait_ld();
 #pragma unroll
-        for (int j = 0; j < 16; ++j) Pw2[(size_t)o * 128 + c0 + j] = __uint_as_float(r[j]);
-        tmem_ld16(tmem + lane_base + DW3 + c0, r);
+        for (int j = 0; j < 16; ++j) Pw2[(size_t)o * 128 + cbase + c0 + j] = __uint_as_float(r[j]);
+        tmem_ld16(tmem + lane_base + DW3 + cbase + c0, r);
         tmem_wait_ld();
         if (o < C::NOUT) {
 #pragma unroll
-          for (int j = 0; j < 16; ++j) Pw3[(size_t)o * 128 + c0 + j] = __uint_as_float(r[j]);
+          for (int j = 0; j < 16; ++j) Pw3[(size_t)o * 128 + cbase + c0 + j] = __uint_as_float(r[j]);
         }
       }
     }
-    // bias sums: combine the two row halves through shared memory (bufC is free now)
+    // bias sums: combine the four row quarters through shared memory (bufC is free now)
     float* scr = reinterpret_cast<float*>(bufC);
     {
-      const int p = tid & 63, half = tid >> 6;
-      scr[half * 128 + 2 * p] = db1a; scr[half * 128 + 2 * p + 1] = db1b;
-      scr[256 + half * 128 + 2 * p] = db2a; scr[256 + half * 128 + 2 * p + 1] = db2b;
-      scr[512 + half * 128 + 2 * p] = db3a; scr[512 + half * 128 + 2 * p + 1] = db3b;
-      scr[1280 + half * 128 + 2 * p] = dbta; scr[1280 + half * 128 + 2 * p + 1] = dbtb;
+      const int p = tid & 63, rq = tid >> 6;
+      scr[rq * 128 + 2 * p] = db1a; scr[rq * 128 + 2 * p + 1] = db1b;
+      scr[512 + rq * 128 + 2 * p] = db2a; scr[512 + rq * 128 + 2 * p + 1] = db2b;
+      scr[1024 + rq * 128 + 2 * p] = db3a; scr[1024 + rq * 128 + 2 * p + 1] = db3b;
+      scr[1536 + rq * 128 + 2 * p] = dbta; scr[1536 + rq * 128 + 2 * p + 1] = dbtb;
       if (C::LN && lane < 16) {
+        // dgam[k] of lane L: column cbase + 16 k + L, summed over this warp's 32 rows
 #pragma unroll
-        for (int i = 0; i < 8; ++i) scr[768 + warp * 128 + i * 16 + lane] = dgam[i];
+        for (int k = 0; k < 4; ++k) scr[2048 + q * 128 + cbase + k * 16 + lane] = dgam[k];
       }
     }
-    epi_bar_sync();
-    {
-      Pb1[tid] = scr[tid] + scr[128 + tid];
-      Pb2[tid] = scr[256 + tid] + scr[384 + tid];
-      if (tid < C::NOUT) Pb3[tid] = scr[512 + tid] + scr[640 + tid];
+    epi_bar_sync256();
+    if (tid < 128) {
+      Pb1[tid] = (scr[tid] + scr[128 + tid]) + (scr[256 + tid] + scr[384 + tid]);
+      Pb2[tid] = (scr[512 + tid] + scr[640 + tid]) + (scr[768 + tid] + scr[896 + tid]);
+      if (tid < C::NOUT) Pb3[tid] = (scr[1024 + tid] + scr[1152 + tid]) + (scr[1280 + tid] + scr[1408 + tid]);
       if (C::LN) {
-        Pg[tid] = scr[768 + tid] + scr[896 + tid] + scr[1024 + tid] + scr[1152 + tid];
-        Pbeta[tid] = scr[1280 + tid] + scr[1408 + tid];
+        Pg[tid] = (scr[2048 + tid] + scr[2176 + tid]) + (scr[2304 + tid] + scr[2432 + tid]);
+        Pbeta[tid] = (scr[1536 + tid] + scr[1664 + tid]) + (scr[1792 + tid] + scr[1920 + tid]);
       }
     }
     tc_fence_before();
   }
   __syncthreads();
-  if (warp == 8) {
+  if (warp == 12) {
     tc_fence_after();
     tmem_dealloc(tmem, 512);
   }
@@ -678,7 +736,7 @@ __global__ void __launch_bounds__(256) tc_partial_reduce_kernel(const float* __r
   out[i] = s;
 }
 
-template <int MODE> constexpr int smem_a() { return 4 * KB_BYTES + 2 * 2 * KB_BYTES + 3 * BUF_BYTES + 4 * 512 + 256; }
+template <int MODE> constexpr int smem_a() { return 4 * KB_BYTES + 4 * BUF_BYTES + 3 * 512 + 2 * 2048 + 256; }
 template <int MODE> constexpr int smem_b() {
   return nkb1(BCfg<MODE>::K1P) * KB_BYTES + 2 * BUF_BYTES + 3 * KB_BYTES + STG_BYTES + 256;
 }
@@ -706,7 +764,7 @@ int launch_tc_bwd(const fvgn_mlp_desc& d, void* stream) {
     attr_set = true;
   }
   const unsigned grid = (unsigned)d.n_partials;
-  ka<<<grid, NTHREADS, smem_a<MODE>(), (cudaStream_t)stream>>>(d);
+  ka<<<grid, A_THREADS, smem_a<MODE>(), (cudaStream_t)stream>>>(d);
   FVGN_CHECK_LAUNCH();
   kb<<<grid, NTHREADS, smem_b<MODE>(), (cudaStream_t)stream>>>(d);
   FVGN_CHECK_LAUNCH();
@@ -732,8 +790,9 @@ int64_t fvgn_mlp_tc_workspace_bytes(int32_t, int64_t rows) {
 int fvgn_mlp_backward_simt(const fvgn_mlp_desc* d, void* stream);
 
 int fvgn_mlp_backward_tc(const fvgn_mlp_desc* d, void* stream) {
-  if (!d->w_bf16 || !d->workspace) return FVGN_ERR_NULL;
-  if ((((uintptr_t)d->w_bf16) & 15) != 0 || (((uintptr_t)d->workspace) & 1023) != 0) return FVGN_ERR_ALIGN;
+  if (!d->w_bf16 || !d->workspace || !d->z1_img) return FVGN_ERR_NULL;
+  if ((((uintptr_t)d->w_bf16) & 15) != 0 || (((uintptr_t)d->workspace) & 1023) != 0 || (((uintptr_t)d->z1_img) & 1023) != 0)
+    return FVGN_ERR_ALIGN;
   if (d->n_partials != fvgn_mlp_tc_partials(d->mode, d->rows)) return FVGN_ERR_SHAPE;
   if (d->rows == 0) {
     const int64_t pc = fvgn_mlp_param_count(d->mode);

@@ -88,21 +88,47 @@ def _mlp_desc(mode, precision, rows, params, in0, in1=None, idx_s=None, idx_r=No
     return d
 
 
+def _img_buffer(nbytes, device):
+    """1024-B aligned device scratch for bf16 tile images -> (owner tensor, aligned pointer)."""
+    buf = torch.empty(nbytes + 1024, dtype=torch.uint8, device=device)
+    return buf, (buf.data_ptr() + 1023) // 1024 * 1024
+
+
+class Z1Image:
+    """bf16 tile images of the first pre-activation (written by the bf16 forward, consumed by its backward)."""
+
+    def __init__(self, mode, rows, device):
+        nbytes = int(_lib.load().fvgn_mlp_bwd_workspace_bytes(mode, PREC["bf16"], rows))
+        self.buf, self.ptr = _img_buffer(nbytes, device)
+
+
 def mlp_forward(mode, precision, rows, params, in0, in1=None, idx_s=None, idx_r=None, want_out=True, want_res=False,
-                flags=0, packed=None):
+                flags=0, packed=None, z1=None):
+    """z1: a Z1Image to fill (bf16 mode, needed by mlp_backward) or None (inference)."""
     d = _mlp_desc(mode, precision, rows, params, in0, in1, idx_s, idx_r, flags, packed)
     nout = 3 if mode == _lib.FVGN_MLP_DEC else 128
     out = _empty((rows, nout), in0) if want_out else None
     res = _empty((rows, 128), in0) if want_res else None
     d.out, d.out_res = fptr(out, True), fptr(res, True)
+    if z1 is not None and precision == "bf16":
+        d.z1_img = z1.ptr
     _lib.call("fvgn_mlp_forward", ctypes.byref(d), _lib.stream_ptr(in0.device))
     return out, res
 
 
+def new_z1(mode, precision, rows, like):
+    return Z1Image(mode, rows, like.device) if precision == "bf16" else None
+
+
 def mlp_backward(mode, precision, rows, params, in0, in1, idx_s, idx_r, d_out, d_gather=None, d_in0=None, d_in1=None,
-                 flags=0, packed=None):
+                 flags=0, packed=None, z1=None):
     """Runs the fused backward; returns the list of parameter gradients (views of one flat buffer).
-    packed: the bf16 weight image used by the matching forward (bf16 mode); repacked from `params` when None."""
+    packed: the bf16 weight image used by the matching forward (bf16 mode); repacked from `params` when None.
+    z1: the Z1Image the matching bf16 forward filled; when None (stand-alone use) the forward is re-run to make it."""
+    if precision == "bf16" and z1 is None:
+        z1 = new_z1(mode, precision, rows, in0)
+        mlp_forward(mode, precision, rows, params, in0, in1, idx_s, idx_r, want_out=True, want_res=False, flags=flags,
+                    packed=packed, z1=z1)
     d = _mlp_desc(mode, precision, rows, params, in0, in1, idx_s, idx_r, flags, packed)
     lib = _lib.load()
     pc = int(lib.fvgn_mlp_param_count(mode))
@@ -114,9 +140,8 @@ def mlp_backward(mode, precision, rows, params, in0, in1, idx_s, idx_r, d_out, d
     d.partials, d.n_partials, d.d_params = fptr(partials), npart, fptr(flat)
     ws_bytes = int(lib.fvgn_mlp_bwd_workspace_bytes(mode, PREC[precision], rows))
     if ws_bytes > 0:
-        ws = torch.empty(ws_bytes + 1024, dtype=torch.uint8, device=in0.device)
-        d._ws = ws
-        d.workspace = (ws.data_ptr() + 1023) // 1024 * 1024
+        d._ws, d.workspace = _img_buffer(ws_bytes, in0.device)
+        d._z1, d.z1_img = z1, z1.ptr
     _lib.call("fvgn_mlp_backward", ctypes.byref(d), _lib.stream_ptr(in0.device))
     k1 = _MLP_K1[mode]
     nout = 3 if mode == _lib.FVGN_MLP_DEC else 128
@@ -145,8 +170,10 @@ class EncoderFn(torch.autograd.Function):
     def forward(ctx, xn, pos, plan, precision, *params):
         nb, eb = params[:8], params[8:]
         ctx.pk = (_packed(_lib.FVGN_MLP_ENC_NODE, precision, nb), _packed(_lib.FVGN_MLP_ENC_EDGE, precision, eb))
-        node, _ = mlp_forward(_lib.FVGN_MLP_ENC_NODE, precision, plan.N, nb, xn, packed=ctx.pk[0])
-        edge, _ = mlp_forward(_lib.FVGN_MLP_ENC_EDGE, precision, plan.E, eb, xn, pos, plan.edge_s, plan.edge_r, packed=ctx.pk[1])
+        ctx.z1 = (new_z1(_lib.FVGN_MLP_ENC_NODE, precision, plan.N, xn), new_z1(_lib.FVGN_MLP_ENC_EDGE, precision, plan.E, xn))
+        node, _ = mlp_forward(_lib.FVGN_MLP_ENC_NODE, precision, plan.N, nb, xn, packed=ctx.pk[0], z1=ctx.z1[0])
+        edge, _ = mlp_forward(_lib.FVGN_MLP_ENC_EDGE, precision, plan.E, eb, xn, pos, plan.edge_s, plan.edge_r, packed=ctx.pk[1],
+                              z1=ctx.z1[1])
         ctx.plan, ctx.precision = plan, precision
         ctx.save_for_backward(xn, pos, *params)
         return node, edge
@@ -156,9 +183,10 @@ class EncoderFn(torch.autograd.Function):
         xn, pos, *params = ctx.saved_tensors
         plan, precision = ctx.plan, ctx.precision
         gn = mlp_backward(_lib.FVGN_MLP_ENC_NODE, precision, plan.N, params[:8], xn, None, None, None, _c(d_node),
-                          packed=ctx.pk[0])
+                          packed=ctx.pk[0], z1=ctx.z1[0])
         ge = mlp_backward(_lib.FVGN_MLP_ENC_EDGE, precision, plan.E, params[8:], xn, pos, plan.edge_s, plan.edge_r,
-                          _c(d_edge), packed=ctx.pk[1])
+                          _c(d_edge), packed=ctx.pk[1], z1=ctx.z1[1])
+        ctx.z1 = None
         return (None, None, None, None, *gn, *ge)
 
 
@@ -176,15 +204,16 @@ class GnBlockFn(torch.autograd.Function):
         eb, nb = params[:8], params[8:]
         x, e = _c(x), _c(e)
         ctx.pk = (_packed(_lib.FVGN_MLP_EDGE, precision, eb), _packed(_lib.FVGN_MLP_NODE, precision, nb))
+        ctx.z1 = (new_z1(_lib.FVGN_MLP_EDGE, precision, plan.E, x), new_z1(_lib.FVGN_MLP_NODE, precision, plan.N, x))
         agg = adj_reduce(x, plan, 128)
         e_new, e_out = mlp_forward(_lib.FVGN_MLP_EDGE, precision, plan.E, eb, agg, e, plan.edge_s, plan.edge_r,
-                                   want_out=True, want_res=True, packed=ctx.pk[0])
+                                   want_out=True, want_res=True, packed=ctx.pk[0], z1=ctx.z1[0])
         a1 = inc_reduce(e_new, plan, 64)
         del e_new
         a2 = adj_reduce(a1, plan, 64, _lib.FVGN_ADJ_DIV_DST_BY_DEG)
         del a1
         _, x_out = mlp_forward(_lib.FVGN_MLP_NODE, precision, plan.N, nb, a2, x, want_out=False, want_res=True,
-                               packed=ctx.pk[1])
+                               packed=ctx.pk[1], z1=ctx.z1[1])
         ctx.plan, ctx.precision = plan, precision
         ctx.save_for_backward(x, e, agg, a2, *params)
         return x_out, e_out
@@ -199,13 +228,14 @@ class GnBlockFn(torch.autograd.Function):
         d_a2 = _empty((plan.N, 64), x)
         d_x = _empty((plan.N, 128), x)
         g_nb = mlp_backward(_lib.FVGN_MLP_NODE, precision, plan.N, nb, a2, x, None, None, d_x_out, None, d_a2, d_x,
-                            packed=ctx.pk[1])
+                            packed=ctx.pk[1], z1=ctx.z1[1])
         d_a1 = adj_reduce(d_a2, plan, 64, _lib.FVGN_ADJ_DIV_SRC_BY_DEG)
         del d_a2
         d_sr = _empty((plan.E, 256), x)
         d_e = _empty((plan.E, 128), x)
         g_eb = mlp_backward(_lib.FVGN_MLP_EDGE, precision, plan.E, eb, agg, e, plan.edge_s, plan.edge_r, d_e_out, d_a1,
-                            d_sr, d_e, packed=ctx.pk[0])
+                            d_sr, d_e, packed=ctx.pk[0], z1=ctx.z1[0])
+        ctx.z1 = None
         d_agg = inc_reduce(d_sr, plan, 128)
         del d_sr
         adj_reduce(d_agg, plan, 128, _lib.FVGN_ADJ_ACCUMULATE, out=d_x)
@@ -220,8 +250,9 @@ class EdgeBlockFn(torch.autograd.Function):
         x, e = _c(x), _c(e)
         agg = adj_reduce(x, plan, 128)
         ctx.pk = _packed(_lib.FVGN_MLP_EDGE, precision, params)
+        ctx.z1 = new_z1(_lib.FVGN_MLP_EDGE, precision, plan.E, x)
         e_new, _ = mlp_forward(_lib.FVGN_MLP_EDGE, precision, plan.E, params, agg, e, plan.edge_s, plan.edge_r,
-                               flags=_lib.FVGN_MLP_NO_RESIDUAL, packed=ctx.pk)
+                               flags=_lib.FVGN_MLP_NO_RESIDUAL, packed=ctx.pk, z1=ctx.z1)
         ctx.plan, ctx.precision = plan, precision
         ctx.save_for_backward(agg, e, *params)
         return e_new
@@ -233,7 +264,7 @@ class EdgeBlockFn(torch.autograd.Function):
         d_sr = _empty((plan.E, 256), e)
         d_e = _empty((plan.E, 128), e)
         g = mlp_backward(_lib.FVGN_MLP_EDGE, precision, plan.E, params, agg, e, plan.edge_s, plan.edge_r, _c(d_e_new), None,
-                         d_sr, d_e, flags=_lib.FVGN_MLP_NO_RESIDUAL, packed=ctx.pk)
+                         d_sr, d_e, flags=_lib.FVGN_MLP_NO_RESIDUAL, packed=ctx.pk, z1=ctx.z1)
         d_agg = inc_reduce(d_sr, plan, 128)
         d_x = adj_reduce(d_agg, plan, 128)
         return (d_x, d_e, None, None, *g)
@@ -248,8 +279,9 @@ class NodeBlockFn(torch.autograd.Function):
         a1 = inc_reduce(e, plan, 64)
         a2 = adj_reduce(a1, plan, 64, _lib.FVGN_ADJ_DIV_DST_BY_DEG)
         ctx.pk = _packed(_lib.FVGN_MLP_NODE, precision, params)
+        ctx.z1 = new_z1(_lib.FVGN_MLP_NODE, precision, plan.N, x)
         x_new, _ = mlp_forward(_lib.FVGN_MLP_NODE, precision, plan.N, params, a2, x, flags=_lib.FVGN_MLP_NO_RESIDUAL,
-                               packed=ctx.pk)
+                               packed=ctx.pk, z1=ctx.z1)
         ctx.plan, ctx.precision = plan, precision
         ctx.save_for_backward(a2, x, *params)
         return x_new
@@ -261,7 +293,7 @@ class NodeBlockFn(torch.autograd.Function):
         d_a2 = _empty((plan.N, 64), x)
         d_x = _empty((plan.N, 128), x)
         g = mlp_backward(_lib.FVGN_MLP_NODE, precision, plan.N, params, a2, x, None, None, _c(d_x_new), None, d_a2, d_x,
-                         flags=_lib.FVGN_MLP_NO_RESIDUAL, packed=ctx.pk)
+                         flags=_lib.FVGN_MLP_NO_RESIDUAL, packed=ctx.pk, z1=ctx.z1)
         d_a1 = adj_reduce(d_a2, plan, 64, _lib.FVGN_ADJ_DIV_SRC_BY_DEG)
         # transpose of the incidence sum: d_e[f] = [d_a1[s_f] | d_a1[r_f]]
         d_e = torch.cat([d_a1[plan.edge_s.long()], d_a1[plan.edge_r.long()]], 1)
@@ -276,7 +308,8 @@ class DecoderFn(torch.autograd.Function):
     def forward(ctx, x, precision, *params):
         x = _c(x)
         ctx.pk = _packed(_lib.FVGN_MLP_DEC, precision, params)
-        out, _ = mlp_forward(_lib.FVGN_MLP_DEC, precision, x.shape[0], params, x, packed=ctx.pk)
+        ctx.z1 = new_z1(_lib.FVGN_MLP_DEC, precision, x.shape[0], x)
+        out, _ = mlp_forward(_lib.FVGN_MLP_DEC, precision, x.shape[0], params, x, packed=ctx.pk, z1=ctx.z1)
         ctx.precision = precision
         ctx.save_for_backward(x, *params)
         return out
@@ -286,7 +319,7 @@ class DecoderFn(torch.autograd.Function):
         x, *params = ctx.saved_tensors
         d_x = _empty(tuple(x.shape), x)
         g = mlp_backward(_lib.FVGN_MLP_DEC, ctx.precision, x.shape[0], params, x, None, None, None, _c(d_out), None, d_x,
-                         packed=ctx.pk)
+                         packed=ctx.pk, z1=ctx.z1)
         return (d_x, None, *g)
 
 

@@ -82,6 +82,10 @@ typedef struct fvgn_mlp_desc {
   int32_t n_partials;  /* = grid size of the backward kernel, from fvgn_mlp_bwd_partials() */
   float* d_params;     /* [param_count] flat: w1,b1,w2,b2,w3,b3,ln_g,ln_b (deterministic reduction of partials) */
   void* workspace;     /* backward scratch of fvgn_mlp_bwd_workspace_bytes() bytes (bf16 dZ1 tile images), 1024-B aligned */
+  /* FVGN_PREC_BF16 only: bf16 tile images of the first pre-activation Z1 = X W1^T + b1 (one 32 KB pre-swizzled
+   * [128 x 128] tile per 128 rows, fvgn_mlp_bwd_workspace_bytes() bytes, 1024-B aligned).  The forward writes it
+   * when non-NULL; the backward REQUIRES it (it replaces the recomputation of layer 1 from the block inputs). */
+  void* z1_img;
 } fvgn_mlp_desc;
 
 int64_t fvgn_mlp_param_count(int32_t mode);

@@ -52,7 +52,7 @@ def _inputs(mode, rows, nodes, dev, seed=0):
 def _emulate(X, params, bf16):
     q = _bf if bf16 else (lambda t: t)
     gelu = torch.nn.functional.gelu
-    h = gelu(q(X) @ q(params[0]).T + params[1])
+    h = gelu(q(q(X) @ q(params[0]).T + params[1]))   # the bf16 path rounds Z1 to bf16 (it is what the backward reads back)
     h = gelu(q(h) @ q(params[2]).T + params[3])
     y = q(h) @ q(params[4]).T + params[5]
     if len(params) == 8:
