@@ -43,6 +43,13 @@ def _carry(graph, **updates):
     return out
 
 
+def _shadow_of(graph, key, master):
+    """The bf16 shadow attached by the producing kernel, if it still belongs to `master` (the latent may have been
+    replaced, e.g. by the Transolver block); None otherwise (the op then makes its own)."""
+    c = getattr(graph, key, None)
+    return c[1] if (c is not None and c[0] is master) else None
+
+
 class Encoder(nn.Module):
     def __init__(self, node_input_size=128, edge_input_size=128, hidden_size=128):
         super().__init__()
@@ -55,9 +62,10 @@ class Encoder(nn.Module):
         """graph_node.x is the normalised [N,12] feature; the [E,15] relative edge feature of
         importer.py:54-78 is computed inside the edge-encoder kernel from x and pos."""
         plan = GraphPlan.of(graph_node)
-        node_, edge_ = ops.EncoderFn.apply(graph_node.x.contiguous(), graph_node.pos.float().contiguous(), plan,
-                                           _precision(self), *mlp_params(self.nb_encoder), *mlp_params(self.eb_encoder))
-        return _carry(graph_node, x=node_, edge_attr=edge_, _fvgn_plan=plan), node_
+        node_, edge_, nh, eh = ops.EncoderFn.apply(graph_node.x.contiguous(), graph_node.pos.float().contiguous(), plan,
+                                                   _precision(self), *mlp_params(self.nb_encoder), *mlp_params(self.eb_encoder))
+        # bf16 mode: the kernels also emit bf16 shadows of the latents; they travel with the graph as (master, shadow)
+        return _carry(graph_node, x=node_, edge_attr=edge_, _fvgn_plan=plan, _xh=(node_, nh), _eh=(edge_, eh)), node_
 
 
 class GnBlock(nn.Module):
@@ -70,9 +78,10 @@ class GnBlock(nn.Module):
 
     def forward(self, graph_node):
         plan = GraphPlan.of(graph_node)
-        x, e = ops.GnBlockFn.apply(graph_node.x, graph_node.edge_attr, plan, _precision(self),
-                                   *mlp_params(self.eb_module.net), *mlp_params(self.nb_module.net))
-        return _carry(graph_node, x=x, edge_attr=e, _fvgn_plan=plan)
+        xh, eh = _shadow_of(graph_node, "_xh", graph_node.x), _shadow_of(graph_node, "_eh", graph_node.edge_attr)
+        x, e, xh, eh = ops.GnBlockFn.apply(graph_node.x, graph_node.edge_attr, xh, eh, plan, _precision(self),
+                                           *mlp_params(self.eb_module.net), *mlp_params(self.nb_module.net))
+        return _carry(graph_node, x=x, edge_attr=e, _fvgn_plan=plan, _xh=(x, xh), _eh=(e, eh))
 
 
 class Decoder(nn.Module):
@@ -84,7 +93,8 @@ class Decoder(nn.Module):
                                                            lay_norm=False, num_layer=2)
 
     def forward(self, latent_graph_node=None):
-        return ops.DecoderFn.apply(latent_graph_node.x, _precision(self), *mlp_params(self.node_decode_module))
+        xh = _shadow_of(latent_graph_node, "_xh", latent_graph_node.x)
+        return ops.DecoderFn.apply(latent_graph_node.x, xh, _precision(self), *mlp_params(self.node_decode_module))
 
 
 class EncoderProcesserDecoder(nn.Module):

@@ -65,13 +65,24 @@ static int check_common(const fvgn_mlp_desc* d) {
   if (!d) return FVGN_ERR_NULL;
   if (d->mode < FVGN_MLP_EDGE || d->mode > FVGN_MLP_DEC) return FVGN_ERR_UNSUPPORTED;
   if (d->rows < 0) return FVGN_ERR_SHAPE;
-  if (!d->in0 || !d->w1 || !d->b1 || !d->w2 || !d->b2 || !d->w3 || !d->b3) return FVGN_ERR_NULL;
+  if (!d->w1 || !d->b1 || !d->w2 || !d->b2 || !d->w3 || !d->b3) return FVGN_ERR_NULL;
   if (d->mode != FVGN_MLP_DEC && (!d->ln_g || !d->ln_b)) return FVGN_ERR_NULL;
-  if ((d->mode == FVGN_MLP_EDGE || d->mode == FVGN_MLP_ENC_EDGE) && (!d->idx_s || !d->idx_r || !d->in1)) return FVGN_ERR_NULL;
-  if (d->mode == FVGN_MLP_NODE && !d->in1) return FVGN_ERR_NULL;
+  // bf16 mode reads the layer-1 operands of EDGE / NODE / DEC from the bf16 shadows; fp32 in0 / in1 are then optional
+  const bool shadow = d->precision == FVGN_PREC_BF16 &&
+                      (d->mode == FVGN_MLP_EDGE || d->mode == FVGN_MLP_NODE || d->mode == FVGN_MLP_DEC);
+  if (shadow) {
+    if (!d->in0h) return FVGN_ERR_NULL;
+    if (d->mode != FVGN_MLP_DEC && !d->in1h) return FVGN_ERR_NULL;
+    if (!fvgn_aligned16(d->in0h) || !fvgn_aligned16(d->in1h)) return FVGN_ERR_ALIGN;
+  } else {
+    if (!d->in0) return FVGN_ERR_NULL;
+    if ((d->mode == FVGN_MLP_EDGE || d->mode == FVGN_MLP_ENC_EDGE || d->mode == FVGN_MLP_NODE) && !d->in1) return FVGN_ERR_NULL;
+  }
+  if ((d->mode == FVGN_MLP_EDGE || d->mode == FVGN_MLP_ENC_EDGE) && (!d->idx_s || !d->idx_r)) return FVGN_ERR_NULL;
   if (!fvgn_aligned16(d->in0) || !fvgn_aligned16(d->in1) || !fvgn_aligned16(d->out) || !fvgn_aligned16(d->out_res) ||
       !fvgn_aligned16(d->d_out) || !fvgn_aligned16(d->d_gather) || !fvgn_aligned16(d->d_in0) ||
-      !fvgn_aligned16(d->d_in1) || !fvgn_aligned16(d->ln_g) || !fvgn_aligned16(d->ln_b))
+      !fvgn_aligned16(d->d_in1) || !fvgn_aligned16(d->ln_g) || !fvgn_aligned16(d->ln_b) || !fvgn_aligned16(d->outh) ||
+      !fvgn_aligned16(d->out_resh) || !fvgn_aligned16(d->d_in0h))
     return FVGN_ERR_ALIGN;
   return FVGN_OK;
 }
@@ -79,7 +90,8 @@ static int check_common(const fvgn_mlp_desc* d) {
 extern "C" int fvgn_mlp_forward(const fvgn_mlp_desc* d, void* stream) {
   int rc = check_common(d);
   if (rc) return rc;
-  if ((d->mode == FVGN_MLP_EDGE || d->mode == FVGN_MLP_NODE) ? (!d->out_res && !d->out) : !d->out) return FVGN_ERR_NULL;
+  if ((d->mode == FVGN_MLP_EDGE || d->mode == FVGN_MLP_NODE) ? (!d->out_res && !d->out && !d->outh) : !d->out) return FVGN_ERR_NULL;
+  if (d->out_res && !d->in1) return FVGN_ERR_NULL;  // the residual is added from the fp32 stream
   if (d->rows == 0) return FVGN_OK;
   if (d->precision == FVGN_PREC_FP32) return fvgn_mlp_forward_simt(d, stream);
 #ifndef FVGN_EMU
@@ -92,7 +104,8 @@ extern "C" int fvgn_mlp_backward(const fvgn_mlp_desc* d, void* stream) {
   int rc = check_common(d);
   if (rc) return rc;
   if (!d->d_out || !d->partials || !d->d_params || d->n_partials < 1) return FVGN_ERR_NULL;
-  if ((d->mode == FVGN_MLP_EDGE || d->mode == FVGN_MLP_NODE) && (!d->d_in0 || !d->d_in1)) return FVGN_ERR_NULL;
+  if ((d->mode == FVGN_MLP_EDGE || d->mode == FVGN_MLP_NODE) && ((!d->d_in0 && !d->d_in0h) || !d->d_in1)) return FVGN_ERR_NULL;
+  if (d->d_in0h && !(d->mode == FVGN_MLP_EDGE && d->precision == FVGN_PREC_BF16)) return FVGN_ERR_UNSUPPORTED;
   if (d->mode == FVGN_MLP_DEC && !d->d_in0) return FVGN_ERR_NULL;
   if (d->precision == FVGN_PREC_FP32) {
     if (d->n_partials != fvgn_mlp_simt_partials(d->rows)) return FVGN_ERR_SHAPE;

@@ -18,18 +18,16 @@ using namespace tc;
 
 namespace {
 
-constexpr int NTHREADS = 544;  // 8 epilogue warps (two tile pipelines) + 8 producer warps (two chunk teams) + 1 MMA warp
+constexpr int NTHREADS = 416;  // 8 epilogue warps (two tile pipelines) + 4 producer warps + 1 MMA warp
 
 template <int MODE> struct TCfg;
-template <> struct TCfg<FVGN_MLP_EDGE> { static constexpr int K1 = 384, K1P = 384, NOUT = 128, NSTAGE = 3; static constexpr bool LN = true; };
-template <> struct TCfg<FVGN_MLP_NODE> { static constexpr int K1 = 192, K1P = 192, NOUT = 128, NSTAGE = 6; static constexpr bool LN = true; };
+template <> struct TCfg<FVGN_MLP_EDGE> { static constexpr int K1 = 384, K1P = 384, NOUT = 128, NSTAGE = 2; static constexpr bool LN = true; };
+template <> struct TCfg<FVGN_MLP_NODE> { static constexpr int K1 = 192, K1P = 192, NOUT = 128, NSTAGE = 4; static constexpr bool LN = true; };
 template <> struct TCfg<FVGN_MLP_ENC_NODE> { static constexpr int K1 = 12, K1P = 16, NOUT = 128, NSTAGE = 4; static constexpr bool LN = true; };
 template <> struct TCfg<FVGN_MLP_ENC_EDGE> { static constexpr int K1 = 15, K1P = 16, NOUT = 128, NSTAGE = 4; static constexpr bool LN = true; };
 template <> struct TCfg<FVGN_MLP_DEC> { static constexpr int K1 = 128, K1P = 128, NOUT = 3, NSTAGE = 4; static constexpr bool LN = false; };
 
-constexpr int STG_COLS = 8;                        // columns per staged store pass
-constexpr int STG_LD = STG_COLS + 4;               // padded row (floats)
-constexpr int STG_BYTES = 8 * 32 * STG_LD * 4;     // 8 epilogue warps x 32 rows
+constexpr int STG_BYTES = 8 * WSTG_BYTES;  // one wide staging tile per epilogue warp
 
 template <int MODE> constexpr int smem_bytes() {
   return image_bytes(TCfg<MODE>::K1P) + TCfg<MODE>::NSTAGE * KB_BYTES + STG_BYTES + 5 * 512 + 256;
@@ -75,6 +73,10 @@ __global__ void pack_weights_kernel(const float* __restrict__ w1, const float* _
 // L3: T2[0:64] -> T1, and the NEXT tile of the pipeline runs its layer 1 into T2 while the epilogue still drains T1.
 // MMA issue order per tile pair:  L2(P0) L2(P1) L3(P0) L1'(P0) L3(P1) L1'(P1)   (L1' = layer 1 of the following pair),
 // so loads, tensor work and the three epilogues of different tiles overlap.
+//
+// Memory side: layer-1 operands come from bf16 shadows (8 x 16 B per thread per chunk, held in registers two chunks
+// ahead of the ring); every result leaves through a 4 KB swizzled staging tile per warp as 128-B row segments
+// (Z1 image: one 4 KB bulk store per 64 columns; fp32 residual stream and bf16 shadows: 4 rows per warp instruction).
 template <int MODE>
 __global__ void __launch_bounds__(NTHREADS, 1) mlp_tc_fwd_kernel(const fvgn_mlp_desc d) {
   using C = TCfg<MODE>;
@@ -84,8 +86,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) mlp_tc_fwd_kernel(const fvgn_mlp_
   FVGN_DYN_SMEM(smem);
   uint8_t* w_img = smem;
   uint8_t* ring = w_img + image_bytes(C::K1P);
-  float* stg = reinterpret_cast<float*>(ring + NSTAGE * KB_BYTES);
-  float* sb1 = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(stg) + STG_BYTES);
+  uint8_t* stg = ring + NSTAGE * KB_BYTES;
+  float* sb1 = reinterpret_cast<float*>(stg + STG_BYTES);
   float* sb2 = sb1 + 128;
   float* sb3 = sb2 + 128;
   float* sg = sb3 + 128;
@@ -105,7 +107,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) mlp_tc_fwd_kernel(const fvgn_mlp_
   if (tid == 0) {
     mbar_init(BAR(B_W), 1);
     for (int s = 0; s < NSTAGE; ++s) {
-      mbar_init(BAR(B_FULL + s), 4);   // one elected lane per producer warp of the team that fills the stage
+      mbar_init(BAR(B_FULL + s), 4);   // one elected lane per producer warp
       mbar_init(BAR(B_EMPTY + s), 1);  // tcgen05.commit
     }
     for (int p = 0; p < 2; ++p) {
@@ -122,13 +124,13 @@ __global__ void __launch_bounds__(NTHREADS, 1) mlp_tc_fwd_kernel(const fvgn_mlp_
     sg[i] = C::LN ? d.ln_g[i] : 1.f;
     sbeta[i] = C::LN ? d.ln_b[i] : 0.f;
   }
-  if (warp == 16) tmem_alloc(smem_u32(tmem_slot), 512);
+  if (warp == 12) tmem_alloc(smem_u32(tmem_slot), 512);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = *tmem_slot;
 
-  if (warp == 16) {
+  if (warp == 12) {
     // =============================================================== MMA issuer (+ weight loader)
     if (lane == 0) {
       constexpr uint32_t img_bytes = (uint32_t)image_bytes(C::K1P);
@@ -184,36 +186,57 @@ __global__ void __launch_bounds__(NTHREADS, 1) mlp_tc_fwd_kernel(const fvgn_mlp_
     }
     __syncwarp();
   } else if (warp >= 8) {
-    // =============================================================== producers: team (warp-8)/4 fills every other chunk
-    const int team = (warp - 8) >> 2, pw = (warp - 8) & 3;
+    // =============================================================== producers (4 warps)
+    const int pw = warp - 8;
     uint32_t it = 0;
-    TileIdx idx, idx_next;
-    load_tile_idx<MODE>(d, (int64_t)blockIdx.x * TILE_M, pw, lane, idx);
-    for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
-      const int64_t row0 = tile * TILE_M;
-      load_tile_idx<MODE>(d, (tile + gridDim.x) * TILE_M, pw, lane, idx_next);  // rows past the end load nothing
-      for (int kb = 0; kb < NKB1; ++kb, ++it) {
-        if ((int)(it & 1) != team) continue;
+    if constexpr (mode_has_shadow(MODE)) {
+      // chunks are held in registers (2-3 deep) ahead of the ring
+      produce_tiles_h<MODE, NKB1>(d, ntiles, pw, lane, [&](const ChunkRegs& c, uint32_t, int) {
         const int s = it % NSTAGE;
         mbar_wait(BAR(B_EMPTY + s), ((it / NSTAGE) & 1) ^ 1);
-        produce_chunk<MODE>(d, row0, kb, ring + s * KB_BYTES, pw, lane, idx);
+        store_chunk_h(ring + s * KB_BYTES, pw, lane, c);
         fence_proxy_async();
         __syncwarp();
         if (lane == 0) mbar_arrive(BAR(B_FULL + s));
+        ++it;
+      });
+    } else {
+      TileIdx idx;
+      for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+        const int64_t row0 = tile * TILE_M;
+        for (int kb = 0; kb < NKB1; ++kb, ++it) {
+          const int s = it % NSTAGE;
+          mbar_wait(BAR(B_EMPTY + s), ((it / NSTAGE) & 1) ^ 1);
+          produce_chunk<MODE>(d, row0, kb, ring + s * KB_BYTES, pw, lane, idx);
+          fence_proxy_async();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(BAR(B_FULL + s));
+        }
       }
-      idx = idx_next;
     }
   } else {
     // =============================================================== epilogue: pipeline p = warp / 4, thread <-> row
     const int p = warp >> 2, q = warp & 3;
     const uint32_t lane_base = (uint32_t)(q * 32) << 16;
     const int rloc = q * 32 + lane;
-    float* mystg = stg + warp * 32 * STG_LD;
+    uint8_t* mystg = stg + warp * WSTG_BYTES;
+    const int orow = lane >> 3, oseg = lane & 7;  // write-out mapping: 4 rows x 8 x 16 B per warp instruction
+    const float* resid = (MODE == FVGN_MLP_EDGE || MODE == FVGN_MLP_NODE) ? d.in1 : nullptr;
+    const bool do_res = resid && d.out_res;
+    bool stg_busy = false;  // a bulk store may still be reading the staging tile
     uint32_t ph1 = 0, ph23 = 0;
     for (int64_t i = p; i < ntl; i += 2) {
-      const int64_t row0 = (blockIdx.x + i * gridDim.x) * TILE_M;
+      const int64_t tile = blockIdx.x + i * gridDim.x;
+      const int64_t row0 = tile * TILE_M;
+      const int64_t wrow0 = row0 + q * 32;  // first row of this warp
       const uint32_t t1 = tmem + lane_base + 256 * (uint32_t)p + 128 * (uint32_t)((i >> 1) & 1);
       const uint32_t t2 = tmem + lane_base + 256 * (uint32_t)p + 128 * (uint32_t)(((i >> 1) & 1) ^ 1);
+      if (do_res && wrow0 + lane < d.rows) {
+        // the fp32 residual row is first touched ~3 epilogue passes from now: pull it into L2 meanwhile
+        const float* rp = resid + (size_t)(wrow0 + lane) * 128;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) prefetch_l2(rp + 32 * k);
+      }
       // ---- hidden layers: +bias, GELU, bf16 written in place over the accumulator's lower 64 columns
 #pragma unroll 1
       for (int layer = 0; layer < 2; ++layer) {
@@ -227,9 +250,10 @@ __global__ void __launch_bounds__(NTHREADS, 1) mlp_tc_fwd_kernel(const fvgn_mlp_
         tc_fence_after();
         const uint32_t acc = layer == 0 ? t1 : t2;
         const float* bias = layer == 0 ? sb1 : sb2;
-        // layer 1 only: Z1 is rounded to bf16 (what the backward reads back) and stored as a pre-swizzled tile image
+        // layer 1 only: Z1 is rounded to bf16 (what the backward reads back) and stored as a pre-swizzled tile image;
+        // this warp's 32 rows x 64 columns are 4 KB contiguous in the image (same XOR pattern as the staging tile)
         uint8_t* zimg = (layer == 0 && d.z1_img)
-                            ? reinterpret_cast<uint8_t*>(d.z1_img) + (size_t)(row0 / TILE_M) * (2 * KB_BYTES) : nullptr;
+                            ? reinterpret_cast<uint8_t*>(d.z1_img) + (size_t)tile * (2 * KB_BYTES) + q * WSTG_BYTES : nullptr;
         for_each_chunk16(acc, [&](int c0, uint32_t (&r)[16]) {
           uint32_t w[8];
           float z[16];
@@ -250,9 +274,20 @@ __global__ void __launch_bounds__(NTHREADS, 1) mlp_tc_fwd_kernel(const fvgn_mlp_
               z[2 * j + 1] = bf16_hi(zw[j]);
             }
             if (zimg) {
-              const int kb = c0 >> 6, chunk = (c0 & 63) >> 3;
-              *reinterpret_cast<uint4*>(zimg + kb * KB_BYTES + sw128_off(rloc, chunk)) = make_uint4(zw[0], zw[1], zw[2], zw[3]);
-              *reinterpret_cast<uint4*>(zimg + kb * KB_BYTES + sw128_off(rloc, chunk + 1)) = make_uint4(zw[4], zw[5], zw[6], zw[7]);
+              const int ch = (c0 & 63) >> 3;
+              if (ch == 0 && stg_busy) {  // previous bulk store must have finished reading the staging tile
+                if (lane == 0) bulk_wait_read0();
+                __syncwarp();
+                stg_busy = false;
+              }
+              *reinterpret_cast<uint4*>(wstg_at(mystg, lane, ch)) = make_uint4(zw[0], zw[1], zw[2], zw[3]);
+              *reinterpret_cast<uint4*>(wstg_at(mystg, lane, ch + 1)) = make_uint4(zw[4], zw[5], zw[6], zw[7]);
+              if (ch == 6) {  // 64 columns staged: one 4 KB bulk store
+                fence_proxy_async();
+                __syncwarp();
+                if (lane == 0) bulk_s2g(zimg + (c0 >> 6) * KB_BYTES, smem_u32(mystg), WSTG_BYTES);
+                stg_busy = true;
+              }
             }
           }
 #pragma unroll
@@ -283,57 +318,57 @@ __global__ void __launch_bounds__(NTHREADS, 1) mlp_tc_fwd_kernel(const fvgn_mlp_
         });
         const float mean = sum * (1.0f / 128.0f);
         const float rstd = rsqrtf(fmaxf(sq * (1.0f / 128.0f) - mean * mean, 0.f) + 1e-5f);
-        const float* resid = (MODE == FVGN_MLP_EDGE || MODE == FVGN_MLP_NODE) ? d.in1 : nullptr;
-        const bool do_res = resid && d.out_res;
+        if (stg_busy) {
+          if (lane == 0) bulk_wait_read0();
+          __syncwarp();
+          stg_busy = false;
+        }
+        uint16_t* outh = reinterpret_cast<uint16_t*>(d.outh);
+        uint16_t* out_resh = reinterpret_cast<uint16_t*>(d.out_resh);
 #pragma unroll 1
-        for (int c0 = 0; c0 < 128; c0 += 16) {
-          uint32_t r[16];
-          tmem_ld16(acc + c0, r);
-          // residual rows for this 16-column group: issue the loads before they are needed
-          float4 xr[2][2];
+        for (int c0 = 0; c0 < 128; c0 += 32) {
+          uint32_t r[32];
+          tmem_ld32(acc + c0, r);
+          // residual: 8 passes x (4 rows x 128 B); issued before the normalisation math
+          float4 xr[8];
 #pragma unroll
-          for (int half = 0; half < 2; ++half)
-#pragma unroll
-            for (int pass = 0; pass < 2; ++pass) {
-              const int64_t row = row0 + q * 32 + pass * 16 + (lane >> 1);
-              xr[half][pass] = make_float4(0.f, 0.f, 0.f, 0.f);
-              if (do_res && row < d.rows)
-                xr[half][pass] = __ldg(reinterpret_cast<const float4*>(resid + (size_t)row * 128 + c0 + half * STG_COLS + (lane & 1) * 4));
-            }
+          for (int ps = 0; ps < 8; ++ps) {
+            const int64_t row = wrow0 + ps * 4 + orow;
+            xr[ps] = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (do_res && row < d.rows) xr[ps] = __ldg(reinterpret_cast<const float4*>(resid + (size_t)row * 128 + c0 + oseg * 4));
+          }
           tmem_wait_ld();
 #pragma unroll
-          for (int half = 0; half < 2; ++half) {
-            const int cb = c0 + half * STG_COLS;
+          for (int j = 0; j < 32; j += 4) {
+            const float4 b = *reinterpret_cast<const float4*>(sb3 + c0 + j);
+            const float4 gm = *reinterpret_cast<const float4*>(sg + c0 + j);
+            const float4 bt = *reinterpret_cast<const float4*>(sbeta + c0 + j);
+            float4 y;
+            y.x = (__uint_as_float(r[j + 0]) + b.x - mean) * rstd * gm.x + bt.x;
+            y.y = (__uint_as_float(r[j + 1]) + b.y - mean) * rstd * gm.y + bt.y;
+            y.z = (__uint_as_float(r[j + 2]) + b.z - mean) * rstd * gm.z + bt.z;
+            y.w = (__uint_as_float(r[j + 3]) + b.w - mean) * rstd * gm.w + bt.w;
+            *reinterpret_cast<float4*>(wstg_at(mystg, lane, j >> 2)) = y;
+          }
+          __syncwarp();
 #pragma unroll
-            for (int j = 0; j < STG_COLS; j += 4) {
-              const float4 b = *reinterpret_cast<const float4*>(sb3 + cb + j);
-              const float4 gm = *reinterpret_cast<const float4*>(sg + cb + j);
-              const float4 bt = *reinterpret_cast<const float4*>(sbeta + cb + j);
-              float4 y;
-              y.x = (__uint_as_float(r[half * 8 + j + 0]) + b.x - mean) * rstd * gm.x + bt.x;
-              y.y = (__uint_as_float(r[half * 8 + j + 1]) + b.y - mean) * rstd * gm.y + bt.y;
-              y.z = (__uint_as_float(r[half * 8 + j + 2]) + b.z - mean) * rstd * gm.z + bt.z;
-              y.w = (__uint_as_float(r[half * 8 + j + 3]) + b.w - mean) * rstd * gm.w + bt.w;
-              *reinterpret_cast<float4*>(mystg + lane * STG_LD + j) = y;
-            }
-            __syncwarp();
-            // coalesced write-out: 2 lanes cover the 32 B of one row, 16 rows per instruction
-#pragma unroll
-            for (int pass = 0; pass < 2; ++pass) {
-              const int rr = pass * 16 + (lane >> 1), cc = (lane & 1) * 4;
-              const int64_t row = row0 + q * 32 + rr;
-              if (row < d.rows) {
-                const float4 y = *reinterpret_cast<const float4*>(mystg + rr * STG_LD + cc);
-                const size_t o = (size_t)row * 128 + cb + cc;
-                if (d.out) *reinterpret_cast<float4*>(d.out + o) = y;
-                if (do_res) {
-                  const float4 x = xr[half][pass];
-                  *reinterpret_cast<float4*>(d.out_res + o) = make_float4(x.x + y.x, x.y + y.y, x.z + y.z, x.w + y.w);
-                }
+          for (int ps = 0; ps < 8; ++ps) {
+            const int rr = ps * 4 + orow;
+            const int64_t row = wrow0 + rr;
+            if (row < d.rows) {
+              const float4 y = *reinterpret_cast<const float4*>(wstg_at(mystg, rr, oseg));
+              const size_t o = (size_t)row * 128 + c0 + oseg * 4;
+              if (d.out) *reinterpret_cast<float4*>(d.out + o) = y;
+              if (outh) *reinterpret_cast<uint2*>(outh + o) = make_uint2(pack_bf16(y.x, y.y), pack_bf16(y.z, y.w));
+              if (do_res) {
+                const float4 x = xr[ps];
+                const float4 t = make_float4(x.x + y.x, x.y + y.y, x.z + y.z, x.w + y.w);
+                *reinterpret_cast<float4*>(d.out_res + o) = t;
+                if (out_resh) *reinterpret_cast<uint2*>(out_resh + o) = make_uint2(pack_bf16(t.x, t.y), pack_bf16(t.z, t.w));
               }
             }
-            __syncwarp();
           }
+          __syncwarp();
         }
       } else {
         // decoder: 3 outputs per row, no LayerNorm
@@ -348,9 +383,10 @@ __global__ void __launch_bounds__(NTHREADS, 1) mlp_tc_fwd_kernel(const fvgn_mlp_
       }
       tc_fence_before();
     }
+    if (lane == 0) bulk_wait0();  // the last Z1 bulk store must be done before shared memory is released
   }
   __syncthreads();
-  if (warp == 16) {
+  if (warp == 12) {
     tc_fence_after();
     tmem_dealloc(tmem, 512);
   }

@@ -249,11 +249,14 @@ __global__ void __launch_bounds__(A_THREADS, 1) mlp_tc_bwd_a_kernel(const fvgn_m
             }
           }
           if (MODE == FVGN_MLP_EDGE && d.d_gather) {
+            int gi[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) gi[i] = kb == 0 ? idx.sender(i, lane) : idx.receiver(i, lane);
 #pragma unroll
             for (int i = 0; i < 8; ++i) {
               const int64_t row = row0 + i * 16 + pw * 4 + (lane >> 3);
               if (row < d.rows) {
-                const float* g = d.d_gather + (size_t)(kb == 0 ? idx.s[i] : idx.r[i]) * 64 + seg * 8;
+                const float* g = d.d_gather + (size_t)gi[i] * 64 + seg * 8;
                 const float4 a = __ldg(reinterpret_cast<const float4*>(g)), b = __ldg(reinterpret_cast<const float4*>(g + 4));
                 lo[i] = make_float4(lo[i].x + a.x, lo[i].y + a.y, lo[i].z + a.z, lo[i].w + a.w);
                 hi[i] = make_float4(hi[i].x + b.x, hi[i].y + b.y, hi[i].z + b.z, hi[i].w + b.w);
@@ -528,8 +531,7 @@ __global__ void __launch_bounds__(A_THREADS, 1) mlp_tc_bwd_a_kernel(const fvgn_m
 }
 
 // =============================================================================================== kernel B
-constexpr int STG_LD = 20;                      // staging row: 16 columns + pad (floats)
-constexpr int STG_BYTES = 4 * 32 * STG_LD * 4;  // 4 epilogue warps x 32 rows
+constexpr int STG_BYTES = 4 * WSTG_BYTES;  // one wide staging tile per epilogue warp
 
 template <int MODE>
 __global__ void __launch_bounds__(NTHREADS, 1) mlp_tc_bwd_b_kernel(const fvgn_mlp_desc d) {
@@ -541,8 +543,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) mlp_tc_bwd_b_kernel(const fvgn_ml
   uint8_t* w1 = smem;                               // resident W1 image (NKB1 K-blocks)
   uint8_t* dz = w1 + NKB1 * KB_BYTES;               // 2 x dZ1 tile
   uint8_t* ring = dz + 2 * BUF_BYTES;               // NSTAGE x X chunk
-  float* stg = reinterpret_cast<float*>(ring + NSTAGE * KB_BYTES);
-  uint64_t* bars = reinterpret_cast<uint64_t*>(reinterpret_cast<uint8_t*>(stg) + STG_BYTES);
+  uint8_t* stg = ring + NSTAGE * KB_BYTES;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(stg + STG_BYTES);
   const uint32_t bar0 = smem_u32(bars);
   auto BAR = [&](int i) { return bar0 + 8u * (uint32_t)i; };
   constexpr int B_W = 0, B_XFULL = 1, B_XEMPTY = 4, B_DZFULL = 7, B_DZEMPTY = 9, B_AFULL = 11, B_AFREE = 13;
@@ -550,6 +552,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) mlp_tc_bwd_b_kernel(const fvgn_ml
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int64_t ntiles = (d.rows + TILE_M - 1) / TILE_M;
+  const int64_t ntl = (ntiles - blockIdx.x + gridDim.x - 1) / gridDim.x;
   const int64_t PC = pcount(C::K1, C::NOUT, C::LN);
   float* Pw1 = d.partials + (size_t)blockIdx.x * PC;
   const uint8_t* dz_img = reinterpret_cast<const uint8_t*>(d.workspace);
@@ -621,85 +624,148 @@ __global__ void __launch_bounds__(NTHREADS, 1) mlp_tc_bwd_b_kernel(const fvgn_ml
     }
     __syncwarp();
   } else if (warp >= 4) {
-    // ============================================================ producers: dZ1 tile (bulk copy) + X chunks (gather)
+    // ============================================================ producers: dZ1 tile (bulk copy) + X chunks
     const int pw = warp - 4;
-    uint32_t it = 0, tcount = 0;
-    TileIdx idx;
-    for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++tcount) {
-      const int64_t row0 = tile * TILE_M;
-      load_tile_idx<MODE>(d, row0, pw, lane, idx);
+    uint32_t it = 0;
+    // the dZ1 tile image of the CTA's t-th tile goes into buffer t & 1
+    auto fetch_dz = [&](uint32_t tcount) {
       if (pw == 0 && lane == 0) {
         const int zb = tcount & 1;
+        const int64_t tile = blockIdx.x + (int64_t)tcount * gridDim.x;
         mbar_wait(BAR(B_DZEMPTY + zb), ((tcount >> 1) & 1) ^ 1);
         mbar_expect_tx(BAR(B_DZFULL + zb), BUF_BYTES);
         bulk_g2s(smem_u32(dz + zb * BUF_BYTES), dz_img + (size_t)tile * BUF_BYTES, BUF_BYTES, BAR(B_DZFULL + zb));
       }
-      for (int kb = 0; kb < NKB1; ++kb, ++it) {
+    };
+    if constexpr (mode_has_shadow(MODE)) {
+      produce_tiles_h<MODE, NKB1>(d, ntiles, pw, lane, [&](const ChunkRegs& c, uint32_t tcount, int kb) {
+        if (kb == 0) fetch_dz(tcount);
         const int s = it % NSTAGE;
         mbar_wait(BAR(B_XEMPTY + s), ((it / NSTAGE) & 1) ^ 1);
-        produce_chunk<MODE>(d, row0, kb, ring + s * KB_BYTES, pw, lane, idx);
+        store_chunk_h(ring + s * KB_BYTES, pw, lane, c);
         fence_proxy_async();
         __syncwarp();
         if (lane == 0) mbar_arrive(BAR(B_XFULL + s));
+        ++it;
+      });
+    } else {
+      TileIdx idx;
+      uint32_t tcount = 0;
+      for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++tcount) {
+        const int64_t row0 = tile * TILE_M;
+        fetch_dz(tcount);
+        for (int kb = 0; kb < NKB1; ++kb, ++it) {
+          const int s = it % NSTAGE;
+          mbar_wait(BAR(B_XEMPTY + s), ((it / NSTAGE) & 1) ^ 1);
+          produce_chunk<MODE>(d, row0, kb, ring + s * KB_BYTES, pw, lane, idx);
+          fence_proxy_async();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(BAR(B_XFULL + s));
+        }
       }
     }
   } else {
     // ============================================================ epilogue
     const uint32_t lane_base = (uint32_t)(warp * 32) << 16;
     const int rloc = warp * 32 + lane;
-    float* mystg = stg + warp * 32 * STG_LD;
+    uint8_t* mystg = stg + warp * WSTG_BYTES;
+    const int orow = lane >> 3, oseg = lane & 7;  // write-out mapping: 4 rows x 8 x 16 B per warp instruction
     if (C::DX) {
       uint32_t blk = 0;
       for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
-        const int64_t row0 = tile * TILE_M;
+        const int64_t wrow0 = tile * TILE_M + warp * 32;
         for (int j = 0; j < NKB1; ++j, ++blk) {
           const int ab = blk & 1;
+          const uint32_t tacc = tmem + lane_base + WACC + 64 * ab;
+          const int col0 = 64 * j;  // first input column of this 64-column block
+          // destination of the block (uniform: boundaries are multiples of 64)
+          float* dst;
+          int ld, colo;
+          bool add_res = false, to_bf16 = false;
+          if (MODE == FVGN_MLP_EDGE) {
+            if (col0 < 256) { dst = d.d_in0; ld = 256; colo = col0; to_bf16 = d.d_in0h != nullptr; }
+            else { dst = d.d_in1; ld = 128; colo = col0 - 256; add_res = resid; }
+          } else if (MODE == FVGN_MLP_NODE) {
+            if (col0 < 64) { dst = d.d_in0; ld = 64; colo = col0; }
+            else { dst = d.d_in1; ld = 128; colo = col0 - 64; add_res = resid; }
+          } else {
+            dst = d.d_in0; ld = 128; colo = col0;
+          }
+          // residual gradient of this block (2 x 8 passes x 16 B per lane would be 64 registers: one half at a time)
+          float4 g[8];
+#pragma unroll
+          for (int ps = 0; ps < 8; ++ps) {
+            const int64_t row = wrow0 + ps * 4 + orow;
+            g[ps] = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (add_res && row < d.rows) g[ps] = __ldg(reinterpret_cast<const float4*>(d.d_out + (size_t)row * 128 + colo + oseg * 4));
+          }
           mbar_wait(BAR(B_AFULL + ab), (blk >> 1) & 1);
           tc_fence_after();
-          for_each_chunk16<64>(tmem + lane_base + WACC + 64 * ab, [&](int c0, uint32_t (&r)[16]) {
-            const int col0 = 64 * j + c0;  // first input column of this 16-column group
-            // which destination does this group go to (uniform over the group: boundaries are multiples of 64)
-            float* dst;
-            int ld, colo;
-            bool add_res = false;
-            if (MODE == FVGN_MLP_EDGE) {
-              if (col0 < 256) { dst = d.d_in0; ld = 256; colo = col0; }
-              else { dst = d.d_in1; ld = 128; colo = col0 - 256; add_res = resid; }
-            } else if (MODE == FVGN_MLP_NODE) {
-              if (col0 < 64) { dst = d.d_in0; ld = 64; colo = col0; }
-              else { dst = d.d_in1; ld = 128; colo = col0 - 64; add_res = resid; }
-            } else {
-              dst = d.d_in0; ld = 128; colo = col0;
-            }
-            // residual gradient rows: issue the loads before the staging round trip
-            float4 g[4];
+          if (to_bf16) {
+            // 64 columns -> 128 B of bf16 per row: one staging tile, one coalesced pass
+            uint32_t r[32];
 #pragma unroll
-            for (int pass = 0; pass < 4; ++pass) {
-              const int64_t row = row0 + warp * 32 + pass * 8 + (lane >> 2);
-              g[pass] = make_float4(0.f, 0.f, 0.f, 0.f);
-              if (add_res && row < d.rows)
-                g[pass] = __ldg(reinterpret_cast<const float4*>(d.d_out + (size_t)row * 128 + colo + (lane & 3) * 4));
-            }
+            for (int half = 0; half < 2; ++half) {
+              tmem_ld32(tacc + 32 * half, r);
+              tmem_wait_ld();
 #pragma unroll
-            for (int q = 0; q < 4; ++q)
-              *reinterpret_cast<float4*>(mystg + lane * STG_LD + 4 * q) =
-                  make_float4(__uint_as_float(r[4 * q]), __uint_as_float(r[4 * q + 1]), __uint_as_float(r[4 * q + 2]),
-                              __uint_as_float(r[4 * q + 3]));
+              for (int k = 0; k < 4; ++k)
+                *reinterpret_cast<uint4*>(wstg_at(mystg, lane, half * 4 + k)) =
+                    make_uint4(pack_bf16(__uint_as_float(r[8 * k]), __uint_as_float(r[8 * k + 1])),
+                               pack_bf16(__uint_as_float(r[8 * k + 2]), __uint_as_float(r[8 * k + 3])),
+                               pack_bf16(__uint_as_float(r[8 * k + 4]), __uint_as_float(r[8 * k + 5])),
+                               pack_bf16(__uint_as_float(r[8 * k + 6]), __uint_as_float(r[8 * k + 7])));
+            }
+            tc_fence_before();
+            mbar_arrive(BAR(B_AFREE + ab));
             __syncwarp();
+            uint8_t* dh = reinterpret_cast<uint8_t*>(d.d_in0h);
 #pragma unroll
-            for (int pass = 0; pass < 4; ++pass) {
-              const int rr = pass * 8 + (lane >> 2), cc = (lane & 3) * 4;
-              const int64_t row = row0 + warp * 32 + rr;
-              if (row < d.rows) {
-                float4 v = *reinterpret_cast<const float4*>(mystg + rr * STG_LD + cc);
-                v = make_float4(v.x + g[pass].x, v.y + g[pass].y, v.z + g[pass].z, v.w + g[pass].w);
-                *reinterpret_cast<float4*>(dst + (size_t)row * ld + colo + cc) = v;
+            for (int ps = 0; ps < 8; ++ps) {
+              const int rr = ps * 4 + orow;
+              const int64_t row = wrow0 + rr;
+              if (row < d.rows)
+                *reinterpret_cast<uint4*>(dh + (size_t)row * 512 + colo * 2 + oseg * 16) =
+                    *reinterpret_cast<const uint4*>(wstg_at(mystg, rr, oseg));
+            }
+            __syncwarp();
+          } else {
+#pragma unroll 1
+            for (int half = 0; half < 2; ++half) {
+              uint32_t r[32];
+              tmem_ld32(tacc + 32 * half, r);
+              if (half == 1 && add_res) {
+#pragma unroll
+                for (int ps = 0; ps < 8; ++ps) {
+                  const int64_t row = wrow0 + ps * 4 + orow;
+                  if (row < d.rows)
+                    g[ps] = __ldg(reinterpret_cast<const float4*>(d.d_out + (size_t)row * 128 + colo + 32 + oseg * 4));
+                }
               }
+              tmem_wait_ld();
+#pragma unroll
+              for (int k = 0; k < 8; ++k)
+                *reinterpret_cast<float4*>(wstg_at(mystg, lane, k)) =
+                    make_float4(__uint_as_float(r[4 * k]), __uint_as_float(r[4 * k + 1]), __uint_as_float(r[4 * k + 2]),
+                                __uint_as_float(r[4 * k + 3]));
+              if (half == 1) {
+                tc_fence_before();
+                mbar_arrive(BAR(B_AFREE + ab));
+              }
+              __syncwarp();
+#pragma unroll
+              for (int ps = 0; ps < 8; ++ps) {
+                const int rr = ps * 4 + orow;
+                const int64_t row = wrow0 + rr;
+                if (row < d.rows) {
+                  float4 v = *reinterpret_cast<const float4*>(wstg_at(mystg, rr, oseg));
+                  v = make_float4(v.x + g[ps].x, v.y + g[ps].y, v.z + g[ps].z, v.w + g[ps].w);
+                  *reinterpret_cast<float4*>(dst + (size_t)row * ld + colo + 32 * half + oseg * 4) = v;
+                }
+              }
+              __syncwarp();
             }
-            __syncwarp();
-          });
-          tc_fence_before();
-          mbar_arrive(BAR(B_AFREE + ab));
+          }
         }
       }
     }

@@ -13,9 +13,31 @@
 // Mapping: W/4 lanes per row, one float4 per lane (a 512-B row is one fully coalesced warp access).
 #include "common.cuh"
 
-template <int W>
-__global__ void __launch_bounds__(256) adj_reduce_kernel(const float* __restrict__ src, const int32_t* __restrict__ ptr,
-                                                         const int32_t* __restrict__ nbr, float* __restrict__ dst,
+// element-type helpers: 4 consecutive elements per lane, fp32 (16 B) or bf16 (8 B)
+#ifndef FVGN_EMU
+#include <cuda_bf16.h>
+#endif
+struct T_F32 { typedef float elem; };
+struct T_BF16 { typedef uint16_t elem; };
+template <class T> __device__ __forceinline__ float4 ldv(const typename T::elem* p);
+template <> __device__ __forceinline__ float4 ldv<T_F32>(const float* p) { return ld4(p); }
+template <class T> __device__ __forceinline__ void stv(typename T::elem* p, float4 v);
+template <> __device__ __forceinline__ void stv<T_F32>(float* p, float4 v) { st4(p, v); }
+#ifndef FVGN_EMU
+template <> __device__ __forceinline__ float4 ldv<T_BF16>(const uint16_t* p) {
+  const uint2 w = *reinterpret_cast<const uint2*>(p);
+  return make_float4(__uint_as_float(w.x << 16), __uint_as_float(w.x & 0xFFFF0000u), __uint_as_float(w.y << 16),
+                     __uint_as_float(w.y & 0xFFFF0000u));
+}
+template <> __device__ __forceinline__ void stv<T_BF16>(uint16_t* p, float4 v) {
+  __nv_bfloat162 a = __floats2bfloat162_rn(v.x, v.y), b = __floats2bfloat162_rn(v.z, v.w);
+  *reinterpret_cast<uint2*>(p) = make_uint2(*reinterpret_cast<uint32_t*>(&a), *reinterpret_cast<uint32_t*>(&b));
+}
+#endif
+
+template <int W, class TS, class TD>
+__global__ void __launch_bounds__(256) adj_reduce_kernel(const typename TS::elem* __restrict__ src, const int32_t* __restrict__ ptr,
+                                                         const int32_t* __restrict__ nbr, typename TD::elem* __restrict__ dst,
                                                          int64_t n, int flags) {
   constexpr int LPR = W / 4;
   constexpr int RPB = 256 / LPR;
@@ -32,7 +54,7 @@ __global__ void __launch_bounds__(256) adj_reduce_kernel(const float* __restrict
 #pragma unroll
     for (int u = 0; u < 4; ++u) j[u] = nbr[t + u];
 #pragma unroll
-    for (int u = 0; u < 4; ++u) v[u] = ld4(src + (size_t)j[u] * W + lane * 4);
+    for (int u = 0; u < 4; ++u) v[u] = ldv<TS>(src + (size_t)j[u] * W + lane * 4);
 #pragma unroll
     for (int u = 0; u < 4; ++u) {
       if (div_src) {
@@ -44,7 +66,7 @@ __global__ void __launch_bounds__(256) adj_reduce_kernel(const float* __restrict
   }
   for (; t < end; ++t) {
     const int j = nbr[t];
-    float4 v = ld4(src + (size_t)j * W + lane * 4);
+    float4 v = ldv<TS>(src + (size_t)j * W + lane * 4);
     if (div_src) {
       const float d = (float)max(ptr[j + 1] - ptr[j], 1);
       v.x /= d; v.y /= d; v.z /= d; v.w /= d;
@@ -55,15 +77,15 @@ __global__ void __launch_bounds__(256) adj_reduce_kernel(const float* __restrict
     const float d = (float)max(end - beg, 1);
     acc.x /= d; acc.y /= d; acc.z /= d; acc.w /= d;
   }
-  float* o = dst + (size_t)row * W + lane * 4;
-  if (flags & FVGN_ADJ_ACCUMULATE) acc = add4(ld4(o), acc);
-  st4(o, acc);
+  typename TD::elem* o = dst + (size_t)row * W + lane * 4;
+  if (flags & FVGN_ADJ_ACCUMULATE) acc = add4(ldv<TD>(o), acc);
+  stv<TD>(o, acc);
 }
 
 // dst[i, 0:W] = sum over incidence entries (edge f, role) of src[f, role*W : role*W + W]
-template <int W>
-__global__ void __launch_bounds__(256) inc_reduce_kernel(const float* __restrict__ src, const int32_t* __restrict__ ptr,
-                                                         const int32_t* __restrict__ code, float* __restrict__ dst,
+template <int W, class TS, class TD>
+__global__ void __launch_bounds__(256) inc_reduce_kernel(const typename TS::elem* __restrict__ src, const int32_t* __restrict__ ptr,
+                                                         const int32_t* __restrict__ code, typename TD::elem* __restrict__ dst,
                                                          int64_t n) {
   constexpr int LPR = W / 4;
   constexpr int RPB = 256 / LPR;
@@ -79,15 +101,55 @@ __global__ void __launch_bounds__(256) inc_reduce_kernel(const float* __restrict
 #pragma unroll
     for (int u = 0; u < 4; ++u) c[u] = code[t + u];
 #pragma unroll
-    for (int u = 0; u < 4; ++u) v[u] = ld4(src + (size_t)(c[u] >> 1) * (2 * W) + (c[u] & 1) * W + lane * 4);
+    for (int u = 0; u < 4; ++u) v[u] = ldv<TS>(src + (size_t)(c[u] >> 1) * (2 * W) + (c[u] & 1) * W + lane * 4);
 #pragma unroll
     for (int u = 0; u < 4; ++u) acc = add4(acc, v[u]);
   }
   for (; t < end; ++t) {
     const int c = code[t];
-    acc = add4(acc, ld4(src + (size_t)(c >> 1) * (2 * W) + (c & 1) * W + lane * 4));
+    acc = add4(acc, ldv<TS>(src + (size_t)(c >> 1) * (2 * W) + (c & 1) * W + lane * 4));
   }
-  st4(dst + (size_t)row * W + lane * 4, acc);
+  stv<TD>(dst + (size_t)row * W + lane * 4, acc);
+}
+
+template <class TS, class TD>
+static int launch_adj(const void* src, const int32_t* ptr, const int32_t* nbr, void* dst, int64_t n_rows, int32_t width,
+                      int32_t flags, void* stream) {
+  const typename TS::elem* s = reinterpret_cast<const typename TS::elem*>(src);
+  typename TD::elem* o = reinterpret_cast<typename TD::elem*>(dst);
+  if (width == 128) {
+    const unsigned grid = (unsigned)((n_rows + 7) / 8);
+    auto kern = adj_reduce_kernel<128, TS, TD>;
+    FVGN_LAUNCH_SEQ(kern, grid, 256, 0, stream, s, ptr, nbr, o, n_rows, flags);
+  } else if (width == 64) {
+    const unsigned grid = (unsigned)((n_rows + 15) / 16);
+    auto kern = adj_reduce_kernel<64, TS, TD>;
+    FVGN_LAUNCH_SEQ(kern, grid, 256, 0, stream, s, ptr, nbr, o, n_rows, flags);
+  } else {
+    return FVGN_ERR_UNSUPPORTED;
+  }
+  FVGN_CHECK_LAUNCH();
+  return FVGN_OK;
+}
+
+template <class TS, class TD>
+static int launch_inc(const void* src, const int32_t* ptr, const int32_t* code, void* dst, int64_t n_rows, int32_t width,
+                      void* stream) {
+  const typename TS::elem* s = reinterpret_cast<const typename TS::elem*>(src);
+  typename TD::elem* o = reinterpret_cast<typename TD::elem*>(dst);
+  if (width == 128) {
+    const unsigned grid = (unsigned)((n_rows + 7) / 8);
+    auto kern = inc_reduce_kernel<128, TS, TD>;
+    FVGN_LAUNCH_SEQ(kern, grid, 256, 0, stream, s, ptr, code, o, n_rows);
+  } else if (width == 64) {
+    const unsigned grid = (unsigned)((n_rows + 15) / 16);
+    auto kern = inc_reduce_kernel<64, TS, TD>;
+    FVGN_LAUNCH_SEQ(kern, grid, 256, 0, stream, s, ptr, code, o, n_rows);
+  } else {
+    return FVGN_ERR_UNSUPPORTED;
+  }
+  FVGN_CHECK_LAUNCH();
+  return FVGN_OK;
 }
 
 extern "C" int fvgn_adj_reduce(const float* src, const int32_t* ptr, const int32_t* nbr, float* dst, int64_t n_rows,
@@ -95,17 +157,7 @@ extern "C" int fvgn_adj_reduce(const float* src, const int32_t* ptr, const int32
   if (n_rows < 0) return FVGN_ERR_SHAPE;
   if (n_rows == 0) return FVGN_OK;
   if (!fvgn_aligned16(src) || !fvgn_aligned16(dst)) return FVGN_ERR_ALIGN;
-  if (width == 128) {
-    const unsigned grid = (unsigned)((n_rows + 7) / 8);
-    FVGN_LAUNCH_SEQ(adj_reduce_kernel<128>, grid, 256, 0, stream, src, ptr, nbr, dst, n_rows, flags);
-  } else if (width == 64) {
-    const unsigned grid = (unsigned)((n_rows + 15) / 16);
-    FVGN_LAUNCH_SEQ(adj_reduce_kernel<64>, grid, 256, 0, stream, src, ptr, nbr, dst, n_rows, flags);
-  } else {
-    return FVGN_ERR_UNSUPPORTED;
-  }
-  FVGN_CHECK_LAUNCH();
-  return FVGN_OK;
+  return launch_adj<T_F32, T_F32>(src, ptr, nbr, dst, n_rows, width, flags, stream);
 }
 
 extern "C" int fvgn_inc_reduce(const float* src, const int32_t* ptr, const int32_t* code, float* dst, int64_t n_rows,
@@ -113,15 +165,33 @@ extern "C" int fvgn_inc_reduce(const float* src, const int32_t* ptr, const int32
   if (n_rows < 0) return FVGN_ERR_SHAPE;
   if (n_rows == 0) return FVGN_OK;
   if (!fvgn_aligned16(src) || !fvgn_aligned16(dst)) return FVGN_ERR_ALIGN;
-  if (width == 128) {
-    const unsigned grid = (unsigned)((n_rows + 7) / 8);
-    FVGN_LAUNCH_SEQ(inc_reduce_kernel<128>, grid, 256, 0, stream, src, ptr, code, dst, n_rows);
-  } else if (width == 64) {
-    const unsigned grid = (unsigned)((n_rows + 15) / 16);
-    FVGN_LAUNCH_SEQ(inc_reduce_kernel<64>, grid, 256, 0, stream, src, ptr, code, dst, n_rows);
-  } else {
-    return FVGN_ERR_UNSUPPORTED;
-  }
-  FVGN_CHECK_LAUNCH();
-  return FVGN_OK;
+  return launch_inc<T_F32, T_F32>(src, ptr, code, dst, n_rows, width, stream);
+}
+
+extern "C" int fvgn_adj_reduce_t(const void* src, int32_t src_type, const int32_t* ptr, const int32_t* nbr, void* dst,
+                                 int32_t dst_type, int64_t n_rows, int32_t width, int32_t flags, void* stream) {
+  if (n_rows < 0) return FVGN_ERR_SHAPE;
+  if (n_rows == 0) return FVGN_OK;
+  if (!fvgn_aligned16(src) || !fvgn_aligned16(dst)) return FVGN_ERR_ALIGN;
+#ifndef FVGN_EMU
+  if (src_type == FVGN_T_F32 && dst_type == FVGN_T_BF16) return launch_adj<T_F32, T_BF16>(src, ptr, nbr, dst, n_rows, width, flags, stream);
+  if (src_type == FVGN_T_BF16 && dst_type == FVGN_T_F32) return launch_adj<T_BF16, T_F32>(src, ptr, nbr, dst, n_rows, width, flags, stream);
+  if (src_type == FVGN_T_BF16 && dst_type == FVGN_T_BF16) return launch_adj<T_BF16, T_BF16>(src, ptr, nbr, dst, n_rows, width, flags, stream);
+#endif
+  if (src_type == FVGN_T_F32 && dst_type == FVGN_T_F32) return launch_adj<T_F32, T_F32>(src, ptr, nbr, dst, n_rows, width, flags, stream);
+  return FVGN_ERR_UNSUPPORTED;
+}
+
+extern "C" int fvgn_inc_reduce_t(const void* src, int32_t src_type, const int32_t* ptr, const int32_t* code, void* dst,
+                                 int32_t dst_type, int64_t n_rows, int32_t width, void* stream) {
+  if (n_rows < 0) return FVGN_ERR_SHAPE;
+  if (n_rows == 0) return FVGN_OK;
+  if (!fvgn_aligned16(src) || !fvgn_aligned16(dst)) return FVGN_ERR_ALIGN;
+#ifndef FVGN_EMU
+  if (src_type == FVGN_T_F32 && dst_type == FVGN_T_BF16) return launch_inc<T_F32, T_BF16>(src, ptr, code, dst, n_rows, width, stream);
+  if (src_type == FVGN_T_BF16 && dst_type == FVGN_T_F32) return launch_inc<T_BF16, T_F32>(src, ptr, code, dst, n_rows, width, stream);
+  if (src_type == FVGN_T_BF16 && dst_type == FVGN_T_BF16) return launch_inc<T_BF16, T_BF16>(src, ptr, code, dst, n_rows, width, stream);
+#endif
+  if (src_type == FVGN_T_F32 && dst_type == FVGN_T_F32) return launch_inc<T_F32, T_F32>(src, ptr, code, dst, n_rows, width, stream);
+  return FVGN_ERR_UNSUPPORTED;
 }

@@ -174,23 +174,24 @@ __device__ __forceinline__ const float* chunk_src(const fvgn_mlp_desc& d, int64_
   }
 }
 
-// endpoint indices of the 8 tile rows a producer lane handles (rows i*16 + pw*4 + lane/8), fetched once per tile so
-// that the gathers of every chunk do not wait on a dependent index load
+// Endpoint indices of the 8 tile rows a producer lane handles (rows i*16 + pw*4 + lane/8, i = 0..7), fetched once per
+// tile so that the gathers of every chunk do not wait on a dependent index load.  The 8 lanes that share lane/8 handle
+// the same rows, so lane (lane & 24) | i keeps the pair of row i and the others read it with a shuffle: 2 registers per
+// tile instead of 16.
 struct TileIdx {
-  int s[8], r[8];
+  int s, r;
+  __device__ __forceinline__ int sender(int i, int lane) const { return __shfl_sync(0xffffffffu, s, (lane & 24) | i); }
+  __device__ __forceinline__ int receiver(int i, int lane) const { return __shfl_sync(0xffffffffu, r, (lane & 24) | i); }
 };
 template <int MODE>
 __device__ __forceinline__ void load_tile_idx(const fvgn_mlp_desc& d, int64_t row0, int pw, int lane, TileIdx& idx) {
-#pragma unroll
-  for (int i = 0; i < 8; ++i) {
-    idx.s[i] = 0;
-    idx.r[i] = 0;
-    if (MODE == FVGN_MLP_EDGE) {
-      const int64_t row = row0 + i * 16 + pw * 4 + (lane >> 3);
-      if (row < d.rows) {
-        idx.s[i] = __ldg(d.idx_s + row);
-        idx.r[i] = __ldg(d.idx_r + row);
-      }
+  idx.s = 0;
+  idx.r = 0;
+  if (MODE == FVGN_MLP_EDGE) {
+    const int64_t row = row0 + (lane & 7) * 16 + pw * 4 + (lane >> 3);
+    if (row < d.rows) {
+      idx.s = __ldg(d.idx_s + row);
+      idx.r = __ldg(d.idx_r + row);
     }
   }
 }
@@ -243,7 +244,7 @@ __device__ __forceinline__ void produce_chunk(const fvgn_mlp_desc& d, int64_t ro
   for (int i = 0; i < 8; ++i) {
     const int rloc = i * 16 + pw * 4 + (lane >> 3);
     const int64_t row = row0 + rloc;
-    src[i] = chunk_src<MODE>(d, row, kb, idx.s[i], idx.r[i]);
+    src[i] = chunk_src<MODE>(d, row, kb, 0, 0);  // only the encoders use this fp32 path (no gathers by index here)
   }
 #pragma unroll
   for (int i = 0; i < 8; ++i) {
@@ -263,6 +264,111 @@ __device__ __forceinline__ void produce_chunk(const fvgn_mlp_desc& d, int64_t ro
                    pack_bf16(hi[i].z, hi[i].w));
   }
 }
+
+
+// ------------------------------------------------------------------------------------------ bf16-shadow producers
+// Layer-1 operand chunks read from the bf16 row-major shadows: every 64-feature chunk of a row is 128 contiguous bytes,
+// fetched as 8 x 16 B by 8 lanes (no conversion).  A chunk is held in registers (8 x uint4 per thread) between the load
+// and the store into the ring, so the global-load latency is decoupled from the depth of the shared-memory ring.
+template <int MODE>
+__device__ __forceinline__ const uint4* chunk_src_h(const fvgn_mlp_desc& d, int64_t row, int kb, int seg, int s, int r) {
+  if (row >= d.rows) return nullptr;
+  const uint8_t* p;
+  if (MODE == FVGN_MLP_EDGE) {
+    if (kb < 2) p = reinterpret_cast<const uint8_t*>(d.in0h) + (size_t)s * 256 + kb * 128;
+    else if (kb < 4) p = reinterpret_cast<const uint8_t*>(d.in0h) + (size_t)r * 256 + (kb - 2) * 128;
+    else p = reinterpret_cast<const uint8_t*>(d.in1h) + (size_t)row * 256 + (kb - 4) * 128;
+  } else if (MODE == FVGN_MLP_NODE) {
+    if (kb == 0) p = reinterpret_cast<const uint8_t*>(d.in0h) + (size_t)row * 128;
+    else p = reinterpret_cast<const uint8_t*>(d.in1h) + (size_t)row * 256 + (kb - 1) * 128;
+  } else {
+    p = reinterpret_cast<const uint8_t*>(d.in0h) + (size_t)row * 256 + kb * 128;
+  }
+  return reinterpret_cast<const uint4*>(p + seg * 16);
+}
+struct ChunkRegs {
+  uint4 v[8];
+};
+template <int MODE>
+__device__ __forceinline__ void load_chunk_h(const fvgn_mlp_desc& d, int64_t row0, int kb, int pw, int lane, const TileIdx& idx,
+                                             ChunkRegs& c) {
+  const int seg = lane & 7;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const int64_t row = row0 + i * 16 + pw * 4 + (lane >> 3);
+    int si = 0, ri = 0;
+    if (MODE == FVGN_MLP_EDGE) {  // kb is a compile-time constant at every call site: one shuffle per gathered row
+      if (kb < 2) si = idx.sender(i, lane);
+      else if (kb < 4) ri = idx.receiver(i, lane);
+    }
+    const uint4* src = chunk_src_h<MODE>(d, row, kb, seg, si, ri);
+    c.v[i] = src ? __ldg(src) : make_uint4(0u, 0u, 0u, 0u);
+  }
+}
+__device__ __forceinline__ void store_chunk_h(uint8_t* stage, int pw, int lane, const ChunkRegs& c) {
+  // row i*16 + r0 (r0 = pw*4 + lane/8 < 16): the swizzle only depends on r0, rows 16 apart are 2048 B apart
+  uint8_t* base = stage + sw128_off(pw * 4 + (lane >> 3), lane & 7);
+#pragma unroll
+  for (int i = 0; i < 8; ++i) *reinterpret_cast<uint4*>(base + i * 2048) = c.v[i];
+}
+// modes whose layer-1 operands come from bf16 shadows (the encoders read their few fp32 input columns directly)
+__host__ __device__ constexpr bool mode_has_shadow(int mode) {
+  return mode == FVGN_MLP_EDGE || mode == FVGN_MLP_NODE || mode == FVGN_MLP_DEC;
+}
+
+// Producer loop of one CTA over its tiles (blockIdx.x + i * gridDim.x): chunk kb of a tile is held in register buffer
+// kb % PF from the moment its loads are issued until `put(buffer, i, kb)` parks it in the ring, PF chunks later.  kb is a
+// compile-time constant everywhere (NKB1 % PF == 0), so the endpoint-index registers are live only where needed.
+template <int MODE>
+__host__ __device__ constexpr int prefetch_depth() { return MODE == FVGN_MLP_DEC ? 2 : 3; }
+
+template <int MODE, int NKB1, class PutFn>
+__device__ __forceinline__ void produce_tiles_h(const fvgn_mlp_desc& d, int64_t ntiles, int pw, int lane, PutFn&& put) {
+  constexpr int PF = prefetch_depth<MODE>();
+  static_assert(NKB1 % PF == 0, "chunks per tile must be a multiple of the prefetch depth");
+  ChunkRegs buf[PF];
+  TileIdx cur, nxt;
+  int64_t tile = blockIdx.x;
+  if (tile >= ntiles) return;
+  load_tile_idx<MODE>(d, tile * TILE_M, pw, lane, cur);
+  load_tile_idx<MODE>(d, (tile + gridDim.x) * TILE_M, pw, lane, nxt);  // rows past the end load nothing
+#pragma unroll
+  for (int kb = 0; kb < PF; ++kb) load_chunk_h<MODE>(d, tile * TILE_M, kb, pw, lane, cur, buf[kb]);
+  for (uint32_t i = 0; tile < ntiles; tile += gridDim.x, ++i) {
+    const int64_t next = tile + gridDim.x;
+#pragma unroll
+    for (int kb = 0; kb < NKB1; ++kb) {
+      put(buf[kb % PF], i, kb);
+      if (kb + PF < NKB1) {
+        load_chunk_h<MODE>(d, tile * TILE_M, kb + PF, pw, lane, cur, buf[kb % PF]);
+      } else if (next < ntiles) {
+        load_chunk_h<MODE>(d, next * TILE_M, kb + PF - NKB1, pw, lane, nxt, buf[kb % PF]);
+      }
+    }
+    cur = nxt;
+    load_tile_idx<MODE>(d, (next + gridDim.x) * TILE_M, pw, lane, nxt);
+  }
+}
+
+// ------------------------------------------------------------------------------------------ wide epilogue staging
+// One 4 KB staging tile per epilogue warp: 32 rows x 128 B, 16-B chunk c of row r at r*128 + ((c ^ (r & 7)) << 4)
+// (conflict-free for thread-per-row writes and for 8-lanes-per-row reads).  It turns the thread-per-row TMEM layout
+// into 128-B row segments, i.e. 4 rows per fully coalesced warp instruction (4 L1 wavefronts instead of 16-32).
+constexpr int WSTG_BYTES = 4096;
+__device__ __forceinline__ uint8_t* wstg_at(uint8_t* stg, int r, int c) { return stg + r * 128 + ((c ^ (r & 7)) << 4); }
+
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,"
+      "%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]), "=r"(r[17]),
+        "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]), "=r"(r[25]), "=r"(r[26]),
+        "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr)
+      : "memory");
+}
+__device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
 
 // ------------------------------------------------------------------------------------------ extra helpers (backward)
 __device__ __forceinline__ void tmem_ld8(uint32_t taddr, uint32_t (&r)[8]) {

@@ -27,21 +27,47 @@ def _c(t):
 
 
 # ------------------------------------------------------------------ raw kernel calls
-def adj_reduce(src, plan, width, flags=0, out=None):
-    """out[i] = sum_{j in Adj(i)} src[j]  (blocks.py:92-99 / :44-51)."""
+BF16 = torch.bfloat16
+
+
+def hptr(t, allow_none=False):
+    return _lib.ptr(t, BF16, allow_none)
+
+
+def _tcode(t):
+    return _lib.FVGN_T_BF16 if t.dtype == BF16 else _lib.FVGN_T_F32
+
+
+def adj_reduce(src, plan, width, flags=0, out=None, out_dtype=torch.float32):
+    """out[i] = sum_{j in Adj(i)} src[j]  (blocks.py:92-99 / :44-51).  src / out may be fp32 or bf16 (fp32 accumulation)."""
     if out is None:
-        out = _empty((plan.N, width), src)
-    _lib.call("fvgn_adj_reduce", fptr(src), iptr(plan.inc_ptr), iptr(plan.inc_nbr), fptr(out), plan.N, width, flags,
-              _lib.stream_ptr(src.device))
+        out = torch.empty((plan.N, width), dtype=out_dtype, device=src.device)
+    if src.dtype == torch.float32 and out.dtype == torch.float32:
+        _lib.call("fvgn_adj_reduce", fptr(src), iptr(plan.inc_ptr), iptr(plan.inc_nbr), fptr(out), plan.N, width, flags,
+                  _lib.stream_ptr(src.device))
+    else:
+        _lib.call("fvgn_adj_reduce_t", _lib.ptr(src), _tcode(src), iptr(plan.inc_ptr), iptr(plan.inc_nbr), _lib.ptr(out),
+                  _tcode(out), plan.N, width, flags, _lib.stream_ptr(src.device))
     return out
 
 
-def inc_reduce(src, plan, width):
+def inc_reduce(src, plan, width, out_dtype=torch.float32):
     """out[i] = sum over incident (edge, role) of src[edge, role*width:(role+1)*width]  (blocks.py:24-42)."""
-    out = _empty((plan.N, width), src)
-    _lib.call("fvgn_inc_reduce", fptr(src), iptr(plan.inc_ptr), iptr(plan.inc_code), fptr(out), plan.N, width,
-              _lib.stream_ptr(src.device))
+    out = torch.empty((plan.N, width), dtype=out_dtype, device=src.device)
+    if src.dtype == torch.float32 and out.dtype == torch.float32:
+        _lib.call("fvgn_inc_reduce", fptr(src), iptr(plan.inc_ptr), iptr(plan.inc_code), fptr(out), plan.N, width,
+                  _lib.stream_ptr(src.device))
+    else:
+        _lib.call("fvgn_inc_reduce_t", _lib.ptr(src), _tcode(src), iptr(plan.inc_ptr), iptr(plan.inc_code), _lib.ptr(out),
+                  _tcode(out), plan.N, width, _lib.stream_ptr(src.device))
     return out
+
+
+def shadow(t, cached=None):
+    """bf16 row-major shadow of an fp32 latent; `cached` = (master, shadow) as attached by the producing kernel."""
+    if cached is not None and cached[0] is t and cached[1] is not None:
+        return cached[1]
+    return t.detach().to(BF16).contiguous()
 
 
 _MLP_K1 = {_lib.FVGN_MLP_EDGE: 384, _lib.FVGN_MLP_NODE: 192, _lib.FVGN_MLP_ENC_NODE: 12, _lib.FVGN_MLP_ENC_EDGE: 15,
@@ -72,22 +98,6 @@ class PackedWeights:
         return buf
 
 
-def _mlp_desc(mode, precision, rows, params, in0, in1=None, idx_s=None, idx_r=None, flags=0, packed=None):
-    d = _lib.MlpDesc()
-    d.mode, d.precision, d.rows, d.flags = mode, PREC[precision], rows, flags
-    d.in0, d.in1 = fptr(in0), fptr(in1, True)
-    d.idx_s, d.idx_r = iptr(idx_s, True), iptr(idx_r, True)
-    ps = [_c(p.detach()) for p in params]
-    d._keep = ps  # keep contiguous copies alive for the duration of the call
-    d.w1, d.b1, d.w2, d.b2, d.w3, d.b3 = (fptr(p) for p in ps[:6])
-    if len(ps) == 8:
-        d.ln_g, d.ln_b = fptr(ps[6]), fptr(ps[7])
-    if precision == "bf16":
-        d._packed = packed if packed is not None else PackedWeights.get(mode, params)
-        d.w_bf16 = _lib.ptr(d._packed)
-    return d
-
-
 def _img_buffer(nbytes, device):
     """1024-B aligned device scratch for bf16 tile images -> (owner tensor, aligned pointer)."""
     buf = torch.empty(nbytes + 1024, dtype=torch.uint8, device=device)
@@ -102,17 +112,57 @@ class Z1Image:
         self.buf, self.ptr = _img_buffer(nbytes, device)
 
 
+_SHADOW_MODES = (_lib.FVGN_MLP_EDGE, _lib.FVGN_MLP_NODE, _lib.FVGN_MLP_DEC)
+
+
+def _mlp_desc(mode, precision, rows, params, in0, in1=None, idx_s=None, idx_r=None, flags=0, packed=None, in0h=None,
+              in1h=None):
+    d = _lib.MlpDesc()
+    d.mode, d.precision, d.rows, d.flags = mode, PREC[precision], rows, flags
+    d.in0, d.in1 = fptr(in0, True), fptr(in1, True)
+    d.idx_s, d.idx_r = iptr(idx_s, True), iptr(idx_r, True)
+    ps = [_c(p.detach()) for p in params]
+    d._keep = ps  # keep contiguous copies alive for the duration of the call
+    d.w1, d.b1, d.w2, d.b2, d.w3, d.b3 = (fptr(p) for p in ps[:6])
+    if len(ps) == 8:
+        d.ln_g, d.ln_b = fptr(ps[6]), fptr(ps[7])
+    if precision == "bf16":
+        d._packed = packed if packed is not None else PackedWeights.get(mode, params)
+        d.w_bf16 = _lib.ptr(d._packed)
+        if mode in _SHADOW_MODES:
+            # layer-1 operands are read from bf16 shadows; make them here when the caller has none (stand-alone use)
+            if in0h is None:
+                in0h = shadow(in0)
+            if in1h is None and in1 is not None:
+                in1h = shadow(in1)
+            d._h = (in0h, in1h)
+            d.in0h, d.in1h = hptr(in0h), hptr(in1h, True)
+    return d
+
+
 def mlp_forward(mode, precision, rows, params, in0, in1=None, idx_s=None, idx_r=None, want_out=True, want_res=False,
-                flags=0, packed=None, z1=None):
-    """z1: a Z1Image to fill (bf16 mode, needed by mlp_backward) or None (inference)."""
-    d = _mlp_desc(mode, precision, rows, params, in0, in1, idx_s, idx_r, flags, packed)
+                flags=0, packed=None, z1=None, in0h=None, in1h=None, want_outh=False, want_resh=False):
+    """-> (out, out_res) [, outh, out_resh when requested: the bf16 shadows written by the bf16 kernels].
+    z1: a Z1Image to fill (bf16 mode, needed by mlp_backward) or None (inference)."""
+    d = _mlp_desc(mode, precision, rows, params, in0, in1, idx_s, idx_r, flags, packed, in0h, in1h)
+    like = in0 if in0 is not None else in0h
     nout = 3 if mode == _lib.FVGN_MLP_DEC else 128
-    out = _empty((rows, nout), in0) if want_out else None
-    res = _empty((rows, 128), in0) if want_res else None
+    out = _empty((rows, nout), like) if want_out else None
+    res = _empty((rows, 128), like) if want_res else None
     d.out, d.out_res = fptr(out, True), fptr(res, True)
-    if z1 is not None and precision == "bf16":
-        d.z1_img = z1.ptr
-    _lib.call("fvgn_mlp_forward", ctypes.byref(d), _lib.stream_ptr(in0.device))
+    outh = resh = None
+    if precision == "bf16":
+        if want_outh:
+            outh = torch.empty((rows, 128), dtype=BF16, device=like.device)
+            d.outh = hptr(outh)
+        if want_resh:
+            resh = torch.empty((rows, 128), dtype=BF16, device=like.device)
+            d.out_resh = hptr(resh)
+        if z1 is not None:
+            d.z1_img = z1.ptr
+    _lib.call("fvgn_mlp_forward", ctypes.byref(d), _lib.stream_ptr(like.device))
+    if want_outh or want_resh:
+        return out, res, outh, resh
     return out, res
 
 
@@ -121,28 +171,31 @@ def new_z1(mode, precision, rows, like):
 
 
 def mlp_backward(mode, precision, rows, params, in0, in1, idx_s, idx_r, d_out, d_gather=None, d_in0=None, d_in1=None,
-                 flags=0, packed=None, z1=None):
+                 flags=0, packed=None, z1=None, in0h=None, in1h=None, d_in0h=None):
     """Runs the fused backward; returns the list of parameter gradients (views of one flat buffer).
     packed: the bf16 weight image used by the matching forward (bf16 mode); repacked from `params` when None.
-    z1: the Z1Image the matching bf16 forward filled; when None (stand-alone use) the forward is re-run to make it."""
+    z1: the Z1Image the matching bf16 forward filled; when None (stand-alone use) the forward is re-run to make it.
+    d_in0h: EDGE, bf16 mode: [E,256] bf16 destination of d(agg[s])|d(agg[r]) (instead of the fp32 d_in0)."""
     if precision == "bf16" and z1 is None:
-        z1 = new_z1(mode, precision, rows, in0)
+        z1 = new_z1(mode, precision, rows, d_out)
         mlp_forward(mode, precision, rows, params, in0, in1, idx_s, idx_r, want_out=True, want_res=False, flags=flags,
-                    packed=packed, z1=z1)
-    d = _mlp_desc(mode, precision, rows, params, in0, in1, idx_s, idx_r, flags, packed)
+                    packed=packed, z1=z1, in0h=in0h, in1h=in1h)
+    d = _mlp_desc(mode, precision, rows, params, in0, in1, idx_s, idx_r, flags, packed, in0h, in1h)
     lib = _lib.load()
     pc = int(lib.fvgn_mlp_param_count(mode))
     npart = int(lib.fvgn_mlp_bwd_partials(mode, PREC[precision], rows))
-    partials = _empty((npart, pc), in0)
-    flat = _empty((pc,), in0)
+    partials = _empty((npart, pc), d_out)
+    flat = _empty((pc,), d_out)
     d.d_out, d.d_gather = fptr(d_out), fptr(d_gather, True)
     d.d_in0, d.d_in1 = fptr(d_in0, True), fptr(d_in1, True)
+    if d_in0h is not None:
+        d.d_in0h = hptr(d_in0h)
     d.partials, d.n_partials, d.d_params = fptr(partials), npart, fptr(flat)
     ws_bytes = int(lib.fvgn_mlp_bwd_workspace_bytes(mode, PREC[precision], rows))
     if ws_bytes > 0:
-        d._ws, d.workspace = _img_buffer(ws_bytes, in0.device)
+        d._ws, d.workspace = _img_buffer(ws_bytes, d_out.device)
         d._z1, d.z1_img = z1, z1.ptr
-    _lib.call("fvgn_mlp_backward", ctypes.byref(d), _lib.stream_ptr(in0.device))
+    _lib.call("fvgn_mlp_backward", ctypes.byref(d), _lib.stream_ptr(d_out.device))
     k1 = _MLP_K1[mode]
     nout = 3 if mode == _lib.FVGN_MLP_DEC else 128
     sizes = [(128, k1), (128,), (128, 128), (128,), (nout, 128), (nout,)]
@@ -164,22 +217,28 @@ def _packed(mode, precision, params):
 
 # ------------------------------------------------------------------ Encoder
 class EncoderFn(torch.autograd.Function):
-    """Encoder.forward (EPD.py:116-153) with the relative edge features of importer.py:54-78 fused in."""
+    """Encoder.forward (EPD.py:116-153) with the relative edge features of importer.py:54-78 fused in.
+    -> (node, edge, node_h, edge_h); the last two are the bf16 shadows (None in fp32 mode)."""
 
     @staticmethod
     def forward(ctx, xn, pos, plan, precision, *params):
         nb, eb = params[:8], params[8:]
         ctx.pk = (_packed(_lib.FVGN_MLP_ENC_NODE, precision, nb), _packed(_lib.FVGN_MLP_ENC_EDGE, precision, eb))
         ctx.z1 = (new_z1(_lib.FVGN_MLP_ENC_NODE, precision, plan.N, xn), new_z1(_lib.FVGN_MLP_ENC_EDGE, precision, plan.E, xn))
-        node, _ = mlp_forward(_lib.FVGN_MLP_ENC_NODE, precision, plan.N, nb, xn, packed=ctx.pk[0], z1=ctx.z1[0])
-        edge, _ = mlp_forward(_lib.FVGN_MLP_ENC_EDGE, precision, plan.E, eb, xn, pos, plan.edge_s, plan.edge_r, packed=ctx.pk[1],
-                              z1=ctx.z1[1])
+        bf = precision == "bf16"
+        rn = mlp_forward(_lib.FVGN_MLP_ENC_NODE, precision, plan.N, nb, xn, packed=ctx.pk[0], z1=ctx.z1[0], want_outh=bf)
+        re = mlp_forward(_lib.FVGN_MLP_ENC_EDGE, precision, plan.E, eb, xn, pos, plan.edge_s, plan.edge_r, packed=ctx.pk[1],
+                         z1=ctx.z1[1], want_outh=bf)
         ctx.plan, ctx.precision = plan, precision
         ctx.save_for_backward(xn, pos, *params)
-        return node, edge
+        node, edge = rn[0], re[0]
+        nodeh, edgeh = (rn[2], re[2]) if bf else (None, None)
+        if bf:
+            ctx.mark_non_differentiable(nodeh, edgeh)
+        return node, edge, nodeh, edgeh
 
     @staticmethod
-    def backward(ctx, d_node, d_edge):
+    def backward(ctx, d_node, d_edge, _dnh=None, _deh=None):
         xn, pos, *params = ctx.saved_tensors
         plan, precision = ctx.plan, ctx.precision
         gn = mlp_backward(_lib.FVGN_MLP_ENC_NODE, precision, plan.N, params[:8], xn, None, None, None, _c(d_node),
@@ -195,51 +254,81 @@ class GnBlockFn(torch.autograd.Function):
     """GnBlock.forward (EPD.py:177-195) = EdgeBlock (blocks.py:71-120) -> NodeBlock (blocks.py:13-63) -> residuals.
 
     forward : agg = Adj x ; e' = MLP_e([agg[s]|agg[r]|e]) ; a1 = incidence-sum(e' halves) ; a2 = D^-1 Adj a1 ;
-              x' = MLP_n([a2|x]) ; returns (x + x', e + e')
-    backward: the transposes of the three reductions are the same CSR kernels; the MLPs recompute their hidden
-              activations from the saved block inputs (x, agg, a2, e)."""
+              x' = MLP_n([a2|x]) ; returns (x + x', e + e', shadows)
+    backward: the transposes of the three reductions are the same CSR kernels.
+    fp32 mode: the MLPs recompute their hidden activations from the saved block inputs (x, agg, a2, e).
+    bf16 mode: fp32 is kept for the residual streams x / e and their gradients only; agg, e', a2 and the gathered
+              gradients d(agg[s])|d(agg[r]) live as bf16 (what the tensor cores consume anyway); saved for backward are
+              the bf16 shadows xh, eh, aggh, a2h and the two Z1 tile images."""
 
     @staticmethod
-    def forward(ctx, x, e, plan, precision, *params):
+    def forward(ctx, x, e, xh, eh, plan, precision, *params):
         eb, nb = params[:8], params[8:]
         x, e = _c(x), _c(e)
         ctx.pk = (_packed(_lib.FVGN_MLP_EDGE, precision, eb), _packed(_lib.FVGN_MLP_NODE, precision, nb))
-        ctx.z1 = (new_z1(_lib.FVGN_MLP_EDGE, precision, plan.E, x), new_z1(_lib.FVGN_MLP_NODE, precision, plan.N, x))
+        ctx.plan, ctx.precision = plan, precision
+        if precision == "bf16":
+            xh = xh if xh is not None else shadow(x)
+            eh = eh if eh is not None else shadow(e)
+            ctx.z1 = (new_z1(_lib.FVGN_MLP_EDGE, precision, plan.E, x), new_z1(_lib.FVGN_MLP_NODE, precision, plan.N, x))
+            aggh = adj_reduce(x, plan, 128, out_dtype=BF16)
+            _, e_out, e_newh, e_outh = mlp_forward(_lib.FVGN_MLP_EDGE, precision, plan.E, eb, None, e, plan.edge_s, plan.edge_r,
+                                                   want_out=False, want_res=True, packed=ctx.pk[0], z1=ctx.z1[0], in0h=aggh,
+                                                   in1h=eh, want_outh=True, want_resh=True)
+            a1 = inc_reduce(e_newh, plan, 64)
+            del e_newh
+            a2h = adj_reduce(a1, plan, 64, _lib.FVGN_ADJ_DIV_DST_BY_DEG, out_dtype=BF16)
+            del a1
+            _, x_out, _, x_outh = mlp_forward(_lib.FVGN_MLP_NODE, precision, plan.N, nb, None, x, want_out=False, want_res=True,
+                                              packed=ctx.pk[1], z1=ctx.z1[1], in0h=a2h, in1h=xh, want_resh=True)
+            ctx.save_for_backward(xh, eh, aggh, a2h, *params)
+            ctx.mark_non_differentiable(x_outh, e_outh)
+            return x_out, e_out, x_outh, e_outh
         agg = adj_reduce(x, plan, 128)
         e_new, e_out = mlp_forward(_lib.FVGN_MLP_EDGE, precision, plan.E, eb, agg, e, plan.edge_s, plan.edge_r,
-                                   want_out=True, want_res=True, packed=ctx.pk[0], z1=ctx.z1[0])
+                                   want_out=True, want_res=True)
         a1 = inc_reduce(e_new, plan, 64)
         del e_new
         a2 = adj_reduce(a1, plan, 64, _lib.FVGN_ADJ_DIV_DST_BY_DEG)
         del a1
-        _, x_out = mlp_forward(_lib.FVGN_MLP_NODE, precision, plan.N, nb, a2, x, want_out=False, want_res=True,
-                               packed=ctx.pk[1], z1=ctx.z1[1])
-        ctx.plan, ctx.precision = plan, precision
+        _, x_out = mlp_forward(_lib.FVGN_MLP_NODE, precision, plan.N, nb, a2, x, want_out=False, want_res=True)
         ctx.save_for_backward(x, e, agg, a2, *params)
-        return x_out, e_out
+        return x_out, e_out, None, None
 
     @staticmethod
-    def backward(ctx, d_x_out, d_e_out):
+    def backward(ctx, d_x_out, d_e_out, _dxh=None, _deh=None):
         x, e, agg, a2, *params = ctx.saved_tensors
         plan, precision = ctx.plan, ctx.precision
         eb, nb = params[:8], params[8:]
-        d_x_out = _c(d_x_out) if d_x_out is not None else torch.zeros_like(x)
-        d_e_out = _c(d_e_out) if d_e_out is not None else torch.zeros_like(e)
-        d_a2 = _empty((plan.N, 64), x)
-        d_x = _empty((plan.N, 128), x)
-        g_nb = mlp_backward(_lib.FVGN_MLP_NODE, precision, plan.N, nb, a2, x, None, None, d_x_out, None, d_a2, d_x,
-                            packed=ctx.pk[1], z1=ctx.z1[1])
-        d_a1 = adj_reduce(d_a2, plan, 64, _lib.FVGN_ADJ_DIV_SRC_BY_DEG)
-        del d_a2
-        d_sr = _empty((plan.E, 256), x)
-        d_e = _empty((plan.E, 128), x)
-        g_eb = mlp_backward(_lib.FVGN_MLP_EDGE, precision, plan.E, eb, agg, e, plan.edge_s, plan.edge_r, d_e_out, d_a1,
-                            d_sr, d_e, packed=ctx.pk[0], z1=ctx.z1[0])
-        ctx.z1 = None
-        d_agg = inc_reduce(d_sr, plan, 128)
-        del d_sr
+        dev = x.device
+        d_x_out = _c(d_x_out) if d_x_out is not None else torch.zeros((plan.N, 128), device=dev)
+        d_e_out = _c(d_e_out) if d_e_out is not None else torch.zeros((plan.E, 128), device=dev)
+        d_a2 = _empty((plan.N, 64), d_x_out)
+        d_x = _empty((plan.N, 128), d_x_out)
+        d_e = _empty((plan.E, 128), d_x_out)
+        if precision == "bf16":
+            xh, eh, aggh, a2h = x, e, agg, a2
+            g_nb = mlp_backward(_lib.FVGN_MLP_NODE, precision, plan.N, nb, None, None, None, None, d_x_out, None, d_a2, d_x,
+                                packed=ctx.pk[1], z1=ctx.z1[1], in0h=a2h, in1h=xh)
+            d_a1 = adj_reduce(d_a2, plan, 64, _lib.FVGN_ADJ_DIV_SRC_BY_DEG)
+            del d_a2
+            d_srh = torch.empty((plan.E, 256), dtype=BF16, device=dev)
+            g_eb = mlp_backward(_lib.FVGN_MLP_EDGE, precision, plan.E, eb, None, None, plan.edge_s, plan.edge_r, d_e_out, d_a1,
+                                None, d_e, packed=ctx.pk[0], z1=ctx.z1[0], in0h=aggh, in1h=eh, d_in0h=d_srh)
+            ctx.z1 = None
+            d_agg = inc_reduce(d_srh, plan, 128)
+            del d_srh
+        else:
+            g_nb = mlp_backward(_lib.FVGN_MLP_NODE, precision, plan.N, nb, a2, x, None, None, d_x_out, None, d_a2, d_x)
+            d_a1 = adj_reduce(d_a2, plan, 64, _lib.FVGN_ADJ_DIV_SRC_BY_DEG)
+            del d_a2
+            d_sr = _empty((plan.E, 256), x)
+            g_eb = mlp_backward(_lib.FVGN_MLP_EDGE, precision, plan.E, eb, agg, e, plan.edge_s, plan.edge_r, d_e_out, d_a1,
+                                d_sr, d_e)
+            d_agg = inc_reduce(d_sr, plan, 128)
+            del d_sr
         adj_reduce(d_agg, plan, 128, _lib.FVGN_ADJ_ACCUMULATE, out=d_x)
-        return (d_x, d_e, None, None, *g_eb, *g_nb)
+        return (d_x, d_e, None, None, None, None, *g_eb, *g_nb)
 
 
 class EdgeBlockFn(torch.autograd.Function):
@@ -305,22 +394,32 @@ class DecoderFn(torch.autograd.Function):
     """Decoder.forward (EPD.py:215-219): Linear-GELU-Linear-GELU-Linear(128->3), no LayerNorm."""
 
     @staticmethod
-    def forward(ctx, x, precision, *params):
+    def forward(ctx, x, xh, precision, *params):
         x = _c(x)
         ctx.pk = _packed(_lib.FVGN_MLP_DEC, precision, params)
         ctx.z1 = new_z1(_lib.FVGN_MLP_DEC, precision, x.shape[0], x)
-        out, _ = mlp_forward(_lib.FVGN_MLP_DEC, precision, x.shape[0], params, x, packed=ctx.pk, z1=ctx.z1)
         ctx.precision = precision
-        ctx.save_for_backward(x, *params)
+        if precision == "bf16":
+            xh = xh if xh is not None else shadow(x)
+            out, _ = mlp_forward(_lib.FVGN_MLP_DEC, precision, x.shape[0], params, None, packed=ctx.pk, z1=ctx.z1, in0h=xh)
+            ctx.save_for_backward(xh, *params)
+        else:
+            out, _ = mlp_forward(_lib.FVGN_MLP_DEC, precision, x.shape[0], params, x)
+            ctx.save_for_backward(x, *params)
         return out
 
     @staticmethod
     def backward(ctx, d_out):
         x, *params = ctx.saved_tensors
-        d_x = _empty(tuple(x.shape), x)
-        g = mlp_backward(_lib.FVGN_MLP_DEC, ctx.precision, x.shape[0], params, x, None, None, None, _c(d_out), None, d_x,
-                         packed=ctx.pk, z1=ctx.z1)
-        return (d_x, None, *g)
+        d_out = _c(d_out)
+        d_x = _empty((x.shape[0], 128), d_out)
+        if ctx.precision == "bf16":
+            g = mlp_backward(_lib.FVGN_MLP_DEC, ctx.precision, x.shape[0], params, None, None, None, None, d_out, None, d_x,
+                             packed=ctx.pk, z1=ctx.z1, in0h=x)
+            ctx.z1 = None
+        else:
+            g = mlp_backward(_lib.FVGN_MLP_DEC, ctx.precision, x.shape[0], params, x, None, None, None, d_out, None, d_x)
+        return (d_x, None, None, *g)
 
 
 INTEGRATORS = {"explicit": 0, "implicit": 1, "imex": 2}

@@ -44,6 +44,14 @@ int fvgn_adj_reduce(const float* src, const int32_t* ptr, const int32_t* nbr, fl
  * agg[senders]/agg[receivers] gathers of blocks.py:101-107 in backward. */
 int fvgn_inc_reduce(const float* src, const int32_t* ptr, const int32_t* code, float* dst, int64_t n_rows,
                     int32_t width, void* stream);
+/* Typed variants for the bf16 throughput mode: src / dst element type chosen by FVGN_T_* (accumulation is always fp32
+ * in CSR order).  dst2, when non-NULL, receives a second copy of the result in the other type (fp32 <-> bf16). */
+#define FVGN_T_F32 0
+#define FVGN_T_BF16 1
+int fvgn_adj_reduce_t(const void* src, int32_t src_type, const int32_t* ptr, const int32_t* nbr, void* dst, int32_t dst_type,
+                      int64_t n_rows, int32_t width, int32_t flags, void* stream);
+int fvgn_inc_reduce_t(const void* src, int32_t src_type, const int32_t* ptr, const int32_t* code, void* dst,
+                      int32_t dst_type, int64_t n_rows, int32_t width, void* stream);
 
 /* ------------------------------------------------------------------ fused MLP blocks */
 #define FVGN_MLP_EDGE 0     /* EdgeBlock  blocks.py:101-111 + EPD.py:170-175,186 : in=[agg[s]|agg[r]|e], K1=384, LN, +e   */
@@ -86,6 +94,15 @@ typedef struct fvgn_mlp_desc {
    * [128 x 128] tile per 128 rows, fvgn_mlp_bwd_workspace_bytes() bytes, 1024-B aligned).  The forward writes it
    * when non-NULL; the backward REQUIRES it (it replaces the recomputation of layer 1 from the block inputs). */
   void* z1_img;
+  /* FVGN_PREC_BF16 only: bf16 row-major shadows of the operands / results (2 bytes per element, 16-B aligned rows).
+   * The tensor-core kernels read their layer-1 operands from the shadows (no conversion, half the gather bytes) and
+   * write the shadow of every latent they produce; fp32 is kept only for the residual streams x / e and their
+   * gradients.  in0h: EDGE aggh[N,128]  NODE a2h[N,64]  DEC xh[N,128]  (ENC_*: unused, in0 fp32 is read).
+   *             in1h: EDGE eh[E,128]    NODE xh[N,128]. */
+  const void* in0h; const void* in1h;
+  void* outh;      /* bf16 copy of `out` (EDGE: e' for the node aggregation; ENC_*: shadow of the encoded latent); optional */
+  void* out_resh;  /* bf16 shadow of out_res; optional */
+  void* d_in0h;    /* EDGE backward: [E,256] bf16 = d(agg[s]) | d(agg[r]) instead of the fp32 d_in0 */
 } fvgn_mlp_desc;
 
 int64_t fvgn_mlp_param_count(int32_t mode);

@@ -33,18 +33,25 @@ else:
     code = _lib.FVGN_MLP_NODE
 d_out = rn(rows, 128)
 z1 = ops.new_z1(code, prec, rows, in0)
+bf = prec == "bf16"
+in0h, in1h = (ops.shadow(in0), ops.shadow(in1)) if bf else (None, None)
+d_in0h = torch.empty((rows, 256), dtype=torch.bfloat16, device=dev) if (bf and mode == "EDGE") else None
+fwd = lambda: ops.mlp_forward(code, prec, rows, params, in0, in1, s, r, want_out=not bf, want_res=True, z1=z1, in0h=in0h,
+                              in1h=in1h, want_outh=bf and mode == "EDGE", want_resh=bf)
+bwd = lambda: ops.mlp_backward(code, prec, rows, params, in0, in1, s, r, d_out, d_gather, None if d_in0h is not None else d_in0,
+                               d_in1, z1=z1, in0h=in0h, in1h=in1h, d_in0h=d_in0h)
 for _ in range(2):
-    ops.mlp_forward(code, prec, rows, params, in0, in1, s, r, want_out=True, want_res=True, z1=z1)
-    ops.mlp_backward(code, prec, rows, params, in0, in1, s, r, d_out, d_gather, d_in0, d_in1, z1=z1)
+    fwd()
+    bwd()
 torch.cuda.synchronize()
 ev = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
 reps = 5
 tf = tb = 0.0
 for _ in range(reps):
     ev[0].record()
-    ops.mlp_forward(code, prec, rows, params, in0, in1, s, r, want_out=True, want_res=True, z1=z1)
+    fwd()
     ev[1].record()
-    ops.mlp_backward(code, prec, rows, params, in0, in1, s, r, d_out, d_gather, d_in0, d_in1, z1=z1)
+    bwd()
     ev[2].record()
     torch.cuda.synchronize()
     tf += ev[0].elapsed_time(ev[1]) / reps
