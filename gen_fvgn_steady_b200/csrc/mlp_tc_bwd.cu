@@ -231,7 +231,8 @@ __global__ void __launch_bounds__(A_THREADS, 1) mlp_tc_bwd_a_kernel(const fvgn_m
     for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++tcount) {
       const int64_t row0 = tile * TILE_M;
       if (C::LN) {
-        if (MODE == FVGN_MLP_EDGE && d.d_gather) load_tile_idx<MODE>(d, row0, pw, lane, idx);
+        const bool gath = MODE == FVGN_MLP_EDGE && (d.d_gather || d.d_gatherh);
+        if (gath) load_tile_idx<MODE>(d, row0, pw, lane, idx);
         const int seg = lane & 7;
         uint4 pk[2][8];
 #pragma unroll
@@ -248,18 +249,36 @@ __global__ void __launch_bounds__(A_THREADS, 1) mlp_tc_bwd_a_kernel(const fvgn_m
               hi[i] = __ldg(reinterpret_cast<const float4*>(p + 4));
             }
           }
-          if (MODE == FVGN_MLP_EDGE && d.d_gather) {
+          if (gath) {
             int gi[8];
 #pragma unroll
             for (int i = 0; i < 8; ++i) gi[i] = kb == 0 ? idx.sender(i, lane) : idx.receiver(i, lane);
+            if (d.d_gatherh) {
+              uint4 gv[8];
 #pragma unroll
-            for (int i = 0; i < 8; ++i) {
-              const int64_t row = row0 + i * 16 + pw * 4 + (lane >> 3);
-              if (row < d.rows) {
-                const float* g = d.d_gather + (size_t)gi[i] * 64 + seg * 8;
-                const float4 a = __ldg(reinterpret_cast<const float4*>(g)), b = __ldg(reinterpret_cast<const float4*>(g + 4));
-                lo[i] = make_float4(lo[i].x + a.x, lo[i].y + a.y, lo[i].z + a.z, lo[i].w + a.w);
-                hi[i] = make_float4(hi[i].x + b.x, hi[i].y + b.y, hi[i].z + b.z, hi[i].w + b.w);
+              for (int i = 0; i < 8; ++i) {
+                const int64_t row = row0 + i * 16 + pw * 4 + (lane >> 3);
+                gv[i] = make_uint4(0u, 0u, 0u, 0u);
+                if (row < d.rows)
+                  gv[i] = __ldg(reinterpret_cast<const uint4*>(reinterpret_cast<const uint8_t*>(d.d_gatherh) + (size_t)gi[i] * 128 + seg * 16));
+              }
+#pragma unroll
+              for (int i = 0; i < 8; ++i) {
+                lo[i] = make_float4(lo[i].x + bf16_lo(gv[i].x), lo[i].y + bf16_hi(gv[i].x), lo[i].z + bf16_lo(gv[i].y),
+                                    lo[i].w + bf16_hi(gv[i].y));
+                hi[i] = make_float4(hi[i].x + bf16_lo(gv[i].z), hi[i].y + bf16_hi(gv[i].z), hi[i].z + bf16_lo(gv[i].w),
+                                    hi[i].w + bf16_hi(gv[i].w));
+              }
+            } else {
+#pragma unroll
+              for (int i = 0; i < 8; ++i) {
+                const int64_t row = row0 + i * 16 + pw * 4 + (lane >> 3);
+                if (row < d.rows) {
+                  const float* g = d.d_gather + (size_t)gi[i] * 64 + seg * 8;
+                  const float4 a = __ldg(reinterpret_cast<const float4*>(g)), b = __ldg(reinterpret_cast<const float4*>(g + 4));
+                  lo[i] = make_float4(lo[i].x + a.x, lo[i].y + a.y, lo[i].z + a.z, lo[i].w + a.w);
+                  hi[i] = make_float4(hi[i].x + b.x, hi[i].y + b.y, hi[i].z + b.z, hi[i].w + b.w);
+                }
               }
             }
           }
@@ -686,7 +705,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) mlp_tc_bwd_b_kernel(const fvgn_ml
             if (col0 < 256) { dst = d.d_in0; ld = 256; colo = col0; to_bf16 = d.d_in0h != nullptr; }
             else { dst = d.d_in1; ld = 128; colo = col0 - 256; add_res = resid; }
           } else if (MODE == FVGN_MLP_NODE) {
-            if (col0 < 64) { dst = d.d_in0; ld = 64; colo = col0; }
+            if (col0 < 64) { dst = d.d_in0; ld = 64; colo = col0; to_bf16 = d.d_in0h != nullptr; }
             else { dst = d.d_in1; ld = 128; colo = col0 - 64; add_res = resid; }
           } else {
             dst = d.d_in0; ld = 128; colo = col0;
@@ -725,7 +744,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) mlp_tc_bwd_b_kernel(const fvgn_ml
               const int rr = ps * 4 + orow;
               const int64_t row = wrow0 + rr;
               if (row < d.rows)
-                *reinterpret_cast<uint4*>(dh + (size_t)row * 512 + colo * 2 + oseg * 16) =
+                *reinterpret_cast<uint4*>(dh + (size_t)row * (ld * 2) + colo * 2 + oseg * 16) =
                     *reinterpret_cast<const uint4*>(wstg_at(mystg, rr, oseg));
             }
             __syncwarp();

@@ -171,7 +171,7 @@ def new_z1(mode, precision, rows, like):
 
 
 def mlp_backward(mode, precision, rows, params, in0, in1, idx_s, idx_r, d_out, d_gather=None, d_in0=None, d_in1=None,
-                 flags=0, packed=None, z1=None, in0h=None, in1h=None, d_in0h=None):
+                 flags=0, packed=None, z1=None, in0h=None, in1h=None, d_in0h=None, d_gatherh=None):
     """Runs the fused backward; returns the list of parameter gradients (views of one flat buffer).
     packed: the bf16 weight image used by the matching forward (bf16 mode); repacked from `params` when None.
     z1: the Z1Image the matching bf16 forward filled; when None (stand-alone use) the forward is re-run to make it.
@@ -190,6 +190,8 @@ def mlp_backward(mode, precision, rows, params, in0, in1, idx_s, idx_r, d_out, d
     d.d_in0, d.d_in1 = fptr(d_in0, True), fptr(d_in1, True)
     if d_in0h is not None:
         d.d_in0h = hptr(d_in0h)
+    if d_gatherh is not None:
+        d.d_gatherh = hptr(d_gatherh)
     d.partials, d.n_partials, d.d_params = fptr(partials), npart, fptr(flat)
     ws_bytes = int(lib.fvgn_mlp_bwd_workspace_bytes(mode, PREC[precision], rows))
     if ws_bytes > 0:
@@ -271,14 +273,14 @@ class GnBlockFn(torch.autograd.Function):
             xh = xh if xh is not None else shadow(x)
             eh = eh if eh is not None else shadow(e)
             ctx.z1 = (new_z1(_lib.FVGN_MLP_EDGE, precision, plan.E, x), new_z1(_lib.FVGN_MLP_NODE, precision, plan.N, x))
-            aggh = adj_reduce(x, plan, 128, out_dtype=BF16)
+            aggh = adj_reduce(xh, plan, 128, out_dtype=BF16)
             _, e_out, e_newh, e_outh = mlp_forward(_lib.FVGN_MLP_EDGE, precision, plan.E, eb, None, e, plan.edge_s, plan.edge_r,
                                                    want_out=False, want_res=True, packed=ctx.pk[0], z1=ctx.z1[0], in0h=aggh,
                                                    in1h=eh, want_outh=True, want_resh=True)
-            a1 = inc_reduce(e_newh, plan, 64)
+            a1h = inc_reduce(e_newh, plan, 64, out_dtype=BF16)
             del e_newh
-            a2h = adj_reduce(a1, plan, 64, _lib.FVGN_ADJ_DIV_DST_BY_DEG, out_dtype=BF16)
-            del a1
+            a2h = adj_reduce(a1h, plan, 64, _lib.FVGN_ADJ_DIV_DST_BY_DEG, out_dtype=BF16)
+            del a1h
             _, x_out, _, x_outh = mlp_forward(_lib.FVGN_MLP_NODE, precision, plan.N, nb, None, x, want_out=False, want_res=True,
                                               packed=ctx.pk[1], z1=ctx.z1[1], in0h=a2h, in1h=xh, want_resh=True)
             ctx.save_for_backward(xh, eh, aggh, a2h, *params)
@@ -303,20 +305,21 @@ class GnBlockFn(torch.autograd.Function):
         dev = x.device
         d_x_out = _c(d_x_out) if d_x_out is not None else torch.zeros((plan.N, 128), device=dev)
         d_e_out = _c(d_e_out) if d_e_out is not None else torch.zeros((plan.E, 128), device=dev)
-        d_a2 = _empty((plan.N, 64), d_x_out)
+        d_a2 = _empty((plan.N, 64), d_x_out) if precision != "bf16" else None
         d_x = _empty((plan.N, 128), d_x_out)
         d_e = _empty((plan.E, 128), d_x_out)
         if precision == "bf16":
             xh, eh, aggh, a2h = x, e, agg, a2
-            g_nb = mlp_backward(_lib.FVGN_MLP_NODE, precision, plan.N, nb, None, None, None, None, d_x_out, None, d_a2, d_x,
-                                packed=ctx.pk[1], z1=ctx.z1[1], in0h=a2h, in1h=xh)
-            d_a1 = adj_reduce(d_a2, plan, 64, _lib.FVGN_ADJ_DIV_SRC_BY_DEG)
-            del d_a2
+            d_a2h = torch.empty((plan.N, 64), dtype=BF16, device=dev)
+            g_nb = mlp_backward(_lib.FVGN_MLP_NODE, precision, plan.N, nb, None, None, None, None, d_x_out, None, None, d_x,
+                                packed=ctx.pk[1], z1=ctx.z1[1], in0h=a2h, in1h=xh, d_in0h=d_a2h)
+            d_a1h = adj_reduce(d_a2h, plan, 64, _lib.FVGN_ADJ_DIV_SRC_BY_DEG, out_dtype=BF16)
+            del d_a2h
             d_srh = torch.empty((plan.E, 256), dtype=BF16, device=dev)
-            g_eb = mlp_backward(_lib.FVGN_MLP_EDGE, precision, plan.E, eb, None, None, plan.edge_s, plan.edge_r, d_e_out, d_a1,
-                                None, d_e, packed=ctx.pk[0], z1=ctx.z1[0], in0h=aggh, in1h=eh, d_in0h=d_srh)
+            g_eb = mlp_backward(_lib.FVGN_MLP_EDGE, precision, plan.E, eb, None, None, plan.edge_s, plan.edge_r, d_e_out, None,
+                                None, d_e, packed=ctx.pk[0], z1=ctx.z1[0], in0h=aggh, in1h=eh, d_in0h=d_srh, d_gatherh=d_a1h)
             ctx.z1 = None
-            d_agg = inc_reduce(d_srh, plan, 128)
+            d_agg = inc_reduce(d_srh, plan, 128, out_dtype=BF16)
             del d_srh
         else:
             g_nb = mlp_backward(_lib.FVGN_MLP_NODE, precision, plan.N, nb, a2, x, None, None, d_x_out, None, d_a2, d_x)

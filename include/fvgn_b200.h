@@ -102,7 +102,8 @@ typedef struct fvgn_mlp_desc {
   const void* in0h; const void* in1h;
   void* outh;      /* bf16 copy of `out` (EDGE: e' for the node aggregation; ENC_*: shadow of the encoded latent); optional */
   void* out_resh;  /* bf16 shadow of out_res; optional */
-  void* d_in0h;    /* EDGE backward: [E,256] bf16 = d(agg[s]) | d(agg[r]) instead of the fp32 d_in0 */
+  void* d_in0h;    /* backward, bf16 destination instead of the fp32 d_in0: EDGE [E,256] = d(agg[s]) | d(agg[r]); NODE d_a2[N,64] */
+  const void* d_gatherh; /* EDGE backward: bf16 d_a1[N,64] gathered instead of the fp32 d_gather */
 } fvgn_mlp_desc;
 
 int64_t fvgn_mlp_param_count(int32_t mode);

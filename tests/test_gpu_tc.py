@@ -135,3 +135,54 @@ def test_tc_backward_matches_fp32(mode, rows):
         json.dump(rep, f, indent=1)
     bad = {k: v for k, v in rep.items() if not (v < 3e-2)}
     assert not bad, rep
+
+
+def test_tc_backward_bf16_streams_match_fp32_streams():
+    """EDGE backward with the bf16 side streams (d_in0h, d_gatherh) vs the same kernel writing / reading fp32."""
+    from gen_fvgn_steady_b200 import ops
+    dev = torch.device("cuda")
+    rows, nodes = 128 * 148 + 300, 3000
+    code, params, in0, in1, s, r, X, res = _inputs("EDGE", rows, nodes, dev, seed=5)
+    g = torch.Generator(device=dev).manual_seed(12)
+    d_out = torch.randn((rows, 128), device=dev, generator=g)
+    d_gather = torch.randn((nodes, 64), device=dev, generator=g).bfloat16().float()  # exactly representable in bf16
+    d_in0, d_in1 = torch.zeros((rows, 256), device=dev), torch.zeros((rows, 128), device=dev)
+    ga = ops.mlp_backward(code, "bf16", rows, params, in0, in1, s, r, d_out, d_gather, d_in0, d_in1)
+    ga = [t.clone() for t in ga]
+    d_in0h = torch.zeros((rows, 256), device=dev, dtype=torch.bfloat16)
+    d_in1b = torch.zeros((rows, 128), device=dev)
+    gb = ops.mlp_backward(code, "bf16", rows, params, in0, in1, s, r, d_out, None, None, d_in1b, d_in0h=d_in0h,
+                          d_gatherh=d_gather.bfloat16())
+    torch.cuda.synchronize()
+    for a, b in zip(ga, gb):
+        assert torch.equal(a, b)                      # same arithmetic: bit-identical parameter gradients
+    assert torch.equal(d_in1, d_in1b)
+    assert torch.equal(d_in0.bfloat16(), d_in0h)      # the bf16 stream is the rounding of the fp32 one
+
+
+@pytest.mark.parametrize("width", [64, 128])
+def test_typed_reductions_match_torch(width):
+    """fvgn_adj_reduce_t / fvgn_inc_reduce_t (bf16 in / out, fp32 accumulation in CSR order) vs torch index_add."""
+    from gen_fvgn_steady_b200 import ops
+    from gen_fvgn_steady_b200.mesh import synthetic
+    from gen_fvgn_steady_b200.plan import GraphPlan
+    from tests.case_inputs import product_graphs
+    dev = torch.device("cuda")
+    mesh, uvp = synthetic.make_case(24, kind="mixed", bc="channel", seed=1)
+    graphs = product_graphs([mesh], [uvp], dev)
+    plan = GraphPlan.of(graphs[0])
+    g = torch.Generator(device=dev).manual_seed(2)
+    x = torch.randn((plan.N, width), device=dev, generator=g)
+    xh = x.bfloat16()
+    s, r = plan.edge_s.long(), plan.edge_r.long()
+    ref = torch.zeros_like(x).index_add_(0, torch.cat([s, r]), xh.float()[torch.cat([r, s])])
+    got = ops.adj_reduce(xh, plan, width, out_dtype=torch.bfloat16)
+    assert float((got.float() - ref).abs().max() / ref.abs().max()) < 1e-2
+    got32 = ops.adj_reduce(xh, plan, width)
+    assert float((got32 - ref).abs().max() / ref.abs().max()) < 1e-5
+    e = torch.randn((plan.E, 2 * width), device=dev, generator=g).bfloat16()
+    ref = torch.zeros_like(x).index_add_(0, torch.cat([s, r]), torch.cat([e.float()[:, :width], e.float()[:, width:]]))
+    got = ops.inc_reduce(e, plan, width)
+    assert float((got - ref).abs().max() / ref.abs().max()) < 1e-5
+    goth = ops.inc_reduce(e, plan, width, out_dtype=torch.bfloat16)
+    assert float((goth.float() - ref).abs().max() / ref.abs().max()) < 1e-2
