@@ -79,15 +79,25 @@ constexpr int A_THREADS = 448;
 constexpr int A_EPI = 256;  // epilogue threads
 __device__ __forceinline__ void epi_bar_sync256() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
 
-// column sums of a bf16 tile by the 256 epilogue threads: thread t owns column pair (2p, 2p+1), p = t & 63, rows [32*(t>>6), +32)
+// column sums of a bf16 tile by the 256 epilogue threads: thread t owns column pair (2p, 2p+1), p = t & 63, rows [32*(t>>6), +32).
+// Four rows at a time are added as packed bf16x2 (2 roundings), the groups are accumulated in fp32.
+__device__ __forceinline__ uint32_t hadd2_bf16(uint32_t a, uint32_t b) {
+  uint32_t r;
+  asm("add.rn.bf16x2 %0, %1, %2;" : "=r"(r) : "r"(a), "r"(b));
+  return r;
+}
 __device__ __forceinline__ void tile_colsum256(const uint8_t* buf, int t, float& s0, float& s1) {
   const int p = t & 63, r0 = (t >> 6) * 32;
   const int kb = (2 * p) >> 6, chunk = ((2 * p) & 63) >> 3, word = p & 3;
   const uint8_t* base = buf + kb * KB_BYTES + word * 4;
   float a = 0.f, b = 0.f;
-#pragma unroll 8
-  for (int r = r0; r < r0 + 32; ++r) {
-    const uint32_t w = *reinterpret_cast<const uint32_t*>(base + sw128_off(r, chunk));
+#pragma unroll
+  for (int r = r0; r < r0 + 32; r += 4) {
+    const uint32_t w0 = *reinterpret_cast<const uint32_t*>(base + sw128_off(r, chunk));
+    const uint32_t w1 = *reinterpret_cast<const uint32_t*>(base + sw128_off(r + 1, chunk));
+    const uint32_t w2 = *reinterpret_cast<const uint32_t*>(base + sw128_off(r + 2, chunk));
+    const uint32_t w3 = *reinterpret_cast<const uint32_t*>(base + sw128_off(r + 3, chunk));
+    const uint32_t w = hadd2_bf16(hadd2_bf16(w0, w1), hadd2_bf16(w2, w3));
     a += bf16_lo(w);
     b += bf16_hi(w);
   }
@@ -107,9 +117,8 @@ __global__ void __launch_bounds__(A_THREADS, 1) mlp_tc_bwd_a_kernel(const fvgn_m
   float* sb2 = reinterpret_cast<float*>(bufC + BUF_BYTES);
   float* sb3 = sb2 + 128;
   float* sg = sb3 + 128;
-  float2* xchA = reinterpret_cast<float2*>(sg + 128);  // [2 halves][128 rows] LayerNorm statistics exchange
-  float2* xchB = xchA + 256;                           // [2][128] LayerNorm-backward row moments exchange
-  uint64_t* bars = reinterpret_cast<uint64_t*>(xchB + 256);
+  float4* xch = reinterpret_cast<float4*>(sg + 128);   // [2 halves][128 rows] LayerNorm row sums exchanged between the halves
+  uint64_t* bars = reinterpret_cast<uint64_t*>(xch + 256);
   const uint32_t bar0 = smem_u32(bars);
   auto BAR = [&](int i) { return bar0 + 8u * (uint32_t)i; };
   constexpr int B_W = 0, B_ZFULL = 1, B_ZEMPTY = 3, B_MMA = 5, B_EPI = 6, B_DO = 7, B_CFREE = 8;
@@ -374,13 +383,17 @@ __global__ void __launch_bounds__(A_THREADS, 1) mlp_tc_bwd_a_kernel(const fvgn_m
       for_each_chunk16<64>(wacc, [&](int c0, uint32_t (&r)[16]) {
         uint32_t hw[8], gw[8];
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          const float2 b = *reinterpret_cast<const float2*>(sb2 + cbase + c0 + 2 * j);
-          float h0, g0, h1, g1;
+        for (int j = 0; j < 8; j += 2) {
+          const float4 b = *reinterpret_cast<const float4*>(sb2 + cbase + c0 + 2 * j);
+          float h0, g0, h1, g1, h2, g2, h3, g3;
           gelu_tanh_pair(__uint_as_float(r[2 * j]) + b.x, h0, g0);
           gelu_tanh_pair(__uint_as_float(r[2 * j + 1]) + b.y, h1, g1);
+          gelu_tanh_pair(__uint_as_float(r[2 * j + 2]) + b.z, h2, g2);
+          gelu_tanh_pair(__uint_as_float(r[2 * j + 3]) + b.w, h3, g3);
           hw[j] = pack_bf16(h0, h1);
           gw[j] = pack_bf16(g0, g1);
+          hw[j + 1] = pack_bf16(h2, h3);
+          gw[j + 1] = pack_bf16(g2, g3);
         }
         store_tile16(bufH2, rloc, cbase + c0, hw);
         tmem_st8(g2c + c0 / 2, gw);
@@ -394,67 +407,60 @@ __global__ void __launch_bounds__(A_THREADS, 1) mlp_tc_bwd_a_kernel(const fvgn_m
       pdo ^= 1;
       if (C::LN) {
         tile_colsum256(bufC, tid, dbta, dbtb);  // d beta = column sums of dO
-        float sum = 0.f, sq = 0.f;
+        // sweep 1 (one pass, no dependence on the statistics): sum y, sum y^2, S1 = sum dO*gamma, S2 = sum dO*gamma*y
+        float sum = 0.f, sq = 0.f, s1 = 0.f, s2 = 0.f;
         for_each_chunk16<64>(wacc, [&](int c0, uint32_t (&r)[16]) {
+          uint32_t ow[8];
+          load_tile16(bufC, rloc, cbase + c0, ow);
 #pragma unroll
-          for (int j = 0; j < 16; ++j) {
-            const float y = __uint_as_float(r[j]) + sb3[cbase + c0 + j];
-            sum += y;
-            sq = fmaf(y, y, sq);
+          for (int j = 0; j < 8; j += 2) {
+            const int c = cbase + c0 + 2 * j;
+            const float4 b = *reinterpret_cast<const float4*>(sb3 + c);
+            const float4 gm = *reinterpret_cast<const float4*>(sg + c);
+            const float y0 = __uint_as_float(r[2 * j]) + b.x, y1 = __uint_as_float(r[2 * j + 1]) + b.y;
+            const float y2 = __uint_as_float(r[2 * j + 2]) + b.z, y3 = __uint_as_float(r[2 * j + 3]) + b.w;
+            const float d0 = bf16_lo(ow[j]) * gm.x, d1 = bf16_hi(ow[j]) * gm.y;
+            const float d2 = bf16_lo(ow[j + 1]) * gm.z, d3 = bf16_hi(ow[j + 1]) * gm.w;
+            sum += (y0 + y1) + (y2 + y3);
+            sq = fmaf(y0, y0, fmaf(y1, y1, fmaf(y2, y2, fmaf(y3, y3, sq))));
+            s1 += (d0 + d1) + (d2 + d3);
+            s2 = fmaf(d0, y0, fmaf(d1, y1, fmaf(d2, y2, fmaf(d3, y3, s2))));
           }
         });
-        xchA[half * 128 + rloc] = make_float2(sum, sq);
-        epi_bar_sync256();
+        xch[half * 128 + rloc] = make_float4(sum, sq, s1, s2);
+        epi_bar_sync256();  // also: every thread has finished reading the dO tile (d beta) before rows are overwritten
         {
-          const float2 o = xchA[(half ^ 1) * 128 + rloc];
-          sum += o.x;
-          sq += o.y;
+          const float4 o = xch[(half ^ 1) * 128 + rloc];
+          sum += o.x; sq += o.y; s1 += o.z; s2 += o.w;
         }
         const float mean = sum * (1.0f / 128.0f);
         const float rstd = rsqrtf(fmaxf(sq * (1.0f / 128.0f) - mean * mean, 0.f) + 1e-5f);
-        float m1 = 0.f, m2 = 0.f;
-        // sweep A: row moments and d gamma
+        const float nmr = -mean * rstd;
+        const float m1 = s1 * (1.0f / 128.0f);                       // mean(dO*gamma)
+        const float m2 = rstd * (s2 * (1.0f / 128.0f) - mean * m1);  // mean(dO*gamma*xhat)
+        // sweep 2: dY = rstd * (dO*gamma - m1 - xhat*m2), d gamma += dO*xhat
         for_each_chunk16<64>(wacc, [&](int c0, uint32_t (&r)[16]) {
           uint32_t ow[8];
           float gx[16];
           load_tile16(bufC, rloc, cbase + c0, ow);
 #pragma unroll
-          for (int j = 0; j < 8; ++j) {
+          for (int j = 0; j < 8; j += 2) {
             const int c = cbase + c0 + 2 * j;
-            const float xh0 = (__uint_as_float(r[2 * j]) + sb3[c] - mean) * rstd;
-            const float xh1 = (__uint_as_float(r[2 * j + 1]) + sb3[c + 1] - mean) * rstd;
-            const float o0 = bf16_lo(ow[j]), o1 = bf16_hi(ow[j]);
-            const float dx0 = o0 * sg[c], dx1 = o1 * sg[c + 1];
-            m1 += dx0 + dx1;
-            m2 = fmaf(dx0, xh0, fmaf(dx1, xh1, m2));
-            gx[2 * j] = o0 * xh0;
-            gx[2 * j + 1] = o1 * xh1;
+            const float4 b = *reinterpret_cast<const float4*>(sb3 + c);
+            const float4 gm = *reinterpret_cast<const float4*>(sg + c);
+            const float xh0 = fmaf(__uint_as_float(r[2 * j]) + b.x, rstd, nmr), xh1 = fmaf(__uint_as_float(r[2 * j + 1]) + b.y, rstd, nmr);
+            const float xh2 = fmaf(__uint_as_float(r[2 * j + 2]) + b.z, rstd, nmr), xh3 = fmaf(__uint_as_float(r[2 * j + 3]) + b.w, rstd, nmr);
+            const float o0 = bf16_lo(ow[j]), o1 = bf16_hi(ow[j]), o2 = bf16_lo(ow[j + 1]), o3 = bf16_hi(ow[j + 1]);
+            gx[2 * j] = o0 * xh0; gx[2 * j + 1] = o1 * xh1; gx[2 * j + 2] = o2 * xh2; gx[2 * j + 3] = o3 * xh3;
+            const float y0 = rstd * fmaf(-xh0, m2, fmaf(o0, gm.x, -m1)), y1 = rstd * fmaf(-xh1, m2, fmaf(o1, gm.y, -m1));
+            const float y2 = rstd * fmaf(-xh2, m2, fmaf(o2, gm.z, -m1)), y3 = rstd * fmaf(-xh3, m2, fmaf(o3, gm.w, -m1));
+            ow[j] = pack_bf16(y0, y1);
+            ow[j + 1] = pack_bf16(y2, y3);
           }
+          store_tile16(bufC, rloc, cbase + c0, ow);
           const float cg = warp_colsum16(gx, lane);
 #pragma unroll
           for (int k = 0; k < 4; ++k) dgam[k] += (k == (c0 >> 4)) ? cg : 0.f;  // static register indexing
-        });
-        xchB[half * 128 + rloc] = make_float2(m1, m2);
-        epi_bar_sync256();  // also: every thread has finished reading the dO tile (d beta) before rows are overwritten
-        {
-          const float2 o = xchB[(half ^ 1) * 128 + rloc];
-          m1 = (m1 + o.x) * (1.0f / 128.0f);
-          m2 = (m2 + o.y) * (1.0f / 128.0f);
-        }
-        // sweep B: dY = rstd * (dO*gamma - m1 - xhat*m2)
-        for_each_chunk16<64>(wacc, [&](int c0, uint32_t (&r)[16]) {
-          uint32_t ow[8];
-          load_tile16(bufC, rloc, cbase + c0, ow);
-#pragma unroll
-          for (int j = 0; j < 8; ++j) {
-            const int c = cbase + c0 + 2 * j;
-            const float xh0 = (__uint_as_float(r[2 * j]) + sb3[c] - mean) * rstd;
-            const float xh1 = (__uint_as_float(r[2 * j + 1]) + sb3[c + 1] - mean) * rstd;
-            const float y0 = rstd * (bf16_lo(ow[j]) * sg[c] - m1 - xh0 * m2);
-            const float y1 = rstd * (bf16_hi(ow[j]) * sg[c + 1] - m1 - xh1 * m2);
-            ow[j] = pack_bf16(y0, y1);
-          }
-          store_tile16(bufC, rloc, cbase + c0, ow);
         });
         fence_proxy_async();
       }

@@ -34,6 +34,7 @@ int fvgn_version(void);
 #define FVGN_ADJ_ACCUMULATE 1      /* dst += result                               */
 #define FVGN_ADJ_DIV_DST_BY_DEG 2  /* result /= max(deg(row),1)   (scatter_mean)   */
 #define FVGN_ADJ_DIV_SRC_BY_DEG 4  /* each term /= max(deg(src),1) (its transpose) */
+#define FVGN_ADJ_SIMPLE_KERNEL 8   /* testing: use the one-row-per-warp kernel (same bits, slower) */
 /* dst[i,:] = sum_{t in [ptr[i],ptr[i+1])} src[nbr[t],:], width in {64,128}.
  * Replaces src/FVMmodel/Models/FVGN/blocks.py:92-99 (x[senders/receivers] + scatter_add) and
  * blocks.py:44-51 (scatter_mean); backward of both is the same call (Adj symmetric). */

@@ -186,3 +186,31 @@ def test_typed_reductions_match_torch(width):
     assert float((got - ref).abs().max() / ref.abs().max()) < 1e-5
     goth = ops.inc_reduce(e, plan, width, out_dtype=torch.bfloat16)
     assert float((goth.float() - ref).abs().max() / ref.abs().max()) < 1e-2
+
+
+@pytest.mark.parametrize("width", [64, 128])
+@pytest.mark.parametrize("flag", ["none", "dst", "src", "acc"])
+def test_chunk_reduce_is_bit_identical_to_row_kernel(width, flag):
+    """The warp-chunk CSR reduction (batched gathers across row boundaries) sums in the same order as the simple
+    one-row-per-warp kernel: identical bits, including ragged / empty rows."""
+    from gen_fvgn_steady_b200 import _lib, ops
+    dev = torch.device("cuda")
+    g = torch.Generator(device=dev).manual_seed(4)
+    n = 5003
+    deg = torch.randint(0, 9, (n,), device=dev, generator=g)
+    deg[::97] = 40                                   # a few rows longer than one 32-entry chunk
+    ptr = torch.zeros(n + 1, dtype=torch.int32, device=dev)
+    ptr[1:] = torch.cumsum(deg, 0).int()
+    nnz = int(ptr[-1])
+    nbr = torch.randint(0, n, (nnz,), device=dev, generator=g, dtype=torch.int32)
+    src = torch.randn((n, width), device=dev, generator=g)
+    fl = {"none": 0, "dst": _lib.FVGN_ADJ_DIV_DST_BY_DEG, "src": _lib.FVGN_ADJ_DIV_SRC_BY_DEG, "acc": _lib.FVGN_ADJ_ACCUMULATE}[flag]
+    init = torch.randn((n, width), device=dev, generator=g)
+    outs = []
+    for extra in (0, _lib.FVGN_ADJ_SIMPLE_KERNEL):
+        out = init.clone()
+        _lib.call("fvgn_adj_reduce", _lib.fptr(src), _lib.iptr(ptr), _lib.iptr(nbr), _lib.fptr(out), n, width, fl | extra,
+                  _lib.stream_ptr(dev))
+        outs.append(out)
+    torch.cuda.synchronize()
+    assert torch.equal(outs[0], outs[1])
