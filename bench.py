@@ -269,10 +269,17 @@ def run_ours(args):
         dist.destroy_process_group()
 
 
+# DRAM bytes per edge of the two kernels of one fused edge-MLP backward call, from the committed ncu capture
+# profiles/r1e_ncu_tc_kernels_2Medges.csv (dram__bytes_read.sum + dram__bytes_write.sum, 2 M edges, N = E/2):
+NCU_TRAFFIC_BYTES_PER_EDGE = {"bf16": None, "fp32": None}
+
+
 def dominant_kernel_roofline(model, plan, dev, args, p):
-    """Times the dominant kernel of the step (fused edge-MLP backward of one GnBlock) alone, CUDA events on its stream.
-    Algorithmic bytes per edge: e, d_e_out read, d_e written (3 x 512 B), d(agg[s])|d(agg[r]) written
-    (1024 B), agg / d_a1 gathers at unique-row volume ((512 + 256) * N/E B)."""
+    """Times the dominant call of the step -- the fused edge-MLP backward of one GnBlock (tcgen05 kernels A + B and the
+    deterministic partial reduction) -- alone, with CUDA events on its stream, on inputs of the step's own size.
+    Algorithmic bytes per edge (DESIGN.md section 5, fp32 volumes of the reference's tensors): e and d_e_out read, d_e
+    written (3 x 512 B), d(agg[s])|d(agg[r]) written (1024 B), agg / d_a1 gathers at unique-row volume
+    ((512 + 256) * N/E B)."""
     from gen_fvgn_steady_b200 import _lib, ops
     from gen_fvgn_steady_b200.FVMmodel.Models.FVGN.blocks import mlp_params
     blk = None
@@ -281,29 +288,46 @@ def dominant_kernel_roofline(model, plan, dev, args, p):
             blk = m
             break
     N, E = plan.N, plan.E
+    bf = args.precision == "bf16"
     gen = torch.Generator(device=dev).manual_seed(1)
     agg = torch.randn((N, 128), device=dev, generator=gen)
     e = torch.randn((E, 128), device=dev, generator=gen)
     d_out = torch.randn((E, 128), device=dev, generator=gen)
     d_a1 = torch.randn((N, 64), device=dev, generator=gen)
-    d_sr = torch.empty((E, 256), device=dev)
     d_e = torch.empty((E, 128), device=dev)
     params = [q.detach() for q in mlp_params(blk.eb_module.net)]
-    reps = 3
+    code = _lib.FVGN_MLP_EDGE
+    if bf:
+        aggh, eh = ops.shadow(agg), ops.shadow(e)
+        del agg, e
+        z1 = ops.new_z1(code, "bf16", E, d_out)
+        ops.mlp_forward(code, "bf16", E, params, None, None, plan.edge_s, plan.edge_r, want_out=False, want_res=False, z1=z1,
+                        in0h=aggh, in1h=eh, want_outh=True)
+        d_srh = torch.empty((E, 256), device=dev, dtype=torch.bfloat16)
+        d_a1h = d_a1.bfloat16()
+        run = lambda: ops.mlp_backward(code, "bf16", E, params, None, None, plan.edge_s, plan.edge_r, d_out, None, None, d_e,
+                                       z1=z1, in0h=aggh, in1h=eh, d_in0h=d_srh, d_gatherh=d_a1h)
+    else:
+        d_sr = torch.empty((E, 256), device=dev)
+        run = lambda: ops.mlp_backward(code, "fp32", E, params, agg, e, plan.edge_s, plan.edge_r, d_out, d_a1, d_sr, d_e)
+    reps = 5
     times = []
-    for i in range(reps + 1):
+    for i in range(reps + 2):
         ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         ev0.record()
-        ops.mlp_backward(_lib.FVGN_MLP_EDGE, args.precision, E, params, agg, e, plan.edge_s, plan.edge_r, d_out, d_a1, d_sr, d_e)
+        run()
         ev1.record()
         torch.cuda.synchronize()
-        if i > 0:
+        if i > 1:
             times.append(ev0.elapsed_time(ev1))
     ms = float(np.mean(times))
     alg = E * (3 * 512 + 1024) + N * (512 + 256)
-    return {"kernel": "mlp_bwd_kernel<EDGE> (fused edge-MLP backward: recompute + dgrad + wgrad)" if args.precision == "fp32"
-            else "mlp_tc_bwd<EDGE>", "bound": "hbm", "achieved": alg / (ms / 1e3) / 1e9, "unit": "GB/s", "ms_per_launch": ms,
-            "alg_bytes_per_launch": alg, "traffic": None}
+    tpe = NCU_TRAFFIC_BYTES_PER_EDGE.get(args.precision)
+    return {"kernel": "mlp_bwd_kernel<EDGE> (fused edge-MLP backward: recompute + dgrad + wgrad)" if not bf
+            else "fvgn_mlp_backward<EDGE> = mlp_tc_bwd_a_kernel<0> + mlp_tc_bwd_b_kernel<0> (tcgen05)", "bound": "hbm",
+            "achieved": alg / (ms / 1e3) / 1e9, "unit": "GB/s", "ms_per_launch": ms, "alg_bytes_per_launch": alg,
+            "traffic": None if tpe is None else tpe * E,
+            "traffic_source": None if tpe is None else "profiles/r1e_ncu_tc_kernels_2Medges.csv, per edge x E"}
 
 
 if __name__ == "__main__":

@@ -35,7 +35,7 @@ def _carry(graph, **updates):
     out = Data(x=graph.x, edge_attr=getattr(graph, "edge_attr", None), edge_index=graph.edge_index,
                face=getattr(graph, "face", None), num_graphs=getattr(graph, "num_graphs", None),
                batch=getattr(graph, "batch", None))
-    for k in ("pos", "_fvgn_plan"):
+    for k in ("pos", "_fvgn_plan", "_fvgn_halo"):
         if hasattr(graph, k):
             setattr(out, k, getattr(graph, k))
     for k, v in updates.items():
@@ -109,7 +109,9 @@ class EncoderProcesserDecoder(nn.Module):
         self.decoder = Decoder(hidden_sze=hidden_size, node_output_size=node_output_size)
 
     def forward(self, graph_node=None, graph_edge=None, graph_cell=None):
-        latent, _ = self.encoder(graph_node)
+        from ....parallel import halo_refresh
+        latent, _ = self.encoder(graph_node)  # point-wise in nodes / edges: exact on the ghost rows too
         for model in self.GN_block_list:
             latent = model(latent)
+            latent = halo_refresh(latent)     # cell-partition mode only: ghost rows <- owners (no-op otherwise)
         return self.decoder(latent)

@@ -43,6 +43,15 @@ class NNmodel(nn.Module):
         self.dp_group = None
         self.initialize_weights()
 
+    def enable_cell_partition(self, group=True):
+        """Cell-partition mode: this rank holds one sub-mesh made by
+        gen_fvgn_steady_b200.partition; per-graph statistics, Normalizer increments and residual norms are completed
+        over the ranks, the latents' ghost rows are refreshed after every GnBlock.  EPD nets only (the Transolver
+        blocks of TransFVGN need global slice tokens)."""
+        if self.params.net not in ("EPD", "FVGN"):
+            raise NotImplementedError("cell partition supports the pure GN composition (net=EPD)")
+        self.dp_group = group
+
     def enable_data_parallel(self, group=True):
         """Data-parallel mode: this rank holds a shard of the batch's graphs; the Normalizer
         increments are summed over ranks so that every rank keeps the statistics of the global batch.  The gradient
@@ -78,14 +87,26 @@ class NNmodel(nn.Module):
                              "please check the graph.norm_uvp")
         x = graph_node.x.float().contiguous()
         N, B = plan.N, plan.B
+        halo = getattr(plan, "halo", None)   # cell-partition mode: graphs [0, nb) = owned rows, [nb, 2 nb) = ghost rows
+        nb = B if halo is None else halo.num_graphs
         sums = ops.segment_colsum(x, 12, 12, plan.node_chunks, plan.node_chunk_ptr, plan.n_node_chunks, B)
         counts = (plan.node_chunk_ptr_counts if hasattr(plan, "node_chunk_ptr_counts") else None)
         if counts is None:
-            counts = torch.bincount(plan.batch_node.long(), minlength=B).clamp(min=1).to(torch.float32).view(-1, 1)
+            counts = torch.bincount(plan.batch_node.long(), minlength=B).to(torch.float32).view(-1, 1)
+            if halo is not None:
+                from ..parallel import allreduce_sum_
+                counts = allreduce_sum_(counts[:nb].contiguous()).repeat(B // nb, 1)
+            counts = counts.clamp(min=1)
             plan.node_chunk_ptr_counts = counts
+        if halo is not None:
+            from ..parallel import allreduce_sum_
+            sums = allreduce_sum_(sums[:nb].contiguous()).repeat(B // nb, 1)   # ghost rows use their graph's statistics
         gmean = (sums[:, 0:3] / counts).contiguous()
         var = ops.segment_colsum(x, 3, 12, plan.node_chunks, plan.node_chunk_ptr, plan.n_node_chunks, B, center=gmean,
-                                 power=2) / counts
+                                 power=2)
+        if halo is not None:
+            var = allreduce_sum_(var[:nb].contiguous()).repeat(B // nb, 1)
+        var = var / counts
         gstd = torch.sqrt(var).contiguous()
         nmean = nstd = None
         if getattr(graph_node, "norm_global", True):
@@ -93,6 +114,9 @@ class NNmodel(nn.Module):
                 sq = ops.segment_colsum(x, 9, 12, plan.node_chunks, plan.node_chunk_ptr, plan.n_node_chunks, B, power=2,
                                         col_offset=3)
                 s1, s2, cnt = sums[:, 3:12].sum(0), sq.sum(0), N
+                if halo is not None:  # owned rows only; `sums` is already global, the squares and the count are local
+                    s1 = sums[:nb, 3:12].sum(0) / halo.world
+                    s2, cnt = sq[:nb].sum(0), halo.rows["node"]["n_owned"]
                 if self.dp_group is not None:
                     from ..parallel import allreduce_normalizer
                     s1, s2, cnt = allreduce_normalizer(self.node_norm, (s1, s2, cnt),

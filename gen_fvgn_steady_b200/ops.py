@@ -528,7 +528,15 @@ class FVLossFn(torch.autograd.Function):
         ps = segment_colsum(res, 1, 4, plan.cell_chunks, plan.cell_chunk_ptr, plan.n_cell_chunks, plan.B, power=1,
                             col_offset=3)
         S = torch.cat([sq, ps], 1)                                           # [B,4]
-        scale = torch.cat([theta[:, 1:2], sigma[:, 0:2].float(), torch.ones_like(theta[:, 0:1])], 1)
+        halo = getattr(plan, "halo", None)
+        nb = plan.B
+        if halo is not None:
+            # cell-partition mode: rows [0, nb) are the real graphs (owned cells), the rest collect the halo cells;
+            # the squared-residual sums are completed over the ranks before the square root
+            from .parallel import allreduce_sum_
+            nb = halo.num_graphs
+            S = allreduce_sum_(S[:nb].contiguous())
+        scale = torch.cat([theta[:nb, 1:2], sigma[:nb, 0:2].float(), torch.ones_like(theta[:nb, 0:1])], 1)
         root = torch.sqrt(S)
         losses = root * scale
         uvp_node = _empty((plan.N, 3), phi)
@@ -547,7 +555,10 @@ class FVLossFn(torch.autograd.Function):
         st = _lib.stream_ptr(phi.device)
         safe = torch.where(root > 0, root, torch.ones_like(root))
         coef = torch.where(root > 0, g_losses * scale / safe, torch.zeros_like(root))
-        coef = torch.cat([coef[:, 0:3], coef[:, 3:4] * 0.5], 1).contiguous()
+        coef = torch.cat([coef[:, 0:3], coef[:, 3:4] * 0.5], 1)
+        if coef.shape[0] < plan.B:  # cell-partition mode: halo cells (graph ids >= nb) get no gradient
+            coef = torch.cat([coef, torch.zeros((plan.B - coef.shape[0], 4), dtype=coef.dtype, device=coef.device)], 0)
+        coef = coef.contiguous()
         d = _fv_desc(plan, phi, grad, theta, dt)
         d_face = _empty((plan.E, 13), phi)
         d_phi = _empty((plan.N, 7), phi)

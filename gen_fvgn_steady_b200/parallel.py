@@ -3,7 +3,12 @@
 Data-parallel mode: graphs of a batch are block-diagonal and independent, the script-level
 loss is a mean over graphs (pre_train_Adam.py:184), so rank r owns the graphs {b : b mod R = r}; the only exchange is
 ONE all-reduce of the flat fp32 gradient per step (1.18 M parameters = 4.7 MB for TransFVGN_v2) and, while the
-Normalizer is still accumulating, an all-reduce of its three accumulators (normalization.py:55-66)."""
+Normalizer is still accumulating, an all-reduce of its three accumulators (normalization.py:55-66).
+
+Cell-partition mode (section 8(e).2, gen_fvgn_steady_b200.partition): one mesh split over the ranks; after every GnBlock
+the ghost rows of the node and edge latents are refreshed from their owners (HaloExchangeFn; its backward returns the
+ghost rows' gradients to the owners and adds them there), the per-graph sums of the hot path are all-reduced, and the
+parameter gradients are SUMMED (every rank back-propagates the same global loss through its own sub-mesh)."""
 import torch
 import torch.distributed as dist
 
@@ -39,3 +44,83 @@ def allreduce_normalizer(normalizer, pending, group=None):
     dist.all_reduce(buf, op=dist.ReduceOp.SUM, group=group)
     n = s.numel()
     return buf[:n], buf[n:2 * n], float(buf[-1])
+
+
+# ----------------------------------------------------------------------------------------------- halo exchange
+def _exchange(x, rows, group, reverse):
+    """forward : ghost rows of x <- the owners' rows (contiguous receives, index-gather sends), in place.
+    reverse : ghost rows' values are sent back to the owners and ADDED to the rows they mirror; ghost rows <- 0."""
+    ops_, keep = [], []
+    peers = sorted(set(rows["send"].keys()) | set(rows["recv"].keys()))
+    for q in peers:
+        if not reverse:
+            if q in rows["send"]:
+                buf = x.index_select(0, rows["send"][q])
+                keep.append(buf)
+                ops_.append(dist.P2POp(dist.isend, buf, q, group=group))
+            if q in rows["recv"]:
+                st, cnt = rows["recv"][q]
+                ops_.append(dist.P2POp(dist.irecv, x[st:st + cnt], q, group=group))
+        else:
+            if q in rows["recv"]:
+                st, cnt = rows["recv"][q]
+                ops_.append(dist.P2POp(dist.isend, x[st:st + cnt], q, group=group))
+            if q in rows["send"]:
+                buf = torch.empty((rows["send"][q].numel(),) + tuple(x.shape[1:]), dtype=x.dtype, device=x.device)
+                keep.append((q, buf))
+                ops_.append(dist.P2POp(dist.irecv, buf, q, group=group))
+    if ops_:
+        for w in dist.batch_isend_irecv(ops_):
+            w.wait()
+    if reverse:
+        for q, buf in keep:  # ascending peer order: deterministic
+            x.index_add_(0, rows["send"][q], buf)
+        if rows["n_local"] > rows["n_owned"]:
+            x[rows["n_owned"]:].zero_()
+
+
+class HaloExchangeFn(torch.autograd.Function):
+    """x[ghost rows] <- owner values (in place).  backward: d x[owned rows] += the ghosts' gradients from every rank
+    that mirrors them, d x[ghost rows] = 0 (their pre-exchange values are dead)."""
+
+    @staticmethod
+    def forward(ctx, x, rows, group):
+        ctx.rows, ctx.group = rows, group
+        _exchange(x, rows, group, reverse=False)
+        ctx.mark_dirty(x)
+        return x
+
+    @staticmethod
+    def backward(ctx, g):
+        g = g.contiguous().clone()
+        _exchange(g, ctx.rows, ctx.group, reverse=True)
+        return g, None, None
+
+
+def halo_refresh(graph, group=None):
+    """Refresh the ghost rows of graph.x / graph.edge_attr (and of their bf16 shadows) after a GnBlock.  No-op when the
+    graph is not a partitioned sub-mesh."""
+    halo = getattr(graph, "_fvgn_halo", None)
+    if halo is None or halo.world == 1:
+        return graph
+    for attr, key, kind in (("x", "_xh", "node"), ("edge_attr", "_eh", "edge")):
+        rows = halo.rows[kind]
+        t = getattr(graph, attr)
+        cached = getattr(graph, key, None)
+        t2 = HaloExchangeFn.apply(t, rows, group)
+        setattr(graph, attr, t2)
+        sh = cached[1] if (cached is not None and cached[0] is t) else None
+        if sh is not None and rows["n_local"] > rows["n_owned"]:
+            sh[rows["n_owned"]:] = t2.detach()[rows["n_owned"]:].to(sh.dtype)
+        setattr(graph, key, (t2, sh))
+    return graph
+
+
+def allreduce_sum_(t, group=None):
+    dist.all_reduce(t, op=dist.ReduceOp.SUM, group=group)
+    return t
+
+
+def sum_gradients(flat, group=None):
+    """Cell-partition mode: every rank differentiates the same global loss through its sub-mesh -> gradients ADD."""
+    dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=group)

@@ -60,6 +60,7 @@ class GraphPlan:
             return plan
         plan = GraphPlan.build(graph_node, graph_node_x, graph_edge, graph_cell, order)
         plan.key, plan.key_fv = key, key_fv
+        plan.halo = getattr(graph_node, "_fvgn_halo", None)  # cell-partition mode (partition.py)
         graph_node._fvgn_plan = plan
         return plan
 
@@ -87,6 +88,7 @@ class GraphPlan:
         p.B = int(batch.max().item()) + 1 if N > 0 else 1
         p.node_chunks, p.node_chunk_ptr, p.n_node_chunks = _chunks(batch, p.B)
         p.has_fv = False
+        p.halo = None
         if graph_node_x is not None:
             p._build_fv(graph_node, graph_node_x, graph_edge, graph_cell, order)
         return p
