@@ -38,6 +38,10 @@ def parse_args():
                     help="bf16: tcgen05 throughput mode (default); fp32: SIMT parity mode")
     ap.add_argument("--cpu-cells", type=int, default=40_000, help="cell count of the bounded CPU-baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--parallel", default="dp", choices=["dp", "cells"],
+                    help="N>1: dp = one mesh of --cells cells per GPU, gradient all-reduce (weak scaling, the default the "
+                         "driver measures); cells = ONE mesh of --cells cells partitioned over the GPUs with a per-GnBlock "
+                         "halo exchange (strong scaling, SURVEY.md section 8(e).2)")
     return ap.parse_args()
 
 
@@ -170,14 +174,27 @@ def run_ours(args):
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
 
-    mesh, uvp = make_mesh(args.cells, rank, dev)
+    cells_mode = args.parallel == "cells" and world > 1
+    halo = None
+    if cells_mode:
+        from gen_fvgn_steady_b200 import partition
+        mesh, uvp = make_mesh(args.cells, 0, dev)            # the same global mesh on every rank
+        C_global = int(mesh["cell|centroid"].shape[0])
+        mesh, uvp, halo = partition.build(mesh, uvp, world, rank, device=dev)
+        torch.cuda.empty_cache()
+    else:
+        mesh, uvp = make_mesh(args.cells, rank, dev)
     graphs = graphs_from_meshes([mesh], [uvp], dev)
     del mesh
+    if cells_mode:
+        partition.mark_partition(graphs, halo)
     gn, gx, ge, gc, gi = graphs
     p = default_params(net=args.net, message_passing_num=args.mp, precision=args.precision)
     torch.manual_seed(0)
     model = NNmodel(p).to(dev)
-    if world > 1:
+    if cells_mode:
+        model.enable_cell_partition(True)
+    elif world > 1:
         model.enable_data_parallel(True)
     flat_grad = parallel.flatten_gradients(model)
     opt = torch.optim.Adam(model.parameters(), lr=p.lr, fused=True)
@@ -199,7 +216,9 @@ def run_ours(args):
         lb = p.loss_press * out[3] + p.loss_cont * out[0] + p.loss_mom * out[1] + p.loss_mom * out[2]
         loss = torch.mean(torch.log(lb))
         loss.backward()
-        if world > 1:
+        if cells_mode:
+            parallel.sum_gradients(flat_grad)
+        elif world > 1:
             parallel.allreduce_gradients(flat_grad, world)
         opt.step()
         if e2e:
@@ -213,8 +232,10 @@ def run_ours(args):
         torch.cuda.synchronize()
         ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         ev0.record()
+        torch.cuda.nvtx.range_push("timed_steps")  # lets `ncu --nvtx --nvtx-include timed_steps/` list exactly these launches
         for _ in range(nsteps):
             step(e2e)
+        torch.cuda.nvtx.range_pop()
         ev1.record()
         torch.cuda.synchronize()
         ms = torch.tensor([ev0.elapsed_time(ev1)], device=dev)
@@ -245,15 +266,20 @@ def run_ours(args):
         return
     hbm, how = peaks()
     sec = ms / 1e3 / args.steps
-    value = world * C / sec
+    value = (C_global if cells_mode else world * C) / sec
     ab = alg_bytes_step(N, E, C, K, X, args.mp)
     line = {"metric": "cells*steps/sec (fwd+bwd train step)", "value": value, "unit": "cells*steps/s", "n_gpus": world,
             "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps, "higher_is_better": True,
-            "scaling": "weak", "vs_baseline": None, "dtype": "f32" if args.precision == "fp32" else "bf16 (fp32 accumulate/storage)",
+            "scaling": "strong" if cells_mode else "weak", "vs_baseline": None,
+            "dtype": "f32" if args.precision == "fp32" else "bf16 (fp32 accumulate/storage)",
             "data": "synthetic", "config": dict(workload_config(args, C_bench=C), N=N, E=E, C=C, K=K, X=X,
-                                                parallelism=f"dp{world}", loss=last_loss),
+                                                parallelism=(f"cells{world} (one {C_global}-cell mesh, RCB partition, "
+                                                             f"3-layer halo, exchange per GnBlock; rank 0: "
+                                                             f"{halo.n_owned_cells} owned of {C} local cells)") if cells_mode
+                                                else f"dp{world}", loss=last_loss),
             "clocks": clocks, "gpu_launches": launches,
-            "e2e": {"value": world * C / (ms_e2e / 1e3 / args.steps), "unit": "cells*steps/s", "h2d_bytes_per_step": N * 12 * 4,
+            "e2e": {"value": (C_global if cells_mode else world * C) / (ms_e2e / 1e3 / args.steps), "unit": "cells*steps/s",
+                    "h2d_bytes_per_step": N * 12 * 4,
                     "d2h_bytes_per_step": N * 3 * 4 + 4, "ms_per_step": ms_e2e / args.steps},
             "roofline": dict(roof, peak=hbm, frac=roof["achieved"] / hbm, peak_source=how),
             "step_roofline": {"alg_bytes_per_step": ab, "achieved_gbs": ab / sec / 1e9, "frac": ab / sec / 1e9 / hbm,
