@@ -232,10 +232,13 @@ def run_ours(args):
         torch.cuda.synchronize()
         ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         ev0.record()
-        torch.cuda.nvtx.range_push("timed_steps")  # lets `ncu --nvtx --nvtx-include timed_steps/` list exactly these launches
+        if not e2e:
+            torch.cuda.profiler.start()  # `ncu --profile-from-start off` then lists exactly the launches of the timed steps
         for _ in range(nsteps):
             step(e2e)
-        torch.cuda.nvtx.range_pop()
+        if not e2e:
+            torch.cuda.synchronize()
+            torch.cuda.profiler.stop()
         ev1.record()
         torch.cuda.synchronize()
         ms = torch.tensor([ev0.elapsed_time(ev1)], device=dev)

@@ -699,6 +699,12 @@ __global__ void __launch_bounds__(NTHREADS, 1) mlp_tc_bwd_b_kernel(const fvgn_ml
       uint32_t blk = 0;
       for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
         const int64_t wrow0 = tile * TILE_M + warp * 32;
+        if (resid && (MODE == FVGN_MLP_EDGE || MODE == FVGN_MLP_NODE) && wrow0 + lane < d.rows) {
+          // the residual-gradient rows are read at the END of this tile (last two blocks): pull them into L2 now
+          const float* rp = d.d_out + (size_t)(wrow0 + lane) * 128;
+#pragma unroll
+          for (int k = 0; k < 4; ++k) prefetch_l2(rp + 32 * k);
+        }
         for (int j = 0; j < NKB1; ++j, ++blk) {
           const int ab = blk & 1;
           const uint32_t tacc = tmem + lane_base + WACC + 64 * ab;
@@ -716,13 +722,18 @@ __global__ void __launch_bounds__(NTHREADS, 1) mlp_tc_bwd_b_kernel(const fvgn_ml
           } else {
             dst = d.d_in0; ld = 128; colo = col0;
           }
-          // residual gradient of this block (2 x 8 passes x 16 B per lane would be 64 registers: one half at a time)
-          float4 g[8];
+          // residual gradient of this block: both 32-column halves are requested before waiting for the accumulator
+          float4 g[8], g1[8];
 #pragma unroll
           for (int ps = 0; ps < 8; ++ps) {
             const int64_t row = wrow0 + ps * 4 + orow;
             g[ps] = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (add_res && row < d.rows) g[ps] = __ldg(reinterpret_cast<const float4*>(d.d_out + (size_t)row * 128 + colo + oseg * 4));
+            g1[ps] = g[ps];
+            if (add_res && row < d.rows) {
+              const float* gp = d.d_out + (size_t)row * 128 + colo + oseg * 4;
+              g[ps] = __ldg(reinterpret_cast<const float4*>(gp));
+              g1[ps] = __ldg(reinterpret_cast<const float4*>(gp + 32));
+            }
           }
           mbar_wait(BAR(B_AFULL + ab), (blk >> 1) & 1);
           tc_fence_after();
@@ -759,13 +770,9 @@ __global__ void __launch_bounds__(NTHREADS, 1) mlp_tc_bwd_b_kernel(const fvgn_ml
             for (int half = 0; half < 2; ++half) {
               uint32_t r[32];
               tmem_ld32(tacc + 32 * half, r);
-              if (half == 1 && add_res) {
+              if (half == 1) {
 #pragma unroll
-                for (int ps = 0; ps < 8; ++ps) {
-                  const int64_t row = wrow0 + ps * 4 + orow;
-                  if (row < d.rows)
-                    g[ps] = __ldg(reinterpret_cast<const float4*>(d.d_out + (size_t)row * 128 + colo + 32 + oseg * 4));
-                }
+                for (int ps = 0; ps < 8; ++ps) g[ps] = g1[ps];
               }
               tmem_wait_ld();
 #pragma unroll

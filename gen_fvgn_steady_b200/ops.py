@@ -225,6 +225,7 @@ class EncoderFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, xn, pos, plan, precision, *params):
         nb, eb = params[:8], params[8:]
+        ctx.set_materialize_grads(False)  # no zero tensors for the (non-differentiable) bf16 shadow outputs
         ctx.pk = (_packed(_lib.FVGN_MLP_ENC_NODE, precision, nb), _packed(_lib.FVGN_MLP_ENC_EDGE, precision, eb))
         ctx.z1 = (new_z1(_lib.FVGN_MLP_ENC_NODE, precision, plan.N, xn), new_z1(_lib.FVGN_MLP_ENC_EDGE, precision, plan.E, xn))
         bf = precision == "bf16"
@@ -243,6 +244,10 @@ class EncoderFn(torch.autograd.Function):
     def backward(ctx, d_node, d_edge, _dnh=None, _deh=None):
         xn, pos, *params = ctx.saved_tensors
         plan, precision = ctx.plan, ctx.precision
+        if d_node is None:
+            d_node = torch.zeros((plan.N, 128), device=xn.device)
+        if d_edge is None:
+            d_edge = torch.zeros((plan.E, 128), device=xn.device)
         gn = mlp_backward(_lib.FVGN_MLP_ENC_NODE, precision, plan.N, params[:8], xn, None, None, None, _c(d_node),
                           packed=ctx.pk[0], z1=ctx.z1[0])
         ge = mlp_backward(_lib.FVGN_MLP_ENC_EDGE, precision, plan.E, params[8:], xn, pos, plan.edge_s, plan.edge_r,
@@ -267,6 +272,7 @@ class GnBlockFn(torch.autograd.Function):
     def forward(ctx, x, e, xh, eh, plan, precision, *params):
         eb, nb = params[:8], params[8:]
         x, e = _c(x), _c(e)
+        ctx.set_materialize_grads(False)  # no zero tensors for the (non-differentiable) bf16 shadow outputs
         ctx.pk = (_packed(_lib.FVGN_MLP_EDGE, precision, eb), _packed(_lib.FVGN_MLP_NODE, precision, nb))
         ctx.plan, ctx.precision = plan, precision
         if precision == "bf16":
