@@ -300,7 +300,8 @@ def run_ours(args):
 
 # DRAM bytes per edge of the two kernels of one fused edge-MLP backward call, from the committed ncu capture
 # profiles/r1e_ncu_tc_kernels_2Medges.csv (dram__bytes_read.sum + dram__bytes_write.sum, 2 M edges, N = E/2):
-NCU_TRAFFIC_BYTES_PER_EDGE = {"bf16": None, "fp32": None}
+#   A: 1.808529 + 0.496310 GB, B: 2.321003 + 2.026685 GB  ->  6.652527 GB / 2e6 edges
+NCU_TRAFFIC_BYTES_PER_EDGE = {"bf16": 6.652527e9 / 2.0e6, "fp32": None}
 
 
 def dominant_kernel_roofline(model, plan, dev, args, p):
