@@ -171,6 +171,9 @@ def run_ours(args):
         raise RuntimeError("bench.py --impl ours needs a CUDA device: this package has no CPU path")
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
+    # the reference's scripts run their (cuBLAS) Linear layers in TF32 (src/pre_train_Adam.py:29); only the PyTorch
+    # Transolver blocks of --net TransFVGN_v* are affected here, the GN / FV kernels never go through cuBLAS
+    torch.set_float32_matmul_precision("high")
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
 

@@ -23,24 +23,32 @@ class Graph_Physics_Attention_1D(nn.Module):
         self.to_out = nn.Sequential(nn.Linear(inner_dim, dim), nn.Dropout(dropout))
 
     def graph_forward(self, x, batch, graph_ptr=None):
+        """GraphTransolver.py:48-95.  The slice / de-slice contractions are written as ONE dense GEMM each against the
+        head-block-diagonal operand ([n, H*G]^T @ [n, H*D] and [n, H*G] @ blockdiag[H*G, H*D]) instead of H batched
+        GEMMs with K = n: same numbers, an order of magnitude faster at million-node scale (the off-diagonal head
+        blocks of the [H*G, H*D] product are never read)."""
         n = x.size(0)
+        H, D = self.heads, self.dim_head
         if graph_ptr is None:
             counts = torch.bincount(batch.reshape(-1).long())
             graph_ptr = [0] + torch.cumsum(counts, 0).cpu().tolist()
-        fx_mid = self.in_project_fx(x).view(n, self.heads, self.dim_head)
-        x_mid = self.in_project_x(x).view(n, self.heads, self.dim_head)
+        fx_mid = self.in_project_fx(x)                                          # [n, H*D]
+        x_mid = self.in_project_x(x).view(n, H, D)
         sw = torch.softmax(self.in_project_slice(x_mid) / self.graph_temperature, dim=-1)  # [n,H,G]
+        G = sw.shape[-1]
+        swf = sw.reshape(n, H * G)
         outs = []
         for b in range(len(graph_ptr) - 1):
             lo, hi = graph_ptr[b], graph_ptr[b + 1]
-            swb, fxb = sw[lo:hi], fx_mid[lo:hi]
-            norm = swb.sum(0)                                                  # [H,G]
-            tok = torch.einsum("nhg,nhd->hgd", swb, fxb) / (norm.unsqueeze(-1) + 1e-5)
+            swb, fxb = swf[lo:hi], fx_mid[lo:hi]
+            norm = swb.sum(0).view(H, G)                                       # [H,G]
+            full = (swb.t() @ fxb).view(H, G, H, D)                            # all head pairs; the diagonal is wanted
+            tok = torch.stack([full[h, :, h, :] for h in range(H)], 0) / (norm.unsqueeze(-1) + 1e-5)
             q, k, v = self.to_q(tok), self.to_k(tok), self.to_v(tok)
             attn = torch.softmax(torch.matmul(q, k.transpose(-1, -2)) * self.scale, dim=-1)
             out_tok = torch.matmul(attn, v)                                    # [H,G,D]
-            outs.append(torch.einsum("nhg,hgd->nhd", swb, out_tok))
-        out_x = torch.cat(outs, 0).reshape(n, self.heads * self.dim_head)
+            outs.append(swb @ torch.block_diag(*out_tok.unbind(0)))            # [nb, H*D]
+        out_x = outs[0] if len(outs) == 1 else torch.cat(outs, 0)
         return self.to_out(out_x)
 
 
