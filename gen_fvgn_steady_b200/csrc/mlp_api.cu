@@ -88,6 +88,7 @@ static int check_common(const fvgn_mlp_desc* d) {
 }
 
 extern "C" int fvgn_mlp_forward(const fvgn_mlp_desc* d, void* stream) {
+  if (d && d->rows == 0 && d->mode >= FVGN_MLP_EDGE && d->mode <= FVGN_MLP_DEC) return FVGN_OK;  // empty graph: nothing to do
   int rc = check_common(d);
   if (rc) return rc;
   if ((d->mode == FVGN_MLP_EDGE || d->mode == FVGN_MLP_NODE) ? (!d->out_res && !d->out && !d->outh) : !d->out) return FVGN_ERR_NULL;
@@ -101,6 +102,16 @@ extern "C" int fvgn_mlp_forward(const fvgn_mlp_desc* d, void* stream) {
 }
 
 extern "C" int fvgn_mlp_backward(const fvgn_mlp_desc* d, void* stream) {
+  if (d && d->rows == 0 && d->mode >= FVGN_MLP_EDGE && d->mode <= FVGN_MLP_DEC) {  // empty graph: zero parameter gradients
+    if (!d->d_params) return FVGN_ERR_NULL;
+#ifndef FVGN_EMU
+    if (cudaMemsetAsync(d->d_params, 0, (size_t)fvgn_mlp_param_count_impl(d->mode) * sizeof(float), (cudaStream_t)stream) != cudaSuccess)
+      return FVGN_ERR_LAUNCH;
+#else
+    for (int64_t i = 0; i < fvgn_mlp_param_count_impl(d->mode); ++i) d->d_params[i] = 0.f;
+#endif
+    return FVGN_OK;
+  }
   int rc = check_common(d);
   if (rc) return rc;
   if (!d->d_out || !d->partials || !d->d_params || d->n_partials < 1) return FVGN_ERR_NULL;

@@ -176,7 +176,7 @@ def mlp_backward(mode, precision, rows, params, in0, in1, idx_s, idx_r, d_out, d
     packed: the bf16 weight image used by the matching forward (bf16 mode); repacked from `params` when None.
     z1: the Z1Image the matching bf16 forward filled; when None (stand-alone use) the forward is re-run to make it.
     d_in0h: EDGE, bf16 mode: [E,256] bf16 destination of d(agg[s])|d(agg[r]) (instead of the fp32 d_in0)."""
-    if precision == "bf16" and z1 is None:
+    if precision == "bf16" and z1 is None and rows > 0:
         z1 = new_z1(mode, precision, rows, d_out)
         mlp_forward(mode, precision, rows, params, in0, in1, idx_s, idx_r, want_out=True, want_res=False, flags=flags,
                     packed=packed, z1=z1, in0h=in0h, in1h=in1h)
@@ -194,7 +194,7 @@ def mlp_backward(mode, precision, rows, params, in0, in1, idx_s, idx_r, d_out, d
         d.d_gatherh = hptr(d_gatherh)
     d.partials, d.n_partials, d.d_params = fptr(partials), npart, fptr(flat)
     ws_bytes = int(lib.fvgn_mlp_bwd_workspace_bytes(mode, PREC[precision], rows))
-    if ws_bytes > 0:
+    if ws_bytes > 0 and rows > 0:
         d._ws, d.workspace = _img_buffer(ws_bytes, d_out.device)
         d._z1, d.z1_img = z1, z1.ptr
     _lib.call("fvgn_mlp_backward", ctypes.byref(d), _lib.stream_ptr(d_out.device))

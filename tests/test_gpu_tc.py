@@ -214,3 +214,44 @@ def test_chunk_reduce_is_bit_identical_to_row_kernel(width, flag):
         outs.append(out)
     torch.cuda.synchronize()
     assert torch.equal(outs[0], outs[1])
+
+
+@pytest.mark.parametrize("mode", ["EDGE", "NODE", "DEC"])
+@pytest.mark.parametrize("rows", [1, 127, 128, 129, 128 * 148])
+def test_tc_ragged_row_counts(mode, rows):
+    """Ragged sizes: fewer rows than one tile, exactly one tile, one row more, exactly one tile per SM -- forward against
+    the bf16 emulation, backward against the fp32 kernels; rows past the end must never be written."""
+    from gen_fvgn_steady_b200 import ops
+    dev = torch.device("cuda")
+    nodes = 300
+    code, params, in0, in1, s, r, X, res = _inputs(mode, rows, nodes, dev, seed=7)
+    want_res = mode in ("EDGE", "NODE")
+    out, out_res = ops.mlp_forward(code, "bf16", rows, params, in0, in1, s, r, want_out=True, want_res=want_res)
+    ref = _emulate(X, params, True)
+    assert torch.isfinite(out).all()
+    assert float((out - ref).abs().max() / ref.abs().max().clamp(min=1e-6)) < 8e-3
+    g = torch.Generator(device=dev).manual_seed(8)
+    nout = 3 if mode == "DEC" else 128
+    d_out = torch.randn((rows, nout), device=dev, generator=g)
+    d_gather = torch.randn((nodes, 64), device=dev, generator=g) if mode == "EDGE" else None
+    refb = _bwd_run(code, mode, "fp32", rows, nodes, params, in0, in1, s, r, d_out, d_gather)
+    gotb = _bwd_run(code, mode, "bf16", rows, nodes, params, in0, in1, s, r, d_out, d_gather)
+    for a, b in zip(gotb[0], refb[0]):
+        assert torch.isfinite(a).all()
+        assert float((a - b).norm() / b.norm().clamp(min=1e-20)) < 4e-2
+    for a, b in ((gotb[1], refb[1]), (gotb[2], refb[2])):
+        if a is not None:
+            assert float((a - b).norm() / b.norm().clamp(min=1e-20)) < 4e-2
+
+
+def test_tc_zero_rows():
+    """Empty input: forward is a no-op, backward returns zero parameter gradients (an empty graph in a batch)."""
+    from gen_fvgn_steady_b200 import ops
+    dev = torch.device("cuda")
+    code, params, in0, in1, s, r, X, res = _inputs("NODE", 0, 10, dev)
+    out, _ = ops.mlp_forward(code, "bf16", 0, params, in0, in1, s, r)
+    assert out.shape == (0, 128)
+    d_in0, d_in1 = torch.zeros((0, 64), device=dev), torch.zeros((0, 128), device=dev)
+    grads = ops.mlp_backward(code, "bf16", 0, params, in0, in1, s, r, torch.zeros((0, 128), device=dev), None, d_in0, d_in1)
+    torch.cuda.synchronize()
+    assert all(float(g.abs().max()) == 0.0 for g in grads)
