@@ -38,6 +38,9 @@ def parse_args():
                     help="bf16: tcgen05 throughput mode (default); fp32: SIMT parity mode")
     ap.add_argument("--cpu-cells", type=int, default=40_000, help="cell count of the bounded CPU-baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--graph", action="store_true",
+                    help="replay the whole step (fwd + bwd + Adam) as ONE CUDA graph (gen_fvgn_steady_b200.graphed); for the "
+                         "launch-bound sizes of the reference's example meshes (10 k - 100 k cells), single GPU")
     ap.add_argument("--parallel", default="dp", choices=["dp", "cells"],
                     help="N>1: dp = one mesh of --cells cells per GPU, gradient all-reduce (weak scaling, the default the "
                          "driver measures); cells = ONE mesh of --cells cells partitioned over the GPUs with a per-GnBlock "
@@ -150,7 +153,7 @@ def run_reference(args):
 def workload_config(args, C_bench=None):
     return {"workload": f"synthetic jittered quad mesh, {args.cells} cells/GPU, cavity BC, NS theta; "
                         f"{args.net} G={args.mp} + FV PDE loss; resident batch (solve_with_grad regime)",
-            "net": args.net, "gn_blocks": args.mp, "cells_per_gpu": args.cells if C_bench is None else C_bench,
+            "net": args.net, "gn_blocks": args.mp, "cuda_graph": bool(getattr(args, "graph", False)), "cells_per_gpu": args.cells if C_bench is None else C_bench,
             "precision": args.precision, "l2": "inputs/activations (GBs) far exceed the 126 MB L2; no explicit flush"}
 
 
@@ -200,7 +203,7 @@ def run_ours(args):
     elif world > 1:
         model.enable_data_parallel(True)
     flat_grad = parallel.flatten_gradients(model)
-    opt = torch.optim.Adam(model.parameters(), lr=p.lr, fused=True)
+    opt = torch.optim.Adam(model.parameters(), lr=p.lr, fused=True, capturable=bool(args.graph))
     plan = GraphPlan.of(gn, gx, ge, gc, p.order)
     N, E, C, K, X = plan.N, plan.E, plan.C, plan.K, int(gx.face_node_x.shape[1])
     x_host = gn.x.detach().cpu().pin_memory()
@@ -229,6 +232,24 @@ def run_ours(args):
             loss_host.copy_(loss.detach(), non_blocking=True)
         return loss
 
+    gstep = None
+    if args.graph:
+        if world > 1:
+            raise SystemExit("--graph is a single-GPU option")
+        from gen_fvgn_steady_b200.graphed import GraphedTrainStep
+        gn.x, gn.norm_uvp, gn.norm_global = x_dev0.clone(), True, True
+        script_loss = lambda out: torch.mean(torch.log(p.loss_press * out[3] + p.loss_cont * out[0] + p.loss_mom * out[1]
+                                                       + p.loss_mom * out[2]))
+        gstep = GraphedTrainStep(model, opt, graphs, script_loss, warmup=max(args.warmup, 3))
+        eager_step = step
+
+        def step(e2e):  # noqa: F811  -- same contract as the eager step
+            loss = gstep.step(x_host if e2e else None)
+            if e2e:
+                uvp_host.copy_(gstep.out[4], non_blocking=True)
+                loss_host.copy_(loss.detach(), non_blocking=True)
+            return loss
+
     def timed(nsteps, e2e):
         if world > 1:
             dist.barrier()
@@ -252,12 +273,17 @@ def run_ours(args):
 
     for _ in range(max(args.warmup, 3)):
         step(False)
+    launches_per_replay = None
+    if gstep is not None:  # count the kernels of one step with the eager path (the graph replays exactly those)
+        l_ = _lib.launch_count
+        eager_step(False)
+        launches_per_replay = _lib.launch_count - l_
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
     l0 = _lib.launch_count
     ms = timed(args.steps, False)
-    launches = _lib.launch_count - l0
+    launches = _lib.launch_count - l0 if gstep is None else launches_per_replay * args.steps
     step(True)
     ms_e2e = timed(args.steps, True)
     clocks = sampler.stop() if rank == 0 else None

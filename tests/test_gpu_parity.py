@@ -81,3 +81,42 @@ def test_product_bf16_within_stated_tolerance(name):
     for k in ("loss_cont", "loss_mom_x", "loss_mom_y", "loss_press", "uvp_node", "uvp_cell", "loss"):
         assert rep[k] < 1e-2, (k, rep[k])
     assert rep["decoder_out"] < 3e-2, rep["decoder_out"]
+
+
+def test_graphed_step_matches_eager_steps():
+    """GraphedTrainStep (whole fwd + bwd + Adam step as one CUDA graph) reproduces the eager training steps bit for bit."""
+    import copy
+    from gen_fvgn_steady_b200.FVMmodel.importer import NNmodel
+    from gen_fvgn_steady_b200.graphed import GraphedTrainStep
+    from gen_fvgn_steady_b200.utils.get_param import params as default_params
+    from gen_fvgn_steady_b200.mesh import synthetic as S
+    from tests.case_inputs import product_graphs
+    PU.use_real_kernels()
+    dev = torch.device("cuda")
+    mesh, uvp = S.make_case(20, kind="mixed", bc="channel", seed=2)
+    p = default_params(net="EPD", message_passing_num=2, dataset_size=1, precision="bf16")
+    torch.manual_seed(0)
+    model_a = NNmodel(p).to(dev)
+    model_b = copy.deepcopy(model_a)
+    loss_fn = lambda out: PU.script_loss(out, p)
+    losses = {}
+    for tag, model in (("eager", model_a), ("graph", model_b)):
+        graphs = product_graphs([mesh], [uvp], dev)
+        x0 = graphs[0].x.clone()
+        opt = torch.optim.Adam(model.parameters(), lr=1e-3, fused=True, capturable=True)
+        ls = []
+        if tag == "eager":
+            for _ in range(6):
+                graphs[0].x, graphs[0].norm_uvp, graphs[0].norm_global = x0, True, True
+                opt.zero_grad(set_to_none=True)
+                loss = loss_fn(model(*graphs, is_training=True))
+                loss.backward()
+                opt.step()
+                ls.append(float(loss.detach()))
+        else:
+            gs = GraphedTrainStep(model, opt, graphs, loss_fn, warmup=3)   # 3 eager warm-up steps + the capture pass (not run)
+            ls = [None] * 3
+            for _ in range(3):
+                ls.append(float(gs.step().detach()))
+        losses[tag] = ls
+    assert losses["graph"][3:] == losses["eager"][3:], losses
