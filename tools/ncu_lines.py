@@ -1,7 +1,10 @@
-"""Aggregate the warp-stall samples of an .ncu-rep by source line: python tools/ncu_lines.py rep [topN]"""
+"""Aggregate the warp-stall samples of an .ncu-rep by source line: python tools/ncu_lines.py rep [topN] [kernel regex]"""
 import csv, subprocess, sys, io
 rep = sys.argv[1]; top = int(sys.argv[2]) if len(sys.argv) > 2 else 25
-out = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv", "--print-source", "cuda,sass"], capture_output=True, text=True).stdout
+cmd = ["ncu", "-i", rep, "--page", "source", "--csv", "--print-source", "cuda,sass"]
+if len(sys.argv) > 3:
+    cmd += ["--kernel-name", "regex:" + sys.argv[3]]
+out = subprocess.run(cmd, capture_output=True, text=True).stdout
 rows = list(csv.reader(io.StringIO(out)))
 hi = [i for i, r in enumerate(rows) if r and r[0] == "Line No"][0]
 h = rows[hi]
