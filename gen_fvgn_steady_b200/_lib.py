@@ -144,6 +144,8 @@ def check(rc, what):
 
 
 # kernels launched per C-ABI call (for bench.py's gpu_launches claim)
+# (fvgn_mlp_backward: kernel A + kernel B + the deterministic partial reduction in bf16 mode, kernel + reduction in fp32 mode:
+#  counted as 2, a lower bound)
 LAUNCHES_PER_CALL = {"fvgn_mlp_backward": 2, "fvgn_fv_backward": 2, "fvgn_fv_outputs": 2}
 launch_count = 0
 

@@ -53,22 +53,6 @@ __device__ __forceinline__ void load_tile16(const uint8_t* buf, int row, int c0,
   const uint4 b = *reinterpret_cast<const uint4*>(buf + kb * KB_BYTES + sw128_off(row, chunk + 1));
   w[0] = a.x; w[1] = a.y; w[2] = a.z; w[3] = a.w; w[4] = b.x; w[5] = b.y; w[6] = b.z; w[7] = b.w;
 }
-// column sums of a bf16 tile: thread t owns column pair (2p, 2p+1), p = t & 63, over rows [64*(t>>6), +64)
-__device__ __forceinline__ void tile_colsum(const uint8_t* buf, int t, float& s0, float& s1) {
-  const int p = t & 63, r0 = (t >> 6) * 64;
-  const int kb = (2 * p) >> 6, chunk = ((2 * p) & 63) >> 3, word = p & 3;
-  const uint8_t* base = buf + kb * KB_BYTES + word * 4;
-  float a = 0.f, b = 0.f;
-#pragma unroll 8
-  for (int r = r0; r < r0 + 64; ++r) {
-    const uint32_t w = *reinterpret_cast<const uint32_t*>(base + sw128_off(r, chunk));
-    a += bf16_lo(w);
-    b += bf16_hi(w);
-  }
-  s0 += a;
-  s1 += b;
-}
-
 // =============================================================================================== kernel A
 // Roles (448 threads): warps 0-7 epilogue (thread <-> (row, column half): warps w and w+4 share a TMEM lane quarter and
 // split the 128 columns), warps 8-11 stage the upstream-gradient tile dO as bf16, warp 12 issues the MMAs, warp 13 is the

@@ -100,18 +100,6 @@ __device__ __forceinline__ uint64_t make_desc_k128(uint32_t saddr) {
 // instruction descriptor: D=f32, A=B=bf16, both K-major, M=128, N=128 (cute::UMMA::InstrDescriptor)
 constexpr uint32_t IDESC = (1u << 4) | (1u << 7) | (1u << 10) | ((128u >> 3) << 17) | ((128u >> 4) << 24);
 
-// erf via Abramowitz-Stegun 7.1.26 (|err| < 1.5e-7): MUFU ex2 + rcp, ~14 instructions
-__device__ __forceinline__ float gelu_fast(float x) {
-  const float z = fabsf(x) * 0.70710678118654752f;
-  const float t = __fdividef(1.0f, fmaf(0.3275911f, z, 1.0f));
-  float p = fmaf(1.061405429f, t, -1.453152027f);
-  p = fmaf(p, t, 1.421413741f);
-  p = fmaf(p, t, -0.284496736f);
-  p = fmaf(p, t, 0.254829592f);
-  const float e = 1.0f - p * t * __expf(-z * z);
-  return 0.5f * x * (1.0f + copysignf(e, x));
-}
-
 // Throughput-mode GELU: tanh form evaluated with the MUFU.TANH approximation (6 instructions).
 // |gelu_tanh - gelu_erf| <= 3e-4 absolute, below the bf16 rounding the value receives right afterwards.
 __device__ __forceinline__ float tanh_approx(float x) {
@@ -403,20 +391,6 @@ __device__ __forceinline__ void for_each_chunk16(uint32_t taddr, F&& f) {
     f(c0 + 16, rb);
     tmem_wait_ld();
   }
-}
-
-// gelu(x) and gelu'(x) from one erf/exp evaluation (A&S 7.1.26)
-__device__ __forceinline__ void gelu_pair(float x, float& h, float& g) {
-  const float z = fabsf(x) * 0.70710678118654752f;
-  const float t = __fdividef(1.0f, fmaf(0.3275911f, z, 1.0f));
-  float p = fmaf(1.061405429f, t, -1.453152027f);
-  p = fmaf(p, t, 1.421413741f);
-  p = fmaf(p, t, -0.284496736f);
-  p = fmaf(p, t, 0.254829592f);
-  const float ex = __expf(-z * z);  // = exp(-x^2/2)
-  const float cdf = 0.5f * (1.0f + copysignf(1.0f - p * t * ex, x));
-  h = x * cdf;
-  g = fmaf(x * 0.39894228040143268f, ex, cdf);
 }
 
 __device__ __forceinline__ float bf16_lo(uint32_t w) { return __uint_as_float(w << 16); }

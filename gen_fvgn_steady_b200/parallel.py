@@ -47,54 +47,73 @@ def allreduce_normalizer(normalizer, pending, group=None):
 
 
 # ----------------------------------------------------------------------------------------------- halo exchange
-def _exchange(x, rows, group, reverse):
-    """forward : ghost rows of x <- the owners' rows (contiguous receives, index-gather sends), in place.
+def _exchange(pairs, group, reverse):
+    """pairs = [(tensor, rows), ...] exchanged in ONE grouped NCCL call.
+    forward : ghost rows <- the owners' rows (contiguous receives, index-gather sends), in place.
     reverse : ghost rows' values are sent back to the owners and ADDED to the rows they mirror; ghost rows <- 0."""
     ops_, keep = [], []
-    peers = sorted(set(rows["send"].keys()) | set(rows["recv"].keys()))
-    for q in peers:
-        if not reverse:
-            if q in rows["send"]:
-                buf = x.index_select(0, rows["send"][q])
-                keep.append(buf)
-                ops_.append(dist.P2POp(dist.isend, buf, q, group=group))
-            if q in rows["recv"]:
-                st, cnt = rows["recv"][q]
-                ops_.append(dist.P2POp(dist.irecv, x[st:st + cnt], q, group=group))
-        else:
-            if q in rows["recv"]:
-                st, cnt = rows["recv"][q]
-                ops_.append(dist.P2POp(dist.isend, x[st:st + cnt], q, group=group))
-            if q in rows["send"]:
-                buf = torch.empty((rows["send"][q].numel(),) + tuple(x.shape[1:]), dtype=x.dtype, device=x.device)
-                keep.append((q, buf))
-                ops_.append(dist.P2POp(dist.irecv, buf, q, group=group))
+    for x, rows in pairs:
+        peers = sorted(set(rows["send"].keys()) | set(rows["recv"].keys()))
+        for q in peers:
+            if not reverse:
+                if q in rows["send"]:
+                    buf = x.index_select(0, rows["send"][q])
+                    keep.append(buf)
+                    ops_.append(dist.P2POp(dist.isend, buf, q, group=group))
+                if q in rows["recv"]:
+                    st, cnt = rows["recv"][q]
+                    ops_.append(dist.P2POp(dist.irecv, x[st:st + cnt], q, group=group))
+            else:
+                if q in rows["recv"]:
+                    st, cnt = rows["recv"][q]
+                    ops_.append(dist.P2POp(dist.isend, x[st:st + cnt], q, group=group))
+                if q in rows["send"]:
+                    buf = torch.empty((rows["send"][q].numel(),) + tuple(x.shape[1:]), dtype=x.dtype, device=x.device)
+                    keep.append((x, rows, q, buf))
+                    ops_.append(dist.P2POp(dist.irecv, buf, q, group=group))
     if ops_:
         for w in dist.batch_isend_irecv(ops_):
             w.wait()
     if reverse:
-        for q, buf in keep:  # ascending peer order: deterministic
+        for x, rows, q, buf in keep:  # ascending peer order per tensor: deterministic
             x.index_add_(0, rows["send"][q], buf)
-        if rows["n_local"] > rows["n_owned"]:
-            x[rows["n_owned"]:].zero_()
+        for x, rows in pairs:
+            if rows["n_local"] > rows["n_owned"]:
+                x[rows["n_owned"]:].zero_()
 
 
 class HaloExchangeFn(torch.autograd.Function):
-    """x[ghost rows] <- owner values (in place).  backward: d x[owned rows] += the ghosts' gradients from every rank
-    that mirrors them, d x[ghost rows] = 0 (their pre-exchange values are dead)."""
+    """(x, e)[ghost rows] <- owner values (in place, one grouped exchange for both latents).  backward: the gradients of
+    the owned rows receive (+=) the ghosts' gradients from every rank that mirrors them, the ghost rows' gradients are 0
+    (their pre-exchange values are dead)."""
 
     @staticmethod
-    def forward(ctx, x, rows, group):
-        ctx.rows, ctx.group = rows, group
-        _exchange(x, rows, group, reverse=False)
-        ctx.mark_dirty(x)
-        return x
+    def forward(ctx, x, e, rows_x, rows_e, group):
+        ctx.rows, ctx.group = (rows_x, rows_e), group
+        ctx.set_materialize_grads(False)
+        _exchange([(x, rows_x), (e, rows_e)], group, reverse=False)
+        ctx.mark_dirty(x, e)
+        return x, e
 
     @staticmethod
-    def backward(ctx, g):
-        g = g.contiguous().clone()
-        _exchange(g, ctx.rows, ctx.group, reverse=True)
-        return g, None, None
+    def backward(ctx, gx, ge):
+        rows_x, rows_e = ctx.rows
+        pairs = []
+        if gx is not None:
+            gx = gx.contiguous().clone()
+            pairs.append((gx, rows_x))
+        if ge is not None:
+            ge = ge.contiguous().clone()
+            pairs.append((ge, rows_e))
+        # both ranks of a pair must post matching operations: a missing gradient is an all-zero one
+        if gx is None:
+            gx = torch.zeros((rows_x["n_local"], 128), device=ge.device)
+            pairs.insert(0, (gx, rows_x))
+        if ge is None:
+            ge = torch.zeros((rows_e["n_local"], 128), device=gx.device)
+            pairs.append((ge, rows_e))
+        _exchange(pairs, ctx.group, reverse=True)
+        return gx, ge, None, None, None
 
 
 def halo_refresh(graph, group=None):
@@ -103,12 +122,12 @@ def halo_refresh(graph, group=None):
     halo = getattr(graph, "_fvgn_halo", None)
     if halo is None or halo.world == 1:
         return graph
-    for attr, key, kind in (("x", "_xh", "node"), ("edge_attr", "_eh", "edge")):
+    x, e = graph.x, graph.edge_attr
+    cx, ce = getattr(graph, "_xh", None), getattr(graph, "_eh", None)
+    x2, e2 = HaloExchangeFn.apply(x, e, halo.rows["node"], halo.rows["edge"], group)
+    graph.x, graph.edge_attr = x2, e2
+    for t, t2, cached, key, kind in ((x, x2, cx, "_xh", "node"), (e, e2, ce, "_eh", "edge")):
         rows = halo.rows[kind]
-        t = getattr(graph, attr)
-        cached = getattr(graph, key, None)
-        t2 = HaloExchangeFn.apply(t, rows, group)
-        setattr(graph, attr, t2)
         sh = cached[1] if (cached is not None and cached[0] is t) else None
         if sh is not None and rows["n_local"] > rows["n_owned"]:
             sh[rows["n_owned"]:] = t2.detach()[rows["n_owned"]:].to(sh.dtype)
