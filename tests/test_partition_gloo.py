@@ -11,7 +11,7 @@ import torch
 import torch.distributed as dist
 import torch.multiprocessing as mp
 
-MESH = dict(n=18, kind="mixed", bc="channel", seed=3)
+MESH = dict(n=14, kind="mixed", bc="channel", seed=3)
 MP_NUM = 2
 
 
