@@ -41,6 +41,9 @@ def parse_args():
     ap.add_argument("--graph", action="store_true",
                     help="replay the whole step (fwd + bwd + Adam) as ONE CUDA graph (gen_fvgn_steady_b200.graphed); for the "
                          "launch-bound sizes of the reference's example meshes (10 k - 100 k cells), single GPU")
+    ap.add_argument("--halo-layers", type=int, default=3,
+                    help="--parallel cells: halo depth in cell layers; 3 = ghost refresh after every GnBlock, 6 = every 2nd "
+                         "block, >= 3*mp+2 = no latent exchange at all (more redundant compute, no per-block synchronisation)")
     ap.add_argument("--parallel", default="dp", choices=["dp", "cells"],
                     help="N>1: dp = one mesh of --cells cells per GPU, gradient all-reduce (weak scaling, the default the "
                          "driver measures); cells = ONE mesh of --cells cells partitioned over the GPUs with a per-GnBlock "
@@ -186,7 +189,7 @@ def run_ours(args):
         from gen_fvgn_steady_b200 import partition
         mesh, uvp = make_mesh(args.cells, 0, dev)            # the same global mesh on every rank
         C_global = int(mesh["cell|centroid"].shape[0])
-        mesh, uvp, halo = partition.build(mesh, uvp, world, rank, device=dev)
+        mesh, uvp, halo = partition.build(mesh, uvp, world, rank, halo_layers=args.halo_layers, device=dev)
         torch.cuda.empty_cache()
     else:
         mesh, uvp = make_mesh(args.cells, rank, dev)
@@ -306,7 +309,9 @@ def run_ours(args):
             "dtype": "f32" if args.precision == "fp32" else "bf16 (fp32 accumulate/storage)",
             "data": "synthetic", "config": dict(workload_config(args, C_bench=C), N=N, E=E, C=C, K=K, X=X,
                                                 parallelism=(f"cells{world} (one {C_global}-cell mesh, RCB partition, "
-                                                             f"3-layer halo, exchange per GnBlock; rank 0: "
+                                                             f"{args.halo_layers}-layer halo, "
+                                                             f"{sum(halo.wants_exchange(i, args.mp) for i in range(args.mp))} "
+                                                             f"ghost refreshes per forward; rank 0: "
                                                              f"{halo.n_owned_cells} owned of {C} local cells)") if cells_mode
                                                 else f"dp{world}", loss=last_loss),
             "clocks": clocks, "gpu_launches": launches,

@@ -111,7 +111,8 @@ class EncoderProcesserDecoder(nn.Module):
     def forward(self, graph_node=None, graph_edge=None, graph_cell=None):
         from ....parallel import halo_refresh
         latent, _ = self.encoder(graph_node)  # point-wise in nodes / edges: exact on the ghost rows too
-        for model in self.GN_block_list:
+        nblk = len(self.GN_block_list)
+        for i, model in enumerate(self.GN_block_list):
             latent = model(latent)
-            latent = halo_refresh(latent)     # cell-partition mode only: ghost rows <- owners (no-op otherwise)
+            latent = halo_refresh(latent, i, nblk)  # cell-partition mode only: ghost rows <- owners (no-op otherwise)
         return self.decoder(latent)

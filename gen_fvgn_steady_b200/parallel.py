@@ -116,11 +116,13 @@ class HaloExchangeFn(torch.autograd.Function):
         return gx, ge, None, None, None
 
 
-def halo_refresh(graph, group=None):
-    """Refresh the ghost rows of graph.x / graph.edge_attr (and of their bf16 shadows) after a GnBlock.  No-op when the
-    graph is not a partitioned sub-mesh."""
+def halo_refresh(graph, block_index=0, n_blocks=1, group=None):
+    """Refresh the ghost rows of graph.x / graph.edge_attr (and of their bf16 shadows) after GnBlock `block_index` of
+    `n_blocks`.  No-op when the graph is not a partitioned sub-mesh, or when the halo is deep enough for this block's
+    result to be exact without it (partition.HaloPlan.wants_exchange: a halo of 3k layers needs an exchange only after
+    every k-th block; 3 n_blocks + 2 layers need none at all)."""
     halo = getattr(graph, "_fvgn_halo", None)
-    if halo is None or halo.world == 1:
+    if halo is None or halo.world == 1 or not halo.wants_exchange(block_index, n_blocks):
         return graph
     x, e = graph.x, graph.edge_attr
     cx, ce = getattr(graph, "_xh", None), getattr(graph, "_eh", None)

@@ -5,7 +5,9 @@ The reference has no multi-GPU path; this module defines one whose result equals
 
 * cells are split by recursive coordinate bisection of their centroids (balanced, contiguous parts);
 * a node / face is OWNED by the lowest rank among its incident cells;
-* rank r keeps its owned cells plus HALO_LAYERS = 3 layers of neighbouring cells (cells sharing a node).  One GnBlock
+* rank r keeps its owned cells plus `halo_layers` (default 3) layers of neighbouring cells (cells sharing a node);
+  deeper halos trade redundant compute for fewer exchanges (6 layers: every 2nd block; 3 G + 2 layers: none at all, the
+  only collectives left are the [B,k]-sized statistics and the gradient all-reduce).  One GnBlock
   reads the node latents within 3 hops (blocks.py: x' <- a2 <- a1(neighbours) <- e'(their edges) <- agg(both ends) <-
   x(neighbours)), and the WLSQ stencil reaches 2 hops, so after every ghost row has been refreshed from its owner one
   whole block (and the FV loss of the owned cells) is computed locally and exactly on the owned rows; the outer halo
@@ -75,6 +77,16 @@ class HaloPlan:
         self.n_owned_cells = 0
         self.cell_gid = None
         self.num_graphs = 1
+        self.layers = HALO_LAYERS
+
+    def wants_exchange(self, block_index, n_blocks):
+        """Is a ghost refresh needed after GnBlock `block_index` (0-based) of `n_blocks`?  One block invalidates 3 more
+        halo layers; the decoder + WLSQ + FV stage needs the 2 innermost layers exact.  With `layers` halo layers the
+        ghosts are refreshed after every k = layers // 3 blocks and after the last one; 3 n_blocks + 2 layers never."""
+        if self.layers >= 3 * n_blocks + 2:
+            return False
+        k = max(self.layers // 3, 1)
+        return (block_index + 1) % k == 0 or block_index == n_blocks - 1
 
     def to(self, device):
         for r in self.rows.values():
@@ -118,6 +130,8 @@ def build(mesh, uvp, world, rank, halo_layers=HALO_LAYERS, device=None):
     """-> (local mesh dict, local initial field, HaloPlan) for `rank` of `world`.
 
     mesh: the converter / loader dictionary of the GLOBAL mesh (SURVEY.md Appendix B keys, numpy or torch)."""
+    if halo_layers < 3:
+        raise ValueError("halo_layers must be >= 3 (one GnBlock reads latents 3 hops away)")
     dev = device
     cn = _t(mesh["cells_node"], dev).reshape(-1).long()
     cf = _t(mesh["cells_face"], dev).reshape(-1).long()
@@ -145,6 +159,7 @@ def build(mesh, uvp, world, rank, halo_layers=HALO_LAYERS, device=None):
 
     cmask, nmask, fmask, outer_nodes = local_sets(rank)
     halo = HaloPlan(rank, world)
+    halo.layers = halo_layers
     node_gid, n_own_nodes, node_recv = _local_order(nmask, node_owner, rank)
     face_gid, n_own_faces, face_recv = _local_order(fmask, face_owner, rank)
     cell_gid, n_own_cells, _ = _local_order(cmask, part, rank)

@@ -11,8 +11,9 @@ import torch
 import torch.distributed as dist
 import torch.multiprocessing as mp
 
-MESH = dict(n=14, kind="mixed", bc="channel", seed=3)
+MESH = dict(n=10, kind="mixed", bc="channel", seed=3)
 MP_NUM = 2
+_CACHE = {}
 
 
 def _model():
@@ -58,7 +59,7 @@ def _global_case():
     return mesh, uvp
 
 
-def _worker(rank, world, port, ret):
+def _worker(rank, world, port, ret, halo_layers=3):
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
     dist.init_process_group("gloo", rank=rank, world_size=world)
     from tests import product_util as PU
@@ -66,7 +67,7 @@ def _worker(rank, world, port, ret):
     PU.use_emulated_kernels()
     torch.set_num_threads(2)
     mesh, uvp = _global_case()
-    lmesh, luvp, halo = partition.build(mesh, uvp, world, rank)
+    lmesh, luvp, halo = partition.build(mesh, uvp, world, rank, halo_layers=halo_layers)
     out, loss, flat = _run(lmesh, luvp, halo)
     n_own = halo.rows["node"]["n_owned"]
     ret[rank] = dict(losses=[o for o in out[:4]], loss=loss, flat=flat, node_gid=halo.rows["node"]["gid"][:n_own].clone(),
@@ -97,7 +98,9 @@ def test_partition_structure():
     assert abs(halos[0].n_owned_cells - halos[1].n_owned_cells) <= 1
 
 
-def test_cell_partition_matches_single_process():
+@pytest.mark.parametrize("halo_layers", [3, 3 * MP_NUM + 2])
+def test_cell_partition_matches_single_process(halo_layers):
+    """halo_layers = 3: ghost refresh after every GnBlock; 3 G + 2: no latent exchange at all (redundant halo compute)."""
     from tests import product_util as PU
     s = socket.socket()
     s.bind(("127.0.0.1", 0))
@@ -105,14 +108,20 @@ def test_cell_partition_matches_single_process():
     s.close()
     mgr = mp.Manager()
     ret = mgr.dict()
-    mp.spawn(_worker, args=(2, port, ret), nprocs=2, join=True)
-    PU.use_emulated_kernels()
-    try:
-        mesh, uvp = _global_case()
-        out, loss, flat = _run(mesh, uvp, None)
-    finally:
-        PU.use_real_kernels()
+    mp.spawn(_worker, args=(2, port, ret, halo_layers), nprocs=2, join=True)
+    if "ref" not in _CACHE:  # the single-process run of the whole mesh (shared by the parametrised cases)
+        PU.use_emulated_kernels()
+        try:
+            mesh, uvp = _global_case()
+            _CACHE["ref"] = _run(mesh, uvp, None)
+        finally:
+            PU.use_real_kernels()
+    out, loss, flat = _CACHE["ref"]
     assert ret[0]["n_local"] > ret[0]["n_own"]  # there really is a halo
+    from gen_fvgn_steady_b200.partition import HaloPlan
+    hp = HaloPlan(0, 2)
+    hp.layers = halo_layers
+    assert any(hp.wants_exchange(i, MP_NUM) for i in range(MP_NUM)) == (halo_layers == 3)
     for r in range(2):
         for a, b in zip(ret[r]["losses"], out[:4]):
             assert torch.allclose(a, b, rtol=2e-5, atol=1e-7), (r, a, b)
