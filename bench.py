@@ -41,9 +41,9 @@ def parse_args():
     ap.add_argument("--graph", action="store_true",
                     help="replay the whole step (fwd + bwd + Adam) as ONE CUDA graph (gen_fvgn_steady_b200.graphed); for the "
                          "launch-bound sizes of the reference's example meshes (10 k - 100 k cells), single GPU")
-    ap.add_argument("--halo-layers", type=int, default=3,
+    ap.add_argument("--halo-layers", type=int, default=None,
                     help="--parallel cells: halo depth in cell layers; 3 = ghost refresh after every GnBlock, 6 = every 2nd "
-                         "block, >= 3*mp+2 = no latent exchange at all (more redundant compute, no per-block synchronisation)")
+                         "block, >= 3*mp+2 = no latent exchange at all (more redundant compute, no per-block synchronisation; the default)")
     ap.add_argument("--parallel", default="dp", choices=["dp", "cells"],
                     help="N>1: dp = one mesh of --cells cells per GPU, gradient all-reduce (weak scaling, the default the "
                          "driver measures); cells = ONE mesh of --cells cells partitioned over the GPUs with a per-GnBlock "
@@ -184,6 +184,8 @@ def run_ours(args):
         dist.init_process_group("nccl", device_id=dev)
 
     cells_mode = args.parallel == "cells" and world > 1
+    if args.halo_layers is None:
+        args.halo_layers = 3 * args.mp + 2
     halo = None
     if cells_mode:
         from gen_fvgn_steady_b200 import partition
