@@ -160,20 +160,24 @@ template <int W, class TS, class TD, bool INC>
 __global__ void __launch_bounds__(256) pipe_reduce_kernel(const typename TS::elem* __restrict__ src, const int32_t* __restrict__ ptr,
                                                           const int32_t* __restrict__ ent, typename TD::elem* __restrict__ dst,
                                                           int64_t n, int flags) {
-  constexpr int V = W / 32;  // elements per lane
-  constexpr int NB = 4;      // gathers in flight per lane
+  // 512-B rows: one warp per row (32 lanes x 4 elements); 256-B rows: one HALF-warp per row (16 lanes x 4 elements), the
+  // two halves of a warp run independent rows (shuffles are confined to the half by mask + width)
+  constexpr int LPR = W / 4;   // lanes per row: 32 or 16
+  constexpr int V = 4;         // elements per lane
+  constexpr int NB = 4;        // gathers in flight per lane
   constexpr int ROW_LD = INC ? 2 * W : W;
   typedef LaneIO<TS, V> SI;
   typedef LaneIO<TD, V> DI;
-  const int lane = threadIdx.x & 31;
-  const int64_t gw = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-  const int64_t GW = (int64_t)gridDim.x * (blockDim.x >> 5);
+  const int lane = threadIdx.x & (LPR - 1);
+  const unsigned hmask = (LPR == 32) ? 0xffffffffu : (0xffffu << (threadIdx.x & 16));
+  const int64_t gw = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) / LPR;
+  const int64_t GW = (int64_t)gridDim.x * blockDim.x / LPR;
   const bool div_src = !INC && (flags & FVGN_ADJ_DIV_SRC_BY_DEG);
   auto load_ptr = [&](int64_t row, int& b, int& e) {
     b = 0; e = 0;
     if (row < n) { b = __ldg(ptr + row); e = __ldg(ptr + row + 1); }
   };
-  auto load_ent = [&](int b, int e) { return (b + lane < e) ? __ldg(ent + b + lane) : 0; };  // first 32 entries, one per lane
+  auto load_ent = [&](int b, int e) { return (b + lane < e) ? __ldg(ent + b + lane) : 0; };  // first LPR entries, one per lane
   int cb, ce, cent;  // row i: pointers and entries (arrived)
   int nb_, ne_;      // row i+1: pointers (arrived), entries being fetched into nent
   load_ptr(gw, cb, ce);
@@ -186,7 +190,7 @@ __global__ void __launch_bounds__(256) pipe_reduce_kernel(const typename TS::ele
     int code[NB];
 #pragma unroll
     for (int k = 0; k < NB; ++k) {
-      code[k] = __shfl_sync(0xffffffffu, cent, k);
+      code[k] = __shfl_sync(hmask, cent, k, LPR);
       if (k < deg) {
         const int r = INC ? (code[k] >> 1) : code[k];
         const int coff = INC ? (code[k] & 1) * W : 0;
@@ -194,7 +198,7 @@ __global__ void __launch_bounds__(256) pipe_reduce_kernel(const typename TS::ele
       }
     }
     float mydiv = 1.f;  // lane k: degree of the source row of entry k (transposed mean)
-    if (div_src && lane < deg && lane < 32) mydiv = (float)max(__ldg(ptr + cent + 1) - __ldg(ptr + cent), 1);
+    if (div_src && lane < deg) mydiv = (float)max(__ldg(ptr + cent + 1) - __ldg(ptr + cent), 1);
     const int nent = load_ent(nb_, ne_);
     int ab, ae;
     load_ptr(row + 2 * GW, ab, ae);
@@ -208,14 +212,14 @@ __global__ void __launch_bounds__(256) pipe_reduce_kernel(const typename TS::ele
       if (k < deg) {
         float4 x = SI::up(v[k]);
         if (div_src) {
-          const float dv = __shfl_sync(0xffffffffu, mydiv, k);
+          const float dv = __shfl_sync(hmask, mydiv, k, LPR);
           x.x /= dv; x.y /= dv; x.z /= dv; x.w /= dv;
         }
         acc = add4(acc, x);
       }
     }
-    for (int t = NB; t < deg; ++t) {  // long rows: the rest, one at a time (entries beyond 32 straight from memory)
-      const int c = (t < 32) ? __shfl_sync(0xffffffffu, cent, t) : __ldg(ent + cb + t);
+    for (int t = NB; t < deg; ++t) {  // long rows: the rest, one at a time (entries beyond LPR straight from memory)
+      const int c = (t < LPR) ? __shfl_sync(hmask, cent, t, LPR) : __ldg(ent + cb + t);
       const int r = INC ? (c >> 1) : c;
       const int coff = INC ? (c & 1) * W : 0;
       float4 x = SI::up(SI::ld(src + (size_t)r * ROW_LD + coff + lane * V));
@@ -257,7 +261,8 @@ static void launch_pipe(const typename TS::elem* s, const int32_t* ptr, const in
   auto kern = pipe_reduce_kernel<W, TS, TD, INC>;
   static unsigned cap_grid = 0;  // per instantiation
   if (cap_grid == 0) cap_grid = pipe_grid(kern, (int64_t)1 << 40);
-  const int64_t want = (n_rows + 7) / 8;
+  const int rows_per_block = 256 / (W / 4);
+  const int64_t want = (n_rows + rows_per_block - 1) / rows_per_block;
   const unsigned grid = (unsigned)(want < cap_grid ? want : cap_grid);
   kern<<<grid, 256, 0, (cudaStream_t)stream>>>(s, ptr, ent, o, n_rows, flags);
 }
@@ -269,9 +274,9 @@ static int launch_adj(const void* src, const int32_t* ptr, const int32_t* nbr, v
   const typename TS::elem* s = reinterpret_cast<const typename TS::elem*>(src);
   typename TD::elem* o = reinterpret_cast<typename TD::elem*>(dst);
 #ifndef FVGN_EMU
-  // measured on B200 (1 M rows, degree 4): the pipelined kernel wins for 512-B rows (0.28 vs 0.36 ms), not for 256-B rows
-  if (!(flags & FVGN_ADJ_SIMPLE_KERNEL) && width == 128) {
-    launch_pipe<128, TS, TD, false>(s, ptr, nbr, o, n_rows, flags, stream);
+  if (!(flags & FVGN_ADJ_SIMPLE_KERNEL) && (width == 128 || width == 64)) {
+    if (width == 128) launch_pipe<128, TS, TD, false>(s, ptr, nbr, o, n_rows, flags, stream);
+    else launch_pipe<64, TS, TD, false>(s, ptr, nbr, o, n_rows, flags, stream);
     FVGN_CHECK_LAUNCH();
     return FVGN_OK;
   }
@@ -297,8 +302,9 @@ static int launch_inc(const void* src, const int32_t* ptr, const int32_t* code, 
   const typename TS::elem* s = reinterpret_cast<const typename TS::elem*>(src);
   typename TD::elem* o = reinterpret_cast<typename TD::elem*>(dst);
 #ifndef FVGN_EMU
-  if (width == 128) {
-    launch_pipe<128, TS, TD, true>(s, ptr, code, o, n_rows, 0, stream);
+  if (width == 128 || width == 64) {
+    if (width == 128) launch_pipe<128, TS, TD, true>(s, ptr, code, o, n_rows, 0, stream);
+    else launch_pipe<64, TS, TD, true>(s, ptr, code, o, n_rows, 0, stream);
     FVGN_CHECK_LAUNCH();
     return FVGN_OK;
   }
