@@ -145,7 +145,7 @@ class NNmodel(nn.Module):
         out_scale = (graph_Index.uvp_dim * graph_Index.sigma).float()
         losses, uvp_node, uvp_cell, grad_phi = ops.FVLossFn.apply(
             phi, plan, graph_Index.theta_PDE, graph_Index.sigma, graph_Index.dt_graph, out_scale,
-            bool(getattr(params, "ncn_smooth", True)))
+            bool(getattr(params, "ncn_smooth", True)), bool(getattr(params, "conserved_form", True)))
         self._last = dict(decoder_out=raw, phi=phi, grad_phi=grad_phi)
         return losses[:, 0:1], losses[:, 1:2], losses[:, 2:3], losses[:, 3:4], uvp_node, uvp_cell
 

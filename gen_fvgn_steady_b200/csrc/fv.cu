@@ -251,8 +251,66 @@ __global__ void __launch_bounds__(128) fv_cell_fwd_kernel(const fvgn_fv_desc d) 
   for (int i = 0; i < 5; ++i) o[i] = pc[i];
 }
 
+// non_conserved_form (FVscheme.py:276-511, hessian_phi = None): one thread per cell
+__global__ void __launch_bounds__(128) fv_cell_fwd_nc_kernel(const fvgn_fv_desc d) {
+  const int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= d.n_cells) return;
+  const int b = d.batch_cell[c];
+  const float* th = d.theta + (size_t)b * 9;
+  const float th0 = th[0], th2 = th[2], th3 = th[3], th4 = th[4], th5 = th[5];
+  const float area = d.cells_area[c];
+  const float cx = d.centroid[(size_t)c * 2], cy = d.centroid[(size_t)c * 2 + 1];
+  const int k0 = d.cell_ptr[c], k1 = d.cell_ptr[c + 1];
+  float vx = 0.f, vy = 0.f, psq = 0.f;
+  float pc[7] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};  // cell values of u,v,p,u_hat,v_hat,u_old,v_old
+  float gc[5][2] = {{0.f, 0.f}, {0.f, 0.f}, {0.f, 0.f}, {0.f, 0.f}, {0.f, 0.f}};  // cell-mean gradients of channels 0..4
+  for (int k = k0; k < k1; ++k) {
+    const int f = d.slot_face[k];
+    const float a = d.face_area[f];
+    const float Sx = d.slot_unv[(size_t)k * 2] * a, Sy = d.slot_unv[(size_t)k * 2 + 1] * a;
+    FaceVals fv;
+    face_values(d, f, fv);
+    // divergence-form diffusion from the plainly averaged face gradients (:457-470)
+    vx += fv.Gh[0][0] * Sx + fv.Gh[0][1] * Sy;
+    vy += fv.Gh[1][0] * Sx + fv.Gh[1][1] * Sy;
+    if (fv.type == NT_OUTFLOW) {  // pressure outlet (:376-396)
+      const float r0 = th4 * (fv.Gn[0][0] * Sx + fv.Gn[0][1] * Sy) - fv.p * Sx;
+      const float r1 = th4 * (fv.Gn[1][0] * Sx + fv.Gn[1][1] * Sy) - fv.p * Sy;
+      psq += r0 * r0 + r1 * r1;
+    }
+    const int nd = d.slot_node[k];
+    const float rx = cx - d.pos[(size_t)nd * 2], ry = cy - d.pos[(size_t)nd * 2 + 1];
+    const float* pn = d.phi + (size_t)nd * 7;
+    const float* gn = d.grad + (size_t)nd * 14;
+#pragma unroll
+    for (int ch = 0; ch < 7; ++ch) pc[ch] += pn[ch] + (gn[ch * 2] * rx + gn[ch * 2 + 1] * ry);
+#pragma unroll
+    for (int ch = 0; ch < 5; ++ch) { gc[ch][0] += gn[ch * 2]; gc[ch][1] += gn[ch * 2 + 1]; }
+  }
+  const float cnt = (float)max(k1 - k0, 1);
+#pragma unroll
+  for (int i = 0; i < 7; ++i) pc[i] /= cnt;
+#pragma unroll
+  for (int i = 0; i < 5; ++i) { gc[i][0] /= cnt; gc[i][1] /= cnt; }
+  const float dt = d.dt[b];
+  const float ux = ((pc[0] - pc[5]) / dt) * area, uy = ((pc[1] - pc[6]) / dt) * area;                 // :399
+  const float cvx = (gc[3][0] * pc[3] + gc[3][1] * pc[4]) * area, cvy = (gc[4][0] * pc[3] + gc[4][1] * pc[4]) * area;  // :447
+  const float gpx = gc[2][0] * area, gpy = gc[2][1] * area;                                           // :454
+  const float src = th5 * area;
+  float* res = d.res + (size_t)c * 4;
+  res[0] = (gc[0][0] + gc[1][1]) * area;                                                              // :403-406
+  res[1] = th0 * ux + th2 * cvx + th3 * gpx - th4 * vx - src;                                         // :472-478
+  res[2] = th0 * uy + th2 * cvy + th3 * gpy - th4 * vy - src;
+  res[3] = psq;
+  float* o = d.phic + (size_t)c * 5;
+  o[0] = pc[0]; o[1] = pc[1]; o[2] = pc[2]; o[3] = pc[5]; o[4] = pc[6];
+  float* ax = d.cell_aux + (size_t)c * 6;
+  ax[0] = pc[3]; ax[1] = pc[4]; ax[2] = gc[3][0]; ax[3] = gc[3][1]; ax[4] = gc[4][0]; ax[5] = gc[4][1];
+}
+
 // ================================================================================ backward, stage 1 (one thread per face)
 // d_face[f] = [d uvn(2), d p, d uvh(2), d Gn(2x2), d Gh(2x2)] summed over the <=2 cells sharing the face
+template <int FORM>
 __global__ void __launch_bounds__(128) fv_bwd_face_kernel(const fvgn_fv_desc d) {
   const int64_t f = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (f >= d.n_faces) return;
@@ -271,13 +329,15 @@ __global__ void __launch_bounds__(128) fv_bwd_face_kernel(const fvgn_fv_desc d) 
     const float* res = d.res + (size_t)c * 4;
     const float dcont = cf[0] * res[0], dmx = cf[1] * res[1], dmy = cf[2] * res[2], dps = cf[3];
     const float Sx = d.slot_unv[(size_t)k * 2] * a, Sy = d.slot_unv[(size_t)k * 2 + 1] * a;
-    dun[0] += dcont * Sx;
-    dun[1] += dcont * Sy;
-    const float us = fv.uvh[0] * Sx + fv.uvh[1] * Sy;
-    const float dmu = dmx * fv.uvh[0] + dmy * fv.uvh[1];
-    duh[0] += th2 * (dmx * us + dmu * Sx);
-    duh[1] += th2 * (dmy * us + dmu * Sy);
-    dp += th3 * (dmx * Sx + dmy * Sy);
+    if (FORM == 0) {
+      dun[0] += dcont * Sx;
+      dun[1] += dcont * Sy;
+      const float us = fv.uvh[0] * Sx + fv.uvh[1] * Sy;
+      const float dmu = dmx * fv.uvh[0] + dmy * fv.uvh[1];
+      duh[0] += th2 * (dmx * us + dmu * Sx);
+      duh[1] += th2 * (dmy * us + dmu * Sy);
+      dp += th3 * (dmx * Sx + dmy * Sy);
+    }  // form 1: the face only carries the diffusion (below) and pressure-outlet terms
     dGh[0][0] -= th4 * dmx * Sx; dGh[0][1] -= th4 * dmx * Sy;
     dGh[1][0] -= th4 * dmy * Sx; dGh[1][1] -= th4 * dmy * Sy;
     if (fv.type == NT_OUTFLOW) {
@@ -297,6 +357,7 @@ __global__ void __launch_bounds__(128) fv_bwd_face_kernel(const fvgn_fv_desc d) 
 }
 
 // ================================================================================ backward, stage 2 (one thread per node)
+template <int FORM>
 __global__ void __launch_bounds__(128) fv_bwd_node_kernel(const fvgn_fv_desc d) {
   const int64_t n = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (n >= d.n_nodes) return;
@@ -329,6 +390,22 @@ __global__ void __launch_bounds__(128) fv_bwd_node_kernel(const fvgn_fv_desc d) 
     const float rx = d.centroid[(size_t)c * 2] - px, ry = d.centroid[(size_t)c * 2 + 1] - py;
     dphi[0] += dux; dg[0][0] += dux * rx; dg[0][1] += dux * ry;
     dphi[1] += duy; dg[1][0] += duy * rx; dg[1][1] += duy * ry;
+    if (FORM == 1) {
+      // non_conserved_form: the cell terms depend on the cell values of u_hat and on the cell-mean gradients
+      const float* th = d.theta + (size_t)b * 9;
+      const float aw = d.cells_area[c] / cnt;
+      const float dmx = cf[1] * res[1], dmy = cf[2] * res[2], dcont = cf[0] * res[0];
+      const float* ax = d.cell_aux + (size_t)c * 6;  // u_hat_c, v_hat_c, d(u_hat)/dx, /dy, d(v_hat)/dx, /dy
+      const float duh = th[2] * aw * (dmx * ax[2] + dmy * ax[4]), dvh = th[2] * aw * (dmx * ax[3] + dmy * ax[5]);
+      dphi[3] += duh; dg[3][0] += duh * rx; dg[3][1] += duh * ry;
+      dphi[4] += dvh; dg[4][0] += dvh * rx; dg[4][1] += dvh * ry;
+      dg[0][0] += dcont * aw;                 // continuity: du/dx + dv/dy
+      dg[1][1] += dcont * aw;
+      dg[2][0] += th[3] * aw * dmx;           // pressure gradient
+      dg[2][1] += th[3] * aw * dmy;
+      dg[3][0] += th[2] * aw * dmx * ax[0]; dg[3][1] += th[2] * aw * dmx * ax[1];   // convection: (grad u_hat) . u_hat
+      dg[4][0] += th[2] * aw * dmy * ax[0]; dg[4][1] += th[2] * aw * dmy * ax[1];
+    }
   }
   float* op = d.d_phi + (size_t)n * 7;
   float* og = d.d_grad + (size_t)n * 14;
@@ -349,8 +426,14 @@ extern "C" int fvgn_fv_forward(const fvgn_fv_desc* d, void* stream) {
   int rc = fv_check(d);
   if (rc) return rc;
   if (!d->phic) return FVGN_ERR_NULL;
+  if (d->form != 0 && d->form != 1) return FVGN_ERR_UNSUPPORTED;
+  if (d->form == 1 && !d->cell_aux) return FVGN_ERR_NULL;
   if (d->n_cells == 0) return FVGN_OK;
-  FVGN_LAUNCH_SEQ(fv_cell_fwd_kernel, (unsigned)((d->n_cells + 127) / 128), 128, 0, stream, *d);
+  if (d->form == 0) {
+    FVGN_LAUNCH_SEQ(fv_cell_fwd_kernel, (unsigned)((d->n_cells + 127) / 128), 128, 0, stream, *d);
+  } else {
+    FVGN_LAUNCH_SEQ(fv_cell_fwd_nc_kernel, (unsigned)((d->n_cells + 127) / 128), 128, 0, stream, *d);
+  }
   FVGN_CHECK_LAUNCH();
   return FVGN_OK;
 }
@@ -359,12 +442,22 @@ extern "C" int fvgn_fv_backward(const fvgn_fv_desc* d, void* stream) {
   int rc = fv_check(d);
   if (rc) return rc;
   if (!d->coef || !d->d_face || !d->d_phi || !d->d_grad) return FVGN_ERR_NULL;
+  if (d->form != 0 && d->form != 1) return FVGN_ERR_UNSUPPORTED;
+  if (d->form == 1 && !d->cell_aux) return FVGN_ERR_NULL;
   if (d->n_faces > 0) {
-    FVGN_LAUNCH_SEQ(fv_bwd_face_kernel, (unsigned)((d->n_faces + 127) / 128), 128, 0, stream, *d);
+    if (d->form == 0) {
+      FVGN_LAUNCH_SEQ(fv_bwd_face_kernel<0>, (unsigned)((d->n_faces + 127) / 128), 128, 0, stream, *d);
+    } else {
+      FVGN_LAUNCH_SEQ(fv_bwd_face_kernel<1>, (unsigned)((d->n_faces + 127) / 128), 128, 0, stream, *d);
+    }
     FVGN_CHECK_LAUNCH();
   }
   if (d->n_nodes > 0) {
-    FVGN_LAUNCH_SEQ(fv_bwd_node_kernel, (unsigned)((d->n_nodes + 127) / 128), 128, 0, stream, *d);
+    if (d->form == 0) {
+      FVGN_LAUNCH_SEQ(fv_bwd_node_kernel<0>, (unsigned)((d->n_nodes + 127) / 128), 128, 0, stream, *d);
+    } else {
+      FVGN_LAUNCH_SEQ(fv_bwd_node_kernel<1>, (unsigned)((d->n_nodes + 127) / 128), 128, 0, stream, *d);
+    }
     FVGN_CHECK_LAUNCH();
   }
   return FVGN_OK;

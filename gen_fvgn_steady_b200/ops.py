@@ -518,7 +518,7 @@ class FVLossFn(torch.autograd.Function):
     = (continuity, momentum-x, momentum-y, pressure-outlet) + non-differentiable uvp_node[N,3], uvp_cell[C,3]."""
 
     @staticmethod
-    def forward(ctx, phi, plan, theta, sigma, dt, out_scale, ncn_smooth):
+    def forward(ctx, phi, plan, theta, sigma, dt, out_scale, ncn_smooth, conserved_form=True):
         phi = _c(phi)
         st = _lib.stream_ptr(phi.device)
         q, qsum, qt = plan.wlsq_weights(2)
@@ -529,6 +529,10 @@ class FVLossFn(torch.autograd.Function):
         theta, dt = _c(theta.float()), _c(dt.reshape(-1).float())
         d = _fv_desc(plan, phi, grad, theta, dt)
         d.res, d.phic = fptr(res), fptr(phic)
+        aux = None
+        if not conserved_form:   # non_conserved_form (FVscheme.py:276-511): per-cell u_hat and grad(u_hat) kept for backward
+            aux = _empty((plan.C, 6), phi)
+            d.form, d.cell_aux = 1, fptr(aux)
         _lib.call("fvgn_fv_forward", ctypes.byref(d), st)
         sq = segment_colsum(res, 3, 4, plan.cell_chunks, plan.cell_chunk_ptr, plan.n_cell_chunks, plan.B, power=2)
         ps = segment_colsum(res, 1, 4, plan.cell_chunks, plan.cell_chunk_ptr, plan.n_cell_chunks, plan.B, power=1,
@@ -549,7 +553,7 @@ class FVLossFn(torch.autograd.Function):
         uvp_cell = _empty((plan.C, 3), phi)
         _lib.call("fvgn_fv_outputs", ctypes.byref(d), iptr(plan.batch_node), fptr(_c(out_scale.float())), int(ncn_smooth),
                   fptr(uvp_node), fptr(uvp_cell), st)
-        ctx.plan = plan
+        ctx.plan, ctx.aux = plan, aux
         ctx.save_for_backward(phi, grad, res, root, scale, theta, dt)
         ctx.mark_non_differentiable(uvp_node, uvp_cell, grad)
         return losses, uvp_node, uvp_cell, grad
@@ -571,8 +575,10 @@ class FVLossFn(torch.autograd.Function):
         d_grad = _empty((plan.N, 7, 2), phi)
         d.res, d.coef = fptr(res), fptr(coef)
         d.d_face, d.d_phi, d.d_grad = fptr(d_face), fptr(d_phi), fptr(d_grad)
+        if ctx.aux is not None:
+            d.form, d.cell_aux = 1, fptr(ctx.aux)
         _lib.call("fvgn_fv_backward", ctypes.byref(d), st)
         q, qsum, qt = plan.wlsq_weights(2)
         _lib.call("fvgn_wlsq_backward", fptr(d_grad), 7, iptr(plan.w_tptr), iptr(plan.w_trow), fptr(qt), fptr(qsum), 2,
                   fptr(d_phi), 1, plan.N, st)
-        return d_phi, None, None, None, None, None, None
+        return d_phi, None, None, None, None, None, None, None

@@ -175,9 +175,15 @@ typedef struct fvgn_fv_desc {
   float* d_face;      /* [E,13] scratch: d phi_f[5], d gradphi_f[(0,1,3,4),2] */
   float* d_phi;       /* [N,7]  */
   float* d_grad;      /* [N,7,2] */
+  /* residual formulation: 0 = Intergrator.conserved_form (FVscheme.py:50-274, the default), 1 = non_conserved_form
+   * (FVscheme.py:276-511: gradient-based continuity, cell-gradient convection / pressure terms, no face BC fix) */
+  int32_t form;
+  int32_t reserved0;
+  float* cell_aux;    /* form 1 only: [C,6] = cell values of u_hat, v_hat and the cell-mean gradient of (u_hat, v_hat);
+                         written by fvgn_fv_forward, read by fvgn_fv_backward */
 } fvgn_fv_desc;
-/* Intergrator.conserved_form FVscheme.py:50-250 with node_to_cell/node_to_face (FVInterpolation.py:36-185) and
- * _fix_face_flux_BC (FVscheme.py:32-48) fused: one pass over cells. */
+/* Intergrator.conserved_form FVscheme.py:50-250 (form 0) or non_conserved_form FVscheme.py:276-511 (form 1) with
+ * node_to_cell/node_to_face (FVInterpolation.py:36-185) and _fix_face_flux_BC (FVscheme.py:32-48) fused: one pass over cells. */
 int fvgn_fv_forward(const fvgn_fv_desc* d, void* stream);
 int fvgn_fv_backward(const fvgn_fv_desc* d, void* stream);
 /* cell_to_node_2nd_order (FVInterpolation.py:218-265) + BC re-enforcement and re-dimensionalisation

@@ -2,6 +2,7 @@
 (/root/reference/src, via oracle/ref_shims.py) on CPU in the build container.
 
     python -m oracle.make_golden            # regenerate every case in tests/golden_util.CASES
+    python -m oracle.make_golden NAME ...   # only these cases
 
 For each case it stores: the inputs that cannot be regenerated elsewhere (the example mesh after the
 reference's own parser + extract_mesh_state + transform_mesh; synthetic meshes are regenerated from
@@ -62,7 +63,8 @@ def run_reference(case, meshes, uvps, dtype):
     import FVMmodel.FVdiscretization.FVscheme as FVscheme
     torch.set_default_dtype(dtype)
     try:
-        params = ref_shims.ref_params(net=case["net"], dataset_size=case["dataset_size"])
+        params = ref_shims.ref_params(net=case["net"], dataset_size=case["dataset_size"],
+                                      conserved_form=case.get("conserved_form", True))
         H.seed_all(0)
         model = H.make_ref_model(params, dtype)
         shapes = {k: tuple(v.shape) for k, v in model.state_dict().items()}
@@ -100,9 +102,14 @@ def run_reference(case, meshes, uvps, dtype):
 
 def main():
     os.makedirs(GU.GOLDEN_DIR, exist_ok=True)
-    manifest = {}
+    mpath = os.path.join(GU.GOLDEN_DIR, "MANIFEST.json")
+    only = sys.argv[1:]  # optional: regenerate just these cases, keep the rest of the manifest
+    manifest = json.load(open(mpath)) if (only and os.path.exists(mpath)) else {}
     for name, case in GU.CASES.items():
-        params = ref_shims.ref_params(net=case["net"], dataset_size=case["dataset_size"])
+        if only and name not in only:
+            continue
+        params = ref_shims.ref_params(net=case["net"], dataset_size=case["dataset_size"],
+                                      conserved_form=case.get("conserved_form", True))
         meshes, uvps, payload = build_case_inputs(case, params)
         keys = None
         for tag, dt in (("f32", torch.float32), ("f64", torch.float64)):
@@ -124,7 +131,7 @@ def main():
                               losses_f64={k: payload[f"f64.{k}"].reshape(-1).tolist()
                                           for k in ("loss_cont", "loss_mom_x", "loss_mom_y", "loss_press", "loss")})
         print(name, manifest[name])
-    json.dump(manifest, open(os.path.join(GU.GOLDEN_DIR, "MANIFEST.json"), "w"), indent=1)
+    json.dump(manifest, open(mpath, "w"), indent=1)
 
 
 if __name__ == "__main__":

@@ -26,6 +26,12 @@ CASES = {
              physics=dict(mean_u=1.2, mu=0.015, dt=0.3, inlet_type="parabolic", init_field_type="parabolic")),
         dict(n=0, nx=6, ny=11, kind="mixed", bc="cavity", seed=6, physics=dict(mean_u=1.0, mu=0.01)),
     ]),
+    # the reference's second residual formulation (FVscheme.py:276-511, --conserved_form False)
+    "synth_ns_batch2_v1_nc": dict(net="TransFVGN_v1", dataset_size=100, conserved_form=False, mesh=[
+        dict(n=0, nx=9, ny=9, kind="quad", bc="channel", seed=5,
+             physics=dict(mean_u=1.2, mu=0.015, dt=0.3, inlet_type="parabolic", init_field_type="parabolic")),
+        dict(n=0, nx=6, ny=11, kind="mixed", bc="cavity", seed=6, physics=dict(mean_u=1.0, mu=0.01)),
+    ]),
 }
 
 
