@@ -21,11 +21,11 @@ namespace {
 constexpr int NTHREADS = 416;  // 8 epilogue warps (two tile pipelines) + 4 producer warps + 1 MMA warp
 
 template <int MODE> struct TCfg;
-template <> struct TCfg<FVGN_MLP_EDGE> { static constexpr int K1 = 384, K1P = 384, NOUT = 128, NSTAGE = 2; static constexpr bool LN = true; };
-template <> struct TCfg<FVGN_MLP_NODE> { static constexpr int K1 = 192, K1P = 192, NOUT = 128, NSTAGE = 4; static constexpr bool LN = true; };
-template <> struct TCfg<FVGN_MLP_ENC_NODE> { static constexpr int K1 = 12, K1P = 16, NOUT = 128, NSTAGE = 4; static constexpr bool LN = true; };
-template <> struct TCfg<FVGN_MLP_ENC_EDGE> { static constexpr int K1 = 15, K1P = 16, NOUT = 128, NSTAGE = 4; static constexpr bool LN = true; };
-template <> struct TCfg<FVGN_MLP_DEC> { static constexpr int K1 = 128, K1P = 128, NOUT = 3, NSTAGE = 4; static constexpr bool LN = false; };
+template <> struct TCfg<FVGN_MLP_EDGE> { static constexpr int K1P = 384, NOUT = 128, NSTAGE = 2; static constexpr bool LN = true; };
+template <> struct TCfg<FVGN_MLP_NODE> { static constexpr int K1P = 192, NOUT = 128, NSTAGE = 4; static constexpr bool LN = true; };
+template <> struct TCfg<FVGN_MLP_ENC_NODE> { static constexpr int K1P = 16, NOUT = 128, NSTAGE = 4; static constexpr bool LN = true; };
+template <> struct TCfg<FVGN_MLP_ENC_EDGE> { static constexpr int K1P = 16, NOUT = 128, NSTAGE = 4; static constexpr bool LN = true; };
+template <> struct TCfg<FVGN_MLP_DEC> { static constexpr int K1P = 128, NOUT = 3, NSTAGE = 4; static constexpr bool LN = false; };
 
 constexpr int STG_BYTES = 8 * WSTG_BYTES;  // one wide staging tile per epilogue warp
 

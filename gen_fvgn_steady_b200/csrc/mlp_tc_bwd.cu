@@ -561,7 +561,6 @@ __global__ void __launch_bounds__(NTHREADS, 1) mlp_tc_bwd_b_kernel(const fvgn_ml
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int64_t ntiles = (d.rows + TILE_M - 1) / TILE_M;
-  const int64_t ntl = (ntiles - blockIdx.x + gridDim.x - 1) / gridDim.x;
   const int64_t PC = pcount(C::K1, C::NOUT, C::LN);
   float* Pw1 = d.partials + (size_t)blockIdx.x * PC;
   const uint8_t* dz_img = reinterpret_cast<const uint8_t*>(d.workspace);
