@@ -120,3 +120,42 @@ def test_graphed_step_matches_eager_steps():
                 ls.append(float(gs.step().detach()))
         losses[tag] = ls
     assert losses["graph"][3:] == losses["eager"][3:], losses
+
+
+def test_bf16_loss_trajectory_tracks_fp32():
+    """north_star: 'bf16 MLP variant within a stated 1e-2 on latents and loss trajectory'.  20 Adam steps from the same
+    initial weights on the same mesh, fp32 (SIMT, parity mode) vs bf16 (tcgen05): the script-level loss agrees within 1e-2
+    (relative) at every step."""
+    import copy
+    from gen_fvgn_steady_b200.FVMmodel.importer import NNmodel
+    from gen_fvgn_steady_b200.utils.get_param import params as default_params
+    from gen_fvgn_steady_b200.mesh import synthetic as S
+    from tests.case_inputs import product_graphs
+    PU.use_real_kernels()
+    dev = torch.device("cuda")
+    mesh, uvp = S.make_case(48, kind="mixed", bc="channel", seed=7)
+    torch.manual_seed(0)
+    base = NNmodel(default_params(net="EPD", message_passing_num=3, dataset_size=1, precision="fp32")).to(dev)
+    traj = {}
+    for prec in ("fp32", "bf16"):
+        p = default_params(net="EPD", message_passing_num=3, dataset_size=1, precision=prec)
+        model = copy.deepcopy(base)
+        model.params = p
+        model.set_precision(prec)
+        graphs = product_graphs([mesh], [uvp], dev)
+        x0 = graphs[0].x.clone()
+        opt = torch.optim.Adam(model.parameters(), lr=2e-4)
+        ls = []
+        for _ in range(20):
+            graphs[0].x, graphs[0].norm_uvp, graphs[0].norm_global = x0, True, True
+            opt.zero_grad(set_to_none=True)
+            loss = PU.script_loss(model(*graphs, is_training=True), p)
+            loss.backward()
+            opt.step()
+            ls.append(float(loss.detach()))
+        traj[prec] = ls
+    with open("gpurun_out/loss_trajectory_bf16_vs_fp32.json", "w") as f:
+        json.dump(traj, f)
+    assert traj["fp32"][-1] < traj["fp32"][0]            # it trains
+    for a, b in zip(traj["fp32"], traj["bf16"]):
+        assert abs(a - b) <= 1e-2 * max(abs(a), 1.0), (traj["fp32"], traj["bf16"])
