@@ -16,8 +16,11 @@ class Simulator(nn.Module):
         self.decoder = Decoder(hidden_sze=hidden_size, node_output_size=node_output_size)
 
     def forward(self, graph_node=None, graph_edge=None, graph_cell=None):
+        from ....parallel import halo_refresh
         latent, node_embedding = self.encoder(graph_node)
-        for model in self.GN_block_list:
+        nblk = len(self.GN_block_list)
+        for i, model in enumerate(self.GN_block_list):
             latent = model(latent)
-        latent.x = self.TransBlock(latent.x + node_embedding, graph_node.batch)
+            latent = halo_refresh(latent, i, nblk)  # cell-partition mode only (no-op otherwise)
+        latent.x = self.TransBlock(latent.x + node_embedding, graph_node.batch, halo=getattr(latent, "_fvgn_halo", None))
         return self.decoder(latent)

@@ -14,12 +14,15 @@ class AttnProcessor(nn.Module):
                                             for _ in range(message_passing_num)])
         self.TransBlock = Transolver_block(num_heads=8, hidden_dim=hidden_size, dropout=0, act="gelu", mlp_ratio=2, slice_num=32)
 
-    def forward(self, latent_graph_node, graph_edge):
+    def forward(self, latent_graph_node, graph_edge, first_block=0, total_blocks=None):
+        from ....parallel import halo_refresh
         node_embedding = latent_graph_node.x
         latent = latent_graph_node
-        for model in self.GN_block_list:
+        total = total_blocks if total_blocks is not None else len(self.GN_block_list)
+        for i, model in enumerate(self.GN_block_list):
             latent = model(latent)
-        latent.x = self.TransBlock(latent.x + node_embedding, latent.batch)
+            latent = halo_refresh(latent, first_block + i, total)  # cell-partition mode only (no-op otherwise)
+        latent.x = self.TransBlock(latent.x + node_embedding, latent.batch, halo=getattr(latent, "_fvgn_halo", None))
         return latent
 
 
@@ -34,6 +37,9 @@ class Simulator(nn.Module):
 
     def forward(self, graph_node=None, graph_edge=None, graph_cell=None):
         latent, _ = self.encoder(graph_node)
+        total = sum(len(m.GN_block_list) for m in self.processpr_list)
+        first = 0
         for model in self.processpr_list:
-            latent = model(latent, graph_edge)
+            latent = model(latent, graph_edge, first, total)
+            first += len(model.GN_block_list)
         return self.decoder(latent)

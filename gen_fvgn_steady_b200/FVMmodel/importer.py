@@ -46,10 +46,8 @@ class NNmodel(nn.Module):
     def enable_cell_partition(self, group=True):
         """Cell-partition mode: this rank holds one sub-mesh made by
         gen_fvgn_steady_b200.partition; per-graph statistics, Normalizer increments and residual norms are completed
-        over the ranks, the latents' ghost rows are refreshed after every GnBlock.  EPD nets only (the Transolver
-        blocks of TransFVGN need global slice tokens)."""
-        if self.params.net not in ("EPD", "FVGN"):
-            raise NotImplementedError("cell partition supports the pure GN composition (net=EPD)")
+        over the ranks, the latents' ghost rows are refreshed after the GnBlocks (as the halo depth requires) and the
+        Transolver slice tokens of TransFVGN_v1/v2 are summed over the ranks' owned rows."""
         self.dp_group = group
 
     def enable_data_parallel(self, group=True):

@@ -145,3 +145,21 @@ def allreduce_sum_(t, group=None):
 def sum_gradients(flat, group=None):
     """Cell-partition mode: every rank differentiates the same global loss through its sub-mesh -> gradients ADD."""
     dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=group)
+
+
+class AllReduceSumFn(torch.autograd.Function):
+    """y = sum over ranks of x, differentiable: every rank's loss depends on the summed quantity, so the gradient of a
+    rank's partial is the SUM of all ranks' gradients of y (used for the Transolver slice tokens in cell-partition mode)."""
+
+    @staticmethod
+    def forward(ctx, x, group):
+        ctx.group = group
+        y = x.contiguous().clone()
+        dist.all_reduce(y, op=dist.ReduceOp.SUM, group=group)
+        return y
+
+    @staticmethod
+    def backward(ctx, g):
+        g = g.contiguous().clone()
+        dist.all_reduce(g, op=dist.ReduceOp.SUM, group=ctx.group)
+        return g, None

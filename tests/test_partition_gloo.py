@@ -16,10 +16,10 @@ MP_NUM = 2
 _CACHE = {}
 
 
-def _model():
+def _model(net="EPD"):
     from gen_fvgn_steady_b200.FVMmodel.importer import NNmodel
     from gen_fvgn_steady_b200.utils.get_param import params as default_params
-    p = default_params(net="EPD", message_passing_num=MP_NUM, dataset_size=1, precision="fp32")
+    p = default_params(net=net, message_passing_num=MP_NUM, dataset_size=1, precision="fp32")
     torch.manual_seed(0)
     model = NNmodel(p)
     # unit-scale weights (the 0.02 init makes every rank's output nearly input independent)
@@ -33,12 +33,12 @@ def _model():
     return model, p
 
 
-def _run(mesh, uvp, halo):
+def _run(mesh, uvp, halo, net="EPD"):
     from tests import product_util as PU
     from tests.case_inputs import product_graphs
     from gen_fvgn_steady_b200 import parallel, partition
     graphs = product_graphs([mesh], [uvp], "cpu")
-    model, p = _model()
+    model, p = _model(net)
     if halo is not None:
         partition.mark_partition(graphs, halo)
         model.enable_cell_partition(True)
@@ -59,7 +59,7 @@ def _global_case():
     return mesh, uvp
 
 
-def _worker(rank, world, port, ret, halo_layers=3):
+def _worker(rank, world, port, ret, halo_layers=3, net="EPD"):
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
     dist.init_process_group("gloo", rank=rank, world_size=world)
     from tests import product_util as PU
@@ -68,7 +68,7 @@ def _worker(rank, world, port, ret, halo_layers=3):
     torch.set_num_threads(2)
     mesh, uvp = _global_case()
     lmesh, luvp, halo = partition.build(mesh, uvp, world, rank, halo_layers=halo_layers)
-    out, loss, flat = _run(lmesh, luvp, halo)
+    out, loss, flat = _run(lmesh, luvp, halo, net)
     n_own = halo.rows["node"]["n_owned"]
     ret[rank] = dict(losses=[o for o in out[:4]], loss=loss, flat=flat, node_gid=halo.rows["node"]["gid"][:n_own].clone(),
                      uvp_node=out[4][:n_own].clone(), cell_gid=halo.cell_gid[:halo.n_owned_cells].clone(),
@@ -98,9 +98,10 @@ def test_partition_structure():
     assert abs(halos[0].n_owned_cells - halos[1].n_owned_cells) <= 1
 
 
-@pytest.mark.parametrize("halo_layers", [3, 3 * MP_NUM + 2])
-def test_cell_partition_matches_single_process(halo_layers):
-    """halo_layers = 3: ghost refresh after every GnBlock; 3 G + 2: no latent exchange at all (redundant halo compute)."""
+@pytest.mark.parametrize("halo_layers,net", [(3, "EPD"), (3 * MP_NUM + 2, "EPD"), (3, "TransFVGN_v1")])
+def test_cell_partition_matches_single_process(halo_layers, net):
+    """halo_layers = 3: ghost refresh after every GnBlock; 3 G + 2: no latent exchange at all (redundant halo compute);
+    TransFVGN_v1: the Transolver slice tokens are summed over the ranks' owned rows."""
     from tests import product_util as PU
     s = socket.socket()
     s.bind(("127.0.0.1", 0))
@@ -108,15 +109,15 @@ def test_cell_partition_matches_single_process(halo_layers):
     s.close()
     mgr = mp.Manager()
     ret = mgr.dict()
-    mp.spawn(_worker, args=(2, port, ret, halo_layers), nprocs=2, join=True)
-    if "ref" not in _CACHE:  # the single-process run of the whole mesh (shared by the parametrised cases)
+    mp.spawn(_worker, args=(2, port, ret, halo_layers, net), nprocs=2, join=True)
+    if net not in _CACHE:  # the single-process run of the whole mesh (shared by the parametrised cases)
         PU.use_emulated_kernels()
         try:
             mesh, uvp = _global_case()
-            _CACHE["ref"] = _run(mesh, uvp, None)
+            _CACHE[net] = _run(mesh, uvp, None, net)
         finally:
             PU.use_real_kernels()
-    out, loss, flat = _CACHE["ref"]
+    out, loss, flat = _CACHE[net]
     assert ret[0]["n_local"] > ret[0]["n_own"]  # there really is a halo
     from gen_fvgn_steady_b200.partition import HaloPlan
     hp = HaloPlan(0, 2)
