@@ -184,8 +184,9 @@ def run_ours(args):
         dist.init_process_group("nccl", device_id=dev)
 
     cells_mode = args.parallel == "cells" and world > 1
+    gn_blocks_total = args.mp * (2 if args.net in ("TransFVGN_v2", "TransFVGN") else 1)  # v2: two processors of mp blocks
     if args.halo_layers is None:
-        args.halo_layers = 3 * args.mp + 2
+        args.halo_layers = 3 * gn_blocks_total + 2
     halo = None
     if cells_mode:
         from gen_fvgn_steady_b200 import partition
@@ -312,7 +313,7 @@ def run_ours(args):
             "data": "synthetic", "config": dict(workload_config(args, C_bench=C), N=N, E=E, C=C, K=K, X=X,
                                                 parallelism=(f"cells{world} (one {C_global}-cell mesh, RCB partition, "
                                                              f"{args.halo_layers}-layer halo, "
-                                                             f"{sum(halo.wants_exchange(i, args.mp) for i in range(args.mp))} "
+                                                             f"{sum(halo.wants_exchange(i, gn_blocks_total) for i in range(gn_blocks_total))} "
                                                              f"ghost refreshes per forward; rank 0: "
                                                              f"{halo.n_owned_cells} owned of {C} local cells)") if cells_mode
                                                 else f"dp{world}", loss=last_loss),
