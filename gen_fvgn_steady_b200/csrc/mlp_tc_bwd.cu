@@ -16,6 +16,7 @@
 // bf16 tiles, warp transpose-reduce for the fp32 LayerNorm terms).  Every CTA owns one partial buffer; tile->CTA is
 // static, so the final reduction (partial_reduce) is deterministic.
 #include "tc_common.cuh"
+#include <type_traits>
 
 using namespace tc;
 
@@ -59,24 +60,33 @@ __device__ __forceinline__ void load_tile16(const uint8_t* buf, int row, int c0,
 // bulk-copy loader (W2/W3 image once, then one 32 KB Z1 tile image per tile, double buffered).
 // Layer 1 is NOT recomputed: the forward left Z1 (bf16) in HBM; E1 turns the tile into H1 (in place, shared memory) and
 // gelu'(Z1) (TMEM).  Per tile:  E1 -> R2 -> E2 -> R3 -> E3 (LayerNorm backward) -> dW3/dH2 -> E4 -> dW2/dH1 -> E5.
-constexpr int A_THREADS = 448;
-constexpr int A_EPI = 256;  // epilogue threads
-__device__ __forceinline__ void epi_bar_sync256() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
+// NEW = number of epilogue warps (8 or 16): the 128 columns of a row are split over NEW / 4 threads.  Measured on B200
+// (2 M edges): 16 warps (80 registers per thread) run the kernel in the same 1.17 ms as 8 warps (128 registers) -- the
+// epilogue stages are already issue bound with two warps per SM sub-partition, the rest of a tile's time is the
+// serialised MMA / barrier hand-offs -- so 8 is the default.
+#ifndef FVGN_BWD_A_EPI_WARPS
+#define FVGN_BWD_A_EPI_WARPS 8
+#endif
+constexpr int A_NEW = FVGN_BWD_A_EPI_WARPS;
+constexpr int A_THREADS = (A_NEW + 6) * 32;
+constexpr int A_EPI = A_NEW * 32;  // epilogue threads
+template <int N> __device__ __forceinline__ void epi_bar_sync_n() { asm volatile("bar.sync 1, %0;" ::"n"(N) : "memory"); }
 
-// column sums of a bf16 tile by the 256 epilogue threads: thread t owns column pair (2p, 2p+1), p = t & 63, rows [32*(t>>6), +32).
+// column sums of a bf16 tile by the epilogue threads: thread t owns column pair (2p, 2p+1), p = t & 63, rows [ROWS*(t>>6), +ROWS).
 // Four rows at a time are added as packed bf16x2 (2 roundings), the groups are accumulated in fp32.
 __device__ __forceinline__ uint32_t hadd2_bf16(uint32_t a, uint32_t b) {
   uint32_t r;
   asm("add.rn.bf16x2 %0, %1, %2;" : "=r"(r) : "r"(a), "r"(b));
   return r;
 }
-__device__ __forceinline__ void tile_colsum256(const uint8_t* buf, int t, float& s0, float& s1) {
-  const int p = t & 63, r0 = (t >> 6) * 32;
+template <int ROWS>
+__device__ __forceinline__ void tile_colsum_n(const uint8_t* buf, int t, float& s0, float& s1) {
+  const int p = t & 63, r0 = (t >> 6) * ROWS;
   const int kb = (2 * p) >> 6, chunk = ((2 * p) & 63) >> 3, word = p & 3;
   const uint8_t* base = buf + kb * KB_BYTES + word * 4;
   float a = 0.f, b = 0.f;
 #pragma unroll
-  for (int r = r0; r < r0 + 32; r += 4) {
+  for (int r = r0; r < r0 + ROWS; r += 4) {
     const uint32_t w0 = *reinterpret_cast<const uint32_t*>(base + sw128_off(r, chunk));
     const uint32_t w1 = *reinterpret_cast<const uint32_t*>(base + sw128_off(r + 1, chunk));
     const uint32_t w2 = *reinterpret_cast<const uint32_t*>(base + sw128_off(r + 2, chunk));
@@ -93,6 +103,14 @@ template <int MODE>
 __global__ void __launch_bounds__(A_THREADS, 1) mlp_tc_bwd_a_kernel(const fvgn_mlp_desc d) {
   using C = BCfg<MODE>;
   constexpr uint32_t DW2 = 0, DW3 = 128, WACC = 256, G1 = 384, G2 = 448;
+  constexpr int NEW = A_NEW;               // epilogue warps
+  constexpr int CSPLIT = NEW / 4;          // threads per row (column groups)
+  constexpr int COLS = 128 / CSPLIT;       // columns per epilogue thread
+  constexpr int CS_ROWS = 128 * 64 / A_EPI;  // rows per thread in a tile column sum
+  constexpr int RG = A_EPI / 64;           // row groups of the column sums
+  constexpr int W_PROD = NEW, W_MMA = NEW + 4, W_LD = NEW + 5;
+  auto epi_bar = [] { epi_bar_sync_n<A_EPI>(); };
+  auto colsum = [](const uint8_t* buf, int t, float& s0, float& s1) { tile_colsum_n<CS_ROWS>(buf, t, s0, s1); };
   FVGN_DYN_SMEM(smem);
   uint8_t* w23 = smem;                              // W2 image | W3 image (64 KB)
   uint8_t* bufZ = w23 + 4 * KB_BYTES;               // 2 x [Z1 -> H1 -> dZ1] tile
@@ -101,8 +119,8 @@ __global__ void __launch_bounds__(A_THREADS, 1) mlp_tc_bwd_a_kernel(const fvgn_m
   float* sb2 = reinterpret_cast<float*>(bufC + BUF_BYTES);
   float* sb3 = sb2 + 128;
   float* sg = sb3 + 128;
-  float4* xch = reinterpret_cast<float4*>(sg + 128);   // [2 halves][128 rows] LayerNorm row sums exchanged between the halves
-  uint64_t* bars = reinterpret_cast<uint64_t*>(xch + 256);
+  float4* xch = reinterpret_cast<float4*>(sg + 128);   // [CSPLIT][128 rows] LayerNorm row sums exchanged between the column groups
+  uint64_t* bars = reinterpret_cast<uint64_t*>(xch + CSPLIT * 128);
   const uint32_t bar0 = smem_u32(bars);
   auto BAR = [&](int i) { return bar0 + 8u * (uint32_t)i; };
   constexpr int B_W = 0, B_ZFULL = 1, B_ZEMPTY = 3, B_MMA = 5, B_EPI = 6, B_DO = 7, B_CFREE = 8;
@@ -141,13 +159,13 @@ __global__ void __launch_bounds__(A_THREADS, 1) mlp_tc_bwd_a_kernel(const fvgn_m
     sb3[i] = (i < C::NOUT) ? d.b3[i] : 0.f;
     sg[i] = C::LN ? d.ln_g[i] : 1.f;
   }
-  if (warp == 12) tmem_alloc(smem_u32(tmem_slot), 512);
+  if (warp == W_MMA) tmem_alloc(smem_u32(tmem_slot), 512);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = *tmem_slot;
 
-  if (warp == 13) {
+  if (warp == W_LD) {
     // ============================================================ loader
     if (lane == 0) {
       mbar_expect_tx(BAR(B_W), 4 * KB_BYTES);
@@ -162,7 +180,7 @@ __global__ void __launch_bounds__(A_THREADS, 1) mlp_tc_bwd_a_kernel(const fvgn_m
       }
     }
     __syncwarp();
-  } else if (warp == 12) {
+  } else if (warp == W_MMA) {
     // ============================================================ MMA issuer
     if (lane == 0) {
       mbar_wait(BAR(B_W), 0);
@@ -214,11 +232,11 @@ __global__ void __launch_bounds__(A_THREADS, 1) mlp_tc_bwd_a_kernel(const fvgn_m
       }
     }
     __syncwarp();
-  } else if (warp >= 8) {
+  } else if (warp >= W_PROD) {
     // ============================================================ producers: the tile of upstream gradients
     // dO = d_out (+ gathered d_a1) as bf16 into bufC.  The loads of the next tile are issued (and packed) before waiting
     // for bufC to be released, so their latency is hidden behind the current tile.
-    const int pw = warp - 8;
+    const int pw = warp - W_PROD;
     uint32_t tcount = 0;
     TileIdx idx;
     for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++tcount) {
@@ -227,67 +245,87 @@ __global__ void __launch_bounds__(A_THREADS, 1) mlp_tc_bwd_a_kernel(const fvgn_m
         const bool gath = MODE == FVGN_MLP_EDGE && (d.d_gather || d.d_gatherh);
         if (gath) load_tile_idx<MODE>(d, row0, pw, lane, idx);
         const int seg = lane & 7;
-        uint4 pk[2][8];
+        // rows i0 .. i0+NR-1 of this thread's 8 (tile rows i*16 + pw*4 + lane/8), 64-column block kb -> packed bf16
+        auto load_pack = [&](int kb, int i0, auto nr_tag, uint4* out) {
+          constexpr int NR = decltype(nr_tag)::value;
+          float4 lo[NR], hi[NR];
 #pragma unroll
-        for (int kb = 0; kb < 2; ++kb) {
-          float4 lo[8], hi[8];
-#pragma unroll
-          for (int i = 0; i < 8; ++i) {
-            const int64_t row = row0 + i * 16 + pw * 4 + (lane >> 3);
-            lo[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-            hi[i] = lo[i];
+          for (int j = 0; j < NR; ++j) {
+            const int64_t row = row0 + (i0 + j) * 16 + pw * 4 + (lane >> 3);
+            lo[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+            hi[j] = lo[j];
             if (row < d.rows) {
               const float* p = d.d_out + (size_t)row * 128 + kb * 64 + seg * 8;
-              lo[i] = __ldg(reinterpret_cast<const float4*>(p));
-              hi[i] = __ldg(reinterpret_cast<const float4*>(p + 4));
+              lo[j] = __ldg(reinterpret_cast<const float4*>(p));
+              hi[j] = __ldg(reinterpret_cast<const float4*>(p + 4));
             }
           }
           if (gath) {
-            int gi[8];
+            int gi[NR];
 #pragma unroll
-            for (int i = 0; i < 8; ++i) gi[i] = kb == 0 ? idx.sender(i, lane) : idx.receiver(i, lane);
+            for (int j = 0; j < NR; ++j) gi[j] = kb == 0 ? idx.sender(i0 + j, lane) : idx.receiver(i0 + j, lane);
             if (d.d_gatherh) {
-              uint4 gv[8];
+              uint4 gv[NR];
 #pragma unroll
-              for (int i = 0; i < 8; ++i) {
-                const int64_t row = row0 + i * 16 + pw * 4 + (lane >> 3);
-                gv[i] = make_uint4(0u, 0u, 0u, 0u);
+              for (int j = 0; j < NR; ++j) {
+                const int64_t row = row0 + (i0 + j) * 16 + pw * 4 + (lane >> 3);
+                gv[j] = make_uint4(0u, 0u, 0u, 0u);
                 if (row < d.rows)
-                  gv[i] = __ldg(reinterpret_cast<const uint4*>(reinterpret_cast<const uint8_t*>(d.d_gatherh) + (size_t)gi[i] * 128 + seg * 16));
+                  gv[j] = __ldg(reinterpret_cast<const uint4*>(reinterpret_cast<const uint8_t*>(d.d_gatherh) + (size_t)gi[j] * 128 + seg * 16));
               }
 #pragma unroll
-              for (int i = 0; i < 8; ++i) {
-                lo[i] = make_float4(lo[i].x + bf16_lo(gv[i].x), lo[i].y + bf16_hi(gv[i].x), lo[i].z + bf16_lo(gv[i].y),
-                                    lo[i].w + bf16_hi(gv[i].y));
-                hi[i] = make_float4(hi[i].x + bf16_lo(gv[i].z), hi[i].y + bf16_hi(gv[i].z), hi[i].z + bf16_lo(gv[i].w),
-                                    hi[i].w + bf16_hi(gv[i].w));
+              for (int j = 0; j < NR; ++j) {
+                lo[j] = make_float4(lo[j].x + bf16_lo(gv[j].x), lo[j].y + bf16_hi(gv[j].x), lo[j].z + bf16_lo(gv[j].y),
+                                    lo[j].w + bf16_hi(gv[j].y));
+                hi[j] = make_float4(hi[j].x + bf16_lo(gv[j].z), hi[j].y + bf16_hi(gv[j].z), hi[j].z + bf16_lo(gv[j].w),
+                                    hi[j].w + bf16_hi(gv[j].w));
               }
             } else {
 #pragma unroll
-              for (int i = 0; i < 8; ++i) {
-                const int64_t row = row0 + i * 16 + pw * 4 + (lane >> 3);
+              for (int j = 0; j < NR; ++j) {
+                const int64_t row = row0 + (i0 + j) * 16 + pw * 4 + (lane >> 3);
                 if (row < d.rows) {
-                  const float* g = d.d_gather + (size_t)gi[i] * 64 + seg * 8;
+                  const float* g = d.d_gather + (size_t)gi[j] * 64 + seg * 8;
                   const float4 a = __ldg(reinterpret_cast<const float4*>(g)), b = __ldg(reinterpret_cast<const float4*>(g + 4));
-                  lo[i] = make_float4(lo[i].x + a.x, lo[i].y + a.y, lo[i].z + a.z, lo[i].w + a.w);
-                  hi[i] = make_float4(hi[i].x + b.x, hi[i].y + b.y, hi[i].z + b.z, hi[i].w + b.w);
+                  lo[j] = make_float4(lo[j].x + a.x, lo[j].y + a.y, lo[j].z + a.z, lo[j].w + a.w);
+                  hi[j] = make_float4(hi[j].x + b.x, hi[j].y + b.y, hi[j].z + b.z, hi[j].w + b.w);
                 }
               }
             }
           }
 #pragma unroll
-          for (int i = 0; i < 8; ++i)
-            pk[kb][i] = make_uint4(pack_bf16(lo[i].x, lo[i].y), pack_bf16(lo[i].z, lo[i].w), pack_bf16(hi[i].x, hi[i].y),
-                                   pack_bf16(hi[i].z, hi[i].w));
-        }
-        mbar_wait(BAR(B_CFREE), (tcount & 1) ^ 1);  // previous tile's dW3 / dH2 MMAs and db3 column sums are done
-#pragma unroll
-        for (int kb = 0; kb < 2; ++kb)
-#pragma unroll
-          for (int i = 0; i < 8; ++i) {
-            const int rloc = i * 16 + pw * 4 + (lane >> 3);
-            *reinterpret_cast<uint4*>(bufC + kb * KB_BYTES + sw128_off(rloc, seg)) = pk[kb][i];
+          for (int j = 0; j < NR; ++j)
+            out[j] = make_uint4(pack_bf16(lo[j].x, lo[j].y), pack_bf16(lo[j].z, lo[j].w), pack_bf16(hi[j].x, hi[j].y),
+                                pack_bf16(hi[j].z, hi[j].w));
+        };
+        auto park = [&](int kb, int i0, int n, const uint4* v) {
+          for (int j = 0; j < n; ++j) {
+            const int rloc = (i0 + j) * 16 + pw * 4 + (lane >> 3);
+            *reinterpret_cast<uint4*>(bufC + kb * KB_BYTES + sw128_off(rloc, seg)) = v[j];
           }
+        };
+        if (A_NEW <= 8) {
+          // registers to spare: both 64-column blocks of the next tile are loaded and packed before bufC is released
+          uint4 pk[2][8];
+          load_pack(0, 0, std::integral_constant<int, 8>{}, pk[0]);
+          load_pack(1, 0, std::integral_constant<int, 8>{}, pk[1]);
+          mbar_wait(BAR(B_CFREE), (tcount & 1) ^ 1);  // previous tile's dW3 / dH2 MMAs and db3 column sums are done
+#pragma unroll
+          for (int kb = 0; kb < 2; ++kb) park(kb, 0, 8, pk[kb]);
+        } else {
+          // 80 registers per thread: block 0 is prefetched two rows at a time, block 1 follows the release in two halves
+          uint4 pk0[8];
+#pragma unroll
+          for (int i0 = 0; i0 < 8; i0 += 2) load_pack(0, i0, std::integral_constant<int, 2>{}, pk0 + i0);
+          mbar_wait(BAR(B_CFREE), (tcount & 1) ^ 1);
+          park(0, 0, 8, pk0);
+#pragma unroll
+          for (int i0 = 0; i0 < 8; i0 += 4) {
+            uint4 pk1[4];
+            load_pack(1, i0, std::integral_constant<int, 4>{}, pk1);
+            park(1, i0, 4, pk1);
+          }
+        }
       } else {
         // decoder: dY = d_out[row, 0:3] zero-padded to 128 columns (one thread per row)
         const int rloc = pw * 32 + lane;
@@ -312,10 +350,10 @@ __global__ void __launch_bounds__(A_THREADS, 1) mlp_tc_bwd_a_kernel(const fvgn_m
     }
   } else {
     // ============================================================ epilogue: thread <-> (row, column half)
-    const int q = warp & 3, half = warp >> 2;
+    const int q = warp & 3, half = warp >> 2;  // TMEM lane quarter, column group
     const uint32_t lane_base = (uint32_t)(q * 32) << 16;
     const int rloc = q * 32 + lane;
-    const int cbase = 64 * half;  // first column of this thread's half
+    const int cbase = COLS * half;  // first column of this thread's group
     uint32_t pm = 0;
     auto wait_mma = [&]() {
       mbar_wait(BAR(B_MMA), pm);
@@ -327,9 +365,9 @@ __global__ void __launch_bounds__(A_THREADS, 1) mlp_tc_bwd_a_kernel(const fvgn_m
       mbar_arrive(BAR(B_EPI));
     };
     float db1a = 0.f, db1b = 0.f, db2a = 0.f, db2b = 0.f, db3a = 0.f, db3b = 0.f, dbta = 0.f, dbtb = 0.f;
-    float dgam[4];
+    float dgam[COLS / 16];
 #pragma unroll
-    for (int i = 0; i < 4; ++i) dgam[i] = 0.f;
+    for (int i = 0; i < COLS / 16; ++i) dgam[i] = 0.f;
     uint32_t pdo = 0, i = 0;
     const uint32_t wacc = tmem + lane_base + WACC + cbase;
     const uint32_t g1c = tmem + lane_base + G1 + cbase / 2, g2c = tmem + lane_base + G2 + cbase / 2;
@@ -340,7 +378,7 @@ __global__ void __launch_bounds__(A_THREADS, 1) mlp_tc_bwd_a_kernel(const fvgn_m
       // ---------------- E1: Z1 (bf16, from the forward) -> H1 in place + gelu'(Z1) into TMEM
       mbar_wait(BAR(B_ZFULL + zb), (i >> 1) & 1);
 #pragma unroll 1
-      for (int c0 = 0; c0 < 64; c0 += 16) {
+      for (int c0 = 0; c0 < COLS; c0 += 16) {
         uint32_t zw[8], hw[8], gw[8];
         load_tile16(bz, rloc, cbase + c0, zw);
 #pragma unroll
@@ -364,7 +402,7 @@ __global__ void __launch_bounds__(A_THREADS, 1) mlp_tc_bwd_a_kernel(const fvgn_m
       }
       // ---------------- E2: H2 (bf16, shared memory) + gelu'(Z2) (bf16, TMEM)
       wait_mma();
-      for_each_chunk16<64>(wacc, [&](int c0, uint32_t (&r)[16]) {
+      for_each_chunk16<COLS>(wacc, [&](int c0, uint32_t (&r)[16]) {
         uint32_t hw[8], gw[8];
 #pragma unroll
         for (int j = 0; j < 8; j += 2) {
@@ -390,10 +428,10 @@ __global__ void __launch_bounds__(A_THREADS, 1) mlp_tc_bwd_a_kernel(const fvgn_m
       mbar_wait(BAR(B_DO), pdo);
       pdo ^= 1;
       if (C::LN) {
-        tile_colsum256(bufC, tid, dbta, dbtb);  // d beta = column sums of dO
+        colsum(bufC, tid, dbta, dbtb);  // d beta = column sums of dO
         // sweep 1 (one pass, no dependence on the statistics): sum y, sum y^2, S1 = sum dO*gamma, S2 = sum dO*gamma*y
         float sum = 0.f, sq = 0.f, s1 = 0.f, s2 = 0.f;
-        for_each_chunk16<64>(wacc, [&](int c0, uint32_t (&r)[16]) {
+        for_each_chunk16<COLS>(wacc, [&](int c0, uint32_t (&r)[16]) {
           uint32_t ow[8];
           load_tile16(bufC, rloc, cbase + c0, ow);
 #pragma unroll
@@ -412,9 +450,10 @@ __global__ void __launch_bounds__(A_THREADS, 1) mlp_tc_bwd_a_kernel(const fvgn_m
           }
         });
         xch[half * 128 + rloc] = make_float4(sum, sq, s1, s2);
-        epi_bar_sync256();  // also: every thread has finished reading the dO tile (d beta) before rows are overwritten
-        {
-          const float4 o = xch[(half ^ 1) * 128 + rloc];
+        epi_bar();  // also: every thread has finished reading the dO tile (d beta) before rows are overwritten
+#pragma unroll
+        for (int g = 1; g < CSPLIT; ++g) {
+          const float4 o = xch[((half + g) % CSPLIT) * 128 + rloc];
           sum += o.x; sq += o.y; s1 += o.z; s2 += o.w;
         }
         const float mean = sum * (1.0f / 128.0f);
@@ -423,7 +462,7 @@ __global__ void __launch_bounds__(A_THREADS, 1) mlp_tc_bwd_a_kernel(const fvgn_m
         const float m1 = s1 * (1.0f / 128.0f);                       // mean(dO*gamma)
         const float m2 = rstd * (s2 * (1.0f / 128.0f) - mean * m1);  // mean(dO*gamma*xhat)
         // sweep 2: dY = rstd * (dO*gamma - m1 - xhat*m2), d gamma += dO*xhat
-        for_each_chunk16<64>(wacc, [&](int c0, uint32_t (&r)[16]) {
+        for_each_chunk16<COLS>(wacc, [&](int c0, uint32_t (&r)[16]) {
           uint32_t ow[8];
           float gx[16];
           load_tile16(bufC, rloc, cbase + c0, ow);
@@ -444,16 +483,16 @@ __global__ void __launch_bounds__(A_THREADS, 1) mlp_tc_bwd_a_kernel(const fvgn_m
           store_tile16(bufC, rloc, cbase + c0, ow);
           const float cg = warp_colsum16(gx, lane);
 #pragma unroll
-          for (int k = 0; k < 4; ++k) dgam[k] += (k == (c0 >> 4)) ? cg : 0.f;  // static register indexing
+          for (int k = 0; k < COLS / 16; ++k) dgam[k] += (k == (c0 >> 4)) ? cg : 0.f;  // static register indexing
         });
         fence_proxy_async();
       }
       done();
-      epi_bar_sync256();                        // the whole dY tile is written
-      tile_colsum256(bufC, tid, db3a, db3b);    // overlaps the dW3 / dH2 MMAs
+      epi_bar();                        // the whole dY tile is written
+      colsum(bufC, tid, db3a, db3b);    // overlaps the dW3 / dH2 MMAs
       // ---------------- E4: dZ2 = dH2 * gelu'(Z2) -> bufH2
       wait_mma();
-      for_each_chunk16<64>(wacc, [&](int c0, uint32_t (&r)[16]) {
+      for_each_chunk16<COLS>(wacc, [&](int c0, uint32_t (&r)[16]) {
         uint32_t g[8], ow[8];
         tmem_ld8(g2c + c0 / 2, g);
         tmem_wait_ld();
@@ -464,12 +503,12 @@ __global__ void __launch_bounds__(A_THREADS, 1) mlp_tc_bwd_a_kernel(const fvgn_m
       });
       fence_proxy_async();
       done();
-      epi_bar_sync256();                         // every thread is past its db3 column sums; the dZ2 tile is complete
+      epi_bar();                         // every thread is past its db3 column sums; the dZ2 tile is complete
       if (tid == 0) mbar_arrive(BAR(B_CFREE));
-      tile_colsum256(bufH2, tid, db2a, db2b);    // overlaps the dW2 / dH1 MMAs
+      colsum(bufH2, tid, db2a, db2b);    // overlaps the dW2 / dH1 MMAs
       // ---------------- E5: dZ1 = dH1 * gelu'(Z1) -> bufZ (in place over H1) -> HBM tile image
       wait_mma();
-      for_each_chunk16<64>(wacc, [&](int c0, uint32_t (&r)[16]) {
+      for_each_chunk16<COLS>(wacc, [&](int c0, uint32_t (&r)[16]) {
         uint32_t g[8], ow[8];
         tmem_ld8(g1c + c0 / 2, g);
         tmem_wait_ld();
@@ -480,19 +519,19 @@ __global__ void __launch_bounds__(A_THREADS, 1) mlp_tc_bwd_a_kernel(const fvgn_m
       });
       fence_proxy_async();
       tc_fence_before();
-      epi_bar_sync256();
+      epi_bar();
       if (tid == 0) bulk_s2g(dz_img + (size_t)tile * BUF_BYTES, smem_u32(bz), BUF_BYTES);
-      tile_colsum256(bz, tid, db1a, db1b);
+      colsum(bz, tid, db1a, db1b);
       mbar_arrive(BAR(B_ZEMPTY + zb));  // this thread no longer reads the buffer (thread 0 adds the bulk store's release)
     }
     // ---------------- flush: weight-gradient accumulators (TMEM) and the column sums -> this CTA's partial buffer
     if (tid == 0) bulk_wait0();
-    epi_bar_sync256();
+    epi_bar();
     tc_fence_after();
     {
       const int o = rloc;  // TMEM lane = output feature
 #pragma unroll 1
-      for (int c0 = 0; c0 < 64; c0 += 16) {
+      for (int c0 = 0; c0 < COLS; c0 += 16) {
         uint32_t r[16];
         tmem_ld16(tmem + lane_base + DW2 + cbase + c0, r);
         tmem_wait_ld();
@@ -506,34 +545,45 @@ __global__ void __launch_bounds__(A_THREADS, 1) mlp_tc_bwd_a_kernel(const fvgn_m
         }
       }
     }
-    // bias sums: combine the four row quarters through shared memory (bufC is free now)
+    // bias sums: combine the RG row groups through shared memory (bufC is free now)
     float* scr = reinterpret_cast<float*>(bufC);
+    constexpr int VS = RG * 128;  // floats per bias vector in the scratch: [RG row groups][128 columns]
     {
       const int p = tid & 63, rq = tid >> 6;
       scr[rq * 128 + 2 * p] = db1a; scr[rq * 128 + 2 * p + 1] = db1b;
-      scr[512 + rq * 128 + 2 * p] = db2a; scr[512 + rq * 128 + 2 * p + 1] = db2b;
-      scr[1024 + rq * 128 + 2 * p] = db3a; scr[1024 + rq * 128 + 2 * p + 1] = db3b;
-      scr[1536 + rq * 128 + 2 * p] = dbta; scr[1536 + rq * 128 + 2 * p + 1] = dbtb;
+      scr[VS + rq * 128 + 2 * p] = db2a; scr[VS + rq * 128 + 2 * p + 1] = db2b;
+      scr[2 * VS + rq * 128 + 2 * p] = db3a; scr[2 * VS + rq * 128 + 2 * p + 1] = db3b;
+      scr[3 * VS + rq * 128 + 2 * p] = dbta; scr[3 * VS + rq * 128 + 2 * p + 1] = dbtb;
       if (C::LN && lane < 16) {
         // dgam[k] of lane L: column cbase + 16 k + L, summed over this warp's 32 rows
 #pragma unroll
-        for (int k = 0; k < 4; ++k) scr[2048 + q * 128 + cbase + k * 16 + lane] = dgam[k];
+        for (int k = 0; k < COLS / 16; ++k) scr[4 * VS + q * 128 + cbase + k * 16 + lane] = dgam[k];
       }
     }
-    epi_bar_sync256();
+    epi_bar();
     if (tid < 128) {
-      Pb1[tid] = (scr[tid] + scr[128 + tid]) + (scr[256 + tid] + scr[384 + tid]);
-      Pb2[tid] = (scr[512 + tid] + scr[640 + tid]) + (scr[768 + tid] + scr[896 + tid]);
-      if (tid < C::NOUT) Pb3[tid] = (scr[1024 + tid] + scr[1152 + tid]) + (scr[1280 + tid] + scr[1408 + tid]);
+      float a1 = 0.f, a2 = 0.f, a3 = 0.f, ab = 0.f, ag = 0.f;
+#pragma unroll
+      for (int g = 0; g < RG; ++g) {
+        a1 += scr[g * 128 + tid];
+        a2 += scr[VS + g * 128 + tid];
+        a3 += scr[2 * VS + g * 128 + tid];
+        ab += scr[3 * VS + g * 128 + tid];
+      }
+#pragma unroll
+      for (int g = 0; g < 4; ++g) ag += scr[4 * VS + g * 128 + tid];
+      Pb1[tid] = a1;
+      Pb2[tid] = a2;
+      if (tid < C::NOUT) Pb3[tid] = a3;
       if (C::LN) {
-        Pg[tid] = (scr[2048 + tid] + scr[2176 + tid]) + (scr[2304 + tid] + scr[2432 + tid]);
-        Pbeta[tid] = (scr[1536 + tid] + scr[1664 + tid]) + (scr[1792 + tid] + scr[1920 + tid]);
+        Pg[tid] = ag;
+        Pbeta[tid] = ab;
       }
     }
     tc_fence_before();
   }
   __syncthreads();
-  if (warp == 12) {
+  if (warp == W_MMA) {
     tc_fence_after();
     tmem_dealloc(tmem, 512);
   }
@@ -817,7 +867,7 @@ __global__ void __launch_bounds__(256) tc_partial_reduce_kernel(const float* __r
   out[i] = s;
 }
 
-template <int MODE> constexpr int smem_a() { return 4 * KB_BYTES + 4 * BUF_BYTES + 3 * 512 + 2 * 2048 + 256; }
+template <int MODE> constexpr int smem_a() { return 4 * KB_BYTES + 4 * BUF_BYTES + 3 * 512 + (A_NEW / 4) * 2048 + 256; }
 template <int MODE> constexpr int smem_b() {
   return nkb1(BCfg<MODE>::K1P) * KB_BYTES + 2 * BUF_BYTES + 3 * KB_BYTES + STG_BYTES + 256;
 }
