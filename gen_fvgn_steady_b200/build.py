@@ -28,7 +28,7 @@ def build(force=False, verbose=False):
     if not force and not _newer(LIB, deps):
         return LIB
     nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
-    flags = [f for f in NVCC_FLAGS if f != "--use_fast_math=false"]
+    flags = [f for f in NVCC_FLAGS if f != "--use_fast_math=false"] + os.environ.get("FVGN_EXTRA_NVCC_FLAGS", "").split()
     cmd = [nvcc] + flags + ["-o", LIB] + srcs + ["-lcuda"]
     res = subprocess.run(cmd, capture_output=True, text=True)
     log = os.path.join(HERE, "build.log")

@@ -68,6 +68,20 @@ __device__ __forceinline__ void load_tile16(const uint8_t* buf, int row, int c0,
 #define FVGN_BWD_A_EPI_WARPS 8
 #endif
 constexpr int A_NEW = FVGN_BWD_A_EPI_WARPS;
+#ifdef FVGN_TIMING
+// debug build: cycle breakdown of kernel A's per-tile chain, summed over the tiles of CTA 0 (thread 0 only)
+__device__ unsigned long long g_prof_a[16];
+#define PROF_T(i)                                  \
+  do {                                             \
+    if (blockIdx.x == 0 && tid == 0) {             \
+      const long long now_ = clock64();            \
+      g_prof_a[i] += (unsigned long long)(now_ - tprev_); \
+      tprev_ = now_;                               \
+    }                                              \
+  } while (0)
+#else
+#define PROF_T(i) do { } while (0)
+#endif
 constexpr int A_THREADS = (A_NEW + 6) * 32;
 constexpr int A_EPI = A_NEW * 32;  // epilogue threads
 template <int N> __device__ __forceinline__ void epi_bar_sync_n() { asm volatile("bar.sync 1, %0;" ::"n"(N) : "memory"); }
@@ -372,11 +386,15 @@ __global__ void __launch_bounds__(A_THREADS, 1) mlp_tc_bwd_a_kernel(const fvgn_m
     const uint32_t wacc = tmem + lane_base + WACC + cbase;
     const uint32_t g1c = tmem + lane_base + G1 + cbase / 2, g2c = tmem + lane_base + G2 + cbase / 2;
 
+#ifdef FVGN_TIMING
+    long long tprev_ = clock64();
+#endif
     for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++i) {
       const int zb = i & 1;
       uint8_t* bz = bufZ + zb * BUF_BYTES;
       // ---------------- E1: Z1 (bf16, from the forward) -> H1 in place + gelu'(Z1) into TMEM
       mbar_wait(BAR(B_ZFULL + zb), (i >> 1) & 1);
+      PROF_T(0);  // wait Z1
 #pragma unroll 1
       for (int c0 = 0; c0 < COLS; c0 += 16) {
         uint32_t zw[8], hw[8], gw[8];
@@ -400,8 +418,10 @@ __global__ void __launch_bounds__(A_THREADS, 1) mlp_tc_bwd_a_kernel(const fvgn_m
         bulk_wait_read0();
         mbar_arrive(BAR(B_ZEMPTY + (zb ^ 1)));
       }
+      PROF_T(1);  // E1
       // ---------------- E2: H2 (bf16, shared memory) + gelu'(Z2) (bf16, TMEM)
       wait_mma();
+      PROF_T(2);  // wait R2
       for_each_chunk16<COLS>(wacc, [&](int c0, uint32_t (&r)[16]) {
         uint32_t hw[8], gw[8];
 #pragma unroll
@@ -423,9 +443,12 @@ __global__ void __launch_bounds__(A_THREADS, 1) mlp_tc_bwd_a_kernel(const fvgn_m
       tmem_wait_st();
       fence_proxy_async();
       done();
+      PROF_T(3);  // E2
       // ---------------- E3: LayerNorm backward -> dY (bf16) in bufC (the producers parked dO there)
       wait_mma();
+      PROF_T(4);  // wait R3
       mbar_wait(BAR(B_DO), pdo);
+      PROF_T(5);  // wait dO
       pdo ^= 1;
       if (C::LN) {
         colsum(bufC, tid, dbta, dbtb);  // d beta = column sums of dO
@@ -490,8 +513,10 @@ __global__ void __launch_bounds__(A_THREADS, 1) mlp_tc_bwd_a_kernel(const fvgn_m
       done();
       epi_bar();                        // the whole dY tile is written
       colsum(bufC, tid, db3a, db3b);    // overlaps the dW3 / dH2 MMAs
+      PROF_T(6);  // E3 (+ db3 column sums)
       // ---------------- E4: dZ2 = dH2 * gelu'(Z2) -> bufH2
       wait_mma();
+      PROF_T(7);  // wait dW3/dH2
       for_each_chunk16<COLS>(wacc, [&](int c0, uint32_t (&r)[16]) {
         uint32_t g[8], ow[8];
         tmem_ld8(g2c + c0 / 2, g);
@@ -506,8 +531,10 @@ __global__ void __launch_bounds__(A_THREADS, 1) mlp_tc_bwd_a_kernel(const fvgn_m
       epi_bar();                         // every thread is past its db3 column sums; the dZ2 tile is complete
       if (tid == 0) mbar_arrive(BAR(B_CFREE));
       colsum(bufH2, tid, db2a, db2b);    // overlaps the dW2 / dH1 MMAs
+      PROF_T(8);  // E4 (+ db2 column sums)
       // ---------------- E5: dZ1 = dH1 * gelu'(Z1) -> bufZ (in place over H1) -> HBM tile image
       wait_mma();
+      PROF_T(9);  // wait dW2/dH1
       for_each_chunk16<COLS>(wacc, [&](int c0, uint32_t (&r)[16]) {
         uint32_t g[8], ow[8];
         tmem_ld8(g1c + c0 / 2, g);
@@ -523,6 +550,10 @@ __global__ void __launch_bounds__(A_THREADS, 1) mlp_tc_bwd_a_kernel(const fvgn_m
       if (tid == 0) bulk_s2g(dz_img + (size_t)tile * BUF_BYTES, smem_u32(bz), BUF_BYTES);
       colsum(bz, tid, db1a, db1b);
       mbar_arrive(BAR(B_ZEMPTY + zb));  // this thread no longer reads the buffer (thread 0 adds the bulk store's release)
+      PROF_T(10);  // E5 (+ db1 column sums)
+#ifdef FVGN_TIMING
+      if (blockIdx.x == 0 && tid == 0) g_prof_a[15] += 1;
+#endif
     }
     // ---------------- flush: weight-gradient accumulators (TMEM) and the column sums -> this CTA's partial buffer
     if (tid == 0) bulk_wait0();
@@ -917,6 +948,17 @@ int64_t fvgn_mlp_tc_workspace_bytes(int32_t, int64_t rows) {
   const int64_t ntiles = (rows + TILE_M - 1) / TILE_M;
   return (ntiles < 1 ? 1 : ntiles) * (int64_t)BUF_BYTES;
 }
+
+#ifdef FVGN_TIMING
+extern "C" int fvgn_debug_profile_a(unsigned long long* out16, int reset) {
+  if (cudaMemcpyFromSymbol(out16, g_prof_a, sizeof(unsigned long long) * 16) != cudaSuccess) return FVGN_ERR_LAUNCH;
+  if (reset) {
+    unsigned long long z[16] = {0};
+    cudaMemcpyToSymbol(g_prof_a, z, sizeof(z));
+  }
+  return FVGN_OK;
+}
+#endif
 
 int fvgn_mlp_backward_simt(const fvgn_mlp_desc* d, void* stream);
 
