@@ -118,41 +118,58 @@ __global__ void __launch_bounds__(256) inc_reduce_kernel(const typename TS::elem
 // index entries of row i+1 and the row pointers of row i+2 are being fetched, so a warp pays ONE exposed memory latency
 // per row instead of three (ptr -> entries -> rows).  Entries are accumulated strictly in CSR order: results are
 // bit-identical to the one-shot kernels above.
-template <int V> struct VecF;  // V fp32 accumulators per lane
-template <> struct VecF<4> { float4 v; };
-template <> struct VecF<2> { float2 v; };
-
+// per-lane vector I/O: V consecutive elements (fp32 or bf16), unpacked to / packed from fp32
 template <class T, int V> struct LaneIO;
 template <> struct LaneIO<T_F32, 4> {
-  typedef float4 raw;
-  static __device__ __forceinline__ raw ld(const float* p) { return *reinterpret_cast<const float4*>(p); }
-  static __device__ __forceinline__ float4 up(raw r) { return r; }
-  static __device__ __forceinline__ void st(float* p, float4 v) { *reinterpret_cast<float4*>(p) = v; }
+  struct raw { float4 a; };
+  static __device__ __forceinline__ raw ld(const float* p) { return raw{*reinterpret_cast<const float4*>(p)}; }
+  static __device__ __forceinline__ void up(const raw& r, float (&x)[4]) { x[0] = r.a.x; x[1] = r.a.y; x[2] = r.a.z; x[3] = r.a.w; }
+  static __device__ __forceinline__ void st(float* p, const float (&x)[4]) { *reinterpret_cast<float4*>(p) = make_float4(x[0], x[1], x[2], x[3]); }
 };
+template <> struct LaneIO<T_F32, 8> {
+  struct raw { float4 a, b; };
+  static __device__ __forceinline__ raw ld(const float* p) {
+    return raw{*reinterpret_cast<const float4*>(p), *reinterpret_cast<const float4*>(p + 4)};
+  }
+  static __device__ __forceinline__ void up(const raw& r, float (&x)[8]) {
+    x[0] = r.a.x; x[1] = r.a.y; x[2] = r.a.z; x[3] = r.a.w; x[4] = r.b.x; x[5] = r.b.y; x[6] = r.b.z; x[7] = r.b.w;
+  }
+  static __device__ __forceinline__ void st(float* p, const float (&x)[8]) {
+    *reinterpret_cast<float4*>(p) = make_float4(x[0], x[1], x[2], x[3]);
+    *reinterpret_cast<float4*>(p + 4) = make_float4(x[4], x[5], x[6], x[7]);
+  }
+};
+__device__ __forceinline__ float bf_lo(uint32_t w) { return __uint_as_float(w << 16); }
+__device__ __forceinline__ float bf_hi(uint32_t w) { return __uint_as_float(w & 0xFFFF0000u); }
+__device__ __forceinline__ uint32_t bf_pack(float lo, float hi) {
+  __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);
+  return *reinterpret_cast<uint32_t*>(&v);
+}
 template <> struct LaneIO<T_BF16, 4> {
-  typedef uint2 raw;
-  static __device__ __forceinline__ raw ld(const uint16_t* p) { return *reinterpret_cast<const uint2*>(p); }
-  static __device__ __forceinline__ float4 up(raw w) {
-    return make_float4(__uint_as_float(w.x << 16), __uint_as_float(w.x & 0xFFFF0000u), __uint_as_float(w.y << 16),
-                       __uint_as_float(w.y & 0xFFFF0000u));
+  struct raw { uint2 a; };
+  static __device__ __forceinline__ raw ld(const uint16_t* p) { return raw{*reinterpret_cast<const uint2*>(p)}; }
+  static __device__ __forceinline__ void up(const raw& r, float (&x)[4]) {
+    x[0] = bf_lo(r.a.x); x[1] = bf_hi(r.a.x); x[2] = bf_lo(r.a.y); x[3] = bf_hi(r.a.y);
   }
-  static __device__ __forceinline__ void st(uint16_t* p, float4 v) { stv<T_BF16>(p, v); }
-};
-template <> struct LaneIO<T_F32, 2> {
-  typedef float2 raw;
-  static __device__ __forceinline__ raw ld(const float* p) { return *reinterpret_cast<const float2*>(p); }
-  static __device__ __forceinline__ float4 up(raw r) { return make_float4(r.x, r.y, 0.f, 0.f); }
-  static __device__ __forceinline__ void st(float* p, float4 v) { *reinterpret_cast<float2*>(p) = make_float2(v.x, v.y); }
-};
-template <> struct LaneIO<T_BF16, 2> {
-  typedef uint32_t raw;
-  static __device__ __forceinline__ raw ld(const uint16_t* p) { return *reinterpret_cast<const uint32_t*>(p); }
-  static __device__ __forceinline__ float4 up(raw w) { return make_float4(__uint_as_float(w << 16), __uint_as_float(w & 0xFFFF0000u), 0.f, 0.f); }
-  static __device__ __forceinline__ void st(uint16_t* p, float4 v) {
-    __nv_bfloat162 a = __floats2bfloat162_rn(v.x, v.y);
-    *reinterpret_cast<uint32_t*>(p) = *reinterpret_cast<uint32_t*>(&a);
+  static __device__ __forceinline__ void st(uint16_t* p, const float (&x)[4]) {
+    *reinterpret_cast<uint2*>(p) = make_uint2(bf_pack(x[0], x[1]), bf_pack(x[2], x[3]));
   }
 };
+template <> struct LaneIO<T_BF16, 8> {
+  struct raw { uint4 a; };
+  static __device__ __forceinline__ raw ld(const uint16_t* p) { return raw{*reinterpret_cast<const uint4*>(p)}; }
+  static __device__ __forceinline__ void up(const raw& r, float (&x)[8]) {
+    x[0] = bf_lo(r.a.x); x[1] = bf_hi(r.a.x); x[2] = bf_lo(r.a.y); x[3] = bf_hi(r.a.y);
+    x[4] = bf_lo(r.a.z); x[5] = bf_hi(r.a.z); x[6] = bf_lo(r.a.w); x[7] = bf_hi(r.a.w);
+  }
+  static __device__ __forceinline__ void st(uint16_t* p, const float (&x)[8]) {
+    *reinterpret_cast<uint4*>(p) = make_uint4(bf_pack(x[0], x[1]), bf_pack(x[2], x[3]), bf_pack(x[4], x[5]), bf_pack(x[6], x[7]));
+  }
+};
+
+// lanes per row: 16 whenever a lane can move 16 bytes of the SOURCE row (bf16 512-col... i.e. 128 bf16 = 16 x 16 B, or
+// 64 fp32 = 16 x 16 B), else 32; the two half-warps of a 16-lane configuration run independent rows
+template <int W, class TS> struct PipeCfg { static constexpr int LPR = (W * (int)sizeof(typename TS::elem) >= 512) ? 32 : 16; };
 
 // INC = false: entries are neighbour rows (src row = entry, W columns);  INC = true: entries are edge*2+role codes
 // (src row = code >> 1 of a [E, 2W] array, column block = code & 1).
@@ -160,11 +177,9 @@ template <int W, class TS, class TD, bool INC>
 __global__ void __launch_bounds__(256) pipe_reduce_kernel(const typename TS::elem* __restrict__ src, const int32_t* __restrict__ ptr,
                                                           const int32_t* __restrict__ ent, typename TD::elem* __restrict__ dst,
                                                           int64_t n, int flags) {
-  // 512-B rows: one warp per row (32 lanes x 4 elements); 256-B rows: one HALF-warp per row (16 lanes x 4 elements), the
-  // two halves of a warp run independent rows (shuffles are confined to the half by mask + width)
-  constexpr int LPR = W / 4;   // lanes per row: 32 or 16
-  constexpr int V = 4;         // elements per lane
-  constexpr int NB = 4;        // gathers in flight per lane
+  constexpr int LPR = PipeCfg<W, TS>::LPR;  // lanes per row: 32 (one warp per row) or 16 (one HALF-warp per row)
+  constexpr int V = W / LPR;                // elements per lane: 4 or 8
+  constexpr int NB = 4;                     // gathers in flight per lane
   constexpr int ROW_LD = INC ? 2 * W : W;
   typedef LaneIO<TS, V> SI;
   typedef LaneIO<TD, V> DI;
@@ -187,13 +202,12 @@ __global__ void __launch_bounds__(256) pipe_reduce_kernel(const typename TS::ele
     const int deg = ce - cb;
     // ---- issue: gathers of this row (first NB), entries of the next row, pointers of the one after
     typename SI::raw v[NB];
-    int code[NB];
 #pragma unroll
     for (int k = 0; k < NB; ++k) {
-      code[k] = __shfl_sync(hmask, cent, k, LPR);
+      const int code = __shfl_sync(hmask, cent, k, LPR);
       if (k < deg) {
-        const int r = INC ? (code[k] >> 1) : code[k];
-        const int coff = INC ? (code[k] & 1) * W : 0;
+        const int r = INC ? (code >> 1) : code;
+        const int coff = INC ? (code & 1) * W : 0;
         v[k] = SI::ld(src + (size_t)r * ROW_LD + coff + lane * V);
       }
     }
@@ -202,38 +216,52 @@ __global__ void __launch_bounds__(256) pipe_reduce_kernel(const typename TS::ele
     const int nent = load_ent(nb_, ne_);
     int ab, ae;
     load_ptr(row + 2 * GW, ab, ae);
-    float4 old = make_float4(0.f, 0.f, 0.f, 0.f);
+    float old[V];
+#pragma unroll
+    for (int j = 0; j < V; ++j) old[j] = 0.f;
     typename TD::elem* o = dst + (size_t)row * W + lane * V;
-    if (!INC && (flags & FVGN_ADJ_ACCUMULATE)) old = DI::up(DI::ld(o));
+    if (!INC && (flags & FVGN_ADJ_ACCUMULATE)) DI::up(DI::ld(o), old);
     // ---- consume in CSR order
-    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    float acc[V];
+#pragma unroll
+    for (int j = 0; j < V; ++j) acc[j] = 0.f;
 #pragma unroll
     for (int k = 0; k < NB; ++k) {
       if (k < deg) {
-        float4 x = SI::up(v[k]);
+        float x[V];
+        SI::up(v[k], x);
         if (div_src) {
           const float dv = __shfl_sync(hmask, mydiv, k, LPR);
-          x.x /= dv; x.y /= dv; x.z /= dv; x.w /= dv;
+#pragma unroll
+          for (int j = 0; j < V; ++j) x[j] /= dv;
         }
-        acc = add4(acc, x);
+#pragma unroll
+        for (int j = 0; j < V; ++j) acc[j] += x[j];
       }
     }
     for (int t = NB; t < deg; ++t) {  // long rows: the rest, one at a time (entries beyond LPR straight from memory)
       const int c = (t < LPR) ? __shfl_sync(hmask, cent, t, LPR) : __ldg(ent + cb + t);
       const int r = INC ? (c >> 1) : c;
       const int coff = INC ? (c & 1) * W : 0;
-      float4 x = SI::up(SI::ld(src + (size_t)r * ROW_LD + coff + lane * V));
+      float x[V];
+      SI::up(SI::ld(src + (size_t)r * ROW_LD + coff + lane * V), x);
       if (div_src) {
         const float dv = (float)max(__ldg(ptr + c + 1) - __ldg(ptr + c), 1);
-        x.x /= dv; x.y /= dv; x.z /= dv; x.w /= dv;
+#pragma unroll
+        for (int j = 0; j < V; ++j) x[j] /= dv;
       }
-      acc = add4(acc, x);
+#pragma unroll
+      for (int j = 0; j < V; ++j) acc[j] += x[j];
     }
     if (!INC && (flags & FVGN_ADJ_DIV_DST_BY_DEG)) {
       const float dd = (float)max(deg, 1);
-      acc.x /= dd; acc.y /= dd; acc.z /= dd; acc.w /= dd;
+#pragma unroll
+      for (int j = 0; j < V; ++j) acc[j] /= dd;
     }
-    if (!INC && (flags & FVGN_ADJ_ACCUMULATE)) acc = add4(old, acc);
+    if (!INC && (flags & FVGN_ADJ_ACCUMULATE)) {
+#pragma unroll
+      for (int j = 0; j < V; ++j) acc[j] = old[j] + acc[j];
+    }
     DI::st(o, acc);
     // ---- rotate the pipeline
     cb = nb_; ce = ne_; cent = nent;
@@ -261,7 +289,7 @@ static void launch_pipe(const typename TS::elem* s, const int32_t* ptr, const in
   auto kern = pipe_reduce_kernel<W, TS, TD, INC>;
   static unsigned cap_grid = 0;  // per instantiation
   if (cap_grid == 0) cap_grid = pipe_grid(kern, (int64_t)1 << 40);
-  const int rows_per_block = 256 / (W / 4);
+  const int rows_per_block = 256 / PipeCfg<W, TS>::LPR;
   const int64_t want = (n_rows + rows_per_block - 1) / rows_per_block;
   const unsigned grid = (unsigned)(want < cap_grid ? want : cap_grid);
   kern<<<grid, 256, 0, (cudaStream_t)stream>>>(s, ptr, ent, o, n_rows, flags);
