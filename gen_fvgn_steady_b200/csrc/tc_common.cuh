@@ -122,6 +122,38 @@ __device__ __forceinline__ void gelu_tanh_pair(float x, float& h, float& g) {
   g = fmaf(hx * fmaf(-t, t, 1.0f), fmaf(0.1070322243f, x2, 0.7978845608f), fmaf(0.5f, t, 0.5f));
 }
 
+// ---- packed bf16x2 arithmetic (two elements per instruction, no unpack / pack): the backward's recomputation of
+// gelu / gelu' from bf16 pre-activations.  Measured against the fp64 tanh-form GELU on N(0, 1.5) inputs (emulated
+// roundings): rms error of h 1.8e-3 (1.6e-3 when evaluated in fp32 and rounded once), of g 2.6e-3 (1.4e-3).
+__device__ __forceinline__ uint32_t bmul2(uint32_t a, uint32_t b) {
+  uint32_t d;
+  asm("mul.rn.bf16x2 %0, %1, %2;" : "=r"(d) : "r"(a), "r"(b));
+  return d;
+}
+__device__ __forceinline__ uint32_t bfma2(uint32_t a, uint32_t b, uint32_t c) {
+  uint32_t d;
+  asm("fma.rn.bf16x2 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(c));
+  return d;
+}
+__device__ __forceinline__ uint32_t btanh2(uint32_t a) {
+  uint32_t d;
+  asm("tanh.approx.bf16x2 %0, %1;" : "=r"(d) : "r"(a));
+  return d;
+}
+// x = two bf16 pre-activations -> h = gelu_tanh(x), g = d gelu_tanh / dx (both packed bf16x2): 12 instructions per pair
+__device__ __forceinline__ void gelu_tanh_pair_bf16x2(uint32_t x, uint32_t& h, uint32_t& g) {
+  constexpr uint32_t C0 = 0x3F4C3F4Cu;    // 0.79788 (sqrt(2/pi))
+  constexpr uint32_t C1 = 0x3D123D12u;    // 0.035677
+  constexpr uint32_t C2 = 0x3DDB3DDBu;    // 0.10703 (3 * C1)
+  constexpr uint32_t HALF = 0x3F003F00u, ONE = 0x3F803F80u;
+  const uint32_t x2 = bmul2(x, x);
+  const uint32_t t = btanh2(bmul2(x, bfma2(C1, x2, C0)));
+  const uint32_t hx = bmul2(HALF, x);
+  h = bfma2(hx, t, hx);
+  const uint32_t s = bfma2(t ^ 0x80008000u, t, ONE);  // 1 - t^2
+  g = bfma2(bmul2(hx, s), bfma2(C2, x2, C0), bfma2(HALF, t, HALF));
+}
+
 __device__ __forceinline__ uint32_t pack_bf16(float lo, float hi) {
   __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);
   return *reinterpret_cast<uint32_t*>(&v);
