@@ -72,6 +72,11 @@ constexpr int A_NEW = FVGN_BWD_A_EPI_WARPS;
 // of 26).  Measured on B200: the kernel gets only 1.5-3 % faster (E1 / E2 are a quarter of the tile time) while the worst
 // parameter-gradient error of the bf16 golden run grows from 3.5e-2 to 1.1e-1 (a LayerNorm gamma), so the default stays
 // the fp32 evaluation with one rounding at the end.
+// FVGN_COLSUM_PACKED = 1 adds four rows of a bias-gradient column sum as packed bf16x2 before going to fp32 (fewer
+// instructions, measured: no change of the golden-run gradient errors, 1 % faster); 0 = plain fp32 accumulation.
+#ifndef FVGN_COLSUM_PACKED
+#define FVGN_COLSUM_PACKED 1
+#endif
 #ifndef FVGN_GELU_PACKED
 #define FVGN_GELU_PACKED 0
 #endif
@@ -94,7 +99,7 @@ constexpr int A_EPI = A_NEW * 32;  // epilogue threads
 template <int N> __device__ __forceinline__ void epi_bar_sync_n() { asm volatile("bar.sync 1, %0;" ::"n"(N) : "memory"); }
 
 // column sums of a bf16 tile by the epilogue threads: thread t owns column pair (2p, 2p+1), p = t & 63, rows [ROWS*(t>>6), +ROWS).
-// Four rows at a time are added as packed bf16x2 (2 roundings), the groups are accumulated in fp32.
+// Accumulated in fp32 (or, FVGN_COLSUM_PACKED, four rows at a time as packed bf16x2).
 __device__ __forceinline__ uint32_t hadd2_bf16(uint32_t a, uint32_t b) {
   uint32_t r;
   asm("add.rn.bf16x2 %0, %1, %2;" : "=r"(r) : "r"(a), "r"(b));
@@ -112,9 +117,14 @@ __device__ __forceinline__ void tile_colsum_n(const uint8_t* buf, int t, float& 
     const uint32_t w1 = *reinterpret_cast<const uint32_t*>(base + sw128_off(r + 1, chunk));
     const uint32_t w2 = *reinterpret_cast<const uint32_t*>(base + sw128_off(r + 2, chunk));
     const uint32_t w3 = *reinterpret_cast<const uint32_t*>(base + sw128_off(r + 3, chunk));
-    const uint32_t w = hadd2_bf16(hadd2_bf16(w0, w1), hadd2_bf16(w2, w3));
+#if FVGN_COLSUM_PACKED
+    const uint32_t w = hadd2_bf16(hadd2_bf16(w0, w1), hadd2_bf16(w2, w3));  // two extra bf16 roundings per 4 rows
     a += bf16_lo(w);
     b += bf16_hi(w);
+#else
+    a += (bf16_lo(w0) + bf16_lo(w1)) + (bf16_lo(w2) + bf16_lo(w3));        // exact fp32 accumulation of the bf16 tile
+    b += (bf16_hi(w0) + bf16_hi(w1)) + (bf16_hi(w2) + bf16_hi(w3));
+#endif
   }
   s0 += a;
   s1 += b;
