@@ -77,6 +77,21 @@ __global__ void pack_weights_kernel(const float* __restrict__ w1, const float* _
 // Memory side: layer-1 operands come from bf16 shadows (8 x 16 B per thread per chunk, held in registers two chunks
 // ahead of the ring); every result leaves through a 4 KB swizzled staging tile per warp as 128-B row segments
 // (Z1 image: one 4 KB bulk store per 64 columns; fp32 residual stream and bf16 shadows: 4 rows per warp instruction).
+#ifdef FVGN_TIMING
+// debug build: cycle breakdown of the forward epilogue chain of pipeline 0 (thread 0 of CTA 0), summed over its tiles
+__device__ unsigned long long g_prof_f[16];
+#define PROF_F(i)                                               \
+  do {                                                          \
+    if (blockIdx.x == 0 && tid == 0) {                          \
+      const long long now_ = clock64();                         \
+      g_prof_f[i] += (unsigned long long)(now_ - tprev_);       \
+      tprev_ = now_;                                            \
+    }                                                           \
+  } while (0)
+#else
+#define PROF_F(i) do { } while (0)
+#endif
+
 template <int MODE>
 __global__ void __launch_bounds__(NTHREADS, 1) mlp_tc_fwd_kernel(const fvgn_mlp_desc d) {
   using C = TCfg<MODE>;
@@ -225,6 +240,9 @@ __global__ void __launch_bounds__(NTHREADS, 1) mlp_tc_fwd_kernel(const fvgn_mlp_
     const bool do_res = resid && d.out_res;
     bool stg_busy = false;  // a bulk store may still be reading the staging tile
     uint32_t ph1 = 0, ph23 = 0;
+#ifdef FVGN_TIMING
+    long long tprev_ = clock64();
+#endif
     for (int64_t i = p; i < ntl; i += 2) {
       const int64_t tile = blockIdx.x + i * gridDim.x;
       const int64_t row0 = tile * TILE_M;
@@ -243,9 +261,11 @@ __global__ void __launch_bounds__(NTHREADS, 1) mlp_tc_fwd_kernel(const fvgn_mlp_
         if (layer == 0) {
           mbar_wait(BAR(B_L1 + p), ph1);
           ph1 ^= 1;
+          PROF_F(0);  // wait layer 1 (producers + MMA)
         } else {
           mbar_wait(BAR(B_L23 + p), ph23);
           ph23 ^= 1;
+          PROF_F(2);  // wait layer 2
         }
         tc_fence_after();
         const uint32_t acc = layer == 0 ? t1 : t2;
@@ -297,10 +317,12 @@ __global__ void __launch_bounds__(NTHREADS, 1) mlp_tc_fwd_kernel(const fvgn_mlp_
         tmem_wait_st();
         tc_fence_before();
         mbar_arrive(BAR(B_A + p));
+        if (layer == 0) PROF_F(1); else PROF_F(3);  // epilogue of layer 1 / layer 2
       }
       // ---- output layer (accumulated into T1)
       mbar_wait(BAR(B_L23 + p), ph23);
       ph23 ^= 1;
+      PROF_F(4);  // wait layer 3
       tc_fence_after();
       const uint32_t acc = t1;
       if (C::LN) {
@@ -318,6 +340,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) mlp_tc_fwd_kernel(const fvgn_mlp_
         });
         const float mean = sum * (1.0f / 128.0f);
         const float rstd = rsqrtf(fmaxf(sq * (1.0f / 128.0f) - mean * mean, 0.f) + 1e-5f);
+        PROF_F(5);  // LayerNorm statistics
         if (stg_busy) {
           if (lane == 0) bulk_wait_read0();
           __syncwarp();
@@ -382,6 +405,10 @@ __global__ void __launch_bounds__(NTHREADS, 1) mlp_tc_fwd_kernel(const fvgn_mlp_
         }
       }
       tc_fence_before();
+      PROF_F(6);  // normalise + residual + write-out
+#ifdef FVGN_TIMING
+      if (blockIdx.x == 0 && tid == 0) g_prof_f[15] += 1;
+#endif
     }
     if (lane == 0) bulk_wait0();  // the last Z1 bulk store must be done before shared memory is released
   }
@@ -416,6 +443,17 @@ int launch_tc_fwd(const fvgn_mlp_desc& d, void* stream) {
 }
 
 }  // namespace
+
+#ifdef FVGN_TIMING
+extern "C" int fvgn_debug_profile_f(unsigned long long* out16, int reset) {
+  if (cudaMemcpyFromSymbol(out16, g_prof_f, sizeof(unsigned long long) * 16) != cudaSuccess) return FVGN_ERR_LAUNCH;
+  if (reset) {
+    unsigned long long z[16] = {0};
+    cudaMemcpyToSymbol(g_prof_f, z, sizeof(z));
+  }
+  return FVGN_OK;
+}
+#endif
 
 int fvgn_mlp_forward_tc(const fvgn_mlp_desc* d, void* stream) {
   if (!d->w_bf16) return FVGN_ERR_NULL;

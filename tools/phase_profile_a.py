@@ -18,6 +18,16 @@ fn = ctypes.CDLL(_lib.LIB_PATH).fvgn_debug_profile_a
 fn.argtypes = [ctypes.c_void_p, ctypes.c_int]
 rc = fn(buf, 0)
 names = ["wait Z1", "E1", "wait R2", "E2", "wait R3", "wait dO", "E3+db3", "wait M3", "E4+db2", "wait M4", "E5+db1"]
+bf = (ctypes.c_ulonglong * 16)()
+ff = ctypes.CDLL(_lib.LIB_PATH).fvgn_debug_profile_f
+ff.argtypes = [ctypes.c_void_p, ctypes.c_int]
+ff(bf, 0)
+nf = ["wait L1", "epi L1", "wait L2", "epi L2", "wait L3", "LN stats", "output"]
+tf = max(int(bf[15]), 1)
+totf = sum(int(bf[i]) for i in range(7))
+print(f"forward (pipeline 0 of CTA 0): tiles={tf} cycles/tile={totf / tf:.0f}")
+for i, n in enumerate(nf):
+    print(f"  {n:10s} {int(bf[i]) / tf:8.0f} cyc  {int(bf[i]) / max(totf, 1) * 100:5.1f}%")
 tiles = max(int(buf[15]), 1)
 tot = sum(int(buf[i]) for i in range(11))
 print(f"rc={rc} tiles(CTA0, all launches)={tiles} cycles/tile={tot / tiles:.0f}")
