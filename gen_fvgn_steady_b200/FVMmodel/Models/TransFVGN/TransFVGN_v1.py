@@ -23,4 +23,5 @@ class Simulator(nn.Module):
             latent = model(latent)
             latent = halo_refresh(latent, i, nblk)  # cell-partition mode only (no-op otherwise)
         latent.x = self.TransBlock(latent.x + node_embedding, graph_node.batch, halo=getattr(latent, "_fvgn_halo", None))
+        latent._xh = self.TransBlock.last_shadow   # bf16 mode: (x, shadow) written by the block's last kernel
         return self.decoder(latent)

@@ -9,7 +9,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libfvgn_b200.so")
-SOURCES = ["segreduce.cu", "mlp_simt.cu", "mlp_tc.cu", "mlp_tc_bwd.cu", "mlp_api.cu", "misc.cu", "fv.cu"]
+SOURCES = ["segreduce.cu", "mlp_simt.cu", "mlp_tc.cu", "mlp_tc_bwd.cu", "mlp_api.cu", "misc.cu", "fv.cu", "transolver.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "--use_fast_math=false",
               "-Xcompiler", "-fPIC", "-shared", "-Xptxas", "-v"]
 

@@ -1,0 +1,595 @@
+// Transolver_block kernels (reference: src/FVMmodel/Models/GraphTransolver/GraphTransolver.py:25-169).
+//
+// The block is  x -> [in_project_fx | in_project_x] -> slice softmax -> per-graph slice tokens -> token attention ->
+// de-slice -> to_out (+x) -> LayerNorm -> Linear-GELU-Linear (+residual).  The four dense projections are plain library
+// GEMMs on the host side; everything the reference does with broadcast products + torch_scatter (its [N,8,32,16]
+// temporary, GraphTransolver.py:62-88) and with separate elementwise launches is fused here:
+//
+//   ts_slice_kernel<true>   in_project_slice + /graph_temperature + softmax (:59-61) and the per-graph token sums
+//                           slice_norm / slice_token (:62-72) as deterministic per-chunk partials
+//   ts_slice_kernel<false>  the same token sum for an arbitrary value tile (backward: d out_slice_token)
+//   ts_deslice_kernel       out_x[n,h,:] = sum_g sw[n,h,g] tok[b(n),h,g,:]   (:83-90)
+//   ts_slice_bwd_kernel     autograd of slice + de-slice w.r.t. the projections, in_project_slice and graph_temperature
+//   ts_res_ln_*             y = a + bias + residual ; z = LayerNorm(y)       (:163-169, to_out bias + ln_2) and backward
+//   ts_bias_gelu_*          h = GELU(hpre + b) (:105,124) and backward ; ts_bias_res: out = a + bias + residual
+//
+// Sizes are the reference's: 8 heads x 16 channels, 32 slices (TransFVGN_v1.py / _v2.py: num_heads=8, slice_num=32).
+// Thread mappings avoid warp shuffles: per-(node, head) work is done by one thread on a padded shared-memory tile
+// (row stride 260 / 132 floats: lane n touches banks 4n..4n+3, conflict-free 16-B accesses), cross-node sums walk the
+// tile in row order, so every result is bit-reproducible for a given chunk table.
+#include "common.cuh"
+
+#ifndef FVGN_EMU
+#include <cuda_bf16.h>
+#endif
+
+namespace {
+
+constexpr int TS_HEADS = 8;
+constexpr int TS_DH = 16;
+constexpr int TS_G = 32;
+constexpr int TS_TILE = 32;                                // nodes per tile (= lanes of the per-head warp)
+constexpr int TS_RS = 260;                                 // padded row stride of a [32][256] tile
+constexpr int TS_RS1 = 132;                                // padded row stride of a [32][128] tile
+constexpr int TS_TOK = TS_HEADS * TS_G * TS_DH;            // 4096 token numerators per graph
+constexpr int TS_TOKW = TS_TOK + TS_HEADS * TS_G;          // + 256 norms
+constexpr int TS_PARAMW = TS_G * TS_DH + TS_G + TS_HEADS + 256;  // dWs | dbs | dT | colsum(dP)
+constexpr int TS_NT = 256;
+
+template <int W, int RS>
+__device__ __forceinline__ void ts_load_tile(float* s, const float* __restrict__ g, int64_t ld, int64_t row0, int64_t r1) {
+  constexpr int V = W / 4;
+  for (int i = threadIdx.x; i < TS_TILE * V; i += TS_NT) {
+    const int r = i / V, c4 = i % V;
+    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (row0 + r < r1) v = ld4(g + (size_t)(row0 + r) * ld + c4 * 4);
+    st4(s + r * RS + c4 * 4, v);
+  }
+}
+
+template <int W, int RS>
+__device__ __forceinline__ void ts_store_tile(const float* s, float* __restrict__ g, int64_t ld, int64_t row0, int64_t r1) {
+  constexpr int V = W / 4;
+  for (int i = threadIdx.x; i < TS_TILE * V; i += TS_NT) {
+    const int r = i / V, c4 = i % V;
+    if (row0 + r < r1) st4(g + (size_t)(row0 + r) * ld + c4 * 4, ld4(s + r * RS + c4 * 4));
+  }
+}
+
+__device__ __forceinline__ void ld16(float* dst, const float* src) {
+#pragma unroll
+  for (int q = 0; q < 4; ++q) {
+    const float4 v = ld4(src + q * 4);
+    dst[q * 4 + 0] = v.x; dst[q * 4 + 1] = v.y; dst[q * 4 + 2] = v.z; dst[q * 4 + 3] = v.w;
+  }
+}
+__device__ __forceinline__ void st16(float* dst, const float* src) {
+#pragma unroll
+  for (int q = 0; q < 4; ++q) st4(dst + q * 4, make_float4(src[q * 4], src[q * 4 + 1], src[q * 4 + 2], src[q * 4 + 3]));
+}
+
+// logits of one (node, head): l[g] = bs[g] + sum_c xm[c] Ws[g,c]   (in_project_slice, GraphTransolver.py:60)
+__device__ __forceinline__ void ts_logits(float* l, const float* xm, const float* Wss, const float* bss) {
+#pragma unroll
+  for (int g = 0; g < TS_G; ++g) {
+    float w[16];
+    ld16(w, Wss + g * 16);
+    float a = bss[g];
+#pragma unroll
+    for (int c = 0; c < 16; ++c) a += xm[c] * w[c];
+    l[g] = a;
+  }
+}
+
+// ----------------------------------------------------------------------------------------------------------------
+// FROM_P : P[N,256] = [fx_mid | x_mid] -> sw[N,256] (written) and partial[chunk] = (sum_n sw (x) fx_mid | sum_n sw)
+// !FROM_P: sw[N,256] (read), V[N,128]  ->                  partial[chunk] = (sum_n sw (x) V      | sum_n sw)
+template <bool FROM_P>
+__global__ void __launch_bounds__(TS_NT) ts_slice_kernel(const float* __restrict__ P, int64_t ldp, float* sw,
+                                                         const float* __restrict__ Ws, const float* __restrict__ bs,
+                                                         const float* __restrict__ temp, const int32_t* __restrict__ chunks,
+                                                         float* __restrict__ partial) {
+  FVGN_DYN_SMEM(smem);
+  float* Ps = reinterpret_cast<float*>(smem);  // [32][260]  (FROM_P: fx|xm ; else V in the first 128 columns)
+  float* sws = Ps + TS_TILE * TS_RS;           // [32][260]
+  float* Wss = sws + TS_TILE * TS_RS;          // [32][16]
+  float* bss = Wss + TS_G * TS_DH;             // [32]
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int64_t r0 = chunks[blockIdx.x * 3 + 1], r1 = chunks[blockIdx.x * 3 + 2];
+  float T = 1.f;
+  if (FROM_P) {
+    for (int i = tid; i < TS_G * TS_DH; i += TS_NT) Wss[i] = Ws[i];
+    if (tid < TS_G) bss[tid] = bs[tid];
+    T = temp[warp];
+  }
+  float acc[16];
+#pragma unroll
+  for (int d = 0; d < 16; ++d) acc[d] = 0.f;
+  float nrm = 0.f;
+  for (int64_t row0 = r0; row0 < r1; row0 += TS_TILE) {
+    if (FROM_P) {
+      ts_load_tile<256, TS_RS>(Ps, P, ldp, row0, r1);
+    } else {
+      ts_load_tile<128, TS_RS>(Ps, P, ldp, row0, r1);
+      ts_load_tile<256, TS_RS>(sws, sw, 256, row0, r1);
+    }
+    __syncthreads();
+    if (FROM_P) {
+      // thread = (head = warp, node = lane)
+      float xm[16], l[TS_G];
+      ld16(xm, Ps + lane * TS_RS + 128 + warp * 16);
+      ts_logits(l, xm, Wss, bss);
+      float m = -INFINITY;
+#pragma unroll
+      for (int g = 0; g < TS_G; ++g) { l[g] = l[g] / T; m = fmaxf(m, l[g]); }
+      float s = 0.f;
+#pragma unroll
+      for (int g = 0; g < TS_G; ++g) { l[g] = expf(l[g] - m); s += l[g]; }
+      const bool valid = row0 + lane < r1;
+#pragma unroll
+      for (int g = 0; g < TS_G; ++g) l[g] = valid ? l[g] / s : 0.f;
+      float* dst = sws + lane * TS_RS + warp * TS_G;
+      st16(dst, l);
+      st16(dst + 16, l + 16);
+      __syncthreads();
+      ts_store_tile<256, TS_RS>(sws, sw, 256, row0, r1);
+    }
+    // thread = (head = warp, slice = lane): token sums in row order
+#pragma unroll 4
+    for (int n = 0; n < TS_TILE; ++n) {
+      const float s = sws[n * TS_RS + warp * TS_G + lane];
+      float f[16];
+      ld16(f, Ps + n * TS_RS + warp * 16);
+#pragma unroll
+      for (int d = 0; d < 16; ++d) acc[d] += s * f[d];
+      nrm += s;
+    }
+    __syncthreads();
+  }
+  float* out = partial + (size_t)blockIdx.x * TS_TOKW;
+  st16(out + (warp * TS_G + lane) * 16, acc);
+  out[TS_TOK + warp * TS_G + lane] = nrm;
+}
+
+// ----------------------------------------------------------------------------------------------------------------
+// out[n, h*16+d] = sum_g sw[n,h,g] tok[seg % tok_mod, h, g, d]
+__global__ void __launch_bounds__(TS_NT) ts_deslice_kernel(const float* __restrict__ sw, const float* __restrict__ tok,
+                                                           int64_t tok_ld, int tok_mod, const int32_t* __restrict__ chunks,
+                                                           float* __restrict__ out) {
+  FVGN_DYN_SMEM(smem);
+  float* sws = reinterpret_cast<float*>(smem);  // [32][260]
+  float* Ts = sws + TS_TILE * TS_RS;            // [8][32][16]
+  float* outs = Ts + TS_TOK;                    // [32][132]
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int seg = chunks[blockIdx.x * 3 + 0];
+  const int64_t r0 = chunks[blockIdx.x * 3 + 1], r1 = chunks[blockIdx.x * 3 + 2];
+  const float* tp = tok + (size_t)(seg % tok_mod) * tok_ld;
+  for (int i = tid; i < TS_TOK / 4; i += TS_NT) st4(Ts + i * 4, ld4(tp + i * 4));
+  for (int64_t row0 = r0; row0 < r1; row0 += TS_TILE) {
+    ts_load_tile<256, TS_RS>(sws, sw, 256, row0, r1);
+    __syncthreads();
+    float s[TS_G], o[16];
+    ld16(s, sws + lane * TS_RS + warp * TS_G);
+    ld16(s + 16, sws + lane * TS_RS + warp * TS_G + 16);
+#pragma unroll
+    for (int d = 0; d < 16; ++d) o[d] = 0.f;
+#pragma unroll
+    for (int g = 0; g < TS_G; ++g) {
+      float t[16];
+      ld16(t, Ts + (warp * TS_G + g) * 16);
+#pragma unroll
+      for (int d = 0; d < 16; ++d) o[d] += s[g] * t[d];
+    }
+    st16(outs + lane * TS_RS1 + warp * 16, o);
+    __syncthreads();
+    ts_store_tile<128, TS_RS1>(outs, out, 128, row0, r1);
+  }
+}
+
+// ----------------------------------------------------------------------------------------------------------------
+// Backward of slice + de-slice for one chunk.  Inputs: P = [fx|xm], sw, dox = d out_x, tok_out (forward tokens after
+// attention), d_tok = [d slice_token numerators | d slice_norm] (zero for chunks of graphs this rank does not own).
+// Outputs: dP[N,256] = [d fx | d xm] and partial[chunk] = (dWs[32,16] | dbs[32] | d graph_temperature[8] | colsum dP[256]).
+__global__ void __launch_bounds__(TS_NT, 1) ts_slice_bwd_kernel(const float* __restrict__ P, const float* __restrict__ sw,
+                                                                const float* __restrict__ dox, const float* __restrict__ tok_out,
+                                                                const float* __restrict__ d_tok, int tok_mod,
+                                                                const float* __restrict__ Ws, const float* __restrict__ bs,
+                                                                const float* __restrict__ temp, const int32_t* __restrict__ chunks,
+                                                                float* __restrict__ dP, float* __restrict__ partial) {
+  FVGN_DYN_SMEM(smem);
+  float* Ps = reinterpret_cast<float*>(smem);  // [32][260]
+  float* sws = Ps + TS_TILE * TS_RS;           // [32][260]
+  float* dxs = sws + TS_TILE * TS_RS;          // [32][132]
+  float* OTs = dxs + TS_TILE * TS_RS1;         // [8][32][16]
+  float* DNs = OTs + TS_TOK;                   // [8][32][16]
+  float* dns = DNs + TS_TOK;                   // [8][32]
+  float* Wss = dns + TS_HEADS * TS_G;          // [32][16]
+  float* bss = Wss + TS_G * TS_DH;             // [32]
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int seg = chunks[blockIdx.x * 3 + 0];
+  const int64_t r0 = chunks[blockIdx.x * 3 + 1], r1 = chunks[blockIdx.x * 3 + 2];
+  const bool own = seg < tok_mod;
+  const float* otp = tok_out + (size_t)(seg % tok_mod) * TS_TOK;
+  const float* dtp = d_tok + (size_t)(seg % tok_mod) * TS_TOKW;
+  for (int i = tid; i < TS_TOK / 4; i += TS_NT) {
+    st4(OTs + i * 4, ld4(otp + i * 4));
+    st4(DNs + i * 4, own ? ld4(dtp + i * 4) : make_float4(0.f, 0.f, 0.f, 0.f));
+  }
+  dns[tid] = own ? dtp[TS_TOK + tid] : 0.f;
+  for (int i = tid; i < TS_G * TS_DH; i += TS_NT) Wss[i] = Ws[i];
+  if (tid < TS_G) bss[tid] = bs[tid];
+  const float T = temp[warp];
+  float accW[16];
+#pragma unroll
+  for (int c = 0; c < 16; ++c) accW[c] = 0.f;
+  float accb = 0.f, accT = 0.f, acccol = 0.f;
+  for (int64_t row0 = r0; row0 < r1; row0 += TS_TILE) {
+    ts_load_tile<256, TS_RS>(Ps, P, 256, row0, r1);
+    ts_load_tile<256, TS_RS>(sws, sw, 256, row0, r1);
+    ts_load_tile<128, TS_RS1>(dxs, dox, 128, row0, r1);
+    __syncthreads();
+    {  // thread = (head = warp, node = lane)
+      float s[TS_G], ds[TS_G], a[16], b[16];
+      float* srow = sws + lane * TS_RS + warp * TS_G;
+      float* frow = Ps + lane * TS_RS + warp * 16;
+      float* xrow = dxs + lane * TS_RS1 + warp * 16;
+      ld16(s, srow);
+      ld16(s + 16, srow + 16);
+      ld16(a, xrow);  // d out_x
+      ld16(b, frow);  // fx_mid
+      float dot = 0.f;
+#pragma unroll
+      for (int g = 0; g < TS_G; ++g) {
+        float o[16], dn[16];
+        ld16(o, OTs + (warp * TS_G + g) * 16);
+        ld16(dn, DNs + (warp * TS_G + g) * 16);
+        float v = dns[warp * TS_G + g];
+#pragma unroll
+        for (int d = 0; d < 16; ++d) v += a[d] * o[d] + b[d] * dn[d];
+        ds[g] = v;
+        dot += s[g] * v;
+      }
+      // d fx_mid[d] = sum_g sw[g] d_num[g,d]   (overwrites fx in the tile)
+#pragma unroll
+      for (int d = 0; d < 16; ++d) a[d] = 0.f;
+#pragma unroll
+      for (int g = 0; g < TS_G; ++g) {
+        float dn[16];
+        ld16(dn, DNs + (warp * TS_G + g) * 16);
+#pragma unroll
+        for (int d = 0; d < 16; ++d) a[d] += s[g] * dn[d];
+      }
+      st16(frow, a);
+      // softmax backward (scaled logits z = l / T), then through /T and in_project_slice
+      ld16(b, Ps + lane * TS_RS + 128 + warp * 16);  // x_mid
+#pragma unroll
+      for (int c = 0; c < 16; ++c) a[c] = 0.f;
+#pragma unroll
+      for (int g = 0; g < TS_G; ++g) {
+        float w[16];
+        ld16(w, Wss + g * 16);
+        float lg = bss[g];
+#pragma unroll
+        for (int c = 0; c < 16; ++c) lg += b[c] * w[c];
+        const float dz = s[g] * (ds[g] - dot);
+        accT += dz * lg;
+        const float dl = dz / T;
+        ds[g] = dl;
+#pragma unroll
+        for (int c = 0; c < 16; ++c) a[c] += dl * w[c];
+      }
+      st16(xrow, a);      // d x_mid
+      st16(srow, ds);     // d logits (pre-temperature) for the dWs sum below
+      st16(srow + 16, ds + 16);
+    }
+    __syncthreads();
+    // thread = (head = warp, slice = lane): dWs[g,c] += dl[n,h,g] x_mid[n,h,c], dbs[g] += dl
+#pragma unroll 4
+    for (int n = 0; n < TS_TILE; ++n) {
+      const float dl = sws[n * TS_RS + warp * TS_G + lane];
+      float x[16];
+      ld16(x, Ps + n * TS_RS + 128 + warp * 16);
+#pragma unroll
+      for (int c = 0; c < 16; ++c) accW[c] += dl * x[c];
+      accb += dl;
+    }
+    // dP tile = [d fx (Ps cols 0..127) | d xm (dxs)], column sums for the projection biases
+    for (int i = tid; i < TS_TILE * 64; i += TS_NT) {
+      const int r = i >> 6, c4 = i & 63;
+      if (row0 + r < r1) {
+        const float4 v = c4 < 32 ? ld4(Ps + r * TS_RS + c4 * 4) : ld4(dxs + r * TS_RS1 + (c4 - 32) * 4);
+        st4(dP + (size_t)(row0 + r) * 256 + c4 * 4, v);
+      }
+    }
+#pragma unroll 4
+    for (int r = 0; r < TS_TILE; ++r) acccol += tid < 128 ? Ps[r * TS_RS + tid] : dxs[r * TS_RS1 + tid - 128];
+    __syncthreads();
+  }
+  // cross-warp (head) sums in fixed order
+  float* red = sws;        // [8][32][16]
+  float* red2 = Ps;        // [8][32] dbs partials, then [8][32] dT partials
+  st16(red + (warp * TS_G + lane) * 16, accW);
+  red2[warp * 32 + lane] = accb;
+  red2[256 + warp * 32 + lane] = accT;
+  __syncthreads();
+  float* out = partial + (size_t)blockIdx.x * TS_PARAMW;
+  for (int i = tid; i < TS_G * TS_DH; i += TS_NT) {
+    float v = 0.f;
+#pragma unroll
+    for (int h = 0; h < TS_HEADS; ++h) v += red[h * TS_G * 16 + i];
+    out[i] = v;
+  }
+  if (tid < TS_G) {
+    float v = 0.f;
+#pragma unroll
+    for (int h = 0; h < TS_HEADS; ++h) v += red2[h * 32 + tid];
+    out[TS_G * TS_DH + tid] = v;
+  }
+  if (tid < TS_HEADS) {
+    float v = 0.f;
+    for (int l = 0; l < 32; ++l) v += red2[256 + tid * 32 + l];
+    const float Th = temp[tid];
+    out[TS_G * TS_DH + TS_G + tid] = -v / (Th * Th);
+  }
+  out[TS_G * TS_DH + TS_G + TS_HEADS + tid] = acccol;
+}
+
+// ----------------------------------------------------------------------------------------------------------------
+// Row-wise kernels on [n,128] rows: warp = row, lane = 4 columns; row sums go through a per-warp shared-memory slot.
+#ifdef FVGN_EMU
+#define TS_WARP_SYNC() emu::syncwarp()
+#else
+#define TS_WARP_SYNC() __syncwarp()
+#endif
+
+__device__ __forceinline__ float ts_sum32(const float* p) {
+  float s = 0.f;
+#pragma unroll
+  for (int q = 0; q < 8; ++q) {
+    const float4 v = ld4(p + q * 4);
+    s += v.x; s += v.y; s += v.z; s += v.w;
+  }
+  return s;
+}
+
+// y = a + bias + res ; z = LayerNorm(y) * gamma + beta ; stats[row] = (mean, rstd)       (eps = 1e-5, nn.LayerNorm default)
+__global__ void __launch_bounds__(TS_NT) ts_res_ln_fwd_kernel(const float* __restrict__ a, const float* __restrict__ bias,
+                                                              const float* __restrict__ res, const float* __restrict__ gamma,
+                                                              const float* __restrict__ beta, float* __restrict__ y,
+                                                              float* __restrict__ z, float* __restrict__ stats, int64_t n) {
+  __shared__ __align__(16) float red[8][4][32];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const float4 b4 = ld4(bias + lane * 4), g4 = ld4(gamma + lane * 4), be4 = ld4(beta + lane * 4);
+  int it = 0;
+  for (int64_t row = (int64_t)blockIdx.x * 8 + warp; row < n; row += (int64_t)gridDim.x * 8, ++it) {
+    float4 v = add4(add4(ld4(a + row * 128 + lane * 4), b4), ld4(res + row * 128 + lane * 4));
+    st4(y + row * 128 + lane * 4, v);
+    float* r1 = red[warp][(it & 1) * 2];
+    float* r2 = red[warp][(it & 1) * 2 + 1];
+    r1[lane] = (v.x + v.y) + (v.z + v.w);
+    TS_WARP_SYNC();
+    const float mean = ts_sum32(r1) * (1.0f / 128.0f);
+    v.x -= mean; v.y -= mean; v.z -= mean; v.w -= mean;
+    r2[lane] = (v.x * v.x + v.y * v.y) + (v.z * v.z + v.w * v.w);
+    TS_WARP_SYNC();
+    const float rstd = 1.0f / sqrtf(ts_sum32(r2) * (1.0f / 128.0f) + 1e-5f);
+    st4(z + row * 128 + lane * 4, make_float4(v.x * rstd * g4.x + be4.x, v.y * rstd * g4.y + be4.y,
+                                              v.z * rstd * g4.z + be4.z, v.w * rstd * g4.w + be4.w));
+    if (lane == 0) { stats[row * 2] = mean; stats[row * 2 + 1] = rstd; }
+  }
+}
+
+// d_y = LayerNorm-backward(dz) + d_y_in ; partial[cta] = (dgamma[128] | dbeta[128] | colsum d_y[128])
+__global__ void __launch_bounds__(TS_NT) ts_res_ln_bwd_kernel(const float* __restrict__ dz, const float* __restrict__ y,
+                                                              const float* __restrict__ stats, const float* __restrict__ gamma,
+                                                              const float* __restrict__ d_y_in, float* __restrict__ d_y,
+                                                              float* __restrict__ partial, int64_t n) {
+  __shared__ __align__(16) float red[8][4][32];
+  __shared__ float redc[8][384];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const float4 g4 = ld4(gamma + lane * 4);
+  float4 ag = make_float4(0.f, 0.f, 0.f, 0.f), ab = ag, ac = ag;
+  int it = 0;
+  for (int64_t row = (int64_t)blockIdx.x * 8 + warp; row < n; row += (int64_t)gridDim.x * 8, ++it) {
+    const float mean = stats[row * 2], rstd = stats[row * 2 + 1];
+    const float4 yv = ld4(y + row * 128 + lane * 4), d = ld4(dz + row * 128 + lane * 4);
+    const float4 yh = make_float4((yv.x - mean) * rstd, (yv.y - mean) * rstd, (yv.z - mean) * rstd, (yv.w - mean) * rstd);
+    const float4 g = make_float4(d.x * g4.x, d.y * g4.y, d.z * g4.z, d.w * g4.w);
+    float* r1 = red[warp][(it & 1) * 2];
+    float* r2 = red[warp][(it & 1) * 2 + 1];
+    r1[lane] = (g.x + g.y) + (g.z + g.w);
+    r2[lane] = (g.x * yh.x + g.y * yh.y) + (g.z * yh.z + g.w * yh.w);
+    TS_WARP_SYNC();
+    const float c1 = ts_sum32(r1) * (1.0f / 128.0f), c2 = ts_sum32(r2) * (1.0f / 128.0f);
+    float4 o = make_float4(rstd * (g.x - c1 - yh.x * c2), rstd * (g.y - c1 - yh.y * c2), rstd * (g.z - c1 - yh.z * c2),
+                           rstd * (g.w - c1 - yh.w * c2));
+    if (d_y_in) o = add4(o, ld4(d_y_in + row * 128 + lane * 4));
+    st4(d_y + row * 128 + lane * 4, o);
+    ag = add4(ag, make_float4(d.x * yh.x, d.y * yh.y, d.z * yh.z, d.w * yh.w));
+    ab = add4(ab, d);
+    ac = add4(ac, o);
+  }
+  st4(&redc[warp][lane * 4], ag);
+  st4(&redc[warp][128 + lane * 4], ab);
+  st4(&redc[warp][256 + lane * 4], ac);
+  __syncthreads();
+  for (int i = threadIdx.x; i < 384; i += TS_NT) {
+    float s = 0.f;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) s += redc[w][i];
+    partial[(size_t)blockIdx.x * 384 + i] = s;
+  }
+}
+
+// h = GELU(hpre + bias) on [n,256] rows (exact erf GELU, nn.GELU default)
+__global__ void __launch_bounds__(TS_NT) ts_bias_gelu_fwd_kernel(const float* __restrict__ hpre, const float* __restrict__ bias,
+                                                                 float* __restrict__ h, int64_t n4) {
+  const int64_t i = (int64_t)blockIdx.x * TS_NT + threadIdx.x;
+  if (i >= n4) return;
+  const float4 b = ld4(bias + (i & 63) * 4), v = ld4(hpre + i * 4);
+  st4(h + i * 4, make_float4(gelu_exact(v.x + b.x), gelu_exact(v.y + b.y), gelu_exact(v.z + b.z), gelu_exact(v.w + b.w)));
+}
+
+// dhpre = dh * GELU'(hpre + bias) ; partial[cta] = colsum dhpre [256]
+__global__ void __launch_bounds__(TS_NT) ts_bias_gelu_bwd_kernel(const float* __restrict__ dh, const float* __restrict__ hpre,
+                                                                 const float* __restrict__ bias, float* __restrict__ dhpre,
+                                                                 float* __restrict__ partial, int64_t n) {
+  __shared__ __align__(16) float red[4][256];
+  const int c4 = threadIdx.x & 63, rsub = threadIdx.x >> 6;
+  const float4 b = ld4(bias + c4 * 4);
+  float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+  for (int64_t row = (int64_t)blockIdx.x * 4 + rsub; row < n; row += (int64_t)gridDim.x * 4) {
+    const float4 v = ld4(hpre + row * 256 + c4 * 4), d = ld4(dh + row * 256 + c4 * 4);
+    const float4 o = make_float4(d.x * gelu_grad(v.x + b.x), d.y * gelu_grad(v.y + b.y), d.z * gelu_grad(v.z + b.z),
+                                 d.w * gelu_grad(v.w + b.w));
+    st4(dhpre + row * 256 + c4 * 4, o);
+    acc = add4(acc, o);
+  }
+  st4(&red[rsub][c4 * 4], acc);
+  __syncthreads();
+  partial[(size_t)blockIdx.x * 256 + threadIdx.x] =
+      ((red[0][threadIdx.x] + red[1][threadIdx.x]) + red[2][threadIdx.x]) + red[3][threadIdx.x];
+}
+
+// out = a + bias + res on [n,128] rows (+ bf16 shadow of out)
+__global__ void __launch_bounds__(TS_NT) ts_bias_res_kernel(const float* __restrict__ a, const float* __restrict__ bias,
+                                                            const float* __restrict__ res, float* __restrict__ out,
+                                                            uint16_t* __restrict__ outh, int64_t n4) {
+  const int64_t i = (int64_t)blockIdx.x * TS_NT + threadIdx.x;
+  if (i >= n4) return;
+  const float4 v = add4(add4(ld4(a + i * 4), ld4(bias + (i & 31) * 4)), ld4(res + i * 4));
+  st4(out + i * 4, v);
+#ifndef FVGN_EMU
+  if (outh) {
+    __nv_bfloat162 lo = __floats2bfloat162_rn(v.x, v.y), hi = __floats2bfloat162_rn(v.z, v.w);
+    *reinterpret_cast<uint2*>(outh + i * 4) = make_uint2(*reinterpret_cast<uint32_t*>(&lo), *reinterpret_cast<uint32_t*>(&hi));
+  }
+#endif
+}
+
+constexpr size_t kSmemSlice = sizeof(float) * (2 * TS_TILE * TS_RS + TS_G * TS_DH + TS_G);
+constexpr size_t kSmemDeslice = sizeof(float) * (TS_TILE * TS_RS + TS_TOK + TS_TILE * TS_RS1);
+constexpr size_t kSmemBwd =
+    sizeof(float) * (2 * TS_TILE * TS_RS + TS_TILE * TS_RS1 + 2 * TS_TOK + TS_HEADS * TS_G + TS_G * TS_DH + TS_G);
+
+template <class K>
+int ts_set_smem(K kern, size_t bytes) {
+#ifndef FVGN_EMU
+  if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes) != cudaSuccess) return FVGN_ERR_LAUNCH;
+#endif
+  return FVGN_OK;
+}
+
+constexpr int kRowCtas = 148 * 4;  // CTAs of the grid-stride row kernels (also their number of partial rows)
+
+}  // namespace
+
+extern "C" int fvgn_ts_row_partials(int64_t n) {
+  const int64_t want = (n + 31) / 32;
+  return (int)(want < 1 ? 1 : (want < kRowCtas ? want : kRowCtas));
+}
+
+extern "C" int fvgn_ts_slice_forward(const float* P, const float* Ws, const float* bs, const float* temp, const int32_t* chunks,
+                                     int32_t nchunks, float* sw, float* partial, void* stream) {
+  if (nchunks <= 0) return FVGN_OK;
+  if (!P || !Ws || !bs || !temp || !chunks || !sw || !partial) return FVGN_ERR_NULL;
+  if (!fvgn_aligned16(P) || !fvgn_aligned16(sw) || !fvgn_aligned16(partial)) return FVGN_ERR_ALIGN;
+  auto kern = ts_slice_kernel<true>;
+  if (ts_set_smem(kern, kSmemSlice) != FVGN_OK) return FVGN_ERR_LAUNCH;
+  FVGN_LAUNCH(kern, (unsigned)nchunks, TS_NT, kSmemSlice, stream, P, (int64_t)256, sw, Ws, bs, temp, chunks, partial);
+  FVGN_CHECK_LAUNCH();
+  return FVGN_OK;
+}
+
+extern "C" int fvgn_ts_accumulate(const float* sw, const float* V, const int32_t* chunks, int32_t nchunks, float* partial,
+                                  void* stream) {
+  if (nchunks <= 0) return FVGN_OK;
+  if (!sw || !V || !chunks || !partial) return FVGN_ERR_NULL;
+  if (!fvgn_aligned16(V) || !fvgn_aligned16(sw) || !fvgn_aligned16(partial)) return FVGN_ERR_ALIGN;
+  auto kern = ts_slice_kernel<false>;
+  if (ts_set_smem(kern, kSmemSlice) != FVGN_OK) return FVGN_ERR_LAUNCH;
+  FVGN_LAUNCH(kern, (unsigned)nchunks, TS_NT, kSmemSlice, stream, V, (int64_t)128, const_cast<float*>(sw),
+              (const float*)nullptr, (const float*)nullptr, (const float*)nullptr, chunks, partial);
+  FVGN_CHECK_LAUNCH();
+  return FVGN_OK;
+}
+
+extern "C" int fvgn_ts_deslice(const float* sw, const float* tok, int64_t tok_ld, int32_t tok_mod, const int32_t* chunks,
+                               int32_t nchunks, float* out, void* stream) {
+  if (nchunks <= 0) return FVGN_OK;
+  if (!sw || !tok || !chunks || !out) return FVGN_ERR_NULL;
+  if (tok_mod < 1 || tok_ld < TS_TOK || (tok_ld & 3)) return FVGN_ERR_SHAPE;
+  if (!fvgn_aligned16(sw) || !fvgn_aligned16(tok) || !fvgn_aligned16(out)) return FVGN_ERR_ALIGN;
+  if (ts_set_smem(ts_deslice_kernel, kSmemDeslice) != FVGN_OK) return FVGN_ERR_LAUNCH;
+  FVGN_LAUNCH(ts_deslice_kernel, (unsigned)nchunks, TS_NT, kSmemDeslice, stream, sw, tok, tok_ld, (int)tok_mod, chunks, out);
+  FVGN_CHECK_LAUNCH();
+  return FVGN_OK;
+}
+
+extern "C" int fvgn_ts_slice_backward(const float* P, const float* sw, const float* d_out, const float* tok_out,
+                                      const float* d_tok, int32_t tok_mod, const float* Ws, const float* bs, const float* temp,
+                                      const int32_t* chunks, int32_t nchunks, float* dP, float* partial, void* stream) {
+  if (nchunks <= 0) return FVGN_OK;
+  if (!P || !sw || !d_out || !tok_out || !d_tok || !Ws || !bs || !temp || !chunks || !dP || !partial) return FVGN_ERR_NULL;
+  if (tok_mod < 1) return FVGN_ERR_SHAPE;
+  if (!fvgn_aligned16(P) || !fvgn_aligned16(sw) || !fvgn_aligned16(d_out) || !fvgn_aligned16(tok_out) ||
+      !fvgn_aligned16(d_tok) || !fvgn_aligned16(dP))
+    return FVGN_ERR_ALIGN;
+  if (ts_set_smem(ts_slice_bwd_kernel, kSmemBwd) != FVGN_OK) return FVGN_ERR_LAUNCH;
+  FVGN_LAUNCH(ts_slice_bwd_kernel, (unsigned)nchunks, TS_NT, kSmemBwd, stream, P, sw, d_out, tok_out, d_tok, (int)tok_mod, Ws,
+              bs, temp, chunks, dP, partial);
+  FVGN_CHECK_LAUNCH();
+  return FVGN_OK;
+}
+
+extern "C" int fvgn_ts_residual_ln_forward(const float* a, const float* bias, const float* res, const float* gamma,
+                                           const float* beta, float* y, float* z, float* stats, int64_t n, void* stream) {
+  if (n <= 0) return FVGN_OK;
+  if (!a || !bias || !res || !gamma || !beta || !y || !z || !stats) return FVGN_ERR_NULL;
+  FVGN_LAUNCH(ts_res_ln_fwd_kernel, (unsigned)fvgn_ts_row_partials(n), TS_NT, 0, stream, a, bias, res, gamma, beta, y, z, stats,
+              n);
+  FVGN_CHECK_LAUNCH();
+  return FVGN_OK;
+}
+
+extern "C" int fvgn_ts_residual_ln_backward(const float* dz, const float* y, const float* stats, const float* gamma,
+                                            const float* d_y_in, float* d_y, float* partial, int64_t n, void* stream) {
+  if (n <= 0) return FVGN_OK;
+  if (!dz || !y || !stats || !gamma || !d_y || !partial) return FVGN_ERR_NULL;
+  FVGN_LAUNCH(ts_res_ln_bwd_kernel, (unsigned)fvgn_ts_row_partials(n), TS_NT, 0, stream, dz, y, stats, gamma, d_y_in, d_y,
+              partial, n);
+  FVGN_CHECK_LAUNCH();
+  return FVGN_OK;
+}
+
+extern "C" int fvgn_ts_bias_gelu_forward(const float* hpre, const float* bias, float* h, int64_t n, void* stream) {
+  if (n <= 0) return FVGN_OK;
+  if (!hpre || !bias || !h) return FVGN_ERR_NULL;
+  const int64_t n4 = n * 64;
+  FVGN_LAUNCH_SEQ(ts_bias_gelu_fwd_kernel, (unsigned)((n4 + TS_NT - 1) / TS_NT), TS_NT, 0, stream, hpre, bias, h, n4);
+  FVGN_CHECK_LAUNCH();
+  return FVGN_OK;
+}
+
+extern "C" int fvgn_ts_bias_gelu_backward(const float* dh, const float* hpre, const float* bias, float* dhpre, float* partial,
+                                          int64_t n, void* stream) {
+  if (n <= 0) return FVGN_OK;
+  if (!dh || !hpre || !bias || !dhpre || !partial) return FVGN_ERR_NULL;
+  FVGN_LAUNCH(ts_bias_gelu_bwd_kernel, (unsigned)fvgn_ts_row_partials(n), TS_NT, 0, stream, dh, hpre, bias, dhpre, partial, n);
+  FVGN_CHECK_LAUNCH();
+  return FVGN_OK;
+}
+
+extern "C" int fvgn_ts_bias_residual(const float* a, const float* bias, const float* res, float* out, void* outh, int64_t n,
+                                     void* stream) {
+  if (n <= 0) return FVGN_OK;
+  if (!a || !bias || !res || !out) return FVGN_ERR_NULL;
+#ifdef FVGN_EMU
+  if (outh) return FVGN_ERR_UNSUPPORTED;
+#endif
+  const int64_t n4 = n * 32;
+  FVGN_LAUNCH_SEQ(ts_bias_res_kernel, (unsigned)((n4 + TS_NT - 1) / TS_NT), TS_NT, 0, stream, a, bias, res, out,
+                  reinterpret_cast<uint16_t*>(outh), n4);
+  FVGN_CHECK_LAUNCH();
+  return FVGN_OK;
+}

@@ -582,3 +582,229 @@ class FVLossFn(torch.autograd.Function):
         _lib.call("fvgn_wlsq_backward", fptr(d_grad), 7, iptr(plan.w_tptr), iptr(plan.w_trow), fptr(qt), fptr(qsum), 2,
                   fptr(d_phi), 1, plan.N, st)
         return d_phi, None, None, None, None, None, None, None
+
+
+# ------------------------------------------------------------------ Transolver_block (GraphTransolver.py:25-169)
+TS_HEADS, TS_DH, TS_G = 8, 16, 32
+TS_TOK = TS_HEADS * TS_G * TS_DH
+
+
+class TsPlan:
+    """Row chunks of the (graph-sorted) node rows for the slice kernels: every chunk lies inside one graph, one CTA per
+    chunk; chunk_ptr groups the chunks per graph for the deterministic combine.  nb = number of graphs whose tokens are
+    formed (cell-partition mode: graphs [nb, 2 nb) are the ghost rows, de-sliced with the tokens of graph id - nb)."""
+
+    def __init__(self, batch, halo=None):
+        batch = batch.reshape(-1)
+        n = int(batch.shape[0])
+        dev = batch.device
+        nseg = int(batch.max().item()) + 1 if n > 0 else 1
+        if halo is not None:
+            nseg = max(nseg, int(halo.num_graphs))
+        counts = torch.bincount(batch.to(torch.int64), minlength=nseg).cpu().tolist()
+        if n > 1 and bool((batch[1:] < batch[:-1]).any()):
+            raise RuntimeError("fvgn_b200: Transolver kernels need the batch vector sorted by graph (Load_mesh batches are)")
+        rows_per_chunk = max(32, min(1024, -(-n // (296 * 32)) * 32))
+        rows, ptr, start = [], [0], 0
+        for seg, cnt in enumerate(counts):
+            r = start
+            while r < start + cnt:
+                e = min(r + rows_per_chunk, start + cnt)
+                rows.append((seg, r, e))
+                r = e
+            start += cnt
+            ptr.append(len(rows))
+        self.n, self.nseg, self.n_chunks = n, nseg, len(rows)
+        self.nb = nseg if halo is None else halo.num_graphs
+        self.chunks = torch.tensor(rows if rows else [(0, 0, 0)], dtype=torch.int32, device=dev).reshape(-1, 3).contiguous()
+        self.chunk_ptr = torch.tensor(ptr, dtype=torch.int32, device=dev)
+        self.all_ptr = torch.tensor([0, len(rows)], dtype=torch.int32, device=dev)
+
+    _cache = {}
+
+    @classmethod
+    def of(cls, batch, halo=None):
+        key = (batch.data_ptr(), tuple(batch.shape), batch.device, None if halo is None else id(halo))
+        hit = cls._cache.get(key)
+        if hit is not None and hit[0]() is batch:
+            return hit[1]
+        import weakref
+        plan = cls(batch, halo)
+        if len(cls._cache) > 64:
+            cls._cache = {k: v for k, v in cls._cache.items() if v[0]() is not None}
+        cls._cache[key] = (weakref.ref(batch), plan)
+        return plan
+
+
+def _combine(partial, width, ptr, nseg):
+    out = _empty((nseg, width), partial)
+    _lib.call("fvgn_chunk_combine", fptr(partial), width, iptr(ptr), nseg, fptr(out), _lib.stream_ptr(partial.device))
+    return out
+
+
+def _row_partials(n):
+    return int(_lib.load().fvgn_ts_row_partials(n))
+
+
+def _token_attention(rec, wq, wk, wv, scale):
+    """GraphTransolver.py:72-81 on the [nb, 4352] token record (numerators | norms) -> attended tokens [nb, 4096].
+    [B,8,32,16]-sized glue: stays in PyTorch (also differentiated by PyTorch inside SliceAttentionFn.backward)."""
+    nb = rec.shape[0]
+    num = rec[:, :TS_TOK].reshape(nb, TS_HEADS, TS_G, TS_DH)
+    norm = rec[:, TS_TOK:].reshape(nb, TS_HEADS, TS_G)
+    tok = num / (norm.unsqueeze(-1) + 1e-5)
+    q, k, v = tok @ wq.t(), tok @ wk.t(), tok @ wv.t()
+    attn = torch.softmax(torch.matmul(q, k.transpose(-1, -2)) * scale, dim=-1)
+    return torch.matmul(attn, v).reshape(nb, TS_TOK)
+
+
+class SliceAttentionFn(torch.autograd.Function):
+    """Graph_Physics_Attention_1D.graph_forward (GraphTransolver.py:48-95) without the to_out bias:
+    x[N,128] -> to_out.weight @ deslice(attention(slice(x))).  Projections are library GEMMs; slice softmax, token sums,
+    de-slice and their autograd are the ts_* kernels; the [B,8,32,16] token attention is PyTorch glue."""
+
+    @staticmethod
+    def forward(ctx, x, wfx, bfx, wx, bx, ws, bs, temp, wq, wk, wv, wo, scale, tsp, halo):
+        x = _c(x)
+        n = x.shape[0]
+        st = _lib.stream_ptr(x.device)
+        wcat = torch.cat([wfx, wx], 0)
+        P = torch.addmm(torch.cat([bfx, bx], 0), x, wcat.t())                  # [N,256] = fx_mid | x_mid
+        ws_c, bs_c, temp_c = _c(ws.detach()), _c(bs.detach()), _c(temp.detach().reshape(-1))
+        sw = _empty((n, 256), x)
+        part = _empty((max(tsp.n_chunks, 1), _lib.FVGN_TS_TOKW), x)
+        _lib.call("fvgn_ts_slice_forward", fptr(P), fptr(ws_c), fptr(bs_c), fptr(temp_c), iptr(tsp.chunks), tsp.n_chunks,
+                  fptr(sw), fptr(part), st)
+        rec = _combine(part, _lib.FVGN_TS_TOKW, tsp.chunk_ptr, tsp.nseg)[:tsp.nb].contiguous()
+        if halo is not None:   # cell-partition mode: tokens are sums over the rows every rank owns
+            from .parallel import allreduce_sum_
+            rec = allreduce_sum_(rec)
+        tok_out = _c(_token_attention(rec, wq, wk, wv, scale))
+        out_x = _empty((n, 128), x)
+        _lib.call("fvgn_ts_deslice", fptr(sw), fptr(tok_out), TS_TOK, tsp.nb, iptr(tsp.chunks), tsp.n_chunks, fptr(out_x), st)
+        ctx.tsp, ctx.halo, ctx.scale = tsp, halo, scale
+        ctx.save_for_backward(x, P, sw, rec, tok_out, out_x, wcat, ws_c, bs_c, temp_c, wq, wk, wv, wo)
+        return out_x @ wo.t()
+
+    @staticmethod
+    def backward(ctx, d_a):
+        x, P, sw, rec, tok_out, out_x, wcat, ws_c, bs_c, temp_c, wq, wk, wv, wo = ctx.saved_tensors
+        tsp, halo = ctx.tsp, ctx.halo
+        n = x.shape[0]
+        st = _lib.stream_ptr(x.device)
+        d_a = _c(d_a)
+        d_wo = d_a.t() @ out_x
+        d_ox = d_a @ wo                                                         # [N,128]
+        part = _empty((max(tsp.n_chunks, 1), _lib.FVGN_TS_TOKW), x)
+        _lib.call("fvgn_ts_accumulate", fptr(sw), fptr(d_ox), iptr(tsp.chunks), tsp.n_chunks, fptr(part), st)
+        acc = _combine(part, _lib.FVGN_TS_TOKW, tsp.chunk_ptr, tsp.nseg)[:, :TS_TOK]
+        d_tok_out = acc[:tsp.nb]
+        if tsp.nseg > tsp.nb:   # ghost rows de-slice with the tokens of graph id - nb
+            extra = acc[tsp.nb:]
+            d_tok_out = d_tok_out.clone()
+            d_tok_out[:extra.shape[0]] += extra
+        with torch.enable_grad():
+            leaves = [t.detach().requires_grad_(True) for t in (rec, wq, wk, wv)]
+            ot = _token_attention(leaves[0], leaves[1], leaves[2], leaves[3], ctx.scale)
+            d_rec, d_wq, d_wk, d_wv = torch.autograd.grad(ot, leaves, d_tok_out)
+        if halo is not None:
+            from .parallel import allreduce_sum_
+            d_rec = allreduce_sum_(d_rec.contiguous())
+        d_rec = _c(d_rec)
+        dP = _empty((n, 256), x)
+        ppart = _empty((max(tsp.n_chunks, 1), _lib.FVGN_TS_PARAMW), x)
+        _lib.call("fvgn_ts_slice_backward", fptr(P), fptr(sw), fptr(d_ox), fptr(tok_out), fptr(d_rec), tsp.nb, fptr(ws_c),
+                  fptr(bs_c), fptr(temp_c), iptr(tsp.chunks), tsp.n_chunks, fptr(dP), fptr(ppart), st)
+        if tsp.n_chunks > 0:
+            pg = _combine(ppart, _lib.FVGN_TS_PARAMW, tsp.all_ptr, 1).reshape(-1)
+        else:
+            pg = torch.zeros(_lib.FVGN_TS_PARAMW, device=x.device)
+        d_ws, d_bs = pg[:512].view(TS_G, TS_DH), pg[512:544]
+        d_temp, d_bcat = pg[544:552].view(1, TS_HEADS, 1), pg[552:808]
+        d_x = dP @ wcat
+        d_wcat = dP.t() @ x
+        return (d_x, d_wcat[:128], d_bcat[:128], d_wcat[128:], d_bcat[128:], d_ws, d_bs, d_temp, d_wq, d_wk, d_wv, d_wo,
+                None, None, None)
+
+
+class ResidualLayerNormFn(torch.autograd.Function):
+    """(a, bias, res) -> y = a + bias + res, z = LayerNorm(y)   (to_out bias + residual + ln_2, GraphTransolver.py:163-169)."""
+
+    @staticmethod
+    def forward(ctx, a, bias, res, gamma, beta):
+        a, res = _c(a), _c(res)
+        n = a.shape[0]
+        y, z, stats = _empty((n, 128), a), _empty((n, 128), a), _empty((n, 2), a)
+        _lib.call("fvgn_ts_residual_ln_forward", fptr(a), fptr(_c(bias.detach())), fptr(res), fptr(_c(gamma.detach())),
+                  fptr(_c(beta.detach())), fptr(y), fptr(z), fptr(stats), n, _lib.stream_ptr(a.device))
+        ctx.set_materialize_grads(False)
+        ctx.save_for_backward(y, stats, gamma)
+        return y, z
+
+    @staticmethod
+    def backward(ctx, d_y_in, d_z):
+        y, stats, gamma = ctx.saved_tensors
+        n = y.shape[0]
+        if d_z is None:
+            d_z = torch.zeros_like(y)
+        npart = _row_partials(n)
+        d_y = _empty((n, 128), y)
+        part = _empty((npart, 384), y)
+        _lib.call("fvgn_ts_residual_ln_backward", fptr(_c(d_z)), fptr(y), fptr(stats), fptr(_c(gamma.detach())),
+                  fptr(_c(d_y_in) if d_y_in is not None else None, True), fptr(d_y), fptr(part), n, _lib.stream_ptr(y.device))
+        if n > 0:
+            ptr = torch.tensor([0, npart], dtype=torch.int32, device=y.device)
+            s = _combine(part, 384, ptr, 1).reshape(-1)
+        else:
+            s = torch.zeros(384, device=y.device)
+        return d_y, s[256:384], d_y, s[0:128], s[128:256]
+
+
+class BiasGeluFn(torch.autograd.Function):
+    """h = GELU(hpre + bias) on [N,256] rows (MLP.linear_pre, GraphTransolver.py:105,124)."""
+
+    @staticmethod
+    def forward(ctx, hpre, bias):
+        hpre = _c(hpre)
+        n = hpre.shape[0]
+        h = _empty((n, 256), hpre)
+        _lib.call("fvgn_ts_bias_gelu_forward", fptr(hpre), fptr(_c(bias.detach())), fptr(h), n, _lib.stream_ptr(hpre.device))
+        ctx.save_for_backward(hpre, bias)
+        return h
+
+    @staticmethod
+    def backward(ctx, d_h):
+        hpre, bias = ctx.saved_tensors
+        n = hpre.shape[0]
+        npart = _row_partials(n)
+        d_hpre = _empty((n, 256), hpre)
+        part = _empty((npart, 256), hpre)
+        _lib.call("fvgn_ts_bias_gelu_backward", fptr(_c(d_h)), fptr(hpre), fptr(_c(bias.detach())), fptr(d_hpre), fptr(part), n,
+                  _lib.stream_ptr(hpre.device))
+        if n > 0:
+            ptr = torch.tensor([0, npart], dtype=torch.int32, device=hpre.device)
+            d_b = _combine(part, 256, ptr, 1).reshape(-1)
+        else:
+            d_b = torch.zeros(256, device=hpre.device)
+        return d_hpre, d_b
+
+
+class BiasResidualFn(torch.autograd.Function):
+    """out = a + bias + res (+ the bf16 shadow of out for the next GnBlock / decoder in bf16 mode)."""
+
+    @staticmethod
+    def forward(ctx, a, bias, res, want_shadow):
+        a, res = _c(a), _c(res)
+        n = a.shape[0]
+        out = _empty((n, 128), a)
+        outh = torch.empty((n, 128), dtype=BF16, device=a.device) if want_shadow else None
+        _lib.call("fvgn_ts_bias_residual", fptr(a), fptr(_c(bias.detach())), fptr(res), fptr(out), hptr(outh, True), n,
+                  _lib.stream_ptr(a.device))
+        ctx.set_materialize_grads(False)
+        if outh is not None:
+            ctx.mark_non_differentiable(outh)
+        return out, outh
+
+    @staticmethod
+    def backward(ctx, d_out, _dh=None):
+        return d_out, d_out.sum(0), d_out, None

@@ -191,6 +191,43 @@ int fvgn_fv_backward(const fvgn_fv_desc* d, void* stream);
 int fvgn_fv_outputs(const fvgn_fv_desc* d, const int32_t* batch_node, const float* scale /*[B,3] uvp_dim*sigma*/,
                     int32_t ncn_smooth, float* uvp_node, float* uvp_cell, void* stream);
 
+/* ------------------------------------------------------------------ Transolver_block
+ * src/FVMmodel/Models/GraphTransolver/GraphTransolver.py:25-169, heads = 8, dim_head = 16, slice_num = 32 (TransFVGN_v1/v2).
+ * The dense projections (in_project_fx/x, to_out, mlp) are library GEMMs on the host side; these entry points replace the
+ * broadcast-product + torch_scatter slice / de-slice (:59-90) and the elementwise launches around the GEMMs.
+ * chunks[nchunks,3] = (graph id, row begin, row end), rows of a chunk belong to one graph; one CTA per chunk. */
+#define FVGN_TS_TOKW 4352   /* per-graph token record: 8*32*16 numerators | 8*32 norms */
+#define FVGN_TS_PARAMW 808  /* slice-backward record: dWs[32,16] | dbs[32] | d graph_temperature[8] | colsum dP[256] */
+/* number of CTAs (= partial rows) of the row-wise backward kernels for n rows */
+int fvgn_ts_row_partials(int64_t n);
+/* P[N,256] = [in_project_fx(x) | in_project_x(x)] -> sw[N,256] = softmax(in_project_slice(x_mid)/graph_temperature) (:59-61)
+ * and partial[nchunks,4352] = per-chunk sums of sw (x) fx_mid | sw (:62-72); combine with fvgn_chunk_combine. */
+int fvgn_ts_slice_forward(const float* P, const float* Ws, const float* bs, const float* temp, const int32_t* chunks,
+                          int32_t nchunks, float* sw, float* partial, void* stream);
+/* partial[nchunks,4352] = per-chunk sums of sw (x) V | sw for V[N,128] (backward of the de-slice w.r.t. the tokens) */
+int fvgn_ts_accumulate(const float* sw, const float* V, const int32_t* chunks, int32_t nchunks, float* partial, void* stream);
+/* out[n, h*16+d] = sum_g sw[n,h,g] tok[graph % tok_mod, h, g, d]  (:83-90); tok rows are tok_ld floats apart */
+int fvgn_ts_deslice(const float* sw, const float* tok, int64_t tok_ld, int32_t tok_mod, const int32_t* chunks, int32_t nchunks,
+                    float* out, void* stream);
+/* autograd of slice + de-slice: d_out = d out_x [N,128], tok_out[.,4096] the attended tokens, d_tok[.,4352] the gradient of
+ * the token record (ignored for graphs >= tok_mod: ghost rows of the cell-partition mode) -> dP[N,256], partial[nchunks,808] */
+int fvgn_ts_slice_backward(const float* P, const float* sw, const float* d_out, const float* tok_out, const float* d_tok,
+                           int32_t tok_mod, const float* Ws, const float* bs, const float* temp, const int32_t* chunks,
+                           int32_t nchunks, float* dP, float* partial, void* stream);
+/* y = a + bias + res ; z = LayerNorm(y) (to_out bias + residual + ln_2, :163-169); stats[N,2] = (mean, rstd) */
+int fvgn_ts_residual_ln_forward(const float* a, const float* bias, const float* res, const float* gamma, const float* beta,
+                                float* y, float* z, float* stats, int64_t n, void* stream);
+/* d_y = LayerNorm-backward(dz) + d_y_in (nullable) ; partial[fvgn_ts_row_partials(n),384] = dgamma | dbeta | colsum d_y */
+int fvgn_ts_residual_ln_backward(const float* dz, const float* y, const float* stats, const float* gamma, const float* d_y_in,
+                                 float* d_y, float* partial, int64_t n, void* stream);
+/* h[N,256] = GELU(hpre + bias) (MLP.linear_pre, :105,124) ; backward: dhpre = dh * GELU'(hpre + bias),
+ * partial[fvgn_ts_row_partials(n),256] = colsum dhpre */
+int fvgn_ts_bias_gelu_forward(const float* hpre, const float* bias, float* h, int64_t n, void* stream);
+int fvgn_ts_bias_gelu_backward(const float* dh, const float* hpre, const float* bias, float* dhpre, float* partial, int64_t n,
+                               void* stream);
+/* out[N,128] = a + bias + res (+ bf16 shadow outh, nullable) (linear_post bias + residual, :168) */
+int fvgn_ts_bias_residual(const float* a, const float* bias, const float* res, float* out, void* outh, int64_t n, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -144,6 +144,13 @@ T shfl(T v, int src_lane) {
   memcpy(&r, &got, sizeof(T));
   return r;
 }
+inline void syncwarp() {
+  if (!g_in_sync_launch) {
+    fprintf(stderr, "emu: warp barrier inside a FVGN_LAUNCH_SEQ kernel\n");
+    abort();
+  }
+  g_warps[t_linear / 32].bar->arrive_and_wait();
+}
 }  // namespace emu
 
 #define threadIdx emu::t_threadIdx
