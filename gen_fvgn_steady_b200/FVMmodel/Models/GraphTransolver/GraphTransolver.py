@@ -83,9 +83,9 @@ class Transolver_block(nn.Module):
         (`self.last_shadow = (out, shadow)`) for the GnBlock / decoder that consumes it."""
         x_in = self.ln_1(fx) if in_layernorm else fx
         a = self.Attn.attend(x_in, batch, halo)
-        y, z = ops.ResidualLayerNormFn.apply(a, self.Attn.to_out[0].bias, fx, self.ln_2.weight, self.ln_2.bias)
-        o = self.mlp.hidden(z) @ self.mlp.linear_post.weight.t()
         want_shadow = (getattr(self, "precision", None) or ops.default_precision()) == "bf16"
-        out, outh = ops.BiasResidualFn.apply(o, self.mlp.linear_post.bias, y, want_shadow)
+        out, outh = ops.BlockTailFn.apply(a, self.Attn.to_out[0].bias, fx, self.ln_2.weight, self.ln_2.bias,
+                                          self.mlp.linear_pre[0].weight, self.mlp.linear_pre[0].bias,
+                                          self.mlp.linear_post.weight, self.mlp.linear_post.bias, want_shadow)
         self.last_shadow = (out, outh) if want_shadow else None
         return out

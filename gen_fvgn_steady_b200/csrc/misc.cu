@@ -42,9 +42,18 @@ __global__ void chunk_combine_kernel(const float* __restrict__ partial, int widt
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= nseg * width) return;
   const int seg = i / width, c = i % width;
-  float s = 0.f;
-  for (int k = chunk_ptr[seg]; k < chunk_ptr[seg + 1]; ++k) s += partial[(size_t)k * width + c];
-  out[i] = s;
+  // fixed summation shape (four interleaved chains + tail): deterministic, and the loads of a long chunk list overlap
+  float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+  int k = chunk_ptr[seg];
+  const int end = chunk_ptr[seg + 1];
+  for (; k + 4 <= end; k += 4) {
+    s0 += partial[(size_t)k * width + c];
+    s1 += partial[(size_t)(k + 1) * width + c];
+    s2 += partial[(size_t)(k + 2) * width + c];
+    s3 += partial[(size_t)(k + 3) * width + c];
+  }
+  for (; k < end; ++k) s0 += partial[(size_t)k * width + c];
+  out[i] = (s0 + s1) + (s2 + s3);
 }
 
 extern "C" int fvgn_chunk_colsum(const float* x, int32_t width, int32_t ld, const float* center, int32_t center_ld,

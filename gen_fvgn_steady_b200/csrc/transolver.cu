@@ -36,15 +36,43 @@ constexpr int TS_TOKW = TS_TOK + TS_HEADS * TS_G;          // + 256 norms
 constexpr int TS_PARAMW = TS_G * TS_DH + TS_G + TS_HEADS + 256;  // dWs | dbs | dT | colsum(dP)
 constexpr int TS_NT = 256;
 
+// Tile prefetch: 16-byte cp.async copies into the padded shared-memory tile (rows past the chunk end are zero-filled), so
+// the next tile's global loads are in flight while the current tile is computed.  Under the CPU emulator (tests only)
+// the same call is a plain copy and commit / wait are no-ops: the double-buffer logic is identical.
+#if defined(FVGN_EMU) || defined(TS_NO_ASYNC)
+#define TS_ASYNC 0
+#else
+#define TS_ASYNC 1
+#include <cuda_pipeline.h>
+#endif
+
 template <int W, int RS>
-__device__ __forceinline__ void ts_load_tile(float* s, const float* __restrict__ g, int64_t ld, int64_t row0, int64_t r1) {
+__device__ __forceinline__ void ts_prefetch_tile(float* s, const float* __restrict__ g, int64_t ld, int64_t row0, int64_t r1) {
   constexpr int V = W / 4;
   for (int i = threadIdx.x; i < TS_TILE * V; i += TS_NT) {
     const int r = i / V, c4 = i % V;
-    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (row0 + r < r1) v = ld4(g + (size_t)(row0 + r) * ld + c4 * 4);
-    st4(s + r * RS + c4 * 4, v);
+    float* dst = s + r * RS + c4 * 4;
+    if (row0 + r < r1) {
+      const float* src = g + (size_t)(row0 + r) * ld + c4 * 4;
+#if TS_ASYNC
+      __pipeline_memcpy_async(dst, src, 16);
+#else
+      st4(dst, ld4(src));
+#endif
+    } else {
+      st4(dst, make_float4(0.f, 0.f, 0.f, 0.f));
+    }
   }
+}
+__device__ __forceinline__ void ts_prefetch_commit() {
+#if TS_ASYNC
+  __pipeline_commit();
+#endif
+}
+__device__ __forceinline__ void ts_prefetch_wait() {
+#if TS_ASYNC
+  __pipeline_wait_prior(0);
+#endif
 }
 
 template <int W, int RS>
@@ -68,31 +96,40 @@ __device__ __forceinline__ void st16(float* dst, const float* src) {
   for (int q = 0; q < 4; ++q) st4(dst + q * 4, make_float4(src[q * 4], src[q * 4 + 1], src[q * 4 + 2], src[q * 4 + 3]));
 }
 
-// logits of one (node, head): l[g] = bs[g] + sum_c xm[c] Ws[g,c]   (in_project_slice, GraphTransolver.py:60)
-__device__ __forceinline__ void ts_logits(float* l, const float* xm, const float* Wss, const float* bss) {
+// 16-term dot product + c as four independent chains (columns k, k+4, k+8, k+12 per chain)
+__device__ __forceinline__ float dot16(const float* x, const float* w, float c) {
+  float p0 = c, p1 = 0.f, p2 = 0.f, p3 = 0.f;
 #pragma unroll
-  for (int g = 0; g < TS_G; ++g) {
-    float w[16];
-    ld16(w, Wss + g * 16);
-    float a = bss[g];
-#pragma unroll
-    for (int c = 0; c < 16; ++c) a += xm[c] * w[c];
-    l[g] = a;
+  for (int q = 0; q < 4; ++q) {
+    p0 += x[q * 4 + 0] * w[q * 4 + 0];
+    p1 += x[q * 4 + 1] * w[q * 4 + 1];
+    p2 += x[q * 4 + 2] * w[q * 4 + 2];
+    p3 += x[q * 4 + 3] * w[q * 4 + 3];
   }
+  return (p0 + p1) + (p2 + p3);
 }
 
 // ----------------------------------------------------------------------------------------------------------------
 // FROM_P : P[N,256] = [fx_mid | x_mid] -> sw[N,256] (written) and partial[chunk] = (sum_n sw (x) fx_mid | sum_n sw)
 // !FROM_P: sw[N,256] (read), V[N,128]  ->                  partial[chunk] = (sum_n sw (x) V      | sum_n sw)
 template <bool FROM_P>
-__global__ void __launch_bounds__(TS_NT) ts_slice_kernel(const float* __restrict__ P, int64_t ldp, float* sw,
-                                                         const float* __restrict__ Ws, const float* __restrict__ bs,
-                                                         const float* __restrict__ temp, const int32_t* __restrict__ chunks,
-                                                         float* __restrict__ partial) {
+struct SliceSmem {
+  static constexpr int VRS = FROM_P ? TS_RS : TS_RS1;         // row stride of the value tile
+  static constexpr int VT = TS_TILE * VRS;                     // floats of one value tile
+  static constexpr int ST = TS_TILE * TS_RS;                   // floats of one sw tile
+  static constexpr int NSW = FROM_P ? 1 : 2;                   // sw tile: produced in place (1) or prefetched (2 buffers)
+  static constexpr size_t bytes = sizeof(float) * (2 * VT + NSW * ST + TS_G * TS_DH + TS_G);
+};
+
+template <bool FROM_P>
+__global__ void __launch_bounds__(TS_NT) ts_slice_kernel(const float* __restrict__ P, float* sw, const float* __restrict__ Ws,
+                                                         const float* __restrict__ bs, const float* __restrict__ temp,
+                                                         const int32_t* __restrict__ chunks, float* __restrict__ partial) {
+  using L = SliceSmem<FROM_P>;
   FVGN_DYN_SMEM(smem);
-  float* Ps = reinterpret_cast<float*>(smem);  // [32][260]  (FROM_P: fx|xm ; else V in the first 128 columns)
-  float* sws = Ps + TS_TILE * TS_RS;           // [32][260]
-  float* Wss = sws + TS_TILE * TS_RS;          // [32][16]
+  float* Vb = reinterpret_cast<float*>(smem);  // 2 x [32][VRS]  (FROM_P: fx|xm ; else the value tile V)
+  float* Sb = Vb + 2 * L::VT;                  // NSW x [32][260]
+  float* Wss = Sb + L::NSW * L::ST;            // [32][16]
   float* bss = Wss + TS_G * TS_DH;             // [32]
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int64_t r0 = chunks[blockIdx.x * 3 + 1], r1 = chunks[blockIdx.x * 3 + 2];
@@ -106,25 +143,52 @@ __global__ void __launch_bounds__(TS_NT) ts_slice_kernel(const float* __restrict
 #pragma unroll
   for (int d = 0; d < 16; ++d) acc[d] = 0.f;
   float nrm = 0.f;
-  for (int64_t row0 = r0; row0 < r1; row0 += TS_TILE) {
+  if (r0 < r1) {
     if (FROM_P) {
-      ts_load_tile<256, TS_RS>(Ps, P, ldp, row0, r1);
+      ts_prefetch_tile<256, TS_RS>(Vb, P, 256, r0, r1);
     } else {
-      ts_load_tile<128, TS_RS>(Ps, P, ldp, row0, r1);
-      ts_load_tile<256, TS_RS>(sws, sw, 256, row0, r1);
+      ts_prefetch_tile<128, TS_RS1>(Vb, P, 128, r0, r1);
+      ts_prefetch_tile<256, TS_RS>(Sb, sw, 256, r0, r1);
     }
-    __syncthreads();
+  }
+  ts_prefetch_commit();
+  int buf = 0;
+  for (int64_t row0 = r0; row0 < r1; row0 += TS_TILE, buf ^= 1) {
+    ts_prefetch_wait();
+    __syncthreads();  // tile `buf` has landed; every thread is done with the previous tile (its buffers may be refilled)
+    if (row0 + TS_TILE < r1) {
+      if (FROM_P) {
+        ts_prefetch_tile<256, TS_RS>(Vb + (buf ^ 1) * L::VT, P, 256, row0 + TS_TILE, r1);
+      } else {
+        ts_prefetch_tile<128, TS_RS1>(Vb + (buf ^ 1) * L::VT, P, 128, row0 + TS_TILE, r1);
+        ts_prefetch_tile<256, TS_RS>(Sb + (buf ^ 1) * L::ST, sw, 256, row0 + TS_TILE, r1);
+      }
+    }
+    ts_prefetch_commit();
+    const float* Vs = Vb + buf * L::VT;
+    float* sws = FROM_P ? Sb : Sb + buf * L::ST;
     if (FROM_P) {
       // thread = (head = warp, node = lane)
       float xm[16], l[TS_G];
-      ld16(xm, Ps + lane * TS_RS + 128 + warp * 16);
-      ts_logits(l, xm, Wss, bss);
+      ld16(xm, Vs + lane * TS_RS + 128 + warp * 16);
+#pragma unroll
+      for (int g = 0; g < TS_G; ++g) {  // in_project_slice (GraphTransolver.py:60)
+        float w[16];
+        ld16(w, Wss + g * 16);
+        l[g] = dot16(xm, w, bss[g]);
+      }
       float m = -INFINITY;
 #pragma unroll
       for (int g = 0; g < TS_G; ++g) { l[g] = l[g] / T; m = fmaxf(m, l[g]); }
-      float s = 0.f;
+      float s0 = 0.f, s1 = 0.f;
 #pragma unroll
-      for (int g = 0; g < TS_G; ++g) { l[g] = expf(l[g] - m); s += l[g]; }
+      for (int g = 0; g < TS_G; g += 2) {
+        l[g] = expf(l[g] - m);
+        l[g + 1] = expf(l[g + 1] - m);
+        s0 += l[g];
+        s1 += l[g + 1];
+      }
+      const float s = s0 + s1;
       const bool valid = row0 + lane < r1;
 #pragma unroll
       for (int g = 0; g < TS_G; ++g) l[g] = valid ? l[g] / s : 0.f;
@@ -137,14 +201,13 @@ __global__ void __launch_bounds__(TS_NT) ts_slice_kernel(const float* __restrict
     // thread = (head = warp, slice = lane): token sums in row order
 #pragma unroll 4
     for (int n = 0; n < TS_TILE; ++n) {
-      const float s = sws[n * TS_RS + warp * TS_G + lane];
+      const float sv = sws[n * TS_RS + warp * TS_G + lane];
       float f[16];
-      ld16(f, Ps + n * TS_RS + warp * 16);
+      ld16(f, Vs + n * L::VRS + warp * 16);
 #pragma unroll
-      for (int d = 0; d < 16; ++d) acc[d] += s * f[d];
-      nrm += s;
+      for (int d = 0; d < 16; ++d) acc[d] += sv * f[d];
+      nrm += sv;
     }
-    __syncthreads();
   }
   float* out = partial + (size_t)blockIdx.x * TS_TOKW;
   st16(out + (warp * TS_G + lane) * 16, acc);
@@ -157,28 +220,37 @@ __global__ void __launch_bounds__(TS_NT) ts_deslice_kernel(const float* __restri
                                                            int64_t tok_ld, int tok_mod, const int32_t* __restrict__ chunks,
                                                            float* __restrict__ out) {
   FVGN_DYN_SMEM(smem);
-  float* sws = reinterpret_cast<float*>(smem);  // [32][260]
-  float* Ts = sws + TS_TILE * TS_RS;            // [8][32][16]
+  float* Sb = reinterpret_cast<float*>(smem);   // 2 x [32][260]
+  float* Ts = Sb + 2 * TS_TILE * TS_RS;         // [8][32][16]
   float* outs = Ts + TS_TOK;                    // [32][132]
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int seg = chunks[blockIdx.x * 3 + 0];
   const int64_t r0 = chunks[blockIdx.x * 3 + 1], r1 = chunks[blockIdx.x * 3 + 2];
   const float* tp = tok + (size_t)(seg % tok_mod) * tok_ld;
   for (int i = tid; i < TS_TOK / 4; i += TS_NT) st4(Ts + i * 4, ld4(tp + i * 4));
-  for (int64_t row0 = r0; row0 < r1; row0 += TS_TILE) {
-    ts_load_tile<256, TS_RS>(sws, sw, 256, row0, r1);
+  if (r0 < r1) ts_prefetch_tile<256, TS_RS>(Sb, sw, 256, r0, r1);
+  ts_prefetch_commit();
+  int buf = 0;
+  for (int64_t row0 = r0; row0 < r1; row0 += TS_TILE, buf ^= 1) {
+    ts_prefetch_wait();
     __syncthreads();
-    float s[TS_G], o[16];
-    ld16(s, sws + lane * TS_RS + warp * TS_G);
-    ld16(s + 16, sws + lane * TS_RS + warp * TS_G + 16);
+    if (row0 + TS_TILE < r1) ts_prefetch_tile<256, TS_RS>(Sb + (buf ^ 1) * TS_TILE * TS_RS, sw, 256, row0 + TS_TILE, r1);
+    ts_prefetch_commit();
+    const float* srow = Sb + buf * TS_TILE * TS_RS + lane * TS_RS + warp * TS_G;
+    float o[16];
 #pragma unroll
     for (int d = 0; d < 16; ++d) o[d] = 0.f;
 #pragma unroll
-    for (int g = 0; g < TS_G; ++g) {
-      float t[16];
-      ld16(t, Ts + (warp * TS_G + g) * 16);
+    for (int g4 = 0; g4 < TS_G / 4; ++g4) {
+      const float4 s4 = ld4(srow + g4 * 4);
+      const float sv[4] = {s4.x, s4.y, s4.z, s4.w};
 #pragma unroll
-      for (int d = 0; d < 16; ++d) o[d] += s[g] * t[d];
+      for (int j = 0; j < 4; ++j) {
+        float t[16];
+        ld16(t, Ts + (warp * TS_G + g4 * 4 + j) * 16);
+#pragma unroll
+        for (int d = 0; d < 16; ++d) o[d] += sv[j] * t[d];
+      }
     }
     st16(outs + lane * TS_RS1 + warp * 16, o);
     __syncthreads();
@@ -190,6 +262,8 @@ __global__ void __launch_bounds__(TS_NT) ts_deslice_kernel(const float* __restri
 // Backward of slice + de-slice for one chunk.  Inputs: P = [fx|xm], sw, dox = d out_x, tok_out (forward tokens after
 // attention), d_tok = [d slice_token numerators | d slice_norm] (zero for chunks of graphs this rank does not own).
 // Outputs: dP[N,256] = [d fx | d xm] and partial[chunk] = (dWs[32,16] | dbs[32] | d graph_temperature[8] | colsum dP[256]).
+constexpr int TS_BSET = 2 * TS_TILE * TS_RS + TS_TILE * TS_RS1;  // floats of one input tile set: P | sw | d out_x
+
 __global__ void __launch_bounds__(TS_NT, 1) ts_slice_bwd_kernel(const float* __restrict__ P, const float* __restrict__ sw,
                                                                 const float* __restrict__ dox, const float* __restrict__ tok_out,
                                                                 const float* __restrict__ d_tok, int tok_mod,
@@ -197,10 +271,8 @@ __global__ void __launch_bounds__(TS_NT, 1) ts_slice_bwd_kernel(const float* __r
                                                                 const float* __restrict__ temp, const int32_t* __restrict__ chunks,
                                                                 float* __restrict__ dP, float* __restrict__ partial) {
   FVGN_DYN_SMEM(smem);
-  float* Ps = reinterpret_cast<float*>(smem);  // [32][260]
-  float* sws = Ps + TS_TILE * TS_RS;           // [32][260]
-  float* dxs = sws + TS_TILE * TS_RS;          // [32][132]
-  float* OTs = dxs + TS_TILE * TS_RS1;         // [8][32][16]
+  float* Bb = reinterpret_cast<float*>(smem);  // 2 x { Ps [32][260] | sws [32][260] | dxs [32][132] }
+  float* OTs = Bb + 2 * TS_BSET;               // [8][32][16]
   float* DNs = OTs + TS_TOK;                   // [8][32][16]
   float* dns = DNs + TS_TOK;                   // [8][32]
   float* Wss = dns + TS_HEADS * TS_G;          // [32][16]
@@ -223,64 +295,82 @@ __global__ void __launch_bounds__(TS_NT, 1) ts_slice_bwd_kernel(const float* __r
 #pragma unroll
   for (int c = 0; c < 16; ++c) accW[c] = 0.f;
   float accb = 0.f, accT = 0.f, acccol = 0.f;
-  for (int64_t row0 = r0; row0 < r1; row0 += TS_TILE) {
-    ts_load_tile<256, TS_RS>(Ps, P, 256, row0, r1);
-    ts_load_tile<256, TS_RS>(sws, sw, 256, row0, r1);
-    ts_load_tile<128, TS_RS1>(dxs, dox, 128, row0, r1);
-    __syncthreads();
-    {  // thread = (head = warp, node = lane)
-      float s[TS_G], ds[TS_G], a[16], b[16];
+  if (r0 < r1) {
+    ts_prefetch_tile<256, TS_RS>(Bb, P, 256, r0, r1);
+    ts_prefetch_tile<256, TS_RS>(Bb + TS_TILE * TS_RS, sw, 256, r0, r1);
+    ts_prefetch_tile<128, TS_RS1>(Bb + 2 * TS_TILE * TS_RS, dox, 128, r0, r1);
+  }
+  ts_prefetch_commit();
+  int buf = 0;
+  for (int64_t row0 = r0; row0 < r1; row0 += TS_TILE, buf ^= 1) {
+    ts_prefetch_wait();
+    __syncthreads();  // tile set `buf` has landed; every thread is done with the previous tile set
+    if (row0 + TS_TILE < r1) {
+      float* nb = Bb + (buf ^ 1) * TS_BSET;
+      ts_prefetch_tile<256, TS_RS>(nb, P, 256, row0 + TS_TILE, r1);
+      ts_prefetch_tile<256, TS_RS>(nb + TS_TILE * TS_RS, sw, 256, row0 + TS_TILE, r1);
+      ts_prefetch_tile<128, TS_RS1>(nb + 2 * TS_TILE * TS_RS, dox, 128, row0 + TS_TILE, r1);
+    }
+    ts_prefetch_commit();
+    float* Ps = Bb + buf * TS_BSET;
+    float* sws = Ps + TS_TILE * TS_RS;
+    float* dxs = sws + TS_TILE * TS_RS;
+    {  // thread = (head = warp, node = lane); sw stays in the tile (16-B reads), d sw / d logits live in registers
+      float ds[TS_G], a[16], b[16], f[16];
       float* srow = sws + lane * TS_RS + warp * TS_G;
       float* frow = Ps + lane * TS_RS + warp * 16;
       float* xrow = dxs + lane * TS_RS1 + warp * 16;
-      ld16(s, srow);
-      ld16(s + 16, srow + 16);
       ld16(a, xrow);  // d out_x
       ld16(b, frow);  // fx_mid
-      float dot = 0.f;
 #pragma unroll
-      for (int g = 0; g < TS_G; ++g) {
-        float o[16], dn[16];
-        ld16(o, OTs + (warp * TS_G + g) * 16);
-        ld16(dn, DNs + (warp * TS_G + g) * 16);
-        float v = dns[warp * TS_G + g];
+      for (int d = 0; d < 16; ++d) f[d] = 0.f;
+      float dot0 = 0.f, dot1 = 0.f;
 #pragma unroll
-        for (int d = 0; d < 16; ++d) v += a[d] * o[d] + b[d] * dn[d];
-        ds[g] = v;
-        dot += s[g] * v;
+      for (int g4 = 0; g4 < TS_G / 4; ++g4) {
+        const float4 s4 = ld4(srow + g4 * 4);
+        const float sv[4] = {s4.x, s4.y, s4.z, s4.w};
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const int g = g4 * 4 + j;
+          float o[16], dn[16];
+          ld16(o, OTs + (warp * TS_G + g) * 16);
+          ld16(dn, DNs + (warp * TS_G + g) * 16);
+          // d sw[g] = d_norm[g] + d out_x . tok_out[g] + fx . d_num[g]
+          const float v = dot16(a, o, dns[warp * TS_G + g]) + dot16(b, dn, 0.f);
+#pragma unroll
+          for (int d = 0; d < 16; ++d) f[d] += sv[j] * dn[d];  // d fx_mid[d] = sum_g sw[g] d_num[g,d]
+          ds[g] = v;
+          if (j & 1) dot1 += sv[j] * v; else dot0 += sv[j] * v;
+        }
       }
-      // d fx_mid[d] = sum_g sw[g] d_num[g,d]   (overwrites fx in the tile)
-#pragma unroll
-      for (int d = 0; d < 16; ++d) a[d] = 0.f;
-#pragma unroll
-      for (int g = 0; g < TS_G; ++g) {
-        float dn[16];
-        ld16(dn, DNs + (warp * TS_G + g) * 16);
-#pragma unroll
-        for (int d = 0; d < 16; ++d) a[d] += s[g] * dn[d];
-      }
-      st16(frow, a);
+      const float dot = dot0 + dot1;
+      st16(frow, f);  // overwrites fx in the tile
       // softmax backward (scaled logits z = l / T), then through /T and in_project_slice
       ld16(b, Ps + lane * TS_RS + 128 + warp * 16);  // x_mid
 #pragma unroll
       for (int c = 0; c < 16; ++c) a[c] = 0.f;
+      float t0 = 0.f, t1 = 0.f;
 #pragma unroll
-      for (int g = 0; g < TS_G; ++g) {
-        float w[16];
-        ld16(w, Wss + g * 16);
-        float lg = bss[g];
+      for (int g4 = 0; g4 < TS_G / 4; ++g4) {
+        const float4 s4 = ld4(srow + g4 * 4);
+        const float sv[4] = {s4.x, s4.y, s4.z, s4.w};
+        float dl[4];
 #pragma unroll
-        for (int c = 0; c < 16; ++c) lg += b[c] * w[c];
-        const float dz = s[g] * (ds[g] - dot);
-        accT += dz * lg;
-        const float dl = dz / T;
-        ds[g] = dl;
+        for (int j = 0; j < 4; ++j) {
+          const int g = g4 * 4 + j;
+          float w[16];
+          ld16(w, Wss + g * 16);
+          const float lg = dot16(b, w, bss[g]);
+          const float dz = sv[j] * (ds[g] - dot);
+          if (j & 1) t1 += dz * lg; else t0 += dz * lg;
+          dl[j] = dz / T;
 #pragma unroll
-        for (int c = 0; c < 16; ++c) a[c] += dl * w[c];
+          for (int c = 0; c < 16; ++c) a[c] += dl[j] * w[c];
+        }
+        st4(srow + g4 * 4, make_float4(dl[0], dl[1], dl[2], dl[3]));  // d logits (pre-temperature) for the dWs sum below
       }
-      st16(xrow, a);      // d x_mid
-      st16(srow, ds);     // d logits (pre-temperature) for the dWs sum below
-      st16(srow + 16, ds + 16);
+      accT += t0 + t1;
+      st16(xrow, a);  // d x_mid
     }
     __syncthreads();
     // thread = (head = warp, slice = lane): dWs[g,c] += dl[n,h,g] x_mid[n,h,c], dbs[g] += dl
@@ -301,13 +391,20 @@ __global__ void __launch_bounds__(TS_NT, 1) ts_slice_bwd_kernel(const float* __r
         st4(dP + (size_t)(row0 + r) * 256 + c4 * 4, v);
       }
     }
+    {
+      float c0 = 0.f, c1 = 0.f;
 #pragma unroll 4
-    for (int r = 0; r < TS_TILE; ++r) acccol += tid < 128 ? Ps[r * TS_RS + tid] : dxs[r * TS_RS1 + tid - 128];
-    __syncthreads();
+      for (int r = 0; r < TS_TILE; r += 2) {
+        c0 += tid < 128 ? Ps[r * TS_RS + tid] : dxs[r * TS_RS1 + tid - 128];
+        c1 += tid < 128 ? Ps[(r + 1) * TS_RS + tid] : dxs[(r + 1) * TS_RS1 + tid - 128];
+      }
+      acccol += c0 + c1;
+    }
   }
+  __syncthreads();
   // cross-warp (head) sums in fixed order
-  float* red = sws;        // [8][32][16]
-  float* red2 = Ps;        // [8][32] dbs partials, then [8][32] dT partials
+  float* red = Bb + TS_TILE * TS_RS;  // [8][32][16]   (sw tile of set 0)
+  float* red2 = Bb;                   // [8][32] dbs partials, then [8][32] dT partials
   st16(red + (warp * TS_G + lane) * 16, accW);
   red2[warp * 32 + lane] = accb;
   red2[256 + warp * 32 + lane] = accT;
@@ -379,16 +476,16 @@ __global__ void __launch_bounds__(TS_NT) ts_res_ln_fwd_kernel(const float* __res
   }
 }
 
-// d_y = LayerNorm-backward(dz) + d_y_in ; partial[cta] = (dgamma[128] | dbeta[128] | colsum d_y[128])
+// d_y = LayerNorm-backward(dz) + d_y_in ; partial[cta] = (dgamma[128] | dbeta[128] | colsum d_y[128] | colsum d_y_in[128])
 __global__ void __launch_bounds__(TS_NT) ts_res_ln_bwd_kernel(const float* __restrict__ dz, const float* __restrict__ y,
                                                               const float* __restrict__ stats, const float* __restrict__ gamma,
                                                               const float* __restrict__ d_y_in, float* __restrict__ d_y,
                                                               float* __restrict__ partial, int64_t n) {
   __shared__ __align__(16) float red[8][4][32];
-  __shared__ float redc[8][384];
+  __shared__ float redc[8][512];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const float4 g4 = ld4(gamma + lane * 4);
-  float4 ag = make_float4(0.f, 0.f, 0.f, 0.f), ab = ag, ac = ag;
+  float4 ag = make_float4(0.f, 0.f, 0.f, 0.f), ab = ag, ac = ag, ai = ag;
   int it = 0;
   for (int64_t row = (int64_t)blockIdx.x * 8 + warp; row < n; row += (int64_t)gridDim.x * 8, ++it) {
     const float mean = stats[row * 2], rstd = stats[row * 2 + 1];
@@ -403,7 +500,11 @@ __global__ void __launch_bounds__(TS_NT) ts_res_ln_bwd_kernel(const float* __res
     const float c1 = ts_sum32(r1) * (1.0f / 128.0f), c2 = ts_sum32(r2) * (1.0f / 128.0f);
     float4 o = make_float4(rstd * (g.x - c1 - yh.x * c2), rstd * (g.y - c1 - yh.y * c2), rstd * (g.z - c1 - yh.z * c2),
                            rstd * (g.w - c1 - yh.w * c2));
-    if (d_y_in) o = add4(o, ld4(d_y_in + row * 128 + lane * 4));
+    if (d_y_in) {
+      const float4 e = ld4(d_y_in + row * 128 + lane * 4);
+      o = add4(o, e);
+      ai = add4(ai, e);
+    }
     st4(d_y + row * 128 + lane * 4, o);
     ag = add4(ag, make_float4(d.x * yh.x, d.y * yh.y, d.z * yh.z, d.w * yh.w));
     ab = add4(ab, d);
@@ -412,12 +513,13 @@ __global__ void __launch_bounds__(TS_NT) ts_res_ln_bwd_kernel(const float* __res
   st4(&redc[warp][lane * 4], ag);
   st4(&redc[warp][128 + lane * 4], ab);
   st4(&redc[warp][256 + lane * 4], ac);
+  st4(&redc[warp][384 + lane * 4], ai);
   __syncthreads();
-  for (int i = threadIdx.x; i < 384; i += TS_NT) {
+  for (int i = threadIdx.x; i < 512; i += TS_NT) {
     float s = 0.f;
 #pragma unroll
     for (int w = 0; w < 8; ++w) s += redc[w][i];
-    partial[(size_t)blockIdx.x * 384 + i] = s;
+    partial[(size_t)blockIdx.x * 512 + i] = s;
   }
 }
 
@@ -430,9 +532,9 @@ __global__ void __launch_bounds__(TS_NT) ts_bias_gelu_fwd_kernel(const float* __
   st4(h + i * 4, make_float4(gelu_exact(v.x + b.x), gelu_exact(v.y + b.y), gelu_exact(v.z + b.z), gelu_exact(v.w + b.w)));
 }
 
-// dhpre = dh * GELU'(hpre + bias) ; partial[cta] = colsum dhpre [256]
-__global__ void __launch_bounds__(TS_NT) ts_bias_gelu_bwd_kernel(const float* __restrict__ dh, const float* __restrict__ hpre,
-                                                                 const float* __restrict__ bias, float* __restrict__ dhpre,
+// dhpre = dh * GELU'(hpre + bias) (dhpre may alias dh) ; partial[cta] = colsum dhpre [256]
+__global__ void __launch_bounds__(TS_NT) ts_bias_gelu_bwd_kernel(const float* dh, const float* __restrict__ hpre,
+                                                                 const float* __restrict__ bias, float* dhpre,
                                                                  float* __restrict__ partial, int64_t n) {
   __shared__ __align__(16) float red[4][256];
   const int c4 = threadIdx.x & 63, rsub = threadIdx.x >> 6;
@@ -467,10 +569,8 @@ __global__ void __launch_bounds__(TS_NT) ts_bias_res_kernel(const float* __restr
 #endif
 }
 
-constexpr size_t kSmemSlice = sizeof(float) * (2 * TS_TILE * TS_RS + TS_G * TS_DH + TS_G);
-constexpr size_t kSmemDeslice = sizeof(float) * (TS_TILE * TS_RS + TS_TOK + TS_TILE * TS_RS1);
-constexpr size_t kSmemBwd =
-    sizeof(float) * (2 * TS_TILE * TS_RS + TS_TILE * TS_RS1 + 2 * TS_TOK + TS_HEADS * TS_G + TS_G * TS_DH + TS_G);
+constexpr size_t kSmemDeslice = sizeof(float) * (2 * TS_TILE * TS_RS + TS_TOK + TS_TILE * TS_RS1);
+constexpr size_t kSmemBwd = sizeof(float) * (2 * TS_BSET + 2 * TS_TOK + TS_HEADS * TS_G + TS_G * TS_DH + TS_G);
 
 template <class K>
 int ts_set_smem(K kern, size_t bytes) {
@@ -495,8 +595,8 @@ extern "C" int fvgn_ts_slice_forward(const float* P, const float* Ws, const floa
   if (!P || !Ws || !bs || !temp || !chunks || !sw || !partial) return FVGN_ERR_NULL;
   if (!fvgn_aligned16(P) || !fvgn_aligned16(sw) || !fvgn_aligned16(partial)) return FVGN_ERR_ALIGN;
   auto kern = ts_slice_kernel<true>;
-  if (ts_set_smem(kern, kSmemSlice) != FVGN_OK) return FVGN_ERR_LAUNCH;
-  FVGN_LAUNCH(kern, (unsigned)nchunks, TS_NT, kSmemSlice, stream, P, (int64_t)256, sw, Ws, bs, temp, chunks, partial);
+  if (ts_set_smem(kern, SliceSmem<true>::bytes) != FVGN_OK) return FVGN_ERR_LAUNCH;
+  FVGN_LAUNCH(kern, (unsigned)nchunks, TS_NT, SliceSmem<true>::bytes, stream, P, sw, Ws, bs, temp, chunks, partial);
   FVGN_CHECK_LAUNCH();
   return FVGN_OK;
 }
@@ -507,9 +607,9 @@ extern "C" int fvgn_ts_accumulate(const float* sw, const float* V, const int32_t
   if (!sw || !V || !chunks || !partial) return FVGN_ERR_NULL;
   if (!fvgn_aligned16(V) || !fvgn_aligned16(sw) || !fvgn_aligned16(partial)) return FVGN_ERR_ALIGN;
   auto kern = ts_slice_kernel<false>;
-  if (ts_set_smem(kern, kSmemSlice) != FVGN_OK) return FVGN_ERR_LAUNCH;
-  FVGN_LAUNCH(kern, (unsigned)nchunks, TS_NT, kSmemSlice, stream, V, (int64_t)128, const_cast<float*>(sw),
-              (const float*)nullptr, (const float*)nullptr, (const float*)nullptr, chunks, partial);
+  if (ts_set_smem(kern, SliceSmem<false>::bytes) != FVGN_OK) return FVGN_ERR_LAUNCH;
+  FVGN_LAUNCH(kern, (unsigned)nchunks, TS_NT, SliceSmem<false>::bytes, stream, V, const_cast<float*>(sw), (const float*)nullptr,
+              (const float*)nullptr, (const float*)nullptr, chunks, partial);
   FVGN_CHECK_LAUNCH();
   return FVGN_OK;
 }

@@ -604,7 +604,7 @@ class TsPlan:
         counts = torch.bincount(batch.to(torch.int64), minlength=nseg).cpu().tolist()
         if n > 1 and bool((batch[1:] < batch[:-1]).any()):
             raise RuntimeError("fvgn_b200: Transolver kernels need the batch vector sorted by graph (Load_mesh batches are)")
-        rows_per_chunk = max(32, min(1024, -(-n // (296 * 32)) * 32))
+        rows_per_chunk = max(32, min(4096, -(-n // (296 * 32)) * 32))
         rows, ptr, start = [], [0], 0
         for seg, cnt in enumerate(counts):
             r = start
@@ -644,6 +644,17 @@ def _combine(partial, width, ptr, nseg):
 
 def _row_partials(n):
     return int(_lib.load().fvgn_ts_row_partials(n))
+
+
+_PTR01 = {}
+
+
+def _ptr01(npart, device):
+    """chunk_ptr [0, npart] of a single-segment combine (cached: no host-to-device copy inside a captured step)."""
+    key = (npart, str(device))
+    if key not in _PTR01:
+        _PTR01[key] = torch.tensor([0, npart], dtype=torch.int32, device=device)
+    return _PTR01[key]
 
 
 def _token_attention(rec, wq, wk, wv, scale):
@@ -727,37 +738,55 @@ class SliceAttentionFn(torch.autograd.Function):
                 None, None, None)
 
 
-class ResidualLayerNormFn(torch.autograd.Function):
-    """(a, bias, res) -> y = a + bias + res, z = LayerNorm(y)   (to_out bias + residual + ln_2, GraphTransolver.py:163-169)."""
+class BlockTailFn(torch.autograd.Function):
+    """Second half of Transolver_block.forward (GraphTransolver.py:163-169) as one autograd node:
+    y = a + to_out.bias + fx ; z = ln_2(y) ; h = GELU(z W1^T + b1) ; out = h W2^T + b2 + y  (+ bf16 shadow of out).
+    The two GEMMs are library calls; bias / residual / LayerNorm / GELU and every bias or LayerNorm gradient (column
+    sums as deterministic per-CTA partials) are the ts_* kernels."""
 
     @staticmethod
-    def forward(ctx, a, bias, res, gamma, beta):
+    def forward(ctx, a, bo, res, gamma, beta, w1, b1, w2, b2, want_shadow):
         a, res = _c(a), _c(res)
         n = a.shape[0]
+        st = _lib.stream_ptr(a.device)
         y, z, stats = _empty((n, 128), a), _empty((n, 128), a), _empty((n, 2), a)
-        _lib.call("fvgn_ts_residual_ln_forward", fptr(a), fptr(_c(bias.detach())), fptr(res), fptr(_c(gamma.detach())),
-                  fptr(_c(beta.detach())), fptr(y), fptr(z), fptr(stats), n, _lib.stream_ptr(a.device))
+        b1c = _c(b1.detach())
+        _lib.call("fvgn_ts_residual_ln_forward", fptr(a), fptr(_c(bo.detach())), fptr(res), fptr(_c(gamma.detach())),
+                  fptr(_c(beta.detach())), fptr(y), fptr(z), fptr(stats), n, st)
+        hpre = z @ w1.t()
+        h = _empty((n, 256), a)
+        _lib.call("fvgn_ts_bias_gelu_forward", fptr(hpre), fptr(b1c), fptr(h), n, st)
+        o = h @ w2.t()
+        out = _empty((n, 128), a)
+        outh = torch.empty((n, 128), dtype=BF16, device=a.device) if want_shadow else None
+        _lib.call("fvgn_ts_bias_residual", fptr(o), fptr(_c(b2.detach())), fptr(y), fptr(out), hptr(outh, True), n, st)
         ctx.set_materialize_grads(False)
-        ctx.save_for_backward(y, stats, gamma)
-        return y, z
+        if outh is not None:
+            ctx.mark_non_differentiable(outh)
+        ctx.save_for_backward(y, stats, z, hpre, h, gamma, w1, b1c, w2)
+        return out, outh
 
     @staticmethod
-    def backward(ctx, d_y_in, d_z):
-        y, stats, gamma = ctx.saved_tensors
+    def backward(ctx, d_out, _dh=None):
+        y, stats, z, hpre, h, gamma, w1, b1c, w2 = ctx.saved_tensors
         n = y.shape[0]
-        if d_z is None:
-            d_z = torch.zeros_like(y)
+        st = _lib.stream_ptr(y.device)
+        d_out = _c(d_out)
         npart = _row_partials(n)
+        ptr = _ptr01(npart, y.device)
+        d_w2 = d_out.t() @ h
+        d_h = d_out @ w2
+        part = _empty((npart, 256), y)
+        _lib.call("fvgn_ts_bias_gelu_backward", fptr(d_h), fptr(hpre), fptr(b1c), fptr(d_h), fptr(part), n, st)  # in place
+        d_b1 = _combine(part, 256, ptr, 1).reshape(-1) if n > 0 else torch.zeros(256, device=y.device)
+        d_w1 = d_h.t() @ z
+        d_z = d_h @ w1
         d_y = _empty((n, 128), y)
-        part = _empty((npart, 384), y)
-        _lib.call("fvgn_ts_residual_ln_backward", fptr(_c(d_z)), fptr(y), fptr(stats), fptr(_c(gamma.detach())),
-                  fptr(_c(d_y_in) if d_y_in is not None else None, True), fptr(d_y), fptr(part), n, _lib.stream_ptr(y.device))
-        if n > 0:
-            ptr = torch.tensor([0, npart], dtype=torch.int32, device=y.device)
-            s = _combine(part, 384, ptr, 1).reshape(-1)
-        else:
-            s = torch.zeros(384, device=y.device)
-        return d_y, s[256:384], d_y, s[0:128], s[128:256]
+        part = _empty((npart, 512), y)
+        _lib.call("fvgn_ts_residual_ln_backward", fptr(d_z), fptr(y), fptr(stats), fptr(_c(gamma.detach())), fptr(d_out),
+                  fptr(d_y), fptr(part), n, st)
+        s = _combine(part, 512, ptr, 1).reshape(-1) if n > 0 else torch.zeros(512, device=y.device)
+        return d_y, s[256:384], d_y, s[0:128], s[128:256], d_w1, d_b1, d_w2, s[384:512], None
 
 
 class BiasGeluFn(torch.autograd.Function):
@@ -782,29 +811,7 @@ class BiasGeluFn(torch.autograd.Function):
         _lib.call("fvgn_ts_bias_gelu_backward", fptr(_c(d_h)), fptr(hpre), fptr(_c(bias.detach())), fptr(d_hpre), fptr(part), n,
                   _lib.stream_ptr(hpre.device))
         if n > 0:
-            ptr = torch.tensor([0, npart], dtype=torch.int32, device=hpre.device)
-            d_b = _combine(part, 256, ptr, 1).reshape(-1)
+            d_b = _combine(part, 256, _ptr01(npart, hpre.device), 1).reshape(-1)
         else:
             d_b = torch.zeros(256, device=hpre.device)
         return d_hpre, d_b
-
-
-class BiasResidualFn(torch.autograd.Function):
-    """out = a + bias + res (+ the bf16 shadow of out for the next GnBlock / decoder in bf16 mode)."""
-
-    @staticmethod
-    def forward(ctx, a, bias, res, want_shadow):
-        a, res = _c(a), _c(res)
-        n = a.shape[0]
-        out = _empty((n, 128), a)
-        outh = torch.empty((n, 128), dtype=BF16, device=a.device) if want_shadow else None
-        _lib.call("fvgn_ts_bias_residual", fptr(a), fptr(_c(bias.detach())), fptr(res), fptr(out), hptr(outh, True), n,
-                  _lib.stream_ptr(a.device))
-        ctx.set_materialize_grads(False)
-        if outh is not None:
-            ctx.mark_non_differentiable(outh)
-        return out, outh
-
-    @staticmethod
-    def backward(ctx, d_out, _dh=None):
-        return d_out, d_out.sum(0), d_out, None

@@ -217,7 +217,8 @@ int fvgn_ts_slice_backward(const float* P, const float* sw, const float* d_out, 
 /* y = a + bias + res ; z = LayerNorm(y) (to_out bias + residual + ln_2, :163-169); stats[N,2] = (mean, rstd) */
 int fvgn_ts_residual_ln_forward(const float* a, const float* bias, const float* res, const float* gamma, const float* beta,
                                 float* y, float* z, float* stats, int64_t n, void* stream);
-/* d_y = LayerNorm-backward(dz) + d_y_in (nullable) ; partial[fvgn_ts_row_partials(n),384] = dgamma | dbeta | colsum d_y */
+/* d_y = LayerNorm-backward(dz) + d_y_in (nullable) ; partial[fvgn_ts_row_partials(n),512] = dgamma | dbeta | colsum d_y |
+ * colsum d_y_in */
 int fvgn_ts_residual_ln_backward(const float* dz, const float* y, const float* stats, const float* gamma, const float* d_y_in,
                                  float* d_y, float* partial, int64_t n, void* stream);
 /* h[N,256] = GELU(hpre + bias) (MLP.linear_pre, :105,124) ; backward: dhpre = dh * GELU'(hpre + bias),
