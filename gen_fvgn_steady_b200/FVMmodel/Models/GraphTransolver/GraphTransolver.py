@@ -78,14 +78,24 @@ class Transolver_block(nn.Module):
         self.mlp = MLP(hidden_dim, hidden_dim * mlp_ratio, hidden_dim, n_layers=0, res=False, act=act)
         self.last_shadow = None
 
-    def forward(self, fx, batch, in_layernorm=False, graph_ptr=None, halo=None):
-        """GraphTransolver.py:163-169.  In bf16 mode the last kernel also emits the bf16 shadow of the result
-        (`self.last_shadow = (out, shadow)`) for the GnBlock / decoder that consumes it."""
-        x_in = self.ln_1(fx) if in_layernorm else fx
-        a = self.Attn.attend(x_in, batch, halo)
+    def forward(self, fx, batch, in_layernorm=False, graph_ptr=None, halo=None, embedding=None):
+        """GraphTransolver.py:163-169.  `embedding` (optional) is added to fx first (the TransFVGN processors pass
+        latent.x and the node embedding separately so that the sum and its gradient stay inside the fused op).
+        In bf16 mode the last kernel also emits the bf16 shadow of the result (`self.last_shadow = (out, shadow)`) for
+        the GnBlock / decoder that consumes it."""
         want_shadow = (getattr(self, "precision", None) or ops.default_precision()) == "bf16"
-        out, outh = ops.BlockTailFn.apply(a, self.Attn.to_out[0].bias, fx, self.ln_2.weight, self.ln_2.bias,
-                                          self.mlp.linear_pre[0].weight, self.mlp.linear_pre[0].bias,
-                                          self.mlp.linear_post.weight, self.mlp.linear_post.bias, want_shadow)
+        A, m = self.Attn, self.mlp
+        tail = (A.to_out[0].bias, self.ln_2.weight, self.ln_2.bias, m.linear_pre[0].weight, m.linear_pre[0].bias,
+                m.linear_post.weight, m.linear_post.bias)
+        if in_layernorm:   # original-Transolver variant: attention on ln_1(fx); not used by TransFVGN_v1/v2
+            if embedding is not None:
+                fx = fx + embedding
+            a = A.attend(self.ln_1(fx), batch, halo)
+            out, outh = ops.BlockTailFn.apply(a, tail[0], fx, *tail[1:], want_shadow)
+        else:
+            out, outh = ops.TransolverBlockFn.apply(
+                fx, embedding, A.in_project_fx.weight, A.in_project_fx.bias, A.in_project_x.weight, A.in_project_x.bias,
+                A.in_project_slice.weight, A.in_project_slice.bias, A.graph_temperature, A.to_q.weight, A.to_k.weight,
+                A.to_v.weight, A.to_out[0].weight, *tail, A.scale, ops.TsPlan.of(batch, halo), halo, want_shadow)
         self.last_shadow = (out, outh) if want_shadow else None
         return out

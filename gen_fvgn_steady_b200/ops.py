@@ -669,6 +669,108 @@ def _token_attention(rec, wq, wk, wv, scale):
     return torch.matmul(attn, v).reshape(nb, TS_TOK)
 
 
+def _attn_forward(x, wfx, bfx, wx, bx, ws, bs, temp, wq, wk, wv, wo, scale, tsp, halo):
+    """-> (a = to_out.weight @ deslice(attention(slice(x))), tensors to keep for _attn_backward)."""
+    n = x.shape[0]
+    st = _lib.stream_ptr(x.device)
+    wcat = torch.cat([wfx, wx], 0)
+    P = torch.addmm(torch.cat([bfx, bx], 0), x, wcat.t())                  # [N,256] = fx_mid | x_mid
+    ws_c, bs_c, temp_c = _c(ws.detach()), _c(bs.detach()), _c(temp.detach().reshape(-1))
+    sw = _empty((n, 256), x)
+    part = _empty((max(tsp.n_chunks, 1), _lib.FVGN_TS_TOKW), x)
+    _lib.call("fvgn_ts_slice_forward", fptr(P), fptr(ws_c), fptr(bs_c), fptr(temp_c), iptr(tsp.chunks), tsp.n_chunks,
+              fptr(sw), fptr(part), st)
+    rec = _combine(part, _lib.FVGN_TS_TOKW, tsp.chunk_ptr, tsp.nseg)[:tsp.nb].contiguous()
+    if halo is not None:   # cell-partition mode: tokens are sums over the rows every rank owns
+        from .parallel import allreduce_sum_
+        rec = allreduce_sum_(rec)
+    tok_out = _c(_token_attention(rec, wq, wk, wv, scale))
+    out_x = _empty((n, 128), x)
+    _lib.call("fvgn_ts_deslice", fptr(sw), fptr(tok_out), TS_TOK, tsp.nb, iptr(tsp.chunks), tsp.n_chunks, fptr(out_x), st)
+    return out_x @ wo.t(), (x, P, sw, rec, tok_out, out_x, wcat, ws_c, bs_c, temp_c, wq, wk, wv, wo)
+
+
+def _attn_backward(saved, d_a, scale, tsp, halo, d_res=None):
+    """-> gradients of (x, wfx, bfx, wx, bx, ws, bs, temp, wq, wk, wv, wo); d_res (optional) is added to d_x inside the
+    last GEMM (the block's residual gradient)."""
+    x, P, sw, rec, tok_out, out_x, wcat, ws_c, bs_c, temp_c, wq, wk, wv, wo = saved
+    n = x.shape[0]
+    st = _lib.stream_ptr(x.device)
+    d_a = _c(d_a)
+    d_wo = d_a.t() @ out_x
+    d_ox = d_a @ wo                                                         # [N,128]
+    part = _empty((max(tsp.n_chunks, 1), _lib.FVGN_TS_TOKW), x)
+    _lib.call("fvgn_ts_accumulate", fptr(sw), fptr(d_ox), iptr(tsp.chunks), tsp.n_chunks, fptr(part), st)
+    acc = _combine(part, _lib.FVGN_TS_TOKW, tsp.chunk_ptr, tsp.nseg)[:, :TS_TOK]
+    d_tok_out = acc[:tsp.nb]
+    if tsp.nseg > tsp.nb:   # ghost rows de-slice with the tokens of graph id - nb
+        extra = acc[tsp.nb:]
+        d_tok_out = d_tok_out.clone()
+        d_tok_out[:extra.shape[0]] += extra
+    with torch.enable_grad():
+        leaves = [t.detach().requires_grad_(True) for t in (rec, wq, wk, wv)]
+        ot = _token_attention(leaves[0], leaves[1], leaves[2], leaves[3], scale)
+        d_rec, d_wq, d_wk, d_wv = torch.autograd.grad(ot, leaves, d_tok_out)
+    if halo is not None:
+        from .parallel import allreduce_sum_
+        d_rec = allreduce_sum_(d_rec.contiguous())
+    d_rec = _c(d_rec)
+    dP = _empty((n, 256), x)
+    ppart = _empty((max(tsp.n_chunks, 1), _lib.FVGN_TS_PARAMW), x)
+    _lib.call("fvgn_ts_slice_backward", fptr(P), fptr(sw), fptr(d_ox), fptr(tok_out), fptr(d_rec), tsp.nb, fptr(ws_c),
+              fptr(bs_c), fptr(temp_c), iptr(tsp.chunks), tsp.n_chunks, fptr(dP), fptr(ppart), st)
+    if tsp.n_chunks > 0:
+        pg = _combine(ppart, _lib.FVGN_TS_PARAMW, tsp.all_ptr, 1).reshape(-1)
+    else:
+        pg = torch.zeros(_lib.FVGN_TS_PARAMW, device=x.device)
+    d_ws, d_bs = pg[:512].view(TS_G, TS_DH), pg[512:544]
+    d_temp, d_bcat = pg[544:552].view(1, TS_HEADS, 1), pg[552:808]
+    d_x = dP @ wcat if d_res is None else torch.addmm(d_res, dP, wcat)
+    d_wcat = dP.t() @ x
+    return (d_x, d_wcat[:128], d_bcat[:128], d_wcat[128:], d_bcat[128:], d_ws, d_bs, d_temp, d_wq, d_wk, d_wv, d_wo)
+
+
+def _tail_forward(a, bo, res, gamma, beta, w1, b1, w2, b2, want_shadow):
+    """y = a + bo + res ; z = ln_2(y) ; h = GELU(z W1^T + b1) ; out = h W2^T + b2 + y -> (out, shadow, kept tensors)."""
+    n = a.shape[0]
+    st = _lib.stream_ptr(a.device)
+    y, z, stats = _empty((n, 128), a), _empty((n, 128), a), _empty((n, 2), a)
+    b1c, gc = _c(b1.detach()), _c(gamma.detach())
+    _lib.call("fvgn_ts_residual_ln_forward", fptr(a), fptr(_c(bo.detach())), fptr(res), fptr(gc), fptr(_c(beta.detach())),
+              fptr(y), fptr(z), fptr(stats), n, st)
+    hpre = z @ w1.t()
+    h = _empty((n, 256), a)
+    _lib.call("fvgn_ts_bias_gelu_forward", fptr(hpre), fptr(b1c), fptr(h), n, st)
+    o = h @ w2.t()
+    out = _empty((n, 128), a)
+    outh = torch.empty((n, 128), dtype=BF16, device=a.device) if want_shadow else None
+    _lib.call("fvgn_ts_bias_residual", fptr(o), fptr(_c(b2.detach())), fptr(y), fptr(out), hptr(outh, True), n, st)
+    return out, outh, (y, stats, z, hpre, h, gc, w1, b1c, w2)
+
+
+def _tail_backward(saved, d_out):
+    """-> (d_y = gradient of both a and res, d_bo, d_gamma, d_beta, d_w1, d_b1, d_w2, d_b2)."""
+    y, stats, z, hpre, h, gc, w1, b1c, w2 = saved
+    n = y.shape[0]
+    st = _lib.stream_ptr(y.device)
+    d_out = _c(d_out)
+    npart = _row_partials(n)
+    ptr = _ptr01(npart, y.device)
+    d_w2 = d_out.t() @ h
+    d_h = d_out @ w2
+    part = _empty((npart, 256), y)
+    _lib.call("fvgn_ts_bias_gelu_backward", fptr(d_h), fptr(hpre), fptr(b1c), fptr(d_h), fptr(part), n, st)  # in place
+    d_b1 = _combine(part, 256, ptr, 1).reshape(-1) if n > 0 else torch.zeros(256, device=y.device)
+    d_w1 = d_h.t() @ z
+    d_z = d_h @ w1
+    d_y = _empty((n, 128), y)
+    part = _empty((npart, 512), y)
+    _lib.call("fvgn_ts_residual_ln_backward", fptr(d_z), fptr(y), fptr(stats), fptr(gc), fptr(d_out), fptr(d_y), fptr(part),
+              n, st)
+    s = _combine(part, 512, ptr, 1).reshape(-1) if n > 0 else torch.zeros(512, device=y.device)
+    return d_y, s[256:384], s[0:128], s[128:256], d_w1, d_b1, d_w2, s[384:512]
+
+
 class SliceAttentionFn(torch.autograd.Function):
     """Graph_Physics_Attention_1D.graph_forward (GraphTransolver.py:48-95) without the to_out bias:
     x[N,128] -> to_out.weight @ deslice(attention(slice(x))).  Projections are library GEMMs; slice softmax, token sums,
@@ -676,117 +778,62 @@ class SliceAttentionFn(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, x, wfx, bfx, wx, bx, ws, bs, temp, wq, wk, wv, wo, scale, tsp, halo):
-        x = _c(x)
-        n = x.shape[0]
-        st = _lib.stream_ptr(x.device)
-        wcat = torch.cat([wfx, wx], 0)
-        P = torch.addmm(torch.cat([bfx, bx], 0), x, wcat.t())                  # [N,256] = fx_mid | x_mid
-        ws_c, bs_c, temp_c = _c(ws.detach()), _c(bs.detach()), _c(temp.detach().reshape(-1))
-        sw = _empty((n, 256), x)
-        part = _empty((max(tsp.n_chunks, 1), _lib.FVGN_TS_TOKW), x)
-        _lib.call("fvgn_ts_slice_forward", fptr(P), fptr(ws_c), fptr(bs_c), fptr(temp_c), iptr(tsp.chunks), tsp.n_chunks,
-                  fptr(sw), fptr(part), st)
-        rec = _combine(part, _lib.FVGN_TS_TOKW, tsp.chunk_ptr, tsp.nseg)[:tsp.nb].contiguous()
-        if halo is not None:   # cell-partition mode: tokens are sums over the rows every rank owns
-            from .parallel import allreduce_sum_
-            rec = allreduce_sum_(rec)
-        tok_out = _c(_token_attention(rec, wq, wk, wv, scale))
-        out_x = _empty((n, 128), x)
-        _lib.call("fvgn_ts_deslice", fptr(sw), fptr(tok_out), TS_TOK, tsp.nb, iptr(tsp.chunks), tsp.n_chunks, fptr(out_x), st)
+        a, saved = _attn_forward(_c(x), wfx, bfx, wx, bx, ws, bs, temp, wq, wk, wv, wo, scale, tsp, halo)
         ctx.tsp, ctx.halo, ctx.scale = tsp, halo, scale
-        ctx.save_for_backward(x, P, sw, rec, tok_out, out_x, wcat, ws_c, bs_c, temp_c, wq, wk, wv, wo)
-        return out_x @ wo.t()
+        ctx.save_for_backward(*saved)
+        return a
 
     @staticmethod
     def backward(ctx, d_a):
-        x, P, sw, rec, tok_out, out_x, wcat, ws_c, bs_c, temp_c, wq, wk, wv, wo = ctx.saved_tensors
-        tsp, halo = ctx.tsp, ctx.halo
-        n = x.shape[0]
-        st = _lib.stream_ptr(x.device)
-        d_a = _c(d_a)
-        d_wo = d_a.t() @ out_x
-        d_ox = d_a @ wo                                                         # [N,128]
-        part = _empty((max(tsp.n_chunks, 1), _lib.FVGN_TS_TOKW), x)
-        _lib.call("fvgn_ts_accumulate", fptr(sw), fptr(d_ox), iptr(tsp.chunks), tsp.n_chunks, fptr(part), st)
-        acc = _combine(part, _lib.FVGN_TS_TOKW, tsp.chunk_ptr, tsp.nseg)[:, :TS_TOK]
-        d_tok_out = acc[:tsp.nb]
-        if tsp.nseg > tsp.nb:   # ghost rows de-slice with the tokens of graph id - nb
-            extra = acc[tsp.nb:]
-            d_tok_out = d_tok_out.clone()
-            d_tok_out[:extra.shape[0]] += extra
-        with torch.enable_grad():
-            leaves = [t.detach().requires_grad_(True) for t in (rec, wq, wk, wv)]
-            ot = _token_attention(leaves[0], leaves[1], leaves[2], leaves[3], ctx.scale)
-            d_rec, d_wq, d_wk, d_wv = torch.autograd.grad(ot, leaves, d_tok_out)
-        if halo is not None:
-            from .parallel import allreduce_sum_
-            d_rec = allreduce_sum_(d_rec.contiguous())
-        d_rec = _c(d_rec)
-        dP = _empty((n, 256), x)
-        ppart = _empty((max(tsp.n_chunks, 1), _lib.FVGN_TS_PARAMW), x)
-        _lib.call("fvgn_ts_slice_backward", fptr(P), fptr(sw), fptr(d_ox), fptr(tok_out), fptr(d_rec), tsp.nb, fptr(ws_c),
-                  fptr(bs_c), fptr(temp_c), iptr(tsp.chunks), tsp.n_chunks, fptr(dP), fptr(ppart), st)
-        if tsp.n_chunks > 0:
-            pg = _combine(ppart, _lib.FVGN_TS_PARAMW, tsp.all_ptr, 1).reshape(-1)
-        else:
-            pg = torch.zeros(_lib.FVGN_TS_PARAMW, device=x.device)
-        d_ws, d_bs = pg[:512].view(TS_G, TS_DH), pg[512:544]
-        d_temp, d_bcat = pg[544:552].view(1, TS_HEADS, 1), pg[552:808]
-        d_x = dP @ wcat
-        d_wcat = dP.t() @ x
-        return (d_x, d_wcat[:128], d_bcat[:128], d_wcat[128:], d_bcat[128:], d_ws, d_bs, d_temp, d_wq, d_wk, d_wv, d_wo,
-                None, None, None)
+        return (*_attn_backward(ctx.saved_tensors, d_a, ctx.scale, ctx.tsp, ctx.halo), None, None, None)
 
 
-class BlockTailFn(torch.autograd.Function):
-    """Second half of Transolver_block.forward (GraphTransolver.py:163-169) as one autograd node:
-    y = a + to_out.bias + fx ; z = ln_2(y) ; h = GELU(z W1^T + b1) ; out = h W2^T + b2 + y  (+ bf16 shadow of out).
-    The two GEMMs are library calls; bias / residual / LayerNorm / GELU and every bias or LayerNorm gradient (column
-    sums as deterministic per-CTA partials) are the ts_* kernels."""
+class TransolverBlockFn(torch.autograd.Function):
+    """Transolver_block.forward with in_layernorm=False (GraphTransolver.py:163-169) as ONE autograd node:
+        fx = xa (+ xb) ; y = graph_forward(fx) + fx ; out = mlp(ln_2(y)) + y      (+ bf16 shadow of out)
+    xb is the node embedding the TransFVGN processors add before the block (TransFVGN_v1.py:70, TransFVGN_v2.py:49).
+    Library GEMMs for the five dense projections; everything else are the ts_* kernels; the residual gradient enters the
+    last backward GEMM as its accumulator, so no separate gradient-accumulation passes remain."""
 
     @staticmethod
-    def forward(ctx, a, bo, res, gamma, beta, w1, b1, w2, b2, want_shadow):
-        a, res = _c(a), _c(res)
-        n = a.shape[0]
-        st = _lib.stream_ptr(a.device)
-        y, z, stats = _empty((n, 128), a), _empty((n, 128), a), _empty((n, 2), a)
-        b1c = _c(b1.detach())
-        _lib.call("fvgn_ts_residual_ln_forward", fptr(a), fptr(_c(bo.detach())), fptr(res), fptr(_c(gamma.detach())),
-                  fptr(_c(beta.detach())), fptr(y), fptr(z), fptr(stats), n, st)
-        hpre = z @ w1.t()
-        h = _empty((n, 256), a)
-        _lib.call("fvgn_ts_bias_gelu_forward", fptr(hpre), fptr(b1c), fptr(h), n, st)
-        o = h @ w2.t()
-        out = _empty((n, 128), a)
-        outh = torch.empty((n, 128), dtype=BF16, device=a.device) if want_shadow else None
-        _lib.call("fvgn_ts_bias_residual", fptr(o), fptr(_c(b2.detach())), fptr(y), fptr(out), hptr(outh, True), n, st)
+    def forward(ctx, xa, xb, wfx, bfx, wx, bx, ws, bs, temp, wq, wk, wv, wo, bo, gamma, beta, w1, b1, w2, b2, scale, tsp,
+                halo, want_shadow):
+        x = _c(xa) if xb is None else xa + xb
+        a, s1 = _attn_forward(x, wfx, bfx, wx, bx, ws, bs, temp, wq, wk, wv, wo, scale, tsp, halo)
+        out, outh, s2 = _tail_forward(a, bo, x, gamma, beta, w1, b1, w2, b2, want_shadow)
+        ctx.tsp, ctx.halo, ctx.scale, ctx.n1, ctx.has_b = tsp, halo, scale, len(s1), xb is not None
         ctx.set_materialize_grads(False)
         if outh is not None:
             ctx.mark_non_differentiable(outh)
-        ctx.save_for_backward(y, stats, z, hpre, h, gamma, w1, b1c, w2)
+        ctx.save_for_backward(*s1, *s2)
         return out, outh
 
     @staticmethod
     def backward(ctx, d_out, _dh=None):
-        y, stats, z, hpre, h, gamma, w1, b1c, w2 = ctx.saved_tensors
-        n = y.shape[0]
-        st = _lib.stream_ptr(y.device)
-        d_out = _c(d_out)
-        npart = _row_partials(n)
-        ptr = _ptr01(npart, y.device)
-        d_w2 = d_out.t() @ h
-        d_h = d_out @ w2
-        part = _empty((npart, 256), y)
-        _lib.call("fvgn_ts_bias_gelu_backward", fptr(d_h), fptr(hpre), fptr(b1c), fptr(d_h), fptr(part), n, st)  # in place
-        d_b1 = _combine(part, 256, ptr, 1).reshape(-1) if n > 0 else torch.zeros(256, device=y.device)
-        d_w1 = d_h.t() @ z
-        d_z = d_h @ w1
-        d_y = _empty((n, 128), y)
-        part = _empty((npart, 512), y)
-        _lib.call("fvgn_ts_residual_ln_backward", fptr(d_z), fptr(y), fptr(stats), fptr(_c(gamma.detach())), fptr(d_out),
-                  fptr(d_y), fptr(part), n, st)
-        s = _combine(part, 512, ptr, 1).reshape(-1) if n > 0 else torch.zeros(512, device=y.device)
-        return d_y, s[256:384], d_y, s[0:128], s[128:256], d_w1, d_b1, d_w2, s[384:512], None
+        s1, s2 = ctx.saved_tensors[:ctx.n1], ctx.saved_tensors[ctx.n1:]
+        d_y, d_bo, d_gamma, d_beta, d_w1, d_b1, d_w2, d_b2 = _tail_backward(s2, d_out)
+        g = _attn_backward(s1, d_y, ctx.scale, ctx.tsp, ctx.halo, d_res=d_y)   # d fx = dP Wcat + d_y in one GEMM
+        return (g[0], g[0] if ctx.has_b else None, *g[1:], d_bo, d_gamma, d_beta, d_w1, d_b1, d_w2, d_b2, None, None, None,
+                None)
+
+
+class BlockTailFn(torch.autograd.Function):
+    """Second half of Transolver_block.forward (GraphTransolver.py:163-169) as one autograd node (used when the first half
+    runs on ln_1(fx), in_layernorm=True): y = a + to_out.bias + fx ; out = mlp(ln_2(y)) + y."""
+
+    @staticmethod
+    def forward(ctx, a, bo, res, gamma, beta, w1, b1, w2, b2, want_shadow):
+        out, outh, saved = _tail_forward(_c(a), bo, _c(res), gamma, beta, w1, b1, w2, b2, want_shadow)
+        ctx.set_materialize_grads(False)
+        if outh is not None:
+            ctx.mark_non_differentiable(outh)
+        ctx.save_for_backward(*saved)
+        return out, outh
+
+    @staticmethod
+    def backward(ctx, d_out, _dh=None):
+        d_y, d_bo, d_gamma, d_beta, d_w1, d_b1, d_w2, d_b2 = _tail_backward(ctx.saved_tensors, d_out)
+        return d_y, d_bo, d_y, d_gamma, d_beta, d_w1, d_b1, d_w2, d_b2, None
 
 
 class BiasGeluFn(torch.autograd.Function):

@@ -93,6 +93,51 @@ def test_public_graph_forward_and_mlp_emulated():
         PU.use_real_kernels()
 
 
+def _inlayernorm_wiring(device):
+    """in_layernorm=True (original-Transolver variant) and the `embedding` argument against a composition of the
+    separately verified public pieces."""
+    import torch.nn.functional as F
+    blk, x, batch, cot = _block_and_inputs((45, 30), device, seed=2)
+    emb = torch.randn_like(x)
+    xr, er = x.clone().requires_grad_(True), emb.clone().requires_grad_(True)
+    out = blk(xr, batch, in_layernorm=True, embedding=er)
+    out.backward(cot)
+    got = [out.detach(), xr.grad.clone(), er.grad.clone()] + [p.grad.clone() for p in blk.parameters() if p.grad is not None]
+    for p in blk.parameters():
+        p.grad = None
+    x2, e2 = x.clone().requires_grad_(True), emb.clone().requires_grad_(True)
+    fx = x2 + e2
+    y = blk.Attn.graph_forward(blk.ln_1(fx), batch) + fx
+    ref = blk.mlp(F.layer_norm(y, (128,), blk.ln_2.weight, blk.ln_2.bias, 1e-5)) + y
+    ref.backward(cot)
+    want = [ref.detach(), x2.grad, e2.grad] + [p.grad for p in blk.parameters() if p.grad is not None]
+    assert len(got) == len(want)
+    for a, b in zip(got, want):
+        assert float((a - b).norm() / b.norm().clamp_min(1e-30)) < 2e-5
+    # embedding on the fused (in_layernorm=False) path == adding it outside
+    for p in blk.parameters():
+        p.grad = None
+    x3, e3 = x.clone().requires_grad_(True), emb.clone().requires_grad_(True)
+    o1 = blk(x3, batch, embedding=e3)
+    o1.backward(cot)
+    o2 = blk((x + emb).clone(), batch)
+    assert float((o1 - o2).norm() / o2.norm()) < 1e-6
+    assert torch.equal(x3.grad, e3.grad)
+
+
+def test_inlayernorm_and_embedding_emulated():
+    PU.use_emulated_kernels()
+    try:
+        _inlayernorm_wiring("cpu")
+    finally:
+        PU.use_real_kernels()
+
+
+@pytest.mark.gpu
+def test_inlayernorm_and_embedding_gpu():
+    _inlayernorm_wiring("cuda")
+
+
 @pytest.mark.gpu
 @pytest.mark.parametrize("sizes", [(70,), (33, 1, 95), (5000, 12345, 777)])
 def test_transolver_block_gpu(sizes):
