@@ -84,29 +84,45 @@ __device__ __forceinline__ void ts_store_tile(const float* s, float* __restrict_
   }
 }
 
-__device__ __forceinline__ void ld16(float* dst, const float* src) {
+// 16-wide fp32 vectors are kept as 8 float2 so the inner products / axpys issue as packed FFMA2 (sm_100: the 3-register
+// scalar FFMA runs at half rate; the packed form restores the full fp32 rate and halves the issue slots).
+#ifdef FVGN_EMU
+static inline float2 fma2(float2 a, float2 b, float2 c) { return make_float2(a.x * b.x + c.x, a.y * b.y + c.y); }
+#else
+__device__ __forceinline__ float2 fma2(float2 a, float2 b, float2 c) { return __ffma2_rn(a, b, c); }
+#endif
+
+__device__ __forceinline__ void ld16(float2* dst, const float* src) {
 #pragma unroll
   for (int q = 0; q < 4; ++q) {
     const float4 v = ld4(src + q * 4);
-    dst[q * 4 + 0] = v.x; dst[q * 4 + 1] = v.y; dst[q * 4 + 2] = v.z; dst[q * 4 + 3] = v.w;
+    dst[q * 2 + 0] = make_float2(v.x, v.y);
+    dst[q * 2 + 1] = make_float2(v.z, v.w);
   }
 }
-__device__ __forceinline__ void st16(float* dst, const float* src) {
+__device__ __forceinline__ void st16(float* dst, const float2* src) {
 #pragma unroll
-  for (int q = 0; q < 4; ++q) st4(dst + q * 4, make_float4(src[q * 4], src[q * 4 + 1], src[q * 4 + 2], src[q * 4 + 3]));
+  for (int q = 0; q < 4; ++q) st4(dst + q * 4, make_float4(src[q * 2].x, src[q * 2].y, src[q * 2 + 1].x, src[q * 2 + 1].y));
 }
-
-// 16-term dot product + c as four independent chains (columns k, k+4, k+8, k+12 per chain)
-__device__ __forceinline__ float dot16(const float* x, const float* w, float c) {
-  float p0 = c, p1 = 0.f, p2 = 0.f, p3 = 0.f;
+__device__ __forceinline__ void zero16(float2* a) {
 #pragma unroll
-  for (int q = 0; q < 4; ++q) {
-    p0 += x[q * 4 + 0] * w[q * 4 + 0];
-    p1 += x[q * 4 + 1] * w[q * 4 + 1];
-    p2 += x[q * 4 + 2] * w[q * 4 + 2];
-    p3 += x[q * 4 + 3] * w[q * 4 + 3];
+  for (int k = 0; k < 8; ++k) a[k] = make_float2(0.f, 0.f);
+}
+// acc += s * x
+__device__ __forceinline__ void axpy16(float2* acc, float s, const float2* x) {
+  const float2 s2 = make_float2(s, s);
+#pragma unroll
+  for (int k = 0; k < 8; ++k) acc[k] = fma2(s2, x[k], acc[k]);
+}
+// c + x . w as four independent chains
+__device__ __forceinline__ float dot16(const float2* x, const float2* w, float c) {
+  float2 p = make_float2(0.f, 0.f), q = make_float2(0.f, 0.f);  // (seeding p.x with c makes ptxas spill: keep c outside)
+#pragma unroll
+  for (int k = 0; k < 8; k += 2) {
+    p = fma2(x[k], w[k], p);
+    q = fma2(x[k + 1], w[k + 1], q);
   }
-  return (p0 + p1) + (p2 + p3);
+  return c + ((p.x + p.y) + (q.x + q.y));
 }
 
 // ----------------------------------------------------------------------------------------------------------------
@@ -139,9 +155,8 @@ __global__ void __launch_bounds__(TS_NT) ts_slice_kernel(const float* __restrict
     if (tid < TS_G) bss[tid] = bs[tid];
     T = temp[warp];
   }
-  float acc[16];
-#pragma unroll
-  for (int d = 0; d < 16; ++d) acc[d] = 0.f;
+  float2 acc[8];
+  zero16(acc);
   float nrm = 0.f;
   if (r0 < r1) {
     if (FROM_P) {
@@ -169,11 +184,12 @@ __global__ void __launch_bounds__(TS_NT) ts_slice_kernel(const float* __restrict
     float* sws = FROM_P ? Sb : Sb + buf * L::ST;
     if (FROM_P) {
       // thread = (head = warp, node = lane)
-      float xm[16], l[TS_G];
+      float2 xm[8];
+      float l[TS_G];
       ld16(xm, Vs + lane * TS_RS + 128 + warp * 16);
 #pragma unroll
       for (int g = 0; g < TS_G; ++g) {  // in_project_slice (GraphTransolver.py:60)
-        float w[16];
+        float2 w[8];
         ld16(w, Wss + g * 16);
         l[g] = dot16(xm, w, bss[g]);
       }
@@ -193,8 +209,8 @@ __global__ void __launch_bounds__(TS_NT) ts_slice_kernel(const float* __restrict
 #pragma unroll
       for (int g = 0; g < TS_G; ++g) l[g] = valid ? l[g] / s : 0.f;
       float* dst = sws + lane * TS_RS + warp * TS_G;
-      st16(dst, l);
-      st16(dst + 16, l + 16);
+#pragma unroll
+      for (int g4 = 0; g4 < TS_G / 4; ++g4) st4(dst + g4 * 4, make_float4(l[g4 * 4], l[g4 * 4 + 1], l[g4 * 4 + 2], l[g4 * 4 + 3]));
       __syncthreads();
       ts_store_tile<256, TS_RS>(sws, sw, 256, row0, r1);
     }
@@ -202,10 +218,9 @@ __global__ void __launch_bounds__(TS_NT) ts_slice_kernel(const float* __restrict
 #pragma unroll 4
     for (int n = 0; n < TS_TILE; ++n) {
       const float sv = sws[n * TS_RS + warp * TS_G + lane];
-      float f[16];
+      float2 f[8];
       ld16(f, Vs + n * L::VRS + warp * 16);
-#pragma unroll
-      for (int d = 0; d < 16; ++d) acc[d] += sv * f[d];
+      axpy16(acc, sv, f);
       nrm += sv;
     }
   }
@@ -237,19 +252,17 @@ __global__ void __launch_bounds__(TS_NT) ts_deslice_kernel(const float* __restri
     if (row0 + TS_TILE < r1) ts_prefetch_tile<256, TS_RS>(Sb + (buf ^ 1) * TS_TILE * TS_RS, sw, 256, row0 + TS_TILE, r1);
     ts_prefetch_commit();
     const float* srow = Sb + buf * TS_TILE * TS_RS + lane * TS_RS + warp * TS_G;
-    float o[16];
-#pragma unroll
-    for (int d = 0; d < 16; ++d) o[d] = 0.f;
+    float2 o[8];
+    zero16(o);
 #pragma unroll
     for (int g4 = 0; g4 < TS_G / 4; ++g4) {
       const float4 s4 = ld4(srow + g4 * 4);
       const float sv[4] = {s4.x, s4.y, s4.z, s4.w};
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
-        float t[16];
+        float2 t[8];
         ld16(t, Ts + (warp * TS_G + g4 * 4 + j) * 16);
-#pragma unroll
-        for (int d = 0; d < 16; ++d) o[d] += sv[j] * t[d];
+        axpy16(o, sv[j], t);
       }
     }
     st16(outs + lane * TS_RS1 + warp * 16, o);
@@ -291,9 +304,8 @@ __global__ void __launch_bounds__(TS_NT, 1) ts_slice_bwd_kernel(const float* __r
   for (int i = tid; i < TS_G * TS_DH; i += TS_NT) Wss[i] = Ws[i];
   if (tid < TS_G) bss[tid] = bs[tid];
   const float T = temp[warp];
-  float accW[16];
-#pragma unroll
-  for (int c = 0; c < 16; ++c) accW[c] = 0.f;
+  float2 accW[8];
+  zero16(accW);
   float accb = 0.f, accT = 0.f, acccol = 0.f;
   if (r0 < r1) {
     ts_prefetch_tile<256, TS_RS>(Bb, P, 256, r0, r1);
@@ -316,14 +328,14 @@ __global__ void __launch_bounds__(TS_NT, 1) ts_slice_bwd_kernel(const float* __r
     float* sws = Ps + TS_TILE * TS_RS;
     float* dxs = sws + TS_TILE * TS_RS;
     {  // thread = (head = warp, node = lane); sw stays in the tile (16-B reads), d sw / d logits live in registers
-      float ds[TS_G], a[16], b[16], f[16];
+      float ds[TS_G];
+      float2 a[8], b[8], f[8];
       float* srow = sws + lane * TS_RS + warp * TS_G;
       float* frow = Ps + lane * TS_RS + warp * 16;
       float* xrow = dxs + lane * TS_RS1 + warp * 16;
       ld16(a, xrow);  // d out_x
       ld16(b, frow);  // fx_mid
-#pragma unroll
-      for (int d = 0; d < 16; ++d) f[d] = 0.f;
+      zero16(f);
       float dot0 = 0.f, dot1 = 0.f;
 #pragma unroll
       for (int g4 = 0; g4 < TS_G / 4; ++g4) {
@@ -332,13 +344,12 @@ __global__ void __launch_bounds__(TS_NT, 1) ts_slice_bwd_kernel(const float* __r
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
           const int g = g4 * 4 + j;
-          float o[16], dn[16];
+          float2 o[8], dn[8];
           ld16(o, OTs + (warp * TS_G + g) * 16);
           ld16(dn, DNs + (warp * TS_G + g) * 16);
           // d sw[g] = d_norm[g] + d out_x . tok_out[g] + fx . d_num[g]
           const float v = dot16(a, o, dns[warp * TS_G + g]) + dot16(b, dn, 0.f);
-#pragma unroll
-          for (int d = 0; d < 16; ++d) f[d] += sv[j] * dn[d];  // d fx_mid[d] = sum_g sw[g] d_num[g,d]
+          axpy16(f, sv[j], dn);  // d fx_mid[d] = sum_g sw[g] d_num[g,d]
           ds[g] = v;
           if (j & 1) dot1 += sv[j] * v; else dot0 += sv[j] * v;
         }
@@ -347,8 +358,7 @@ __global__ void __launch_bounds__(TS_NT, 1) ts_slice_bwd_kernel(const float* __r
       st16(frow, f);  // overwrites fx in the tile
       // softmax backward (scaled logits z = l / T), then through /T and in_project_slice
       ld16(b, Ps + lane * TS_RS + 128 + warp * 16);  // x_mid
-#pragma unroll
-      for (int c = 0; c < 16; ++c) a[c] = 0.f;
+      zero16(a);
       float t0 = 0.f, t1 = 0.f;
 #pragma unroll
       for (int g4 = 0; g4 < TS_G / 4; ++g4) {
@@ -358,14 +368,13 @@ __global__ void __launch_bounds__(TS_NT, 1) ts_slice_bwd_kernel(const float* __r
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
           const int g = g4 * 4 + j;
-          float w[16];
+          float2 w[8];
           ld16(w, Wss + g * 16);
           const float lg = dot16(b, w, bss[g]);
           const float dz = sv[j] * (ds[g] - dot);
           if (j & 1) t1 += dz * lg; else t0 += dz * lg;
           dl[j] = dz / T;
-#pragma unroll
-          for (int c = 0; c < 16; ++c) a[c] += dl[j] * w[c];
+          axpy16(a, dl[j], w);
         }
         st4(srow + g4 * 4, make_float4(dl[0], dl[1], dl[2], dl[3]));  // d logits (pre-temperature) for the dWs sum below
       }
@@ -377,10 +386,9 @@ __global__ void __launch_bounds__(TS_NT, 1) ts_slice_bwd_kernel(const float* __r
 #pragma unroll 4
     for (int n = 0; n < TS_TILE; ++n) {
       const float dl = sws[n * TS_RS + warp * TS_G + lane];
-      float x[16];
+      float2 x[8];
       ld16(x, Ps + n * TS_RS + 128 + warp * 16);
-#pragma unroll
-      for (int c = 0; c < 16; ++c) accW[c] += dl * x[c];
+      axpy16(accW, dl, x);
       accb += dl;
     }
     // dP tile = [d fx (Ps cols 0..127) | d xm (dxs)], column sums for the projection biases

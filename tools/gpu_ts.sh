@@ -12,3 +12,6 @@ grep '^{' gpurun_out/bench_v2_$tag.log | cut -c1-330
 timeout 400 ncu --metrics gpu__time_duration.sum --clock-control none -c 4000 --csv --log-file gpurun_out/launches_v2_$tag.csv \
   python bench.py --net TransFVGN_v2 --mp 3 --cells $cells --steps 1 --warmup 1 --no-cpu-baseline > gpurun_out/ncu_v2_$tag.log 2>&1; echo "ncu rc=$?"
 python tools/launch_summary.py gpurun_out/launches_v2_$tag.csv | tee gpurun_out/launches_v2_${tag}_summary.txt | head -40
+# one full-metrics capture of the slice / de-slice kernels (first step), read back with tools/ncu_lines.py / ncu -i
+timeout 400 ncu --set full --clock-control none --import-source on -k regex:'ts_slice|ts_deslice' -c 8 -f -o gpurun_out/prof_ts_$tag \
+  python bench.py --net TransFVGN_v2 --mp 3 --cells $cells --steps 1 --warmup 1 --no-cpu-baseline > gpurun_out/ncu_full_ts_$tag.log 2>&1; echo "ncu full rc=$?"
