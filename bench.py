@@ -153,10 +153,15 @@ def run_reference(args):
     print(json.dumps(line))
 
 
+def _gn_blocks(args):
+    """GnBlocks per forward: TransFVGN_v2 runs two processors of --mp blocks each (TransFVGN_v2.py:73-82)."""
+    return args.mp * (2 if args.net in ("TransFVGN_v2", "TransFVGN") else 1)
+
+
 def workload_config(args, C_bench=None):
     return {"workload": f"synthetic jittered quad mesh, {args.cells} cells/GPU, cavity BC, NS theta; "
-                        f"{args.net} G={args.mp} + FV PDE loss; resident batch (solve_with_grad regime)",
-            "net": args.net, "gn_blocks": args.mp, "cuda_graph": bool(getattr(args, "graph", False)), "cells_per_gpu": args.cells if C_bench is None else C_bench,
+                        f"{args.net} G={_gn_blocks(args)} + FV PDE loss; resident batch (solve_with_grad regime)",
+            "net": args.net, "gn_blocks": _gn_blocks(args), "cuda_graph": bool(getattr(args, "graph", False)), "cells_per_gpu": args.cells if C_bench is None else C_bench,
             "precision": args.precision, "l2": "inputs/activations (GBs) far exceed the 126 MB L2; no explicit flush"}
 
 
@@ -184,7 +189,7 @@ def run_ours(args):
         dist.init_process_group("nccl", device_id=dev)
 
     cells_mode = args.parallel == "cells" and world > 1
-    gn_blocks_total = args.mp * (2 if args.net in ("TransFVGN_v2", "TransFVGN") else 1)  # v2: two processors of mp blocks
+    gn_blocks_total = _gn_blocks(args)  # v2: two processors of mp blocks
     if args.halo_layers is None:
         args.halo_layers = 3 * gn_blocks_total + 2
     halo = None
@@ -305,7 +310,7 @@ def run_ours(args):
     hbm, how = peaks()
     sec = ms / 1e3 / args.steps
     value = (C_global if cells_mode else world * C) / sec
-    ab = alg_bytes_step(N, E, C, K, X, args.mp)
+    ab = alg_bytes_step(N, E, C, K, X, gn_blocks_total)   # SURVEY 8(d) counts the GN + FV bytes only (Transolver blocks add none)
     line = {"metric": "cells*steps/sec (fwd+bwd train step)", "value": value, "unit": "cells*steps/s", "n_gpus": world,
             "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps, "higher_is_better": True,
             "scaling": "strong" if cells_mode else "weak", "vs_baseline": None,
