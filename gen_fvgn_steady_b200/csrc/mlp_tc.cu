@@ -276,6 +276,15 @@ __global__ void __launch_bounds__(NTHREADS, 1) mlp_tc_fwd_kernel(const fvgn_mlp_
                             ? reinterpret_cast<uint8_t*>(d.z1_img) + (size_t)tile * (2 * KB_BYTES) + q * WSTG_BYTES : nullptr;
         for_each_chunk16(acc, [&](int c0, uint32_t (&r)[16]) {
           uint32_t w[8];
+#if FVGN_F32X2
+          float2 z[8];   // z[j] = columns (2j, 2j+1)
+#pragma unroll
+          for (int j = 0; j < 8; j += 2) {
+            const float4 b = *reinterpret_cast<const float4*>(bias + c0 + 2 * j);
+            z[j] = __fadd2_rn(f2u(r[2 * j], r[2 * j + 1]), make_float2(b.x, b.y));
+            z[j + 1] = __fadd2_rn(f2u(r[2 * j + 2], r[2 * j + 3]), make_float2(b.z, b.w));
+          }
+#else
           float z[16];
 #pragma unroll
           for (int j = 0; j < 16; j += 4) {
@@ -285,13 +294,19 @@ __global__ void __launch_bounds__(NTHREADS, 1) mlp_tc_fwd_kernel(const fvgn_mlp_
             z[j + 2] = __uint_as_float(r[j + 2]) + b.z;
             z[j + 3] = __uint_as_float(r[j + 3]) + b.w;
           }
+#endif
           if (layer == 0) {
             uint32_t zw[8];
 #pragma unroll
             for (int j = 0; j < 8; ++j) {
+#if FVGN_F32X2
+              zw[j] = pack_bf16(z[j]);
+              z[j] = bf16x2_f2(zw[j]);
+#else
               zw[j] = pack_bf16(z[2 * j], z[2 * j + 1]);
               z[2 * j] = bf16_lo(zw[j]);
               z[2 * j + 1] = bf16_hi(zw[j]);
+#endif
             }
             if (zimg) {
               const int ch = (c0 & 63) >> 3;
@@ -311,7 +326,11 @@ __global__ void __launch_bounds__(NTHREADS, 1) mlp_tc_fwd_kernel(const fvgn_mlp_
             }
           }
 #pragma unroll
+#if FVGN_F32X2
+          for (int j = 0; j < 8; ++j) w[j] = pack_bf16(gelu_tanh2(z[j]));
+#else
           for (int j = 0; j < 8; ++j) w[j] = pack_bf16(gelu_tanh(z[2 * j]), gelu_tanh(z[2 * j + 1]));
+#endif
           tmem_st8(acc + c0 / 2, w);  // in place: always behind the columns still to be read (and the one in flight)
         });
         tmem_wait_st();
@@ -328,16 +347,30 @@ __global__ void __launch_bounds__(NTHREADS, 1) mlp_tc_fwd_kernel(const fvgn_mlp_
       if (C::LN) {
         // LayerNorm statistics in one pass over the accumulator (sum / sum of squares in fp32)
         float sum = 0.f, sq = 0.f;
+#if FVGN_F32X2
+        float2 sum2 = splat2(0.f), sq2 = splat2(0.f);
+#endif
         for_each_chunk16(acc, [&](int c0, uint32_t (&r)[16]) {
 #pragma unroll
           for (int j = 0; j < 16; j += 4) {
             const float4 b = *reinterpret_cast<const float4*>(sb3 + c0 + j);
+#if FVGN_F32X2
+            const float2 ya = __fadd2_rn(f2u(r[j], r[j + 1]), make_float2(b.x, b.y));
+            const float2 yb = __fadd2_rn(f2u(r[j + 2], r[j + 3]), make_float2(b.z, b.w));
+            sum2 = __fadd2_rn(sum2, __fadd2_rn(ya, yb));
+            sq2 = __ffma2_rn(ya, ya, __ffma2_rn(yb, yb, sq2));
+            continue;
+#endif
             const float y0 = __uint_as_float(r[j]) + b.x, y1 = __uint_as_float(r[j + 1]) + b.y;
             const float y2 = __uint_as_float(r[j + 2]) + b.z, y3 = __uint_as_float(r[j + 3]) + b.w;
             sum += (y0 + y1) + (y2 + y3);
             sq = fmaf(y0, y0, fmaf(y1, y1, fmaf(y2, y2, fmaf(y3, y3, sq))));
           }
         });
+#if FVGN_F32X2
+        sum = sum2.x + sum2.y;
+        sq = sq2.x + sq2.y;
+#endif
         const float mean = sum * (1.0f / 128.0f);
         const float rstd = rsqrtf(fmaxf(sq * (1.0f / 128.0f) - mean * mean, 0.f) + 1e-5f);
         PROF_F(5);  // LayerNorm statistics
@@ -367,10 +400,21 @@ __global__ void __launch_bounds__(NTHREADS, 1) mlp_tc_fwd_kernel(const fvgn_mlp_
             const float4 gm = *reinterpret_cast<const float4*>(sg + c0 + j);
             const float4 bt = *reinterpret_cast<const float4*>(sbeta + c0 + j);
             float4 y;
+#if FVGN_F32X2
+            {  // ((acc + b) - mean) * rstd * gamma + beta, same operation order as the scalar form
+              const float2 nm = splat2(-mean), rs = splat2(rstd);
+              const float2 ya = __ffma2_rn(__fmul2_rn(__fadd2_rn(__fadd2_rn(f2u(r[j], r[j + 1]), make_float2(b.x, b.y)), nm), rs),
+                                           make_float2(gm.x, gm.y), make_float2(bt.x, bt.y));
+              const float2 yb = __ffma2_rn(__fmul2_rn(__fadd2_rn(__fadd2_rn(f2u(r[j + 2], r[j + 3]), make_float2(b.z, b.w)), nm), rs),
+                                           make_float2(gm.z, gm.w), make_float2(bt.z, bt.w));
+              y = make_float4(ya.x, ya.y, yb.x, yb.y);
+            }
+#else
             y.x = (__uint_as_float(r[j + 0]) + b.x - mean) * rstd * gm.x + bt.x;
             y.y = (__uint_as_float(r[j + 1]) + b.y - mean) * rstd * gm.y + bt.y;
             y.z = (__uint_as_float(r[j + 2]) + b.z - mean) * rstd * gm.z + bt.z;
             y.w = (__uint_as_float(r[j + 3]) + b.w - mean) * rstd * gm.w + bt.w;
+#endif
             *reinterpret_cast<float4*>(wstg_at(mystg, lane, j >> 2)) = y;
           }
           __syncwarp();

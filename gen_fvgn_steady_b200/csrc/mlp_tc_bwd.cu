@@ -420,6 +420,11 @@ __global__ void __launch_bounds__(A_THREADS, 1) mlp_tc_bwd_a_kernel(const fvgn_m
         for (int j = 0; j < 8; ++j) {
 #if FVGN_GELU_PACKED
           gelu_tanh_pair_bf16x2(zw[j], hw[j], gw[j]);
+#elif FVGN_F32X2
+          float2 h, g;
+          gelu_tanh_pair2(bf16x2_f2(zw[j]), h, g);
+          hw[j] = pack_bf16(h);
+          gw[j] = pack_bf16(g);
 #else
           float h0, g0, h1, g1;
           gelu_tanh_pair(bf16_lo(zw[j]), h0, g0);
@@ -452,6 +457,14 @@ __global__ void __launch_bounds__(A_THREADS, 1) mlp_tc_bwd_a_kernel(const fvgn_m
           gelu_tanh_pair_bf16x2(pack_bf16(__uint_as_float(r[2 * j]) + b.x, __uint_as_float(r[2 * j + 1]) + b.y), hw[j], gw[j]);
           gelu_tanh_pair_bf16x2(pack_bf16(__uint_as_float(r[2 * j + 2]) + b.z, __uint_as_float(r[2 * j + 3]) + b.w), hw[j + 1],
                                 gw[j + 1]);
+#elif FVGN_F32X2
+          float2 ha, ga, hb, gb;
+          gelu_tanh_pair2(__fadd2_rn(f2u(r[2 * j], r[2 * j + 1]), make_float2(b.x, b.y)), ha, ga);
+          gelu_tanh_pair2(__fadd2_rn(f2u(r[2 * j + 2], r[2 * j + 3]), make_float2(b.z, b.w)), hb, gb);
+          hw[j] = pack_bf16(ha);
+          gw[j] = pack_bf16(ga);
+          hw[j + 1] = pack_bf16(hb);
+          gw[j + 1] = pack_bf16(gb);
 #else
           float h0, g0, h1, g1, h2, g2, h3, g3;
           gelu_tanh_pair(__uint_as_float(r[2 * j]) + b.x, h0, g0);
@@ -481,6 +494,9 @@ __global__ void __launch_bounds__(A_THREADS, 1) mlp_tc_bwd_a_kernel(const fvgn_m
         colsum(bufC, tid, dbta, dbtb);  // d beta = column sums of dO
         // sweep 1 (one pass, no dependence on the statistics): sum y, sum y^2, S1 = sum dO*gamma, S2 = sum dO*gamma*y
         float sum = 0.f, sq = 0.f, s1 = 0.f, s2 = 0.f;
+#if FVGN_F32X2
+        float2 sum2 = splat2(0.f), sq2 = splat2(0.f), s12 = splat2(0.f), s22 = splat2(0.f);
+#endif
         for_each_chunk16<COLS>(wacc, [&](int c0, uint32_t (&r)[16]) {
           uint32_t ow[8];
           load_tile16(bufC, rloc, cbase + c0, ow);
@@ -489,6 +505,17 @@ __global__ void __launch_bounds__(A_THREADS, 1) mlp_tc_bwd_a_kernel(const fvgn_m
             const int c = cbase + c0 + 2 * j;
             const float4 b = *reinterpret_cast<const float4*>(sb3 + c);
             const float4 gm = *reinterpret_cast<const float4*>(sg + c);
+#if FVGN_F32X2
+            const float2 ya = __fadd2_rn(f2u(r[2 * j], r[2 * j + 1]), make_float2(b.x, b.y));
+            const float2 yb = __fadd2_rn(f2u(r[2 * j + 2], r[2 * j + 3]), make_float2(b.z, b.w));
+            const float2 da = __fmul2_rn(bf16x2_f2(ow[j]), make_float2(gm.x, gm.y));
+            const float2 db = __fmul2_rn(bf16x2_f2(ow[j + 1]), make_float2(gm.z, gm.w));
+            sum2 = __fadd2_rn(sum2, __fadd2_rn(ya, yb));
+            sq2 = __ffma2_rn(ya, ya, __ffma2_rn(yb, yb, sq2));
+            s12 = __fadd2_rn(s12, __fadd2_rn(da, db));
+            s22 = __ffma2_rn(da, ya, __ffma2_rn(db, yb, s22));
+            continue;
+#endif
             const float y0 = __uint_as_float(r[2 * j]) + b.x, y1 = __uint_as_float(r[2 * j + 1]) + b.y;
             const float y2 = __uint_as_float(r[2 * j + 2]) + b.z, y3 = __uint_as_float(r[2 * j + 3]) + b.w;
             const float d0 = bf16_lo(ow[j]) * gm.x, d1 = bf16_hi(ow[j]) * gm.y;
@@ -499,6 +526,9 @@ __global__ void __launch_bounds__(A_THREADS, 1) mlp_tc_bwd_a_kernel(const fvgn_m
             s2 = fmaf(d0, y0, fmaf(d1, y1, fmaf(d2, y2, fmaf(d3, y3, s2))));
           }
         });
+#if FVGN_F32X2
+        sum = sum2.x + sum2.y; sq = sq2.x + sq2.y; s1 = s12.x + s12.y; s2 = s22.x + s22.y;
+#endif
         xch[half * 128 + rloc] = make_float4(sum, sq, s1, s2);
         epi_bar();  // also: every thread has finished reading the dO tile (d beta) before rows are overwritten
 #pragma unroll
@@ -521,6 +551,22 @@ __global__ void __launch_bounds__(A_THREADS, 1) mlp_tc_bwd_a_kernel(const fvgn_m
             const int c = cbase + c0 + 2 * j;
             const float4 b = *reinterpret_cast<const float4*>(sb3 + c);
             const float4 gm = *reinterpret_cast<const float4*>(sg + c);
+#if FVGN_F32X2
+            {
+              const float2 rs = splat2(rstd), nm = splat2(nmr), nm1 = splat2(-m1), nm2 = splat2(-m2);
+              const float2 xa = __ffma2_rn(__fadd2_rn(f2u(r[2 * j], r[2 * j + 1]), make_float2(b.x, b.y)), rs, nm);
+              const float2 xb = __ffma2_rn(__fadd2_rn(f2u(r[2 * j + 2], r[2 * j + 3]), make_float2(b.z, b.w)), rs, nm);
+              const float2 oa = bf16x2_f2(ow[j]), ob = bf16x2_f2(ow[j + 1]);
+              const float2 ga = __fmul2_rn(oa, xa), gb = __fmul2_rn(ob, xb);
+              gx[2 * j] = ga.x; gx[2 * j + 1] = ga.y; gx[2 * j + 2] = gb.x; gx[2 * j + 3] = gb.y;
+              // rstd * (o*gamma - m1 - xhat*m2) = rstd * fma(xhat, -m2, fma(o, gamma, -m1))
+              const float2 ya = __fmul2_rn(rs, __ffma2_rn(xa, nm2, __ffma2_rn(oa, make_float2(gm.x, gm.y), nm1)));
+              const float2 yb = __fmul2_rn(rs, __ffma2_rn(xb, nm2, __ffma2_rn(ob, make_float2(gm.z, gm.w), nm1)));
+              ow[j] = pack_bf16(ya);
+              ow[j + 1] = pack_bf16(yb);
+              continue;
+            }
+#endif
             const float xh0 = fmaf(__uint_as_float(r[2 * j]) + b.x, rstd, nmr), xh1 = fmaf(__uint_as_float(r[2 * j + 1]) + b.y, rstd, nmr);
             const float xh2 = fmaf(__uint_as_float(r[2 * j + 2]) + b.z, rstd, nmr), xh3 = fmaf(__uint_as_float(r[2 * j + 3]) + b.w, rstd, nmr);
             const float o0 = bf16_lo(ow[j]), o1 = bf16_hi(ow[j]), o2 = bf16_lo(ow[j + 1]), o3 = bf16_hi(ow[j + 1]);
@@ -550,7 +596,11 @@ __global__ void __launch_bounds__(A_THREADS, 1) mlp_tc_bwd_a_kernel(const fvgn_m
         tmem_wait_ld();
 #pragma unroll
         for (int j = 0; j < 8; ++j)
+#if FVGN_F32X2
+          ow[j] = pack_bf16(__fmul2_rn(f2u(r[2 * j], r[2 * j + 1]), bf16x2_f2(g[j])));
+#else
           ow[j] = pack_bf16(__uint_as_float(r[2 * j]) * bf16_lo(g[j]), __uint_as_float(r[2 * j + 1]) * bf16_hi(g[j]));
+#endif
         store_tile16(bufH2, rloc, cbase + c0, ow);
       });
       fence_proxy_async();
@@ -568,7 +618,11 @@ __global__ void __launch_bounds__(A_THREADS, 1) mlp_tc_bwd_a_kernel(const fvgn_m
         tmem_wait_ld();
 #pragma unroll
         for (int j = 0; j < 8; ++j)
+#if FVGN_F32X2
+          ow[j] = pack_bf16(__fmul2_rn(f2u(r[2 * j], r[2 * j + 1]), bf16x2_f2(g[j])));
+#else
           ow[j] = pack_bf16(__uint_as_float(r[2 * j]) * bf16_lo(g[j]), __uint_as_float(r[2 * j + 1]) * bf16_hi(g[j]));
+#endif
         store_tile16(bz, rloc, cbase + c0, ow);
       });
       fence_proxy_async();

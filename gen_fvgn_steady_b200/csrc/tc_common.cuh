@@ -428,6 +428,33 @@ __device__ __forceinline__ void for_each_chunk16(uint32_t taddr, F&& f) {
 __device__ __forceinline__ float bf16_lo(uint32_t w) { return __uint_as_float(w << 16); }
 __device__ __forceinline__ float bf16_hi(uint32_t w) { return __uint_as_float(w & 0xFFFF0000u); }
 
+// ---- packed fp32x2 epilogue arithmetic (FVGN_F32X2 = 1, default): sm_100 executes fma / mul / add on register PAIRS
+// (FFMA2 / FMUL2 / FADD2, IEEE per element), which halves the fp32 instruction count of the issue-bound epilogue stages.
+// Every packed helper below performs, per element, exactly the operations of its scalar twin (bit-identical results).
+#ifndef FVGN_F32X2
+#define FVGN_F32X2 1
+#endif
+__device__ __forceinline__ float2 splat2(float a) { return make_float2(a, a); }
+__device__ __forceinline__ float2 f2u(uint32_t lo, uint32_t hi) { return make_float2(__uint_as_float(lo), __uint_as_float(hi)); }
+__device__ __forceinline__ float2 bf16x2_f2(uint32_t w) { return make_float2(bf16_lo(w), bf16_hi(w)); }
+__device__ __forceinline__ uint32_t pack_bf16(float2 v) { return pack_bf16(v.x, v.y); }
+__device__ __forceinline__ float2 gelu_tanh2(float2 x) {
+  const float2 u = __fmul2_rn(x, __ffma2_rn(splat2(0.0356774081f), __fmul2_rn(x, x), splat2(0.7978845608f)));
+  const float2 hx = __fmul2_rn(splat2(0.5f), x);
+  return __ffma2_rn(hx, make_float2(tanh_approx(u.x), tanh_approx(u.y)), hx);
+}
+// gelu_tanh_pair on two elements: (1 - t^2) and the polynomial are carried with flipped signs (exact), so no negations
+__device__ __forceinline__ void gelu_tanh_pair2(float2 x, float2& h, float2& g) {
+  const float2 x2 = __fmul2_rn(x, x);
+  const float2 u = __fmul2_rn(x, __ffma2_rn(splat2(0.0356774081f), x2, splat2(0.7978845608f)));
+  const float2 t = make_float2(tanh_approx(u.x), tanh_approx(u.y));
+  const float2 hx = __fmul2_rn(splat2(0.5f), x);
+  h = __ffma2_rn(hx, t, hx);
+  const float2 q = __ffma2_rn(t, t, splat2(-1.0f));                                         // -(1 - t^2)
+  const float2 pn = __ffma2_rn(splat2(-0.1070322243f), x2, splat2(-0.7978845608f));         // -(a + 3 b x^2)
+  g = __ffma2_rn(__fmul2_rn(hx, q), pn, __ffma2_rn(splat2(0.5f), t, splat2(0.5f)));
+}
+
 // Column sums over the 32 lanes (rows) of a warp for 16 columns held per lane: returns, in lane L, the total of
 // column (L & 15).  16 + 8 + 4 + 2 + 1 = 31 shuffles.
 __device__ __forceinline__ float warp_colsum16(float (&v)[16], int lane) {
