@@ -167,6 +167,17 @@ template <> struct LaneIO<T_BF16, 8> {
   }
 };
 
+// acc += x on register pairs (FADD2: IEEE per element, half the fp32 instructions of the accumulate)
+template <int V>
+__device__ __forceinline__ void add_vec(float (&acc)[V], const float (&x)[V]) {
+#pragma unroll
+  for (int j = 0; j < V; j += 2) {
+    const float2 r = __fadd2_rn(make_float2(acc[j], acc[j + 1]), make_float2(x[j], x[j + 1]));
+    acc[j] = r.x;
+    acc[j + 1] = r.y;
+  }
+}
+
 // lanes per row: 16 whenever a lane can move 16 bytes of the SOURCE row (bf16 512-col... i.e. 128 bf16 = 16 x 16 B, or
 // 64 fp32 = 16 x 16 B), else 32; the two half-warps of a 16-lane configuration run independent rows
 template <int W, class TS> struct PipeCfg { static constexpr int LPR = (W * (int)sizeof(typename TS::elem) >= 512) ? 32 : 16; };
@@ -235,8 +246,7 @@ __global__ void __launch_bounds__(256) pipe_reduce_kernel(const typename TS::ele
 #pragma unroll
           for (int j = 0; j < V; ++j) x[j] /= dv;
         }
-#pragma unroll
-        for (int j = 0; j < V; ++j) acc[j] += x[j];
+        add_vec<V>(acc, x);
       }
     }
     for (int t = NB; t < deg; ++t) {  // long rows: the rest, one at a time (entries beyond LPR straight from memory)
@@ -250,8 +260,7 @@ __global__ void __launch_bounds__(256) pipe_reduce_kernel(const typename TS::ele
 #pragma unroll
         for (int j = 0; j < V; ++j) x[j] /= dv;
       }
-#pragma unroll
-      for (int j = 0; j < V; ++j) acc[j] += x[j];
+      add_vec<V>(acc, x);
     }
     if (!INC && (flags & FVGN_ADJ_DIV_DST_BY_DEG)) {
       const float dd = (float)max(deg, 1);

@@ -83,8 +83,10 @@ def test_product_bf16_within_stated_tolerance(name):
     assert rep["decoder_out"] < 3e-2, rep["decoder_out"]
 
 
-def test_graphed_step_matches_eager_steps():
-    """GraphedTrainStep (whole fwd + bwd + Adam step as one CUDA graph) reproduces the eager training steps bit for bit."""
+@pytest.mark.parametrize("net", ["EPD", "TransFVGN_v2"])
+def test_graphed_step_matches_eager_steps(net):
+    """GraphedTrainStep (whole fwd + bwd + Adam step as one CUDA graph) reproduces the eager training steps bit for bit
+    (TransFVGN_v2: the Transolver kernels, their library GEMMs and the PyTorch token attention are captured too)."""
     import copy
     from gen_fvgn_steady_b200.FVMmodel.importer import NNmodel
     from gen_fvgn_steady_b200.graphed import GraphedTrainStep
@@ -94,7 +96,7 @@ def test_graphed_step_matches_eager_steps():
     PU.use_real_kernels()
     dev = torch.device("cuda")
     mesh, uvp = S.make_case(20, kind="mixed", bc="channel", seed=2)
-    p = default_params(net="EPD", message_passing_num=2, dataset_size=1, precision="bf16")
+    p = default_params(net=net, message_passing_num=2, dataset_size=1, precision="bf16")
     torch.manual_seed(0)
     model_a = NNmodel(p).to(dev)
     model_b = copy.deepcopy(model_a)
