@@ -162,3 +162,42 @@ def test_transolver_block_gpu_deterministic_and_shadow():
     assert all(torch.equal(a, b) for a, b in zip(outs[0][2], outs[1][2]))
     master, sh = blk.last_shadow
     assert master is out and torch.equal(sh, out.detach().to(torch.bfloat16))
+
+
+@pytest.mark.gpu
+def test_transolver_properties_at_scale():
+    """Size-independent properties at BASELINE's mesh scale (1 M node rows, 3 ragged graphs): slice weights are
+    distributions, the deterministic token sums and the de-slice equal their dense fp64 definitions
+    (GraphTransolver.py:62-90), and the whole backward is exactly linear in the cotangent (x2 is exact in fp32)."""
+    from gen_fvgn_steady_b200 import ops
+    sizes = (400_000, 250_001, 349_999)
+    blk, x, batch, cot = _block_and_inputs(sizes, "cuda", seed=5)
+    A = blk.Attn
+    tsp = ops.TsPlan.of(batch, None)
+    with torch.no_grad():
+        a, saved = ops._attn_forward(x, A.in_project_fx.weight, A.in_project_fx.bias, A.in_project_x.weight, A.in_project_x.bias,
+                                     A.in_project_slice.weight, A.in_project_slice.bias, A.graph_temperature, A.to_q.weight,
+                                     A.to_k.weight, A.to_v.weight, A.to_out[0].weight, A.scale, tsp, None)
+        _, P, sw, rec, tok_out, out_x = saved[:6]
+        n = x.shape[0]
+        s3 = sw.view(n, 8, 32)
+        assert float((s3.sum(-1) - 1).abs().max()) < 1e-5 and float(s3.min()) >= 0.0
+        fx = P[:, :128].view(n, 8, 16).double()
+        for b, (lo, hi) in enumerate(zip([0, sizes[0], sizes[0] + sizes[1]], [sizes[0], sizes[0] + sizes[1], n])):
+            sb = s3[lo:hi].double()
+            num = torch.einsum("nhg,nhd->hgd", sb, fx[lo:hi]).reshape(-1)
+            nrm = sb.sum(0).reshape(-1)
+            got = rec[b].double()
+            assert float((got[:4096] - num).norm() / num.norm()) < 1e-5
+            assert float((got[4096:] - nrm).norm() / nrm.norm()) < 1e-5
+            want = torch.einsum("nhg,hgd->nhd", sb, tok_out[b].view(8, 32, 16).double()).reshape(hi - lo, 128)
+            assert float((out_x[lo:hi].double() - want).norm() / want.norm()) < 1e-5
+    grads = []
+    for scale in (1.0, 2.0):
+        xr = x.clone().requires_grad_(True)
+        for p in blk.parameters():
+            p.grad = None
+        blk(xr, batch).backward(cot * scale)
+        grads.append([xr.grad.clone()] + [p.grad.clone() for p in blk.parameters() if p.grad is not None])
+    for g1, g2 in zip(*grads):
+        assert torch.equal(g1 * 2.0, g2)
