@@ -170,6 +170,12 @@ def new_z1(mode, precision, rows, like):
     return Z1Image(mode, rows, like.device) if precision == "bf16" else None
 
 
+def _z1_for(ctx, mode, precision, rows, like):
+    """The Z1 image is only needed by a backward pass: under torch.no_grad() / with nothing requiring a gradient (the
+    rollout regime of solve_without_grad_GPU.py) the forward kernel skips that store (256 B per row) altogether."""
+    return new_z1(mode, precision, rows, like) if any(ctx.needs_input_grad) else None
+
+
 def mlp_backward(mode, precision, rows, params, in0, in1, idx_s, idx_r, d_out, d_gather=None, d_in0=None, d_in1=None,
                  flags=0, packed=None, z1=None, in0h=None, in1h=None, d_in0h=None, d_gatherh=None):
     """Runs the fused backward; returns the list of parameter gradients (views of one flat buffer).
@@ -227,7 +233,7 @@ class EncoderFn(torch.autograd.Function):
         nb, eb = params[:8], params[8:]
         ctx.set_materialize_grads(False)  # no zero tensors for the (non-differentiable) bf16 shadow outputs
         ctx.pk = (_packed(_lib.FVGN_MLP_ENC_NODE, precision, nb), _packed(_lib.FVGN_MLP_ENC_EDGE, precision, eb))
-        ctx.z1 = (new_z1(_lib.FVGN_MLP_ENC_NODE, precision, plan.N, xn), new_z1(_lib.FVGN_MLP_ENC_EDGE, precision, plan.E, xn))
+        ctx.z1 = (_z1_for(ctx, _lib.FVGN_MLP_ENC_NODE, precision, plan.N, xn), _z1_for(ctx, _lib.FVGN_MLP_ENC_EDGE, precision, plan.E, xn))
         bf = precision == "bf16"
         rn = mlp_forward(_lib.FVGN_MLP_ENC_NODE, precision, plan.N, nb, xn, packed=ctx.pk[0], z1=ctx.z1[0], want_outh=bf)
         re = mlp_forward(_lib.FVGN_MLP_ENC_EDGE, precision, plan.E, eb, xn, pos, plan.edge_s, plan.edge_r, packed=ctx.pk[1],
@@ -278,7 +284,7 @@ class GnBlockFn(torch.autograd.Function):
         if precision == "bf16":
             xh = xh if xh is not None else shadow(x)
             eh = eh if eh is not None else shadow(e)
-            ctx.z1 = (new_z1(_lib.FVGN_MLP_EDGE, precision, plan.E, x), new_z1(_lib.FVGN_MLP_NODE, precision, plan.N, x))
+            ctx.z1 = (_z1_for(ctx, _lib.FVGN_MLP_EDGE, precision, plan.E, x), _z1_for(ctx, _lib.FVGN_MLP_NODE, precision, plan.N, x))
             aggh = adj_reduce(xh, plan, 128, out_dtype=BF16)
             _, e_out, e_newh, e_outh = mlp_forward(_lib.FVGN_MLP_EDGE, precision, plan.E, eb, None, e, plan.edge_s, plan.edge_r,
                                                    want_out=False, want_res=True, packed=ctx.pk[0], z1=ctx.z1[0], in0h=aggh,
@@ -348,7 +354,7 @@ class EdgeBlockFn(torch.autograd.Function):
         x, e = _c(x), _c(e)
         agg = adj_reduce(x, plan, 128)
         ctx.pk = _packed(_lib.FVGN_MLP_EDGE, precision, params)
-        ctx.z1 = new_z1(_lib.FVGN_MLP_EDGE, precision, plan.E, x)
+        ctx.z1 = _z1_for(ctx, _lib.FVGN_MLP_EDGE, precision, plan.E, x)
         e_new, _ = mlp_forward(_lib.FVGN_MLP_EDGE, precision, plan.E, params, agg, e, plan.edge_s, plan.edge_r,
                                flags=_lib.FVGN_MLP_NO_RESIDUAL, packed=ctx.pk, z1=ctx.z1)
         ctx.plan, ctx.precision = plan, precision
@@ -377,7 +383,7 @@ class NodeBlockFn(torch.autograd.Function):
         a1 = inc_reduce(e, plan, 64)
         a2 = adj_reduce(a1, plan, 64, _lib.FVGN_ADJ_DIV_DST_BY_DEG)
         ctx.pk = _packed(_lib.FVGN_MLP_NODE, precision, params)
-        ctx.z1 = new_z1(_lib.FVGN_MLP_NODE, precision, plan.N, x)
+        ctx.z1 = _z1_for(ctx, _lib.FVGN_MLP_NODE, precision, plan.N, x)
         x_new, _ = mlp_forward(_lib.FVGN_MLP_NODE, precision, plan.N, params, a2, x, flags=_lib.FVGN_MLP_NO_RESIDUAL,
                                packed=ctx.pk, z1=ctx.z1)
         ctx.plan, ctx.precision = plan, precision
@@ -406,7 +412,7 @@ class DecoderFn(torch.autograd.Function):
     def forward(ctx, x, xh, precision, *params):
         x = _c(x)
         ctx.pk = _packed(_lib.FVGN_MLP_DEC, precision, params)
-        ctx.z1 = new_z1(_lib.FVGN_MLP_DEC, precision, x.shape[0], x)
+        ctx.z1 = _z1_for(ctx, _lib.FVGN_MLP_DEC, precision, x.shape[0], x)
         ctx.precision = precision
         if precision == "bf16":
             xh = xh if xh is not None else shadow(x)
