@@ -201,3 +201,28 @@ def test_transolver_properties_at_scale():
         grads.append([xr.grad.clone()] + [p.grad.clone() for p in blk.parameters() if p.grad is not None])
     for g1, g2 in zip(*grads):
         assert torch.equal(g1 * 2.0, g2)
+
+
+@pytest.mark.parametrize("sizes", [(1,), (31, 33, 1), (5000, 0, 123), (300_000, 17)])
+def test_ts_plan_chunk_table(sizes):
+    """Host logic of the chunk table: chunks tile the rows in order, never straddle a graph (empty graphs get no chunk),
+    chunk_ptr groups them per graph; the batch vector must be sorted."""
+    from gen_fvgn_steady_b200 import ops
+    batch = torch.cat([torch.full((c,), b, dtype=torch.int64) for b, c in enumerate(sizes)])
+    tsp = ops.TsPlan(batch)
+    ch = tsp.chunks[:tsp.n_chunks].tolist()
+    ptr = tsp.chunk_ptr.tolist()
+    assert tsp.nseg == len(sizes) and tsp.nb == len(sizes) and len(ptr) == len(sizes) + 1 and ptr[-1] == tsp.n_chunks
+    pos = 0
+    for seg, r0, r1 in ch:
+        assert r0 == pos and r1 > r0 and (r1 - r0) <= 4096
+        assert int(batch[r0]) == seg and int(batch[r1 - 1]) == seg
+        pos = r1
+    assert pos == sum(sizes)
+    for b, c in enumerate(sizes):
+        rows = sum(r1 - r0 for seg, r0, r1 in ch[ptr[b]:ptr[b + 1]])
+        assert rows == c and all(seg == b for seg, _, _ in ch[ptr[b]:ptr[b + 1]])
+    assert tsp.all_ptr.tolist() == [0, tsp.n_chunks]
+    if len(sizes) > 1 and sizes[0] > 0 and sizes[1] > 0:
+        with pytest.raises(RuntimeError):
+            ops.TsPlan(torch.flip(batch, [0]))
