@@ -18,6 +18,9 @@ CASES = {
     # BASELINE.json configs[0]: the reference's own CPU-runnable Navier-Stokes case (N = 10 404 nodes, C = 10 201 cells)
     "lid_cavity_101_v2": dict(net="TransFVGN_v2", dataset_size=1,
                               mesh="example:lid_driven_cavity/lid_driven_cavity_101x101-Re=100/mesh.mphtxt"),
+    # BASELINE.json configs[2]: mixed tri/quad cylinder-flow example mesh (N = 11 923 nodes, C = 22 065 cells), pure GN net
+    "cylinder_tri_quad_v1": dict(net="TransFVGN_v1", dataset_size=1,
+                                 mesh="example:cylinder_flow_tri_quad/mesh.mphtxt"),
     "synth_ns_batch2_v2": dict(net="TransFVGN_v2", dataset_size=100, mesh=[
         dict(n=0, nx=10, ny=8, kind="mixed", bc="channel", seed=3,
              physics=dict(mean_u=1.5, mu=0.02, dt=0.4, aoa=0.0)),
