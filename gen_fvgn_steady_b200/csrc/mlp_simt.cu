@@ -51,7 +51,9 @@ __device__ __forceinline__ void gemm_tile(const float* In, int ldin, int K, cons
       float v;
       if (TRANS) {
         const int c = idx >> 4, kk = idx & 15;
-        v = (k0 + kk < K) ? Wg[(size_t)c * ldw + k0 + kk] : 0.f;
+        // K may be the zero-padded width of the input tile (layer 1 of the encoders: 12 / 15 -> 16): never read past a
+        // weight row -- the pad columns multiply zeros, but 0 x (NaN bits past the end of the tensor) is NaN
+        v = (k0 + kk < K && k0 + kk < ldw) ? Wg[(size_t)c * ldw + k0 + kk] : 0.f;
         Ws[kk * LDH + c] = v;
       } else {
         const int kk = idx >> 7, c = idx & 127;
