@@ -34,8 +34,9 @@ def parse_args():
     ap.add_argument("--cells", type=int, default=int(os.environ.get("FVGN_BENCH_CELLS", 4_000_000)))
     ap.add_argument("--net", default=os.environ.get("FVGN_BENCH_NET", "EPD"))
     ap.add_argument("--mp", type=int, default=int(os.environ.get("FVGN_BENCH_MP", 6)))
-    ap.add_argument("--precision", default=os.environ.get("FVGN_PRECISION", "bf16"), choices=["bf16", "fp32"],
-                    help="bf16: tcgen05 throughput mode (default); fp32: SIMT parity mode")
+    ap.add_argument("--precision", default=os.environ.get("FVGN_PRECISION", "bf16"), choices=["bf16", "f16", "fp32"],
+                    help="bf16 / f16: tcgen05 modes (f16 = IEEE-half operands, the 11-bit significand of the reference's TF32 "
+                         "GPU arithmetic); fp32: SIMT FMA mode")
     ap.add_argument("--cpu-cells", type=int, default=40_000, help="cell count of the bounded CPU-baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--graph", action="store_true",
@@ -314,7 +315,8 @@ def run_ours(args):
     line = {"metric": "cells*steps/sec (fwd+bwd train step)", "value": value, "unit": "cells*steps/s", "n_gpus": world,
             "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps, "higher_is_better": True,
             "scaling": "strong" if cells_mode else "weak", "vs_baseline": None,
-            "dtype": "f32" if args.precision == "fp32" else "bf16 (fp32 accumulate/storage)",
+            "dtype": {"fp32": "f32", "bf16": "bf16 operands and derived streams, f32 accumulate and residual streams",
+                      "f16": "f16 operands and derived streams (TF32-grade 11-bit significand), f32 accumulate and residual streams"}[args.precision],
             "data": "synthetic", "config": dict(workload_config(args, C_bench=C), N=N, E=E, C=C, K=K, X=X,
                                                 parallelism=(f"cells{world} (one {C_global}-cell mesh, RCB partition, "
                                                              f"{args.halo_layers}-layer halo, "
@@ -360,7 +362,9 @@ def dominant_kernel_roofline(model, plan, dev, args, p):
             blk = m
             break
     N, E = plan.N, plan.E
-    bf = args.precision == "bf16"
+    bf = ops.is_tc(args.precision)
+    prec = args.precision
+    hdt = ops.HDTYPE.get(prec)
     gen = torch.Generator(device=dev).manual_seed(1)
     agg = torch.randn((N, 128), device=dev, generator=gen)
     e = torch.randn((E, 128), device=dev, generator=gen)
@@ -370,14 +374,14 @@ def dominant_kernel_roofline(model, plan, dev, args, p):
     params = [q.detach() for q in mlp_params(blk.eb_module.net)]
     code = _lib.FVGN_MLP_EDGE
     if bf:
-        aggh, eh = ops.shadow(agg), ops.shadow(e)
+        aggh, eh = ops.shadow(agg, dtype=hdt), ops.shadow(e, dtype=hdt)
         del agg, e
-        z1 = ops.new_z1(code, "bf16", E, d_out)
-        ops.mlp_forward(code, "bf16", E, params, None, None, plan.edge_s, plan.edge_r, want_out=False, want_res=False, z1=z1,
+        z1 = ops.new_z1(code, prec, E, d_out)
+        ops.mlp_forward(code, prec, E, params, None, None, plan.edge_s, plan.edge_r, want_out=False, want_res=False, z1=z1,
                         in0h=aggh, in1h=eh, want_outh=True)
-        d_srh = torch.empty((E, 256), device=dev, dtype=torch.bfloat16)
-        d_a1h = d_a1.bfloat16()
-        run = lambda: ops.mlp_backward(code, "bf16", E, params, None, None, plan.edge_s, plan.edge_r, d_out, None, None, d_e,
+        d_srh = torch.empty((E, 256), device=dev, dtype=hdt)
+        d_a1h = d_a1.to(hdt)
+        run = lambda: ops.mlp_backward(code, prec, E, params, None, None, plan.edge_s, plan.edge_r, d_out, None, None, d_e,
                                        z1=z1, in0h=aggh, in1h=eh, d_in0h=d_srh, d_gatherh=d_a1h)
     else:
         d_sr = torch.empty((E, 256), device=dev)
@@ -394,7 +398,7 @@ def dominant_kernel_roofline(model, plan, dev, args, p):
             times.append(ev0.elapsed_time(ev1))
     ms = float(np.mean(times))
     alg = E * (3 * 512 + 1024) + N * (512 + 256)
-    tpe = NCU_TRAFFIC_BYTES_PER_EDGE.get(args.precision)
+    tpe = NCU_TRAFFIC_BYTES_PER_EDGE.get("bf16" if bf else args.precision)
     return {"kernel": "mlp_bwd_kernel<EDGE> (fused edge-MLP backward: recompute + dgrad + wgrad)" if not bf
             else "fvgn_mlp_backward<EDGE> = mlp_tc_bwd_a_kernel<0> + mlp_tc_bwd_b_kernel<0> (tcgen05)", "bound": "hbm",
             "achieved": alg / (ms / 1e3) / 1e9, "unit": "GB/s", "ms_per_launch": ms, "alg_bytes_per_launch": alg,

@@ -38,7 +38,8 @@ class Graph_Physics_Attention_1D(nn.Module):
         return ops.SliceAttentionFn.apply(x, self.in_project_fx.weight, self.in_project_fx.bias, self.in_project_x.weight,
                                           self.in_project_x.bias, self.in_project_slice.weight, self.in_project_slice.bias,
                                           self.graph_temperature, self.to_q.weight, self.to_k.weight, self.to_v.weight,
-                                          self.to_out[0].weight, self.scale, tsp, halo)
+                                          self.to_out[0].weight, self.scale, tsp, halo,
+                                          getattr(self, "precision", None) or ops.default_precision())
 
     def graph_forward(self, x, batch, graph_ptr=None, halo=None):
         """GraphTransolver.py:48-95: x[N,128], batch[N] (sorted by graph) -> [N,128].
@@ -83,7 +84,8 @@ class Transolver_block(nn.Module):
         latent.x and the node embedding separately so that the sum and its gradient stay inside the fused op).
         In bf16 mode the last kernel also emits the bf16 shadow of the result (`self.last_shadow = (out, shadow)`) for
         the GnBlock / decoder that consumes it."""
-        want_shadow = (getattr(self, "precision", None) or ops.default_precision()) == "bf16"
+        precision = getattr(self, "precision", None) or ops.default_precision()
+        want_shadow = ops.HDTYPE.get(precision)   # None (fp32 mode) or the 16-bit dtype of the tensor-core mode
         A, m = self.Attn, self.mlp
         tail = (A.to_out[0].bias, self.ln_2.weight, self.ln_2.bias, m.linear_pre[0].weight, m.linear_pre[0].bias,
                 m.linear_post.weight, m.linear_post.bias)
@@ -97,5 +99,5 @@ class Transolver_block(nn.Module):
                 fx, embedding, A.in_project_fx.weight, A.in_project_fx.bias, A.in_project_x.weight, A.in_project_x.bias,
                 A.in_project_slice.weight, A.in_project_slice.bias, A.graph_temperature, A.to_q.weight, A.to_k.weight,
                 A.to_v.weight, A.to_out[0].weight, *tail, A.scale, ops.TsPlan.of(batch, halo), halo, want_shadow)
-        self.last_shadow = (out, outh) if want_shadow else None
+        self.last_shadow = (out, outh) if want_shadow is not None else None
         return out

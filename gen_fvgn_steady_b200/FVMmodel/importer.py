@@ -57,7 +57,8 @@ class NNmodel(nn.Module):
         self.dp_group = group
 
     def set_precision(self, precision):
-        """'fp32' (SIMT, parity) or 'bf16' (tcgen05, throughput).  None -> $FVGN_PRECISION or fp32."""
+        """'fp32' (SIMT FMA), 'bf16' or 'f16' (tcgen05; f16 = IEEE-half operands, the 11-bit significand of the TF32
+        arithmetic the reference's GPU path uses, with power-of-two gradient pre-scaling).  None -> $FVGN_PRECISION or fp32."""
         precision = precision or ops.default_precision()
         if precision not in ops.PREC:
             raise ValueError(precision)
@@ -139,6 +140,8 @@ class NNmodel(nn.Module):
         graph_node.norm_uvp = False
         graph_node.norm_global = False
         raw = self.simulator(graph_node, graph_edge, graph_cell)
+        if self.precision == "f16" and torch.is_grad_enabled():
+            raw = ops.GradScaleFn.apply(raw)   # backward: gradient operands of the half-precision MMAs are kept in range
         phi = ops.HeadFn.apply(raw, uv_old, plan.y, plan.node_type, ops.INTEGRATORS[params.integrator])
         out_scale = (graph_Index.uvp_dim * graph_Index.sigma).float()
         losses, uvp_node, uvp_cell, grad_phi = ops.FVLossFn.apply(

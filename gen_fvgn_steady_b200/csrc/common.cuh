@@ -28,6 +28,25 @@ enum { NT_NORMAL = 0, NT_INFLOW = 1, NT_OUTFLOW = 2, NT_WALL = 3, NT_PRESS_POINT
 
 static inline int fvgn_aligned16(const void* p) { return (((uintptr_t)p) & 15) == 0; }
 
+#ifndef FVGN_EMU
+// per-device caches (one process may drive several GPUs): current device index and its SM count
+#define FVGN_MAX_DEV 64
+static inline int fvgn_cur_device() {
+  int dev = 0;
+  cudaGetDevice(&dev);
+  return dev & (FVGN_MAX_DEV - 1);
+}
+static inline int fvgn_num_sms() {
+  static int n[FVGN_MAX_DEV] = {0};
+  const int dev = fvgn_cur_device();
+  if (n[dev] == 0) {
+    cudaDeviceGetAttribute(&n[dev], cudaDevAttrMultiProcessorCount, dev);
+    if (n[dev] <= 0) n[dev] = 148;
+  }
+  return n[dev];
+}
+#endif
+
 __device__ __forceinline__ float4 ld4(const float* p) { return *reinterpret_cast<const float4*>(p); }
 __device__ __forceinline__ void st4(float* p, float4 v) { *reinterpret_cast<float4*>(p) = v; }
 __device__ __forceinline__ float4 add4(float4 a, float4 b) { return make_float4(a.x + b.x, a.y + b.y, a.z + b.z, a.w + b.w); }

@@ -12,8 +12,10 @@ int fvgn_mlp_backward_tc(const fvgn_mlp_desc* d, void* stream);
 int fvgn_mlp_tc_partials(int32_t mode, int64_t rows);
 int64_t fvgn_mlp_tc_packed_bytes(int32_t mode);
 int64_t fvgn_mlp_tc_workspace_bytes(int32_t mode, int64_t rows);
-int fvgn_mlp_tc_pack(int32_t mode, const float* w1, const float* w2, const float* w3, void* packed, void* stream);
+int fvgn_mlp_tc_pack(int32_t mode, int32_t precision, const float* w1, const float* w2, const float* w3, void* packed, void* stream);
 #endif
+
+static inline bool is_tc(int32_t precision) { return precision == FVGN_PREC_BF16 || precision == FVGN_PREC_F16; }
 
 extern "C" int fvgn_version(void) {
 #ifdef FVGN_EMU
@@ -27,7 +29,7 @@ extern "C" int64_t fvgn_mlp_param_count(int32_t mode) { return fvgn_mlp_param_co
 
 extern "C" int32_t fvgn_mlp_bwd_partials(int32_t mode, int32_t precision, int64_t rows) {
 #ifndef FVGN_EMU
-  if (precision == FVGN_PREC_BF16) return fvgn_mlp_tc_partials(mode, rows);
+  if (is_tc(precision)) return fvgn_mlp_tc_partials(mode, rows);
 #endif
   (void)mode;
   (void)precision;
@@ -36,7 +38,7 @@ extern "C" int32_t fvgn_mlp_bwd_partials(int32_t mode, int32_t precision, int64_
 
 extern "C" int64_t fvgn_mlp_bwd_workspace_bytes(int32_t mode, int32_t precision, int64_t rows) {
 #ifndef FVGN_EMU
-  if (precision == FVGN_PREC_BF16) return fvgn_mlp_tc_workspace_bytes(mode, rows);
+  if (is_tc(precision)) return fvgn_mlp_tc_workspace_bytes(mode, rows);
 #endif
   (void)mode; (void)precision; (void)rows;
   return 0;
@@ -51,12 +53,13 @@ extern "C" int64_t fvgn_mlp_packed_bytes(int32_t mode) {
 #endif
 }
 
-extern "C" int fvgn_mlp_pack_weights(int32_t mode, const float* w1, const float* w2, const float* w3, void* packed,
-                                     void* stream) {
+extern "C" int fvgn_mlp_pack_weights(int32_t mode, int32_t precision, const float* w1, const float* w2, const float* w3,
+                                     void* packed, void* stream) {
 #ifndef FVGN_EMU
-  return fvgn_mlp_tc_pack(mode, w1, w2, w3, packed, stream);
+  if (!is_tc(precision)) return FVGN_ERR_UNSUPPORTED;
+  return fvgn_mlp_tc_pack(mode, precision, w1, w2, w3, packed, stream);
 #else
-  (void)mode; (void)w1; (void)w2; (void)w3; (void)packed; (void)stream;
+  (void)mode; (void)precision; (void)w1; (void)w2; (void)w3; (void)packed; (void)stream;
   return FVGN_ERR_UNSUPPORTED;
 #endif
 }
@@ -68,7 +71,7 @@ static int check_common(const fvgn_mlp_desc* d) {
   if (!d->w1 || !d->b1 || !d->w2 || !d->b2 || !d->w3 || !d->b3) return FVGN_ERR_NULL;
   if (d->mode != FVGN_MLP_DEC && (!d->ln_g || !d->ln_b)) return FVGN_ERR_NULL;
   // bf16 mode reads the layer-1 operands of EDGE / NODE / DEC from the bf16 shadows; fp32 in0 / in1 are then optional
-  const bool shadow = d->precision == FVGN_PREC_BF16 &&
+  const bool shadow = is_tc(d->precision) &&
                       (d->mode == FVGN_MLP_EDGE || d->mode == FVGN_MLP_NODE || d->mode == FVGN_MLP_DEC);
   if (shadow) {
     if (!d->in0h) return FVGN_ERR_NULL;
@@ -96,7 +99,7 @@ extern "C" int fvgn_mlp_forward(const fvgn_mlp_desc* d, void* stream) {
   if (d->rows == 0) return FVGN_OK;
   if (d->precision == FVGN_PREC_FP32) return fvgn_mlp_forward_simt(d, stream);
 #ifndef FVGN_EMU
-  if (d->precision == FVGN_PREC_BF16) return fvgn_mlp_forward_tc(d, stream);
+  if (is_tc(d->precision)) return fvgn_mlp_forward_tc(d, stream);
 #endif
   return FVGN_ERR_UNSUPPORTED;
 }
@@ -116,7 +119,7 @@ extern "C" int fvgn_mlp_backward(const fvgn_mlp_desc* d, void* stream) {
   if (rc) return rc;
   if (!d->d_out || !d->partials || !d->d_params || d->n_partials < 1) return FVGN_ERR_NULL;
   if ((d->mode == FVGN_MLP_EDGE || d->mode == FVGN_MLP_NODE) && ((!d->d_in0 && !d->d_in0h) || !d->d_in1)) return FVGN_ERR_NULL;
-  if ((d->d_in0h || d->d_gatherh) && d->precision != FVGN_PREC_BF16) return FVGN_ERR_UNSUPPORTED;
+  if ((d->d_in0h || d->d_gatherh) && !is_tc(d->precision)) return FVGN_ERR_UNSUPPORTED;
   if (d->d_in0h && d->mode != FVGN_MLP_EDGE && d->mode != FVGN_MLP_NODE) return FVGN_ERR_UNSUPPORTED;
   if (!fvgn_aligned16(d->d_gatherh)) return FVGN_ERR_ALIGN;
   if (d->mode == FVGN_MLP_DEC && !d->d_in0) return FVGN_ERR_NULL;
@@ -125,7 +128,7 @@ extern "C" int fvgn_mlp_backward(const fvgn_mlp_desc* d, void* stream) {
     return fvgn_mlp_backward_simt(d, stream);
   }
 #ifndef FVGN_EMU
-  if (d->precision == FVGN_PREC_BF16) return fvgn_mlp_backward_tc(d, stream);
+  if (is_tc(d->precision)) return fvgn_mlp_backward_tc(d, stream);
 #endif
   return FVGN_ERR_UNSUPPORTED;
 }

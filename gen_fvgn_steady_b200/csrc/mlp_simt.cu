@@ -496,11 +496,12 @@ int launch_fwd(const fvgn_mlp_desc& d, void* stream) {
   const unsigned grid = (unsigned)(ntiles < kMaxCtasFwd ? ntiles : kMaxCtasFwd);
   auto kern = mlp_fwd_kernel<MODE>;
 #ifndef FVGN_EMU
-  static bool attr_set = false;
-  if (!attr_set) {
+  static bool attr_set[FVGN_MAX_DEV] = {false};  // the attribute is per device
+  const int dev = fvgn_cur_device();
+  if (!attr_set[dev]) {
     if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fwd_smem<MODE>()) != cudaSuccess)
       return FVGN_ERR_LAUNCH;
-    attr_set = true;
+    attr_set[dev] = true;
   }
 #endif
   FVGN_LAUNCH(kern, grid, NT, fwd_smem<MODE>(), stream, d);
@@ -512,11 +513,12 @@ template <int MODE>
 int launch_bwd(const fvgn_mlp_desc& d, void* stream) {
   auto kern = mlp_bwd_kernel<MODE>;
 #ifndef FVGN_EMU
-  static bool attr_set = false;
-  if (!attr_set) {
+  static bool attr_set[FVGN_MAX_DEV] = {false};  // the attribute is per device
+  const int dev = fvgn_cur_device();
+  if (!attr_set[dev]) {
     if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bwd_smem<MODE>()) != cudaSuccess)
       return FVGN_ERR_LAUNCH;
-    attr_set = true;
+    attr_set[dev] = true;
   }
 #endif
   FVGN_LAUNCH(kern, (unsigned)d.n_partials, NT, bwd_smem<MODE>(), stream, d);

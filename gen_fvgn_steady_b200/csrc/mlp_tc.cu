@@ -1,5 +1,6 @@
-// Fused 3-layer MLP blocks on 5th-gen tensor cores (FVGN_PREC_BF16): tcgen05.mma kind::f16, bf16 operands,
-// fp32 accumulators in TMEM, fp32 bias / GELU / LayerNorm / residual, fp32 activations in HBM.
+// Fused 3-layer MLP blocks on 5th-gen tensor cores (FVGN_PREC_BF16 / FVGN_PREC_F16): tcgen05.mma kind::f16, 16-bit
+// operands (bf16, or IEEE half = the 11-bit significand of TF32), fp32 accumulators in TMEM, fp32 bias / GELU /
+// LayerNorm / residual, fp32 residual streams in HBM.
 //
 // Persistent kernel, one CTA per SM, tile = 128 rows (UMMA M=128, N=128, K=16):
 //   warps 4-7  producers : gather the input rows (edge endpoints / concatenations / relative edge features),
@@ -35,6 +36,7 @@ template <int MODE> constexpr int smem_bytes() {
 
 // ------------------------------------------------------------------------------------------ weight image
 // image = [W1 K-blocks][W2: 2 K-blocks][W3: 2 K-blocks], each K-block 128 rows x 64 k, bf16, pre-swizzled
+template <class P>
 __global__ void pack_weights_kernel(const float* __restrict__ w1, const float* __restrict__ w2, const float* __restrict__ w3,
                                     int k1, int k1p, int nout, uint8_t* __restrict__ img) {
   const int nkb = nkb1(k1p);
@@ -59,7 +61,7 @@ __global__ void pack_weights_kernel(const float* __restrict__ w1, const float* _
         }
         v[h] = x;
       }
-      packed[j] = pack_bf16(v[0], v[1]);
+      packed[j] = pack16<P>(v[0], v[1]);
     }
     *reinterpret_cast<uint4*>(img + (size_t)kb * KB_BYTES + sw128_off(row, chunk)) =
         make_uint4(packed[0], packed[1], packed[2], packed[3]);
@@ -92,9 +94,10 @@ __device__ unsigned long long g_prof_f[16];
 #define PROF_F(i) do { } while (0)
 #endif
 
-template <int MODE>
+template <int MODE, class P>
 __global__ void __launch_bounds__(NTHREADS, 1) mlp_tc_fwd_kernel(const fvgn_mlp_desc d) {
   using C = TCfg<MODE>;
+  constexpr uint32_t IDESC = make_idesc(P::FMT, 128, 0, 0);
   constexpr int NKB1 = nkb1(C::K1P);
   constexpr int LASTK = (C::K1P - 64 * (NKB1 - 1)) / 16;  // MMAs (K=16) in the last K-block of layer 1
   constexpr int NSTAGE = C::NSTAGE;
@@ -222,7 +225,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) mlp_tc_fwd_kernel(const fvgn_mlp_
         for (int kb = 0; kb < NKB1; ++kb, ++it) {
           const int s = it % NSTAGE;
           mbar_wait(BAR(B_EMPTY + s), ((it / NSTAGE) & 1) ^ 1);
-          produce_chunk<MODE>(d, row0, kb, ring + s * KB_BYTES, pw, lane, idx);
+          produce_chunk<MODE, P>(d, row0, kb, ring + s * KB_BYTES, pw, lane, idx);
           fence_proxy_async();
           __syncwarp();
           if (lane == 0) mbar_arrive(BAR(B_FULL + s));
@@ -300,12 +303,12 @@ __global__ void __launch_bounds__(NTHREADS, 1) mlp_tc_fwd_kernel(const fvgn_mlp_
 #pragma unroll
             for (int j = 0; j < 8; ++j) {
 #if FVGN_F32X2
-              zw[j] = pack_bf16(z[j]);
-              z[j] = bf16x2_f2(zw[j]);
+              zw[j] = pack16<P>(z[j]);
+              z[j] = unpack16<P>(zw[j]);
 #else
-              zw[j] = pack_bf16(z[2 * j], z[2 * j + 1]);
-              z[2 * j] = bf16_lo(zw[j]);
-              z[2 * j + 1] = bf16_hi(zw[j]);
+              zw[j] = pack16<P>(z[2 * j], z[2 * j + 1]);
+              z[2 * j] = P::lo(zw[j]);
+              z[2 * j + 1] = P::hi(zw[j]);
 #endif
             }
             if (zimg) {
@@ -327,9 +330,9 @@ __global__ void __launch_bounds__(NTHREADS, 1) mlp_tc_fwd_kernel(const fvgn_mlp_
           }
 #pragma unroll
 #if FVGN_F32X2
-          for (int j = 0; j < 8; ++j) w[j] = pack_bf16(gelu_tanh2(z[j]));
+          for (int j = 0; j < 8; ++j) w[j] = pack16<P>(gelu_tanh2(z[j]));
 #else
-          for (int j = 0; j < 8; ++j) w[j] = pack_bf16(gelu_tanh(z[2 * j]), gelu_tanh(z[2 * j + 1]));
+          for (int j = 0; j < 8; ++j) w[j] = pack16<P>(gelu_tanh(z[2 * j]), gelu_tanh(z[2 * j + 1]));
 #endif
           tmem_st8(acc + c0 / 2, w);  // in place: always behind the columns still to be read (and the one in flight)
         });
@@ -426,12 +429,12 @@ __global__ void __launch_bounds__(NTHREADS, 1) mlp_tc_fwd_kernel(const fvgn_mlp_
               const float4 y = *reinterpret_cast<const float4*>(wstg_at(mystg, rr, oseg));
               const size_t o = (size_t)row * 128 + c0 + oseg * 4;
               if (d.out) *reinterpret_cast<float4*>(d.out + o) = y;
-              if (outh) *reinterpret_cast<uint2*>(outh + o) = make_uint2(pack_bf16(y.x, y.y), pack_bf16(y.z, y.w));
+              if (outh) *reinterpret_cast<uint2*>(outh + o) = make_uint2(pack16<P>(y.x, y.y), pack16<P>(y.z, y.w));
               if (do_res) {
                 const float4 x = xr[ps];
                 const float4 t = make_float4(x.x + y.x, x.y + y.y, x.z + y.z, x.w + y.w);
                 *reinterpret_cast<float4*>(d.out_res + o) = t;
-                if (out_resh) *reinterpret_cast<uint2*>(out_resh + o) = make_uint2(pack_bf16(t.x, t.y), pack_bf16(t.z, t.w));
+                if (out_resh) *reinterpret_cast<uint2*>(out_resh + o) = make_uint2(pack16<P>(t.x, t.y), pack16<P>(t.z, t.w));
               }
             }
           }
@@ -463,22 +466,17 @@ __global__ void __launch_bounds__(NTHREADS, 1) mlp_tc_fwd_kernel(const fvgn_mlp_
   }
 }
 
-template <int MODE>
+template <int MODE, class P>
 int launch_tc_fwd(const fvgn_mlp_desc& d, void* stream) {
-  auto kern = mlp_tc_fwd_kernel<MODE>;
-  static bool attr_set = false;
-  if (!attr_set) {
+  auto kern = mlp_tc_fwd_kernel<MODE, P>;
+  static bool attr_set[FVGN_MAX_DEV] = {false};  // the attribute is per device
+  const int dev = fvgn_cur_device();
+  if (!attr_set[dev]) {
     if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes<MODE>()) != cudaSuccess)
       return FVGN_ERR_LAUNCH;
-    attr_set = true;
+    attr_set[dev] = true;
   }
-  static int num_sms = 0;
-  if (num_sms == 0) {
-    int dev = 0;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev);
-    if (num_sms <= 0) num_sms = 148;
-  }
+  const int num_sms = fvgn_num_sms();
   const int64_t ntiles = (d.rows + TILE_M - 1) / TILE_M;
   const unsigned grid = (unsigned)(ntiles < num_sms ? ntiles : num_sms);
   kern<<<grid, NTHREADS, smem_bytes<MODE>(), (cudaStream_t)stream>>>(d);
@@ -502,13 +500,16 @@ extern "C" int fvgn_debug_profile_f(unsigned long long* out16, int reset) {
 int fvgn_mlp_forward_tc(const fvgn_mlp_desc* d, void* stream) {
   if (!d->w_bf16) return FVGN_ERR_NULL;
   if ((((uintptr_t)d->w_bf16) & 15) != 0) return FVGN_ERR_ALIGN;
+  const bool f16 = d->precision == FVGN_PREC_F16;
+#define FVGN_TC_FWD_CASE(M) case M: return f16 ? launch_tc_fwd<M, PF16>(*d, stream) : launch_tc_fwd<M, PBF16>(*d, stream);
   switch (d->mode) {
-    case FVGN_MLP_EDGE: return launch_tc_fwd<FVGN_MLP_EDGE>(*d, stream);
-    case FVGN_MLP_NODE: return launch_tc_fwd<FVGN_MLP_NODE>(*d, stream);
-    case FVGN_MLP_ENC_NODE: return launch_tc_fwd<FVGN_MLP_ENC_NODE>(*d, stream);
-    case FVGN_MLP_ENC_EDGE: return launch_tc_fwd<FVGN_MLP_ENC_EDGE>(*d, stream);
-    case FVGN_MLP_DEC: return launch_tc_fwd<FVGN_MLP_DEC>(*d, stream);
+    FVGN_TC_FWD_CASE(FVGN_MLP_EDGE)
+    FVGN_TC_FWD_CASE(FVGN_MLP_NODE)
+    FVGN_TC_FWD_CASE(FVGN_MLP_ENC_NODE)
+    FVGN_TC_FWD_CASE(FVGN_MLP_ENC_EDGE)
+    FVGN_TC_FWD_CASE(FVGN_MLP_DEC)
   }
+#undef FVGN_TC_FWD_CASE
   return FVGN_ERR_UNSUPPORTED;
 }
 
@@ -523,7 +524,8 @@ int64_t fvgn_mlp_tc_packed_bytes(int32_t mode) {
   return -1;
 }
 
-int fvgn_mlp_tc_pack(int32_t mode, const float* w1, const float* w2, const float* w3, void* packed, void* stream) {
+int fvgn_mlp_tc_pack(int32_t mode, int32_t precision, const float* w1, const float* w2, const float* w3, void* packed,
+                     void* stream) {
   int k1, k1p, nout = 128;
   switch (mode) {
     case FVGN_MLP_EDGE: k1 = 384; k1p = 384; break;
@@ -534,7 +536,10 @@ int fvgn_mlp_tc_pack(int32_t mode, const float* w1, const float* w2, const float
     default: return FVGN_ERR_UNSUPPORTED;
   }
   if (!w1 || !w2 || !w3 || !packed) return FVGN_ERR_NULL;
-  pack_weights_kernel<<<64, 256, 0, (cudaStream_t)stream>>>(w1, w2, w3, k1, k1p, nout, reinterpret_cast<uint8_t*>(packed));
+  if (precision == FVGN_PREC_F16)
+    pack_weights_kernel<PF16><<<64, 256, 0, (cudaStream_t)stream>>>(w1, w2, w3, k1, k1p, nout, reinterpret_cast<uint8_t*>(packed));
+  else
+    pack_weights_kernel<PBF16><<<64, 256, 0, (cudaStream_t)stream>>>(w1, w2, w3, k1, k1p, nout, reinterpret_cast<uint8_t*>(packed));
   FVGN_CHECK_LAUNCH();
   return FVGN_OK;
 }

@@ -36,11 +36,6 @@ __host__ __device__ inline int64_t pcount(int k1, int nout, bool ln) {
   return (int64_t)128 * k1 + 128 + 128 * 128 + 128 + (int64_t)nout * 128 + nout + (ln ? 256 : 0);
 }
 
-constexpr uint32_t IDESC_KK = make_idesc(128, 0, 0);
-constexpr uint32_t IDESC_MM = make_idesc(128, 1, 1);
-constexpr uint32_t IDESC_KM = make_idesc(128, 0, 1);
-constexpr uint32_t IDESC_MM64 = make_idesc(64, 1, 1);
-constexpr uint32_t IDESC_KM64 = make_idesc(64, 0, 1);
 
 // write 16 consecutive columns [c0, c0+16) of row `row` as bf16 into a [128x128] swizzled tile
 __device__ __forceinline__ void store_tile16(uint8_t* buf, int row, int c0, const uint32_t (&w)[8]) {
@@ -68,17 +63,10 @@ __device__ __forceinline__ void load_tile16(const uint8_t* buf, int row, int c0,
 #define FVGN_BWD_A_EPI_WARPS 8
 #endif
 constexpr int A_NEW = FVGN_BWD_A_EPI_WARPS;
-// FVGN_GELU_PACKED = 1: E1 / E2 evaluate gelu and gelu' with packed bf16x2 arithmetic (12 instructions per PAIR instead
-// of 26).  Measured on B200: the kernel gets only 1.5-3 % faster (E1 / E2 are a quarter of the tile time) while the worst
-// parameter-gradient error of the bf16 golden run grows from 3.5e-2 to 1.1e-1 (a LayerNorm gamma), so the default stays
-// the fp32 evaluation with one rounding at the end.
 // FVGN_COLSUM_PACKED = 1 adds four rows of a bias-gradient column sum as packed bf16x2 before going to fp32 (fewer
 // instructions, measured: no change of the golden-run gradient errors, 1 % faster); 0 = plain fp32 accumulation.
 #ifndef FVGN_COLSUM_PACKED
 #define FVGN_COLSUM_PACKED 1
-#endif
-#ifndef FVGN_GELU_PACKED
-#define FVGN_GELU_PACKED 0
 #endif
 #ifdef FVGN_TIMING
 // debug build: cycle breakdown of kernel A's per-tile chain, summed over the tiles of CTA 0 (thread 0 only)
@@ -100,12 +88,7 @@ template <int N> __device__ __forceinline__ void epi_bar_sync_n() { asm volatile
 
 // column sums of a bf16 tile by the epilogue threads: thread t owns column pair (2p, 2p+1), p = t & 63, rows [ROWS*(t>>6), +ROWS).
 // Accumulated in fp32 (or, FVGN_COLSUM_PACKED, four rows at a time as packed bf16x2).
-__device__ __forceinline__ uint32_t hadd2_bf16(uint32_t a, uint32_t b) {
-  uint32_t r;
-  asm("add.rn.bf16x2 %0, %1, %2;" : "=r"(r) : "r"(a), "r"(b));
-  return r;
-}
-template <int ROWS>
+template <int ROWS, class P>
 __device__ __forceinline__ void tile_colsum_n(const uint8_t* buf, int t, float& s0, float& s1) {
   const int p = t & 63, r0 = (t >> 6) * ROWS;
   const int kb = (2 * p) >> 6, chunk = ((2 * p) & 63) >> 3, word = p & 3;
@@ -118,21 +101,23 @@ __device__ __forceinline__ void tile_colsum_n(const uint8_t* buf, int t, float& 
     const uint32_t w2 = *reinterpret_cast<const uint32_t*>(base + sw128_off(r + 2, chunk));
     const uint32_t w3 = *reinterpret_cast<const uint32_t*>(base + sw128_off(r + 3, chunk));
 #if FVGN_COLSUM_PACKED
-    const uint32_t w = hadd2_bf16(hadd2_bf16(w0, w1), hadd2_bf16(w2, w3));  // two extra bf16 roundings per 4 rows
-    a += bf16_lo(w);
-    b += bf16_hi(w);
+    const uint32_t w = P::add2(P::add2(w0, w1), P::add2(w2, w3));  // two extra bf16 roundings per 4 rows
+    a += P::lo(w);
+    b += P::hi(w);
 #else
-    a += (bf16_lo(w0) + bf16_lo(w1)) + (bf16_lo(w2) + bf16_lo(w3));        // exact fp32 accumulation of the bf16 tile
-    b += (bf16_hi(w0) + bf16_hi(w1)) + (bf16_hi(w2) + bf16_hi(w3));
+    a += (P::lo(w0) + P::lo(w1)) + (P::lo(w2) + P::lo(w3));        // exact fp32 accumulation of the bf16 tile
+    b += (P::hi(w0) + P::hi(w1)) + (P::hi(w2) + P::hi(w3));
 #endif
   }
   s0 += a;
   s1 += b;
 }
 
-template <int MODE>
+template <int MODE, class P>
 __global__ void __launch_bounds__(A_THREADS, 1) mlp_tc_bwd_a_kernel(const fvgn_mlp_desc d) {
   using C = BCfg<MODE>;
+  constexpr uint32_t IDESC_KK = make_idesc(P::FMT, 128, 0, 0), IDESC_MM = make_idesc(P::FMT, 128, 1, 1),
+                     IDESC_KM = make_idesc(P::FMT, 128, 0, 1);
   constexpr uint32_t DW2 = 0, DW3 = 128, WACC = 256, G1 = 384, G2 = 448;
   constexpr int NEW = A_NEW;               // epilogue warps
   constexpr int CSPLIT = NEW / 4;          // threads per row (column groups)
@@ -141,7 +126,7 @@ __global__ void __launch_bounds__(A_THREADS, 1) mlp_tc_bwd_a_kernel(const fvgn_m
   constexpr int RG = A_EPI / 64;           // row groups of the column sums
   constexpr int W_PROD = NEW, W_MMA = NEW + 4, W_LD = NEW + 5;
   auto epi_bar = [] { epi_bar_sync_n<A_EPI>(); };
-  auto colsum = [](const uint8_t* buf, int t, float& s0, float& s1) { tile_colsum_n<CS_ROWS>(buf, t, s0, s1); };
+  auto colsum = [](const uint8_t* buf, int t, float& s0, float& s1) { tile_colsum_n<CS_ROWS, P>(buf, t, s0, s1); };
   FVGN_DYN_SMEM(smem);
   uint8_t* w23 = smem;                              // W2 image | W3 image (64 KB)
   uint8_t* bufZ = w23 + 4 * KB_BYTES;               // 2 x [Z1 -> H1 -> dZ1] tile
@@ -160,8 +145,8 @@ __global__ void __launch_bounds__(A_THREADS, 1) mlp_tc_bwd_a_kernel(const fvgn_m
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int64_t ntiles = (d.rows + TILE_M - 1) / TILE_M;
   const int64_t PC = pcount(C::K1, C::NOUT, C::LN);
-  float* P = d.partials + (size_t)blockIdx.x * PC;
-  float* Pb1 = P + 128 * C::K1;
+  float* Pbase = d.partials + (size_t)blockIdx.x * PC;
+  float* Pb1 = Pbase + 128 * C::K1;
   float* Pw2 = Pb1 + 128;
   float* Pb2 = Pw2 + 128 * 128;
   float* Pw3 = Pb2 + 128;
@@ -306,10 +291,10 @@ __global__ void __launch_bounds__(A_THREADS, 1) mlp_tc_bwd_a_kernel(const fvgn_m
               }
 #pragma unroll
               for (int j = 0; j < NR; ++j) {
-                lo[j] = make_float4(lo[j].x + bf16_lo(gv[j].x), lo[j].y + bf16_hi(gv[j].x), lo[j].z + bf16_lo(gv[j].y),
-                                    lo[j].w + bf16_hi(gv[j].y));
-                hi[j] = make_float4(hi[j].x + bf16_lo(gv[j].z), hi[j].y + bf16_hi(gv[j].z), hi[j].z + bf16_lo(gv[j].w),
-                                    hi[j].w + bf16_hi(gv[j].w));
+                lo[j] = make_float4(lo[j].x + P::lo(gv[j].x), lo[j].y + P::hi(gv[j].x), lo[j].z + P::lo(gv[j].y),
+                                    lo[j].w + P::hi(gv[j].y));
+                hi[j] = make_float4(hi[j].x + P::lo(gv[j].z), hi[j].y + P::hi(gv[j].z), hi[j].z + P::lo(gv[j].w),
+                                    hi[j].w + P::hi(gv[j].w));
               }
             } else {
 #pragma unroll
@@ -326,8 +311,8 @@ __global__ void __launch_bounds__(A_THREADS, 1) mlp_tc_bwd_a_kernel(const fvgn_m
           }
 #pragma unroll
           for (int j = 0; j < NR; ++j)
-            out[j] = make_uint4(pack_bf16(lo[j].x, lo[j].y), pack_bf16(lo[j].z, lo[j].w), pack_bf16(hi[j].x, hi[j].y),
-                                pack_bf16(hi[j].z, hi[j].w));
+            out[j] = make_uint4(pack16<P>(lo[j].x, lo[j].y), pack16<P>(lo[j].z, lo[j].w), pack16<P>(hi[j].x, hi[j].y),
+                                pack16<P>(hi[j].z, hi[j].w));
         };
         auto park = [&](int kb, int i0, int n, const uint4* v) {
           for (int j = 0; j < n; ++j) {
@@ -373,7 +358,7 @@ __global__ void __launch_bounds__(A_THREADS, 1) mlp_tc_bwd_a_kernel(const fvgn_m
 #pragma unroll
           for (int ch = 0; ch < 8; ++ch)
             *reinterpret_cast<uint4*>(bufC + kb * KB_BYTES + sw128_off(rloc, ch)) =
-                (kb == 0 && ch == 0) ? make_uint4(pack_bf16(a, b), pack_bf16(c, 0.f), 0u, 0u) : make_uint4(0u, 0u, 0u, 0u);
+                (kb == 0 && ch == 0) ? make_uint4(pack16<P>(a, b), pack16<P>(c, 0.f), 0u, 0u) : make_uint4(0u, 0u, 0u, 0u);
       }
       fence_proxy_async();
       __syncwarp();
@@ -418,19 +403,17 @@ __global__ void __launch_bounds__(A_THREADS, 1) mlp_tc_bwd_a_kernel(const fvgn_m
         load_tile16(bz, rloc, cbase + c0, zw);
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
-#if FVGN_GELU_PACKED
-          gelu_tanh_pair_bf16x2(zw[j], hw[j], gw[j]);
-#elif FVGN_F32X2
+#if FVGN_F32X2
           float2 h, g;
-          gelu_tanh_pair2(bf16x2_f2(zw[j]), h, g);
-          hw[j] = pack_bf16(h);
-          gw[j] = pack_bf16(g);
+          gelu_tanh_pair2(unpack16<P>(zw[j]), h, g);
+          hw[j] = pack16<P>(h);
+          gw[j] = pack16<P>(g);
 #else
           float h0, g0, h1, g1;
-          gelu_tanh_pair(bf16_lo(zw[j]), h0, g0);
-          gelu_tanh_pair(bf16_hi(zw[j]), h1, g1);
-          hw[j] = pack_bf16(h0, h1);
-          gw[j] = pack_bf16(g0, g1);
+          gelu_tanh_pair(P::lo(zw[j]), h0, g0);
+          gelu_tanh_pair(P::hi(zw[j]), h1, g1);
+          hw[j] = pack16<P>(h0, h1);
+          gw[j] = pack16<P>(g0, g1);
 #endif
         }
         store_tile16(bz, rloc, cbase + c0, hw);
@@ -453,28 +436,24 @@ __global__ void __launch_bounds__(A_THREADS, 1) mlp_tc_bwd_a_kernel(const fvgn_m
 #pragma unroll
         for (int j = 0; j < 8; j += 2) {
           const float4 b = *reinterpret_cast<const float4*>(sb2 + cbase + c0 + 2 * j);
-#if FVGN_GELU_PACKED
-          gelu_tanh_pair_bf16x2(pack_bf16(__uint_as_float(r[2 * j]) + b.x, __uint_as_float(r[2 * j + 1]) + b.y), hw[j], gw[j]);
-          gelu_tanh_pair_bf16x2(pack_bf16(__uint_as_float(r[2 * j + 2]) + b.z, __uint_as_float(r[2 * j + 3]) + b.w), hw[j + 1],
-                                gw[j + 1]);
-#elif FVGN_F32X2
+#if FVGN_F32X2
           float2 ha, ga, hb, gb;
           gelu_tanh_pair2(__fadd2_rn(f2u(r[2 * j], r[2 * j + 1]), make_float2(b.x, b.y)), ha, ga);
           gelu_tanh_pair2(__fadd2_rn(f2u(r[2 * j + 2], r[2 * j + 3]), make_float2(b.z, b.w)), hb, gb);
-          hw[j] = pack_bf16(ha);
-          gw[j] = pack_bf16(ga);
-          hw[j + 1] = pack_bf16(hb);
-          gw[j + 1] = pack_bf16(gb);
+          hw[j] = pack16<P>(ha);
+          gw[j] = pack16<P>(ga);
+          hw[j + 1] = pack16<P>(hb);
+          gw[j + 1] = pack16<P>(gb);
 #else
           float h0, g0, h1, g1, h2, g2, h3, g3;
           gelu_tanh_pair(__uint_as_float(r[2 * j]) + b.x, h0, g0);
           gelu_tanh_pair(__uint_as_float(r[2 * j + 1]) + b.y, h1, g1);
           gelu_tanh_pair(__uint_as_float(r[2 * j + 2]) + b.z, h2, g2);
           gelu_tanh_pair(__uint_as_float(r[2 * j + 3]) + b.w, h3, g3);
-          hw[j] = pack_bf16(h0, h1);
-          gw[j] = pack_bf16(g0, g1);
-          hw[j + 1] = pack_bf16(h2, h3);
-          gw[j + 1] = pack_bf16(g2, g3);
+          hw[j] = pack16<P>(h0, h1);
+          gw[j] = pack16<P>(g0, g1);
+          hw[j + 1] = pack16<P>(h2, h3);
+          gw[j + 1] = pack16<P>(g2, g3);
 #endif
         }
         store_tile16(bufH2, rloc, cbase + c0, hw);
@@ -508,8 +487,8 @@ __global__ void __launch_bounds__(A_THREADS, 1) mlp_tc_bwd_a_kernel(const fvgn_m
 #if FVGN_F32X2
             const float2 ya = __fadd2_rn(f2u(r[2 * j], r[2 * j + 1]), make_float2(b.x, b.y));
             const float2 yb = __fadd2_rn(f2u(r[2 * j + 2], r[2 * j + 3]), make_float2(b.z, b.w));
-            const float2 da = __fmul2_rn(bf16x2_f2(ow[j]), make_float2(gm.x, gm.y));
-            const float2 db = __fmul2_rn(bf16x2_f2(ow[j + 1]), make_float2(gm.z, gm.w));
+            const float2 da = __fmul2_rn(unpack16<P>(ow[j]), make_float2(gm.x, gm.y));
+            const float2 db = __fmul2_rn(unpack16<P>(ow[j + 1]), make_float2(gm.z, gm.w));
             sum2 = __fadd2_rn(sum2, __fadd2_rn(ya, yb));
             sq2 = __ffma2_rn(ya, ya, __ffma2_rn(yb, yb, sq2));
             s12 = __fadd2_rn(s12, __fadd2_rn(da, db));
@@ -518,8 +497,8 @@ __global__ void __launch_bounds__(A_THREADS, 1) mlp_tc_bwd_a_kernel(const fvgn_m
 #endif
             const float y0 = __uint_as_float(r[2 * j]) + b.x, y1 = __uint_as_float(r[2 * j + 1]) + b.y;
             const float y2 = __uint_as_float(r[2 * j + 2]) + b.z, y3 = __uint_as_float(r[2 * j + 3]) + b.w;
-            const float d0 = bf16_lo(ow[j]) * gm.x, d1 = bf16_hi(ow[j]) * gm.y;
-            const float d2 = bf16_lo(ow[j + 1]) * gm.z, d3 = bf16_hi(ow[j + 1]) * gm.w;
+            const float d0 = P::lo(ow[j]) * gm.x, d1 = P::hi(ow[j]) * gm.y;
+            const float d2 = P::lo(ow[j + 1]) * gm.z, d3 = P::hi(ow[j + 1]) * gm.w;
             sum += (y0 + y1) + (y2 + y3);
             sq = fmaf(y0, y0, fmaf(y1, y1, fmaf(y2, y2, fmaf(y3, y3, sq))));
             s1 += (d0 + d1) + (d2 + d3);
@@ -556,25 +535,25 @@ __global__ void __launch_bounds__(A_THREADS, 1) mlp_tc_bwd_a_kernel(const fvgn_m
               const float2 rs = splat2(rstd), nm = splat2(nmr), nm1 = splat2(-m1), nm2 = splat2(-m2);
               const float2 xa = __ffma2_rn(__fadd2_rn(f2u(r[2 * j], r[2 * j + 1]), make_float2(b.x, b.y)), rs, nm);
               const float2 xb = __ffma2_rn(__fadd2_rn(f2u(r[2 * j + 2], r[2 * j + 3]), make_float2(b.z, b.w)), rs, nm);
-              const float2 oa = bf16x2_f2(ow[j]), ob = bf16x2_f2(ow[j + 1]);
+              const float2 oa = unpack16<P>(ow[j]), ob = unpack16<P>(ow[j + 1]);
               const float2 ga = __fmul2_rn(oa, xa), gb = __fmul2_rn(ob, xb);
               gx[2 * j] = ga.x; gx[2 * j + 1] = ga.y; gx[2 * j + 2] = gb.x; gx[2 * j + 3] = gb.y;
               // rstd * (o*gamma - m1 - xhat*m2) = rstd * fma(xhat, -m2, fma(o, gamma, -m1))
               const float2 ya = __fmul2_rn(rs, __ffma2_rn(xa, nm2, __ffma2_rn(oa, make_float2(gm.x, gm.y), nm1)));
               const float2 yb = __fmul2_rn(rs, __ffma2_rn(xb, nm2, __ffma2_rn(ob, make_float2(gm.z, gm.w), nm1)));
-              ow[j] = pack_bf16(ya);
-              ow[j + 1] = pack_bf16(yb);
+              ow[j] = pack16<P>(ya);
+              ow[j + 1] = pack16<P>(yb);
               continue;
             }
 #endif
             const float xh0 = fmaf(__uint_as_float(r[2 * j]) + b.x, rstd, nmr), xh1 = fmaf(__uint_as_float(r[2 * j + 1]) + b.y, rstd, nmr);
             const float xh2 = fmaf(__uint_as_float(r[2 * j + 2]) + b.z, rstd, nmr), xh3 = fmaf(__uint_as_float(r[2 * j + 3]) + b.w, rstd, nmr);
-            const float o0 = bf16_lo(ow[j]), o1 = bf16_hi(ow[j]), o2 = bf16_lo(ow[j + 1]), o3 = bf16_hi(ow[j + 1]);
+            const float o0 = P::lo(ow[j]), o1 = P::hi(ow[j]), o2 = P::lo(ow[j + 1]), o3 = P::hi(ow[j + 1]);
             gx[2 * j] = o0 * xh0; gx[2 * j + 1] = o1 * xh1; gx[2 * j + 2] = o2 * xh2; gx[2 * j + 3] = o3 * xh3;
             const float y0 = rstd * fmaf(-xh0, m2, fmaf(o0, gm.x, -m1)), y1 = rstd * fmaf(-xh1, m2, fmaf(o1, gm.y, -m1));
             const float y2 = rstd * fmaf(-xh2, m2, fmaf(o2, gm.z, -m1)), y3 = rstd * fmaf(-xh3, m2, fmaf(o3, gm.w, -m1));
-            ow[j] = pack_bf16(y0, y1);
-            ow[j + 1] = pack_bf16(y2, y3);
+            ow[j] = pack16<P>(y0, y1);
+            ow[j + 1] = pack16<P>(y2, y3);
           }
           store_tile16(bufC, rloc, cbase + c0, ow);
           const float cg = warp_colsum16(gx, lane);
@@ -597,9 +576,9 @@ __global__ void __launch_bounds__(A_THREADS, 1) mlp_tc_bwd_a_kernel(const fvgn_m
 #pragma unroll
         for (int j = 0; j < 8; ++j)
 #if FVGN_F32X2
-          ow[j] = pack_bf16(__fmul2_rn(f2u(r[2 * j], r[2 * j + 1]), bf16x2_f2(g[j])));
+          ow[j] = pack16<P>(__fmul2_rn(f2u(r[2 * j], r[2 * j + 1]), unpack16<P>(g[j])));
 #else
-          ow[j] = pack_bf16(__uint_as_float(r[2 * j]) * bf16_lo(g[j]), __uint_as_float(r[2 * j + 1]) * bf16_hi(g[j]));
+          ow[j] = pack16<P>(__uint_as_float(r[2 * j]) * P::lo(g[j]), __uint_as_float(r[2 * j + 1]) * P::hi(g[j]));
 #endif
         store_tile16(bufH2, rloc, cbase + c0, ow);
       });
@@ -619,9 +598,9 @@ __global__ void __launch_bounds__(A_THREADS, 1) mlp_tc_bwd_a_kernel(const fvgn_m
 #pragma unroll
         for (int j = 0; j < 8; ++j)
 #if FVGN_F32X2
-          ow[j] = pack_bf16(__fmul2_rn(f2u(r[2 * j], r[2 * j + 1]), bf16x2_f2(g[j])));
+          ow[j] = pack16<P>(__fmul2_rn(f2u(r[2 * j], r[2 * j + 1]), unpack16<P>(g[j])));
 #else
-          ow[j] = pack_bf16(__uint_as_float(r[2 * j]) * bf16_lo(g[j]), __uint_as_float(r[2 * j + 1]) * bf16_hi(g[j]));
+          ow[j] = pack16<P>(__uint_as_float(r[2 * j]) * P::lo(g[j]), __uint_as_float(r[2 * j + 1]) * P::hi(g[j]));
 #endif
         store_tile16(bz, rloc, cbase + c0, ow);
       });
@@ -704,9 +683,10 @@ __global__ void __launch_bounds__(A_THREADS, 1) mlp_tc_bwd_a_kernel(const fvgn_m
 // =============================================================================================== kernel B
 constexpr int STG_BYTES = 4 * WSTG_BYTES;  // one wide staging tile per epilogue warp
 
-template <int MODE>
+template <int MODE, class P>
 __global__ void __launch_bounds__(NTHREADS, 1) mlp_tc_bwd_b_kernel(const fvgn_mlp_desc d) {
   using C = BCfg<MODE>;
+  constexpr uint32_t IDESC_MM64 = make_idesc(P::FMT, 64, 1, 1), IDESC_KM64 = make_idesc(P::FMT, 64, 0, 1);
   constexpr int NKB1 = nkb1(C::K1P);
   constexpr int NSTAGE = 3;
   constexpr uint32_t DW1 = 0, WACC = 384;  // dW1: NKB1 x 64 columns; two 64-column dX accumulators
@@ -827,7 +807,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) mlp_tc_bwd_b_kernel(const fvgn_ml
         for (int kb = 0; kb < NKB1; ++kb, ++it) {
           const int s = it % NSTAGE;
           mbar_wait(BAR(B_XEMPTY + s), ((it / NSTAGE) & 1) ^ 1);
-          produce_chunk<MODE>(d, row0, kb, ring + s * KB_BYTES, pw, lane, idx);
+          produce_chunk<MODE, P>(d, row0, kb, ring + s * KB_BYTES, pw, lane, idx);
           fence_proxy_async();
           __syncwarp();
           if (lane == 0) mbar_arrive(BAR(B_XFULL + s));
@@ -892,10 +872,10 @@ __global__ void __launch_bounds__(NTHREADS, 1) mlp_tc_bwd_b_kernel(const fvgn_ml
 #pragma unroll
               for (int k = 0; k < 4; ++k)
                 *reinterpret_cast<uint4*>(wstg_at(mystg, lane, half * 4 + k)) =
-                    make_uint4(pack_bf16(__uint_as_float(r[8 * k]), __uint_as_float(r[8 * k + 1])),
-                               pack_bf16(__uint_as_float(r[8 * k + 2]), __uint_as_float(r[8 * k + 3])),
-                               pack_bf16(__uint_as_float(r[8 * k + 4]), __uint_as_float(r[8 * k + 5])),
-                               pack_bf16(__uint_as_float(r[8 * k + 6]), __uint_as_float(r[8 * k + 7])));
+                    make_uint4(pack16<P>(__uint_as_float(r[8 * k]), __uint_as_float(r[8 * k + 1])),
+                               pack16<P>(__uint_as_float(r[8 * k + 2]), __uint_as_float(r[8 * k + 3])),
+                               pack16<P>(__uint_as_float(r[8 * k + 4]), __uint_as_float(r[8 * k + 5])),
+                               pack16<P>(__uint_as_float(r[8 * k + 6]), __uint_as_float(r[8 * k + 7])));
             }
             tc_fence_before();
             mbar_arrive(BAR(B_AFREE + ab));
@@ -970,13 +950,15 @@ __global__ void __launch_bounds__(NTHREADS, 1) mlp_tc_bwd_b_kernel(const fvgn_ml
   }
 }
 
+// out[i] = unscale * sum over the CTAs' partial buffers (fixed order: deterministic).  unscale (nullable device scalar) is
+// 1 / S of the power-of-two gradient pre-scaling of the fp16 mode (ops.GradScaleFn): the multiplication is exact.
 __global__ void __launch_bounds__(256) tc_partial_reduce_kernel(const float* __restrict__ partials, int n_partials, int64_t pc,
-                                                                float* __restrict__ out) {
+                                                                const float* __restrict__ unscale, float* __restrict__ out) {
   const int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x;
   if (i >= pc) return;
   float s = 0.f;
   for (int g = 0; g < n_partials; ++g) s += partials[(size_t)g * pc + i];
-  out[i] = s;
+  out[i] = unscale ? s * __ldg(unscale) : s;
 }
 
 template <int MODE> constexpr int smem_a() { return 4 * KB_BYTES + 4 * BUF_BYTES + 3 * 512 + (A_NEW / 4) * 2048 + 256; }
@@ -984,27 +966,19 @@ template <int MODE> constexpr int smem_b() {
   return nkb1(BCfg<MODE>::K1P) * KB_BYTES + 2 * BUF_BYTES + 3 * KB_BYTES + STG_BYTES + 256;
 }
 
-int num_sms() {
-  static int n = 0;
-  if (n == 0) {
-    int dev = 0;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
-    if (n <= 0) n = 148;
-  }
-  return n;
-}
+int num_sms() { return fvgn_num_sms(); }
 
-template <int MODE>
+template <int MODE, class P>
 int launch_tc_bwd(const fvgn_mlp_desc& d, void* stream) {
   using C = BCfg<MODE>;
-  auto ka = mlp_tc_bwd_a_kernel<MODE>;
-  auto kb = mlp_tc_bwd_b_kernel<MODE>;
-  static bool attr_set = false;
-  if (!attr_set) {
+  auto ka = mlp_tc_bwd_a_kernel<MODE, P>;
+  auto kb = mlp_tc_bwd_b_kernel<MODE, P>;
+  static bool attr_set[FVGN_MAX_DEV] = {false};  // the attribute is per device
+  const int dev = fvgn_cur_device();
+  if (!attr_set[dev]) {
     if (cudaFuncSetAttribute(ka, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_a<MODE>()) != cudaSuccess) return FVGN_ERR_LAUNCH;
     if (cudaFuncSetAttribute(kb, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_b<MODE>()) != cudaSuccess) return FVGN_ERR_LAUNCH;
-    attr_set = true;
+    attr_set[dev] = true;
   }
   const unsigned grid = (unsigned)d.n_partials;
   ka<<<grid, A_THREADS, smem_a<MODE>(), (cudaStream_t)stream>>>(d);
@@ -1012,7 +986,8 @@ int launch_tc_bwd(const fvgn_mlp_desc& d, void* stream) {
   kb<<<grid, NTHREADS, smem_b<MODE>(), (cudaStream_t)stream>>>(d);
   FVGN_CHECK_LAUNCH();
   const int64_t pc = pcount(C::K1, C::NOUT, C::LN);
-  tc_partial_reduce_kernel<<<(unsigned)((pc + 255) / 256), 256, 0, (cudaStream_t)stream>>>(d.partials, d.n_partials, pc, d.d_params);
+  tc_partial_reduce_kernel<<<(unsigned)((pc + 255) / 256), 256, 0, (cudaStream_t)stream>>>(d.partials, d.n_partials, pc, d.grad_unscale,
+                                                                                       d.d_params);
   FVGN_CHECK_LAUNCH();
   return FVGN_OK;
 }
@@ -1053,12 +1028,15 @@ int fvgn_mlp_backward_tc(const fvgn_mlp_desc* d, void* stream) {
     if (cudaMemsetAsync(d->d_params, 0, (size_t)pc * sizeof(float), (cudaStream_t)stream) != cudaSuccess) return FVGN_ERR_LAUNCH;
     return FVGN_OK;
   }
+  const bool f16 = d->precision == FVGN_PREC_F16;
+#define FVGN_TC_BWD_CASE(M) case M: return f16 ? launch_tc_bwd<M, PF16>(*d, stream) : launch_tc_bwd<M, PBF16>(*d, stream);
   switch (d->mode) {
-    case FVGN_MLP_EDGE: return launch_tc_bwd<FVGN_MLP_EDGE>(*d, stream);
-    case FVGN_MLP_NODE: return launch_tc_bwd<FVGN_MLP_NODE>(*d, stream);
-    case FVGN_MLP_ENC_NODE: return launch_tc_bwd<FVGN_MLP_ENC_NODE>(*d, stream);
-    case FVGN_MLP_ENC_EDGE: return launch_tc_bwd<FVGN_MLP_ENC_EDGE>(*d, stream);
-    case FVGN_MLP_DEC: return launch_tc_bwd<FVGN_MLP_DEC>(*d, stream);
+    FVGN_TC_BWD_CASE(FVGN_MLP_EDGE)
+    FVGN_TC_BWD_CASE(FVGN_MLP_NODE)
+    FVGN_TC_BWD_CASE(FVGN_MLP_ENC_NODE)
+    FVGN_TC_BWD_CASE(FVGN_MLP_ENC_EDGE)
+    FVGN_TC_BWD_CASE(FVGN_MLP_DEC)
   }
+#undef FVGN_TC_BWD_CASE
   return FVGN_ERR_UNSUPPORTED;
 }

@@ -16,9 +16,11 @@
 // element-type helpers: 4 consecutive elements per lane, fp32 (16 B) or bf16 (8 B)
 #ifndef FVGN_EMU
 #include <cuda_bf16.h>
+#include <cuda_fp16.h>
 #endif
 struct T_F32 { typedef float elem; };
 struct T_BF16 { typedef uint16_t elem; };
+struct T_F16 { typedef uint16_t elem; };   // IEEE half (FVGN_PREC_F16 streams); same storage as bf16
 template <class T> __device__ __forceinline__ float4 ldv(const typename T::elem* p);
 template <> __device__ __forceinline__ float4 ldv<T_F32>(const float* p) { return ld4(p); }
 template <class T> __device__ __forceinline__ void stv(typename T::elem* p, float4 v);
@@ -32,6 +34,20 @@ template <> __device__ __forceinline__ float4 ldv<T_BF16>(const uint16_t* p) {
 template <> __device__ __forceinline__ void stv<T_BF16>(uint16_t* p, float4 v) {
   __nv_bfloat162 a = __floats2bfloat162_rn(v.x, v.y), b = __floats2bfloat162_rn(v.z, v.w);
   *reinterpret_cast<uint2*>(p) = make_uint2(*reinterpret_cast<uint32_t*>(&a), *reinterpret_cast<uint32_t*>(&b));
+}
+__device__ __forceinline__ float hf_lo(uint32_t w) { return __low2float(*reinterpret_cast<const __half2*>(&w)); }
+__device__ __forceinline__ float hf_hi(uint32_t w) { return __high2float(*reinterpret_cast<const __half2*>(&w)); }
+__device__ __forceinline__ uint32_t hf_pack(float lo, float hi) {  // round to nearest, saturate to +-65504
+  uint32_t r;
+  asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
+  return r;
+}
+template <> __device__ __forceinline__ float4 ldv<T_F16>(const uint16_t* p) {
+  const uint2 w = *reinterpret_cast<const uint2*>(p);
+  return make_float4(hf_lo(w.x), hf_hi(w.x), hf_lo(w.y), hf_hi(w.y));
+}
+template <> __device__ __forceinline__ void stv<T_F16>(uint16_t* p, float4 v) {
+  *reinterpret_cast<uint2*>(p) = make_uint2(hf_pack(v.x, v.y), hf_pack(v.z, v.w));
 }
 #endif
 
@@ -164,6 +180,28 @@ template <> struct LaneIO<T_BF16, 8> {
   }
   static __device__ __forceinline__ void st(uint16_t* p, const float (&x)[8]) {
     *reinterpret_cast<uint4*>(p) = make_uint4(bf_pack(x[0], x[1]), bf_pack(x[2], x[3]), bf_pack(x[4], x[5]), bf_pack(x[6], x[7]));
+  }
+};
+
+template <> struct LaneIO<T_F16, 4> {
+  struct raw { uint2 a; };
+  static __device__ __forceinline__ raw ld(const uint16_t* p) { return raw{*reinterpret_cast<const uint2*>(p)}; }
+  static __device__ __forceinline__ void up(const raw& r, float (&x)[4]) {
+    x[0] = hf_lo(r.a.x); x[1] = hf_hi(r.a.x); x[2] = hf_lo(r.a.y); x[3] = hf_hi(r.a.y);
+  }
+  static __device__ __forceinline__ void st(uint16_t* p, const float (&x)[4]) {
+    *reinterpret_cast<uint2*>(p) = make_uint2(hf_pack(x[0], x[1]), hf_pack(x[2], x[3]));
+  }
+};
+template <> struct LaneIO<T_F16, 8> {
+  struct raw { uint4 a; };
+  static __device__ __forceinline__ raw ld(const uint16_t* p) { return raw{*reinterpret_cast<const uint4*>(p)}; }
+  static __device__ __forceinline__ void up(const raw& r, float (&x)[8]) {
+    x[0] = hf_lo(r.a.x); x[1] = hf_hi(r.a.x); x[2] = hf_lo(r.a.y); x[3] = hf_hi(r.a.y);
+    x[4] = hf_lo(r.a.z); x[5] = hf_hi(r.a.z); x[6] = hf_lo(r.a.w); x[7] = hf_hi(r.a.w);
+  }
+  static __device__ __forceinline__ void st(uint16_t* p, const float (&x)[8]) {
+    *reinterpret_cast<uint4*>(p) = make_uint4(hf_pack(x[0], x[1]), hf_pack(x[2], x[3]), hf_pack(x[4], x[5]), hf_pack(x[6], x[7]));
   }
 };
 
@@ -386,6 +424,9 @@ extern "C" int fvgn_adj_reduce_t(const void* src, int32_t src_type, const int32_
   if (src_type == FVGN_T_F32 && dst_type == FVGN_T_BF16) return launch_adj<T_F32, T_BF16>(src, ptr, nbr, dst, n_rows, width, flags, stream);
   if (src_type == FVGN_T_BF16 && dst_type == FVGN_T_F32) return launch_adj<T_BF16, T_F32>(src, ptr, nbr, dst, n_rows, width, flags, stream);
   if (src_type == FVGN_T_BF16 && dst_type == FVGN_T_BF16) return launch_adj<T_BF16, T_BF16>(src, ptr, nbr, dst, n_rows, width, flags, stream);
+  if (src_type == FVGN_T_F32 && dst_type == FVGN_T_F16) return launch_adj<T_F32, T_F16>(src, ptr, nbr, dst, n_rows, width, flags, stream);
+  if (src_type == FVGN_T_F16 && dst_type == FVGN_T_F32) return launch_adj<T_F16, T_F32>(src, ptr, nbr, dst, n_rows, width, flags, stream);
+  if (src_type == FVGN_T_F16 && dst_type == FVGN_T_F16) return launch_adj<T_F16, T_F16>(src, ptr, nbr, dst, n_rows, width, flags, stream);
 #endif
   if (src_type == FVGN_T_F32 && dst_type == FVGN_T_F32) return launch_adj<T_F32, T_F32>(src, ptr, nbr, dst, n_rows, width, flags, stream);
   return FVGN_ERR_UNSUPPORTED;
@@ -400,6 +441,9 @@ extern "C" int fvgn_inc_reduce_t(const void* src, int32_t src_type, const int32_
   if (src_type == FVGN_T_F32 && dst_type == FVGN_T_BF16) return launch_inc<T_F32, T_BF16>(src, ptr, code, dst, n_rows, width, stream);
   if (src_type == FVGN_T_BF16 && dst_type == FVGN_T_F32) return launch_inc<T_BF16, T_F32>(src, ptr, code, dst, n_rows, width, stream);
   if (src_type == FVGN_T_BF16 && dst_type == FVGN_T_BF16) return launch_inc<T_BF16, T_BF16>(src, ptr, code, dst, n_rows, width, stream);
+  if (src_type == FVGN_T_F32 && dst_type == FVGN_T_F16) return launch_inc<T_F32, T_F16>(src, ptr, code, dst, n_rows, width, stream);
+  if (src_type == FVGN_T_F16 && dst_type == FVGN_T_F32) return launch_inc<T_F16, T_F32>(src, ptr, code, dst, n_rows, width, stream);
+  if (src_type == FVGN_T_F16 && dst_type == FVGN_T_F16) return launch_inc<T_F16, T_F16>(src, ptr, code, dst, n_rows, width, stream);
 #endif
   if (src_type == FVGN_T_F32 && dst_type == FVGN_T_F32) return launch_inc<T_F32, T_F32>(src, ptr, code, dst, n_rows, width, stream);
   return FVGN_ERR_UNSUPPORTED;

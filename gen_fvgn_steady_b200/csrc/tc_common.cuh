@@ -3,8 +3,51 @@
 #pragma once
 #include "common.cuh"
 #include <cuda_bf16.h>
+#include <cuda_fp16.h>
 
 namespace tc {
+
+// ------------------------------------------------------------------------------------------ 16-bit operand formats
+// The tensor-core path is templated on the operand format P of tcgen05.mma kind::f16:
+//   PBF16 (FVGN_PREC_BF16): bfloat16, 8-bit significand, fp32 exponent range;
+//   PF16  (FVGN_PREC_F16) : IEEE half, 11-bit significand -- the significand of TF32, the arithmetic the reference's GPU
+//                           path runs its Linear layers in (src/pre_train_Adam.py:29) -- conversions round to nearest and
+//                           saturate to +-65504 instead of overflowing to infinity (gradients are pre-scaled by a power of
+//                           two chosen per backward pass, ops.GradScaleFn).
+// Both accumulate in fp32 (TMEM); everything outside the MMA operands (bias, GELU, LayerNorm, residuals) is fp32.
+struct PBF16 {
+  static constexpr uint32_t FMT = 1;  // InstrDescriptor a_format / b_format: 1 = BF16
+  static __device__ __forceinline__ uint32_t pack(float lo, float hi) {
+    uint32_t r;
+    asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
+    return r;
+  }
+  static __device__ __forceinline__ float lo(uint32_t w) { return __uint_as_float(w << 16); }
+  static __device__ __forceinline__ float hi(uint32_t w) { return __uint_as_float(w & 0xFFFF0000u); }
+  static __device__ __forceinline__ uint32_t add2(uint32_t a, uint32_t b) {
+    uint32_t r;
+    asm("add.rn.bf16x2 %0, %1, %2;" : "=r"(r) : "r"(a), "r"(b));
+    return r;
+  }
+};
+struct PF16 {
+  static constexpr uint32_t FMT = 0;  // 0 = F16
+  static __device__ __forceinline__ uint32_t pack(float lo, float hi) {
+    uint32_t r;
+    asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
+    return r;
+  }
+  static __device__ __forceinline__ float lo(uint32_t w) { return __low2float(*reinterpret_cast<const __half2*>(&w)); }
+  static __device__ __forceinline__ float hi(uint32_t w) { return __high2float(*reinterpret_cast<const __half2*>(&w)); }
+  static __device__ __forceinline__ uint32_t add2(uint32_t a, uint32_t b) {
+    uint32_t r;
+    asm("add.rn.f16x2 %0, %1, %2;" : "=r"(r) : "r"(a), "r"(b));
+    return r;
+  }
+};
+template <class P> __device__ __forceinline__ uint32_t pack16(float lo, float hi) { return P::pack(lo, hi); }
+template <class P> __device__ __forceinline__ uint32_t pack16(float2 v) { return P::pack(v.x, v.y); }
+template <class P> __device__ __forceinline__ float2 unpack16(uint32_t w) { return make_float2(P::lo(w), P::hi(w)); }
 
 constexpr int TILE_M = 128;
 constexpr int KB_BYTES = 128 * 128;  // one K-block: 128 rows x 64 bf16 (128 B per row), SWIZZLE_128B
@@ -97,8 +140,12 @@ __device__ __forceinline__ void tmem_wait_st() { asm volatile("tcgen05.wait::st.
 __device__ __forceinline__ uint64_t make_desc_k128(uint32_t saddr) {
   return (uint64_t)((saddr >> 4) & 0x3FFF) | (1ull << 16) | (64ull << 32) | (1ull << 46) | (2ull << 61);
 }
-// instruction descriptor: D=f32, A=B=bf16, both K-major, M=128, N=128 (cute::UMMA::InstrDescriptor)
-constexpr uint32_t IDESC = (1u << 4) | (1u << 7) | (1u << 10) | ((128u >> 3) << 17) | ((128u >> 4) << 24);
+// instruction descriptor (cute::UMMA::InstrDescriptor): D = f32 (bit 4), A / B format fmt (bits 7-9 / 10-12: 0 = f16,
+// 1 = bf16), major-ness of A / B (bits 15 / 16: 0 = K-major), N >> 3 (bits 17-22), M >> 4 (bits 24-28) with M = 128
+__host__ __device__ constexpr uint32_t make_idesc(uint32_t fmt, int n, int a_mn_major, int b_mn_major) {
+  return (1u << 4) | (fmt << 7) | (fmt << 10) | ((uint32_t)a_mn_major << 15) | ((uint32_t)b_mn_major << 16) |
+         ((uint32_t)(n >> 3) << 17) | ((128u >> 4) << 24);
+}
 
 // Throughput-mode GELU: tanh form evaluated with the MUFU.TANH approximation (6 instructions).
 // |gelu_tanh - gelu_erf| <= 3e-4 absolute, below the bf16 rounding the value receives right afterwards.
@@ -122,43 +169,6 @@ __device__ __forceinline__ void gelu_tanh_pair(float x, float& h, float& g) {
   g = fmaf(hx * fmaf(-t, t, 1.0f), fmaf(0.1070322243f, x2, 0.7978845608f), fmaf(0.5f, t, 0.5f));
 }
 
-// ---- packed bf16x2 arithmetic (two elements per instruction, no unpack / pack): the backward's recomputation of
-// gelu / gelu' from bf16 pre-activations.  Measured against the fp64 tanh-form GELU on N(0, 1.5) inputs (emulated
-// roundings): rms error of h 1.8e-3 (1.6e-3 when evaluated in fp32 and rounded once), of g 2.6e-3 (1.4e-3).
-__device__ __forceinline__ uint32_t bmul2(uint32_t a, uint32_t b) {
-  uint32_t d;
-  asm("mul.rn.bf16x2 %0, %1, %2;" : "=r"(d) : "r"(a), "r"(b));
-  return d;
-}
-__device__ __forceinline__ uint32_t bfma2(uint32_t a, uint32_t b, uint32_t c) {
-  uint32_t d;
-  asm("fma.rn.bf16x2 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(c));
-  return d;
-}
-__device__ __forceinline__ uint32_t btanh2(uint32_t a) {
-  uint32_t d;
-  asm("tanh.approx.bf16x2 %0, %1;" : "=r"(d) : "r"(a));
-  return d;
-}
-// x = two bf16 pre-activations -> h = gelu_tanh(x), g = d gelu_tanh / dx (both packed bf16x2): 12 instructions per pair
-__device__ __forceinline__ void gelu_tanh_pair_bf16x2(uint32_t x, uint32_t& h, uint32_t& g) {
-  constexpr uint32_t C0 = 0x3F4C3F4Cu;    // 0.79788 (sqrt(2/pi))
-  constexpr uint32_t C1 = 0x3D123D12u;    // 0.035677
-  constexpr uint32_t C2 = 0x3DDB3DDBu;    // 0.10703 (3 * C1)
-  constexpr uint32_t HALF = 0x3F003F00u, ONE = 0x3F803F80u;
-  const uint32_t x2 = bmul2(x, x);
-  const uint32_t t = btanh2(bmul2(x, bfma2(C1, x2, C0)));
-  const uint32_t hx = bmul2(HALF, x);
-  h = bfma2(hx, t, hx);
-  const uint32_t s = bfma2(t ^ 0x80008000u, t, ONE);  // 1 - t^2
-  g = bfma2(bmul2(hx, s), bfma2(C2, x2, C0), bfma2(HALF, t, HALF));
-}
-
-__device__ __forceinline__ uint32_t pack_bf16(float lo, float hi) {
-  __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);
-  return *reinterpret_cast<uint32_t*>(&v);
-}
-
 // byte offset of (row, 16-byte chunk) inside one K-block in the SWIZZLE_128B K-major layout
 __device__ __host__ __forceinline__ uint32_t sw128_off(int row, int chunk) {
   return (uint32_t)((row >> 3) * 1024 + (row & 7) * 128 + ((chunk ^ (row & 7)) << 4));
@@ -170,11 +180,6 @@ __device__ __host__ __forceinline__ uint32_t sw128_off(int row, int chunk) {
 __device__ __forceinline__ uint64_t make_desc_mn128(uint32_t saddr, uint32_t lbo_bytes) {
   return (uint64_t)((saddr >> 4) & 0x3FFF) | ((uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16) | (64ull << 32) | (1ull << 46) |
          (2ull << 61);
-}
-// instruction descriptor: D=f32, A=B=bf16, M=128
-__host__ __device__ constexpr uint32_t make_idesc(int n, int a_mn_major, int b_mn_major) {
-  return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)a_mn_major << 15) | ((uint32_t)b_mn_major << 16) |
-         ((uint32_t)(n >> 3) << 17) | ((128u >> 4) << 24);
 }
 
 // ------------------------------------------------------------------------------------------ producers
@@ -216,7 +221,7 @@ __device__ __forceinline__ void load_tile_idx(const fvgn_mlp_desc& d, int64_t ro
   }
 }
 
-template <int MODE>
+template <int MODE, class P>
 __device__ __forceinline__ void produce_chunk(const fvgn_mlp_desc& d, int64_t row0, int kb, uint8_t* stage, int pw, int lane,
                                               const TileIdx& idx) {
   if (MODE == FVGN_MLP_ENC_NODE || MODE == FVGN_MLP_ENC_EDGE) {
@@ -249,8 +254,8 @@ __device__ __forceinline__ void produce_chunk(const fvgn_mlp_desc& d, int64_t ro
 #pragma unroll
     for (int c = 0; c < 2; ++c)
       *reinterpret_cast<uint4*>(stage + sw128_off(rloc, c)) =
-          make_uint4(pack_bf16(v[c * 8 + 0], v[c * 8 + 1]), pack_bf16(v[c * 8 + 2], v[c * 8 + 3]),
-                     pack_bf16(v[c * 8 + 4], v[c * 8 + 5]), pack_bf16(v[c * 8 + 6], v[c * 8 + 7]));
+          make_uint4(pack16<P>(v[c * 8 + 0], v[c * 8 + 1]), pack16<P>(v[c * 8 + 2], v[c * 8 + 3]),
+                     pack16<P>(v[c * 8 + 4], v[c * 8 + 5]), pack16<P>(v[c * 8 + 6], v[c * 8 + 7]));
 #pragma unroll
     for (int c = 2; c < 8; ++c)  // the rest of the 64-wide block must be zero (it is an MMA operand in the wgrad pass)
       *reinterpret_cast<uint4*>(stage + sw128_off(rloc, c)) = make_uint4(0u, 0u, 0u, 0u);
@@ -280,8 +285,8 @@ __device__ __forceinline__ void produce_chunk(const fvgn_mlp_desc& d, int64_t ro
   for (int i = 0; i < 8; ++i) {
     const int rloc = i * 16 + pw * 4 + (lane >> 3);
     *reinterpret_cast<uint4*>(stage + sw128_off(rloc, seg)) =
-        make_uint4(pack_bf16(lo[i].x, lo[i].y), pack_bf16(lo[i].z, lo[i].w), pack_bf16(hi[i].x, hi[i].y),
-                   pack_bf16(hi[i].z, hi[i].w));
+        make_uint4(pack16<P>(lo[i].x, lo[i].y), pack16<P>(lo[i].z, lo[i].w), pack16<P>(hi[i].x, hi[i].y),
+                   pack16<P>(hi[i].z, hi[i].w));
   }
 }
 
@@ -425,8 +430,6 @@ __device__ __forceinline__ void for_each_chunk16(uint32_t taddr, F&& f) {
   }
 }
 
-__device__ __forceinline__ float bf16_lo(uint32_t w) { return __uint_as_float(w << 16); }
-__device__ __forceinline__ float bf16_hi(uint32_t w) { return __uint_as_float(w & 0xFFFF0000u); }
 
 // ---- packed fp32x2 epilogue arithmetic (FVGN_F32X2 = 1, default): sm_100 executes fma / mul / add on register PAIRS
 // (FFMA2 / FMUL2 / FADD2, IEEE per element), which halves the fp32 instruction count of the issue-bound epilogue stages.
@@ -436,8 +439,6 @@ __device__ __forceinline__ float bf16_hi(uint32_t w) { return __uint_as_float(w 
 #endif
 __device__ __forceinline__ float2 splat2(float a) { return make_float2(a, a); }
 __device__ __forceinline__ float2 f2u(uint32_t lo, uint32_t hi) { return make_float2(__uint_as_float(lo), __uint_as_float(hi)); }
-__device__ __forceinline__ float2 bf16x2_f2(uint32_t w) { return make_float2(bf16_lo(w), bf16_hi(w)); }
-__device__ __forceinline__ uint32_t pack_bf16(float2 v) { return pack_bf16(v.x, v.y); }
 __device__ __forceinline__ float2 gelu_tanh2(float2 x) {
   const float2 u = __fmul2_rn(x, __ffma2_rn(splat2(0.0356774081f), __fmul2_rn(x, x), splat2(0.7978845608f)));
   const float2 hx = __fmul2_rn(splat2(0.5f), x);

@@ -564,15 +564,22 @@ __global__ void __launch_bounds__(TS_NT) ts_bias_gelu_bwd_kernel(const float* dh
 // out = a + bias + res on [n,128] rows (+ bf16 shadow of out)
 __global__ void __launch_bounds__(TS_NT) ts_bias_res_kernel(const float* __restrict__ a, const float* __restrict__ bias,
                                                             const float* __restrict__ res, float* __restrict__ out,
-                                                            uint16_t* __restrict__ outh, int64_t n4) {
+                                                            uint16_t* __restrict__ outh, int outh_f16, int64_t n4) {
   const int64_t i = (int64_t)blockIdx.x * TS_NT + threadIdx.x;
   if (i >= n4) return;
   const float4 v = add4(add4(ld4(a + i * 4), ld4(bias + (i & 31) * 4)), ld4(res + i * 4));
   st4(out + i * 4, v);
 #ifndef FVGN_EMU
   if (outh) {
-    __nv_bfloat162 lo = __floats2bfloat162_rn(v.x, v.y), hi = __floats2bfloat162_rn(v.z, v.w);
-    *reinterpret_cast<uint2*>(outh + i * 4) = make_uint2(*reinterpret_cast<uint32_t*>(&lo), *reinterpret_cast<uint32_t*>(&hi));
+    uint32_t lo, hi;
+    if (outh_f16) {
+      asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(lo) : "f"(v.y), "f"(v.x));
+      asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(hi) : "f"(v.w), "f"(v.z));
+    } else {
+      asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(lo) : "f"(v.y), "f"(v.x));
+      asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(hi) : "f"(v.w), "f"(v.z));
+    }
+    *reinterpret_cast<uint2*>(outh + i * 4) = make_uint2(lo, hi);
   }
 #endif
 }
@@ -688,8 +695,8 @@ extern "C" int fvgn_ts_bias_gelu_backward(const float* dh, const float* hpre, co
   return FVGN_OK;
 }
 
-extern "C" int fvgn_ts_bias_residual(const float* a, const float* bias, const float* res, float* out, void* outh, int64_t n,
-                                     void* stream) {
+extern "C" int fvgn_ts_bias_residual(const float* a, const float* bias, const float* res, float* out, void* outh,
+                                     int32_t outh_type, int64_t n, void* stream) {
   if (n <= 0) return FVGN_OK;
   if (!a || !bias || !res || !out) return FVGN_ERR_NULL;
 #ifdef FVGN_EMU
@@ -697,7 +704,7 @@ extern "C" int fvgn_ts_bias_residual(const float* a, const float* bias, const fl
 #endif
   const int64_t n4 = n * 32;
   FVGN_LAUNCH_SEQ(ts_bias_res_kernel, (unsigned)((n4 + TS_NT - 1) / TS_NT), TS_NT, 0, stream, a, bias, res, out,
-                  reinterpret_cast<uint16_t*>(outh), n4);
+                  reinterpret_cast<uint16_t*>(outh), (int)(outh_type == FVGN_T_F16), n4);
   FVGN_CHECK_LAUNCH();
   return FVGN_OK;
 }

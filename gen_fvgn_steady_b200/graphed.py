@@ -7,14 +7,27 @@ bound (5.5 ms eager on a B200, independent of the mesh size), so the step is cap
 
     gstep = GraphedTrainStep(model, optimizer, graphs, loss_fn)      # optimizer: Adam(..., fused=True, capturable=True)
     for it in range(n): loss = gstep.step()                          # optional: gstep.step(new_x) refreshes graph_node.x
+    gstep.close()                                                    # restores the Normalizer's accumulation window
+
+Construction does NOT advance training: the eager warm-up steps the capture needs run on a snapshot of the model /
+optimizer state, which is restored before the capture.  A Normalizer that is still accumulating cannot be captured (its
+host-side counter decides which kernels run): pass freeze_normalizer=True to freeze its statistics for the lifetime of
+this object (a warning says so; close() re-opens the window) or capture after `dataset_size` accumulations.
+Replays update the weights in place without moving Tensor._version, so every step() invalidates the packed 16-bit
+weight images (ops.PackedWeights): eager forwards between / after replays always see the current weights.
 
 Every kernel of the path enqueues on torch's current stream and never allocates or synchronises (include/fvgn_b200.h),
 so the capture needs nothing special; torch's caching allocator serves the transient buffers from the graph's pool."""
+import copy
+import warnings
+
 import torch
+
+from . import ops
 
 
 class GraphedTrainStep:
-    def __init__(self, model, optimizer, graphs, loss_fn, warmup=3, freeze_normalizer=True):
+    def __init__(self, model, optimizer, graphs, loss_fn, warmup=3, freeze_normalizer=False):
         if not torch.cuda.is_available():
             raise RuntimeError("GraphedTrainStep needs a CUDA device: this package has no CPU path")
         self.model, self.optimizer, self.graphs, self.loss_fn = model, optimizer, graphs, loss_fn
@@ -24,16 +37,33 @@ class GraphedTrainStep:
             if not g.get("capturable", False):
                 raise ValueError("GraphedTrainStep: build the optimizer with capturable=True (e.g. Adam(fused=True, capturable=True))")
         self._norm_flags = (getattr(gn, "norm_uvp", True), getattr(gn, "norm_global", True))
+        norm = getattr(model, "node_norm", None)
+        self._norm, self._norm_max = norm, None
+        # warm-up (allocator pools, lazy initialisation) on a snapshot: construction leaves model and optimizer untouched
+        model_state = {k: v.detach().clone() for k, v in model.state_dict().items()}
+        opt_state = copy.deepcopy(optimizer.state_dict())
         side = torch.cuda.Stream()
         side.wait_stream(torch.cuda.current_stream())
         with torch.cuda.stream(side):
             for _ in range(max(warmup, 1)):
                 self._eager_step()
         torch.cuda.current_stream().wait_stream(side)
-        norm = getattr(model, "node_norm", None)
+        with torch.no_grad():
+            for k, v in model.state_dict().items():
+                v.copy_(model_state[k])
+        optimizer.load_state_dict(opt_state)
+        if norm is not None:
+            norm._n_acc_host = None
+        ops.PackedWeights.invalidate()
         if norm is not None and norm.wants_accumulation():
             if not freeze_normalizer:
-                raise RuntimeError("the Normalizer is still accumulating; capture after it froze or pass freeze_normalizer=True")
+                raise RuntimeError("GraphedTrainStep: the Normalizer is still accumulating (num_accumulations < dataset_size); "
+                                   "capture after it froze or pass freeze_normalizer=True to freeze its statistics while "
+                                   "this object is alive")
+            warnings.warn("GraphedTrainStep(freeze_normalizer=True): the Normalizer stops accumulating at "
+                          f"{float(norm.num_accumulations):.0f} accumulations until close() is called; a checkpoint saved "
+                          "meanwhile holds these statistics")
+            self._norm_max = norm.max_accumulations
             norm.max_accumulations = float(norm.num_accumulations)  # statistics stay as accumulated so far
         if norm is not None:
             norm._n_acc_host = float(norm.num_accumulations)        # host mirror fixed now: no device sync inside the capture
@@ -72,4 +102,12 @@ class GraphedTrainStep:
             self.x_static.copy_(x, non_blocking=True)
         self.graph.replay()
         self.replays += 1
+        ops.PackedWeights.invalidate()   # the replayed optimizer step rewrote the weights without touching Tensor._version
         return self.loss
+
+    def close(self):
+        """Drop the captured graph and give the Normalizer its accumulation window back."""
+        if self._norm is not None and self._norm_max is not None:
+            self._norm.max_accumulations = self._norm_max
+            self._norm_max = None
+        self.graph = None

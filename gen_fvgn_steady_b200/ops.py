@@ -11,7 +11,17 @@ import torch
 from . import _lib
 from ._lib import fptr, iptr
 
-PREC = {"fp32": _lib.FVGN_PREC_FP32, "bf16": _lib.FVGN_PREC_BF16}
+PREC = {"fp32": _lib.FVGN_PREC_FP32, "bf16": _lib.FVGN_PREC_BF16, "f16": _lib.FVGN_PREC_F16}
+# tensor-core (tcgen05) modes and the torch dtype of their 16-bit operand streams:
+#   bf16: bfloat16 operands (8-bit significand);
+#   f16 : IEEE-half operands -- the 11-bit significand of TF32, the arithmetic the reference's GPU path runs its Linear
+#         layers in (src/pre_train_Adam.py:29) -- with the backward's gradient operands pre-scaled by a power of two
+#         (GradScaleFn below) so that they stay inside half's exponent range.
+HDTYPE = {"bf16": torch.bfloat16, "f16": torch.float16}
+
+
+def is_tc(precision):
+    return precision in HDTYPE
 
 
 def default_precision():
@@ -28,14 +38,17 @@ def _c(t):
 
 # ------------------------------------------------------------------ raw kernel calls
 BF16 = torch.bfloat16
+_TCODE = {torch.float32: _lib.FVGN_T_F32, torch.bfloat16: _lib.FVGN_T_BF16, torch.float16: _lib.FVGN_T_F16}
 
 
 def hptr(t, allow_none=False):
-    return _lib.ptr(t, BF16, allow_none)
+    if t is not None and t.dtype not in (torch.bfloat16, torch.float16):
+        raise RuntimeError(f"fvgn_b200: expected a 16-bit operand stream, got {t.dtype}")
+    return _lib.ptr(t, None, allow_none)
 
 
 def _tcode(t):
-    return _lib.FVGN_T_BF16 if t.dtype == BF16 else _lib.FVGN_T_F32
+    return _TCODE[t.dtype]
 
 
 def adj_reduce(src, plan, width, flags=0, out=None, out_dtype=torch.float32):
@@ -63,11 +76,13 @@ def inc_reduce(src, plan, width, out_dtype=torch.float32):
     return out
 
 
-def shadow(t, cached=None):
-    """bf16 row-major shadow of an fp32 latent; `cached` = (master, shadow) as attached by the producing kernel."""
-    if cached is not None and cached[0] is t and cached[1] is not None:
+def shadow(t, cached=None, dtype=BF16):
+    """16-bit row-major shadow of an fp32 latent; `cached` = (master, shadow) as attached by the producing kernel."""
+    if cached is not None and cached[0] is t and cached[1] is not None and cached[1].dtype == dtype:
         return cached[1]
-    return t.detach().to(BF16).contiguous()
+    if dtype == torch.float16:
+        return t.detach().clamp(-65504.0, 65504.0).to(dtype).contiguous()   # saturate like the kernels' conversions
+    return t.detach().to(dtype).contiguous()
 
 
 _MLP_K1 = {_lib.FVGN_MLP_EDGE: 384, _lib.FVGN_MLP_NODE: 192, _lib.FVGN_MLP_ENC_NODE: 12, _lib.FVGN_MLP_ENC_EDGE: 15,
@@ -75,23 +90,31 @@ _MLP_K1 = {_lib.FVGN_MLP_EDGE: 384, _lib.FVGN_MLP_NODE: 192, _lib.FVGN_MLP_ENC_N
 
 
 class PackedWeights:
-    """bf16 UMMA operand images of the MLP weights.  Cached per (w1, w2, w3) tensor objects (weak references) and
-    rebuilt whenever a parameter's version counter moves (optimizer step, load_state_dict, ...)."""
+    """16-bit UMMA operand images of the MLP weights.  Cached per (w1, w2, w3) tensor objects (weak references) and
+    rebuilt whenever a parameter's version counter moves (optimizer step, load_state_dict, ...) or the global
+    generation is bumped: PackedWeights.invalidate() is what code that rewrites weights behind autograd's back must call
+    (CUDA-graph replays of an optimizer step, `p.data` surgery, external kernels) -- graphed.GraphedTrainStep does."""
     _cache = {}
+    _generation = 0
 
     @classmethod
-    def get(cls, mode, params):
+    def invalidate(cls):
+        cls._generation += 1
+
+    @classmethod
+    def get(cls, mode, params, precision="bf16"):
         import weakref
         w1, w2, w3 = params[0], params[2], params[4]
-        key = (id(w1), id(w2), id(w3), mode)
-        ver = (w1._version, w2._version, w3._version, w1.data_ptr(), w2.data_ptr(), w3.data_ptr())
+        key = (id(w1), id(w2), id(w3), mode, precision)
+        ver = (w1._version, w2._version, w3._version, w1.data_ptr(), w2.data_ptr(), w3.data_ptr(), cls._generation)
         hit = cls._cache.get(key)
         if hit is not None and hit[0] == ver and all(r() is t for r, t in zip(hit[2], (w1, w2, w3))):
             return hit[1]
         nbytes = int(_lib.load().fvgn_mlp_packed_bytes(mode))
+        # always a fresh buffer: an autograd node of an earlier forward may still hold the previous image for its backward
         buf = torch.empty(max(nbytes, 16), dtype=torch.uint8, device=w1.device)
-        _lib.call("fvgn_mlp_pack_weights", mode, fptr(_c(w1.detach())), fptr(_c(w2.detach())), fptr(_c(w3.detach())),
-                  _lib.ptr(buf), _lib.stream_ptr(w1.device))
+        _lib.call("fvgn_mlp_pack_weights", mode, PREC[precision], fptr(_c(w1.detach())), fptr(_c(w2.detach())),
+                  fptr(_c(w3.detach())), _lib.ptr(buf), _lib.stream_ptr(w1.device))
         if len(cls._cache) > 256:
             cls._cache = {k: v for k, v in cls._cache.items() if all(r() is not None for r in v[2])}
         cls._cache[key] = (ver, buf, tuple(weakref.ref(t) for t in (w1, w2, w3)))
@@ -105,7 +128,7 @@ def _img_buffer(nbytes, device):
 
 
 class Z1Image:
-    """bf16 tile images of the first pre-activation (written by the bf16 forward, consumed by its backward)."""
+    """16-bit tile images of the first pre-activation (written by the tensor-core forward, consumed by its backward)."""
 
     def __init__(self, mode, rows, device):
         nbytes = int(_lib.load().fvgn_mlp_bwd_workspace_bytes(mode, PREC["bf16"], rows))
@@ -126,15 +149,15 @@ def _mlp_desc(mode, precision, rows, params, in0, in1=None, idx_s=None, idx_r=No
     d.w1, d.b1, d.w2, d.b2, d.w3, d.b3 = (fptr(p) for p in ps[:6])
     if len(ps) == 8:
         d.ln_g, d.ln_b = fptr(ps[6]), fptr(ps[7])
-    if precision == "bf16":
-        d._packed = packed if packed is not None else PackedWeights.get(mode, params)
+    if is_tc(precision):
+        d._packed = packed if packed is not None else PackedWeights.get(mode, params, precision)
         d.w_bf16 = _lib.ptr(d._packed)
         if mode in _SHADOW_MODES:
-            # layer-1 operands are read from bf16 shadows; make them here when the caller has none (stand-alone use)
+            # layer-1 operands are read from 16-bit shadows; make them here when the caller has none (stand-alone use)
             if in0h is None:
-                in0h = shadow(in0)
+                in0h = shadow(in0, dtype=HDTYPE[precision])
             if in1h is None and in1 is not None:
-                in1h = shadow(in1)
+                in1h = shadow(in1, dtype=HDTYPE[precision])
             d._h = (in0h, in1h)
             d.in0h, d.in1h = hptr(in0h), hptr(in1h, True)
     return d
@@ -151,12 +174,12 @@ def mlp_forward(mode, precision, rows, params, in0, in1=None, idx_s=None, idx_r=
     res = _empty((rows, 128), like) if want_res else None
     d.out, d.out_res = fptr(out, True), fptr(res, True)
     outh = resh = None
-    if precision == "bf16":
+    if is_tc(precision):
         if want_outh:
-            outh = torch.empty((rows, 128), dtype=BF16, device=like.device)
+            outh = torch.empty((rows, 128), dtype=HDTYPE[precision], device=like.device)
             d.outh = hptr(outh)
         if want_resh:
-            resh = torch.empty((rows, 128), dtype=BF16, device=like.device)
+            resh = torch.empty((rows, 128), dtype=HDTYPE[precision], device=like.device)
             d.out_resh = hptr(resh)
         if z1 is not None:
             d.z1_img = z1.ptr
@@ -167,13 +190,14 @@ def mlp_forward(mode, precision, rows, params, in0, in1=None, idx_s=None, idx_r=
 
 
 def new_z1(mode, precision, rows, like):
-    return Z1Image(mode, rows, like.device) if precision == "bf16" else None
+    return Z1Image(mode, rows, like.device) if is_tc(precision) else None
 
 
 def _z1_for(ctx, mode, precision, rows, like):
     """The Z1 image is only needed by a backward pass: under torch.no_grad() / with nothing requiring a gradient (the
-    rollout regime of solve_without_grad_GPU.py) the forward kernel skips that store (256 B per row) altogether."""
-    return new_z1(mode, precision, rows, like) if any(ctx.needs_input_grad) else None
+    rollout regime of solve_without_grad_GPU.py) the forward kernel skips that store (256 B per row) altogether.
+    ctx.needs_input_grad mirrors requires_grad of the inputs even under no_grad, hence the explicit grad-mode test."""
+    return new_z1(mode, precision, rows, like) if (torch.is_grad_enabled() and any(ctx.needs_input_grad)) else None
 
 
 def mlp_backward(mode, precision, rows, params, in0, in1, idx_s, idx_r, d_out, d_gather=None, d_in0=None, d_in1=None,
@@ -182,7 +206,7 @@ def mlp_backward(mode, precision, rows, params, in0, in1, idx_s, idx_r, d_out, d
     packed: the bf16 weight image used by the matching forward (bf16 mode); repacked from `params` when None.
     z1: the Z1Image the matching bf16 forward filled; when None (stand-alone use) the forward is re-run to make it.
     d_in0h: EDGE, bf16 mode: [E,256] bf16 destination of d(agg[s])|d(agg[r]) (instead of the fp32 d_in0)."""
-    if precision == "bf16" and z1 is None and rows > 0:
+    if is_tc(precision) and z1 is None and rows > 0:
         z1 = new_z1(mode, precision, rows, d_out)
         mlp_forward(mode, precision, rows, params, in0, in1, idx_s, idx_r, want_out=True, want_res=False, flags=flags,
                     packed=packed, z1=z1, in0h=in0h, in1h=in1h)
@@ -199,6 +223,8 @@ def mlp_backward(mode, precision, rows, params, in0, in1, idx_s, idx_r, d_out, d
     if d_gatherh is not None:
         d.d_gatherh = hptr(d_gatherh)
     d.partials, d.n_partials, d.d_params = fptr(partials), npart, fptr(flat)
+    if precision == "f16":
+        d.grad_unscale = grad_scale(d_out.device)[1:2].data_ptr()
     ws_bytes = int(lib.fvgn_mlp_bwd_workspace_bytes(mode, PREC[precision], rows))
     if ws_bytes > 0 and rows > 0:
         d._ws, d.workspace = _img_buffer(ws_bytes, d_out.device)
@@ -220,7 +246,51 @@ def mlp_backward(mode, precision, rows, params, in0, in1, idx_s, idx_r, d_out, d
 
 
 def _packed(mode, precision, params):
-    return PackedWeights.get(mode, params) if precision == "bf16" else None
+    return PackedWeights.get(mode, params, precision) if is_tc(precision) else None
+
+
+# ------------------------------------------------------------------ gradient pre-scaling of the f16 mode
+_GRAD_SCALE = {}
+GRAD_SCALE_TARGET = 16.0   # the largest |d raw| of a backward pass is brought into [8, 16)
+
+
+def grad_scale(device):
+    """Device record [S, 1/S] of the current backward pass (S = 1 until a GradScaleFn.backward has run)."""
+    key = str(device)
+    if key not in _GRAD_SCALE:
+        _GRAD_SCALE[key] = torch.ones(2, dtype=torch.float32, device=device)
+    return _GRAD_SCALE[key]
+
+
+class GradScaleFn(torch.autograd.Function):
+    """Identity in forward.  Backward (f16 mode only): the gradient entering the network (d loss / d decoder output) is
+    multiplied by S = 2^k, k chosen on the device so that its largest magnitude lands in [8, 16): half-precision gradient
+    operands of the tensor-core backward (11-bit significand, 5-bit exponent) then sit in the middle of their range.
+    The backward pass is linear in that gradient, so every fp32 gradient stream upstream carries S times its value and
+    every PARAMETER gradient is multiplied by 1/S where it is emitted (fvgn_mlp_desc.grad_unscale for the fused MLPs,
+    _unscale() for the Transolver block): both factors are powers of two, i.e. exact.  No host synchronisation."""
+
+    @staticmethod
+    def forward(ctx, raw):
+        return raw.view_as(raw)
+
+    @staticmethod
+    def backward(ctx, g):
+        rec = grad_scale(g.device)
+        amax = g.detach().abs().max()
+        k = torch.floor(torch.log2(GRAD_SCALE_TARGET / amax.clamp(min=1e-30))).clamp(-60.0, 60.0)
+        k = torch.where(torch.isfinite(amax) & (amax > 0), k, torch.zeros_like(k))
+        rec[0] = torch.exp2(k)
+        rec[1] = torch.exp2(-k)
+        return g * rec[0]
+
+
+def _unscale(precision, grads, device):
+    """f16 mode: parameter gradients computed by PyTorch / the ts_* kernels from pre-scaled streams -> true scale."""
+    if precision != "f16":
+        return grads
+    inv = grad_scale(device)[1]
+    return tuple(None if g is None else g * inv for g in grads)
 
 
 # ------------------------------------------------------------------ Encoder
@@ -234,7 +304,7 @@ class EncoderFn(torch.autograd.Function):
         ctx.set_materialize_grads(False)  # no zero tensors for the (non-differentiable) bf16 shadow outputs
         ctx.pk = (_packed(_lib.FVGN_MLP_ENC_NODE, precision, nb), _packed(_lib.FVGN_MLP_ENC_EDGE, precision, eb))
         ctx.z1 = (_z1_for(ctx, _lib.FVGN_MLP_ENC_NODE, precision, plan.N, xn), _z1_for(ctx, _lib.FVGN_MLP_ENC_EDGE, precision, plan.E, xn))
-        bf = precision == "bf16"
+        bf = is_tc(precision)
         rn = mlp_forward(_lib.FVGN_MLP_ENC_NODE, precision, plan.N, nb, xn, packed=ctx.pk[0], z1=ctx.z1[0], want_outh=bf)
         re = mlp_forward(_lib.FVGN_MLP_ENC_EDGE, precision, plan.E, eb, xn, pos, plan.edge_s, plan.edge_r, packed=ctx.pk[1],
                          z1=ctx.z1[1], want_outh=bf)
@@ -281,9 +351,10 @@ class GnBlockFn(torch.autograd.Function):
         ctx.set_materialize_grads(False)  # no zero tensors for the (non-differentiable) bf16 shadow outputs
         ctx.pk = (_packed(_lib.FVGN_MLP_EDGE, precision, eb), _packed(_lib.FVGN_MLP_NODE, precision, nb))
         ctx.plan, ctx.precision = plan, precision
-        if precision == "bf16":
-            xh = xh if xh is not None else shadow(x)
-            eh = eh if eh is not None else shadow(e)
+        if is_tc(precision):
+            BF16 = HDTYPE[precision]
+            xh = xh if (xh is not None and xh.dtype == BF16) else shadow(x, dtype=BF16)
+            eh = eh if (eh is not None and eh.dtype == BF16) else shadow(e, dtype=BF16)
             ctx.z1 = (_z1_for(ctx, _lib.FVGN_MLP_EDGE, precision, plan.E, x), _z1_for(ctx, _lib.FVGN_MLP_NODE, precision, plan.N, x))
             aggh = adj_reduce(xh, plan, 128, out_dtype=BF16)
             _, e_out, e_newh, e_outh = mlp_forward(_lib.FVGN_MLP_EDGE, precision, plan.E, eb, None, e, plan.edge_s, plan.edge_r,
@@ -317,10 +388,11 @@ class GnBlockFn(torch.autograd.Function):
         dev = x.device
         d_x_out = _c(d_x_out) if d_x_out is not None else torch.zeros((plan.N, 128), device=dev)
         d_e_out = _c(d_e_out) if d_e_out is not None else torch.zeros((plan.E, 128), device=dev)
-        d_a2 = _empty((plan.N, 64), d_x_out) if precision != "bf16" else None
+        d_a2 = _empty((plan.N, 64), d_x_out) if not is_tc(precision) else None
         d_x = _empty((plan.N, 128), d_x_out)
         d_e = _empty((plan.E, 128), d_x_out)
-        if precision == "bf16":
+        if is_tc(precision):
+            BF16 = HDTYPE[precision]
             xh, eh, aggh, a2h = x, e, agg, a2
             d_a2h = torch.empty((plan.N, 64), dtype=BF16, device=dev)
             g_nb = mlp_backward(_lib.FVGN_MLP_NODE, precision, plan.N, nb, None, None, None, None, d_x_out, None, None, d_x,
@@ -414,8 +486,8 @@ class DecoderFn(torch.autograd.Function):
         ctx.pk = _packed(_lib.FVGN_MLP_DEC, precision, params)
         ctx.z1 = _z1_for(ctx, _lib.FVGN_MLP_DEC, precision, x.shape[0], x)
         ctx.precision = precision
-        if precision == "bf16":
-            xh = xh if xh is not None else shadow(x)
+        if is_tc(precision):
+            xh = xh if (xh is not None and xh.dtype == HDTYPE[precision]) else shadow(x, dtype=HDTYPE[precision])
             out, _ = mlp_forward(_lib.FVGN_MLP_DEC, precision, x.shape[0], params, None, packed=ctx.pk, z1=ctx.z1, in0h=xh)
             ctx.save_for_backward(xh, *params)
         else:
@@ -428,7 +500,7 @@ class DecoderFn(torch.autograd.Function):
         x, *params = ctx.saved_tensors
         d_out = _c(d_out)
         d_x = _empty((x.shape[0], 128), d_out)
-        if ctx.precision == "bf16":
+        if is_tc(ctx.precision):
             g = mlp_backward(_lib.FVGN_MLP_DEC, ctx.precision, x.shape[0], params, None, None, None, None, d_out, None, d_x,
                              packed=ctx.pk, z1=ctx.z1, in0h=x)
             ctx.z1 = None
@@ -749,8 +821,11 @@ def _tail_forward(a, bo, res, gamma, beta, w1, b1, w2, b2, want_shadow):
     _lib.call("fvgn_ts_bias_gelu_forward", fptr(hpre), fptr(b1c), fptr(h), n, st)
     o = h @ w2.t()
     out = _empty((n, 128), a)
-    outh = torch.empty((n, 128), dtype=BF16, device=a.device) if want_shadow else None
-    _lib.call("fvgn_ts_bias_residual", fptr(o), fptr(_c(b2.detach())), fptr(y), fptr(out), hptr(outh, True), n, st)
+    # want_shadow: None / False, or the 16-bit dtype of the shadow the next GnBlock / decoder reads
+    sdt = BF16 if want_shadow is True else (want_shadow or None)
+    outh = torch.empty((n, 128), dtype=sdt, device=a.device) if sdt is not None else None
+    _lib.call("fvgn_ts_bias_residual", fptr(o), fptr(_c(b2.detach())), fptr(y), fptr(out), hptr(outh, True),
+              _TCODE[sdt] if sdt is not None else 0, n, st)
     return out, outh, (y, stats, z, hpre, h, gc, w1, b1c, w2)
 
 
@@ -783,15 +858,16 @@ class SliceAttentionFn(torch.autograd.Function):
     de-slice and their autograd are the ts_* kernels; the [B,8,32,16] token attention is PyTorch glue."""
 
     @staticmethod
-    def forward(ctx, x, wfx, bfx, wx, bx, ws, bs, temp, wq, wk, wv, wo, scale, tsp, halo):
+    def forward(ctx, x, wfx, bfx, wx, bx, ws, bs, temp, wq, wk, wv, wo, scale, tsp, halo, precision=None):
         a, saved = _attn_forward(_c(x), wfx, bfx, wx, bx, ws, bs, temp, wq, wk, wv, wo, scale, tsp, halo)
-        ctx.tsp, ctx.halo, ctx.scale = tsp, halo, scale
+        ctx.tsp, ctx.halo, ctx.scale, ctx.precision = tsp, halo, scale, precision
         ctx.save_for_backward(*saved)
         return a
 
     @staticmethod
     def backward(ctx, d_a):
-        return (*_attn_backward(ctx.saved_tensors, d_a, ctx.scale, ctx.tsp, ctx.halo), None, None, None)
+        g = _attn_backward(ctx.saved_tensors, d_a, ctx.scale, ctx.tsp, ctx.halo)
+        return (g[0], *_unscale(ctx.precision, g[1:], d_a.device), None, None, None, None)
 
 
 class TransolverBlockFn(torch.autograd.Function):
@@ -808,6 +884,7 @@ class TransolverBlockFn(torch.autograd.Function):
         a, s1 = _attn_forward(x, wfx, bfx, wx, bx, ws, bs, temp, wq, wk, wv, wo, scale, tsp, halo)
         out, outh, s2 = _tail_forward(a, bo, x, gamma, beta, w1, b1, w2, b2, want_shadow)
         ctx.tsp, ctx.halo, ctx.scale, ctx.n1, ctx.has_b = tsp, halo, scale, len(s1), xb is not None
+        ctx.precision = "f16" if want_shadow == torch.float16 else None
         ctx.set_materialize_grads(False)
         if outh is not None:
             ctx.mark_non_differentiable(outh)
@@ -819,8 +896,8 @@ class TransolverBlockFn(torch.autograd.Function):
         s1, s2 = ctx.saved_tensors[:ctx.n1], ctx.saved_tensors[ctx.n1:]
         d_y, d_bo, d_gamma, d_beta, d_w1, d_b1, d_w2, d_b2 = _tail_backward(s2, d_out)
         g = _attn_backward(s1, d_y, ctx.scale, ctx.tsp, ctx.halo, d_res=d_y)   # d fx = dP Wcat + d_y in one GEMM
-        return (g[0], g[0] if ctx.has_b else None, *g[1:], d_bo, d_gamma, d_beta, d_w1, d_b1, d_w2, d_b2, None, None, None,
-                None)
+        pg = _unscale(ctx.precision, (*g[1:], d_bo, d_gamma, d_beta, d_w1, d_b1, d_w2, d_b2), d_out.device)
+        return (g[0], g[0] if ctx.has_b else None, *pg, None, None, None, None)
 
 
 class BlockTailFn(torch.autograd.Function):
@@ -830,6 +907,7 @@ class BlockTailFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, a, bo, res, gamma, beta, w1, b1, w2, b2, want_shadow):
         out, outh, saved = _tail_forward(_c(a), bo, _c(res), gamma, beta, w1, b1, w2, b2, want_shadow)
+        ctx.precision = "f16" if want_shadow == torch.float16 else None
         ctx.set_materialize_grads(False)
         if outh is not None:
             ctx.mark_non_differentiable(outh)
@@ -839,6 +917,8 @@ class BlockTailFn(torch.autograd.Function):
     @staticmethod
     def backward(ctx, d_out, _dh=None):
         d_y, d_bo, d_gamma, d_beta, d_w1, d_b1, d_w2, d_b2 = _tail_backward(ctx.saved_tensors, d_out)
+        d_bo, d_gamma, d_beta, d_w1, d_b1, d_w2, d_b2 = _unscale(ctx.precision, (d_bo, d_gamma, d_beta, d_w1, d_b1, d_w2, d_b2),
+                                                                 d_out.device)
         return d_y, d_bo, d_y, d_gamma, d_beta, d_w1, d_b1, d_w2, d_b2, None
 
 

@@ -117,7 +117,10 @@ class GraphPlan:
         self.cell_chunks, self.cell_chunk_ptr, self.n_cell_chunks = _chunks(graph_cell.batch, self.B)
         # geometry (fp32 copies in the layout the kernels read)
         self.pos = graph_node.pos.to(f32).contiguous()
-        self.y = graph_node.y.to(f32).contiguous()
+        # Dirichlet targets: the reference reads graph_node.y[:, 0:2] (importer.py:141-154); a loader may carry more columns
+        if graph_node.y.dim() != 2 or graph_node.y.shape[1] < 2:
+            raise ValueError(f"graph_node.y must be [N, >=2] (u, v targets), got {tuple(graph_node.y.shape)}")
+        self.y = graph_node.y[:, 0:2].to(f32).contiguous()
         self.node_type = _i32(graph_node.node_type.reshape(-1))
         self.face_pos = graph_edge.pos.to(f32).contiguous()
         self.face_area = graph_edge.face_area.reshape(-1).to(f32).contiguous()

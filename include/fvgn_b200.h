@@ -45,10 +45,11 @@ int fvgn_adj_reduce(const float* src, const int32_t* ptr, const int32_t* nbr, fl
  * agg[senders]/agg[receivers] gathers of blocks.py:101-107 in backward. */
 int fvgn_inc_reduce(const float* src, const int32_t* ptr, const int32_t* code, float* dst, int64_t n_rows,
                     int32_t width, void* stream);
-/* Typed variants for the bf16 throughput mode: src / dst element type chosen by FVGN_T_* (accumulation is always fp32
- * in CSR order).  dst2, when non-NULL, receives a second copy of the result in the other type (fp32 <-> bf16). */
+/* Typed variants for the 16-bit tensor-core modes: src / dst element type chosen by FVGN_T_* (accumulation is always
+ * fp32 in CSR order). */
 #define FVGN_T_F32 0
 #define FVGN_T_BF16 1
+#define FVGN_T_F16 2
 int fvgn_adj_reduce_t(const void* src, int32_t src_type, const int32_t* ptr, const int32_t* nbr, void* dst, int32_t dst_type,
                       int64_t n_rows, int32_t width, int32_t flags, void* stream);
 int fvgn_inc_reduce_t(const void* src, int32_t src_type, const int32_t* ptr, const int32_t* code, void* dst,
@@ -63,6 +64,9 @@ int fvgn_inc_reduce_t(const void* src, int32_t src_type, const int32_t* ptr, con
 #define FVGN_MLP_NO_RESIDUAL 1 /* desc.flags */
 #define FVGN_PREC_FP32 0    /* SIMT fp32 FMA (parity mode, rel 1e-5 vs the reference's CPU fp32)   */
 #define FVGN_PREC_BF16 1    /* tcgen05.mma kind::f16 bf16 operands, fp32 accumulate in TMEM (throughput mode) */
+#define FVGN_PREC_F16 2     /* tcgen05.mma kind::f16 IEEE-half operands: the 11-bit significand of TF32, the arithmetic the
+                               reference's GPU path uses for its Linear layers (src/pre_train_Adam.py:29), at the bytes of
+                               bf16; fp32 accumulate; same kernels, same layouts ("bf16" below reads "16-bit") */
 
 typedef struct fvgn_mlp_desc {
   int32_t mode;      /* FVGN_MLP_*  */
@@ -105,14 +109,20 @@ typedef struct fvgn_mlp_desc {
   void* out_resh;  /* bf16 shadow of out_res; optional */
   void* d_in0h;    /* backward, bf16 destination instead of the fp32 d_in0: EDGE [E,256] = d(agg[s]) | d(agg[r]); NODE d_a2[N,64] */
   const void* d_gatherh; /* EDGE backward: bf16 d_a1[N,64] gathered instead of the fp32 d_gather */
+  /* backward, optional device scalar: every parameter gradient is multiplied by *grad_unscale when it leaves the
+   * deterministic partial reduction (1 / S of the power-of-two gradient pre-scaling the FVGN_PREC_F16 mode applies at the
+   * root of the backward pass so that half-precision gradient operands stay in range; exact). */
+  const float* grad_unscale;
 } fvgn_mlp_desc;
 
 int64_t fvgn_mlp_param_count(int32_t mode);
 int32_t fvgn_mlp_bwd_partials(int32_t mode, int32_t precision, int64_t rows); /* number of per-CTA partial buffers to allocate */
 int64_t fvgn_mlp_bwd_workspace_bytes(int32_t mode, int32_t precision, int64_t rows);
 int64_t fvgn_mlp_packed_bytes(int32_t mode);
-/* fp32 parameters -> bf16 UMMA operand image (weights change every optimiser step; call once per step) */
-int fvgn_mlp_pack_weights(int32_t mode, const float* w1, const float* w2, const float* w3, void* packed, void* stream);
+/* fp32 parameters -> 16-bit UMMA operand image in the format of `precision` (FVGN_PREC_BF16 / FVGN_PREC_F16); weights
+ * change every optimiser step: call once per step */
+int fvgn_mlp_pack_weights(int32_t mode, int32_t precision, const float* w1, const float* w2, const float* w3, void* packed,
+                          void* stream);
 int fvgn_mlp_forward(const fvgn_mlp_desc* d, void* stream);
 int fvgn_mlp_backward(const fvgn_mlp_desc* d, void* stream);
 
@@ -226,8 +236,10 @@ int fvgn_ts_residual_ln_backward(const float* dz, const float* y, const float* s
 int fvgn_ts_bias_gelu_forward(const float* hpre, const float* bias, float* h, int64_t n, void* stream);
 int fvgn_ts_bias_gelu_backward(const float* dh, const float* hpre, const float* bias, float* dhpre, float* partial, int64_t n,
                                void* stream);
-/* out[N,128] = a + bias + res (+ bf16 shadow outh, nullable) (linear_post bias + residual, :168) */
-int fvgn_ts_bias_residual(const float* a, const float* bias, const float* res, float* out, void* outh, int64_t n, void* stream);
+/* out[N,128] = a + bias + res (+ 16-bit shadow outh of type outh_type = FVGN_T_BF16 / FVGN_T_F16, nullable)
+ * (linear_post bias + residual, :168) */
+int fvgn_ts_bias_residual(const float* a, const float* bias, const float* res, float* out, void* outh, int32_t outh_type,
+                          int64_t n, void* stream);
 
 #ifdef __cplusplus
 }

@@ -33,9 +33,10 @@ else:
     code = _lib.FVGN_MLP_NODE
 d_out = rn(rows, 128)
 z1 = ops.new_z1(code, prec, rows, in0)
-bf = prec == "bf16"
-in0h, in1h = (ops.shadow(in0), ops.shadow(in1)) if bf else (None, None)
-d_in0h = torch.empty((rows, 256), dtype=torch.bfloat16, device=dev) if (bf and mode == "EDGE") else None
+bf = ops.is_tc(prec)
+hdt = ops.HDTYPE.get(prec)
+in0h, in1h = (ops.shadow(in0, dtype=hdt), ops.shadow(in1, dtype=hdt)) if bf else (None, None)
+d_in0h = torch.empty((rows, 256), dtype=hdt, device=dev) if (bf and mode == "EDGE") else None
 fwd = lambda: ops.mlp_forward(code, prec, rows, params, in0, in1, s, r, want_out=not bf, want_res=True, z1=z1, in0h=in0h,
                               in1h=in1h, want_outh=bf and mode == "EDGE", want_resh=bf)
 bwd = lambda: ops.mlp_backward(code, prec, rows, params, in0, in1, s, r, d_out, d_gather, None if d_in0h is not None else d_in0,
