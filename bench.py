@@ -39,6 +39,8 @@ def parse_args():
                          "GPU arithmetic); fp32: SIMT FMA mode")
     ap.add_argument("--cpu-cells", type=int, default=40_000, help="cell count of the bounded CPU-baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--kernel-summary", default=None, metavar="PATH",
+                    help="after the timed runs: 2 more steps under torch.profiler (CUPTI), per-kernel device time table -> PATH")
     ap.add_argument("--graph", action="store_true",
                     help="replay the whole step (fwd + bwd + Adam) as ONE CUDA graph (gen_fvgn_steady_b200.graphed); for the "
                          "launch-bound sizes of the reference's example meshes (10 k - 100 k cells), single GPU")
@@ -300,6 +302,19 @@ def run_ours(args):
     ms_e2e = timed(args.steps, True)
     clocks = sampler.stop() if rank == 0 else None
     last_loss = float(loss_host)
+
+    if args.kernel_summary and rank == 0:
+        from torch.profiler import profile, ProfilerActivity
+        with profile(activities=[ProfilerActivity.CUDA]) as prof:
+            for _ in range(2):
+                step(False)
+            torch.cuda.synchronize()
+        rows = sorted(((e.key, e.count, e.device_time_total / 1e3) for e in prof.key_averages()), key=lambda r: -r[2])
+        tot = sum(r[2] for r in rows)
+        with open(args.kernel_summary, "w") as f:
+            f.write(f"# torch.profiler (CUPTI) device time over 2 steps, in situ (concurrent, warm): total {tot:.3f} ms\n")
+            for k, c, ms in rows:
+                f.write(f"{ms:10.3f} ms {c:6d} {100 * ms / max(tot, 1e-9):5.1f}%  {k[:150]}\n")
 
     # dominant kernel: timed alone with CUDA events on the launching stream
     roof = dominant_kernel_roofline(model, plan, dev, args, p)

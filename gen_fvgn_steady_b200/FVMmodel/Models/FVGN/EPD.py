@@ -62,7 +62,7 @@ class Encoder(nn.Module):
         """graph_node.x is the normalised [N,12] feature; the [E,15] relative edge feature of
         importer.py:54-78 is computed inside the edge-encoder kernel from x and pos."""
         plan = GraphPlan.of(graph_node)
-        node_, edge_, nh, eh = ops.EncoderFn.apply(graph_node.x.contiguous(), graph_node.pos.float().contiguous(), plan,
+        node_, edge_, nh, eh = ops.apply(ops.EncoderFn, graph_node.x.contiguous(), graph_node.pos.float().contiguous(), plan,
                                                    _precision(self), *mlp_params(self.nb_encoder), *mlp_params(self.eb_encoder))
         # bf16 mode: the kernels also emit bf16 shadows of the latents; they travel with the graph as (master, shadow)
         return _carry(graph_node, x=node_, edge_attr=edge_, _fvgn_plan=plan, _xh=(node_, nh), _eh=(edge_, eh)), node_
@@ -79,7 +79,7 @@ class GnBlock(nn.Module):
     def forward(self, graph_node):
         plan = GraphPlan.of(graph_node)
         xh, eh = _shadow_of(graph_node, "_xh", graph_node.x), _shadow_of(graph_node, "_eh", graph_node.edge_attr)
-        x, e, xh, eh = ops.GnBlockFn.apply(graph_node.x, graph_node.edge_attr, xh, eh, plan, _precision(self),
+        x, e, xh, eh = ops.apply(ops.GnBlockFn, graph_node.x, graph_node.edge_attr, xh, eh, plan, _precision(self),
                                            *mlp_params(self.eb_module.net), *mlp_params(self.nb_module.net))
         return _carry(graph_node, x=x, edge_attr=e, _fvgn_plan=plan, _xh=(x, xh), _eh=(e, eh))
 
@@ -94,7 +94,7 @@ class Decoder(nn.Module):
 
     def forward(self, latent_graph_node=None):
         xh = _shadow_of(latent_graph_node, "_xh", latent_graph_node.x)
-        return ops.DecoderFn.apply(latent_graph_node.x, xh, _precision(self), *mlp_params(self.node_decode_module))
+        return ops.apply(ops.DecoderFn, latent_graph_node.x, xh, _precision(self), *mlp_params(self.node_decode_module))
 
 
 class EncoderProcesserDecoder(nn.Module):

@@ -26,7 +26,7 @@ class EdgeBlock(nn.Module):
 
     def forward(self, graph_node, graph_cell=None):
         plan = GraphPlan.of(graph_node)
-        e_new = ops.EdgeBlockFn.apply(graph_node.x, graph_node.edge_attr, plan, _precision(self), *mlp_params(self.net))
+        e_new = ops.apply(ops.EdgeBlockFn, graph_node.x, graph_node.edge_attr, plan, _precision(self), *mlp_params(self.net))
         return Data(x=graph_node.x, edge_attr=e_new, edge_index=graph_node.edge_index, face=getattr(graph_node, "face", None),
                     num_graphs=getattr(graph_node, "num_graphs", None), batch=getattr(graph_node, "batch", None),
                     _fvgn_plan=plan)
@@ -39,7 +39,7 @@ class NodeBlock(nn.Module):
 
     def forward(self, graph_node, graph_cell=None):
         plan = GraphPlan.of(graph_node)
-        x_new = ops.NodeBlockFn.apply(graph_node.x, graph_node.edge_attr, plan, _precision(self), *mlp_params(self.net))
+        x_new = ops.apply(ops.NodeBlockFn, graph_node.x, graph_node.edge_attr, plan, _precision(self), *mlp_params(self.net))
         return Data(x=x_new, edge_attr=graph_node.edge_attr, edge_index=graph_node.edge_index,
                     face=getattr(graph_node, "face", None), num_graphs=getattr(graph_node, "num_graphs", None),
                     batch=getattr(graph_node, "batch", None), _fvgn_plan=plan)

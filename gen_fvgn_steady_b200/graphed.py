@@ -13,8 +13,8 @@ Construction does NOT advance training: the eager warm-up steps the capture need
 optimizer state, which is restored before the capture.  A Normalizer that is still accumulating cannot be captured (its
 host-side counter decides which kernels run): pass freeze_normalizer=True to freeze its statistics for the lifetime of
 this object (a warning says so; close() re-opens the window) or capture after `dataset_size` accumulations.
-Replays update the weights in place without moving Tensor._version, so every step() invalidates the packed 16-bit
-weight images (ops.PackedWeights): eager forwards between / after replays always see the current weights.
+The packed 16-bit weight images (ops.PackedWeights) are rebuilt by every forward, captured or eager, so replays and
+eager forwards between / after them always see the current weights.
 
 Every kernel of the path enqueues on torch's current stream and never allocates or synchronises (include/fvgn_b200.h),
 so the capture needs nothing special; torch's caching allocator serves the transient buffers from the graph's pool."""
@@ -22,8 +22,6 @@ import copy
 import warnings
 
 import torch
-
-from . import ops
 
 
 class GraphedTrainStep:
@@ -41,7 +39,8 @@ class GraphedTrainStep:
         self._norm, self._norm_max = norm, None
         # warm-up (allocator pools, lazy initialisation) on a snapshot: construction leaves model and optimizer untouched
         model_state = {k: v.detach().clone() for k, v in model.state_dict().items()}
-        opt_state = copy.deepcopy(optimizer.state_dict())
+        opt_state = {p: {k: (v.detach().clone() if torch.is_tensor(v) else copy.deepcopy(v)) for k, v in st.items()}
+                     for p, st in optimizer.state.items()}
         side = torch.cuda.Stream()
         side.wait_stream(torch.cuda.current_stream())
         with torch.cuda.stream(side):
@@ -51,10 +50,21 @@ class GraphedTrainStep:
         with torch.no_grad():
             for k, v in model.state_dict().items():
                 v.copy_(model_state[k])
-        optimizer.load_state_dict(opt_state)
+        # optimizer state: values back to the snapshot IN PLACE (a fresh optimizer: zeros), the tensors stay allocated --
+        # lazily creating them inside the capture would record their zero-initialisation into every replay
+        with torch.no_grad():
+            for p, st in optimizer.state.items():
+                old = opt_state.get(p)
+                for k, v in st.items():
+                    if torch.is_tensor(v):
+                        if old is not None and k in old:
+                            v.copy_(old[k])
+                        else:
+                            v.zero_()
+                    elif old is not None and k in old:
+                        st[k] = old[k]
         if norm is not None:
             norm._n_acc_host = None
-        ops.PackedWeights.invalidate()
         if norm is not None and norm.wants_accumulation():
             if not freeze_normalizer:
                 raise RuntimeError("GraphedTrainStep: the Normalizer is still accumulating (num_accumulations < dataset_size); "
@@ -102,7 +112,6 @@ class GraphedTrainStep:
             self.x_static.copy_(x, non_blocking=True)
         self.graph.replay()
         self.replays += 1
-        ops.PackedWeights.invalidate()   # the replayed optimizer step rewrote the weights without touching Tensor._version
         return self.loss
 
     def close(self):

@@ -90,34 +90,22 @@ _MLP_K1 = {_lib.FVGN_MLP_EDGE: 384, _lib.FVGN_MLP_NODE: 192, _lib.FVGN_MLP_ENC_N
 
 
 class PackedWeights:
-    """16-bit UMMA operand images of the MLP weights.  Cached per (w1, w2, w3) tensor objects (weak references) and
-    rebuilt whenever a parameter's version counter moves (optimizer step, load_state_dict, ...) or the global
-    generation is bumped: PackedWeights.invalidate() is what code that rewrites weights behind autograd's back must call
-    (CUDA-graph replays of an optimizer step, `p.data` surgery, external kernels) -- graphed.GraphedTrainStep does."""
-    _cache = {}
-    _generation = 0
+    """16-bit UMMA operand images of the MLP weights, rebuilt by EVERY forward (one ~3 us kernel per fused MLP; its
+    backward reuses the forward's image through ctx.pk).  Nothing is cached across forwards on purpose: Tensor._version
+    does not move under the in-place updates that matter most -- torch.optim.Adam(fused=True) leaves it untouched, and so
+    do CUDA-graph replays of an optimizer step or `p.data` surgery -- so a cache keyed on it served stale weights."""
 
-    @classmethod
-    def invalidate(cls):
-        cls._generation += 1
+    packs = 0   # pack launches so far (tests)
 
     @classmethod
     def get(cls, mode, params, precision="bf16"):
-        import weakref
         w1, w2, w3 = params[0], params[2], params[4]
-        key = (id(w1), id(w2), id(w3), mode, precision)
-        ver = (w1._version, w2._version, w3._version, w1.data_ptr(), w2.data_ptr(), w3.data_ptr(), cls._generation)
-        hit = cls._cache.get(key)
-        if hit is not None and hit[0] == ver and all(r() is t for r, t in zip(hit[2], (w1, w2, w3))):
-            return hit[1]
         nbytes = int(_lib.load().fvgn_mlp_packed_bytes(mode))
         # always a fresh buffer: an autograd node of an earlier forward may still hold the previous image for its backward
         buf = torch.empty(max(nbytes, 16), dtype=torch.uint8, device=w1.device)
         _lib.call("fvgn_mlp_pack_weights", mode, PREC[precision], fptr(_c(w1.detach())), fptr(_c(w2.detach())),
                   fptr(_c(w3.detach())), _lib.ptr(buf), _lib.stream_ptr(w1.device))
-        if len(cls._cache) > 256:
-            cls._cache = {k: v for k, v in cls._cache.items() if all(r() is not None for r in v[2])}
-        cls._cache[key] = (ver, buf, tuple(weakref.ref(t) for t in (w1, w2, w3)))
+        cls.packs += 1
         return buf
 
 
@@ -130,7 +118,10 @@ def _img_buffer(nbytes, device):
 class Z1Image:
     """16-bit tile images of the first pre-activation (written by the tensor-core forward, consumed by its backward)."""
 
+    made = 0   # instances so far (tests: a rollout forward makes none, a training step exactly one per fused MLP)
+
     def __init__(self, mode, rows, device):
+        Z1Image.made += 1
         nbytes = int(_lib.load().fvgn_mlp_bwd_workspace_bytes(mode, PREC["bf16"], rows))
         self.buf, self.ptr = _img_buffer(nbytes, device)
 
@@ -193,11 +184,25 @@ def new_z1(mode, precision, rows, like):
     return Z1Image(mode, rows, like.device) if is_tc(precision) else None
 
 
+_CALLER_GRAD_MODE = [True]
+
+
+def apply(fn, *args):
+    """fn.apply(*args) with the CALLER's grad mode recorded for _z1_for: inside Function.forward grad mode is always off
+    and ctx.needs_input_grad mirrors requires_grad of the inputs even under torch.no_grad(), so neither tells a training
+    forward from a rollout forward.  Direct fn.apply() calls keep the safe default (Z1 image written)."""
+    prev = _CALLER_GRAD_MODE[0]
+    _CALLER_GRAD_MODE[0] = torch.is_grad_enabled()
+    try:
+        return fn.apply(*args)
+    finally:
+        _CALLER_GRAD_MODE[0] = prev
+
+
 def _z1_for(ctx, mode, precision, rows, like):
     """The Z1 image is only needed by a backward pass: under torch.no_grad() / with nothing requiring a gradient (the
-    rollout regime of solve_without_grad_GPU.py) the forward kernel skips that store (256 B per row) altogether.
-    ctx.needs_input_grad mirrors requires_grad of the inputs even under no_grad, hence the explicit grad-mode test."""
-    return new_z1(mode, precision, rows, like) if (torch.is_grad_enabled() and any(ctx.needs_input_grad)) else None
+    rollout regime of solve_without_grad_GPU.py) the forward kernel skips that store (256 B per row) altogether."""
+    return new_z1(mode, precision, rows, like) if (_CALLER_GRAD_MODE[0] and any(ctx.needs_input_grad)) else None
 
 
 def mlp_backward(mode, precision, rows, params, in0, in1, idx_s, idx_r, d_out, d_gather=None, d_in0=None, d_in1=None,

@@ -77,15 +77,53 @@ def test_no_grad_forward_equals_training_forward(net):
     p = default_params(net=net, message_passing_num=2, dataset_size=1, precision="bf16")
     torch.manual_seed(0)
     model = NNmodel(p).to(dev)
-    outs = []
+    from gen_fvgn_steady_b200 import ops
+    outs, made = [], []
     for no_grad in (False, True):
         graphs = product_graphs([mesh], [uvp], dev)
+        m0 = ops.Z1Image.made
         with torch.no_grad() if no_grad else torch.enable_grad():
             out = model(*graphs, is_training=True)
+        made.append(ops.Z1Image.made - m0)
         outs.append([o.detach().clone() for o in out])
+        if not no_grad:   # the backward consumes the forward's images: it must not re-run a forward to make them
+            PU.script_loss(out, p).backward()
+            assert ops.Z1Image.made - m0 == made[0]
+    # one image per fused MLP with a backward (2 encoders + 2 per GnBlock + decoder); none in the rollout regime
+    assert made[0] == 2 + 2 * 2 * (2 if net == "TransFVGN_v2" else 1) + 1 and made[1] == 0, made
     # dataset_size=1: the Normalizer does not accumulate, both calls see the same statistics
     for a, b in zip(*outs):
         assert torch.equal(a, b)
+
+
+def test_weight_updates_invisible_to_autograd_are_seen():
+    """torch.optim.Adam(fused=True) (and CUDA-graph replays, p.data surgery) rewrite the weights without moving
+    Tensor._version: the next forward must still run on the current weights (the 16-bit weight images are rebuilt by every
+    forward, never cached across forwards)."""
+    import copy
+    from gen_fvgn_steady_b200.FVMmodel.importer import NNmodel
+    from gen_fvgn_steady_b200.utils.get_param import params as default_params
+    from gen_fvgn_steady_b200.mesh import synthetic as S
+    from tests.case_inputs import product_graphs
+    PU.use_real_kernels()
+    dev = torch.device("cuda")
+    mesh, uvp = S.make_case(20, kind="mixed", bc="channel", seed=2)
+    p = default_params(net="EPD", message_passing_num=2, dataset_size=1, precision="bf16")
+    torch.manual_seed(0)
+    model = NNmodel(p).to(dev)
+    opt = torch.optim.Adam(model.parameters(), lr=1e-2, fused=True)
+    versions = [q._version for q in model.parameters()]
+    loss0 = PU.script_loss(model(*product_graphs([mesh], [uvp], dev), is_training=True), p)
+    loss0.backward()
+    opt.step()
+    if [q._version for q in model.parameters()] != versions:
+        pytest.skip("this torch build bumps Tensor._version in the fused optimizer step")
+    with torch.no_grad():
+        seen = float(PU.script_loss(model(*product_graphs([mesh], [uvp], dev), is_training=True), p))
+        model._last = None
+        fresh = copy.deepcopy(model)     # new tensor objects: nothing that could be cached applies
+        want = float(PU.script_loss(fresh(*product_graphs([mesh], [uvp], dev), is_training=True), p))
+    assert seen == want and seen != float(loss0), (float(loss0), seen, want)
 
 
 def test_missing_library_fails_loudly(monkeypatch):
