@@ -34,11 +34,15 @@ def parse_args():
     ap.add_argument("--cells", type=int, default=int(os.environ.get("FVGN_BENCH_CELLS", 4_000_000)))
     ap.add_argument("--net", default=os.environ.get("FVGN_BENCH_NET", "EPD"))
     ap.add_argument("--mp", type=int, default=int(os.environ.get("FVGN_BENCH_MP", 6)))
-    ap.add_argument("--precision", default=os.environ.get("FVGN_PRECISION", "bf16"), choices=["bf16", "f16", "fp32"],
+    ap.add_argument("--precision", default=os.environ.get("FVGN_PRECISION", "f16"), choices=["bf16", "f16", "fp32"],
                     help="bf16 / f16: tcgen05 modes (f16 = IEEE-half operands, the 11-bit significand of the reference's TF32 "
                          "GPU arithmetic); fp32: SIMT FMA mode")
-    ap.add_argument("--cpu-cells", type=int, default=40_000, help="cell count of the bounded CPU-baseline sample")
+    ap.add_argument("--cpu-cells", type=int, default=0,
+                    help="cell count of the bounded CPU sample (cpu_baseline / --impl reference); 0 = sized from a calibration "
+                         "step so that the sample takes ~20 s (cpu_baseline) / the whole run ~3 min (--impl reference)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-extras", action="store_true",
+                    help="skip the sub-records (precision_modes, nets, example_meshes at N=1; cells at N>1)")
     ap.add_argument("--kernel-summary", default=None, metavar="PATH",
                     help="after the timed runs: 2 more steps under torch.profiler (CUPTI), per-kernel device time table -> PATH")
     ap.add_argument("--graph", action="store_true",
@@ -110,10 +114,11 @@ class ClockSampler:
 
 
 # ----------------------------------------------------------------------------------------------- CPU reference arm
-def cpu_reference_step_time(cells, net, mp, steps, warmup, threads):
+def cpu_reference_step_times(cells, net, mp, steps, warmup, threads):
     """The reference's algorithm on the host cores: oracle/fvgn_oracle.py (a CPU restatement pinned to the unmodified
-    reference's golden vectors; the reference itself needs torch_scatter/PyG and /root/reference, neither exists on the
-    GPU box).  fwd + backward + Adam on one synthetic quad mesh of `cells` cells.  Returns (sec/step, cells, N, E)."""
+    reference's golden vectors; the reference itself is Python that needs torch_scatter / PyG and /root/reference, none of
+    which exists on the GPU box, so it cannot travel).  fwd + backward + Adam on one synthetic quad mesh of `cells` cells,
+    initial weights from the same seeded initialiser as the GPU arm.  Returns ([sec per timed step], cells)."""
     from oracle import fvgn_oracle as O
     from gen_fvgn_steady_b200.FVMmodel.importer import NNmodel
     from gen_fvgn_steady_b200.utils.get_param import params as default_params
@@ -121,7 +126,7 @@ def cpu_reference_step_time(cells, net, mp, steps, warmup, threads):
     mesh, uvp = make_mesh(cells, 0, None)
     g = O.graphs_from_meshes([mesh], [uvp], torch.float32)
     torch.manual_seed(0)
-    model = NNmodel(default_params(net=net, message_passing_num=mp))
+    model = NNmodel(default_params(net=net, message_passing_num=mp))   # parameter container only: no kernel runs
     sd = {k: v.detach().clone() for k, v in model.state_dict().items()}
     leaves = {k: v.requires_grad_(True) for k, v in sd.items() if not k.startswith("node_norm.")}
     opt = torch.optim.Adam(list(leaves.values()), lr=5e-5)
@@ -135,48 +140,241 @@ def cpu_reference_step_time(cells, net, mp, steps, warmup, threads):
         opt.step()
         if it >= warmup:
             times.append(time.perf_counter() - t0)
-    C = int(g["centroid"].shape[0])
-    return float(np.mean(times)), C
+    return times, int(g["centroid"].shape[0])
+
+
+def cpu_sample_cells(net, mp, threads, n_steps, budget_s, lo=20_000, hi=1_000_000):
+    """Cell count of the bounded CPU sample: one calibration step at `lo` cells, then the largest mesh whose
+    `n_steps` steps fit `budget_s` seconds (the CPU path is linear in the mesh size)."""
+    t, c = cpu_reference_step_times(lo, net, mp, 1, 1, threads)
+    rate = c / t[0]
+    return int(min(max(rate * budget_s / max(n_steps, 1), lo), hi)), rate
 
 
 def run_reference(args):
+    """Reference arm: the reference's CPU path (the pinned port, see cpu_reference_step_times) on all host cores of the
+    box, same net / G / loss / metric as the GPU arm.  Each step is a BOUNDED SAMPLE of the GPU arm's 4 M-cell workload:
+    the largest mesh of the same generator for which warm-up + K steps end within ~3 minutes (stated in `config`)."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
     threads = os.cpu_count() or 1
-    sec, C = cpu_reference_step_time(args.cpu_cells, args.net, args.mp, max(args.steps, 1), max(min(args.warmup, 1), 0), threads)
+    warm = max(min(args.warmup, 1), 0)
+    steps = max(args.steps, 1)
+    cells = args.cpu_cells
+    if cells <= 0:
+        cells, _ = cpu_sample_cells(args.net, args.mp, threads, steps + warm, 170.0)
+    times, C = cpu_reference_step_times(cells, args.net, args.mp, steps, warm, threads)
+    sec = float(np.median(times))
     val = C / sec
-    sample = f"{C}-cell synthetic quad mesh (same generator, net, G, loss as the GPU arm), fwd+bwd+Adam, fp32, {threads} threads"
+    sample = (f"{C}-cell synthetic quad mesh (same generator, net, G, loss as the GPU arm's {args.cells}-cell mesh; sized so "
+              f"that {warm} warm-up + {steps} steps fit ~3 min), fwd+bwd+Adam, fp32, {threads} threads, median step")
     line = {"impl": "reference", "metric": "cells*steps/sec (fwd+bwd train step)", "value": val, "unit": "cells*steps/s",
             "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": sec * 1e3,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": workload_config(args, C_bench=C),
+            "config": dict(workload_config(args), precision="fp32 (CPU)", cpu_sample_cells=C),
             "cpu_baseline": {"value": val, "unit": "cells*steps/s", "cores": threads, "kind": "port", "sample": sample},
             "e2e": {"value": val, "unit": "cells*steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line))
 
 
-def _gn_blocks(args):
+def _gn_blocks(net, mp):
     """GnBlocks per forward: TransFVGN_v2 runs two processors of --mp blocks each (TransFVGN_v2.py:73-82)."""
-    return args.mp * (2 if args.net in ("TransFVGN_v2", "TransFVGN") else 1)
+    return mp * (2 if net in ("TransFVGN_v2", "TransFVGN") else 1)
 
 
-def workload_config(args, C_bench=None):
+def workload_config(args):
     return {"workload": f"synthetic jittered quad mesh, {args.cells} cells/GPU, cavity BC, NS theta; "
-                        f"{args.net} G={_gn_blocks(args)} + FV PDE loss; resident batch (solve_with_grad regime)",
-            "net": args.net, "gn_blocks": _gn_blocks(args), "cuda_graph": bool(getattr(args, "graph", False)), "cells_per_gpu": args.cells if C_bench is None else C_bench,
-            "precision": args.precision, "l2": "inputs/activations (GBs) far exceed the 126 MB L2; no explicit flush"}
+                        f"{args.net} G={_gn_blocks(args.net, args.mp)} + FV PDE loss; resident batch (solve_with_grad regime)",
+            "net": args.net, "gn_blocks": _gn_blocks(args.net, args.mp), "cuda_graph": bool(getattr(args, "graph", False)),
+            "cells_per_gpu": args.cells, "precision": args.precision,
+            "l2": "inputs/activations (GBs) far exceed the 126 MB L2; no explicit flush"}
+
+
+DTYPE_TEXT = {"fp32": "f32 (SIMT FMA)",
+              "bf16": "bf16 tcgen05 operands and derived streams; f32 accumulators, LayerNorm, residual streams and gradients of them",
+              "f16": "f16 tcgen05 operands and derived streams (11-bit significand = the reference's TF32 GPU arithmetic); f32 "
+                     "accumulators, LayerNorm, residual streams and gradients of them"}
 
 
 # ----------------------------------------------------------------------------------------------- our arm
+class Job:
+    """One resident-batch training job (model + optimizer + graphs) on this rank: step(), timed(), close()."""
+
+    def __init__(self, dev, rank, world, graphs, net, mp, precision, cells_mode=False, halo=None, graph=False, warmup=3):
+        from gen_fvgn_steady_b200.FVMmodel.importer import NNmodel
+        from gen_fvgn_steady_b200.plan import GraphPlan
+        from gen_fvgn_steady_b200.utils.get_param import params as default_params
+        from gen_fvgn_steady_b200 import parallel
+        self.dev, self.rank, self.world, self.cells_mode, self.halo = dev, rank, world, cells_mode, halo
+        self.parallel = parallel
+        self.graphs = graphs
+        gn, gx, ge, gc, gi = graphs
+        self.p = p = default_params(net=net, message_passing_num=mp, precision=precision)
+        torch.manual_seed(0)
+        self.model = model = NNmodel(p).to(dev)
+        if cells_mode:
+            model.enable_cell_partition(True)
+        elif world > 1:
+            model.enable_data_parallel(True)
+        self.flat_grad = parallel.flatten_gradients(model)
+        self.opt = torch.optim.Adam(model.parameters(), lr=p.lr, fused=True, capturable=bool(graph))
+        self.plan = plan = GraphPlan.of(gn, gx, ge, gc, p.order)
+        self.sizes = (plan.N, plan.E, plan.C, plan.K, int(gx.face_node_x.shape[1]))
+        N = plan.N
+        raw = getattr(gn, "_bench_x_raw", None)   # the model normalises graph_node.x in place: keep the loader's raw features
+        if raw is None:
+            raw = gn._bench_x_raw = gn.x.detach().clone()
+        self.x_host = raw.cpu().pin_memory()
+        self.x_dev0 = raw
+        # e2e regime: the next step's x[N,12] is copied host -> device on a side stream into the other of two buffers while
+        # the current step computes (what a loader with a prefetch queue does); results leave on the same side stream
+        self.copy_stream = torch.cuda.Stream(device=dev)
+        self.x_bufs, self.x_ready, self.k = [torch.empty_like(raw), torch.empty_like(raw)], [None, None], 0
+        self._keep = None
+        self.uvp_host = torch.empty((N, 3), dtype=torch.float32).pin_memory()
+        self.loss_host = torch.empty((), dtype=torch.float32).pin_memory()
+        self.gstep = None
+        if graph:
+            if world > 1:
+                raise SystemExit("--graph is a single-GPU option")
+            from gen_fvgn_steady_b200.graphed import GraphedTrainStep
+            gn.x, gn.norm_uvp, gn.norm_global = self.x_dev0.clone(), True, True
+            self.gstep = GraphedTrainStep(model, self.opt, graphs, self.script_loss, warmup=max(warmup, 3),
+                                          freeze_normalizer=True)
+
+    def script_loss(self, out):
+        p = self.p
+        return torch.mean(torch.log(p.loss_press * out[3] + p.loss_cont * out[0] + p.loss_mom * out[1] + p.loss_mom * out[2]))
+
+    def _prefetch(self, slot):
+        with torch.cuda.stream(self.copy_stream):
+            self.x_bufs[slot].copy_(self.x_host, non_blocking=True)
+            self.x_ready[slot] = torch.cuda.Event()
+            self.x_ready[slot].record(self.copy_stream)
+
+    def _next_x(self):
+        """This step's input (prefetched during the previous step) + the H2D copy of the next step's input in flight."""
+        cur = torch.cuda.current_stream()
+        slot = self.k & 1
+        self.k += 1
+        if self.x_ready[slot] is None:
+            self._prefetch(slot)
+        cur.wait_event(self.x_ready[slot])
+        self.x_ready[slot] = None
+        self.copy_stream.wait_stream(cur)      # everything enqueued so far (the previous step) is done with the other buffer
+        self._prefetch(slot ^ 1)
+        return self.x_bufs[slot]
+
+    def _results_to_host(self, uvp, loss):
+        ev = torch.cuda.Event()
+        ev.record(torch.cuda.current_stream())
+        self._keep = (uvp, loss)               # alive until the next step's copies are enqueued
+        with torch.cuda.stream(self.copy_stream):
+            self.copy_stream.wait_event(ev)
+            self.uvp_host.copy_(uvp, non_blocking=True)
+            self.loss_host.copy_(loss, non_blocking=True)
+        uvp.record_stream(self.copy_stream)
+        loss.record_stream(self.copy_stream)
+
+    def eager_step(self, e2e):
+        gn, gx, ge, gc, gi = self.graphs
+        gn.x = self._next_x() if e2e else self.x_dev0
+        gn.norm_uvp, gn.norm_global = True, True
+        self.flat_grad.zero_()
+        out = self.model(gn, gx, ge, gc, gi, is_training=True)
+        loss = self.script_loss(out)
+        loss.backward()
+        if self.cells_mode:
+            self.parallel.sum_gradients(self.flat_grad)
+        elif self.world > 1:
+            self.parallel.allreduce_gradients(self.flat_grad, self.world)
+        self.opt.step()
+        if e2e:
+            self._results_to_host(out[4], loss.detach())
+        return loss
+
+    def step(self, e2e):
+        if self.gstep is None:
+            return self.eager_step(e2e)
+        loss = self.gstep.step(self.x_host if e2e else None)
+        if e2e:
+            self.uvp_host.copy_(self.gstep.out[4], non_blocking=True)
+            self.loss_host.copy_(loss.detach(), non_blocking=True)
+        return loss
+
+    def timed(self, nsteps, e2e, profiler_range=False):
+        """ms for nsteps steps: CUDA events on the launching stream, barrier + synchronize on both sides, max over ranks."""
+        import torch.distributed as dist
+        if self.world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        ev0.record()
+        if profiler_range:
+            torch.cuda.profiler.start()  # `ncu --profile-from-start off` then lists exactly the launches of the timed steps
+        for _ in range(nsteps):
+            self.step(e2e)
+        if profiler_range:
+            torch.cuda.synchronize()
+            torch.cuda.profiler.stop()
+        ev1.record()
+        torch.cuda.synchronize()
+        ms = torch.tensor([ev0.elapsed_time(ev1)], device=self.dev)
+        if self.world > 1:
+            dist.barrier()
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return float(ms.item())
+
+    def close(self):
+        if self.gstep is not None:
+            self.gstep.close()
+        self.gstep = self.model = self.opt = self.flat_grad = self.graphs = self.plan = None
+        import gc
+        gc.collect()
+        torch.cuda.empty_cache()
+
+
+def quick_rate(dev, rank, world, graphs, net, mp, precision, steps, cells_total, graph=False, **kw):
+    """cells*steps/s of a secondary configuration (sub-records of the JSON line): 3 warm-up + `steps` timed steps."""
+    job = Job(dev, rank, world, graphs, net, mp, precision, graph=graph, **kw)
+    for _ in range(3):
+        job.step(False)
+    ms = job.timed(steps, False)
+    loss = float(job.step(False).detach())
+    job.close()
+    return {"value": cells_total / (ms / 1e3 / steps), "unit": "cells*steps/s", "ms_per_step": ms / steps, "steps": steps, "loss": loss}
+
+
+def example_mesh_records(dev, precision, steps):
+    """Throughput on the reference's own example meshes (BASELINE.json configs 0-2), taken from the golden fixtures
+    (tests/golden/*.npz hold the meshes as parsed by the reference's COMSOL parser; /root/reference is not needed):
+    the default net TransFVGN_v2 (6 GnBlocks + 2 Transolver blocks), eager and as one CUDA graph per step."""
+    from gen_fvgn_steady_b200.mesh.batching import graphs_from_meshes
+    from tests import golden_util as GU
+    out = {}
+    for name, label in (("lid_cavity_101_v2", "lid_driven_cavity_101x101-Re=100"), ("cylinder_tri_quad_v1", "cylinder_flow_tri_quad"),
+                        ("poisson_quad_tri_v2", "poisson/cavity_poisson_quad_tri")):
+        path = os.path.join(GU.GOLDEN_DIR, name + ".npz")
+        if not os.path.exists(path):
+            continue
+        z = GU.load_case(name)
+        mesh = GU.mesh_from_npz(z)
+        rec = {}
+        for graph in (False, True):
+            graphs = graphs_from_meshes([mesh], [z["uvp0"]], dev)
+            C = int(graphs[3].pos.shape[0])
+            r = quick_rate(dev, 0, 1, graphs, "TransFVGN_v2", 3, precision, steps, C, graph=graph)
+            rec["cuda_graph" if graph else "eager"] = {"value": r["value"], "ms_per_step": r["ms_per_step"]}
+            rec.update(cells=C, nodes=int(graphs[0].pos.shape[0]))
+        out[label] = rec
+    return out
+
+
 def run_ours(args):
     import torch.distributed as dist
-    from gen_fvgn_steady_b200 import _lib, ops
-    from gen_fvgn_steady_b200.FVMmodel.importer import NNmodel
+    from gen_fvgn_steady_b200 import _lib
     from gen_fvgn_steady_b200.mesh.batching import graphs_from_meshes
-    from gen_fvgn_steady_b200.plan import GraphPlan
-    from gen_fvgn_steady_b200.utils.get_param import params as default_params
-    from gen_fvgn_steady_b200 import parallel
 
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -185,173 +383,149 @@ def run_ours(args):
         raise RuntimeError("bench.py --impl ours needs a CUDA device: this package has no CPU path")
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
-    # the reference's scripts run their (cuBLAS) Linear layers in TF32 (src/pre_train_Adam.py:29); only the PyTorch
-    # Transolver blocks of --net TransFVGN_v* are affected here, the GN / FV kernels never go through cuBLAS
+    # the reference's scripts run their (cuBLAS) Linear layers in TF32 (src/pre_train_Adam.py:29); only the library GEMMs
+    # of the Transolver blocks of --net TransFVGN_v* are affected here, the GN / FV kernels never go through cuBLAS
     torch.set_float32_matmul_precision("high")
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
 
+    def partitioned_graphs(cells, halo_layers):
+        from gen_fvgn_steady_b200 import partition
+        mesh, uvp = make_mesh(cells, 0, dev)            # the same global mesh on every rank
+        c_global = int(mesh["cell|centroid"].shape[0])
+        mesh, uvp, halo = partition.build(mesh, uvp, world, rank, halo_layers=halo_layers, device=dev)
+        torch.cuda.empty_cache()
+        graphs = graphs_from_meshes([mesh], [uvp], dev)
+        partition.mark_partition(graphs, halo)
+        return graphs, halo, c_global
+
     cells_mode = args.parallel == "cells" and world > 1
-    gn_blocks_total = _gn_blocks(args)  # v2: two processors of mp blocks
+    gn_blocks_total = _gn_blocks(args.net, args.mp)
     if args.halo_layers is None:
         args.halo_layers = 3 * gn_blocks_total + 2
     halo = None
     if cells_mode:
-        from gen_fvgn_steady_b200 import partition
-        mesh, uvp = make_mesh(args.cells, 0, dev)            # the same global mesh on every rank
-        C_global = int(mesh["cell|centroid"].shape[0])
-        mesh, uvp, halo = partition.build(mesh, uvp, world, rank, halo_layers=args.halo_layers, device=dev)
-        torch.cuda.empty_cache()
+        graphs, halo, C_global = partitioned_graphs(args.cells, args.halo_layers)
     else:
         mesh, uvp = make_mesh(args.cells, rank, dev)
-    graphs = graphs_from_meshes([mesh], [uvp], dev)
-    del mesh
-    if cells_mode:
-        partition.mark_partition(graphs, halo)
-    gn, gx, ge, gc, gi = graphs
-    p = default_params(net=args.net, message_passing_num=args.mp, precision=args.precision)
-    torch.manual_seed(0)
-    model = NNmodel(p).to(dev)
-    if cells_mode:
-        model.enable_cell_partition(True)
-    elif world > 1:
-        model.enable_data_parallel(True)
-    flat_grad = parallel.flatten_gradients(model)
-    opt = torch.optim.Adam(model.parameters(), lr=p.lr, fused=True, capturable=bool(args.graph))
-    plan = GraphPlan.of(gn, gx, ge, gc, p.order)
-    N, E, C, K, X = plan.N, plan.E, plan.C, plan.K, int(gx.face_node_x.shape[1])
-    x_host = gn.x.detach().cpu().pin_memory()
-    x_dev0 = gn.x.clone()
-    uvp_host = torch.empty((N, 3), dtype=torch.float32).pin_memory()
-    loss_host = torch.empty((), dtype=torch.float32).pin_memory()
-
-    def step(e2e):
-        if e2e:
-            gn.x = x_host.to(dev, non_blocking=True)
-        else:
-            gn.x = x_dev0
-        gn.norm_uvp, gn.norm_global = True, True
-        flat_grad.zero_()
-        out = model(gn, gx, ge, gc, gi, is_training=True)
-        lb = p.loss_press * out[3] + p.loss_cont * out[0] + p.loss_mom * out[1] + p.loss_mom * out[2]
-        loss = torch.mean(torch.log(lb))
-        loss.backward()
-        if cells_mode:
-            parallel.sum_gradients(flat_grad)
-        elif world > 1:
-            parallel.allreduce_gradients(flat_grad, world)
-        opt.step()
-        if e2e:
-            uvp_host.copy_(out[4], non_blocking=True)
-            loss_host.copy_(loss.detach(), non_blocking=True)
-        return loss
-
-    gstep = None
-    if args.graph:
-        if world > 1:
-            raise SystemExit("--graph is a single-GPU option")
-        from gen_fvgn_steady_b200.graphed import GraphedTrainStep
-        gn.x, gn.norm_uvp, gn.norm_global = x_dev0.clone(), True, True
-        script_loss = lambda out: torch.mean(torch.log(p.loss_press * out[3] + p.loss_cont * out[0] + p.loss_mom * out[1]
-                                                       + p.loss_mom * out[2]))
-        gstep = GraphedTrainStep(model, opt, graphs, script_loss, warmup=max(args.warmup, 3))
-        eager_step = step
-
-        def step(e2e):  # noqa: F811  -- same contract as the eager step
-            loss = gstep.step(x_host if e2e else None)
-            if e2e:
-                uvp_host.copy_(gstep.out[4], non_blocking=True)
-                loss_host.copy_(loss.detach(), non_blocking=True)
-            return loss
-
-    def timed(nsteps, e2e):
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
-        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        ev0.record()
-        if not e2e:
-            torch.cuda.profiler.start()  # `ncu --profile-from-start off` then lists exactly the launches of the timed steps
-        for _ in range(nsteps):
-            step(e2e)
-        if not e2e:
-            torch.cuda.synchronize()
-            torch.cuda.profiler.stop()
-        ev1.record()
-        torch.cuda.synchronize()
-        ms = torch.tensor([ev0.elapsed_time(ev1)], device=dev)
-        if world > 1:
-            dist.barrier()
-            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
-        return float(ms.item())
+        graphs = graphs_from_meshes([mesh], [uvp], dev)
+        del mesh
+    job = Job(dev, rank, world, graphs, args.net, args.mp, args.precision, cells_mode=cells_mode, halo=halo, graph=args.graph,
+              warmup=args.warmup)
+    N, E, C, K, X = job.sizes
+    cells_total = C_global if cells_mode else world * C
 
     for _ in range(max(args.warmup, 3)):
-        step(False)
+        job.step(False)
     launches_per_replay = None
-    if gstep is not None:  # count the kernels of one step with the eager path (the graph replays exactly those)
+    if job.gstep is not None:  # count the kernels of one step with the eager path (the graph replays exactly those)
         l_ = _lib.launch_count
-        eager_step(False)
+        job.eager_step(False)
         launches_per_replay = _lib.launch_count - l_
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
     l0 = _lib.launch_count
-    ms = timed(args.steps, False)
-    launches = _lib.launch_count - l0 if gstep is None else launches_per_replay * args.steps
-    step(True)
-    ms_e2e = timed(args.steps, True)
+    ms = job.timed(args.steps, False, profiler_range=True)
+    launches = _lib.launch_count - l0 if job.gstep is None else launches_per_replay * args.steps
+    job.step(True)
+    ms_e2e = job.timed(args.steps, True)
     clocks = sampler.stop() if rank == 0 else None
-    last_loss = float(loss_host)
+    last_loss = float(job.loss_host)
 
     if args.kernel_summary and rank == 0:
         from torch.profiler import profile, ProfilerActivity
         with profile(activities=[ProfilerActivity.CUDA]) as prof:
             for _ in range(2):
-                step(False)
+                job.step(False)
             torch.cuda.synchronize()
         rows = sorted(((e.key, e.count, e.device_time_total / 1e3) for e in prof.key_averages()), key=lambda r: -r[2])
         tot = sum(r[2] for r in rows)
         with open(args.kernel_summary, "w") as f:
             f.write(f"# torch.profiler (CUPTI) device time over 2 steps, in situ (concurrent, warm): total {tot:.3f} ms\n")
-            for k, c, ms in rows:
-                f.write(f"{ms:10.3f} ms {c:6d} {100 * ms / max(tot, 1e-9):5.1f}%  {k[:150]}\n")
+            for k, c, kms in rows:
+                f.write(f"{kms:10.3f} ms {c:6d} {100 * kms / max(tot, 1e-9):5.1f}%  {k[:150]}\n")
 
     # dominant kernel: timed alone with CUDA events on the launching stream
-    roof = dominant_kernel_roofline(model, plan, dev, args, p)
+    roof = dominant_kernel_roofline(job.model, job.plan, dev, args, job.p)
+    halo_text = None
+    if cells_mode:
+        halo_text = (f"cells{world} (one {C_global}-cell mesh, RCB partition, {args.halo_layers}-layer halo, "
+                     f"{sum(halo.wants_exchange(i, gn_blocks_total) for i in range(gn_blocks_total))} ghost refreshes per forward; "
+                     f"rank 0: {halo.n_owned_cells} owned of {C} local cells)")
+    job.close()
 
-    if rank != 0:
-        if world > 1:
-            dist.destroy_process_group()
-        return
     hbm, how = peaks()
     sec = ms / 1e3 / args.steps
-    value = (C_global if cells_mode else world * C) / sec
     ab = alg_bytes_step(N, E, C, K, X, gn_blocks_total)   # SURVEY 8(d) counts the GN + FV bytes only (Transolver blocks add none)
-    line = {"metric": "cells*steps/sec (fwd+bwd train step)", "value": value, "unit": "cells*steps/s", "n_gpus": world,
+    line = {"metric": "cells*steps/sec (fwd+bwd train step)", "value": cells_total / sec, "unit": "cells*steps/s", "n_gpus": world,
             "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps, "higher_is_better": True,
-            "scaling": "strong" if cells_mode else "weak", "vs_baseline": None,
-            "dtype": {"fp32": "f32", "bf16": "bf16 operands and derived streams, f32 accumulate and residual streams",
-                      "f16": "f16 operands and derived streams (TF32-grade 11-bit significand), f32 accumulate and residual streams"}[args.precision],
-            "data": "synthetic", "config": dict(workload_config(args, C_bench=C), N=N, E=E, C=C, K=K, X=X,
-                                                parallelism=(f"cells{world} (one {C_global}-cell mesh, RCB partition, "
-                                                             f"{args.halo_layers}-layer halo, "
-                                                             f"{sum(halo.wants_exchange(i, gn_blocks_total) for i in range(gn_blocks_total))} "
-                                                             f"ghost refreshes per forward; rank 0: "
-                                                             f"{halo.n_owned_cells} owned of {C} local cells)") if cells_mode
-                                                else f"dp{world}", loss=last_loss),
+            "scaling": "strong" if cells_mode else "weak", "vs_baseline": None, "dtype": DTYPE_TEXT[args.precision],
+            "data": "synthetic", "config": dict(workload_config(args), N=N, E=E, C=C, K=K, X=X,
+                                                parallelism=halo_text if cells_mode else f"dp{world}", loss=last_loss),
             "clocks": clocks, "gpu_launches": launches,
-            "e2e": {"value": (C_global if cells_mode else world * C) / (ms_e2e / 1e3 / args.steps), "unit": "cells*steps/s",
+            "e2e": {"value": cells_total / (ms_e2e / 1e3 / args.steps), "unit": "cells*steps/s",
                     "h2d_bytes_per_step": N * 12 * 4,
                     "d2h_bytes_per_step": N * 3 * 4 + 4, "ms_per_step": ms_e2e / args.steps},
             "roofline": dict(roof, peak=hbm, frac=roof["achieved"] / hbm, peak_source=how),
             "step_roofline": {"alg_bytes_per_step": ab, "achieved_gbs": ab / sec / 1e9, "frac": ab / sec / 1e9 / hbm,
                               "alg_kb_per_cell": ab / C / 1e3}}
+
+    # ------------------------------------------------------------------ sub-records (secondary configurations)
+    if not args.no_extras and not cells_mode and not args.graph:
+        sub_steps = max(min(args.steps, 10), 3)
+        if world == 1:
+            # every tensor-core mode bench.py can time, on the same mesh (tests/test_gpu_parity.py asserts all goldens in both)
+            modes = {args.precision: {"value": line["value"], "unit": "cells*steps/s", "ms_per_step": line["ms_per_step"],
+                                      "steps": args.steps}}
+            for prec in ("f16", "bf16"):
+                if prec not in modes:
+                    modes[prec] = quick_rate(dev, rank, world, graphs, args.net, args.mp, prec, sub_steps, C)
+            line["precision_modes"] = modes
+            # the reference's default net (get_param.py:37): 2 x (3 GnBlocks + Transolver block), same mesh
+            if args.net != "TransFVGN_v2":
+                r = quick_rate(dev, rank, world, graphs, "TransFVGN_v2", 3, args.precision, sub_steps, C)
+                ab2 = alg_bytes_step(N, E, C, K, X, 6)
+                r.update(gn_blocks=6, transolver_blocks=2, step_roofline_frac=ab2 / (r["ms_per_step"] / 1e3) / 1e9 / hbm)
+                line["nets"] = {"TransFVGN_v2": r}
+            del graphs
+            torch.cuda.empty_cache()
+            try:
+                line["example_meshes"] = example_mesh_records(dev, args.precision, 20)
+            except Exception as e:  # noqa: BLE001 -- a sub-record must not take the headline down
+                line["example_meshes"] = {"error": repr(e)}
+        else:
+            # strong scaling of ONE mesh of --cells cells over the ranks: cell partition + halo
+            del graphs
+            torch.cuda.empty_cache()
+            recs = {}
+            for hl in (3 * gn_blocks_total + 2, 3):
+                g2, h2, cg = partitioned_graphs(args.cells, hl)
+                owned = torch.tensor([h2.n_owned_cells, int(g2[3].pos.shape[0])], device=dev, dtype=torch.int64)
+                allv = [torch.zeros_like(owned) for _ in range(world)]
+                dist.all_gather(allv, owned)
+                r = quick_rate(dev, rank, world, g2, args.net, args.mp, args.precision, sub_steps, cg, cells_mode=True, halo=h2)
+                r.update(halo_layers=hl, ghost_refreshes_per_forward=sum(h2.wants_exchange(i, gn_blocks_total) for i in range(gn_blocks_total)),
+                         owned_cells_per_rank=[int(v[0]) for v in allv], local_cells_per_rank=[int(v[1]) for v in allv])
+                recs[f"halo{hl}"] = r
+                del g2, h2
+                torch.cuda.empty_cache()
+            line["cells"] = {"mesh_cells": cg, "scaling": "strong", "partition": "recursive coordinate bisection", **recs}
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
     if not args.no_cpu_baseline:
         threads = os.cpu_count() or 1
-        sec_cpu, C_cpu = cpu_reference_step_time(args.cpu_cells, args.net, args.mp, 2, 1, threads)
+        cells_cpu = args.cpu_cells
+        if cells_cpu <= 0:
+            cells_cpu, _ = cpu_sample_cells(args.net, args.mp, threads, 6, 20.0)
+        times, C_cpu = cpu_reference_step_times(cells_cpu, args.net, args.mp, 5, 1, threads)
+        sec_cpu = float(np.median(times))
         line["cpu_baseline"] = {"value": C_cpu / sec_cpu, "unit": "cells*steps/s", "cores": threads, "kind": "port",
-                                "sample": f"{C_cpu}-cell synthetic quad mesh, same net/loss, fwd+bwd+Adam fp32, 2 steps after 1 warm-up "
-                                          f"(oracle/fvgn_oracle.py on the host cores)"}
+                                "sample": f"{C_cpu}-cell synthetic quad mesh (same generator, net, G, loss), fwd+bwd+Adam fp32, median "
+                                          f"of 5 steps after 1 warm-up (oracle/fvgn_oracle.py on the host cores)"}
     print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
