@@ -865,10 +865,17 @@ __global__ void __launch_bounds__(NTHREADS, 1) mlp_tc_bwd_b_kernel(const fvgn_ml
           if (to_bf16) {
             // 64 columns -> 128 B of bf16 per row: one staging tile, one coalesced pass
             uint32_t r[32];
+            float rs = 1.f;  // NODE: D^-1 of the transposed scatter_mean applied to this thread's row of d_a2
+            if (MODE == FVGN_MLP_NODE && d.d_in0_row_ptr != nullptr && wrow0 + lane < d.rows)
+              rs = 1.f / (float)max(__ldg(d.d_in0_row_ptr + wrow0 + lane + 1) - __ldg(d.d_in0_row_ptr + wrow0 + lane), 1);
 #pragma unroll
             for (int half = 0; half < 2; ++half) {
               tmem_ld32(tacc + 32 * half, r);
               tmem_wait_ld();
+              if (MODE == FVGN_MLP_NODE) {
+#pragma unroll
+                for (int k = 0; k < 32; ++k) r[k] = __float_as_uint(__uint_as_float(r[k]) * rs);
+              }
 #pragma unroll
               for (int k = 0; k < 4; ++k)
                 *reinterpret_cast<uint4*>(wstg_at(mystg, lane, half * 4 + k)) =

@@ -216,103 +216,183 @@ __device__ __forceinline__ void add_vec(float (&acc)[V], const float (&x)[V]) {
   }
 }
 
-// lanes per row: 16 whenever a lane can move 16 bytes of the SOURCE row (bf16 512-col... i.e. 128 bf16 = 16 x 16 B, or
-// 64 fp32 = 16 x 16 B), else 32; the two half-warps of a 16-lane configuration run independent rows
-template <int W, class TS> struct PipeCfg { static constexpr int LPR = (W * (int)sizeof(typename TS::elem) >= 512) ? 32 : 16; };
+// ------------------------------------------------------------------------------------------ block-staged kernels
+// Round-1 ncu of the warp-pipelined version of these reductions: 132 warp instructions per row, issue slots 48 % busy at
+// 25 % of the DRAM bandwidth -- the rows' own data path is ~30 instructions, the rest was index bookkeeping (row pointers
+// and entries fetched per warp through a three-deep register pipeline, shuffles, 64-bit predicated address chains).
+// Here the INDEX traffic is staged per CTA instead: a CTA owns blocks of RB = 128 consecutive rows; the row pointers of
+// block b+2 and the entries of block b+1 arrive by cp.async into shared memory while block b is reduced, so inside a
+// block a row costs two LDS for its pointers, one LDS + one LDG.128 per entry and the arithmetic.  A group of LPR lanes
+// (16 B of the source row per lane) owns a row; R rows per group are in flight together.  Entries are accumulated
+// strictly in CSR order in fp32: bit-identical to the one-shot kernels above.
+template <int W, class TS> struct PipeCfg {
+  static constexpr int LPR = W * (int)sizeof(typename TS::elem) / 16;   // lanes per row: 8, 16 or 32
+  static_assert(LPR == 8 || LPR == 16 || LPR == 32, "row of 128, 256 or 512 bytes");
+};
+// Measured on a B200 (4 M rows, degree 4, tools/reduce_variants.py, profiles/r2e_reduce_variants.txt): these kernels are
+// bound by L2 -> SM gather throughput (every source row is read by each of its ~4 neighbours: 4x the DRAM volume through
+// L2) and want many resident warps rather than deep per-thread pipelines -- R = 1 row per group at 5 CTAs per SM
+// (48 registers) beats R = 2 at 2-4 CTAs and R = 1 at 8 CTAs (spills).
+#ifndef FVGN_PIPE_ROWS
+#define FVGN_PIPE_ROWS 1
+#endif
+#ifndef FVGN_PIPE_MINB
+#define FVGN_PIPE_MINB 5   // resident 256-thread blocks per SM the register allocation is held to
+#endif
+constexpr int RB = 128;    // rows per block
+constexpr int ECAP = 1536; // entries of a block held in shared memory (the rest, if any, are read from global memory)
+
+__device__ __forceinline__ void cp_async4(void* smem, const void* gmem) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"((uint32_t)__cvta_generic_to_shared(smem)), "l"(gmem) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit_wait_all() {
+  asm volatile("cp.async.commit_group;\ncp.async.wait_group 0;" ::: "memory");
+}
 
 // INC = false: entries are neighbour rows (src row = entry, W columns);  INC = true: entries are edge*2+role codes
-// (src row = code >> 1 of a [E, 2W] array, column block = code & 1).
-template <int W, class TS, class TD, bool INC>
-__global__ void __launch_bounds__(256) pipe_reduce_kernel(const typename TS::elem* __restrict__ src, const int32_t* __restrict__ ptr,
-                                                          const int32_t* __restrict__ ent, typename TD::elem* __restrict__ dst,
-                                                          int64_t n, int flags) {
-  constexpr int LPR = PipeCfg<W, TS>::LPR;  // lanes per row: 32 (one warp per row) or 16 (one HALF-warp per row)
-  constexpr int V = W / LPR;                // elements per lane: 4 or 8
-  constexpr int NB = 4;                     // gathers in flight per lane
+// (src row = code >> 1 of a [E, 2W] array, column block = code & 1).  FL: FVGN_ADJ_* flags, compile time.
+template <int W, class TS, class TD, bool INC, int FL, int R>
+__global__ void __launch_bounds__(256, FVGN_PIPE_MINB) pipe_reduce_kernel(const typename TS::elem* __restrict__ src,
+                                                                          const int32_t* __restrict__ ptr,
+                                                                          const int32_t* __restrict__ ent,
+                                                                          typename TD::elem* __restrict__ dst, int64_t n) {
+  constexpr int LPR = PipeCfg<W, TS>::LPR;  // lanes per row
+  constexpr int V = W / LPR;                // elements per lane: 8 (16-bit source) or 4 (fp32 source)
+  constexpr int NB = 4;                     // gathers in flight per lane and row
+  constexpr int G = 256 / LPR;              // row groups per CTA
   constexpr int ROW_LD = INC ? 2 * W : W;
+  constexpr bool DIV_SRC = !INC && (FL & FVGN_ADJ_DIV_SRC_BY_DEG), DIV_DST = !INC && (FL & FVGN_ADJ_DIV_DST_BY_DEG),
+                 ACCUM = !INC && (FL & FVGN_ADJ_ACCUMULATE);
   typedef LaneIO<TS, V> SI;
   typedef LaneIO<TD, V> DI;
-  const int lane = threadIdx.x & (LPR - 1);
-  const unsigned hmask = (LPR == 32) ? 0xffffffffu : (0xffffu << (threadIdx.x & 16));
-  const int64_t gw = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) / LPR;
-  const int64_t GW = (int64_t)gridDim.x * blockDim.x / LPR;
-  const bool div_src = !INC && (flags & FVGN_ADJ_DIV_SRC_BY_DEG);
-  auto load_ptr = [&](int64_t row, int& b, int& e) {
-    b = 0; e = 0;
-    if (row < n) { b = __ldg(ptr + row); e = __ldg(ptr + row + 1); }
+  __shared__ int s_ptr[3][RB + 1];
+  __shared__ int s_ent[2][ECAP];
+  const int tid = threadIdx.x, lane = tid & (LPR - 1), g = tid / LPR;
+  const int64_t nblk = (n + RB - 1) / RB;
+  auto fetch_ptr = [&](int64_t blk, int buf) {      // row pointers of block blk (clamped: rows past n repeat ptr[n])
+    if (blk < nblk && tid <= RB) {
+      const int64_t row = blk * RB + tid;
+      cp_async4(&s_ptr[buf][tid], ptr + (row < n ? row : n));
+    }
   };
-  auto load_ent = [&](int b, int e) { return (b + lane < e) ? __ldg(ent + b + lane) : 0; };  // first LPR entries, one per lane
-  int cb, ce, cent;  // row i: pointers and entries (arrived)
-  int nb_, ne_;      // row i+1: pointers (arrived), entries being fetched into nent
-  load_ptr(gw, cb, ce);
-  load_ptr(gw + GW, nb_, ne_);
-  cent = load_ent(cb, ce);
-  for (int64_t row = gw; row < n; row += GW) {
-    const int deg = ce - cb;
-    // ---- issue: gathers of this row (first NB), entries of the next row, pointers of the one after
-    typename SI::raw v[NB];
-#pragma unroll
-    for (int k = 0; k < NB; ++k) {
-      const int code = __shfl_sync(hmask, cent, k, LPR);
-      if (k < deg) {
-        const int r = INC ? (code >> 1) : code;
-        const int coff = INC ? (code & 1) * W : 0;
-        v[k] = SI::ld(src + (size_t)r * ROW_LD + coff + lane * V);
-      }
+  auto fetch_ent = [&](int64_t blk, int pbuf, int ebuf) {   // entries of block blk, whose pointers are in s_ptr[pbuf]
+    if (blk < nblk) {
+      const int e0 = s_ptr[pbuf][0];
+      const int ne = min(s_ptr[pbuf][RB] - e0, ECAP);
+      for (int i = tid; i < ne; i += 256) cp_async4(&s_ent[ebuf][i], ent + e0 + i);
     }
-    float mydiv = 1.f;  // lane k: degree of the source row of entry k (transposed mean)
-    if (div_src && lane < deg) mydiv = (float)max(__ldg(ptr + cent + 1) - __ldg(ptr + cent), 1);
-    const int nent = load_ent(nb_, ne_);
-    int ab, ae;
-    load_ptr(row + 2 * GW, ab, ae);
-    float old[V];
+  };
+  int64_t blk = blockIdx.x;
+  fetch_ptr(blk, 0);
+  fetch_ptr(blk + gridDim.x, 1);
+  cp_async_commit_wait_all();
+  __syncthreads();
+  fetch_ent(blk, 0, 0);
+  cp_async_commit_wait_all();
+  __syncthreads();
+  for (uint32_t it = 0; blk < nblk; blk += gridDim.x, ++it) {
+    const int pb = it % 3, eb = it & 1;
+    fetch_ptr(blk + 2 * (int64_t)gridDim.x, (it + 2) % 3);
+    fetch_ent(blk + gridDim.x, (it + 1) % 3, eb ^ 1);
+    const int* sp = s_ptr[pb];
+    const int* se = s_ent[eb];
+    const int e0 = sp[0];
+    const int64_t row0 = blk * RB;
+    const int nr = (int)min((int64_t)RB, n - row0);
+    auto entry = [&](int t) { return (t - e0 < ECAP) ? se[t - e0] : __ldg(ent + t); };
+    auto src_of = [&](int code) {
+      const int r = INC ? (code >> 1) : code;
+      const int coff = INC ? (code & 1) * W : 0;
+      return src + (size_t)r * ROW_LD + coff + lane * V;
+    };
+#pragma unroll 1
+    for (int rr = g; rr < nr; rr += G * R) {
+      int b_[R], deg[R], c[R][NB];
+      typename SI::raw v[R][NB];
+      typename DI::raw oldraw[R];
+      float dv[R][NB];
+      // ---- issue phase: every gather (and the transposed-mean degrees / the old destination rows) of the R rows
 #pragma unroll
-    for (int j = 0; j < V; ++j) old[j] = 0.f;
-    typename TD::elem* o = dst + (size_t)row * W + lane * V;
-    if (!INC && (flags & FVGN_ADJ_ACCUMULATE)) DI::up(DI::ld(o), old);
-    // ---- consume in CSR order
-    float acc[V];
+      for (int r = 0; r < R; ++r) {
+        const int row = rr + r * G;
+        b_[r] = 0; deg[r] = 0;
+        if (row < nr) { b_[r] = sp[row]; deg[r] = sp[row + 1] - b_[r]; }
 #pragma unroll
-    for (int j = 0; j < V; ++j) acc[j] = 0.f;
-#pragma unroll
-    for (int k = 0; k < NB; ++k) {
-      if (k < deg) {
-        float x[V];
-        SI::up(v[k], x);
-        if (div_src) {
-          const float dv = __shfl_sync(hmask, mydiv, k, LPR);
-#pragma unroll
-          for (int j = 0; j < V; ++j) x[j] /= dv;
+        for (int k = 0; k < NB; ++k) {
+          if (k < deg[r]) {
+            c[r][k] = entry(b_[r] + k);
+            v[r][k] = SI::ld(src_of(c[r][k]));
+          }
         }
-        add_vec<V>(acc, x);
+        if (DIV_SRC) {
+#pragma unroll
+          for (int k = 0; k < NB; ++k)
+            if (k < deg[r]) dv[r][k] = (float)max(__ldg(ptr + c[r][k] + 1) - __ldg(ptr + c[r][k]), 1);
+        }
+        if (ACCUM && row < nr) oldraw[r] = DI::ld(dst + (size_t)(row0 + row) * W + lane * V);
+      }
+      // ---- consume in CSR order
+#pragma unroll
+      for (int r = 0; r < R; ++r) {
+        const int row = rr + r * G;
+        float acc[V];
+#pragma unroll
+        for (int j = 0; j < V; ++j) acc[j] = 0.f;
+#pragma unroll
+        for (int k = 0; k < NB; ++k) {
+          if (k < deg[r]) {
+            float x[V];
+            SI::up(v[r][k], x);
+            if (DIV_SRC) {
+#pragma unroll
+              for (int j = 0; j < V; ++j) x[j] /= dv[r][k];
+            }
+            add_vec<V>(acc, x);
+          }
+        }
+        for (int t0 = NB; t0 < deg[r]; t0 += NB) {  // rows longer than NB entries: the rest, NB at a time
+          typename SI::raw w[NB];
+          int cc[NB];
+#pragma unroll
+          for (int k = 0; k < NB; ++k) {
+            cc[k] = 0;
+            if (t0 + k < deg[r]) {
+              cc[k] = entry(b_[r] + t0 + k);
+              w[k] = SI::ld(src_of(cc[k]));
+            }
+          }
+#pragma unroll
+          for (int k = 0; k < NB; ++k) {
+            if (t0 + k < deg[r]) {
+              float x[V];
+              SI::up(w[k], x);
+              if (DIV_SRC) {
+                const float d = (float)max(__ldg(ptr + cc[k] + 1) - __ldg(ptr + cc[k]), 1);
+#pragma unroll
+                for (int j = 0; j < V; ++j) x[j] /= d;
+              }
+              add_vec<V>(acc, x);
+            }
+          }
+        }
+        if (DIV_DST) {
+          const float dd = (float)max(deg[r], 1);
+#pragma unroll
+          for (int j = 0; j < V; ++j) acc[j] /= dd;
+        }
+        if (row < nr) {
+          if (ACCUM) {
+            float old[V];
+            DI::up(oldraw[r], old);
+#pragma unroll
+            for (int j = 0; j < V; ++j) acc[j] = old[j] + acc[j];
+          }
+          DI::st(dst + (size_t)(row0 + row) * W + lane * V, acc);
+        }
       }
     }
-    for (int t = NB; t < deg; ++t) {  // long rows: the rest, one at a time (entries beyond LPR straight from memory)
-      const int c = (t < LPR) ? __shfl_sync(hmask, cent, t, LPR) : __ldg(ent + cb + t);
-      const int r = INC ? (c >> 1) : c;
-      const int coff = INC ? (c & 1) * W : 0;
-      float x[V];
-      SI::up(SI::ld(src + (size_t)r * ROW_LD + coff + lane * V), x);
-      if (div_src) {
-        const float dv = (float)max(__ldg(ptr + c + 1) - __ldg(ptr + c), 1);
-#pragma unroll
-        for (int j = 0; j < V; ++j) x[j] /= dv;
-      }
-      add_vec<V>(acc, x);
-    }
-    if (!INC && (flags & FVGN_ADJ_DIV_DST_BY_DEG)) {
-      const float dd = (float)max(deg, 1);
-#pragma unroll
-      for (int j = 0; j < V; ++j) acc[j] /= dd;
-    }
-    if (!INC && (flags & FVGN_ADJ_ACCUMULATE)) {
-#pragma unroll
-      for (int j = 0; j < V; ++j) acc[j] = old[j] + acc[j];
-    }
-    DI::st(o, acc);
-    // ---- rotate the pipeline
-    cb = nb_; ce = ne_; cent = nent;
-    nb_ = ab; ne_ = ae;
+    cp_async_commit_wait_all();   // the next block's entries and the pointers of the one after have landed
+    __syncthreads();              // ... for every thread; and everybody is done with this block's buffers
   }
 }
 #endif  // FVGN_EMU
@@ -330,16 +410,27 @@ static unsigned pipe_grid(K kern, int64_t n_rows) {
   const int64_t cap = (int64_t)sms * per_sm;
   return (unsigned)(want < cap ? want : cap);
 }
+template <int W, class TS, class TD, bool INC, int FL>
+static void launch_pipe_fl(const typename TS::elem* s, const int32_t* ptr, const int32_t* ent, typename TD::elem* o, int64_t n_rows,
+                           void* stream) {
+  auto kern = pipe_reduce_kernel<W, TS, TD, INC, FL, FVGN_PIPE_ROWS>;
+  static unsigned cap_grid[FVGN_MAX_DEV] = {0};  // per instantiation and device
+  const int dev = fvgn_cur_device();
+  if (cap_grid[dev] == 0) cap_grid[dev] = pipe_grid(kern, (int64_t)1 << 40);
+  const int64_t want = (n_rows + RB - 1) / RB;
+  const unsigned grid = (unsigned)(want < cap_grid[dev] ? want : cap_grid[dev]);
+  kern<<<grid, 256, 0, (cudaStream_t)stream>>>(s, ptr, ent, o, n_rows);
+}
 template <int W, class TS, class TD, bool INC>
 static void launch_pipe(const typename TS::elem* s, const int32_t* ptr, const int32_t* ent, typename TD::elem* o, int64_t n_rows,
                         int flags, void* stream) {
-  auto kern = pipe_reduce_kernel<W, TS, TD, INC>;
-  static unsigned cap_grid = 0;  // per instantiation
-  if (cap_grid == 0) cap_grid = pipe_grid(kern, (int64_t)1 << 40);
-  const int rows_per_block = 256 / PipeCfg<W, TS>::LPR;
-  const int64_t want = (n_rows + rows_per_block - 1) / rows_per_block;
-  const unsigned grid = (unsigned)(want < cap_grid ? want : cap_grid);
-  kern<<<grid, 256, 0, (cudaStream_t)stream>>>(s, ptr, ent, o, n_rows, flags);
+  switch (INC ? 0 : (flags & 7)) {
+    case 0: launch_pipe_fl<W, TS, TD, INC, 0>(s, ptr, ent, o, n_rows, stream); break;
+    case 1: launch_pipe_fl<W, TS, TD, INC, INC ? 0 : 1>(s, ptr, ent, o, n_rows, stream); break;
+    case 2: launch_pipe_fl<W, TS, TD, INC, INC ? 0 : 2>(s, ptr, ent, o, n_rows, stream); break;
+    case 4: launch_pipe_fl<W, TS, TD, INC, INC ? 0 : 4>(s, ptr, ent, o, n_rows, stream); break;
+    default: launch_pipe_fl<W, TS, TD, INC, INC ? 0 : 7>(s, ptr, ent, o, n_rows, stream); break;   // any other combination
+  }
 }
 #endif
 

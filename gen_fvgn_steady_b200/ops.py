@@ -206,7 +206,7 @@ def _z1_for(ctx, mode, precision, rows, like):
 
 
 def mlp_backward(mode, precision, rows, params, in0, in1, idx_s, idx_r, d_out, d_gather=None, d_in0=None, d_in1=None,
-                 flags=0, packed=None, z1=None, in0h=None, in1h=None, d_in0h=None, d_gatherh=None):
+                 flags=0, packed=None, z1=None, in0h=None, in1h=None, d_in0h=None, d_gatherh=None, d_in0_row_ptr=None):
     """Runs the fused backward; returns the list of parameter gradients (views of one flat buffer).
     packed: the bf16 weight image used by the matching forward (bf16 mode); repacked from `params` when None.
     z1: the Z1Image the matching bf16 forward filled; when None (stand-alone use) the forward is re-run to make it.
@@ -227,6 +227,8 @@ def mlp_backward(mode, precision, rows, params, in0, in1, idx_s, idx_r, d_out, d
         d.d_in0h = hptr(d_in0h)
     if d_gatherh is not None:
         d.d_gatherh = hptr(d_gatherh)
+    if d_in0_row_ptr is not None:   # NODE, tensor-core modes: d_a2 rows leave divided by their node degree
+        d.d_in0_row_ptr = iptr(d_in0_row_ptr)
     d.partials, d.n_partials, d.d_params = fptr(partials), npart, fptr(flat)
     if precision == "f16":
         d.grad_unscale = grad_scale(d_out.device)[1:2].data_ptr()
@@ -400,9 +402,10 @@ class GnBlockFn(torch.autograd.Function):
             BF16 = HDTYPE[precision]
             xh, eh, aggh, a2h = x, e, agg, a2
             d_a2h = torch.empty((plan.N, 64), dtype=BF16, device=dev)
+            # transposed scatter_mean: d_a1 = Adj (D^-1 d_a2); the D^-1 is applied by the producing kernel's epilogue
             g_nb = mlp_backward(_lib.FVGN_MLP_NODE, precision, plan.N, nb, None, None, None, None, d_x_out, None, None, d_x,
-                                packed=ctx.pk[1], z1=ctx.z1[1], in0h=a2h, in1h=xh, d_in0h=d_a2h)
-            d_a1h = adj_reduce(d_a2h, plan, 64, _lib.FVGN_ADJ_DIV_SRC_BY_DEG, out_dtype=BF16)
+                                packed=ctx.pk[1], z1=ctx.z1[1], in0h=a2h, in1h=xh, d_in0h=d_a2h, d_in0_row_ptr=plan.inc_ptr)
+            d_a1h = adj_reduce(d_a2h, plan, 64, out_dtype=BF16)
             del d_a2h
             d_srh = torch.empty((plan.E, 256), dtype=BF16, device=dev)
             g_eb = mlp_backward(_lib.FVGN_MLP_EDGE, precision, plan.E, eb, None, None, plan.edge_s, plan.edge_r, d_e_out, None,

@@ -113,6 +113,11 @@ typedef struct fvgn_mlp_desc {
    * deterministic partial reduction (1 / S of the power-of-two gradient pre-scaling the FVGN_PREC_F16 mode applies at the
    * root of the backward pass so that half-precision gradient operands stay in range; exact). */
   const float* grad_unscale;
+  /* NODE backward, tensor-core modes, optional: CSR row pointers ptr[N+1] of the node adjacency.  Row i of d_in0h
+   * (d_a2, the gradient of the scatter_mean of blocks.py:44-51) leaves divided by max(ptr[i+1] - ptr[i], 1): the
+   * transposed mean d_a1 = Adj (D^-1 d_a2) then is a plain adjacency sum (no per-source degree lookups in
+   * fvgn_adj_reduce_t; FVGN_ADJ_DIV_SRC_BY_DEG must not be passed as well). */
+  const int32_t* d_in0_row_ptr;
 } fvgn_mlp_desc;
 
 int64_t fvgn_mlp_param_count(int32_t mode);

@@ -190,30 +190,69 @@ def test_typed_reductions_match_torch(width):
 
 @pytest.mark.parametrize("width", [64, 128])
 @pytest.mark.parametrize("flag", ["none", "dst", "src", "acc"])
-def test_chunk_reduce_is_bit_identical_to_row_kernel(width, flag):
-    """The warp-chunk CSR reduction (batched gathers across row boundaries) sums in the same order as the simple
-    one-row-per-warp kernel: identical bits, including ragged / empty rows."""
-    from gen_fvgn_steady_b200 import _lib, ops
+@pytest.mark.parametrize("types", ["f32->f32", "bf16->bf16", "f16->f16", "bf16->f32", "f32->f16"])
+def test_staged_reduce_is_bit_identical_to_row_kernel(width, flag, types):
+    """The block-staged CSR reduction (indices through shared memory, several rows per lane group in flight) sums in the
+    same order as the simple one-row-per-warp kernel: identical bits for every element-type pair, including ragged / empty
+    rows, rows longer than the 4 prefetched entries, a row count that is not a multiple of the 128-row block and blocks
+    with more entries than the shared-memory stage holds."""
+    from gen_fvgn_steady_b200 import _lib
     dev = torch.device("cuda")
     g = torch.Generator(device=dev).manual_seed(4)
     n = 5003
     deg = torch.randint(0, 9, (n,), device=dev, generator=g)
-    deg[::97] = 40                                   # a few rows longer than one 32-entry chunk
+    deg[::97] = 40                                   # a few long rows
+    deg[1000:1128] = 30                              # one block with > 1536 entries: the tail comes straight from global memory
     ptr = torch.zeros(n + 1, dtype=torch.int32, device=dev)
     ptr[1:] = torch.cumsum(deg, 0).int()
     nnz = int(ptr[-1])
     nbr = torch.randint(0, n, (nnz,), device=dev, generator=g, dtype=torch.int32)
-    src = torch.randn((n, width), device=dev, generator=g)
+    tdt = {"f32": torch.float32, "bf16": torch.bfloat16, "f16": torch.float16}
+    ts, td = (tdt[t] for t in types.split("->"))
+    src = torch.randn((n, width), device=dev, generator=g).to(ts)
     fl = {"none": 0, "dst": _lib.FVGN_ADJ_DIV_DST_BY_DEG, "src": _lib.FVGN_ADJ_DIV_SRC_BY_DEG, "acc": _lib.FVGN_ADJ_ACCUMULATE}[flag]
-    init = torch.randn((n, width), device=dev, generator=g)
+    init = torch.randn((n, width), device=dev, generator=g).to(td)
+    code = {torch.float32: _lib.FVGN_T_F32, torch.bfloat16: _lib.FVGN_T_BF16, torch.float16: _lib.FVGN_T_F16}
     outs = []
     for extra in (0, _lib.FVGN_ADJ_SIMPLE_KERNEL):
         out = init.clone()
-        _lib.call("fvgn_adj_reduce", _lib.fptr(src), _lib.iptr(ptr), _lib.iptr(nbr), _lib.fptr(out), n, width, fl | extra,
-                  _lib.stream_ptr(dev))
+        _lib.call("fvgn_adj_reduce_t", _lib.ptr(src), code[ts], _lib.iptr(ptr), _lib.iptr(nbr), _lib.ptr(out), code[td], n, width,
+                  fl | extra, _lib.stream_ptr(dev))
         outs.append(out)
     torch.cuda.synchronize()
     assert torch.equal(outs[0], outs[1])
+    if flag == "none":   # and against torch, fp32 accumulation of the (rounded) source rows
+        ref = torch.zeros((n, width), device=dev).index_add_(0, torch.repeat_interleave(torch.arange(n, device=dev), deg),
+                                                             src.float()[nbr.long()])
+        tol = 1e-5 if td == torch.float32 else 1e-2
+        assert float((outs[0].float() - ref).abs().max() / ref.abs().max()) < tol
+
+
+@pytest.mark.parametrize("width", [64, 128])
+@pytest.mark.parametrize("types", ["f32->f32", "bf16->bf16", "f16->f32"])
+def test_staged_incidence_reduce_matches_torch(width, types):
+    """fvgn_inc_reduce_t on ragged rows (same generator as above): entries are edge*2+role codes into an [E, 2W] array."""
+    from gen_fvgn_steady_b200 import _lib
+    dev = torch.device("cuda")
+    g = torch.Generator(device=dev).manual_seed(5)
+    n, E = 3001, 7000
+    deg = torch.randint(0, 9, (n,), device=dev, generator=g)
+    deg[::89] = 37
+    ptr = torch.zeros(n + 1, dtype=torch.int32, device=dev)
+    ptr[1:] = torch.cumsum(deg, 0).int()
+    nnz = int(ptr[-1])
+    codes = torch.randint(0, 2 * E, (nnz,), device=dev, generator=g, dtype=torch.int32)
+    tdt = {"f32": torch.float32, "bf16": torch.bfloat16, "f16": torch.float16}
+    ts, td = (tdt[t] for t in types.split("->"))
+    tcode = {torch.float32: _lib.FVGN_T_F32, torch.bfloat16: _lib.FVGN_T_BF16, torch.float16: _lib.FVGN_T_F16}
+    src = torch.randn((E, 2 * width), device=dev, generator=g).to(ts)
+    out = torch.empty((n, width), device=dev, dtype=td)
+    _lib.call("fvgn_inc_reduce_t", _lib.ptr(src), tcode[ts], _lib.iptr(ptr), _lib.iptr(codes), _lib.ptr(out), tcode[td], n, width,
+              _lib.stream_ptr(dev))
+    rows = src.float().reshape(2 * E, width)[codes.long()]     # code = edge*2 + role  <->  row of the [2E, W] view
+    ref = torch.zeros((n, width), device=dev).index_add_(0, torch.repeat_interleave(torch.arange(n, device=dev), deg), rows)
+    tol = 1e-5 if td == torch.float32 else 1e-2
+    assert float((out.float() - ref).abs().max() / ref.abs().max()) < tol
 
 
 @pytest.mark.parametrize("mode", ["EDGE", "NODE", "DEC"])
