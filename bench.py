@@ -371,6 +371,59 @@ def example_mesh_records(dev, precision, steps):
     return out
 
 
+def loader_regime_record(dev, precision, steps, cells=100_000):
+    """SURVEY 8(f) row f4 at the size of the reference's larger example meshes: the same EPD step (a) on a resident batch,
+    (b) on a fresh batch object per step from the device pool (gen_fvgn_steady_b200.pool: sample + payback, plan found on
+    the batch), (c) on a fresh batch with NEW tensors per step, as a foreign loader produces (plan found by content hash)."""
+    from gen_fvgn_steady_b200.FVMmodel.importer import NNmodel
+    from gen_fvgn_steady_b200.mesh.batching import graphs_from_meshes
+    from gen_fvgn_steady_b200.pool import DevicePool
+    from gen_fvgn_steady_b200.utils.get_param import params as default_params
+    mesh, uvp = make_mesh(cells, 0, dev)
+    p = default_params(net="EPD", message_passing_num=6, precision=precision, dataset_size=1)
+    torch.manual_seed(0)
+    model = NNmodel(p).to(dev)
+    opt = torch.optim.Adam(model.parameters(), lr=p.lr, fused=True)
+    pool = DevicePool([mesh], [uvp], dev)
+    resident = graphs_from_meshes([mesh], [uvp], dev)
+    x0 = resident[0].x.clone()
+
+    def one(graphs):
+        opt.zero_grad(set_to_none=True)
+        out = model(*graphs, is_training=True)
+        loss = torch.mean(torch.log(p.loss_press * out[3] + p.loss_cont * out[0] + p.loss_mom * out[1] + p.loss_mom * out[2]))
+        loss.backward()
+        opt.step()
+        return out
+
+    def step_resident():
+        resident[0].x, resident[0].norm_uvp, resident[0].norm_global = x0, True, True
+        one(resident)
+
+    def step_pool():
+        graphs, gidx = pool.sample([0])
+        pool.payback(one(graphs)[4], gidx)
+
+    def step_foreign():
+        one(graphs_from_meshes([mesh], [uvp], dev))
+
+    rec = {"cells": int(resident[3].pos.shape[0])}
+    for name, fn in (("resident", step_resident), ("device_pool", step_pool), ("fresh_tensors_content_hash", step_foreign)):
+        for _ in range(3):
+            fn()
+        torch.cuda.synchronize()
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        ev0.record()
+        for _ in range(steps):
+            fn()
+        ev1.record()
+        torch.cuda.synchronize()
+        rec[name] = {"ms_per_step": ev0.elapsed_time(ev1) / steps}
+    for k in ("device_pool", "fresh_tensors_content_hash"):
+        rec[k]["vs_resident"] = rec[k]["ms_per_step"] / rec["resident"]["ms_per_step"]
+    return rec
+
+
 def run_ours(args):
     import torch.distributed as dist
     from gen_fvgn_steady_b200 import _lib
@@ -490,10 +543,12 @@ def run_ours(args):
                 line["nets"] = {"TransFVGN_v2": r}
             del graphs
             torch.cuda.empty_cache()
-            try:
-                line["example_meshes"] = example_mesh_records(dev, args.precision, 20)
-            except Exception as e:  # noqa: BLE001 -- a sub-record must not take the headline down
-                line["example_meshes"] = {"error": repr(e)}
+            for key, fn in (("example_meshes", lambda: example_mesh_records(dev, args.precision, 20)),
+                            ("loader_regime", lambda: loader_regime_record(dev, args.precision, 20))):
+                try:
+                    line[key] = fn()
+                except Exception as e:  # noqa: BLE001 -- a sub-record must not take the headline down
+                    line[key] = {"error": repr(e)}
         else:
             # strong scaling of ONE mesh of --cells cells over the ranks: cell partition + halo
             del graphs

@@ -1,8 +1,12 @@
 """Interplot (src/FVMmodel/FVdiscretization/FVInterpolation.py:36-265): the three interpolation calls the live path uses.
-Inside Intergrator.forward they are fused into the flux kernel (csrc/fv.cu).  The stand-alone methods below only serve
-callers that use Interplot directly; they are plain differentiable torch restatements and are NOT on the fused path."""
+Inside Intergrator.forward they are fused into the flux kernel (csrc/fv.cu).  The stand-alone methods below serve callers
+that use Interplot directly: gathers and per-slot arithmetic are torch elementwise ops, every scatter of the reference is
+the deterministic CSR segment sum ops.segment_sum (fvgn_csr_weighted_sum over a stable CSR built by fvgn_csr_build): no
+atomics, fp32 sums in the reference's scatter order, differentiable."""
 import torch
 from torch import nn
+
+from ... import ops
 
 
 class Interplot(nn.Module):
@@ -11,9 +15,7 @@ class Interplot(nn.Module):
 
     @staticmethod
     def _segment_mean(values, index, n):
-        out = torch.zeros((n,) + tuple(values.shape[1:]), dtype=values.dtype, device=values.device).index_add_(0, index, values)
-        cnt = torch.bincount(index, minlength=n).clamp(min=1).to(values.dtype)
-        return out / cnt.view((-1,) + (1,) * (values.dim() - 1))
+        return ops.segment_sum(values, index, n, "mean")
 
     def node_to_cell_2nd_order(self, node_phi=None, node_grad=None, node_hessian=None, graph_node=None, graph_cell=None,
                                cells_node=None, cells_index=None, mesh_pos=None, centroid=None):
@@ -51,6 +53,6 @@ class Interplot(nn.Module):
         cells_node, cells_index = cells_node.reshape(-1).long(), cells_index.reshape(-1).long()
         w = 1.0 / torch.norm(mesh_pos[cells_node] - centroid[cells_index], dim=-1, keepdim=True).to(cell_phi.dtype)
         n = mesh_pos.shape[0]
-        num = torch.zeros((n, cell_phi.shape[1]), dtype=cell_phi.dtype, device=cell_phi.device).index_add_(0, cells_node, cell_phi[cells_index] * w)
-        den = torch.zeros((n, 1), dtype=cell_phi.dtype, device=cell_phi.device).index_add_(0, cells_node, w)
+        num = ops.segment_sum(cell_phi[cells_index] * w, cells_node, n, "sum")
+        den = ops.segment_sum(w, cells_node, n, "sum")
         return num / den

@@ -555,6 +555,73 @@ def segment_colsum(x, width, ld, chunks, chunk_ptr, nchunks, nseg, center=None, 
     return out
 
 
+# ------------------------------------------------------------------ generic deterministic segment sums
+class SegmentPlan:
+    """Stable CSR (ptr, perm) of an index vector: row i lists the entries k with index[k] == i in storage order, the order
+    a sequential index_add_ / torch_scatter visits them.  Cached per index tensor (weak reference)."""
+    _cache = {}
+
+    def __init__(self, index, n):
+        from .plan import csr_stable
+        self.n = int(n)
+        self.ptr, perm = csr_stable(index.reshape(-1), self.n)
+        self.perm = perm.to(torch.int32).contiguous()
+
+    @classmethod
+    def of(cls, index, n):
+        import weakref
+        key = (index.data_ptr(), tuple(index.shape), index.dtype, str(index.device), int(n))
+        hit = cls._cache.get(key)
+        if hit is not None and hit[0]() is index:
+            return hit[1]
+        plan = cls(index, n)
+        if len(cls._cache) > 64:
+            cls._cache = {k: v for k, v in cls._cache.items() if v[0]() is not None}
+        cls._cache[key] = (weakref.ref(index), plan)
+        return plan
+
+
+class SegmentSumFn(torch.autograd.Function):
+    """out[i] = reduce_{k: index[k] == i} values[k]  (reduce = 'sum' | 'mean'), any trailing shape: the deterministic
+    replacement of scatter(src, index, reduce=...) / index_add_ (utils/utilities.py:16-61, FVInterpolation.py:36-109,
+    218-265, FVgrad.py:183-232).  fp32 sums in storage order = the result of a sequential index_add_.  Backward is a gather."""
+
+    @staticmethod
+    def forward(ctx, values, index, n, reduce):
+        if reduce not in ("sum", "add", "mean"):
+            raise ValueError(f"reduce={reduce!r} is not supported by fvgn_b200 (sum / mean are what the hot path uses)")
+        shape = tuple(values.shape[1:])
+        width = 1
+        for d in shape:
+            width *= int(d)
+        f64 = values.dtype == torch.float64
+        cdt = torch.float64 if f64 else torch.float32
+        v2 = _c(values.reshape(values.shape[0], width).to(cdt))
+        sp = SegmentPlan.of(index, n)
+        out = torch.empty((sp.n, width), dtype=cdt, device=values.device)
+        mean = reduce == "mean"
+        if width > 0 and sp.n > 0:
+            _lib.call("fvgn_csr_weighted_sum_f64" if f64 else "fvgn_csr_weighted_sum", _lib.ptr(v2, cdt), width, width, iptr(sp.ptr),
+                      iptr(sp.perm), None, 1 if mean else 0, _lib.ptr(out, cdt), sp.n, _lib.stream_ptr(values.device))
+        ctx.mean, ctx.shape, ctx.dtype = mean, shape, values.dtype
+        ctx.save_for_backward(index, sp.ptr)
+        return out.reshape((sp.n,) + shape).to(values.dtype)
+
+    @staticmethod
+    def backward(ctx, g):
+        index, ptr = ctx.saved_tensors
+        idx = index.reshape(-1).long()
+        g = g.reshape(g.shape[0], -1)
+        if ctx.mean:
+            cnt = (ptr[1:] - ptr[:-1]).clamp(min=1).to(g.dtype).view(-1, 1)
+            g = g / cnt
+        return g[idx].reshape((idx.shape[0],) + ctx.shape).to(ctx.dtype), None, None, None
+
+
+def segment_sum(values, index, n, reduce="sum"):
+    return SegmentSumFn.apply(values, index, int(n), reduce)
+
+
 # ------------------------------------------------------------------ WLSQ
 class WlsqFn(torch.autograd.Function):
     """node_based_WLSQ (FVgrad.py:235-367, precomputed-moments branch) -> [N, C, nq]."""

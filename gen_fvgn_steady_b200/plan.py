@@ -22,8 +22,22 @@ def _i32(t):
 
 
 def csr_stable(dest, n):
-    """rowptr[n+1] (int32), perm (int64): entries grouped by destination row, original order kept inside a row."""
-    dest = dest.reshape(-1).to(torch.int64)
+    """rowptr[n+1] (int32), perm (int64): entries grouped by destination row, original order kept inside a row.
+    Device tensors: fvgn_csr_build (csrc/plan_build.cu: counting sort + per-row ordering, no library sort, no host sync)."""
+    dest = dest.reshape(-1)
+    if dest.is_cuda:
+        if dest.dtype not in (torch.int32, torch.int64):
+            dest = dest.to(torch.int64)
+        dest = dest.contiguous()
+        m = int(dest.shape[0])
+        ptr = torch.empty(n + 1, dtype=torch.int32, device=dest.device)
+        perm = torch.empty(max(m, 1), dtype=torch.int32, device=dest.device)
+        ws = torch.empty(int(_lib.load().fvgn_csr_build_workspace_bytes(n)), dtype=torch.uint8, device=dest.device)
+        _lib.call("fvgn_csr_build", _lib.ptr(dest), int(dest.dtype == torch.int64), m, n, _lib.iptr(ptr), _lib.iptr(perm), _lib.ptr(ws),
+                  _lib.stream_ptr(dest.device))
+        return ptr, perm[:m].to(torch.int64)
+    # host tensors: only the CPU test harness (tests/test_plan.py, the emulator runs) builds plans on the host
+    dest = dest.to(torch.int64)
     perm = torch.sort(dest, stable=True).indices
     counts = torch.bincount(dest, minlength=n)
     rowptr = torch.zeros(n + 1, dtype=torch.int64, device=dest.device)
@@ -31,37 +45,99 @@ def csr_stable(dest, n):
     return rowptr.to(torch.int32), perm
 
 
-def _chunks(batch, nseg):
-    """Row chunks of <= CHUNK_ROWS rows that never straddle a graph: (chunks[nchunks,3], chunk_ptr[nseg+1])."""
-    counts = torch.bincount(batch.to(torch.int64), minlength=nseg).cpu().tolist()
-    rows, ptr, start = [], [0], 0
-    for seg, cnt in enumerate(counts):
-        r = start
-        while r < start + cnt:
-            e = min(r + CHUNK_ROWS, start + cnt)
-            rows.append((seg, r, e))
-            r = e
-        start += cnt
-        ptr.append(len(rows))
+def _chunks(batch, nseg, rows_per_chunk=CHUNK_ROWS):
+    """Row chunks of <= rows_per_chunk rows that never straddle a graph: (chunks[U,3] = (graph, row begin, row end),
+    chunk_ptr[nseg+1], U).  Built with device ops only (no host round trip): U = N // rows_per_chunk + nseg is an upper
+    bound of the chunk count; slots past chunk_ptr[nseg] are empty chunks (0, 0, 0) that no combine ever reads.
+    `batch` must be sorted by graph (Load_mesh batches are)."""
     dev = batch.device
-    chunks = torch.tensor(rows if rows else [(0, 0, 0)], dtype=torch.int32, device=dev).reshape(-1, 3)
-    return chunks.contiguous(), torch.tensor(ptr, dtype=torch.int32, device=dev), len(rows)
+    n = int(batch.shape[0])
+    U = max(n // rows_per_chunk + nseg, 1)
+    counts = torch.bincount(batch.reshape(-1).to(torch.int64), minlength=nseg)[:nseg]
+    row_ptr = torch.zeros(nseg + 1, dtype=torch.int64, device=dev)
+    torch.cumsum(counts, 0, out=row_ptr[1:])
+    cpg = (counts + rows_per_chunk - 1) // rows_per_chunk
+    chunk_ptr = torch.zeros(nseg + 1, dtype=torch.int64, device=dev)
+    torch.cumsum(cpg, 0, out=chunk_ptr[1:])
+    ids = torch.arange(U, dtype=torch.int64, device=dev)
+    seg = torch.searchsorted(chunk_ptr[1:].contiguous(), ids, right=True).clamp(max=nseg - 1)
+    begin = row_ptr[seg] + (ids - chunk_ptr[seg]) * rows_per_chunk
+    end = torch.minimum(begin + rows_per_chunk, row_ptr[seg + 1])
+    live = ids < chunk_ptr[nseg]
+    zero = torch.zeros_like(ids)
+    chunks = torch.stack([torch.where(live, seg, zero), torch.where(live, begin, zero), torch.where(live, end, zero)], 1)
+    return chunks.to(torch.int32).contiguous(), chunk_ptr.to(torch.int32), U
+
+
+def num_graphs_of(graph, batch):
+    """Number of graphs of a batch object without a device round trip when the loader says so (PyG Batch.num_graphs)."""
+    ng = getattr(graph, "num_graphs", None)
+    if ng is not None:
+        return int(ng)
+    return int(batch.max().item()) + 1 if batch.numel() > 0 else 1
+
+
+def content_hash(tensors):
+    """64-bit content hash of a list of device tensors (fvgn_hash_words; one 8-byte device -> host read)."""
+    dev = tensors[0].device
+    acc = torch.zeros(1, dtype=torch.int64, device=dev)
+    st = _lib.stream_ptr(dev)
+    for i, t in enumerate(tensors):
+        t = t.contiguous()
+        nbytes = t.numel() * t.element_size()
+        if nbytes % 4 != 0:   # bool / int8 / 16-bit tensors of odd length: widen
+            t = t.to(torch.int32)
+            nbytes = t.numel() * 4
+        _lib.call("fvgn_hash_words", _lib.ptr(t), nbytes // 4, 1000003 * (i + 1) + t.numel(), _lib.ptr(acc), st)
+    return int(acc.item())
 
 
 class GraphPlan:
     """Device-resident topology plan of one batch.  Build with GraphPlan.build(...) or GraphPlan.of(...) (cached)."""
 
+    _by_content = {}   # content hash -> plan (most recent 8 topologies)
+
+    @staticmethod
+    def _plan_inputs(graph_node, graph_node_x, graph_edge, graph_cell):
+        ts = [graph_node.edge_index]
+        if getattr(graph_node, "batch", None) is not None:
+            ts.append(graph_node.batch)
+        if graph_node_x is not None:
+            ts += [graph_node.face, graph_node.pos, graph_node.node_type, graph_node.y, graph_node_x.face_node_x,
+                   graph_node_x.support_edge, graph_node_x.A_node_to_node, graph_node_x.single_B_node_to_node,
+                   graph_node_x.extra_B_node_to_node, graph_edge.face, graph_edge.pos, graph_edge.face_area, graph_edge.face_type,
+                   graph_cell.face, graph_cell.pos, graph_cell.cells_area, graph_cell.cells_face_unv, graph_cell.batch]
+        return ts
+
     @staticmethod
     def of(graph_node, graph_node_x=None, graph_edge=None, graph_cell=None, order="2nd"):
+        """The plan of this batch.  Fast path: the batch object (or one sharing its index tensors) was seen before.  A
+        loader that hands a NEW batch object every step (Graph_loader.py:830-1006) is recognised by CONTENT: a 64-bit
+        hash of every tensor the plan is built from (connectivity, geometry, boundary targets, WLSQ matrices) costs one
+        read pass + an 8-byte device -> host copy instead of the ~25 plan-building launches."""
         key = (graph_node.edge_index.data_ptr(), tuple(graph_node.edge_index.shape))
         key_fv = None if graph_node_x is None else (graph_node_x.face_node_x.data_ptr(), graph_cell.face.data_ptr(), order)
         plan = getattr(graph_node, "_fvgn_plan", None)
         if plan is not None and plan.key == key and (key_fv is None or plan.key_fv == key_fv):
             return plan
+        halo = getattr(graph_node, "_fvgn_halo", None)
+        h = None
+        if graph_node.edge_index.is_cuda and halo is None:
+            h = (content_hash(GraphPlan._plan_inputs(graph_node, graph_node_x, graph_edge, graph_cell)), order,
+                 graph_node_x is not None, str(graph_node.edge_index.device))
+            plan = GraphPlan._by_content.get(h)
+            if plan is not None:
+                graph_node._fvgn_plan = plan
+                plan.key, plan.key_fv = key, key_fv
+                return plan
         plan = GraphPlan.build(graph_node, graph_node_x, graph_edge, graph_cell, order)
         plan.key, plan.key_fv = key, key_fv
-        plan.halo = getattr(graph_node, "_fvgn_halo", None)  # cell-partition mode (partition.py)
+        plan.halo = halo  # cell-partition mode (partition.py)
         graph_node._fvgn_plan = plan
+        if h is not None:
+            if len(GraphPlan._by_content) >= 8:
+                GraphPlan._by_content.pop(next(iter(GraphPlan._by_content)))
+            GraphPlan._by_content[h] = plan
         return plan
 
     @staticmethod
@@ -85,7 +161,7 @@ class GraphPlan:
         if batch is None:
             batch = torch.zeros(N, dtype=torch.int64, device=dev)
         p.batch_node = _i32(batch)
-        p.B = int(batch.max().item()) + 1 if N > 0 else 1
+        p.B = num_graphs_of(graph_node, batch) if N > 0 else 1
         p.node_chunks, p.node_chunk_ptr, p.n_node_chunks = _chunks(batch, p.B)
         p.has_fv = False
         p.halo = None

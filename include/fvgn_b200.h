@@ -55,6 +55,28 @@ int fvgn_adj_reduce_t(const void* src, int32_t src_type, const int32_t* ptr, con
 int fvgn_inc_reduce_t(const void* src, int32_t src_type, const int32_t* ptr, const int32_t* code, void* dst,
                       int32_t dst_type, int64_t n_rows, int32_t width, void* stream);
 
+/* ------------------------------------------------------------------ plan-time kernels
+ * Stable CSR of a scatter entry list: ptr[n_rows+1], perm[n_entries] = the entries grouped by destination row, inside a
+ * row in their original order -- the order torch_scatter / index_add_ visit them (blocks.py:24-51,84-99;
+ * FVgrad.py:264-325; Load_mesh/Graph_loader.py builds no CSR: the reference scatters by atomics).  dest: int32 or int64
+ * entries in [0, n_rows) (out-of-range entries are skipped).  workspace: fvgn_csr_build_workspace_bytes(n_rows) bytes.
+ * Deterministic: counts and fill use integer atomics, then every row orders its own entries by entry number. */
+int64_t fvgn_csr_build_workspace_bytes(int64_t n_rows);
+int fvgn_csr_build(const void* dest, int32_t dest_is_int64, int64_t n_entries, int64_t n_rows, int32_t* ptr, int32_t* perm,
+                   void* workspace, void* stream);
+/* *out_u64 += order-sensitive 64-bit content hash of n_words 32-bit words (the key of the topology plan cache: a loader
+ * hands a NEW batch object with the SAME index tensors every step, Graph_loader.py:830-1006) */
+int fvgn_hash_words(const void* data, int64_t n_words, int64_t seed, void* out_u64, void* stream);
+/* dst[i, 0:width] = sum_{t in [ptr[i], ptr[i+1])} w[t] * src[idx[t], 0:width]  (idx NULL: identity, w NULL: 1), entries in
+ * CSR order, products rounded before the add (= a sequential index_add_ of src * w); mode 0 sum, 1 mean over the row's
+ * entries (count clamped to 1), 2 divided by the row's sum of w.  Deterministic replacement of the scatter / index_add_
+ * calls of the stand-alone FV API: utils/utilities.py:16-61, FVInterpolation.py:36-109,218-265, FVgrad.py:183-232. */
+int fvgn_csr_weighted_sum(const float* src, int32_t width, int32_t ld, const int32_t* ptr, const int32_t* idx, const float* w,
+                          int32_t mode, float* dst, int64_t n_rows, void* stream);
+/* the same on fp64 data (setup-time callers: compute_normal_matrix assembles the WLSQ moment matrices in fp64) */
+int fvgn_csr_weighted_sum_f64(const void* src, int32_t width, int32_t ld, const int32_t* ptr, const int32_t* idx, const void* w,
+                              int32_t mode, void* dst, int64_t n_rows, void* stream);
+
 /* ------------------------------------------------------------------ fused MLP blocks */
 #define FVGN_MLP_EDGE 0     /* EdgeBlock  blocks.py:101-111 + EPD.py:170-175,186 : in=[agg[s]|agg[r]|e], K1=384, LN, +e   */
 #define FVGN_MLP_NODE 1     /* NodeBlock  blocks.py:54 + EPD.py:163-168,185      : in=[a2|x],           K1=192, LN, +x   */

@@ -9,7 +9,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(os.path.dirname(HERE))
 CSRC = os.path.join(ROOT, "gen_fvgn_steady_b200", "csrc")
 LIB = os.path.join(HERE, "libfvgn_emu.so")
-SOURCES = ["segreduce.cu", "mlp_simt.cu", "mlp_api.cu", "misc.cu", "fv.cu", "transolver.cu"]
+SOURCES = ["segreduce.cu", "mlp_simt.cu", "mlp_api.cu", "misc.cu", "fv.cu", "transolver.cu", "plan_build.cu"]
 
 
 def build(force=False):
