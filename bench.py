@@ -279,7 +279,7 @@ class Job:
 
     def eager_step(self, e2e):
         gn, gx, ge, gc, gi = self.graphs
-        gn.x = self._next_x() if e2e else self.x_dev0
+        gn.x = self._next_x() if e2e else self.x_dev0.clone()   # the forward normalises graph_node.x in place
         gn.norm_uvp, gn.norm_global = True, True
         self.flat_grad.zero_()
         out = self.model(gn, gx, ge, gc, gi, is_training=True)
@@ -397,7 +397,7 @@ def loader_regime_record(dev, precision, steps, cells=100_000):
         return out
 
     def step_resident():
-        resident[0].x, resident[0].norm_uvp, resident[0].norm_global = x0, True, True
+        resident[0].x, resident[0].norm_uvp, resident[0].norm_global = x0.clone(), True, True
         one(resident)
 
     def step_pool():

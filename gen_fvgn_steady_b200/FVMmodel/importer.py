@@ -136,7 +136,15 @@ class NNmodel(nn.Module):
         params = self.params
         plan = GraphPlan.of(graph_node, graph_node_x, graph_edge, graph_cell, getattr(params, "order", "2nd"))
         xn, uv_old = self.update_x_attr(graph_node, graph_Index, plan)
-        graph_node.x = xn                       # the reference normalises graph_node.x in place (:121,:127)
+        # The reference normalises graph_node.x IN PLACE (importer.py:121,127): a caller that keeps an alias of the tensor
+        # -- solve_with_grad_GPU.py:138-145 restores `graph_node.x = uvp_pde_theta_backup` every inner iteration, the very
+        # tensor the previous forward normalised -- sees the normalised values.  Same observable behaviour here.
+        x_in = graph_node.x
+        if (x_in.dtype == torch.float32 and x_in.is_contiguous() and x_in.shape == xn.shape and not x_in.requires_grad
+                and x_in.data_ptr() != xn.data_ptr()):
+            x_in.copy_(xn)
+            xn = x_in
+        graph_node.x = xn
         graph_node.norm_uvp = False
         graph_node.norm_global = False
         raw = self.simulator(graph_node, graph_edge, graph_cell)

@@ -88,7 +88,7 @@ class GraphedTrainStep:
 
     def _prepare(self):
         gn = self.graphs[0]
-        gn.x = self.x_static
+        gn.x = self.x_static.clone()   # the forward normalises graph_node.x in place (as the reference does): keep the raw copy
         gn.norm_uvp, gn.norm_global = self._norm_flags
 
     def _body(self):

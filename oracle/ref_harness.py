@@ -137,6 +137,42 @@ def build_ref_graphs(meshes, uvps, dtype=torch.float32):
     return graph_node, graph_node_x, graph_edge, graph_cell, graph_Index
 
 
+def ref_loader_graphs(meshes, uvps, ids=None):
+    """The five batch objects made by the REFERENCE's own dataset classes (Graph_loader.py:503-784: GraphNodeDataset,
+    GraphNode_X_Dataset, GraphEdgeDataset, GraphCellDataset, Graph_INDEX_Dataset .get) on a stand-in for Data_Pool's
+    storage (meta_pool / uvp_node_pool / init_loss, Graph_loader.py:60-128), batched with the PyG collate rule driven by
+    the reference's CustomGraphData.__inc__ / __cat_dim__ (ref_shims.collate), then Data_Pool.datapreprocessing (:130-152).
+    meshes: dicts of torch tensors with the converter keys; ids: the sampled graph indices (default: all, in order)."""
+    ref_shims.install()
+    import Load_mesh.Graph_loader as GL
+    pool, off = [], 0
+    for i, m in enumerate(meshes):
+        m = dict(m)
+        n = m["node|pos"].shape[0]
+        m["global_idx"] = torch.arange(off, off + n)
+        m.setdefault("case_name", f"case{i}")
+        # the converter's per-graph scalars are rows of the batched [B, k] tensors (Load_mesh.py:133-211)
+        for k in ("theta_PDE", "sigma", "uvp_dim", "dt_graph"):
+            m[k] = torch.as_tensor(m[k]).reshape(1, -1)
+        m["face|face_area"] = torch.as_tensor(m["face|face_area"]).reshape(-1, 1)
+        off += n
+        pool.append(m)
+
+    class _Pool:   # the attributes the dataset classes read from Data_Pool
+        meta_pool = pool
+        uvp_node_pool = torch.cat([torch.as_tensor(u, dtype=torch.float32) for u in uvps], 0)
+        init_loss = torch.full((len(pool),), 1.0)
+        params = None
+    ids = list(range(len(pool))) if ids is None else list(ids)
+    batches = []
+    for cls in (GL.GraphNodeDataset, GL.GraphNode_X_Dataset, GL.GraphEdgeDataset, GL.GraphCellDataset, GL.Graph_INDEX_Dataset):
+        ds = cls(_Pool)
+        batches.append(ref_shims.collate([ds.get(i) for i in ids]))
+    graphs = GL.Data_Pool.datapreprocessing(*batches)
+    graphs[0].norm_uvp, graphs[0].norm_global = True, True
+    return graphs
+
+
 def make_ref_model(params, dtype=torch.float32):
     ref_shims.install()
     from FVMmodel.importer import NNmodel

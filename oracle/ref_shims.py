@@ -97,7 +97,10 @@ class Data:
 
     def __init__(self, **kwargs):
         for k, v in kwargs.items():
-            setattr(self, k, v)
+            setattr(self, k, v)      # num_nodes goes through the property setter below
+
+    def __init_subclass__(cls, **kw):
+        super().__init_subclass__(**kw)
 
     def keys(self):
         return [k for k in self.__dict__ if not k.startswith("_")]
@@ -123,10 +126,61 @@ class Data:
         return d
 
     def __inc__(self, key, value, *a, **k):
+        # torch_geometric.data.Data.__inc__: 'batch' and '*index' / 'face' attributes are offset by num_nodes
+        if "batch" in key and torch.is_tensor(value):
+            return int(value.max()) + 1
+        if "index" in key or key == "face":
+            return self.num_nodes
         return 0
 
     def __cat_dim__(self, key, value, *a, **k):
+        # torch_geometric.data.Data.__cat_dim__: '*index' / 'face' attributes concatenate along the last dimension
+        if "index" in key or key == "face":
+            return -1
         return 0
+
+    _N_KEYS = ("x", "feat", "pos", "batch", "node_type", "n_id", "tf")
+
+    @property
+    def num_nodes(self):
+        """torch_geometric NodeStorage.num_nodes: the explicit value, else the size of the first node-level attribute."""
+        if "_num_nodes" in self.__dict__:
+            return self.__dict__["_num_nodes"]
+        for k, v in self.__dict__.items():
+            if torch.is_tensor(v) and k in self._N_KEYS:
+                return v.size(self.__cat_dim__(k, v))
+        return None
+
+    @num_nodes.setter
+    def num_nodes(self, n):
+        self.__dict__["_num_nodes"] = n
+
+
+def collate(data_list):
+    """torch_geometric.data.Batch.from_data_list restated for tensor attributes: every attribute is concatenated along
+    data.__cat_dim__(key, value) after adding the running sum of data.__inc__(key, value) of the preceding graphs; the
+    node -> graph vector `batch` and `num_graphs` are added (torch_geometric/data/collate.py).  The offsets and
+    concatenation axes therefore come from the REFERENCE's CustomGraphData.__inc__ / __cat_dim__ (Graph_loader.py:405-480)."""
+    first = data_list[0]
+    out = first.__class__()
+    for key in first.keys():
+        vals = [getattr(d, key) for d in data_list]
+        if not torch.is_tensor(vals[0]):
+            setattr(out, key, vals)
+            continue
+        dim = first.__cat_dim__(key, vals[0])
+        inc, shifted = 0, []
+        for d, v in zip(data_list, vals):
+            shifted.append(v + inc if (isinstance(inc, int) and inc != 0) or torch.is_tensor(inc) else v)
+            step = d.__inc__(key, v)
+            inc = inc + (step if step is not None else 0)
+        setattr(out, key, torch.stack(shifted, 0) if dim is None else torch.cat(shifted, dim))
+    nn = [d.num_nodes for d in data_list]
+    if all(n is not None for n in nn):
+        out.batch = torch.cat([torch.full((int(n),), i, dtype=torch.long) for i, n in enumerate(nn)])
+        out.num_nodes = int(sum(nn))
+    out.num_graphs = len(data_list)
+    return out
 
 
 def _global_add_pool(x, batch, size=None):

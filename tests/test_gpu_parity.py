@@ -192,7 +192,7 @@ def test_graphed_step_matches_eager_steps(net):
         ls = []
         if tag == "eager":
             for _ in range(6):
-                graphs[0].x, graphs[0].norm_uvp, graphs[0].norm_global = x0, True, True
+                graphs[0].x, graphs[0].norm_uvp, graphs[0].norm_global = x0.clone(), True, True
                 opt.zero_grad(set_to_none=True)
                 loss = loss_fn(model(*graphs, is_training=True))
                 loss.backward()
@@ -233,7 +233,7 @@ def test_tensor_core_loss_trajectory_tracks_fp32():
         opt = torch.optim.Adam(model.parameters(), lr=2e-4)
         ls = []
         for _ in range(20):
-            graphs[0].x, graphs[0].norm_uvp, graphs[0].norm_global = x0, True, True
+            graphs[0].x, graphs[0].norm_uvp, graphs[0].norm_global = x0.clone(), True, True
             opt.zero_grad(set_to_none=True)
             loss = PU.script_loss(model(*graphs, is_training=True), p)
             loss.backward()

@@ -29,7 +29,7 @@ x0 = graphs[0].x.clone()
 opt_a = torch.optim.Adam(model_a.parameters(), lr=1e-3, fused=True, capturable=True)
 snaps = []
 for it in range(3):
-    graphs[0].x, graphs[0].norm_uvp, graphs[0].norm_global = x0, True, True
+    graphs[0].x, graphs[0].norm_uvp, graphs[0].norm_global = x0.clone(), True, True
     opt_a.zero_grad(set_to_none=True)
     loss = loss_fn(model_a(*graphs, is_training=True))
     loss.backward()
