@@ -64,7 +64,7 @@ def run_reference(case, meshes, uvps, dtype):
     torch.set_default_dtype(dtype)
     try:
         params = ref_shims.ref_params(net=case["net"], dataset_size=case["dataset_size"],
-                                      conserved_form=case.get("conserved_form", True))
+                                      conserved_form=case.get("conserved_form", True), integrator=case.get("integrator", "imex"))
         H.seed_all(0)
         model = H.make_ref_model(params, dtype)
         shapes = {k: tuple(v.shape) for k, v in model.state_dict().items()}
@@ -109,7 +109,7 @@ def main():
         if only and name not in only:
             continue
         params = ref_shims.ref_params(net=case["net"], dataset_size=case["dataset_size"],
-                                      conserved_form=case.get("conserved_form", True))
+                                      conserved_form=case.get("conserved_form", True), integrator=case.get("integrator", "imex"))
         meshes, uvps, payload = build_case_inputs(case, params)
         keys = None
         for tag, dt in (("f32", torch.float32), ("f64", torch.float64)):

@@ -38,6 +38,17 @@ CASES = {
              physics=dict(mean_u=1.2, mu=0.015, dt=0.3, inlet_type="parabolic", init_field_type="parabolic")),
         dict(n=0, nx=6, ny=11, kind="mixed", bc="cavity", seed=6, physics=dict(mean_u=1.0, mu=0.01)),
     ]),
+    # the two other time integrators of importer.py:192-201 (--integrator explicit / implicit; imex is the default)
+    "synth_ns_batch2_v1_explicit": dict(net="TransFVGN_v1", dataset_size=100, integrator="explicit", mesh=[
+        dict(n=0, nx=9, ny=9, kind="quad", bc="channel", seed=5,
+             physics=dict(mean_u=1.2, mu=0.015, dt=0.3, inlet_type="parabolic", init_field_type="parabolic")),
+        dict(n=0, nx=6, ny=11, kind="mixed", bc="cavity", seed=6, physics=dict(mean_u=1.0, mu=0.01)),
+    ]),
+    "synth_ns_batch2_v1_implicit": dict(net="TransFVGN_v1", dataset_size=100, integrator="implicit", mesh=[
+        dict(n=0, nx=9, ny=9, kind="quad", bc="channel", seed=5,
+             physics=dict(mean_u=1.2, mu=0.015, dt=0.3, inlet_type="parabolic", init_field_type="parabolic")),
+        dict(n=0, nx=6, ny=11, kind="mixed", bc="cavity", seed=6, physics=dict(mean_u=1.0, mu=0.01)),
+    ]),
 }
 
 

@@ -35,7 +35,7 @@ def run_product(name, device, precision="fp32"):
     meshes, uvps, z = case_meshes(name)
     graphs = product_graphs(meshes, uvps, device)
     p = default_params(net=case["net"], dataset_size=case["dataset_size"], precision=precision,
-                       conserved_form=case.get("conserved_form", True))
+                       conserved_form=case.get("conserved_form", True), integrator=case.get("integrator", "imex"))
     model = NNmodel(p)
     sd = case_state_dict(z)
     missing = model.load_state_dict(sd, strict=True)

@@ -14,7 +14,8 @@ def _emu():
     PU.use_real_kernels()
 
 
-@pytest.mark.parametrize("name", ["synth_ns_batch2_v1", "synth_ns_batch2_v2", "synth_ns_batch2_v1_nc"])
+@pytest.mark.parametrize("name", ["synth_ns_batch2_v1", "synth_ns_batch2_v2", "synth_ns_batch2_v1_nc", "synth_ns_batch2_v1_explicit",
+                                  "synth_ns_batch2_v1_implicit"])
 def test_emulated_product_matches_reference(name):
     model, out, loss, z = PU.run_product(name, "cpu")
     rep = {}

@@ -16,7 +16,7 @@ def _run(name, dtype):
     sd = {k: (v.clone().requires_grad_(True) if not k.startswith("node_norm.") else v)
           for k, v in case_state_dict(z, dtype).items()}
     res = O.nnmodel_forward(sd, g, net=case["net"], dataset_size=case["dataset_size"], return_aux=True,
-                            conserved_form=case.get("conserved_form", True))
+                            conserved_form=case.get("conserved_form", True), integrator=case.get("integrator", "imex"))
     loss = O.script_loss(res)
     loss.backward()
     return res, loss, sd, z
