@@ -347,28 +347,44 @@ def quick_rate(dev, rank, world, graphs, net, mp, precision, steps, cells_total,
 
 
 def example_mesh_records(dev, precision, steps):
-    """Throughput on the reference's own example meshes (BASELINE.json configs 0-2), taken from the golden fixtures
-    (tests/golden/*.npz hold the meshes as parsed by the reference's COMSOL parser; /root/reference is not needed):
-    the default net TransFVGN_v2 (6 GnBlocks + 2 Transolver blocks), eager and as one CUDA graph per step."""
+    """Throughput on the reference's own example meshes (BASELINE.json configs 0-3), taken from the golden fixtures
+    (tests/golden/*.npz hold the meshes as parsed by the reference's COMSOL / Tecplot parsers; /root/reference is not
+    needed): the default net TransFVGN_v2 (6 GnBlocks + 2 Transolver blocks), eager and as one CUDA graph per step.  The
+    airfoil case is BASELINE config 3: a batch of 64 graphs (N = 1.08 M nodes) -- the two parameter draws the reference's
+    sampler made for the golden case, 32 copies each."""
     from gen_fvgn_steady_b200.mesh.batching import graphs_from_meshes
     from tests import golden_util as GU
     out = {}
-    for name, label in (("lid_cavity_101_v2", "lid_driven_cavity_101x101-Re=100"), ("cylinder_tri_quad_v1", "cylinder_flow_tri_quad"),
-                        ("poisson_quad_tri_v2", "poisson/cavity_poisson_quad_tri")):
+    for name, label, copies in (("lid_cavity_101_v2", "lid_driven_cavity_101x101-Re=100", 1),
+                                ("cylinder_tri_quad_v1", "cylinder_flow_tri_quad", 1),
+                                ("cylinder_poly_v1", "cylinder_flow_poly (polygon cells)", 1),
+                                ("poisson_quad_tri_v2", "poisson/cavity_poisson_quad_tri", 1),
+                                ("airfoil_naca0012_b2_v2", "airfoil_L=1/NACA0012, batch of 64 graphs", 32)):
         path = os.path.join(GU.GOLDEN_DIR, name + ".npz")
         if not os.path.exists(path):
             continue
         z = GU.load_case(name)
-        mesh = GU.mesh_from_npz(z)
+        meshes, uvps = GU.example_case_graphs(z)
+        meshes, uvps = meshes * copies, uvps * copies
         rec = {}
         for graph in (False, True):
-            graphs = graphs_from_meshes([mesh], [z["uvp0"]], dev)
+            graphs = graphs_from_meshes(meshes, uvps, dev)
             C = int(graphs[3].pos.shape[0])
             r = quick_rate(dev, 0, 1, graphs, "TransFVGN_v2", 3, precision, steps, C, graph=graph)
             rec["cuda_graph" if graph else "eager"] = {"value": r["value"], "ms_per_step": r["ms_per_step"]}
-            rec.update(cells=C, nodes=int(graphs[0].pos.shape[0]))
+            rec.update(graphs=len(meshes), cells=C, nodes=int(graphs[0].pos.shape[0]))
+            del graphs
         out[label] = rec
     return out
+
+
+def grad_rec_record(dev):
+    """BASELINE.json config 1: the loop of src/grad_rec_speed_test.py:118-159 (node_based_WLSQ on one mesh, scalar field,
+    precomputed moments) at the size of the cavity_poisson_81x81 example and at 1 M nodes, eager and as a CUDA graph."""
+    sys.path.insert(0, os.path.join(ROOT, "tools"))
+    import grad_rec_speed as G
+    hbm, _ = peaks()
+    return [G.measure(n, dev, hbm, cg) for n in (80, 1000) for cg in (False, True)]
 
 
 def loader_regime_record(dev, precision, steps, cells=100_000):
@@ -544,7 +560,8 @@ def run_ours(args):
             del graphs
             torch.cuda.empty_cache()
             for key, fn in (("example_meshes", lambda: example_mesh_records(dev, args.precision, 20)),
-                            ("loader_regime", lambda: loader_regime_record(dev, args.precision, 20))):
+                            ("loader_regime", lambda: loader_regime_record(dev, args.precision, 20)),
+                            ("grad_rec_speed", lambda: grad_rec_record(dev))):
                 try:
                     line[key] = fn()
                 except Exception as e:  # noqa: BLE001 -- a sub-record must not take the headline down

@@ -40,14 +40,25 @@ def build_case_inputs(case, params):
     payload = {}
     if isinstance(case["mesh"], str):
         rel = case["mesh"].split(":", 1)[1]
-        mesh, uvp = H.load_example(os.path.join(REF_MESH_ROOT, rel), params, seed=0)
-        uvp = torch.from_numpy(GU.perturbed_field(uvp.numpy(), 0))
-        for k in GU.MESH_KEYS_F64 + GU.MESH_KEYS_F32:
-            payload["mesh." + k] = mesh[k].numpy()
-        for k in GU.MESH_KEYS_I:
-            payload["mesh." + k] = mesh[k].numpy().astype(np.int32)
-        payload["uvp0"] = uvp.numpy()
-        return [mesh], [uvp], payload
+        meshes, uvps = [], []
+        for gi, seed in enumerate(case.get("batch_seeds", [0])):
+            # one run of the reference's parser + transform_mesh per graph: the sampler (random.choice over the BC.json
+            # grid, Load_mesh.py:133-211) draws this graph's inlet velocity / viscosity from its seed
+            mesh, uvp = H.load_example(os.path.join(REF_MESH_ROOT, rel), params, seed=seed)
+            uvp = torch.from_numpy(GU.perturbed_field(uvp.numpy(), seed))
+            if gi == 0:
+                for k in GU.MESH_KEYS_F64 + GU.MESH_KEYS_F32:
+                    payload["mesh." + k] = mesh[k].numpy()
+                for k in GU.MESH_KEYS_I:
+                    payload["mesh." + k] = mesh[k].numpy().astype(np.int32)
+                payload["uvp0"] = uvp.numpy()
+            else:
+                for k in ("theta_PDE", "dt_graph", "sigma", "uvp_dim", "target|uvp"):
+                    payload[f"g{gi}.{k}"] = mesh[k].numpy()
+                payload[f"g{gi}.uvp0"] = uvp.numpy()
+            meshes.append(mesh)
+            uvps.append(uvp)
+        return meshes, uvps, payload
     meshes, uvps = [], []
     for i, spec in enumerate(case["mesh"]):
         m, uvp = S.make_case(**spec)

@@ -67,9 +67,27 @@ def attach_bc_and_transform(mesh, bc, case_name, params):
     return mesh_t, init_uvp
 
 
+def extract_tecplot_mesh(mesh_path):
+    """Run the reference's Tecplot FEPolygon parser (parse_tecplot.py:50-679) + extract_mesh_state on one .dat file."""
+    ref_shims.install()
+    from Extract_mesh import parse_tecplot
+    file_dir = os.path.dirname(mesh_path)
+    case_name = os.path.basename(file_dir)
+    path = {"simulator": "Tecplot", "mesh_only": True, "file_dir": file_dir, "case_name": case_name,
+            "file_name": os.path.basename(mesh_path)}
+    parse_tecplot.TecplotMesh.save_to_vtu = lambda self, *a, **k: None
+    with redirect_stdout(io.StringIO()):
+        mgr = parse_tecplot.TecplotMesh(mesh_file=mesh_path, data_file=None, file_dir=file_dir, case_name=case_name, path=path)
+        mesh = mgr.extract_mesh(mesh_only=True)
+    return mesh, file_dir, case_name
+
+
 def load_example(mesh_path, params, seed=0):
     seed_all(seed)
-    mesh, file_dir, case_name = extract_comsol_mesh(mesh_path)
+    if mesh_path.endswith(".dat"):
+        mesh, file_dir, case_name = extract_tecplot_mesh(mesh_path)
+    else:
+        mesh, file_dir, case_name = extract_comsol_mesh(mesh_path)
     bc = json.load(open(os.path.join(file_dir, "BC.json")))
     return attach_bc_and_transform(mesh, bc, case_name, params)
 

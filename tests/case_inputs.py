@@ -13,7 +13,8 @@ def case_meshes(name):
     case = GU.CASES[name]
     z = GU.load_case(name)
     if isinstance(case["mesh"], str):
-        return [GU.mesh_from_npz(z)], [z["uvp0"]], z
+        meshes, uvps = GU.example_case_graphs(z)
+        return meshes, uvps, z
     meshes, uvps = [], []
     for i, spec in enumerate(case["mesh"]):
         m, uvp = S.make_case(**spec)

@@ -38,6 +38,14 @@ CASES = {
              physics=dict(mean_u=1.2, mu=0.015, dt=0.3, inlet_type="parabolic", init_field_type="parabolic")),
         dict(n=0, nx=6, ny=11, kind="mixed", bc="cavity", seed=6, physics=dict(mean_u=1.0, mu=0.01)),
     ]),
+    # BASELINE.json configs[3]: parametric steady NS on the NACA0012 airfoil example mesh (N = 16 861 nodes, C = 30 684 mixed
+    # cells, WLSQ moment matrices with condition numbers up to 1e9: the gradient-reconstruction stress case), a batch of two
+    # graphs with inlet velocities drawn from the BC.json grid by the reference's own sampler (seeds 0 and 1)
+    "airfoil_naca0012_b2_v2": dict(net="TransFVGN_v2", dataset_size=100, batch_seeds=[0, 1],
+                                   mesh="example:airfoil_L=1/farfield_NACA0012_with_quad_bc/mesh_2.mphtxt"),
+    # BASELINE.json configs[2]: the polygonal cylinder-flow example (Tecplot FEPolygon, cells of 3-9 vertices that are NOT
+    # grouped by type, N = 27 778 nodes, C = 17 436 cells) parsed by the reference's parse_tecplot.py
+    "cylinder_poly_v1": dict(net="TransFVGN_v1", dataset_size=100, mesh="example:cylinder_flow_poly/mesh.dat"),
     # the two other time integrators of importer.py:192-201 (--integrator explicit / implicit; imex is the default)
     "synth_ns_batch2_v1_explicit": dict(net="TransFVGN_v1", dataset_size=100, integrator="explicit", mesh=[
         dict(n=0, nx=9, ny=9, kind="quad", bc="channel", seed=5,
@@ -104,9 +112,20 @@ MESH_KEYS_F32 = ("A_node_to_node", "single_B_node_to_node", "extra_B_node_to_nod
                  "uvp_dim", "target|uvp")
 
 
-def mesh_from_npz(z, prefix="mesh."):
+def mesh_from_npz(z, prefix="mesh.", graph=0):
+    """Mesh dictionary of graph `graph` of an example-mesh case: graphs > 0 share the geometry / connectivity of graph 0
+    and carry their own physical parameters and targets under the prefix g{graph}."""
     m = {}
     for k in MESH_KEYS_F64 + MESH_KEYS_I + MESH_KEYS_F32:
-        v = z[prefix + k]
+        own = f"g{graph}.{k}"
+        v = z[own] if (graph > 0 and own in z) else z[prefix + k]
         m[k] = v.astype(np.int64) if k in MESH_KEYS_I else v
     return m
+
+
+def example_case_graphs(z):
+    """-> (meshes, uvps) of an example-mesh case (1 graph, or len(batch_seeds) graphs on the same mesh)."""
+    n = 1
+    while f"g{n}.uvp0" in z:
+        n += 1
+    return [mesh_from_npz(z, graph=i) for i in range(n)], [z["uvp0"] if i == 0 else z[f"g{i}.uvp0"] for i in range(n)]

@@ -15,14 +15,8 @@ import torch
 from gen_fvgn_steady_b200.mesh import synthetic_torch as ST
 from gen_fvgn_steady_b200.FVMmodel.FVdiscretization.FVgrad import node_based_WLSQ
 
-sides = [int(a) for a in sys.argv[1:]] or [80, 1000, 2000]
-dev = torch.device("cuda")
-peak = 6545.3
-try:
-    peak = float(json.load(open(os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "MEASURED_PEAKS.json")))["hbm_gbs"])
-except Exception:
-    pass
-for n in sides:
+def measure(n, dev, peak, cuda_graph=False):
+    """One mesh of n x n quad cells: us per node_based_WLSQ call (eager, or replayed as a one-call CUDA graph)."""
     mesh, _ = ST.make_case(n, kind="quad", bc="cavity", seed=0, device=dev)
     pos = mesh["node|pos"].float().contiguous()
     fx, se = mesh["face_node_x"].long(), mesh["support_edge"].long()
@@ -38,11 +32,26 @@ for n in sides:
     with torch.no_grad():
         g = call()
         torch.cuda.synchronize()
+        run = call
+        if cuda_graph:
+            side = torch.cuda.Stream()
+            side.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(side):
+                for _ in range(3):
+                    call()
+            torch.cuda.current_stream().wait_stream(side)
+            cg = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(cg):
+                g = call()
+            run = cg.replay
         reps = 2000 if n <= 200 else 100
+        for _ in range(10):
+            run()
+        torch.cuda.synchronize()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
         for _ in range(reps):
-            g = call()
+            run()
         e1.record()
         torch.cuda.synchronize()
     us = e0.elapsed_time(e1) * 1e3 / reps
@@ -51,6 +60,19 @@ for n in sides:
     alg = nnz * (4 + 5 * 4) + N * (4 + 5 * 4)  # column index + five folded weights per entry; field in, 5 moments out
     ref = torch.stack([gx, gy], 1)
     err = float((g[:, 0, 0:2].double() - ref).norm() / ref.norm())
-    print(json.dumps({"n_side": n, "nodes": N, "stencil_entries": nnz, "us_per_call": round(us, 2), "nodes_per_s": round(N / us * 1e6),
-                      "alg_GBps": round(alg / us / 1e3, 1), "frac_of_measured_hbm": round(alg / us / 1e3 / peak, 3),
-                      "grad_rel_l2_err": err}))
+    return {"n_side": n, "nodes": N, "stencil_entries": nnz, "cuda_graph": cuda_graph, "us_per_call": round(us, 2),
+            "nodes_per_s": round(N / us * 1e6), "alg_GBps": round(alg / us / 1e3, 1),
+            "frac_of_measured_hbm": round(alg / us / 1e3 / peak, 3), "grad_rel_l2_err": err}
+
+
+if __name__ == "__main__":
+    sides = [int(a) for a in sys.argv[1:]] or [80, 1000, 2000]
+    dev = torch.device("cuda")
+    peak = 6545.3
+    try:
+        peak = float(json.load(open(os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "MEASURED_PEAKS.json")))["hbm_gbs"])
+    except Exception:
+        pass
+    for n in sides:
+        for cg in (False, True):
+            print(json.dumps(measure(n, dev, peak, cg)))
