@@ -604,9 +604,10 @@ def run_ours(args):
 
 
 # DRAM bytes per edge of the two kernels of one fused edge-MLP backward call, from the committed ncu capture
-# profiles/r1f_ncu_tc_kernels_2Medges.csv (dram__bytes_read.sum + dram__bytes_write.sum, 2 M edges, N = E/2):
-#   A: 1.809841 + 0.495496 GB, B: 2.339586 + 2.027414 GB  ->  6.672337 GB / 2e6 edges
-NCU_TRAFFIC_BYTES_PER_EDGE = {"bf16": 6.672337e9 / 2.0e6, "fp32": None}
+# profiles/r2p_ncu_tc_kernels_EDGE_8Medges.csv (dram__bytes_read.sum + dram__bytes_write.sum, 8 M edges, N = E/2, f16; the
+# bf16 kernels move the same bytes):  A: 7.312526 + 2.032588 GB, B: 9.492903 + 8.173909 GB  ->  27.011926 GB / 8e6 edges
+NCU_TRAFFIC_BYTES_PER_EDGE = {"bf16": 27.011926e9 / 8.0e6, "fp32": None}
+NCU_TRAFFIC_SOURCE = "profiles/r2p_ncu_tc_kernels_EDGE_8Medges.csv, per edge x E"
 
 
 def dominant_kernel_roofline(model, plan, dev, args, p):
@@ -664,7 +665,7 @@ def dominant_kernel_roofline(model, plan, dev, args, p):
             else "fvgn_mlp_backward<EDGE> = mlp_tc_bwd_a_kernel<0> + mlp_tc_bwd_b_kernel<0> (tcgen05)", "bound": "hbm",
             "achieved": alg / (ms / 1e3) / 1e9, "unit": "GB/s", "ms_per_launch": ms, "alg_bytes_per_launch": alg,
             "traffic": None if tpe is None else tpe * E,
-            "traffic_source": None if tpe is None else "profiles/r1f_ncu_tc_kernels_2Medges.csv, per edge x E"}
+            "traffic_source": None if tpe is None else NCU_TRAFFIC_SOURCE}
 
 
 if __name__ == "__main__":

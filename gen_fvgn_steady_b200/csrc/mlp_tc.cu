@@ -159,23 +159,11 @@ __global__ void __launch_bounds__(NTHREADS, 1) mlp_tc_fwd_kernel(const fvgn_mlp_
       const uint32_t w1s = smem_u32(w_img), w2s = w1s + NKB1 * KB_BYTES, w3s = w2s + 2 * KB_BYTES;
       uint32_t it = 0;
       uint32_t pa[2] = {0, 0}, pl[2] = {0, 0};
-      // layer 1 of tile i into accumulator `acc`: consumes NKB1 ring chunks in production order
-      auto layer1 = [&](uint32_t acc, int p) {
-        for (int kb = 0; kb < NKB1; ++kb, ++it) {
-          const int s = it % NSTAGE;
-          mbar_wait(BAR(B_FULL + s), (it / NSTAGE) & 1);
-          tc_fence_after();
-          const uint64_t ad = make_desc_k128(smem_u32(ring + s * KB_BYTES));
-          const uint64_t bd = make_desc_k128(w1s + kb * KB_BYTES);
-          const int nk = (kb == NKB1 - 1) ? LASTK : 4;
-          for (int k = 0; k < nk; ++k) umma_ss(acc, ad + 2 * k, bd + 2 * k, IDESC, (kb | k) != 0);
-          umma_commit(BAR(B_EMPTY + s));
-        }
-        umma_commit(BAR(B_L1 + p));
-      };
+      // accumulators of tile i: T1 = first target (layer 1, layer 3), T2 = layer 2 target; they swap every tile
+      auto T1 = [&](int64_t i) { return tmem + 256 * (uint32_t)(i & 1) + 128 * (uint32_t)((i >> 1) & 1); };
+      auto T2 = [&](int64_t i) { return tmem + 256 * (uint32_t)(i & 1) + 128 * (uint32_t)(((i >> 1) & 1) ^ 1); };
       // layers 2/3: A = bf16 image in the lower 64 columns of `src`, D = `dst`
-      auto layer23 = [&](uint32_t dst, uint32_t src, uint32_t ws, int p) {
-        mbar_wait(BAR(B_A + p), pa[p]);
+      auto issue23 = [&](uint32_t dst, uint32_t src, uint32_t ws, int p) {
         pa[p] ^= 1;
         tc_fence_after();
         for (int k = 0; k < 8; ++k)
@@ -183,21 +171,61 @@ __global__ void __launch_bounds__(NTHREADS, 1) mlp_tc_fwd_kernel(const fvgn_mlp_
         umma_commit(BAR(B_L23 + p));
         pl[p] ^= 1;
       };
-      // accumulators of tile i: T1 = first target (layer 1, layer 3), T2 = layer 2 target; they swap every tile
-      auto T1 = [&](int64_t i) { return tmem + 256 * (uint32_t)(i & 1) + 128 * (uint32_t)((i >> 1) & 1); };
-      auto T2 = [&](int64_t i) { return tmem + 256 * (uint32_t)(i & 1) + 128 * (uint32_t)(((i >> 1) & 1) ^ 1); };
-      for (int64_t i = 0; i < 2 && i < ntl; ++i) layer1(T1(i), (int)(i & 1));
-      for (int64_t i0 = 0; i0 < ntl; i0 += 2) {
-        const int np = (i0 + 1 < ntl) ? 2 : 1;
-        for (int p = 0; p < np; ++p) layer23(T2(i0 + p), T1(i0 + p), w2s, p);
-        for (int p = 0; p < np; ++p) {
-          layer23(T1(i0 + p), T2(i0 + p), w3s, p);
-          if (i0 + p + 2 < ntl) {
-            // the next tile's layer 1 targets T2 of this tile, whose lower half is the A operand of the layer 3 just
-            // issued: wait until that MMA group has retired before overwriting it
-            mbar_wait(BAR(B_L23 + p), pl[p] ^ 1);
-            tc_fence_after();
-            layer1(T1(i0 + p + 2), p);
+      // EVENT-DRIVEN issue.  Per pipeline p (tiles p, p+2, ..) the program order is  L1 L2 L3 | L1 L2 L3 | ..; the layer-1
+      // chunks of ALL tiles are consumed from the ring in tile order.  Instead of blocking on one barrier at a time (the
+      // layer-2/3 MMAs of one pipeline then queue behind the ring waits of the other pipeline's layer 1: 23 % of an EDGE
+      // tile's timeline in the round-1 profile), the issuing thread polls: whichever of {next layer-2/3 step of P0, of P1,
+      // next ring chunk of the layer-1 stream} has its operands ready is issued.
+      int64_t l23_tile[2] = {0, 1};   // tile whose layer 2 / 3 is next on pipeline p
+      int l23_step[2] = {0, 0};       // 0: layer 2 next, 1: layer 3 next
+      int64_t l1_tile = 0;            // layer-1 stream: tile and K-block to issue next
+      int l1_kb = 0;
+      bool l1_open = false;           // accumulator of l1_tile known to be free (layer 3 of tile l1_tile - 2 retired)
+      while (l1_tile < ntl || l23_tile[0] < ntl || l23_tile[1] < ntl) {
+#pragma unroll
+        for (int p = 0; p < 2; ++p) {
+          const int64_t t = l23_tile[p];
+          // layer 2/3 of tile t needs its layer 1 issued (program order) and the epilogue's bf16 A operand in TMEM
+          if (t < ntl && (t < l1_tile) && mbar_test(BAR(B_A + p), pa[p])) {
+            if (l23_step[p] == 0) {
+              issue23(T2(t), T1(t), w2s, p);
+              l23_step[p] = 1;
+            } else {
+              issue23(T1(t), T2(t), w3s, p);
+              l23_step[p] = 0;
+              l23_tile[p] = t + 2;
+            }
+          }
+        }
+        if (l1_tile < ntl) {
+          const int p = (int)(l1_tile & 1);
+          if (!l1_open) {
+            // layer 1 of tile t targets T2 of tile t-2, whose lower half is the A operand of that tile's layer 3: it must
+            // have been issued (l23_tile[p] moved past t-2) and retired
+            if (l1_tile < 2) l1_open = true;
+            else if (l23_tile[p] >= l1_tile && l23_step[p] == 0 && mbar_test(BAR(B_L23 + p), pl[p] ^ 1)) {
+              tc_fence_after();
+              l1_open = true;
+            }
+          }
+          if (l1_open) {
+            const int s = it % NSTAGE;
+            if (mbar_test(BAR(B_FULL + s), (it / NSTAGE) & 1)) {
+              tc_fence_after();
+              const uint32_t acc = T1(l1_tile);
+              const uint64_t ad = make_desc_k128(smem_u32(ring + s * KB_BYTES));
+              const uint64_t bd = make_desc_k128(w1s + l1_kb * KB_BYTES);
+              const int nk = (l1_kb == NKB1 - 1) ? LASTK : 4;
+              for (int k = 0; k < nk; ++k) umma_ss(acc, ad + 2 * k, bd + 2 * k, IDESC, (l1_kb | k) != 0);
+              umma_commit(BAR(B_EMPTY + s));
+              ++it;
+              if (++l1_kb == NKB1) {
+                umma_commit(BAR(B_L1 + p));
+                l1_kb = 0;
+                ++l1_tile;
+                l1_open = false;
+              }
+            }
           }
         }
       }
