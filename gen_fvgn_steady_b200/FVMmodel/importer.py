@@ -149,7 +149,8 @@ class NNmodel(nn.Module):
         graph_node.norm_global = False
         raw = self.simulator(graph_node, graph_edge, graph_cell)
         if self.precision == "f16" and torch.is_grad_enabled():
-            raw = ops.GradScaleFn.apply(raw)   # backward: gradient operands of the half-precision MMAs are kept in range
+            # backward: gradient operands of the half-precision MMAs are kept in range (one S for all ranks of a partition)
+            raw = ops.GradScaleFn.apply(raw, getattr(plan, "halo", None) is not None)
         phi = ops.HeadFn.apply(raw, uv_old, plan.y, plan.node_type, ops.INTEGRATORS[params.integrator])
         out_scale = (graph_Index.uvp_dim * graph_Index.sigma).float()
         losses, uvp_node, uvp_cell, grad_phi = ops.FVLossFn.apply(

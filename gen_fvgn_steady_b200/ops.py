@@ -278,18 +278,24 @@ class GradScaleFn(torch.autograd.Function):
     _unscale() for the Transolver block): both factors are powers of two, i.e. exact.  No host synchronisation."""
 
     @staticmethod
-    def forward(ctx, raw):
+    def forward(ctx, raw, sync_ranks=False):
+        ctx.sync_ranks = bool(sync_ranks)
         return raw.view_as(raw)
 
     @staticmethod
     def backward(ctx, g):
         rec = grad_scale(g.device)
         amax = g.detach().abs().max()
+        if ctx.sync_ranks:
+            # cell-partition mode: ghost-row gradients travel between ranks (HaloExchangeFn.backward) while they still carry
+            # the factor S, so every rank must use the same S
+            import torch.distributed as dist
+            dist.all_reduce(amax, op=dist.ReduceOp.MAX)
         k = torch.floor(torch.log2(GRAD_SCALE_TARGET / amax.clamp(min=1e-30))).clamp(-60.0, 60.0)
         k = torch.where(torch.isfinite(amax) & (amax > 0), k, torch.zeros_like(k))
         rec[0] = torch.exp2(k)
         rec[1] = torch.exp2(-k)
-        return g * rec[0]
+        return g * rec[0], None
 
 
 def _unscale(precision, grads, device):

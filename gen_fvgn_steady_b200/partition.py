@@ -257,5 +257,8 @@ def mark_partition(graphs, halo):
     if hasattr(gi, "x"):
         gi.x = torch.cat([gi.x, gi.x], 0)
     halo.num_graphs = B
+    for g in graphs:                      # the batch objects now describe 2 B graphs (B real + B ghost collectors)
+        if getattr(g, "num_graphs", None) is not None:
+            g.num_graphs = 2 * B
     gn._fvgn_halo = halo
     return graphs
