@@ -236,12 +236,15 @@ class Job:
         self.loss_host = torch.empty((), dtype=torch.float32).pin_memory()
         self.gstep = None
         if graph:
-            if world > 1:
-                raise SystemExit("--graph is a single-GPU option")
             from gen_fvgn_steady_b200.graphed import GraphedTrainStep
             gn.x, gn.norm_uvp, gn.norm_global = self.x_dev0.clone(), True, True
+            post = None
+            if cells_mode:
+                post = lambda: parallel.sum_gradients(self.flat_grad)
+            elif world > 1:
+                post = lambda: parallel.allreduce_gradients(self.flat_grad, world)
             self.gstep = GraphedTrainStep(model, self.opt, graphs, self.script_loss, warmup=max(warmup, 3),
-                                          freeze_normalizer=True)
+                                          freeze_normalizer=True, post_backward=post)
 
     def script_loss(self, out):
         p = self.p
@@ -571,15 +574,17 @@ def run_ours(args):
             del graphs
             torch.cuda.empty_cache()
             recs = {}
-            for hl in (3 * gn_blocks_total + 2, 3):
+            for hl, use_graph in ((3 * gn_blocks_total + 2, False), (3 * gn_blocks_total + 2, True), (3, False)):
                 g2, h2, cg = partitioned_graphs(args.cells, hl)
                 owned = torch.tensor([h2.n_owned_cells, int(g2[3].pos.shape[0])], device=dev, dtype=torch.int64)
                 allv = [torch.zeros_like(owned) for _ in range(world)]
                 dist.all_gather(allv, owned)
-                r = quick_rate(dev, rank, world, g2, args.net, args.mp, args.precision, sub_steps, cg, cells_mode=True, halo=h2)
-                r.update(halo_layers=hl, ghost_refreshes_per_forward=sum(h2.wants_exchange(i, gn_blocks_total) for i in range(gn_blocks_total)),
+                r = quick_rate(dev, rank, world, g2, args.net, args.mp, args.precision, sub_steps, cg, cells_mode=True, halo=h2,
+                               graph=use_graph)
+                r.update(halo_layers=hl, cuda_graph=use_graph,
+                         ghost_refreshes_per_forward=sum(h2.wants_exchange(i, gn_blocks_total) for i in range(gn_blocks_total)),
                          owned_cells_per_rank=[int(v[0]) for v in allv], local_cells_per_rank=[int(v[1]) for v in allv])
-                recs[f"halo{hl}"] = r
+                recs[f"halo{hl}" + ("_cuda_graph" if use_graph else "")] = r
                 del g2, h2
                 torch.cuda.empty_cache()
             line["cells"] = {"mesh_cells": cg, "scaling": "strong", "partition": "recursive coordinate bisection", **recs}

@@ -25,10 +25,13 @@ import torch
 
 
 class GraphedTrainStep:
-    def __init__(self, model, optimizer, graphs, loss_fn, warmup=3, freeze_normalizer=False):
+    def __init__(self, model, optimizer, graphs, loss_fn, warmup=3, freeze_normalizer=False, post_backward=None):
         if not torch.cuda.is_available():
             raise RuntimeError("GraphedTrainStep needs a CUDA device: this package has no CPU path")
         self.model, self.optimizer, self.graphs, self.loss_fn = model, optimizer, graphs, loss_fn
+        # multi-GPU: called between backward and the optimizer step inside the captured body (gradient all-reduce; NCCL
+        # collectives are captured into the graph like kernels)
+        self.post_backward = post_backward
         gn = graphs[0]
         self.x_static = gn.x.detach().clone()          # raw [N,3] / [N,12] node features, read by the captured prologue
         for g in optimizer.param_groups:
@@ -100,6 +103,8 @@ class GraphedTrainStep:
         out = self.model(*self.graphs, is_training=True)
         loss = self.loss_fn(out)
         loss.backward()
+        if self.post_backward is not None:
+            self.post_backward()
         self.optimizer.step()
         return out, loss
 
