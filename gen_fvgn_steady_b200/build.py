@@ -14,7 +14,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 OBJ = os.path.join(CSRC, "_obj")
 LIB = os.path.join(HERE, "libfvgn_b200.so")
-SOURCES = ["segreduce.cu", "mlp_simt.cu", "mlp_tc.cu", "mlp_tc_bwd.cu", "mlp_api.cu", "misc.cu", "fv.cu", "transolver.cu",
+SOURCES = ["segreduce.cu", "mlp_simt.cu", "mlp_tc.cu", "mlp_tc_bwd.cu", "mlp_tc_bwd_node.cu", "mlp_api.cu", "misc.cu", "fv.cu", "transolver.cu",
            "plan_build.cu", "gemm_tf32.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-Xcompiler", "-fPIC", "-Xptxas", "-v"]

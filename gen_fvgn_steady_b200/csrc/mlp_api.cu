@@ -10,6 +10,7 @@ int64_t fvgn_mlp_param_count_impl(int32_t mode);
 int fvgn_mlp_forward_tc(const fvgn_mlp_desc* d, void* stream);
 int fvgn_mlp_backward_tc(const fvgn_mlp_desc* d, void* stream);
 int fvgn_mlp_tc_partials(int32_t mode, int64_t rows);
+int fvgn_mlp_tc_node_partials(int64_t n_nodes);
 int64_t fvgn_mlp_tc_packed_bytes(int32_t mode);
 int64_t fvgn_mlp_tc_workspace_bytes(int32_t mode, int64_t rows);
 int fvgn_mlp_tc_pack(int32_t mode, int32_t precision, const float* w1, const float* w2, const float* w3, void* packed, void* stream);
@@ -34,6 +35,15 @@ extern "C" int32_t fvgn_mlp_bwd_partials(int32_t mode, int32_t precision, int64_
   (void)mode;
   (void)precision;
   return fvgn_mlp_simt_partials(rows);
+}
+
+extern "C" int32_t fvgn_mlp_bwd_node_partials(int64_t n_nodes) {
+#ifndef FVGN_EMU
+  return fvgn_mlp_tc_node_partials(n_nodes);
+#else
+  (void)n_nodes;
+  return 0;
+#endif
 }
 
 extern "C" int64_t fvgn_mlp_bwd_workspace_bytes(int32_t mode, int32_t precision, int64_t rows) {
@@ -118,7 +128,14 @@ extern "C" int fvgn_mlp_backward(const fvgn_mlp_desc* d, void* stream) {
   int rc = check_common(d);
   if (rc) return rc;
   if (!d->d_out || !d->partials || !d->d_params || d->n_partials < 1) return FVGN_ERR_NULL;
-  if ((d->mode == FVGN_MLP_EDGE || d->mode == FVGN_MLP_NODE) && ((!d->d_in0 && !d->d_in0h) || !d->d_in1)) return FVGN_ERR_NULL;
+  const bool node_path = d->d_aggh != nullptr;   // EDGE, tensor-core modes: node-level layer-1 backward
+  if (node_path) {
+    if (d->mode != FVGN_MLP_EDGE || !is_tc(d->precision)) return FVGN_ERR_UNSUPPORTED;
+    if (!d->inc_ptr || !d->inc_code || !d->node_partials || !d->in0h) return FVGN_ERR_NULL;
+    if (d->n_nodes < 1 || d->n_node_partials != fvgn_mlp_bwd_node_partials(d->n_nodes)) return FVGN_ERR_SHAPE;
+    if (!fvgn_aligned16(d->d_aggh)) return FVGN_ERR_ALIGN;
+  }
+  if ((d->mode == FVGN_MLP_EDGE || d->mode == FVGN_MLP_NODE) && ((!d->d_in0 && !d->d_in0h && !node_path) || !d->d_in1)) return FVGN_ERR_NULL;
   if ((d->d_in0h || d->d_gatherh) && !is_tc(d->precision)) return FVGN_ERR_UNSUPPORTED;
   if (d->d_in0h && d->mode != FVGN_MLP_EDGE && d->mode != FVGN_MLP_NODE) return FVGN_ERR_UNSUPPORTED;
   if (!fvgn_aligned16(d->d_gatherh)) return FVGN_ERR_ALIGN;

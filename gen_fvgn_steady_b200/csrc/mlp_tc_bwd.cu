@@ -683,7 +683,11 @@ __global__ void __launch_bounds__(A_THREADS, 1) mlp_tc_bwd_a_kernel(const fvgn_m
 // =============================================================================================== kernel B
 constexpr int STG_BYTES = 4 * WSTG_BYTES;  // one wide staging tile per epilogue warp
 
-template <int MODE, class P>
+// KB0: first 64-column block of the layer-1 input this kernel handles.  0: everything.  4 (EDGE, node-level layer-1 path,
+// mlp_tc_bwd_node.cu): only the e columns 256..383 -- dW1[:, 256:384] += dZ1^T e, d_e = dZ1 W1[:, 256:384] (+ residual
+// gradient); the agg[s] | agg[r] columns are differentiated per node by mlp_tc_bwd_node_kernel, so no gathered operand
+// chunks, no [E,256] gradient stream.
+template <int MODE, class P, int KB0>
 __global__ void __launch_bounds__(NTHREADS, 1) mlp_tc_bwd_b_kernel(const fvgn_mlp_desc d) {
   using C = BCfg<MODE>;
   constexpr uint32_t IDESC_MM64 = make_idesc(P::FMT, 64, 1, 1), IDESC_KM64 = make_idesc(P::FMT, 64, 0, 1);
@@ -744,7 +748,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) mlp_tc_bwd_b_kernel(const fvgn_ml
         mbar_wait(BAR(B_DZFULL + zb), (tcount >> 1) & 1);
         tc_fence_after();
         // G1: dW1[:, 64 kb .. 64 kb + 64) += dZ1^T X_kb   (A = dZ1 MN-major, B = X chunk MN-major, K = rows)
-        for (int kb = 0; kb < NKB1; ++kb, ++it) {
+        for (int kb = KB0; kb < NKB1; ++kb, ++it) {
           const int s = it % NSTAGE;
           mbar_wait(BAR(B_XFULL + s), (it / NSTAGE) & 1);
           tc_fence_after();
@@ -756,7 +760,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) mlp_tc_bwd_b_kernel(const fvgn_ml
         }
         // D1: dX[:, 64 j .. 64 j + 64) = dZ1 W1[:, block j]   (A = dZ1 K-major, B = W1 image block j read MN-major)
         if (C::DX) {
-          for (int j = 0; j < NKB1; ++j, ++blk) {
+          for (int j = KB0; j < NKB1; ++j, ++blk) {
             const int ab = blk & 1;
             mbar_wait(BAR(B_AFREE + ab), ((blk >> 1) & 1) ^ 1);
             tc_fence_after();
@@ -788,8 +792,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) mlp_tc_bwd_b_kernel(const fvgn_ml
       }
     };
     if constexpr (mode_has_shadow(MODE)) {
-      produce_tiles_h<MODE, NKB1>(d, ntiles, pw, lane, [&](const ChunkRegs& c, uint32_t tcount, int kb) {
-        if (kb == 0) fetch_dz(tcount);
+      produce_tiles_h<MODE, NKB1, KB0>(d, ntiles, pw, lane, [&](const ChunkRegs& c, uint32_t tcount, int kb) {
+        if (kb == KB0) fetch_dz(tcount);
         const int s = it % NSTAGE;
         mbar_wait(BAR(B_XEMPTY + s), ((it / NSTAGE) & 1) ^ 1);
         store_chunk_h(ring + s * KB_BYTES, pw, lane, c);
@@ -804,7 +808,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) mlp_tc_bwd_b_kernel(const fvgn_ml
       for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++tcount) {
         const int64_t row0 = tile * TILE_M;
         fetch_dz(tcount);
-        for (int kb = 0; kb < NKB1; ++kb, ++it) {
+        for (int kb = KB0; kb < NKB1; ++kb, ++it) {
           const int s = it % NSTAGE;
           mbar_wait(BAR(B_XEMPTY + s), ((it / NSTAGE) & 1) ^ 1);
           produce_chunk<MODE, P>(d, row0, kb, ring + s * KB_BYTES, pw, lane, idx);
@@ -830,7 +834,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) mlp_tc_bwd_b_kernel(const fvgn_ml
 #pragma unroll
           for (int k = 0; k < 4; ++k) prefetch_l2(rp + 32 * k);
         }
-        for (int j = 0; j < NKB1; ++j, ++blk) {
+        for (int j = KB0; j < NKB1; ++j, ++blk) {
           const int ab = blk & 1;
           const uint32_t tacc = tmem + lane_base + WACC + 64 * ab;
           const int col0 = 64 * j;  // first input column of this 64-column block
@@ -944,8 +948,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) mlp_tc_bwd_b_kernel(const fvgn_ml
         tmem_ld16(tmem + lane_base + DW1 + c0, r);
         tmem_wait_ld();
 #pragma unroll
-        for (int j = 0; j < 16; ++j)
-          if (c0 + j < C::K1) Pw1[(size_t)o * C::K1 + c0 + j] = __uint_as_float(r[j]);
+        for (int j = 0; j < 16; ++j)   // columns below KB0 * 64 belong to the node-level kernel: zero here
+          if (c0 + j < C::K1) Pw1[(size_t)o * C::K1 + c0 + j] = (c0 < KB0 * 64) ? 0.f : __uint_as_float(r[j]);
       }
     }
     tc_fence_before();
@@ -975,27 +979,37 @@ template <int MODE> constexpr int smem_b() {
 
 int num_sms() { return fvgn_num_sms(); }
 
+}  // namespace
+template <class P> int launch_tc_bwd_node(const fvgn_mlp_desc& d, void* stream);   // mlp_tc_bwd_node.cu
+namespace {
+
 template <int MODE, class P>
 int launch_tc_bwd(const fvgn_mlp_desc& d, void* stream) {
   using C = BCfg<MODE>;
   auto ka = mlp_tc_bwd_a_kernel<MODE, P>;
-  auto kb = mlp_tc_bwd_b_kernel<MODE, P>;
+  auto kb = mlp_tc_bwd_b_kernel<MODE, P, 0>;
+  constexpr int KBN = (MODE == FVGN_MLP_EDGE) ? 4 : 0;
+  auto kbn = mlp_tc_bwd_b_kernel<MODE, P, KBN>;   // EDGE with the node-level layer-1 path: e columns only
+  const bool node_path = MODE == FVGN_MLP_EDGE && d.d_aggh != nullptr;
   static bool attr_set[FVGN_MAX_DEV] = {false};  // the attribute is per device
   const int dev = fvgn_cur_device();
   if (!attr_set[dev]) {
     if (cudaFuncSetAttribute(ka, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_a<MODE>()) != cudaSuccess) return FVGN_ERR_LAUNCH;
     if (cudaFuncSetAttribute(kb, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_b<MODE>()) != cudaSuccess) return FVGN_ERR_LAUNCH;
+    if (cudaFuncSetAttribute(kbn, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_b<MODE>()) != cudaSuccess) return FVGN_ERR_LAUNCH;
     attr_set[dev] = true;
   }
   const unsigned grid = (unsigned)d.n_partials;
   ka<<<grid, A_THREADS, smem_a<MODE>(), (cudaStream_t)stream>>>(d);
   FVGN_CHECK_LAUNCH();
-  kb<<<grid, NTHREADS, smem_b<MODE>(), (cudaStream_t)stream>>>(d);
+  if (node_path) kbn<<<grid, NTHREADS, smem_b<MODE>(), (cudaStream_t)stream>>>(d);
+  else kb<<<grid, NTHREADS, smem_b<MODE>(), (cudaStream_t)stream>>>(d);
   FVGN_CHECK_LAUNCH();
   const int64_t pc = pcount(C::K1, C::NOUT, C::LN);
   tc_partial_reduce_kernel<<<(unsigned)((pc + 255) / 256), 256, 0, (cudaStream_t)stream>>>(d.partials, d.n_partials, pc, d.grad_unscale,
                                                                                        d.d_params);
   FVGN_CHECK_LAUNCH();
+  if (node_path) return launch_tc_bwd_node<P>(d, stream);   // d(agg) and dW1[:, 0:256] at node level (overwrites those columns)
   return FVGN_OK;
 }
 

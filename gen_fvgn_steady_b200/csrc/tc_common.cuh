@@ -359,8 +359,29 @@ __host__ __device__ constexpr bool mode_has_shadow(int mode) {
 template <int MODE>
 __host__ __device__ constexpr int prefetch_depth() { return MODE == FVGN_MLP_DEC ? 2 : 3; }
 
-template <int MODE, int NKB1, class PutFn>
+// KB0 > 0: only chunks KB0 .. NKB1-1 of every tile are produced (kernel B of the node-level layer-1 path skips the gathered
+// agg[s] | agg[r] chunks); `put` still receives the true chunk number.
+template <int MODE, int NKB1, int KB0 = 0, class PutFn>
 __device__ __forceinline__ void produce_tiles_h(const fvgn_mlp_desc& d, int64_t ntiles, int pw, int lane, PutFn&& put) {
+  if constexpr (KB0 > 0) {
+    constexpr int NC = NKB1 - KB0;   // chunks per tile, all of them plain row-major rows (no endpoint indices)
+    ChunkRegs buf[NC];
+    TileIdx none;
+    none.s = none.r = 0;
+    int64_t tile = blockIdx.x;
+    if (tile >= ntiles) return;
+#pragma unroll
+    for (int c = 0; c < NC; ++c) load_chunk_h<MODE>(d, tile * TILE_M, KB0 + c, pw, lane, none, buf[c]);
+    for (uint32_t i = 0; tile < ntiles; tile += gridDim.x, ++i) {
+      const int64_t next = tile + gridDim.x;
+#pragma unroll
+      for (int c = 0; c < NC; ++c) {
+        put(buf[c], i, KB0 + c);
+        if (next < ntiles) load_chunk_h<MODE>(d, next * TILE_M, KB0 + c, pw, lane, none, buf[c]);
+      }
+    }
+    return;
+  }
   constexpr int PF = prefetch_depth<MODE>();
   static_assert(NKB1 % PF == 0, "chunks per tile must be a multiple of the prefetch depth");
   ChunkRegs buf[PF];

@@ -24,6 +24,14 @@ def is_tc(precision):
     return precision in HDTYPE
 
 
+# tensor-core modes, FVGN_NODE_LEVEL_LAYER1=1: differentiate the agg[senders] | agg[receivers] columns of the edge MLP's
+# first layer per node (fvgn_mlp_desc.d_aggh, csrc/mlp_tc_bwd_node.cu) instead of per edge.  Correct (tests/test_gpu_tc.py)
+# but OFF by default: measured on a B200 at 4 M cells it removes 1.6 ms per GnBlock from kernel B and the 0.85 ms incidence
+# reduction, yet its own gather runs with one CTA per SM and takes 2.7 ms (150.0 ms per step against 145-148 ms edge-level;
+# DESIGN.md section 4.2).
+NODE_LEVEL_LAYER1 = os.environ.get("FVGN_NODE_LEVEL_LAYER1", "0") == "1"
+
+
 def default_precision():
     return os.environ.get("FVGN_PRECISION", "fp32")
 
@@ -206,7 +214,8 @@ def _z1_for(ctx, mode, precision, rows, like):
 
 
 def mlp_backward(mode, precision, rows, params, in0, in1, idx_s, idx_r, d_out, d_gather=None, d_in0=None, d_in1=None,
-                 flags=0, packed=None, z1=None, in0h=None, in1h=None, d_in0h=None, d_gatherh=None, d_in0_row_ptr=None):
+                 flags=0, packed=None, z1=None, in0h=None, in1h=None, d_in0h=None, d_gatherh=None, d_in0_row_ptr=None,
+                 node_path=None):
     """Runs the fused backward; returns the list of parameter gradients (views of one flat buffer).
     packed: the bf16 weight image used by the matching forward (bf16 mode); repacked from `params` when None.
     z1: the Z1Image the matching bf16 forward filled; when None (stand-alone use) the forward is re-run to make it.
@@ -229,6 +238,12 @@ def mlp_backward(mode, precision, rows, params, in0, in1, idx_s, idx_r, d_out, d
         d.d_gatherh = hptr(d_gatherh)
     if d_in0_row_ptr is not None:   # NODE, tensor-core modes: d_a2 rows leave divided by their node degree
         d.d_in0_row_ptr = iptr(d_in0_row_ptr)
+    if node_path is not None:       # EDGE, tensor-core modes: node-level layer-1 backward -> (plan, d_aggh [N,128] 16-bit)
+        nplan, d_aggh = node_path
+        nnp = int(lib.fvgn_mlp_bwd_node_partials(nplan.N))
+        d._node_partials = _empty((nnp, 128 * 256), d_out)
+        d.inc_ptr, d.inc_code, d.n_nodes = iptr(nplan.inc_ptr), iptr(nplan.inc_code), nplan.N
+        d.d_aggh, d.node_partials, d.n_node_partials = hptr(d_aggh), fptr(d._node_partials), nnp
     d.partials, d.n_partials, d.d_params = fptr(partials), npart, fptr(flat)
     if precision == "f16":
         d.grad_unscale = grad_scale(d_out.device)[1:2].data_ptr()
@@ -413,12 +428,22 @@ class GnBlockFn(torch.autograd.Function):
                                 packed=ctx.pk[1], z1=ctx.z1[1], in0h=a2h, in1h=xh, d_in0h=d_a2h, d_in0_row_ptr=plan.inc_ptr)
             d_a1h = adj_reduce(d_a2h, plan, 64, out_dtype=BF16)
             del d_a2h
-            d_srh = torch.empty((plan.E, 256), dtype=BF16, device=dev)
-            g_eb = mlp_backward(_lib.FVGN_MLP_EDGE, precision, plan.E, eb, None, None, plan.edge_s, plan.edge_r, d_e_out, None,
-                                None, d_e, packed=ctx.pk[0], z1=ctx.z1[0], in0h=aggh, in1h=eh, d_in0h=d_srh, d_gatherh=d_a1h)
-            ctx.z1 = None
-            d_agg = inc_reduce(d_srh, plan, 128, out_dtype=BF16)
-            del d_srh
+            if NODE_LEVEL_LAYER1:
+                # agg[s] | agg[r] columns of the edge MLP's first layer differentiated per NODE (csrc/mlp_tc_bwd_node.cu):
+                # no [E,256] gradient stream, no incidence reduction of it
+                d_agg = torch.empty((plan.N, 128), dtype=BF16, device=dev)
+                g_eb = mlp_backward(_lib.FVGN_MLP_EDGE, precision, plan.E, eb, None, None, plan.edge_s, plan.edge_r, d_e_out,
+                                    None, None, d_e, packed=ctx.pk[0], z1=ctx.z1[0], in0h=aggh, in1h=eh, d_gatherh=d_a1h,
+                                    node_path=(plan, d_agg))
+                ctx.z1 = None
+            else:
+                d_srh = torch.empty((plan.E, 256), dtype=BF16, device=dev)
+                g_eb = mlp_backward(_lib.FVGN_MLP_EDGE, precision, plan.E, eb, None, None, plan.edge_s, plan.edge_r, d_e_out,
+                                    None, None, d_e, packed=ctx.pk[0], z1=ctx.z1[0], in0h=aggh, in1h=eh, d_in0h=d_srh,
+                                    d_gatherh=d_a1h)
+                ctx.z1 = None
+                d_agg = inc_reduce(d_srh, plan, 128, out_dtype=BF16)
+                del d_srh
         else:
             g_nb = mlp_backward(_lib.FVGN_MLP_NODE, precision, plan.N, nb, a2, x, None, None, d_x_out, None, d_a2, d_x)
             d_a1 = adj_reduce(d_a2, plan, 64, _lib.FVGN_ADJ_DIV_SRC_BY_DEG)

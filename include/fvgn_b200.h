@@ -140,10 +140,26 @@ typedef struct fvgn_mlp_desc {
    * transposed mean d_a1 = Adj (D^-1 d_a2) then is a plain adjacency sum (no per-source degree lookups in
    * fvgn_adj_reduce_t; FVGN_ADJ_DIV_SRC_BY_DEG must not be passed as well). */
   const int32_t* d_in0_row_ptr;
+  /* EDGE backward, tensor-core modes, optional "node-level layer 1" path (selected by d_aggh != NULL; d_in0 / d_in0h are
+   * then not written).  The first 256 input columns of the edge MLP are agg[senders] | agg[receivers]
+   * (blocks.py:101-107), so by linearity their part of the layer-1 backward can run per NODE instead of per EDGE:
+   *   U_s[i] = sum_{f: s_f = i} dZ1[f],  U_r[i] = sum_{f: r_f = i} dZ1[f]      (incidence CSR order, fp32 sums)
+   *   d(agg)[i] = U_s[i] W1[:, 0:128] + U_r[i] W1[:, 128:256]                  -> d_aggh [n_nodes,128] 16-bit
+   *   dW1[:, 0:128] = U_s^T agg,  dW1[:, 128:256] = U_r^T agg
+   * which removes the [E,256] gradient stream d(agg[s])|d(agg[r]), its incidence reduction and the gathered operand
+   * chunks of the edge-level weight gradient.  inc_ptr / inc_code: node incidence CSR (code = edge*2 + role);
+   * in0h = aggh is read per node; node_partials: [fvgn_mlp_bwd_node_partials(n_nodes), 128*256] fp32 scratch. */
+  const int32_t* inc_ptr; const int32_t* inc_code;
+  int64_t n_nodes;
+  void* d_aggh;
+  float* node_partials;
+  int32_t n_node_partials;
+  int32_t reserved1;
 } fvgn_mlp_desc;
 
 int64_t fvgn_mlp_param_count(int32_t mode);
 int32_t fvgn_mlp_bwd_partials(int32_t mode, int32_t precision, int64_t rows); /* number of per-CTA partial buffers to allocate */
+int32_t fvgn_mlp_bwd_node_partials(int64_t n_nodes); /* rows of fvgn_mlp_desc.node_partials (node-level layer-1 path) */
 int64_t fvgn_mlp_bwd_workspace_bytes(int32_t mode, int32_t precision, int64_t rows);
 int64_t fvgn_mlp_packed_bytes(int32_t mode);
 /* fp32 parameters -> 16-bit UMMA operand image in the format of `precision` (FVGN_PREC_BF16 / FVGN_PREC_F16); weights
