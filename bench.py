@@ -618,9 +618,9 @@ NCU_TRAFFIC_SOURCE = "profiles/r2p_ncu_tc_kernels_EDGE_8Medges.csv, per edge x E
 def dominant_kernel_roofline(model, plan, dev, args, p):
     """Times the dominant call of the step -- the fused edge-MLP backward of one GnBlock (tcgen05 kernels A + B and the
     deterministic partial reduction) -- alone, with CUDA events on its stream, on inputs of the step's own size.
-    Algorithmic bytes per edge (DESIGN.md section 5, fp32 volumes of the reference's tensors): e and d_e_out read, d_e
-    written (3 x 512 B), d(agg[s])|d(agg[r]) written (1024 B), agg / d_a1 gathers at unique-row volume
-    ((512 + 256) * N/E B)."""
+    Algorithmic bytes (SURVEY.md section 8(d) accounting: fp32 volumes of the reference's tensors, every tensor row counted
+    once): e and d_e_out read, d_e written (3 x 512 B per edge); agg read, d_a1 read, d(agg) written per NODE
+    (512 + 256 + 512 B) -- the per-edge d(agg[s]) | d(agg[r]) stream this implementation writes is traffic, not algorithm."""
     from gen_fvgn_steady_b200 import _lib, ops
     from gen_fvgn_steady_b200.FVMmodel.Models.FVGN.blocks import mlp_params
     blk = None
@@ -664,7 +664,7 @@ def dominant_kernel_roofline(model, plan, dev, args, p):
         if i > 1:
             times.append(ev0.elapsed_time(ev1))
     ms = float(np.mean(times))
-    alg = E * (3 * 512 + 1024) + N * (512 + 256)
+    alg = E * (3 * 512) + N * (512 + 256 + 512)
     tpe = NCU_TRAFFIC_BYTES_PER_EDGE.get("bf16" if bf else args.precision)
     return {"kernel": "mlp_bwd_kernel<EDGE> (fused edge-MLP backward: recompute + dgrad + wgrad)" if not bf
             else "fvgn_mlp_backward<EDGE> = mlp_tc_bwd_a_kernel<0> + mlp_tc_bwd_b_kernel<0> (tcgen05)", "bound": "hbm",
