@@ -95,7 +95,13 @@ def content_hash(tensors):
 class GraphPlan:
     """Device-resident topology plan of one batch.  Build with GraphPlan.build(...) or GraphPlan.of(...) (cached)."""
 
-    _by_content = {}   # content hash -> plan (most recent 8 topologies)
+    _by_content = {}   # content hash -> plan (most recent MAX_CONTENT_PLANS topologies; a plan of a 4 M-cell mesh holds ~2 GB)
+    MAX_CONTENT_PLANS = 4
+
+    @staticmethod
+    def clear_cache():
+        """Drop the content-keyed plans (plans attached to live batch objects stay with them)."""
+        GraphPlan._by_content.clear()
 
     @staticmethod
     def _plan_inputs(graph_node, graph_node_x, graph_edge, graph_cell):
@@ -135,7 +141,7 @@ class GraphPlan:
         plan.halo = halo  # cell-partition mode (partition.py)
         graph_node._fvgn_plan = plan
         if h is not None:
-            if len(GraphPlan._by_content) >= 8:
+            if len(GraphPlan._by_content) >= GraphPlan.MAX_CONTENT_PLANS:
                 GraphPlan._by_content.pop(next(iter(GraphPlan._by_content)))
             GraphPlan._by_content[h] = plan
         return plan
