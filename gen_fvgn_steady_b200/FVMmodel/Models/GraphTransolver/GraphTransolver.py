@@ -79,7 +79,7 @@ class Transolver_block(nn.Module):
         self.mlp = MLP(hidden_dim, hidden_dim * mlp_ratio, hidden_dim, n_layers=0, res=False, act=act)
         self.last_shadow = None
 
-    def forward(self, fx, batch, in_layernorm=False, graph_ptr=None, halo=None, embedding=None):
+    def forward(self, fx, batch, in_layernorm=False, graph_ptr=None, halo=None, embedding=None, num_graphs=None):
         """GraphTransolver.py:163-169.  `embedding` (optional) is added to fx first (the TransFVGN processors pass
         latent.x and the node embedding separately so that the sum and its gradient stay inside the fused op).
         In bf16 mode the last kernel also emits the bf16 shadow of the result (`self.last_shadow = (out, shadow)`) for
@@ -98,6 +98,6 @@ class Transolver_block(nn.Module):
             out, outh = ops.TransolverBlockFn.apply(
                 fx, embedding, A.in_project_fx.weight, A.in_project_fx.bias, A.in_project_x.weight, A.in_project_x.bias,
                 A.in_project_slice.weight, A.in_project_slice.bias, A.graph_temperature, A.to_q.weight, A.to_k.weight,
-                A.to_v.weight, A.to_out[0].weight, *tail, A.scale, ops.TsPlan.of(batch, halo), halo, want_shadow)
+                A.to_v.weight, A.to_out[0].weight, *tail, A.scale, ops.TsPlan.of(batch, halo, num_graphs), halo, want_shadow)
         self.last_shadow = (out, outh) if want_shadow is not None else None
         return out

@@ -22,7 +22,7 @@ class Simulator(nn.Module):
         for i, model in enumerate(self.GN_block_list):
             latent = model(latent)
             latent = halo_refresh(latent, i, nblk)  # cell-partition mode only (no-op otherwise)
-        latent.x = self.TransBlock(latent.x, graph_node.batch, halo=getattr(latent, "_fvgn_halo", None),
+        latent.x = self.TransBlock(latent.x, graph_node.batch, halo=getattr(latent, "_fvgn_halo", None), num_graphs=getattr(latent, "num_graphs", None),
                                    embedding=node_embedding)
         latent._xh = self.TransBlock.last_shadow   # bf16 mode: (x, shadow) written by the block's last kernel
         return self.decoder(latent)

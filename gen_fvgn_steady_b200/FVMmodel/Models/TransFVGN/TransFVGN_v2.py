@@ -22,7 +22,7 @@ class AttnProcessor(nn.Module):
         for i, model in enumerate(self.GN_block_list):
             latent = model(latent)
             latent = halo_refresh(latent, first_block + i, total)  # cell-partition mode only (no-op otherwise)
-        latent.x = self.TransBlock(latent.x, latent.batch, halo=getattr(latent, "_fvgn_halo", None),
+        latent.x = self.TransBlock(latent.x, latent.batch, halo=getattr(latent, "_fvgn_halo", None), num_graphs=getattr(latent, "num_graphs", None),
                                    embedding=node_embedding)
         latent._xh = self.TransBlock.last_shadow   # bf16 mode: (x, shadow) written by the block's last kernel
         return latent

@@ -149,3 +149,12 @@ extern "C" int fvgn_mlp_backward(const fvgn_mlp_desc* d, void* stream) {
 #endif
   return FVGN_ERR_UNSUPPORTED;
 }
+
+#ifdef FVGN_EMU
+// tests/emu build: the tcgen05 GEMMs do not exist on the host (the Transolver mirror uses them in tensor-core modes only)
+extern "C" int32_t fvgn_gemm_tf32_partials(int64_t) { return 0; }
+extern "C" int fvgn_gemm_tf32(int32_t, const float*, const float*, const float*, const float*, float*, int64_t, int32_t, int32_t,
+                              float*, int32_t, void*) {
+  return FVGN_ERR_UNSUPPORTED;
+}
+#endif

@@ -768,6 +768,55 @@ class FVLossFn(torch.autograd.Function):
         return d_phi, None, None, None, None, None, None, None
 
 
+# ------------------------------------------------------------------ dense projections (tcgen05 kind::tf32)
+# Tensor-core precision modes: the Linear layers of the Transolver block and their autograd run on fvgn_gemm_tf32
+# (csrc/gemm_tf32.cu) -- TF32 operands, fp32 accumulation, the arithmetic the reference's GPU scripts select for nn.Linear
+# (src/pre_train_Adam.py:29).  The fp32 parity mode keeps exact fp32 library GEMMs.  FVGN_TC_GEMM=0 forces the library.
+TC_GEMM = os.environ.get("FVGN_TC_GEMM", "1") != "0"
+
+
+def _gemm_ok(*dims):
+    return TC_GEMM and all(d in (128, 256) for d in dims)
+
+
+def linear_fwd(x, w, b=None, addend=None, tc=False):
+    """y = x w^T (+ b) (+ addend); x [M,I], w [O,I]."""
+    if tc and x.is_cuda and _gemm_ok(w.shape[0], w.shape[1]):
+        x, w = _c(x), _c(w.detach())
+        y = _empty((x.shape[0], w.shape[0]), x)
+        _lib.call("fvgn_gemm_tf32", _lib.FVGN_GEMM_NT, fptr(x), fptr(w), fptr(None if b is None else _c(b.detach()), True),
+                  fptr(None if addend is None else _c(addend), True), fptr(y), x.shape[0], w.shape[0], w.shape[1], None, 0,
+                  _lib.stream_ptr(x.device))
+        return y
+    y = x @ w.t() if b is None else torch.addmm(b, x, w.t())
+    return y if addend is None else y + addend
+
+
+def linear_dgrad(dy, w, addend=None, tc=False):
+    """dx = dy w (+ addend); dy [M,O], w [O,I]."""
+    if tc and dy.is_cuda and _gemm_ok(w.shape[0], w.shape[1]):
+        dy, w = _c(dy), _c(w.detach())
+        dx = _empty((dy.shape[0], w.shape[1]), dy)
+        _lib.call("fvgn_gemm_tf32", _lib.FVGN_GEMM_NN, fptr(dy), fptr(w), None, fptr(None if addend is None else _c(addend), True),
+                  fptr(dx), dy.shape[0], w.shape[1], w.shape[0], None, 0, _lib.stream_ptr(dy.device))
+        return dx
+    return dy @ w if addend is None else torch.addmm(addend, dy, w)
+
+
+def linear_wgrad(dy, x, tc=False):
+    """dW = dy^T x; dy [M,O], x [M,I] -> [O,I] (deterministic: static row split, fixed-order sum of the per-CTA partials)."""
+    if tc and dy.is_cuda and _gemm_ok(dy.shape[1], x.shape[1]) and dy.shape[1] // 128 * x.shape[1] <= 512:
+        dy, x = _c(dy), _c(x)
+        O, I, M = dy.shape[1], x.shape[1], dy.shape[0]
+        npart = int(_lib.load().fvgn_gemm_tf32_partials(M))
+        part = _empty((npart, O * I), dy)
+        dw = _empty((O, I), dy)
+        _lib.call("fvgn_gemm_tf32", _lib.FVGN_GEMM_TN, fptr(dy), fptr(x), None, None, fptr(dw), M, I, O, fptr(part), npart,
+                  _lib.stream_ptr(dy.device))
+        return dw
+    return dy.t() @ x
+
+
 # ------------------------------------------------------------------ Transolver_block (GraphTransolver.py:25-169)
 TS_HEADS, TS_DH, TS_G = 8, 16, 32
 TS_TOK = TS_HEADS * TS_G * TS_DH
@@ -778,42 +827,36 @@ class TsPlan:
     chunk; chunk_ptr groups the chunks per graph for the deterministic combine.  nb = number of graphs whose tokens are
     formed (cell-partition mode: graphs [nb, 2 nb) are the ghost rows, de-sliced with the tokens of graph id - nb)."""
 
-    def __init__(self, batch, halo=None):
+    def __init__(self, batch, halo=None, num_graphs=None):
+        from .plan import _chunks
         batch = batch.reshape(-1)
         n = int(batch.shape[0])
         dev = batch.device
-        nseg = int(batch.max().item()) + 1 if n > 0 else 1
+        if num_graphs is None:   # a loader that does not say how many graphs it batched: one device round trip
+            if n > 1 and bool((batch[1:] < batch[:-1]).any()):
+                raise RuntimeError("fvgn_b200: Transolver kernels need the batch vector sorted by graph (Load_mesh batches are)")
+            num_graphs = int(batch.max().item()) + 1 if n > 0 else 1
+        nseg = int(num_graphs)
         if halo is not None:
             nseg = max(nseg, int(halo.num_graphs))
-        counts = torch.bincount(batch.to(torch.int64), minlength=nseg).cpu().tolist()
-        if n > 1 and bool((batch[1:] < batch[:-1]).any()):
-            raise RuntimeError("fvgn_b200: Transolver kernels need the batch vector sorted by graph (Load_mesh batches are)")
         rows_per_chunk = max(32, min(4096, -(-n // (296 * 32)) * 32))
-        rows, ptr, start = [], [0], 0
-        for seg, cnt in enumerate(counts):
-            r = start
-            while r < start + cnt:
-                e = min(r + rows_per_chunk, start + cnt)
-                rows.append((seg, r, e))
-                r = e
-            start += cnt
-            ptr.append(len(rows))
-        self.n, self.nseg, self.n_chunks = n, nseg, len(rows)
+        # chunk table built on the device (plan._chunks): U is an upper bound of the chunk count, slots past the last real
+        # chunk are empty (0, 0, 0) -- their CTAs write zero partials, which every combine may read
+        self.chunks, self.chunk_ptr, self.n_chunks = _chunks(batch, nseg, rows_per_chunk)
+        self.n, self.nseg = n, nseg
         self.nb = nseg if halo is None else halo.num_graphs
-        self.chunks = torch.tensor(rows if rows else [(0, 0, 0)], dtype=torch.int32, device=dev).reshape(-1, 3).contiguous()
-        self.chunk_ptr = torch.tensor(ptr, dtype=torch.int32, device=dev)
-        self.all_ptr = torch.tensor([0, len(rows)], dtype=torch.int32, device=dev)
+        self.all_ptr = torch.tensor([0, self.n_chunks], dtype=torch.int32, device=dev)
 
     _cache = {}
 
     @classmethod
-    def of(cls, batch, halo=None):
+    def of(cls, batch, halo=None, num_graphs=None):
         key = (batch.data_ptr(), tuple(batch.shape), batch.device, None if halo is None else id(halo))
         hit = cls._cache.get(key)
         if hit is not None and hit[0]() is batch:
             return hit[1]
         import weakref
-        plan = cls(batch, halo)
+        plan = cls(batch, halo, num_graphs)
         if len(cls._cache) > 64:
             cls._cache = {k: v for k, v in cls._cache.items() if v[0]() is not None}
         cls._cache[key] = (weakref.ref(batch), plan)
@@ -853,12 +896,12 @@ def _token_attention(rec, wq, wk, wv, scale):
     return torch.matmul(attn, v).reshape(nb, TS_TOK)
 
 
-def _attn_forward(x, wfx, bfx, wx, bx, ws, bs, temp, wq, wk, wv, wo, scale, tsp, halo):
+def _attn_forward(x, wfx, bfx, wx, bx, ws, bs, temp, wq, wk, wv, wo, scale, tsp, halo, tc=False):
     """-> (a = to_out.weight @ deslice(attention(slice(x))), tensors to keep for _attn_backward)."""
     n = x.shape[0]
     st = _lib.stream_ptr(x.device)
     wcat = torch.cat([wfx, wx], 0)
-    P = torch.addmm(torch.cat([bfx, bx], 0), x, wcat.t())                  # [N,256] = fx_mid | x_mid
+    P = linear_fwd(x, wcat, torch.cat([bfx, bx], 0), tc=tc)               # [N,256] = fx_mid | x_mid
     ws_c, bs_c, temp_c = _c(ws.detach()), _c(bs.detach()), _c(temp.detach().reshape(-1))
     sw = _empty((n, 256), x)
     part = _empty((max(tsp.n_chunks, 1), _lib.FVGN_TS_TOKW), x)
@@ -871,18 +914,18 @@ def _attn_forward(x, wfx, bfx, wx, bx, ws, bs, temp, wq, wk, wv, wo, scale, tsp,
     tok_out = _c(_token_attention(rec, wq, wk, wv, scale))
     out_x = _empty((n, 128), x)
     _lib.call("fvgn_ts_deslice", fptr(sw), fptr(tok_out), TS_TOK, tsp.nb, iptr(tsp.chunks), tsp.n_chunks, fptr(out_x), st)
-    return out_x @ wo.t(), (x, P, sw, rec, tok_out, out_x, wcat, ws_c, bs_c, temp_c, wq, wk, wv, wo)
+    return linear_fwd(out_x, wo, tc=tc), (x, P, sw, rec, tok_out, out_x, wcat, ws_c, bs_c, temp_c, wq, wk, wv, wo)
 
 
-def _attn_backward(saved, d_a, scale, tsp, halo, d_res=None):
+def _attn_backward(saved, d_a, scale, tsp, halo, d_res=None, tc=False):
     """-> gradients of (x, wfx, bfx, wx, bx, ws, bs, temp, wq, wk, wv, wo); d_res (optional) is added to d_x inside the
     last GEMM (the block's residual gradient)."""
     x, P, sw, rec, tok_out, out_x, wcat, ws_c, bs_c, temp_c, wq, wk, wv, wo = saved
     n = x.shape[0]
     st = _lib.stream_ptr(x.device)
     d_a = _c(d_a)
-    d_wo = d_a.t() @ out_x
-    d_ox = d_a @ wo                                                         # [N,128]
+    d_wo = linear_wgrad(d_a, out_x, tc=tc)
+    d_ox = linear_dgrad(d_a, wo, tc=tc)                                     # [N,128]
     part = _empty((max(tsp.n_chunks, 1), _lib.FVGN_TS_TOKW), x)
     _lib.call("fvgn_ts_accumulate", fptr(sw), fptr(d_ox), iptr(tsp.chunks), tsp.n_chunks, fptr(part), st)
     acc = _combine(part, _lib.FVGN_TS_TOKW, tsp.chunk_ptr, tsp.nseg)[:, :TS_TOK]
@@ -909,12 +952,12 @@ def _attn_backward(saved, d_a, scale, tsp, halo, d_res=None):
         pg = torch.zeros(_lib.FVGN_TS_PARAMW, device=x.device)
     d_ws, d_bs = pg[:512].view(TS_G, TS_DH), pg[512:544]
     d_temp, d_bcat = pg[544:552].view(1, TS_HEADS, 1), pg[552:808]
-    d_x = dP @ wcat if d_res is None else torch.addmm(d_res, dP, wcat)
-    d_wcat = dP.t() @ x
+    d_x = linear_dgrad(dP, wcat, d_res, tc=tc)
+    d_wcat = linear_wgrad(dP, x, tc=tc)
     return (d_x, d_wcat[:128], d_bcat[:128], d_wcat[128:], d_bcat[128:], d_ws, d_bs, d_temp, d_wq, d_wk, d_wv, d_wo)
 
 
-def _tail_forward(a, bo, res, gamma, beta, w1, b1, w2, b2, want_shadow):
+def _tail_forward(a, bo, res, gamma, beta, w1, b1, w2, b2, want_shadow, tc=False):
     """y = a + bo + res ; z = ln_2(y) ; h = GELU(z W1^T + b1) ; out = h W2^T + b2 + y -> (out, shadow, kept tensors)."""
     n = a.shape[0]
     st = _lib.stream_ptr(a.device)
@@ -922,10 +965,10 @@ def _tail_forward(a, bo, res, gamma, beta, w1, b1, w2, b2, want_shadow):
     b1c, gc = _c(b1.detach()), _c(gamma.detach())
     _lib.call("fvgn_ts_residual_ln_forward", fptr(a), fptr(_c(bo.detach())), fptr(res), fptr(gc), fptr(_c(beta.detach())),
               fptr(y), fptr(z), fptr(stats), n, st)
-    hpre = z @ w1.t()
+    hpre = linear_fwd(z, w1, tc=tc)
     h = _empty((n, 256), a)
     _lib.call("fvgn_ts_bias_gelu_forward", fptr(hpre), fptr(b1c), fptr(h), n, st)
-    o = h @ w2.t()
+    o = linear_fwd(h, w2, tc=tc)
     out = _empty((n, 128), a)
     # want_shadow: None / False, or the 16-bit dtype of the shadow the next GnBlock / decoder reads
     sdt = BF16 if want_shadow is True else (want_shadow or None)
@@ -935,7 +978,7 @@ def _tail_forward(a, bo, res, gamma, beta, w1, b1, w2, b2, want_shadow):
     return out, outh, (y, stats, z, hpre, h, gc, w1, b1c, w2)
 
 
-def _tail_backward(saved, d_out):
+def _tail_backward(saved, d_out, tc=False):
     """-> (d_y = gradient of both a and res, d_bo, d_gamma, d_beta, d_w1, d_b1, d_w2, d_b2)."""
     y, stats, z, hpre, h, gc, w1, b1c, w2 = saved
     n = y.shape[0]
@@ -943,13 +986,13 @@ def _tail_backward(saved, d_out):
     d_out = _c(d_out)
     npart = _row_partials(n)
     ptr = _ptr01(npart, y.device)
-    d_w2 = d_out.t() @ h
-    d_h = d_out @ w2
+    d_w2 = linear_wgrad(d_out, h, tc=tc)
+    d_h = linear_dgrad(d_out, w2, tc=tc)
     part = _empty((npart, 256), y)
     _lib.call("fvgn_ts_bias_gelu_backward", fptr(d_h), fptr(hpre), fptr(b1c), fptr(d_h), fptr(part), n, st)  # in place
     d_b1 = _combine(part, 256, ptr, 1).reshape(-1) if n > 0 else torch.zeros(256, device=y.device)
-    d_w1 = d_h.t() @ z
-    d_z = d_h @ w1
+    d_w1 = linear_wgrad(d_h, z, tc=tc)
+    d_z = linear_dgrad(d_h, w1, tc=tc)
     d_y = _empty((n, 128), y)
     part = _empty((npart, 512), y)
     _lib.call("fvgn_ts_residual_ln_backward", fptr(d_z), fptr(y), fptr(stats), fptr(gc), fptr(d_out), fptr(d_y), fptr(part),
@@ -965,14 +1008,14 @@ class SliceAttentionFn(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, x, wfx, bfx, wx, bx, ws, bs, temp, wq, wk, wv, wo, scale, tsp, halo, precision=None):
-        a, saved = _attn_forward(_c(x), wfx, bfx, wx, bx, ws, bs, temp, wq, wk, wv, wo, scale, tsp, halo)
+        a, saved = _attn_forward(_c(x), wfx, bfx, wx, bx, ws, bs, temp, wq, wk, wv, wo, scale, tsp, halo, tc=is_tc(precision))
         ctx.tsp, ctx.halo, ctx.scale, ctx.precision = tsp, halo, scale, precision
         ctx.save_for_backward(*saved)
         return a
 
     @staticmethod
     def backward(ctx, d_a):
-        g = _attn_backward(ctx.saved_tensors, d_a, ctx.scale, ctx.tsp, ctx.halo)
+        g = _attn_backward(ctx.saved_tensors, d_a, ctx.scale, ctx.tsp, ctx.halo, tc=is_tc(ctx.precision))
         return (g[0], *_unscale(ctx.precision, g[1:], d_a.device), None, None, None, None)
 
 
@@ -987,8 +1030,10 @@ class TransolverBlockFn(torch.autograd.Function):
     def forward(ctx, xa, xb, wfx, bfx, wx, bx, ws, bs, temp, wq, wk, wv, wo, bo, gamma, beta, w1, b1, w2, b2, scale, tsp,
                 halo, want_shadow):
         x = _c(xa) if xb is None else xa + xb
-        a, s1 = _attn_forward(x, wfx, bfx, wx, bx, ws, bs, temp, wq, wk, wv, wo, scale, tsp, halo)
-        out, outh, s2 = _tail_forward(a, bo, x, gamma, beta, w1, b1, w2, b2, want_shadow)
+        tc = want_shadow is not None and want_shadow is not False
+        a, s1 = _attn_forward(x, wfx, bfx, wx, bx, ws, bs, temp, wq, wk, wv, wo, scale, tsp, halo, tc=tc)
+        out, outh, s2 = _tail_forward(a, bo, x, gamma, beta, w1, b1, w2, b2, want_shadow, tc=tc)
+        ctx.tc = tc
         ctx.tsp, ctx.halo, ctx.scale, ctx.n1, ctx.has_b = tsp, halo, scale, len(s1), xb is not None
         ctx.precision = "f16" if want_shadow == torch.float16 else None
         ctx.set_materialize_grads(False)
@@ -1000,8 +1045,8 @@ class TransolverBlockFn(torch.autograd.Function):
     @staticmethod
     def backward(ctx, d_out, _dh=None):
         s1, s2 = ctx.saved_tensors[:ctx.n1], ctx.saved_tensors[ctx.n1:]
-        d_y, d_bo, d_gamma, d_beta, d_w1, d_b1, d_w2, d_b2 = _tail_backward(s2, d_out)
-        g = _attn_backward(s1, d_y, ctx.scale, ctx.tsp, ctx.halo, d_res=d_y)   # d fx = dP Wcat + d_y in one GEMM
+        d_y, d_bo, d_gamma, d_beta, d_w1, d_b1, d_w2, d_b2 = _tail_backward(s2, d_out, tc=ctx.tc)
+        g = _attn_backward(s1, d_y, ctx.scale, ctx.tsp, ctx.halo, d_res=d_y, tc=ctx.tc)   # d fx = dP Wcat + d_y in one GEMM
         pg = _unscale(ctx.precision, (*g[1:], d_bo, d_gamma, d_beta, d_w1, d_b1, d_w2, d_b2), d_out.device)
         return (g[0], g[0] if ctx.has_b else None, *pg, None, None, None, None)
 
@@ -1012,7 +1057,9 @@ class BlockTailFn(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, a, bo, res, gamma, beta, w1, b1, w2, b2, want_shadow):
-        out, outh, saved = _tail_forward(_c(a), bo, _c(res), gamma, beta, w1, b1, w2, b2, want_shadow)
+        tc = want_shadow is not None and want_shadow is not False
+        out, outh, saved = _tail_forward(_c(a), bo, _c(res), gamma, beta, w1, b1, w2, b2, want_shadow, tc=tc)
+        ctx.tc = tc
         ctx.precision = "f16" if want_shadow == torch.float16 else None
         ctx.set_materialize_grads(False)
         if outh is not None:
@@ -1022,7 +1069,7 @@ class BlockTailFn(torch.autograd.Function):
 
     @staticmethod
     def backward(ctx, d_out, _dh=None):
-        d_y, d_bo, d_gamma, d_beta, d_w1, d_b1, d_w2, d_b2 = _tail_backward(ctx.saved_tensors, d_out)
+        d_y, d_bo, d_gamma, d_beta, d_w1, d_b1, d_w2, d_b2 = _tail_backward(ctx.saved_tensors, d_out, tc=ctx.tc)
         d_bo, d_gamma, d_beta, d_w1, d_b1, d_w2, d_b2 = _unscale(ctx.precision, (d_bo, d_gamma, d_beta, d_w1, d_b1, d_w2, d_b2),
                                                                  d_out.device)
         return d_y, d_bo, d_y, d_gamma, d_beta, d_w1, d_b1, d_w2, d_b2, None

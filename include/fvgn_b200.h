@@ -284,6 +284,22 @@ int fvgn_ts_bias_gelu_backward(const float* dh, const float* hpre, const float* 
 int fvgn_ts_bias_residual(const float* a, const float* bias, const float* res, float* out, void* outh, int32_t outh_type,
                           int64_t n, void* stream);
 
+/* ------------------------------------------------------------------ dense projections on tcgen05 kind::tf32
+ * The Linear layers of the Transolver block (GraphTransolver.py:48-58 in_project_fx / in_project_x, :92-95 to_out, :105-127
+ * mlp.linear_pre / linear_post) and their autograd in the arithmetic the reference's GPU scripts select
+ * (torch.backends.cuda.matmul.allow_tf32, src/pre_train_Adam.py:29): fp32 operands read by the tensor core as TF32, fp32
+ * accumulation.  All matrices fp32 row-major; n, k in {128, 256}.
+ *   FVGN_GEMM_NT: C[rows,n] = A[rows,k] B[n,k]^T (+ bias[n]) (+ addend[rows,n])        y  = x W^T + b
+ *   FVGN_GEMM_NN: C[rows,n] = A[rows,k] B[k,n]   (+ addend[rows,n])                     dx = dy W (+ residual gradient)
+ *   FVGN_GEMM_TN: C[k,n]    = A[rows,k]^T B[rows,n]                                     dW = dy^T x; deterministic: one
+ *                 partial [k,n] per CTA over a static row split (partials: [fvgn_gemm_tf32_partials(rows), k*n]), fixed-order sum */
+#define FVGN_GEMM_NT 0
+#define FVGN_GEMM_NN 1
+#define FVGN_GEMM_TN 2
+int32_t fvgn_gemm_tf32_partials(int64_t rows);
+int fvgn_gemm_tf32(int32_t mode, const float* A, const float* B, const float* bias, const float* addend, float* C, int64_t rows,
+                   int32_t n, int32_t k, float* partials, int32_t n_partials, void* stream);
+
 #ifdef __cplusplus
 }
 #endif
