@@ -1,8 +1,8 @@
 // Transolver_block kernels (reference: src/FVMmodel/Models/GraphTransolver/GraphTransolver.py:25-169).
 //
 // The block is  x -> [in_project_fx | in_project_x] -> slice softmax -> per-graph slice tokens -> token attention ->
-// de-slice -> to_out (+x) -> LayerNorm -> Linear-GELU-Linear (+residual).  The four dense projections are plain library
-// GEMMs on the host side; everything the reference does with broadcast products + torch_scatter (its [N,8,32,16]
+// de-slice -> to_out (+x) -> LayerNorm -> Linear-GELU-Linear (+residual).  The four dense projections are fvgn_gemm_tf32
+// calls (csrc/gemm_tf32.cu) in the tensor-core modes, fp32 library GEMMs in the parity mode; everything the reference does with broadcast products + torch_scatter (its [N,8,32,16]
 // temporary, GraphTransolver.py:62-88) and with separate elementwise launches is fused here:
 //
 //   ts_slice_kernel<true>   in_project_slice + /graph_temperature + softmax (:59-61) and the per-graph token sums

@@ -246,7 +246,8 @@ int fvgn_fv_outputs(const fvgn_fv_desc* d, const int32_t* batch_node, const floa
 
 /* ------------------------------------------------------------------ Transolver_block
  * src/FVMmodel/Models/GraphTransolver/GraphTransolver.py:25-169, heads = 8, dim_head = 16, slice_num = 32 (TransFVGN_v1/v2).
- * The dense projections (in_project_fx/x, to_out, mlp) are library GEMMs on the host side; these entry points replace the
+ * The dense projections (in_project_fx/x, to_out, mlp) are fvgn_gemm_tf32 calls (below) in the tensor-core modes and fp32
+ * library GEMMs in the parity mode; these entry points replace the
  * broadcast-product + torch_scatter slice / de-slice (:59-90) and the elementwise launches around the GEMMs.
  * chunks[nchunks,3] = (graph id, row begin, row end), rows of a chunk belong to one graph; one CTA per chunk. */
 #define FVGN_TS_TOKW 4352   /* per-graph token record: 8*32*16 numerators | 8*32 norms */
