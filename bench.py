@@ -562,7 +562,26 @@ def run_ours(args):
                 line["nets"] = {"TransFVGN_v2": r}
             del graphs
             torch.cuda.empty_cache()
-            for key, fn in (("example_meshes", lambda: example_mesh_records(dev, args.precision, 20)),
+            def size_sweep():
+                """north_star: 'synthetic meshes scaled to 1M-16M cells' -- the sizes one GPU holds (16 M cells needs the cell
+                partition: the N > 1 `cells` record); same net / precision / loss as the headline."""
+                out = {}
+                for c in (1_000_000, 2_000_000, 8_000_000):
+                    m_, u_ = make_mesh(c, 0, dev)
+                    g_ = graphs_from_meshes([m_], [u_], dev)
+                    del m_, u_
+                    c_real = int(g_[3].pos.shape[0])
+                    r_ = quick_rate(dev, 0, 1, g_, args.net, args.mp, args.precision, 5, c_real)
+                    r_["cells"] = c_real
+                    r_["peak_memory_gb"] = torch.cuda.max_memory_allocated(dev) / 1e9
+                    out[f"{c // 1_000_000}M"] = r_
+                    del g_
+                    torch.cuda.empty_cache()
+                    torch.cuda.reset_peak_memory_stats(dev)
+                return out
+
+            for key, fn in (("size_sweep", size_sweep),
+                            ("example_meshes", lambda: example_mesh_records(dev, args.precision, 20)),
                             ("loader_regime", lambda: loader_regime_record(dev, args.precision, 20)),
                             ("grad_rec_speed", lambda: grad_rec_record(dev))):
                 try:
@@ -608,20 +627,64 @@ def run_ours(args):
         dist.destroy_process_group()
 
 
-# DRAM bytes per edge of the two kernels of one fused edge-MLP backward call, from the committed ncu capture
-# profiles/r2p_ncu_tc_kernels_EDGE_8Medges.csv (dram__bytes_read.sum + dram__bytes_write.sum, 8 M edges, N = E/2, f16; the
-# bf16 kernels move the same bytes):  A: 7.312526 + 2.032588 GB, B: 9.492903 + 8.173909 GB  ->  27.011926 GB / 8e6 edges
-NCU_TRAFFIC_BYTES_PER_EDGE = {"bf16": 27.011926e9 / 8.0e6, "fp32": None}
-NCU_TRAFFIC_SOURCE = "profiles/r2p_ncu_tc_kernels_EDGE_8Medges.csv, per edge x E"
+# DRAM bytes per edge of the kernels of one fused edge-MLP backward call (dram__bytes_read.sum + dram__bytes_write.sum of ncu
+# --set full captures, 8 M edges, N = E/2, f16; the bf16 kernels move the same bytes) -> (bytes per edge, source):
+#   edge-level: A 7.312526 + 2.032588 GB, B 9.492903 + 8.173909 GB = 27.011926 GB / 8e6 edges
+NCU_TRAFFIC_BYTES_PER_EDGE = {
+    "tc_edge_level": (27.011926e9 / 8.0e6, "profiles/r2p_ncu_tc_kernels_EDGE_8Medges.csv, per edge x E"),
+    # node-level layer 1 (default): A 6.774442 + 2.031280, B<KB0=4> 8.196782 + 4.080255, dz_incidence 2.435244 + 2.033738,
+    # node GEMM 3.075269 + 1.008122 GB = 29.635132 GB / 8.004e6 edges (this call ends in d(agg) [N,128]; the edge-level call
+    # above is followed by a separate 5 GB incidence reduction)
+    "tc_node_level": (29.635132e9 / 8.004e6, "profiles/r2y_ncu_edge_bwd_node_level_8Medges.csv, per edge x E"),
+    "fp32": None,
+}
+
+
+def edge_backward_runner(plan, dev, prec, params):
+    """-> (run, label): one fused edge-MLP backward call of a GnBlock on random inputs of the plan's size (the product's own
+    call: node-level layer 1 unless FVGN_NODE_LEVEL_LAYER1=0).  Also used by tools/edge_bwd_profile.py under ncu."""
+    from gen_fvgn_steady_b200 import _lib, ops
+    N, E = plan.N, plan.E
+    bf = ops.is_tc(prec)
+    hdt = ops.HDTYPE.get(prec)
+    gen = torch.Generator(device=dev).manual_seed(1)
+    agg = torch.randn((N, 128), device=dev, generator=gen)
+    e = torch.randn((E, 128), device=dev, generator=gen)
+    d_out = torch.randn((E, 128), device=dev, generator=gen)
+    d_a1 = torch.randn((N, 64), device=dev, generator=gen)
+    d_e = torch.empty((E, 128), device=dev)
+    code = _lib.FVGN_MLP_EDGE
+    if not bf:
+        d_sr = torch.empty((E, 256), device=dev)
+        return (lambda: ops.mlp_backward(code, "fp32", E, params, agg, e, plan.edge_s, plan.edge_r, d_out, d_a1, d_sr, d_e),
+                "mlp_bwd_kernel<EDGE> (fused edge-MLP backward: recompute + dgrad + wgrad)")
+    aggh, eh = ops.shadow(agg, dtype=hdt), ops.shadow(e, dtype=hdt)
+    del agg, e
+    z1 = ops.new_z1(code, prec, E, d_out)
+    ops.mlp_forward(code, prec, E, params, None, None, plan.edge_s, plan.edge_r, want_out=False, want_res=False, z1=z1,
+                    in0h=aggh, in1h=eh, want_outh=True)
+    d_a1h = d_a1.to(hdt)
+    if ops.NODE_LEVEL_LAYER1:
+        d_agg = torch.empty((N, 128), device=dev, dtype=hdt)
+        return (lambda: ops.mlp_backward(code, prec, E, params, None, None, plan.edge_s, plan.edge_r, d_out, None, None, d_e,
+                                         z1=z1, in0h=aggh, in1h=eh, d_gatherh=d_a1h, node_path=(plan, d_agg)),
+                "fvgn_mlp_backward<EDGE>, node-level layer 1 = mlp_tc_bwd_a_kernel<0> + mlp_tc_bwd_b_kernel<0,KB0=4> + "
+                "dz_incidence_kernel + mlp_tc_bwd_node_kernel (tcgen05)")
+    d_srh = torch.empty((E, 256), device=dev, dtype=hdt)
+    return (lambda: ops.mlp_backward(code, prec, E, params, None, None, plan.edge_s, plan.edge_r, d_out, None, None, d_e,
+                                     z1=z1, in0h=aggh, in1h=eh, d_in0h=d_srh, d_gatherh=d_a1h),
+            "fvgn_mlp_backward<EDGE> = mlp_tc_bwd_a_kernel<0> + mlp_tc_bwd_b_kernel<0> (tcgen05)")
 
 
 def dominant_kernel_roofline(model, plan, dev, args, p):
-    """Times the dominant call of the step -- the fused edge-MLP backward of one GnBlock (tcgen05 kernels A + B and the
-    deterministic partial reduction) -- alone, with CUDA events on its stream, on inputs of the step's own size.
+    """Times the dominant call of the step -- the fused edge-MLP backward of one GnBlock (tcgen05 kernels and the
+    deterministic partial reductions) -- alone, with CUDA events on its stream, on inputs of the step's own size.
     Algorithmic bytes (SURVEY.md section 8(d) accounting: fp32 volumes of the reference's tensors, every tensor row counted
     once): e and d_e_out read, d_e written (3 x 512 B per edge); agg read, d_a1 read, d(agg) written per NODE
-    (512 + 256 + 512 B) -- the per-edge d(agg[s]) | d(agg[r]) stream this implementation writes is traffic, not algorithm."""
-    from gen_fvgn_steady_b200 import _lib, ops
+    (512 + 256 + 512 B).  With the node-level layer 1 (default) the call really ends in d(agg) [N,128]; the edge-level
+    variant (FVGN_NODE_LEVEL_LAYER1=0) ends in the per-edge stream d(agg[s]) | d(agg[r]), whose incidence reduction is then a
+    separate launch outside this timing."""
+    from gen_fvgn_steady_b200 import ops
     from gen_fvgn_steady_b200.FVMmodel.Models.FVGN.blocks import mlp_params
     blk = None
     for m in model.modules():
@@ -630,29 +693,8 @@ def dominant_kernel_roofline(model, plan, dev, args, p):
             break
     N, E = plan.N, plan.E
     bf = ops.is_tc(args.precision)
-    prec = args.precision
-    hdt = ops.HDTYPE.get(prec)
-    gen = torch.Generator(device=dev).manual_seed(1)
-    agg = torch.randn((N, 128), device=dev, generator=gen)
-    e = torch.randn((E, 128), device=dev, generator=gen)
-    d_out = torch.randn((E, 128), device=dev, generator=gen)
-    d_a1 = torch.randn((N, 64), device=dev, generator=gen)
-    d_e = torch.empty((E, 128), device=dev)
     params = [q.detach() for q in mlp_params(blk.eb_module.net)]
-    code = _lib.FVGN_MLP_EDGE
-    if bf:
-        aggh, eh = ops.shadow(agg, dtype=hdt), ops.shadow(e, dtype=hdt)
-        del agg, e
-        z1 = ops.new_z1(code, prec, E, d_out)
-        ops.mlp_forward(code, prec, E, params, None, None, plan.edge_s, plan.edge_r, want_out=False, want_res=False, z1=z1,
-                        in0h=aggh, in1h=eh, want_outh=True)
-        d_srh = torch.empty((E, 256), device=dev, dtype=hdt)
-        d_a1h = d_a1.to(hdt)
-        run = lambda: ops.mlp_backward(code, prec, E, params, None, None, plan.edge_s, plan.edge_r, d_out, None, None, d_e,
-                                       z1=z1, in0h=aggh, in1h=eh, d_in0h=d_srh, d_gatherh=d_a1h)
-    else:
-        d_sr = torch.empty((E, 256), device=dev)
-        run = lambda: ops.mlp_backward(code, "fp32", E, params, agg, e, plan.edge_s, plan.edge_r, d_out, d_a1, d_sr, d_e)
+    run, label = edge_backward_runner(plan, dev, args.precision, params)
     reps = 5
     times = []
     for i in range(reps + 2):
@@ -665,12 +707,12 @@ def dominant_kernel_roofline(model, plan, dev, args, p):
             times.append(ev0.elapsed_time(ev1))
     ms = float(np.mean(times))
     alg = E * (3 * 512) + N * (512 + 256 + 512)
-    tpe = NCU_TRAFFIC_BYTES_PER_EDGE.get("bf16" if bf else args.precision)
-    return {"kernel": "mlp_bwd_kernel<EDGE> (fused edge-MLP backward: recompute + dgrad + wgrad)" if not bf
-            else "fvgn_mlp_backward<EDGE> = mlp_tc_bwd_a_kernel<0> + mlp_tc_bwd_b_kernel<0> (tcgen05)", "bound": "hbm",
+    key = "fp32" if not bf else ("tc_node_level" if ops.NODE_LEVEL_LAYER1 else "tc_edge_level")
+    tpe = NCU_TRAFFIC_BYTES_PER_EDGE.get(key)
+    return {"kernel": label, "bound": "hbm",
             "achieved": alg / (ms / 1e3) / 1e9, "unit": "GB/s", "ms_per_launch": ms, "alg_bytes_per_launch": alg,
-            "traffic": None if tpe is None else tpe * E,
-            "traffic_source": None if tpe is None else NCU_TRAFFIC_SOURCE}
+            "traffic": None if tpe is None else tpe[0] * E,
+            "traffic_source": None if tpe is None else tpe[1]}
 
 
 if __name__ == "__main__":

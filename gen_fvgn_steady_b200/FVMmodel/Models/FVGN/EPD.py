@@ -76,11 +76,14 @@ class GnBlock(nn.Module):
         self.nb_module = NodeBlock(hidden_size, custom_func=build_mlp(nb_input_dim, hidden_size, int(hidden_size), drop_out=drop_out))
         self.eb_module = EdgeBlock(input_size=hidden_size, custom_func=build_mlp(eb_input_dim, hidden_size, int(hidden_size), drop_out=drop_out))
 
-    def forward(self, graph_node):
+    def forward(self, graph_node, keep_edge_latent=True):
+        """keep_edge_latent=False (passed by the models for their last GnBlock, whose edge latent e + e' nothing reads:
+        EPD.py:262-270 decodes graph.x only): tensor-core modes skip that residual stream and its gradient; the returned
+        graph then carries edge_attr = None."""
         plan = GraphPlan.of(graph_node)
         xh, eh = _shadow_of(graph_node, "_xh", graph_node.x), _shadow_of(graph_node, "_eh", graph_node.edge_attr)
         x, e, xh, eh = ops.apply(ops.GnBlockFn, graph_node.x, graph_node.edge_attr, xh, eh, plan, _precision(self),
-                                           *mlp_params(self.eb_module.net), *mlp_params(self.nb_module.net))
+                                 keep_edge_latent, *mlp_params(self.eb_module.net), *mlp_params(self.nb_module.net))
         return _carry(graph_node, x=x, edge_attr=e, _fvgn_plan=plan, _xh=(x, xh), _eh=(e, eh))
 
 
@@ -112,7 +115,8 @@ class EncoderProcesserDecoder(nn.Module):
         from ....parallel import halo_refresh
         latent, _ = self.encoder(graph_node)  # point-wise in nodes / edges: exact on the ghost rows too
         nblk = len(self.GN_block_list)
+        whole = getattr(graph_node, "_fvgn_halo", None) is None   # a partitioned sub-mesh refreshes the ghost rows of e too
         for i, model in enumerate(self.GN_block_list):
-            latent = model(latent)
+            latent = model(latent, keep_edge_latent=not (whole and i == nblk - 1))
             latent = halo_refresh(latent, i, nblk)  # cell-partition mode only: ghost rows <- owners (no-op otherwise)
         return self.decoder(latent)

@@ -19,8 +19,9 @@ class Simulator(nn.Module):
         from ....parallel import halo_refresh
         latent, node_embedding = self.encoder(graph_node)
         nblk = len(self.GN_block_list)
+        whole = getattr(graph_node, "_fvgn_halo", None) is None
         for i, model in enumerate(self.GN_block_list):
-            latent = model(latent)
+            latent = model(latent, keep_edge_latent=not (whole and i == nblk - 1))   # nothing reads the last edge latent
             latent = halo_refresh(latent, i, nblk)  # cell-partition mode only (no-op otherwise)
         latent.x = self.TransBlock(latent.x, graph_node.batch, halo=getattr(latent, "_fvgn_halo", None), num_graphs=getattr(latent, "num_graphs", None),
                                    embedding=node_embedding)

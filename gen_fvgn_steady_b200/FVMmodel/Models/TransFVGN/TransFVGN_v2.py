@@ -19,8 +19,9 @@ class AttnProcessor(nn.Module):
         node_embedding = latent_graph_node.x
         latent = latent_graph_node
         total = total_blocks if total_blocks is not None else len(self.GN_block_list)
+        whole = getattr(latent, "_fvgn_halo", None) is None
         for i, model in enumerate(self.GN_block_list):
-            latent = model(latent)
+            latent = model(latent, keep_edge_latent=not (whole and first_block + i == total - 1))   # nothing reads the last e
             latent = halo_refresh(latent, first_block + i, total)  # cell-partition mode only (no-op otherwise)
         latent.x = self.TransBlock(latent.x, latent.batch, halo=getattr(latent, "_fvgn_halo", None), num_graphs=getattr(latent, "num_graphs", None),
                                    embedding=node_embedding)

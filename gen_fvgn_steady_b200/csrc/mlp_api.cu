@@ -11,6 +11,7 @@ int fvgn_mlp_forward_tc(const fvgn_mlp_desc* d, void* stream);
 int fvgn_mlp_backward_tc(const fvgn_mlp_desc* d, void* stream);
 int fvgn_mlp_tc_partials(int32_t mode, int64_t rows);
 int fvgn_mlp_tc_node_partials(int64_t n_nodes);
+int64_t fvgn_mlp_tc_node_ws_bytes(int64_t n_nodes);
 int64_t fvgn_mlp_tc_packed_bytes(int32_t mode);
 int64_t fvgn_mlp_tc_workspace_bytes(int32_t mode, int64_t rows);
 int fvgn_mlp_tc_pack(int32_t mode, int32_t precision, const float* w1, const float* w2, const float* w3, void* packed, void* stream);
@@ -40,6 +41,15 @@ extern "C" int32_t fvgn_mlp_bwd_partials(int32_t mode, int32_t precision, int64_
 extern "C" int32_t fvgn_mlp_bwd_node_partials(int64_t n_nodes) {
 #ifndef FVGN_EMU
   return fvgn_mlp_tc_node_partials(n_nodes);
+#else
+  (void)n_nodes;
+  return 0;
+#endif
+}
+
+extern "C" int64_t fvgn_mlp_bwd_node_workspace_bytes(int64_t n_nodes) {
+#ifndef FVGN_EMU
+  return fvgn_mlp_tc_node_ws_bytes(n_nodes);
 #else
   (void)n_nodes;
   return 0;
@@ -127,13 +137,16 @@ extern "C" int fvgn_mlp_backward(const fvgn_mlp_desc* d, void* stream) {
   }
   int rc = check_common(d);
   if (rc) return rc;
-  if (!d->d_out || !d->partials || !d->d_params || d->n_partials < 1) return FVGN_ERR_NULL;
+  // d_out == NULL: EDGE, tensor-core modes only -- the block's outputs e' / e + e' have no consumer but the node block
+  // (last GnBlock of a processor): the upstream gradient is the gathered d_a1 alone
+  const bool dead_out = !d->d_out && d->mode == FVGN_MLP_EDGE && is_tc(d->precision) && (d->d_gather || d->d_gatherh);
+  if ((!d->d_out && !dead_out) || !d->partials || !d->d_params || d->n_partials < 1) return FVGN_ERR_NULL;
   const bool node_path = d->d_aggh != nullptr;   // EDGE, tensor-core modes: node-level layer-1 backward
   if (node_path) {
     if (d->mode != FVGN_MLP_EDGE || !is_tc(d->precision)) return FVGN_ERR_UNSUPPORTED;
     if (!d->inc_ptr || !d->inc_code || !d->node_partials || !d->in0h) return FVGN_ERR_NULL;
     if (d->n_nodes < 1 || d->n_node_partials != fvgn_mlp_bwd_node_partials(d->n_nodes)) return FVGN_ERR_SHAPE;
-    if (!fvgn_aligned16(d->d_aggh)) return FVGN_ERR_ALIGN;
+    if (!fvgn_aligned16(d->d_aggh) || ((uintptr_t)d->node_ws & 1023)) return FVGN_ERR_ALIGN;
   }
   if ((d->mode == FVGN_MLP_EDGE || d->mode == FVGN_MLP_NODE) && ((!d->d_in0 && !d->d_in0h && !node_path) || !d->d_in1)) return FVGN_ERR_NULL;
   if ((d->d_in0h || d->d_gatherh) && !is_tc(d->precision)) return FVGN_ERR_UNSUPPORTED;

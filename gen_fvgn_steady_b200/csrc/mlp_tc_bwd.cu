@@ -270,7 +270,7 @@ __global__ void __launch_bounds__(A_THREADS, 1) mlp_tc_bwd_a_kernel(const fvgn_m
             const int64_t row = row0 + (i0 + j) * 16 + pw * 4 + (lane >> 3);
             lo[j] = make_float4(0.f, 0.f, 0.f, 0.f);
             hi[j] = lo[j];
-            if (row < d.rows) {
+            if (row < d.rows && d.d_out) {   // d_out == NULL (EDGE): no upstream gradient but the gathered d_a1
               const float* p = d.d_out + (size_t)row * 128 + kb * 64 + seg * 8;
               lo[j] = __ldg(reinterpret_cast<const float4*>(p));
               hi[j] = __ldg(reinterpret_cast<const float4*>(p + 4));
@@ -711,7 +711,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) mlp_tc_bwd_b_kernel(const fvgn_ml
   float* Pw1 = d.partials + (size_t)blockIdx.x * PC;
   const uint8_t* dz_img = reinterpret_cast<const uint8_t*>(d.workspace);
   const uint8_t* w_img = reinterpret_cast<const uint8_t*>(d.w_bf16);
-  const bool resid = !(d.flags & FVGN_MLP_NO_RESIDUAL);
+  const bool resid = !(d.flags & FVGN_MLP_NO_RESIDUAL) && d.d_out != nullptr;
 
   if (tid == 0) {
     mbar_init(BAR(B_W), 1);

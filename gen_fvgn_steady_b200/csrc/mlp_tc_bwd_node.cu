@@ -51,7 +51,108 @@ __device__ __forceinline__ void cp_async16(void* smem, const void* gmem, int src
 
 constexpr int smem_node() { return 4 * KB_BYTES + 3 * BUF_BYTES + 4 * WSTG_BYTES + 3 * 132 * 4 + 2 * NECAP * 4 + 256; }
 
+// Two-kernel variant (fvgn_mlp_desc.node_ws != NULL): the incidence sums are formed by a separate, many-CTA kernel that is
+// bound by memory rather than by one CTA's gather latency, and written as ready-made operand tile images:
+// node tile t -> [U_s kb0 | U_s kb1 | U_r kb0 | U_r kb1], 4 x 16 KB at node_ws + t * 64 KB.
 template <class P>
+__global__ void __launch_bounds__(256, 5) dz_incidence_kernel(const uint8_t* __restrict__ dz_img, const int32_t* __restrict__ ptr,
+                                                               const int32_t* __restrict__ ent, uint8_t* __restrict__ u_img, int64_t n) {
+  constexpr int RB = TILE_M, ECAP = 1536, NB = 4, G = 16;
+  __shared__ int s_ptr[3][RB + 1];
+  __shared__ int s_ent[2][ECAP];
+  const int tid = threadIdx.x, l16 = tid & 15, g = tid >> 4;
+  const int kb = l16 >> 3, ch = l16 & 7;
+  const int64_t nblk = (n + RB - 1) / RB;
+  auto fetch_ptr = [&](int64_t blk, int buf) {
+    if (blk < nblk && tid <= RB) {
+      const int64_t row = blk * RB + tid;
+      cp_async4(&s_ptr[buf][tid], ptr + (row < n ? row : n));
+    }
+  };
+  auto fetch_ent = [&](int64_t blk, int pbuf, int ebuf) {
+    if (blk < nblk) {
+      const int e0 = s_ptr[pbuf][0];
+      const int ne = min(s_ptr[pbuf][RB] - e0, ECAP);
+      for (int i = tid; i < ne; i += 256) cp_async4(&s_ent[ebuf][i], ent + e0 + i);
+    }
+  };
+  int64_t blk = blockIdx.x;
+  fetch_ptr(blk, 0);
+  fetch_ptr(blk + gridDim.x, 1);
+  cp_async_commit_wait_all();
+  __syncthreads();
+  fetch_ent(blk, 0, 0);
+  cp_async_commit_wait_all();
+  __syncthreads();
+  for (uint32_t it = 0; blk < nblk; blk += gridDim.x, ++it) {
+    const int pb = it % 3, eb = it & 1;
+    fetch_ptr(blk + 2 * (int64_t)gridDim.x, (it + 2) % 3);
+    fetch_ent(blk + gridDim.x, (it + 1) % 3, eb ^ 1);
+    const int* sp = s_ptr[pb];
+    const int* se = s_ent[eb];
+    const int e0 = sp[0];
+    const int nr = (int)min((int64_t)RB, n - blk * RB);
+    auto entry = [&](int t) { return (t - e0 < ECAP) ? se[t - e0] : __ldg(ent + t); };
+    auto dz_row = [&](int f) {   // this lane's 16 bytes of row f of the dZ1 tile images (8 columns)
+      return reinterpret_cast<const uint4*>(dz_img + (size_t)(f >> 7) * BUF_BYTES + kb * KB_BYTES + sw128_off(f & 127, ch));
+    };
+    uint8_t* ut = u_img + (size_t)blk * (2 * BUF_BYTES);
+#pragma unroll 1
+    for (int rr = g; rr < RB; rr += G) {   // rows past the last node are written as zeros (they are MMA operands)
+      int b = 0, deg = 0, c[NB];
+      uint4 v[NB];
+      if (rr < nr) { b = sp[rr]; deg = sp[rr + 1] - b; }
+#pragma unroll
+      for (int k = 0; k < NB; ++k) {
+        c[k] = 0;
+        if (k < deg) {
+          c[k] = entry(b + k);
+          v[k] = __ldg(dz_row(c[k] >> 1));
+        }
+      }
+      float as[8], ar[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) { as[j] = 0.f; ar[j] = 0.f; }
+      auto add = [&](const uint4& w, int code) {
+        const float x[8] = {P::lo(w.x), P::hi(w.x), P::lo(w.y), P::hi(w.y), P::lo(w.z), P::hi(w.z), P::lo(w.w), P::hi(w.w)};
+        if (code & 1) {
+#pragma unroll
+          for (int j = 0; j < 8; ++j) ar[j] += x[j];
+        } else {
+#pragma unroll
+          for (int j = 0; j < 8; ++j) as[j] += x[j];
+        }
+      };
+#pragma unroll
+      for (int k = 0; k < NB; ++k)
+        if (k < deg) add(v[k], c[k]);
+      for (int t0 = NB; t0 < deg; t0 += NB) {
+        uint4 w[NB];
+        int cc[NB];
+#pragma unroll
+        for (int k = 0; k < NB; ++k) {
+          cc[k] = 0;
+          if (t0 + k < deg) {
+            cc[k] = entry(b + t0 + k);
+            w[k] = __ldg(dz_row(cc[k] >> 1));
+          }
+        }
+#pragma unroll
+        for (int k = 0; k < NB; ++k)
+          if (t0 + k < deg) add(w[k], cc[k]);
+      }
+      const uint32_t off = kb * KB_BYTES + sw128_off(rr, ch);
+      *reinterpret_cast<uint4*>(ut + off) =
+          make_uint4(pack16<P>(as[0], as[1]), pack16<P>(as[2], as[3]), pack16<P>(as[4], as[5]), pack16<P>(as[6], as[7]));
+      *reinterpret_cast<uint4*>(ut + BUF_BYTES + off) =
+          make_uint4(pack16<P>(ar[0], ar[1]), pack16<P>(ar[2], ar[3]), pack16<P>(ar[4], ar[5]), pack16<P>(ar[6], ar[7]));
+    }
+    cp_async_commit_wait_all();
+    __syncthreads();
+  }
+}
+
+template <class P, bool IMG>
 __global__ void __launch_bounds__(N_THREADS, 1) mlp_tc_bwd_node_kernel(const fvgn_mlp_desc d) {
   constexpr uint32_t IDESC_KM = make_idesc(P::FMT, 128, 0, 1), IDESC_MM = make_idesc(P::FMT, 128, 1, 1);
   constexpr uint32_t DWA = 0, DWB = 128, ACC = 256;
@@ -66,7 +167,7 @@ __global__ void __launch_bounds__(N_THREADS, 1) mlp_tc_bwd_node_kernel(const fvg
   uint64_t* bars = reinterpret_cast<uint64_t*>(s_ent + 2 * NECAP);
   const uint32_t bar0 = smem_u32(bars);
   auto BAR = [&](int i) { return bar0 + 8u * (uint32_t)i; };
-  constexpr int B_W = 0, B_UFULL = 1, B_UFREE = 2, B_ACCFULL = 3, B_ACCFREE = 5;
+  constexpr int B_W = 0, B_UFULL = 1, B_UFREE = 2, B_ACCFULL = 3, B_ACCFREE = 5, B_UTX = 7;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 8);
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -79,6 +180,7 @@ __global__ void __launch_bounds__(N_THREADS, 1) mlp_tc_bwd_node_kernel(const fvg
     mbar_init(BAR(B_W), 1);
     mbar_init(BAR(B_UFULL), 1);
     mbar_init(BAR(B_UFREE), 1);
+    mbar_init(BAR(B_UTX), 1);
     for (int s = 0; s < 2; ++s) {
       mbar_init(BAR(B_ACCFULL + s), 1);
       mbar_init(BAR(B_ACCFREE + s), 128);
@@ -103,6 +205,7 @@ __global__ void __launch_bounds__(N_THREADS, 1) mlp_tc_bwd_node_kernel(const fvg
       for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
         const int ab = it & 1;
         mbar_wait(BAR(B_UFULL), it & 1);
+        if (IMG) mbar_wait(BAR(B_UTX), it & 1);
         mbar_wait(BAR(B_ACCFREE + ab), ((it >> 1) & 1) ^ 1);
         tc_fence_after();
         const uint32_t acc = tmem + ACC + 128 * ab;
@@ -145,17 +248,21 @@ __global__ void __launch_bounds__(N_THREADS, 1) mlp_tc_bwd_node_kernel(const fvg
       }
     };
     int64_t tile = blockIdx.x;
-    fetch_ptr(tile, 0);
-    fetch_ptr(tile + gridDim.x, 1);
-    cp_async_commit_wait_all();
-    gather_bar();
-    fetch_ent(tile, 0, 0);
-    cp_async_commit_wait_all();
-    gather_bar();
+    if (!IMG) {
+      fetch_ptr(tile, 0);
+      fetch_ptr(tile + gridDim.x, 1);
+      cp_async_commit_wait_all();
+      gather_bar();
+      fetch_ent(tile, 0, 0);
+      cp_async_commit_wait_all();
+      gather_bar();
+    }
     for (uint32_t it = 0; tile < ntiles; tile += gridDim.x, ++it) {
       const int pb = it % 3, eb = it & 1;
-      fetch_ptr(tile + 2 * (int64_t)gridDim.x, (it + 2) % 3);
-      fetch_ent(tile + gridDim.x, (it + 1) % 3, eb ^ 1);
+      if (!IMG) {
+        fetch_ptr(tile + 2 * (int64_t)gridDim.x, (it + 2) % 3);
+        fetch_ent(tile + gridDim.x, (it + 1) % 3, eb ^ 1);
+      }
       const int* sp = s_ptr + pb * 132;
       const int* se = s_ent + eb * NECAP;
       const int e0 = sp[0];
@@ -166,6 +273,12 @@ __global__ void __launch_bounds__(N_THREADS, 1) mlp_tc_bwd_node_kernel(const fvg
         return reinterpret_cast<const uint4*>(dz_img + (size_t)(f >> 7) * BUF_BYTES + kb * KB_BYTES + sw128_off(f & 127, ch));
       };
       mbar_wait(BAR(B_UFREE), (it & 1) ^ 1);   // the MMAs of the previous tile have finished reading the three tiles
+      if (IMG && tg == 0) {   // the two U tiles are ready-made images: two 32-KB bulk copies
+        const uint8_t* ut = reinterpret_cast<const uint8_t*>(d.node_ws) + (size_t)tile * (2 * BUF_BYTES);
+        mbar_expect_tx(BAR(B_UTX), 2 * BUF_BYTES);
+        bulk_g2s(smem_u32(us), ut, BUF_BYTES, BAR(B_UTX));
+        bulk_g2s(smem_u32(ur), ut + BUF_BYTES, BUF_BYTES, BAR(B_UTX));
+      }
       // aggh rows of the tile -> swizzled tile: asynchronous 16-byte copies (no registers), zero-filled past the last node
       for (int idx = tg; idx < TILE_M * 16; idx += N_GATHER) {
         const int row = idx >> 4, c16 = idx & 15;
@@ -175,7 +288,7 @@ __global__ void __launch_bounds__(N_THREADS, 1) mlp_tc_bwd_node_kernel(const fvg
       }
       // incidence sums, R nodes per group in flight
 #pragma unroll 1
-      for (int base = grp; base < TILE_M; base += N_GROUPS * R) {
+      for (int base = grp; !IMG && base < TILE_M; base += N_GROUPS * R) {
         int b_[R], deg[R], c[R][NB];
         uint4 v[R][NB];
 #pragma unroll
@@ -325,16 +438,33 @@ int fvgn_mlp_tc_node_partials(int64_t n_nodes) {
   return (int)(ntiles < 1 ? 1 : (ntiles < sms ? ntiles : sms));
 }
 
+int64_t fvgn_mlp_tc_node_ws_bytes(int64_t n_nodes) { return ((n_nodes + TILE_M - 1) / TILE_M) * (int64_t)(2 * BUF_BYTES); }
+
 template <class P>
 int launch_tc_bwd_node(const fvgn_mlp_desc& d, void* stream) {
-  auto kn = mlp_tc_bwd_node_kernel<P>;
+  auto kn = mlp_tc_bwd_node_kernel<P, false>;
+  auto ki = mlp_tc_bwd_node_kernel<P, true>;
+  auto kz = dz_incidence_kernel<P>;
   static bool attr_set[FVGN_MAX_DEV] = {false};
+  static unsigned inc_grid[FVGN_MAX_DEV] = {0};
   const int dev = fvgn_cur_device();
   if (!attr_set[dev]) {
     if (cudaFuncSetAttribute(kn, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_node()) != cudaSuccess) return FVGN_ERR_LAUNCH;
+    if (cudaFuncSetAttribute(ki, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_node()) != cudaSuccess) return FVGN_ERR_LAUNCH;
+    int per_sm = 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kz, 256, 0) != cudaSuccess || per_sm < 1) return FVGN_ERR_LAUNCH;
+    inc_grid[dev] = (unsigned)(per_sm * fvgn_num_sms());
     attr_set[dev] = true;
   }
-  kn<<<(unsigned)d.n_node_partials, N_THREADS, smem_node(), (cudaStream_t)stream>>>(d);
+  if (d.node_ws) {
+    const int64_t ntiles = (d.n_nodes + TILE_M - 1) / TILE_M;
+    kz<<<(unsigned)(ntiles < inc_grid[dev] ? ntiles : inc_grid[dev]), 256, 0, (cudaStream_t)stream>>>(
+        reinterpret_cast<const uint8_t*>(d.workspace), d.inc_ptr, d.inc_code, reinterpret_cast<uint8_t*>(d.node_ws), d.n_nodes);
+    FVGN_CHECK_LAUNCH();
+    ki<<<(unsigned)d.n_node_partials, N_THREADS, smem_node(), (cudaStream_t)stream>>>(d);
+  } else {
+    kn<<<(unsigned)d.n_node_partials, N_THREADS, smem_node(), (cudaStream_t)stream>>>(d);
+  }
   FVGN_CHECK_LAUNCH();
   node_partial_reduce_kernel<<<128, 256, 0, (cudaStream_t)stream>>>(d.node_partials, d.n_node_partials, d.grad_unscale, d.d_params);
   FVGN_CHECK_LAUNCH();

@@ -24,12 +24,12 @@ def is_tc(precision):
     return precision in HDTYPE
 
 
-# tensor-core modes, FVGN_NODE_LEVEL_LAYER1=1: differentiate the agg[senders] | agg[receivers] columns of the edge MLP's
-# first layer per node (fvgn_mlp_desc.d_aggh, csrc/mlp_tc_bwd_node.cu) instead of per edge.  Correct (tests/test_gpu_tc.py)
-# but OFF by default: measured on a B200 at 4 M cells it removes 1.6 ms per GnBlock from kernel B and the 0.85 ms incidence
-# reduction, yet its own gather runs with one CTA per SM and takes 2.7 ms (150.0 ms per step against 145-148 ms edge-level;
-# DESIGN.md section 4.2).
-NODE_LEVEL_LAYER1 = os.environ.get("FVGN_NODE_LEVEL_LAYER1", "0") == "1"
+# tensor-core modes: the agg[senders] | agg[receivers] columns of the edge MLP's first layer are differentiated per NODE
+# (fvgn_mlp_desc.d_aggh, csrc/mlp_tc_bwd_node.cu) instead of per edge: no [E,256] gradient stream and no incidence
+# reduction of it.  FVGN_NODE_LEVEL_LAYER1 = 2 (default): incidence sums of dZ1 by a many-CTA kernel into operand tile images
+# + a node GEMM kernel fed by bulk copies; 1: one fused kernel (its gather runs one CTA per SM: slower); 0: edge-level path.
+# Measured at 4 M cells on a B200: 145.8 ms per step (2) against 148.4-149.7 (0) and 150.0 (1); DESIGN.md section 4.2.
+NODE_LEVEL_LAYER1 = int(os.environ.get("FVGN_NODE_LEVEL_LAYER1", "2") or 0)
 
 
 def default_precision():
@@ -220,17 +220,18 @@ def mlp_backward(mode, precision, rows, params, in0, in1, idx_s, idx_r, d_out, d
     packed: the bf16 weight image used by the matching forward (bf16 mode); repacked from `params` when None.
     z1: the Z1Image the matching bf16 forward filled; when None (stand-alone use) the forward is re-run to make it.
     d_in0h: EDGE, bf16 mode: [E,256] bf16 destination of d(agg[s])|d(agg[r]) (instead of the fp32 d_in0)."""
+    like = d_out if d_out is not None else d_in1   # d_out None: EDGE block whose outputs only feed the node block
     if is_tc(precision) and z1 is None and rows > 0:
-        z1 = new_z1(mode, precision, rows, d_out)
+        z1 = new_z1(mode, precision, rows, like)
         mlp_forward(mode, precision, rows, params, in0, in1, idx_s, idx_r, want_out=True, want_res=False, flags=flags,
                     packed=packed, z1=z1, in0h=in0h, in1h=in1h)
     d = _mlp_desc(mode, precision, rows, params, in0, in1, idx_s, idx_r, flags, packed, in0h, in1h)
     lib = _lib.load()
     pc = int(lib.fvgn_mlp_param_count(mode))
     npart = int(lib.fvgn_mlp_bwd_partials(mode, PREC[precision], rows))
-    partials = _empty((npart, pc), d_out)
-    flat = _empty((pc,), d_out)
-    d.d_out, d.d_gather = fptr(d_out), fptr(d_gather, True)
+    partials = _empty((npart, pc), like)
+    flat = _empty((pc,), like)
+    d.d_out, d.d_gather = fptr(d_out, True), fptr(d_gather, True)
     d.d_in0, d.d_in1 = fptr(d_in0, True), fptr(d_in1, True)
     if d_in0h is not None:
         d.d_in0h = hptr(d_in0h)
@@ -241,17 +242,19 @@ def mlp_backward(mode, precision, rows, params, in0, in1, idx_s, idx_r, d_out, d
     if node_path is not None:       # EDGE, tensor-core modes: node-level layer-1 backward -> (plan, d_aggh [N,128] 16-bit)
         nplan, d_aggh = node_path
         nnp = int(lib.fvgn_mlp_bwd_node_partials(nplan.N))
-        d._node_partials = _empty((nnp, 128 * 256), d_out)
+        d._node_partials = _empty((nnp, 128 * 256), like)
         d.inc_ptr, d.inc_code, d.n_nodes = iptr(nplan.inc_ptr), iptr(nplan.inc_code), nplan.N
         d.d_aggh, d.node_partials, d.n_node_partials = hptr(d_aggh), fptr(d._node_partials), nnp
+        if NODE_LEVEL_LAYER1 == 2:
+            d._node_ws, d.node_ws = _img_buffer(int(lib.fvgn_mlp_bwd_node_workspace_bytes(nplan.N)), like.device)
     d.partials, d.n_partials, d.d_params = fptr(partials), npart, fptr(flat)
     if precision == "f16":
-        d.grad_unscale = grad_scale(d_out.device)[1:2].data_ptr()
+        d.grad_unscale = grad_scale(like.device)[1:2].data_ptr()
     ws_bytes = int(lib.fvgn_mlp_bwd_workspace_bytes(mode, PREC[precision], rows))
     if ws_bytes > 0 and rows > 0:
-        d._ws, d.workspace = _img_buffer(ws_bytes, d_out.device)
+        d._ws, d.workspace = _img_buffer(ws_bytes, like.device)
         d._z1, d.z1_img = z1, z1.ptr
-    _lib.call("fvgn_mlp_backward", ctypes.byref(d), _lib.stream_ptr(d_out.device))
+    _lib.call("fvgn_mlp_backward", ctypes.byref(d), _lib.stream_ptr(like.device))
     k1 = _MLP_K1[mode]
     nout = 3 if mode == _lib.FVGN_MLP_DEC else 128
     sizes = [(128, k1), (128,), (128, 128), (128,), (nout, 128), (nout,)]
@@ -373,9 +376,10 @@ class GnBlockFn(torch.autograd.Function):
               the bf16 shadows xh, eh, aggh, a2h and the two Z1 tile images."""
 
     @staticmethod
-    def forward(ctx, x, e, xh, eh, plan, precision, *params):
+    def forward(ctx, x, e, xh, eh, plan, precision, keep_e, *params):
         eb, nb = params[:8], params[8:]
         x, e = _c(x), _c(e)
+        ctx.keep_e = keep_e = bool(keep_e) or not is_tc(precision)
         ctx.set_materialize_grads(False)  # no zero tensors for the (non-differentiable) bf16 shadow outputs
         ctx.pk = (_packed(_lib.FVGN_MLP_EDGE, precision, eb), _packed(_lib.FVGN_MLP_NODE, precision, nb))
         ctx.plan, ctx.precision = plan, precision
@@ -385,9 +389,11 @@ class GnBlockFn(torch.autograd.Function):
             eh = eh if (eh is not None and eh.dtype == BF16) else shadow(e, dtype=BF16)
             ctx.z1 = (_z1_for(ctx, _lib.FVGN_MLP_EDGE, precision, plan.E, x), _z1_for(ctx, _lib.FVGN_MLP_NODE, precision, plan.N, x))
             aggh = adj_reduce(xh, plan, 128, out_dtype=BF16)
-            _, e_out, e_newh, e_outh = mlp_forward(_lib.FVGN_MLP_EDGE, precision, plan.E, eb, None, e, plan.edge_s, plan.edge_r,
-                                                   want_out=False, want_res=True, packed=ctx.pk[0], z1=ctx.z1[0], in0h=aggh,
-                                                   in1h=eh, want_outh=True, want_resh=True)
+            # keep_e False (last GnBlock of a model: the decoder / Transolver block read x only): the residual stream
+            # e + e' and its shadow are never written, and the backward gets no upstream edge gradient (d_out = NULL)
+            _, e_out, e_newh, e_outh = mlp_forward(_lib.FVGN_MLP_EDGE, precision, plan.E, eb, None, e if keep_e else None,
+                                                   plan.edge_s, plan.edge_r, want_out=False, want_res=keep_e, packed=ctx.pk[0],
+                                                   z1=ctx.z1[0], in0h=aggh, in1h=eh, want_outh=True, want_resh=keep_e)
             a1h = inc_reduce(e_newh, plan, 64, out_dtype=BF16)
             del e_newh
             a2h = adj_reduce(a1h, plan, 64, _lib.FVGN_ADJ_DIV_DST_BY_DEG, out_dtype=BF16)
@@ -395,7 +401,7 @@ class GnBlockFn(torch.autograd.Function):
             _, x_out, _, x_outh = mlp_forward(_lib.FVGN_MLP_NODE, precision, plan.N, nb, None, x, want_out=False, want_res=True,
                                               packed=ctx.pk[1], z1=ctx.z1[1], in0h=a2h, in1h=xh, want_resh=True)
             ctx.save_for_backward(xh, eh, aggh, a2h, *params)
-            ctx.mark_non_differentiable(x_outh, e_outh)
+            ctx.mark_non_differentiable(*(t for t in (x_outh, e_outh) if t is not None))
             return x_out, e_out, x_outh, e_outh
         agg = adj_reduce(x, plan, 128)
         e_new, e_out = mlp_forward(_lib.FVGN_MLP_EDGE, precision, plan.E, eb, agg, e, plan.edge_s, plan.edge_r,
@@ -415,7 +421,10 @@ class GnBlockFn(torch.autograd.Function):
         eb, nb = params[:8], params[8:]
         dev = x.device
         d_x_out = _c(d_x_out) if d_x_out is not None else torch.zeros((plan.N, 128), device=dev)
-        d_e_out = _c(d_e_out) if d_e_out is not None else torch.zeros((plan.E, 128), device=dev)
+        if d_e_out is not None:
+            d_e_out = _c(d_e_out)
+        elif ctx.keep_e:
+            d_e_out = torch.zeros((plan.E, 128), device=dev)
         d_a2 = _empty((plan.N, 64), d_x_out) if not is_tc(precision) else None
         d_x = _empty((plan.N, 128), d_x_out)
         d_e = _empty((plan.E, 128), d_x_out)
@@ -454,7 +463,7 @@ class GnBlockFn(torch.autograd.Function):
             d_agg = inc_reduce(d_sr, plan, 128)
             del d_sr
         adj_reduce(d_agg, plan, 128, _lib.FVGN_ADJ_ACCUMULATE, out=d_x)
-        return (d_x, d_e, None, None, None, None, *g_eb, *g_nb)
+        return (d_x, d_e, None, None, None, None, None, *g_eb, *g_nb)
 
 
 class EdgeBlockFn(torch.autograd.Function):

@@ -108,7 +108,8 @@ typedef struct fvgn_mlp_desc {
   float* out;     /* y = MLP(in)  [rows,128] ([rows,3] for DEC); may be NULL for EDGE/NODE if only out_res is wanted */
   float* out_res; /* EDGE: e + y, NODE: x + y; NULL otherwise */
   /* backward inputs */
-  const float* d_out;    /* grad wrt out_res (EDGE/NODE) or out (ENC_*, DEC) */
+  const float* d_out;    /* grad wrt out_res (EDGE/NODE) or out (ENC_*, DEC).  EDGE, tensor-core modes: may be NULL when d_gather /
+                          * d_gatherh is given (a block whose e' / e + e' only feed its node block: zero upstream gradient) */
   const float* d_gather; /* EDGE: d_a1[N,64]; [d_a1[s]|d_a1[r]] is added to d_out (transpose of blocks.py:24-42) */
   /* backward outputs */
   float* d_in0; /* EDGE: [E,256] = d(agg[s]) | d(agg[r]);  NODE: d_a2[N,64];  DEC: d_x[N,128];  ENC_*: NULL */
@@ -155,11 +156,14 @@ typedef struct fvgn_mlp_desc {
   float* node_partials;
   int32_t n_node_partials;
   int32_t reserved1;
+  void* node_ws;       /* optional, fvgn_mlp_bwd_node_workspace_bytes(n_nodes) bytes, 1024-B aligned: when given, the incidence sums
+                        * U_s / U_r are formed by a separate memory-bound kernel as operand tile images (two kernels) */
 } fvgn_mlp_desc;
 
 int64_t fvgn_mlp_param_count(int32_t mode);
 int32_t fvgn_mlp_bwd_partials(int32_t mode, int32_t precision, int64_t rows); /* number of per-CTA partial buffers to allocate */
 int32_t fvgn_mlp_bwd_node_partials(int64_t n_nodes); /* rows of fvgn_mlp_desc.node_partials (node-level layer-1 path) */
+int64_t fvgn_mlp_bwd_node_workspace_bytes(int64_t n_nodes); /* bytes of fvgn_mlp_desc.node_ws */
 int64_t fvgn_mlp_bwd_workspace_bytes(int32_t mode, int32_t precision, int64_t rows);
 int64_t fvgn_mlp_packed_bytes(int32_t mode);
 /* fp32 parameters -> 16-bit UMMA operand image in the format of `precision` (FVGN_PREC_BF16 / FVGN_PREC_F16); weights

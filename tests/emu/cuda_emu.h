@@ -4,20 +4,23 @@
 // The product package never loads the emulated library (it hard-fails without CUDA);
 // only tests/ build and load it (tests/emu/build_emu.py).
 //
-// Execution model: blocks run one after another; the threads of a block are OS threads that
-// meet at a std::barrier for __syncthreads(); `__shared__` becomes a function-local static
-// (safe because only one block is alive at a time).  Kernels launched through
-// FVGN_LAUNCH_SEQ (no barrier / shuffle inside) are run as a plain loop in the caller.
+// Execution model: blocks run one after another; the threads of a block are user-level fibers
+// (ucontext) of the calling OS thread, scheduled round-robin: __syncthreads() / warp shuffles
+// yield until every fiber of the block / warp has arrived (a generation-counting barrier), so a
+// barrier costs a few context swaps instead of the futex storm of 256 OS threads on 8 cores;
+// `__shared__` becomes a function-local static (safe because only one block is alive at a
+// time).  Kernels launched through FVGN_LAUNCH_SEQ (no barrier / shuffle inside) are run as a
+// plain loop in the caller.
 #pragma once
 #include <algorithm>
-#include <barrier>
+#include <ucontext.h>
 #include <cmath>
 #include <cstdint>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
 #include <memory>
-#include <thread>
+#include <functional>
 #include <vector>
 
 #define __global__
@@ -49,18 +52,79 @@ static inline cudaError_t cudaGetLastError() { return 0; }
 static inline cudaError_t cudaPeekAtLastError() { return 0; }
 
 namespace emu {
-struct WarpCtx {
-  uint64_t buf[32];
-  std::unique_ptr<std::barrier<>> bar;
+struct Fiber {
+  ucontext_t ctx;
+  std::vector<unsigned char> stack;
+  dim3 tid;
+  unsigned long long bid = 0;
+  bool done = false;
+};
+struct Barrier {
+  unsigned count = 0, gen = 0;
 };
 inline thread_local dim3 t_threadIdx, t_blockIdx;
 inline thread_local unsigned t_linear = 0;
 inline dim3 g_blockDim, g_gridDim;
-inline std::barrier<>* g_bar = nullptr;
-inline std::vector<WarpCtx> g_warps;
+inline std::vector<Fiber> g_fibers;
+inline ucontext_t g_main_ctx;
+inline Barrier g_block_bar;
+inline std::vector<Barrier> g_warp_bar;
+inline std::vector<uint64_t> g_warp_buf;   // [warp][32] shuffle exchange
+inline std::vector<unsigned> g_warp_size;
 inline std::vector<unsigned char> g_dyn;
 inline unsigned char* g_dyn_ptr = nullptr;
 inline bool g_in_sync_launch = false;
+inline std::function<void()>* g_body = nullptr;
+constexpr size_t FIBER_STACK = 512 * 1024;
+
+inline void set_bid(unsigned long long b) {
+  t_blockIdx.x = (unsigned)(b % g_gridDim.x);
+  t_blockIdx.y = (unsigned)((b / g_gridDim.x) % g_gridDim.y);
+  t_blockIdx.z = (unsigned)(b / ((unsigned long long)g_gridDim.x * g_gridDim.y));
+}
+// switch to the next unfinished fiber (round robin); returns when this fiber is resumed
+inline void yield() {
+  const unsigned me = t_linear, T = (unsigned)g_fibers.size();
+  unsigned nxt = me;
+  do { nxt = (nxt + 1) % T; } while (g_fibers[nxt].done && nxt != me);
+  if (nxt == me) return;
+  swapcontext(&g_fibers[me].ctx, &g_fibers[nxt].ctx);
+  t_linear = me;   // the thread_local "registers" are shared by the fibers: restore ours
+  t_threadIdx = g_fibers[me].tid;
+  set_bid(g_fibers[me].bid);
+}
+inline void barrier_wait(Barrier& b, unsigned parties) {
+  const unsigned my_gen = b.gen;
+  if (++b.count == parties) {
+    b.count = 0;
+    ++b.gen;
+    return;
+  }
+  while (b.gen == my_gen) yield();
+}
+inline void fiber_main(unsigned t) {
+  Fiber& f = g_fibers[t];
+  t_linear = t;
+  t_threadIdx = f.tid;
+  const unsigned long long nb = (unsigned long long)g_gridDim.x * g_gridDim.y * g_gridDim.z;
+  const unsigned T = (unsigned)g_fibers.size();
+  for (unsigned long long b = 0; b < nb; ++b) {
+    f.bid = b;
+    set_bid(b);
+    (*g_body)();
+    barrier_wait(g_block_bar, T);   // one block alive at a time (function-local static "shared memory")
+  }
+  f.done = true;
+  // hand over to any unfinished fiber, else back to the launcher
+  for (unsigned i = 1; i <= T; ++i) {
+    const unsigned nxt = (t + i) % T;
+    if (!g_fibers[nxt].done) {
+      setcontext(&g_fibers[nxt].ctx);
+    }
+  }
+  setcontext(&g_main_ctx);
+}
+inline void fiber_entry(int t) { fiber_main((unsigned)t); }
 
 template <class F>
 void launch(bool sync, dim3 grid, dim3 block, size_t smem, F&& body) {
@@ -70,52 +134,44 @@ void launch(bool sync, dim3 grid, dim3 block, size_t smem, F&& body) {
   g_dyn_ptr = (unsigned char*)(((uintptr_t)g_dyn.data() + 1023) & ~(uintptr_t)1023);
   const unsigned T = block.x * block.y * block.z;
   const unsigned long long nb = (unsigned long long)grid.x * grid.y * grid.z;
-  auto set_tid = [&](unsigned t) {
-    t_linear = t;
-    t_threadIdx.x = t % block.x;
-    t_threadIdx.y = (t / block.x) % block.y;
-    t_threadIdx.z = t / (block.x * block.y);
-  };
-  auto set_bid = [&](unsigned long long b) {
-    t_blockIdx.x = (unsigned)(b % grid.x);
-    t_blockIdx.y = (unsigned)((b / grid.x) % grid.y);
-    t_blockIdx.z = (unsigned)(b / ((unsigned long long)grid.x * grid.y));
-  };
+  auto tid_of = [&](unsigned t) { return dim3(t % block.x, (t / block.x) % block.y, t / (block.x * block.y)); };
   if (!sync) {
     g_in_sync_launch = false;
     for (unsigned long long b = 0; b < nb; ++b) {
       set_bid(b);
       for (unsigned t = 0; t < T; ++t) {
-        set_tid(t);
+        t_linear = t;
+        t_threadIdx = tid_of(t);
         body();
       }
     }
     return;
   }
+  if (nb == 0 || T == 0) return;
   g_in_sync_launch = true;
-  std::barrier<> bar(T);
-  g_bar = &bar;
+  std::function<void()> fn = [&] { body(); };
+  g_body = &fn;
+  g_block_bar = Barrier();
   const unsigned nw = (T + 31) / 32;
-  g_warps.clear();
-  g_warps.resize(nw);
-  for (unsigned w = 0; w < nw; ++w) {
-    unsigned cnt = std::min(32u, T - w * 32);
-    g_warps[w].bar = std::make_unique<std::barrier<>>(cnt);
-  }
-  std::vector<std::thread> th;
-  th.reserve(T);
+  g_warp_bar.assign(nw, Barrier());
+  g_warp_buf.assign((size_t)nw * 32, 0);
+  g_warp_size.resize(nw);
+  for (unsigned w = 0; w < nw; ++w) g_warp_size[w] = std::min(32u, T - w * 32);
+  if (g_fibers.size() != T) g_fibers.resize(T);
   for (unsigned t = 0; t < T; ++t) {
-    th.emplace_back([&, t] {
-      set_tid(t);
-      for (unsigned long long b = 0; b < nb; ++b) {
-        set_bid(b);
-        body();
-        bar.arrive_and_wait();
-      }
-    });
+    Fiber& f = g_fibers[t];
+    if (f.stack.size() != FIBER_STACK) f.stack.resize(FIBER_STACK);
+    f.tid = tid_of(t);
+    f.bid = 0;
+    f.done = false;
+    getcontext(&f.ctx);
+    f.ctx.uc_stack.ss_sp = f.stack.data();
+    f.ctx.uc_stack.ss_size = f.stack.size();
+    f.ctx.uc_link = &g_main_ctx;
+    makecontext(&f.ctx, (void (*)())fiber_entry, 1, (int)t);
   }
-  for (auto& x : th) x.join();
-  g_bar = nullptr;
+  swapcontext(&g_main_ctx, &g_fibers[0].ctx);   // returns when the last fiber has finished
+  g_body = nullptr;
   g_in_sync_launch = false;
 }
 
@@ -124,7 +180,7 @@ inline void syncthreads() {
     fprintf(stderr, "emu: __syncthreads() inside a FVGN_LAUNCH_SEQ kernel\n");
     abort();
   }
-  g_bar->arrive_and_wait();
+  barrier_wait(g_block_bar, (unsigned)g_fibers.size());
 }
 template <class T>
 T shfl(T v, int src_lane) {
@@ -133,13 +189,13 @@ T shfl(T v, int src_lane) {
     fprintf(stderr, "emu: warp shuffle inside a FVGN_LAUNCH_SEQ kernel\n");
     abort();
   }
-  WarpCtx& w = g_warps[t_linear / 32];
+  const unsigned w = t_linear / 32;
   uint64_t bits = 0;
   memcpy(&bits, &v, sizeof(T));
-  w.buf[t_linear % 32] = bits;
-  w.bar->arrive_and_wait();
-  uint64_t got = w.buf[src_lane & 31];
-  w.bar->arrive_and_wait();
+  g_warp_buf[(size_t)w * 32 + t_linear % 32] = bits;
+  barrier_wait(g_warp_bar[w], g_warp_size[w]);
+  uint64_t got = g_warp_buf[(size_t)w * 32 + (src_lane & 31)];
+  barrier_wait(g_warp_bar[w], g_warp_size[w]);
   T r;
   memcpy(&r, &got, sizeof(T));
   return r;
@@ -149,7 +205,8 @@ inline void syncwarp() {
     fprintf(stderr, "emu: warp barrier inside a FVGN_LAUNCH_SEQ kernel\n");
     abort();
   }
-  g_warps[t_linear / 32].bar->arrive_and_wait();
+  const unsigned w = t_linear / 32;
+  barrier_wait(g_warp_bar[w], g_warp_size[w]);
 }
 }  // namespace emu
 

@@ -297,8 +297,9 @@ def test_tc_zero_rows():
 
 
 @pytest.mark.parametrize("prec", ["bf16", "f16"])
-@pytest.mark.parametrize("n", [7, 40])
-def test_node_level_layer1_backward_matches_edge_level(prec, n):
+@pytest.mark.parametrize("n", [7, 40, 150])   # 150: more node tiles than SMs (several tiles per persistent CTA)
+@pytest.mark.parametrize("variant", [1, 2])
+def test_node_level_layer1_backward_matches_edge_level(prec, n, variant, monkeypatch):
     """fvgn_mlp_desc.d_aggh (csrc/mlp_tc_bwd_node.cu): the agg[s] | agg[r] columns of the edge MLP's first layer
     differentiated per node -- d(agg) = U_s W1a + U_r W1b with U = incidence sums of dZ1, dW1ab = U^T agg -- against the
     edge-level path (kernel B writes d(agg[s]) | d(agg[r]) per edge, then the incidence reduction).  Everything the two
@@ -308,6 +309,7 @@ def test_node_level_layer1_backward_matches_edge_level(prec, n):
     from gen_fvgn_steady_b200.mesh import synthetic
     from gen_fvgn_steady_b200.plan import GraphPlan
     from tests.case_inputs import product_graphs
+    monkeypatch.setattr(ops, "NODE_LEVEL_LAYER1", variant)   # 1: one fused kernel; 2: incidence-sum kernel + node GEMM kernel
     dev = torch.device("cuda")
     hdt = ops.HDTYPE[prec]
     mesh, uvp = synthetic.make_case(n, kind="mixed", bc="channel", seed=3)
@@ -350,3 +352,36 @@ def test_node_level_layer1_backward_matches_edge_level(prec, n):
     assert rel < (2e-2 if prec == "bf16" else 3e-3), rel
     # and against an fp64 evaluation of the same linear maps from the dZ1 implied by the reference path: d_srh = dZ1 W1[:, :256]
     # is what both paths approximate; the node path must not be further from the fp32 incidence sum of d_srh than 16-bit rounding
+
+
+@pytest.mark.parametrize("prec", ["bf16", "f16"])
+def test_last_block_without_edge_latent_is_identical(prec):
+    """GnBlock(keep_edge_latent=False) -- what the models pass for their last block, whose e + e' nothing reads
+    (EPD.py:262-270 decodes graph.x only): the forward skips the [E,128] residual stream and its shadow, the backward runs with
+    fvgn_mlp_desc.d_out = NULL instead of a zero tensor.  Node output and every gradient must be bit-identical."""
+    from gen_fvgn_steady_b200 import ops
+    from gen_fvgn_steady_b200.mesh import synthetic
+    from gen_fvgn_steady_b200.plan import GraphPlan
+    from tests.case_inputs import product_graphs
+    dev = torch.device("cuda")
+    mesh, uvp = synthetic.make_case(40, kind="mixed", bc="channel", seed=3)
+    plan = GraphPlan.of(product_graphs([mesh], [uvp], dev)[0])
+    g = torch.Generator(device=dev).manual_seed(11)
+    rn = lambda *s: torch.randn(*s, device=dev, generator=g)
+
+    def mlp(k1):
+        return [rn(128, k1) / k1 ** 0.5, 0.1 * rn(128), rn(128, 128) / 128 ** 0.5, 0.1 * rn(128), rn(128, 128) / 128 ** 0.5,
+                0.1 * rn(128), 1 + 0.1 * rn(128), 0.1 * rn(128)]
+    params = [p.requires_grad_() for p in mlp(384) + mlp(192)]
+    x0, e0, dx = rn(plan.N, 128), rn(plan.E, 128), rn(plan.N, 128)
+    res = []
+    for keep in (True, False):
+        x, e = x0.clone().requires_grad_(), e0.clone().requires_grad_()
+        x_out, e_out, _, _ = ops.apply(ops.GnBlockFn, x, e, None, None, plan, prec, keep, *params)
+        assert (e_out is None) == (not keep)
+        grads = torch.autograd.grad(x_out, [x, e] + params, dx)
+        res.append((x_out.detach(), grads))
+    torch.cuda.synchronize()
+    assert torch.equal(res[0][0], res[1][0])
+    for i, (a, b) in enumerate(zip(res[0][1], res[1][1])):
+        assert torch.equal(a, b), i
