@@ -184,10 +184,13 @@ def _gn_blocks(net, mp):
 
 
 def workload_config(args):
-    return {"workload": f"synthetic jittered quad mesh, {args.cells} cells/GPU, cavity BC, NS theta; "
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    cells_mode = getattr(args, "parallel", "dp") == "cells" and world > 1
+    size = f"ONE {args.cells}-cell mesh partitioned over {world} GPUs" if cells_mode else f"{args.cells} cells/GPU"
+    return {"workload": f"synthetic jittered quad mesh, {size}, cavity BC, NS theta; "
                         f"{args.net} G={_gn_blocks(args.net, args.mp)} + FV PDE loss; resident batch (solve_with_grad regime)",
             "net": args.net, "gn_blocks": _gn_blocks(args.net, args.mp), "cuda_graph": bool(getattr(args, "graph", False)),
-            "cells_per_gpu": args.cells, "precision": args.precision,
+            "cells_per_gpu": args.cells // world if cells_mode else args.cells, "precision": args.precision,
             "l2": "inputs/activations (GBs) far exceed the 126 MB L2; no explicit flush"}
 
 
@@ -567,6 +570,8 @@ def run_ours(args):
                 partition: the N > 1 `cells` record); same net / precision / loss as the headline."""
                 out = {}
                 for c in (1_000_000, 2_000_000, 8_000_000):
+                    torch.cuda.empty_cache()
+                    torch.cuda.reset_peak_memory_stats(dev)
                     m_, u_ = make_mesh(c, 0, dev)
                     g_ = graphs_from_meshes([m_], [u_], dev)
                     del m_, u_

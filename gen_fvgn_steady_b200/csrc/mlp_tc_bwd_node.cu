@@ -54,9 +54,9 @@ constexpr int smem_node() { return 4 * KB_BYTES + 3 * BUF_BYTES + 4 * WSTG_BYTES
 // Two-kernel variant (fvgn_mlp_desc.node_ws != NULL): the incidence sums are formed by a separate, many-CTA kernel that is
 // bound by memory rather than by one CTA's gather latency, and written as ready-made operand tile images:
 // node tile t -> [U_s kb0 | U_s kb1 | U_r kb0 | U_r kb1], 4 x 16 KB at node_ws + t * 64 KB.
-template <class P>
-__global__ void __launch_bounds__(256, 5) dz_incidence_kernel(const uint8_t* __restrict__ dz_img, const int32_t* __restrict__ ptr,
-                                                               const int32_t* __restrict__ ent, uint8_t* __restrict__ u_img, int64_t n) {
+template <class P, int R, int MINB>
+__global__ void __launch_bounds__(256, MINB) dz_incidence_kernel(const uint8_t* __restrict__ dz_img, const int32_t* __restrict__ ptr,
+                                                                  const int32_t* __restrict__ ent, uint8_t* __restrict__ u_img, int64_t n) {
   constexpr int RB = TILE_M, ECAP = 1536, NB = 4, G = 16;
   __shared__ int s_ptr[3][RB + 1];
   __shared__ int s_ent[2][ECAP];
@@ -98,54 +98,65 @@ __global__ void __launch_bounds__(256, 5) dz_incidence_kernel(const uint8_t* __r
     };
     uint8_t* ut = u_img + (size_t)blk * (2 * BUF_BYTES);
 #pragma unroll 1
-    for (int rr = g; rr < RB; rr += G) {   // rows past the last node are written as zeros (they are MMA operands)
-      int b = 0, deg = 0, c[NB];
-      uint4 v[NB];
-      if (rr < nr) { b = sp[rr]; deg = sp[rr + 1] - b; }
+    for (int r0 = g; r0 < RB; r0 += G * R) {   // rows past the last node are written as zeros (they are MMA operands)
+      int b[R], deg[R], c[R][NB];
+      uint4 v[R][NB];
 #pragma unroll
-      for (int k = 0; k < NB; ++k) {
-        c[k] = 0;
-        if (k < deg) {
-          c[k] = entry(b + k);
-          v[k] = __ldg(dz_row(c[k] >> 1));
-        }
-      }
-      float as[8], ar[8];
-#pragma unroll
-      for (int j = 0; j < 8; ++j) { as[j] = 0.f; ar[j] = 0.f; }
-      auto add = [&](const uint4& w, int code) {
-        const float x[8] = {P::lo(w.x), P::hi(w.x), P::lo(w.y), P::hi(w.y), P::lo(w.z), P::hi(w.z), P::lo(w.w), P::hi(w.w)};
-        if (code & 1) {
-#pragma unroll
-          for (int j = 0; j < 8; ++j) ar[j] += x[j];
-        } else {
-#pragma unroll
-          for (int j = 0; j < 8; ++j) as[j] += x[j];
-        }
-      };
-#pragma unroll
-      for (int k = 0; k < NB; ++k)
-        if (k < deg) add(v[k], c[k]);
-      for (int t0 = NB; t0 < deg; t0 += NB) {
-        uint4 w[NB];
-        int cc[NB];
+      for (int r = 0; r < R; ++r) {   // issue phase: the first NB gathers of R rows
+        const int rr = r0 + r * G;
+        b[r] = 0; deg[r] = 0;
+        if (rr < nr) { b[r] = sp[rr]; deg[r] = sp[rr + 1] - b[r]; }
 #pragma unroll
         for (int k = 0; k < NB; ++k) {
-          cc[k] = 0;
-          if (t0 + k < deg) {
-            cc[k] = entry(b + t0 + k);
-            w[k] = __ldg(dz_row(cc[k] >> 1));
+          c[r][k] = 0;
+          if (k < deg[r]) {
+            c[r][k] = entry(b[r] + k);
+            v[r][k] = __ldg(dz_row(c[r][k] >> 1));
           }
         }
+      }
+#pragma unroll
+      for (int r = 0; r < R; ++r) {
+        const int rr = r0 + r * G;
+        float as[8], ar[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) { as[j] = 0.f; ar[j] = 0.f; }
+        // role mask as a multiplier (adding 0 * x is exact): the two 16-lane groups of a warp never diverge
+        auto add = [&](const uint4& w, int code) {
+          const float x[8] = {P::lo(w.x), P::hi(w.x), P::lo(w.y), P::hi(w.y), P::lo(w.z), P::hi(w.z), P::lo(w.w), P::hi(w.w)};
+          const float mr = (float)(code & 1), ms = 1.f - mr;
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            as[j] = fmaf(ms, x[j], as[j]);
+            ar[j] = fmaf(mr, x[j], ar[j]);
+          }
+        };
 #pragma unroll
         for (int k = 0; k < NB; ++k)
-          if (t0 + k < deg) add(w[k], cc[k]);
+          if (k < deg[r]) add(v[r][k], c[r][k]);
+        for (int t0 = NB; t0 < deg[r]; t0 += NB) {
+          uint4 w[NB];
+          int cc[NB];
+#pragma unroll
+          for (int k = 0; k < NB; ++k) {
+            cc[k] = 0;
+            if (t0 + k < deg[r]) {
+              cc[k] = entry(b[r] + t0 + k);
+              w[k] = __ldg(dz_row(cc[k] >> 1));
+            }
+          }
+#pragma unroll
+          for (int k = 0; k < NB; ++k)
+            if (t0 + k < deg[r]) add(w[k], cc[k]);
+        }
+        if (rr < RB) {
+          const uint32_t off = kb * KB_BYTES + sw128_off(rr, ch);
+          *reinterpret_cast<uint4*>(ut + off) =
+              make_uint4(pack16<P>(as[0], as[1]), pack16<P>(as[2], as[3]), pack16<P>(as[4], as[5]), pack16<P>(as[6], as[7]));
+          *reinterpret_cast<uint4*>(ut + BUF_BYTES + off) =
+              make_uint4(pack16<P>(ar[0], ar[1]), pack16<P>(ar[2], ar[3]), pack16<P>(ar[4], ar[5]), pack16<P>(ar[6], ar[7]));
+        }
       }
-      const uint32_t off = kb * KB_BYTES + sw128_off(rr, ch);
-      *reinterpret_cast<uint4*>(ut + off) =
-          make_uint4(pack16<P>(as[0], as[1]), pack16<P>(as[2], as[3]), pack16<P>(as[4], as[5]), pack16<P>(as[6], as[7]));
-      *reinterpret_cast<uint4*>(ut + BUF_BYTES + off) =
-          make_uint4(pack16<P>(ar[0], ar[1]), pack16<P>(ar[2], ar[3]), pack16<P>(ar[4], ar[5]), pack16<P>(ar[6], ar[7]));
     }
     cp_async_commit_wait_all();
     __syncthreads();
@@ -440,27 +451,58 @@ int fvgn_mlp_tc_node_partials(int64_t n_nodes) {
 
 int64_t fvgn_mlp_tc_node_ws_bytes(int64_t n_nodes) { return ((n_nodes + TILE_M - 1) / TILE_M) * (int64_t)(2 * BUF_BYTES); }
 
+#ifndef FVGN_DZI_R
+#define FVGN_DZI_R 1
+#endif
+#ifndef FVGN_DZI_MINB
+#define FVGN_DZI_MINB 4   // 63 registers, no spills: 1.19 ms per 4 M nodes (5: 48 registers + spills 1.46, R = 2: 1.31; profiles/r2z_dzi_sweep.txt)
+#endif
+
+template <class P, int R, int MINB>
+static int launch_dz_incidence(const fvgn_mlp_desc& d, void* stream) {
+  auto kz = dz_incidence_kernel<P, R, MINB>;
+  static unsigned inc_grid[FVGN_MAX_DEV] = {0};
+  const int dev = fvgn_cur_device();
+  if (inc_grid[dev] == 0) {
+    int per_sm = 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kz, 256, 0) != cudaSuccess || per_sm < 1) return FVGN_ERR_LAUNCH;
+    inc_grid[dev] = (unsigned)(per_sm * fvgn_num_sms());
+  }
+  const int64_t ntiles = (d.n_nodes + TILE_M - 1) / TILE_M;
+  kz<<<(unsigned)(ntiles < inc_grid[dev] ? ntiles : inc_grid[dev]), 256, 0, (cudaStream_t)stream>>>(
+      reinterpret_cast<const uint8_t*>(d.workspace), d.inc_ptr, d.inc_code, reinterpret_cast<uint8_t*>(d.node_ws), d.n_nodes);
+  FVGN_CHECK_LAUNCH();
+  return FVGN_OK;
+}
+
 template <class P>
 int launch_tc_bwd_node(const fvgn_mlp_desc& d, void* stream) {
   auto kn = mlp_tc_bwd_node_kernel<P, false>;
   auto ki = mlp_tc_bwd_node_kernel<P, true>;
-  auto kz = dz_incidence_kernel<P>;
   static bool attr_set[FVGN_MAX_DEV] = {false};
-  static unsigned inc_grid[FVGN_MAX_DEV] = {0};
   const int dev = fvgn_cur_device();
   if (!attr_set[dev]) {
     if (cudaFuncSetAttribute(kn, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_node()) != cudaSuccess) return FVGN_ERR_LAUNCH;
     if (cudaFuncSetAttribute(ki, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_node()) != cudaSuccess) return FVGN_ERR_LAUNCH;
-    int per_sm = 0;
-    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kz, 256, 0) != cudaSuccess || per_sm < 1) return FVGN_ERR_LAUNCH;
-    inc_grid[dev] = (unsigned)(per_sm * fvgn_num_sms());
     attr_set[dev] = true;
   }
   if (d.node_ws) {
-    const int64_t ntiles = (d.n_nodes + TILE_M - 1) / TILE_M;
-    kz<<<(unsigned)(ntiles < inc_grid[dev] ? ntiles : inc_grid[dev]), 256, 0, (cudaStream_t)stream>>>(
-        reinterpret_cast<const uint8_t*>(d.workspace), d.inc_ptr, d.inc_code, reinterpret_cast<uint8_t*>(d.node_ws), d.n_nodes);
-    FVGN_CHECK_LAUNCH();
+#ifdef FVGN_DZI_SWEEP   // tools/dzi_sweep.sh: variant picked per call
+    static int variant = -1;
+    if (variant < 0) { const char* e = getenv("FVGN_DZI_VARIANT"); variant = e ? atoi(e) : 0; }
+    int rc;
+    switch (variant) {
+      case 1: rc = launch_dz_incidence<P, 1, 4>(d, stream); break;
+      case 2: rc = launch_dz_incidence<P, 2, 4>(d, stream); break;
+      case 3: rc = launch_dz_incidence<P, 2, 3>(d, stream); break;
+      case 4: rc = launch_dz_incidence<P, 1, 6>(d, stream); break;
+      case 5: rc = launch_dz_incidence<P, 2, 5>(d, stream); break;
+      default: rc = launch_dz_incidence<P, 1, 5>(d, stream); break;
+    }
+#else
+    const int rc = launch_dz_incidence<P, FVGN_DZI_R, FVGN_DZI_MINB>(d, stream);
+#endif
+    if (rc != FVGN_OK) return rc;
     ki<<<(unsigned)d.n_node_partials, N_THREADS, smem_node(), (cudaStream_t)stream>>>(d);
   } else {
     kn<<<(unsigned)d.n_node_partials, N_THREADS, smem_node(), (cudaStream_t)stream>>>(d);
