@@ -195,9 +195,10 @@ def workload_config(args):
 
 
 DTYPE_TEXT = {"fp32": "f32 (SIMT FMA)",
-              "bf16": "bf16 tcgen05 operands and derived streams; f32 accumulators, LayerNorm, residual streams and gradients of them",
-              "f16": "f16 tcgen05 operands and derived streams (11-bit significand = the reference's TF32 GPU arithmetic); f32 "
-                     "accumulators, LayerNorm, residual streams and gradients of them"}
+              "bf16": "bf16 tcgen05 operands and latent streams between the GnBlocks; f32 accumulators, LayerNorm, residual adds and "
+                      "every gradient stream",
+              "f16": "f16 tcgen05 operands and latent streams between the GnBlocks (11-bit significand = the reference's TF32 GPU "
+                     "arithmetic); f32 accumulators, LayerNorm, residual adds and every gradient stream"}
 
 
 # ----------------------------------------------------------------------------------------------- our arm

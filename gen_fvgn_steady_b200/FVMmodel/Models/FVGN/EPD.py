@@ -58,12 +58,14 @@ class Encoder(nn.Module):
         self.eb_encoder = build_mlp(edge_input_size, hidden_size, int(hidden_size), drop_out=False)
         self.nb_encoder = build_mlp(node_input_size, hidden_size, int(hidden_size), drop_out=False)
 
-    def forward(self, graph_node, graph_cell=None):
+    def forward(self, graph_node, graph_cell=None, latents_16bit=False, x_fp32=True):
         """graph_node.x is the normalised [N,12] feature; the [E,15] relative edge feature of
-        importer.py:54-78 is computed inside the edge-encoder kernel from x and pos."""
+        importer.py:54-78 is computed inside the edge-encoder kernel from x and pos.
+        latents_16bit / x_fp32: as GnBlock.forward (passed by the models; tensor-core modes only)."""
         plan = GraphPlan.of(graph_node)
+        opts = (ops.GN_LATENTS16 if latents_16bit and ops.LATENTS16 else 0) | (ops.GN_X_FP32 if x_fp32 else 0)
         node_, edge_, nh, eh = ops.apply(ops.EncoderFn, graph_node.x.contiguous(), graph_node.pos.float().contiguous(), plan,
-                                                   _precision(self), *mlp_params(self.nb_encoder), *mlp_params(self.eb_encoder))
+                                         _precision(self), opts, *mlp_params(self.nb_encoder), *mlp_params(self.eb_encoder))
         # bf16 mode: the kernels also emit bf16 shadows of the latents; they travel with the graph as (master, shadow)
         return _carry(graph_node, x=node_, edge_attr=edge_, _fvgn_plan=plan, _xh=(node_, nh), _eh=(edge_, eh)), node_
 
@@ -76,14 +78,19 @@ class GnBlock(nn.Module):
         self.nb_module = NodeBlock(hidden_size, custom_func=build_mlp(nb_input_dim, hidden_size, int(hidden_size), drop_out=drop_out))
         self.eb_module = EdgeBlock(input_size=hidden_size, custom_func=build_mlp(eb_input_dim, hidden_size, int(hidden_size), drop_out=drop_out))
 
-    def forward(self, graph_node, keep_edge_latent=True):
+    def forward(self, graph_node, keep_edge_latent=True, latents_16bit=False, x_fp32=True):
         """keep_edge_latent=False (passed by the models for their last GnBlock, whose edge latent e + e' nothing reads:
         EPD.py:262-270 decodes graph.x only): tensor-core modes skip that residual stream and its gradient; the returned
-        graph then carries edge_attr = None."""
+        graph then carries edge_attr = None.
+        latents_16bit=True (passed by the models for blocks whose outputs feed another GnBlock / the decoder; tensor-core modes
+        only): the latent streams live as 16-bit rows (graph._xh / graph._eh); graph.x / graph.edge_attr of the returned graph
+        are placeholders that carry the gradients, unless x_fp32 (a Transolver block reads x next)."""
         plan = GraphPlan.of(graph_node)
         xh, eh = _shadow_of(graph_node, "_xh", graph_node.x), _shadow_of(graph_node, "_eh", graph_node.edge_attr)
+        opts = (ops.GN_KEEP_E if keep_edge_latent else 0) | (ops.GN_LATENTS16 if latents_16bit and ops.LATENTS16 else 0) | \
+               (ops.GN_X_FP32 if x_fp32 else 0)
         x, e, xh, eh = ops.apply(ops.GnBlockFn, graph_node.x, graph_node.edge_attr, xh, eh, plan, _precision(self),
-                                 keep_edge_latent, *mlp_params(self.eb_module.net), *mlp_params(self.nb_module.net))
+                                 opts, *mlp_params(self.eb_module.net), *mlp_params(self.nb_module.net))
         return _carry(graph_node, x=x, edge_attr=e, _fvgn_plan=plan, _xh=(x, xh), _eh=(e, eh))
 
 
@@ -112,11 +119,12 @@ class EncoderProcesserDecoder(nn.Module):
         self.decoder = Decoder(hidden_sze=hidden_size, node_output_size=node_output_size)
 
     def forward(self, graph_node=None, graph_edge=None, graph_cell=None):
-        from ....parallel import halo_refresh
-        latent, _ = self.encoder(graph_node)  # point-wise in nodes / edges: exact on the ghost rows too
+        from ....parallel import halo_refresh, no_ghost_refresh
         nblk = len(self.GN_block_list)
-        whole = getattr(graph_node, "_fvgn_halo", None) is None   # a partitioned sub-mesh refreshes the ghost rows of e too
+        whole = no_ghost_refresh(graph_node, nblk)   # (a ghost refresh exchanges the fp32 rows of x and e)
+        latent, _ = self.encoder(graph_node, latents_16bit=whole, x_fp32=False)  # point-wise: exact on the ghost rows too
         for i, model in enumerate(self.GN_block_list):
-            latent = model(latent, keep_edge_latent=not (whole and i == nblk - 1))
+            # no ghost refresh: 16-bit latent streams between the blocks (the decoder reads the shadow of x)
+            latent = model(latent, keep_edge_latent=not (whole and i == nblk - 1), latents_16bit=whole, x_fp32=False)
             latent = halo_refresh(latent, i, nblk)  # cell-partition mode only: ghost rows <- owners (no-op otherwise)
         return self.decoder(latent)

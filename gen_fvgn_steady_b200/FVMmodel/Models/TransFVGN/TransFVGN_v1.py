@@ -17,11 +17,14 @@ class Simulator(nn.Module):
 
     def forward(self, graph_node=None, graph_edge=None, graph_cell=None):
         from ....parallel import halo_refresh
-        latent, node_embedding = self.encoder(graph_node)
+        from ....parallel import no_ghost_refresh
+        whole_ = no_ghost_refresh(graph_node, len(self.GN_block_list))
+        latent, node_embedding = self.encoder(graph_node, latents_16bit=whole_, x_fp32=True)   # x: the Transolver embedding
         nblk = len(self.GN_block_list)
-        whole = getattr(graph_node, "_fvgn_halo", None) is None
+        whole = whole_
         for i, model in enumerate(self.GN_block_list):
-            latent = model(latent, keep_edge_latent=not (whole and i == nblk - 1))   # nothing reads the last edge latent
+            latent = model(latent, keep_edge_latent=not (whole and i == nblk - 1),   # nothing reads the last edge latent
+                           latents_16bit=whole, x_fp32=i == nblk - 1)                        # the Transolver block reads x in fp32
             latent = halo_refresh(latent, i, nblk)  # cell-partition mode only (no-op otherwise)
         latent.x = self.TransBlock(latent.x, graph_node.batch, halo=getattr(latent, "_fvgn_halo", None), num_graphs=getattr(latent, "num_graphs", None),
                                    embedding=node_embedding)

@@ -19,9 +19,12 @@ class AttnProcessor(nn.Module):
         node_embedding = latent_graph_node.x
         latent = latent_graph_node
         total = total_blocks if total_blocks is not None else len(self.GN_block_list)
-        whole = getattr(latent, "_fvgn_halo", None) is None
+        from ....parallel import no_ghost_refresh
+        whole = no_ghost_refresh(latent, total)
         for i, model in enumerate(self.GN_block_list):
-            latent = model(latent, keep_edge_latent=not (whole and first_block + i == total - 1))   # nothing reads the last e
+            last = i == len(self.GN_block_list) - 1   # the Transolver block reads x in fp32
+            latent = model(latent, keep_edge_latent=not (whole and first_block + i == total - 1),   # nothing reads the last e
+                           latents_16bit=whole, x_fp32=last)
             latent = halo_refresh(latent, first_block + i, total)  # cell-partition mode only (no-op otherwise)
         latent.x = self.TransBlock(latent.x, latent.batch, halo=getattr(latent, "_fvgn_halo", None), num_graphs=getattr(latent, "num_graphs", None),
                                    embedding=node_embedding)
@@ -39,7 +42,9 @@ class Simulator(nn.Module):
         self.decoder = Decoder(hidden_sze=hidden_size, node_output_size=node_output_size)
 
     def forward(self, graph_node=None, graph_edge=None, graph_cell=None):
-        latent, _ = self.encoder(graph_node)
+        from ....parallel import no_ghost_refresh
+        whole_ = no_ghost_refresh(graph_node, sum(len(m.GN_block_list) for m in self.processpr_list))
+        latent, _ = self.encoder(graph_node, latents_16bit=whole_, x_fp32=True)   # x: the Transolver embedding of processor 1
         total = sum(len(m.GN_block_list) for m in self.processpr_list)
         first = 0
         for model in self.processpr_list:

@@ -114,8 +114,12 @@ extern "C" int fvgn_mlp_forward(const fvgn_mlp_desc* d, void* stream) {
   if (d && d->rows == 0 && d->mode >= FVGN_MLP_EDGE && d->mode <= FVGN_MLP_DEC) return FVGN_OK;  // empty graph: nothing to do
   int rc = check_common(d);
   if (rc) return rc;
-  if ((d->mode == FVGN_MLP_EDGE || d->mode == FVGN_MLP_NODE) ? (!d->out_res && !d->out && !d->outh) : !d->out) return FVGN_ERR_NULL;
-  if (d->out_res && !d->in1) return FVGN_ERR_NULL;  // the residual is added from the fp32 stream
+  const bool enc = d->mode == FVGN_MLP_ENC_NODE || d->mode == FVGN_MLP_ENC_EDGE;
+  if ((d->mode == FVGN_MLP_EDGE || d->mode == FVGN_MLP_NODE) ? (!d->out_res && !d->out && !d->outh && !d->out_resh)
+      : (!d->out && !(enc && is_tc(d->precision) && d->outh))) return FVGN_ERR_NULL;   // encoders: the 16-bit latent alone will do
+  const bool res16 = (d->flags & FVGN_MLP_RESIDUAL_FROM_SHADOW) != 0;
+  if (res16 && (!is_tc(d->precision) || (d->mode != FVGN_MLP_EDGE && d->mode != FVGN_MLP_NODE) || !d->in1h)) return FVGN_ERR_UNSUPPORTED;
+  if (d->out_res && !d->in1 && !res16) return FVGN_ERR_NULL;  // the residual is added from the fp32 stream
   if (d->rows == 0) return FVGN_OK;
   if (d->precision == FVGN_PREC_FP32) return fvgn_mlp_forward_simt(d, stream);
 #ifndef FVGN_EMU

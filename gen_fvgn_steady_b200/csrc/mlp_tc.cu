@@ -267,8 +267,12 @@ __global__ void __launch_bounds__(NTHREADS, 1) mlp_tc_fwd_kernel(const fvgn_mlp_
     const int rloc = q * 32 + lane;
     uint8_t* mystg = stg + warp * WSTG_BYTES;
     const int orow = lane >> 3, oseg = lane & 7;  // write-out mapping: 4 rows x 8 x 16 B per warp instruction
-    const float* resid = (MODE == FVGN_MLP_EDGE || MODE == FVGN_MLP_NODE) ? d.in1 : nullptr;
-    const bool do_res = resid && d.out_res;
+    // residual row: the fp32 stream in1, or (FVGN_MLP_RESIDUAL_FROM_SHADOW: 16-bit latent streams) the 16-bit shadow in1h the
+    // layer-1 operand was read from -- then the fp32 row is neither read nor (out_res == NULL) written
+    const bool res16 = (MODE == FVGN_MLP_EDGE || MODE == FVGN_MLP_NODE) && (d.flags & FVGN_MLP_RESIDUAL_FROM_SHADOW);
+    const float* resid = (MODE == FVGN_MLP_EDGE || MODE == FVGN_MLP_NODE) && !res16 ? d.in1 : nullptr;
+    const uint16_t* resid_h = res16 ? reinterpret_cast<const uint16_t*>(d.in1h) : nullptr;
+    const bool do_res = (resid && d.out_res) || (resid_h && (d.out_res || d.out_resh));
     bool stg_busy = false;  // a bulk store may still be reading the staging tile
     uint32_t ph1 = 0, ph23 = 0;
 #ifdef FVGN_TIMING
@@ -282,9 +286,15 @@ __global__ void __launch_bounds__(NTHREADS, 1) mlp_tc_fwd_kernel(const fvgn_mlp_
       const uint32_t t2 = tmem + lane_base + 256 * (uint32_t)p + 128 * (uint32_t)(((i >> 1) & 1) ^ 1);
       if (do_res && wrow0 + lane < d.rows) {
         // the fp32 residual row is first touched ~3 epilogue passes from now: pull it into L2 meanwhile
-        const float* rp = resid + (size_t)(wrow0 + lane) * 128;
+        if (resid_h) {
+          const uint16_t* rp = resid_h + (size_t)(wrow0 + lane) * 128;
+          prefetch_l2(rp);
+          prefetch_l2(rp + 64);
+        } else {
+          const float* rp = resid + (size_t)(wrow0 + lane) * 128;
 #pragma unroll
-        for (int k = 0; k < 4; ++k) prefetch_l2(rp + 32 * k);
+          for (int k = 0; k < 4; ++k) prefetch_l2(rp + 32 * k);
+        }
       }
       // ---- hidden layers: +bias, GELU, bf16 written in place over the accumulator's lower 64 columns
 #pragma unroll 1
@@ -422,7 +432,15 @@ __global__ void __launch_bounds__(NTHREADS, 1) mlp_tc_fwd_kernel(const fvgn_mlp_
           for (int ps = 0; ps < 8; ++ps) {
             const int64_t row = wrow0 + ps * 4 + orow;
             xr[ps] = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (do_res && row < d.rows) xr[ps] = __ldg(reinterpret_cast<const float4*>(resid + (size_t)row * 128 + c0 + oseg * 4));
+            if (do_res && row < d.rows) {
+              if (resid_h) {   // raw bits now, unpacked where the row is used: the load latency stays behind the LayerNorm math
+                const uint2 h = __ldg(reinterpret_cast<const uint2*>(resid_h + (size_t)row * 128 + c0 + oseg * 4));
+                xr[ps].x = __uint_as_float(h.x);
+                xr[ps].y = __uint_as_float(h.y);
+              } else {
+                xr[ps] = __ldg(reinterpret_cast<const float4*>(resid + (size_t)row * 128 + c0 + oseg * 4));
+              }
+            }
           }
           tmem_wait_ld();
 #pragma unroll
@@ -459,9 +477,13 @@ __global__ void __launch_bounds__(NTHREADS, 1) mlp_tc_fwd_kernel(const fvgn_mlp_
               if (d.out) *reinterpret_cast<float4*>(d.out + o) = y;
               if (outh) *reinterpret_cast<uint2*>(outh + o) = make_uint2(pack16<P>(y.x, y.y), pack16<P>(y.z, y.w));
               if (do_res) {
-                const float4 x = xr[ps];
+                float4 x = xr[ps];
+                if (resid_h) {
+                  const uint32_t h0 = __float_as_uint(x.x), h1 = __float_as_uint(x.y);
+                  x = make_float4(P::lo(h0), P::hi(h0), P::lo(h1), P::hi(h1));
+                }
                 const float4 t = make_float4(x.x + y.x, x.y + y.y, x.z + y.z, x.w + y.w);
-                *reinterpret_cast<float4*>(d.out_res + o) = t;
+                if (d.out_res) *reinterpret_cast<float4*>(d.out_res + o) = t;
                 if (out_resh) *reinterpret_cast<uint2*>(out_resh + o) = make_uint2(pack16<P>(t.x, t.y), pack16<P>(t.z, t.w));
               }
             }

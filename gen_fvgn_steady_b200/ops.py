@@ -32,6 +32,11 @@ def is_tc(precision):
 NODE_LEVEL_LAYER1 = int(os.environ.get("FVGN_NODE_LEVEL_LAYER1", "2") or 0)
 
 
+# tensor-core modes: 16-bit latent streams between the GnBlocks of a model (GnBlockFn, GN_LATENTS16); FVGN_LATENTS16=0 keeps
+# the fp32 residual streams x / e in HBM (rounded to 16 bit only as MLP operands).
+LATENTS16 = os.environ.get("FVGN_LATENTS16", "1") != "0"
+
+
 def default_precision():
     return os.environ.get("FVGN_PRECISION", "fp32")
 
@@ -270,6 +275,19 @@ def mlp_backward(mode, precision, rows, params, in0, in1, idx_s, idx_r, d_out, d
     return grads
 
 
+GN_KEEP_E, GN_LATENTS16, GN_X_FP32 = 1, 2, 4   # GnBlockFn option bits
+
+
+def placeholder(rows, like):
+    """Stand-in for an fp32 latent stream that is not materialised (16-bit latent streams): a [rows,128] stride-0 view of one
+    NaN -- it carries the autograd edge (its gradient is a real fp32 tensor), never data; reading it is loudly wrong."""
+    return torch.full((1, 1), float("nan"), dtype=torch.float32, device=like.device).expand(rows, 128)
+
+
+def is_placeholder(t):
+    return t is not None and t.dim() == 2 and t.shape[0] > 1 and t.stride() == (0, 0)
+
+
 def _packed(mode, precision, params):
     return PackedWeights.get(mode, params, precision) if is_tc(precision) else None
 
@@ -330,18 +348,24 @@ class EncoderFn(torch.autograd.Function):
     -> (node, edge, node_h, edge_h); the last two are the bf16 shadows (None in fp32 mode)."""
 
     @staticmethod
-    def forward(ctx, xn, pos, plan, precision, *params):
+    def forward(ctx, xn, pos, plan, precision, opts, *params):
         nb, eb = params[:8], params[8:]
         ctx.set_materialize_grads(False)  # no zero tensors for the (non-differentiable) bf16 shadow outputs
         ctx.pk = (_packed(_lib.FVGN_MLP_ENC_NODE, precision, nb), _packed(_lib.FVGN_MLP_ENC_EDGE, precision, eb))
         ctx.z1 = (_z1_for(ctx, _lib.FVGN_MLP_ENC_NODE, precision, plan.N, xn), _z1_for(ctx, _lib.FVGN_MLP_ENC_EDGE, precision, plan.E, xn))
         bf = is_tc(precision)
-        rn = mlp_forward(_lib.FVGN_MLP_ENC_NODE, precision, plan.N, nb, xn, packed=ctx.pk[0], z1=ctx.z1[0], want_outh=bf)
-        re = mlp_forward(_lib.FVGN_MLP_ENC_EDGE, precision, plan.E, eb, xn, pos, plan.edge_s, plan.edge_r, packed=ctx.pk[1],
-                         z1=ctx.z1[1], want_outh=bf)
+        # 16-bit latent streams (GN_LATENTS16, see GnBlockFn): the fp32 latents are not written -- placeholders carry the
+        # gradients -- except the node latent when GN_X_FP32 (TransFVGN adds it as embedding before its Transolver blocks)
+        lat16 = bf and bool(int(opts) & GN_LATENTS16)
+        x32 = not lat16 or bool(int(opts) & GN_X_FP32)
+        rn = mlp_forward(_lib.FVGN_MLP_ENC_NODE, precision, plan.N, nb, xn, want_out=x32, packed=ctx.pk[0], z1=ctx.z1[0],
+                         want_outh=bf)
+        re = mlp_forward(_lib.FVGN_MLP_ENC_EDGE, precision, plan.E, eb, xn, pos, plan.edge_s, plan.edge_r, want_out=not lat16,
+                         packed=ctx.pk[1], z1=ctx.z1[1], want_outh=bf)
         ctx.plan, ctx.precision = plan, precision
         ctx.save_for_backward(xn, pos, *params)
-        node, edge = rn[0], re[0]
+        node = rn[0] if x32 else placeholder(plan.N, xn)
+        edge = re[0] if not lat16 else placeholder(plan.E, xn)
         nodeh, edgeh = (rn[2], re[2]) if bf else (None, None)
         if bf:
             ctx.mark_non_differentiable(nodeh, edgeh)
@@ -360,7 +384,7 @@ class EncoderFn(torch.autograd.Function):
         ge = mlp_backward(_lib.FVGN_MLP_ENC_EDGE, precision, plan.E, params[8:], xn, pos, plan.edge_s, plan.edge_r,
                           _c(d_edge), packed=ctx.pk[1], z1=ctx.z1[1])
         ctx.z1 = None
-        return (None, None, None, None, *gn, *ge)
+        return (None, None, None, None, None, *gn, *ge)
 
 
 # ------------------------------------------------------------------ GnBlock
@@ -371,35 +395,54 @@ class GnBlockFn(torch.autograd.Function):
               x' = MLP_n([a2|x]) ; returns (x + x', e + e', shadows)
     backward: the transposes of the three reductions are the same CSR kernels.
     fp32 mode: the MLPs recompute their hidden activations from the saved block inputs (x, agg, a2, e).
-    bf16 mode: fp32 is kept for the residual streams x / e and their gradients only; agg, e', a2 and the gathered
-              gradients d(agg[s])|d(agg[r]) live as bf16 (what the tensor cores consume anyway); saved for backward are
+    tensor-core modes: fp32 is kept for the GRADIENTS of the residual streams x / e (and, without GN_LATENTS16, for the
+              streams themselves); agg, e', a2 and the gathered gradients d(agg[s])|d(agg[r]) live as 16-bit rows (what the
+              tensor cores consume anyway); saved for backward are
               the bf16 shadows xh, eh, aggh, a2h and the two Z1 tile images."""
 
     @staticmethod
-    def forward(ctx, x, e, xh, eh, plan, precision, keep_e, *params):
+    def forward(ctx, x, e, xh, eh, plan, precision, opts, *params):
         eb, nb = params[:8], params[8:]
-        x, e = _c(x), _c(e)
-        ctx.keep_e = keep_e = bool(keep_e) or not is_tc(precision)
+        opts = int(opts) if is_tc(precision) else GN_KEEP_E
+        ctx.keep_e = keep_e = bool(opts & GN_KEEP_E)
+        # 16-bit latent streams (tensor-core modes, set by the models for their inner blocks): the residual rows are read from
+        # the 16-bit shadows the MLPs consume anyway, e + e' / x + x' leave as 16-bit rows only -- the fp32 rows of both
+        # streams (1 KB per edge and per node, read + written) never touch HBM; x / e and the fp32 outputs are placeholders
+        # that only carry the (fp32) gradients.  GN_X_FP32: x + x' is also written in fp32 (a Transolver block reads it).
+        lat16 = bool(opts & GN_LATENTS16)
+        if lat16:
+            if (xh is None and is_placeholder(x)) or (eh is None and is_placeholder(e)):
+                raise RuntimeError("fvgn_b200: a 16-bit latent stream arrived without its shadow")
+        else:
+            x, e = _c(x), _c(e)
         ctx.set_materialize_grads(False)  # no zero tensors for the (non-differentiable) bf16 shadow outputs
         ctx.pk = (_packed(_lib.FVGN_MLP_EDGE, precision, eb), _packed(_lib.FVGN_MLP_NODE, precision, nb))
         ctx.plan, ctx.precision = plan, precision
         if is_tc(precision):
             BF16 = HDTYPE[precision]
-            xh = xh if (xh is not None and xh.dtype == BF16) else shadow(x, dtype=BF16)
-            eh = eh if (eh is not None and eh.dtype == BF16) else shadow(e, dtype=BF16)
-            ctx.z1 = (_z1_for(ctx, _lib.FVGN_MLP_EDGE, precision, plan.E, x), _z1_for(ctx, _lib.FVGN_MLP_NODE, precision, plan.N, x))
+            xh = xh if (xh is not None and xh.dtype == BF16) else shadow(_c(x), dtype=BF16)
+            eh = eh if (eh is not None and eh.dtype == BF16) else shadow(_c(e), dtype=BF16)
+            ctx.z1 = (_z1_for(ctx, _lib.FVGN_MLP_EDGE, precision, plan.E, xh), _z1_for(ctx, _lib.FVGN_MLP_NODE, precision, plan.N, xh))
             aggh = adj_reduce(xh, plan, 128, out_dtype=BF16)
             # keep_e False (last GnBlock of a model: the decoder / Transolver block read x only): the residual stream
             # e + e' and its shadow are never written, and the backward gets no upstream edge gradient (d_out = NULL)
-            _, e_out, e_newh, e_outh = mlp_forward(_lib.FVGN_MLP_EDGE, precision, plan.E, eb, None, e if keep_e else None,
-                                                   plan.edge_s, plan.edge_r, want_out=False, want_res=keep_e, packed=ctx.pk[0],
+            fl = _lib.FVGN_MLP_RESIDUAL_FROM_SHADOW if lat16 else 0
+            _, e_out, e_newh, e_outh = mlp_forward(_lib.FVGN_MLP_EDGE, precision, plan.E, eb, None,
+                                                   e if (keep_e and not lat16) else None, plan.edge_s, plan.edge_r,
+                                                   want_out=False, want_res=keep_e and not lat16, flags=fl, packed=ctx.pk[0],
                                                    z1=ctx.z1[0], in0h=aggh, in1h=eh, want_outh=True, want_resh=keep_e)
             a1h = inc_reduce(e_newh, plan, 64, out_dtype=BF16)
             del e_newh
             a2h = adj_reduce(a1h, plan, 64, _lib.FVGN_ADJ_DIV_DST_BY_DEG, out_dtype=BF16)
             del a1h
-            _, x_out, _, x_outh = mlp_forward(_lib.FVGN_MLP_NODE, precision, plan.N, nb, None, x, want_out=False, want_res=True,
+            _, x_out, _, x_outh = mlp_forward(_lib.FVGN_MLP_NODE, precision, plan.N, nb, None, None if lat16 else x,
+                                              want_out=False, want_res=(not lat16) or bool(opts & GN_X_FP32), flags=fl,
                                               packed=ctx.pk[1], z1=ctx.z1[1], in0h=a2h, in1h=xh, want_resh=True)
+            if lat16:
+                if x_out is None:
+                    x_out = placeholder(plan.N, xh)
+                if keep_e:
+                    e_out = placeholder(plan.E, xh)
             ctx.save_for_backward(xh, eh, aggh, a2h, *params)
             ctx.mark_non_differentiable(*(t for t in (x_outh, e_outh) if t is not None))
             return x_out, e_out, x_outh, e_outh
@@ -530,7 +573,8 @@ class DecoderFn(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, x, xh, precision, *params):
-        x = _c(x)
+        if not (is_tc(precision) and xh is not None and xh.dtype == HDTYPE[precision]):
+            x = _c(x)   # (a 16-bit latent stream arrives as placeholder + shadow: only the shadow is read)
         ctx.pk = _packed(_lib.FVGN_MLP_DEC, precision, params)
         ctx.z1 = _z1_for(ctx, _lib.FVGN_MLP_DEC, precision, x.shape[0], x)
         ctx.precision = precision

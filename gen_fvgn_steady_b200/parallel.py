@@ -116,6 +116,14 @@ class HaloExchangeFn(torch.autograd.Function):
         return gx, ge, None, None, None
 
 
+def no_ghost_refresh(graph, n_blocks):
+    """True for a whole mesh and for a partitioned sub-mesh whose halo is deep enough (3 n_blocks + 2 layers) that no GnBlock
+    is followed by a ghost refresh: the models then keep their latent streams in 16 bit and drop the last edge latent
+    (halo_refresh exchanges the fp32 rows)."""
+    halo = getattr(graph, "_fvgn_halo", None)
+    return halo is None or halo.world == 1 or not any(halo.wants_exchange(i, n_blocks) for i in range(n_blocks))
+
+
 def halo_refresh(graph, block_index=0, n_blocks=1, group=None):
     """Refresh the ghost rows of graph.x / graph.edge_attr (and of their bf16 shadows) after GnBlock `block_index` of
     `n_blocks`.  No-op when the graph is not a partitioned sub-mesh, or when the halo is deep enough for this block's

@@ -84,6 +84,9 @@ int fvgn_csr_weighted_sum_f64(const void* src, int32_t width, int32_t ld, const 
 #define FVGN_MLP_ENC_EDGE 3 /* importer.py:54-78 + Encoder.eb_encoder EPD.py:119  : in=[xn[s]-xn[r]|dpos|norm], K1=15, LN */
 #define FVGN_MLP_DEC 4      /* Decoder EPD.py:215-219                             : in=x[N,128], K1=128, out=3, no LN    */
 #define FVGN_MLP_NO_RESIDUAL 1 /* desc.flags */
+#define FVGN_MLP_RESIDUAL_FROM_SHADOW 2 /* desc.flags, forward, EDGE / NODE, tensor-core modes ("16-bit latent streams"): the
+                                         * residual row is read from the 16-bit shadow in1h instead of the fp32 stream in1 (in1
+                                         * may be NULL); out_res may be NULL (only out_resh is written) */
 #define FVGN_PREC_FP32 0    /* SIMT fp32 FMA (parity mode, rel 1e-5 vs the reference's CPU fp32)   */
 #define FVGN_PREC_BF16 1    /* tcgen05.mma kind::f16 bf16 operands, fp32 accumulate in TMEM (throughput mode) */
 #define FVGN_PREC_F16 2     /* tcgen05.mma kind::f16 IEEE-half operands: the 11-bit significand of TF32, the arithmetic the

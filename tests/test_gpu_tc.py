@@ -385,3 +385,45 @@ def test_last_block_without_edge_latent_is_identical(prec):
     assert torch.equal(res[0][0], res[1][0])
     for i, (a, b) in enumerate(zip(res[0][1], res[1][1])):
         assert torch.equal(a, b), i
+
+
+@pytest.mark.parametrize("prec,tol", [("f16", 3e-3), ("bf16", 3e-2)])
+def test_16bit_latent_streams_track_fp32_streams(prec, tol):
+    """GnBlockFn with GN_LATENTS16 (what the models pass for their inner blocks): residual rows read from the 16-bit shadows,
+    e + e' / x + x' written as 16-bit rows only, fp32 x / e replaced by placeholders that carry the gradients.  Two chained
+    blocks + decoder against the same chain with fp32 residual streams: outputs and every gradient agree to the rounding of
+    the streams (one 16-bit rounding of the carried state per block); GN_X_FP32 additionally materialises x + x'."""
+    from gen_fvgn_steady_b200 import ops
+    from gen_fvgn_steady_b200.mesh import synthetic
+    from gen_fvgn_steady_b200.plan import GraphPlan
+    from tests.case_inputs import product_graphs
+    dev = torch.device("cuda")
+    mesh, uvp = synthetic.make_case(40, kind="mixed", bc="channel", seed=3)
+    plan = GraphPlan.of(product_graphs([mesh], [uvp], dev)[0])
+    g = torch.Generator(device=dev).manual_seed(13)
+    rn = lambda *s: torch.randn(*s, device=dev, generator=g)
+
+    def mlp(k1, nout=128, ln=True):
+        p = [rn(128, k1) / k1 ** 0.5, 0.1 * rn(128), rn(128, 128) / 128 ** 0.5, 0.1 * rn(128), rn(nout, 128) / 128 ** 0.5,
+             0.1 * rn(nout)]
+        return p + ([1 + 0.1 * rn(128), 0.1 * rn(128)] if ln else [])
+    blocks = [[p.requires_grad_() for p in mlp(384) + mlp(192)] for _ in range(2)]
+    dec = [p.requires_grad_() for p in mlp(128, 3, False)]
+    x0, e0, cot = rn(plan.N, 128), rn(plan.E, 128), rn(plan.N, 3)
+    res = []
+    for lat in (0, ops.GN_LATENTS16):
+        x, e = x0.clone().requires_grad_(), e0.clone().requires_grad_()
+        xa, ea, xh, eh = ops.apply(ops.GnBlockFn, x, e, None, None, plan, prec, ops.GN_KEEP_E | lat, *blocks[0])
+        if lat:
+            assert ops.is_placeholder(xa) and ops.is_placeholder(ea) and xh is not None and eh is not None
+        xb, eb, xh2, _ = ops.apply(ops.GnBlockFn, xa, ea, xh, eh, plan, prec, lat | ops.GN_X_FP32, *blocks[1])
+        assert eb is None and not ops.is_placeholder(xb)
+        assert float((xb - xh2.float()).abs().max()) <= (2e-3 if prec == "f16" else 2e-2) * float(xb.abs().max())
+        out = ops.apply(ops.DecoderFn, xb, xh2, prec, *dec)
+        grads = torch.autograd.grad(out, [x, e] + blocks[0] + blocks[1] + dec, cot)
+        res.append((out.detach(), xh2.float(), grads))
+    torch.cuda.synchronize()
+    rel = lambda a, b: float((a - b).norm() / b.norm().clamp_min(1e-30))
+    assert rel(res[1][0], res[0][0]) < tol and rel(res[1][1], res[0][1]) < tol
+    for i, (a, b) in enumerate(zip(res[1][2], res[0][2])):
+        assert torch.isfinite(a).all() and rel(a, b) < 10 * tol, (i, rel(a, b))
