@@ -1,9 +1,9 @@
 """Transolver_block (src/FVMmodel/Models/GraphTransolver/GraphTransolver.py:25-169) -- SURVEY.md section 8(f) row f1.
 
 Same classes, constructor arguments and state_dict keys as the reference.  The forward is the fused path of ops.py:
-the four dense projections are library GEMMs, everything else (slice softmax, deterministic per-graph token sums,
-de-slice, bias + residual + LayerNorm, bias + GELU, and all their backward passes) are the sm_100a kernels of
-csrc/transolver.cu; only the [B,8,32,16] token attention stays in PyTorch.  No CPU path (the kernels raise on host
+the dense projections are fvgn_gemm_tf32 calls (tensor-core modes; exact fp32 library GEMMs in the parity mode), everything
+else (slice softmax, deterministic per-graph token sums, token attention, de-slice, bias + residual + LayerNorm, bias + GELU,
+and all their backward passes) are the sm_100a kernels of csrc/transolver.cu.  No CPU path (the kernels raise on host
 tensors); the reference's [N,8,32,16] broadcast temporary and its two torch_scatter calls do not exist here."""
 import torch
 from torch import nn

@@ -8,6 +8,7 @@
 //   ts_slice_kernel<true>   in_project_slice + /graph_temperature + softmax (:59-61) and the per-graph token sums
 //                           slice_norm / slice_token (:62-72) as deterministic per-chunk partials
 //   ts_slice_kernel<false>  the same token sum for an arbitrary value tile (backward: d out_slice_token)
+//   ts_token_attention_*    attention among the 32 slice tokens of a (graph, head) (:72-81) and its autograd
 //   ts_deslice_kernel       out_x[n,h,:] = sum_g sw[n,h,g] tok[b(n),h,g,:]   (:83-90)
 //   ts_slice_bwd_kernel     autograd of slice + de-slice w.r.t. the projections, in_project_slice and graph_temperature
 //   ts_res_ln_*             y = a + bias + residual ; z = LayerNorm(y)       (:163-169, to_out bias + ln_2) and backward
@@ -597,6 +598,153 @@ int ts_set_smem(K kern, size_t bytes) {
 
 constexpr int kRowCtas = 148 * 4;  // CTAs of the grid-stride row kernels (also their number of partial rows)
 
+// ----------------------------------------------------------------------------------------------------------------
+// Attention among the slice tokens of one (graph, head) (GraphTransolver.py:72-81): tok = num / (norm + 1e-5),
+// q, k, v = tok Wq^T, tok Wk^T, tok Wv^T (16 x 16, shared by the heads), attn = softmax(q k^T * scale), out = attn v.
+// One 32-thread CTA per (graph, head), thread = token g: its row of the 32 x 32 score matrix lives in registers; k, v (and in
+// the backward q, d out, the score gradients) are exchanged through padded shared-memory tiles.  No shuffles, fixed
+// summation order.  The backward recomputes the forward from the token record.
+constexpr int TA_RS = 17;   // padded row stride of a [32][16] tile
+constexpr int TA_RS2 = 33;  // padded row stride of a [32][32] tile
+
+struct TokAttnFwd {   // what forward and backward both need, per thread (token g)
+  float tok[TS_DH], q[TS_DH], k[TS_DH], v[TS_DH], attn[TS_G], inv;
+};
+
+// rec_b: the token record of this graph [4352]; W*: [16][16] in shared memory; ks / vs: [32][TA_RS] tiles (written here)
+__device__ __forceinline__ void tok_attn_forward(const float* __restrict__ rec_b, int h, int g, const float* Wq, const float* Wk,
+                                                 const float* Wv, float scale, float* ks, float* vs, TokAttnFwd& f) {
+  const float* num = rec_b + ((size_t)h * TS_G + g) * TS_DH;
+  f.inv = 1.0f / (rec_b[TS_TOK + h * TS_G + g] + 1e-5f);
+  for (int i = 0; i < TS_DH; ++i) f.tok[i] = num[i] * f.inv;
+  for (int o = 0; o < TS_DH; ++o) {
+    float aq = 0.f, ak = 0.f, av = 0.f;
+    for (int i = 0; i < TS_DH; ++i) {
+      aq = fmaf(f.tok[i], Wq[o * TS_DH + i], aq);
+      ak = fmaf(f.tok[i], Wk[o * TS_DH + i], ak);
+      av = fmaf(f.tok[i], Wv[o * TS_DH + i], av);
+    }
+    f.q[o] = aq; f.k[o] = ak; f.v[o] = av;
+    ks[g * TA_RS + o] = ak;
+    vs[g * TA_RS + o] = av;
+  }
+  __syncthreads();
+  float m = -INFINITY;
+  for (int j = 0; j < TS_G; ++j) {
+    float d = 0.f;
+    for (int i = 0; i < TS_DH; ++i) d = fmaf(f.q[i], ks[j * TA_RS + i], d);
+    f.attn[j] = d * scale;
+    m = fmaxf(m, f.attn[j]);
+  }
+  float sum = 0.f;
+  for (int j = 0; j < TS_G; ++j) {
+    f.attn[j] = expf(f.attn[j] - m);
+    sum += f.attn[j];
+  }
+  const float rs = 1.0f / sum;
+  for (int j = 0; j < TS_G; ++j) f.attn[j] *= rs;
+}
+
+__global__ void __launch_bounds__(TS_G) ts_token_attention_fwd_kernel(const float* __restrict__ rec, const float* __restrict__ wq,
+                                                                      const float* __restrict__ wk, const float* __restrict__ wv,
+                                                                      float scale, float* __restrict__ out) {
+  __shared__ float Wq[TS_DH * TS_DH], Wk[TS_DH * TS_DH], Wv[TS_DH * TS_DH], ks[TS_G * TA_RS], vs[TS_G * TA_RS];
+  const int g = threadIdx.x, b = blockIdx.x / TS_HEADS, h = blockIdx.x % TS_HEADS;
+  for (int i = g; i < TS_DH * TS_DH; i += TS_G) { Wq[i] = wq[i]; Wk[i] = wk[i]; Wv[i] = wv[i]; }
+  __syncthreads();
+  TokAttnFwd f;
+  tok_attn_forward(rec + (size_t)b * TS_TOKW, h, g, Wq, Wk, Wv, scale, ks, vs, f);
+  float o[TS_DH];
+  for (int i = 0; i < TS_DH; ++i) o[i] = 0.f;
+  for (int j = 0; j < TS_G; ++j)
+    for (int i = 0; i < TS_DH; ++i) o[i] = fmaf(f.attn[j], vs[j * TA_RS + i], o[i]);
+  float* dst = out + (size_t)b * TS_TOK + ((size_t)h * TS_G + g) * TS_DH;
+  for (int i = 0; i < TS_DH; ++i) dst[i] = o[i];
+}
+
+// d_rec[b] = gradient of the token record; wpart[(b, h)] = this CTA's (dWq | dWk | dWv) [3][16][16]
+__global__ void __launch_bounds__(TS_G) ts_token_attention_bwd_kernel(const float* __restrict__ rec, const float* __restrict__ wq,
+                                                                      const float* __restrict__ wk, const float* __restrict__ wv,
+                                                                      float scale, const float* __restrict__ d_out,
+                                                                      float* __restrict__ d_rec, float* __restrict__ wpart) {
+  __shared__ float Wq[TS_DH * TS_DH], Wk[TS_DH * TS_DH], Wv[TS_DH * TS_DH];
+  __shared__ float ks[TS_G * TA_RS], vs[TS_G * TA_RS], qs[TS_G * TA_RS], dos[TS_G * TA_RS], toks[TS_G * TA_RS];
+  __shared__ float dqs[TS_G * TA_RS], dks[TS_G * TA_RS], dvs[TS_G * TA_RS];
+  __shared__ float as_[TS_G * TA_RS2], dss[TS_G * TA_RS2];
+  const int g = threadIdx.x, b = blockIdx.x / TS_HEADS, h = blockIdx.x % TS_HEADS;
+  for (int i = g; i < TS_DH * TS_DH; i += TS_G) { Wq[i] = wq[i]; Wk[i] = wk[i]; Wv[i] = wv[i]; }
+  __syncthreads();
+  TokAttnFwd f;
+  tok_attn_forward(rec + (size_t)b * TS_TOKW, h, g, Wq, Wk, Wv, scale, ks, vs, f);
+  const float* dsrc = d_out + (size_t)b * TS_TOK + ((size_t)h * TS_G + g) * TS_DH;
+  float dO[TS_DH];
+  for (int i = 0; i < TS_DH; ++i) {
+    dO[i] = dsrc[i];
+    dos[g * TA_RS + i] = dO[i];
+    qs[g * TA_RS + i] = f.q[i];
+    toks[g * TA_RS + i] = f.tok[i];
+  }
+  // d attn[g][j] = dO[g] . v[j]; softmax backward; d dots = scale * attn * (d attn - sum_j attn d attn)
+  float da[TS_G], dot = 0.f;
+  for (int j = 0; j < TS_G; ++j) {
+    float d = 0.f;
+    for (int i = 0; i < TS_DH; ++i) d = fmaf(dO[i], vs[j * TA_RS + i], d);
+    da[j] = d;
+    dot = fmaf(f.attn[j], d, dot);
+  }
+  float dq[TS_DH];
+  for (int i = 0; i < TS_DH; ++i) dq[i] = 0.f;
+  for (int j = 0; j < TS_G; ++j) {
+    const float ds = scale * f.attn[j] * (da[j] - dot);
+    as_[g * TA_RS2 + j] = f.attn[j];
+    dss[g * TA_RS2 + j] = ds;
+    for (int i = 0; i < TS_DH; ++i) dq[i] = fmaf(ds, ks[j * TA_RS + i], dq[i]);
+  }
+  __syncthreads();
+  // thread g now acts as key / value token j = g:  dk[j] = sum_g' ds[g'][j] q[g'],  dv[j] = sum_g' attn[g'][j] dO[g']
+  float dk[TS_DH], dv[TS_DH];
+  for (int i = 0; i < TS_DH; ++i) { dk[i] = 0.f; dv[i] = 0.f; }
+  for (int r = 0; r < TS_G; ++r) {
+    const float ds = dss[r * TA_RS2 + g], a = as_[r * TA_RS2 + g];
+    for (int i = 0; i < TS_DH; ++i) {
+      dk[i] = fmaf(ds, qs[r * TA_RS + i], dk[i]);
+      dv[i] = fmaf(a, dos[r * TA_RS + i], dv[i]);
+    }
+  }
+  // d tok[g][i] = sum_o dq[o] Wq[o][i] + dk[o] Wk[o][i] + dv[o] Wv[o][i]; then through tok = num / (norm + eps)
+  float dn = 0.f;
+  float* drow = d_rec + (size_t)b * TS_TOKW + ((size_t)h * TS_G + g) * TS_DH;
+  for (int i = 0; i < TS_DH; ++i) {
+    float t = 0.f;
+    for (int o = 0; o < TS_DH; ++o)
+      t = fmaf(dq[o], Wq[o * TS_DH + i], fmaf(dk[o], Wk[o * TS_DH + i], fmaf(dv[o], Wv[o * TS_DH + i], t)));
+    drow[i] = t * f.inv;
+    dn = fmaf(t, f.tok[i], dn);
+  }
+  d_rec[(size_t)b * TS_TOKW + TS_TOK + h * TS_G + g] = -dn * f.inv;
+  for (int i = 0; i < TS_DH; ++i) {
+    dqs[g * TA_RS + i] = dq[i];
+    dks[g * TA_RS + i] = dk[i];
+    dvs[g * TA_RS + i] = dv[i];
+  }
+  __syncthreads();
+  // weight gradients of this (graph, head): dW[o][i] = sum_g d{q,k,v}[g][o] tok[g][i]; 8 of the 256 entries per thread
+  float* wp = wpart + (size_t)blockIdx.x * (3 * TS_DH * TS_DH);
+  for (int e = g; e < TS_DH * TS_DH; e += TS_G) {
+    const int o = e / TS_DH, i = e % TS_DH;
+    float sq = 0.f, sk = 0.f, sv = 0.f;
+    for (int r = 0; r < TS_G; ++r) {
+      const float t = toks[r * TA_RS + i];
+      sq = fmaf(dqs[r * TA_RS + o], t, sq);
+      sk = fmaf(dks[r * TA_RS + o], t, sk);
+      sv = fmaf(dvs[r * TA_RS + o], t, sv);
+    }
+    wp[e] = sq;
+    wp[TS_DH * TS_DH + e] = sk;
+    wp[2 * TS_DH * TS_DH + e] = sv;
+  }
+}
+
 }  // namespace
 
 extern "C" int fvgn_ts_row_partials(int64_t n) {
@@ -625,6 +773,25 @@ extern "C" int fvgn_ts_accumulate(const float* sw, const float* V, const int32_t
   if (ts_set_smem(kern, SliceSmem<false>::bytes) != FVGN_OK) return FVGN_ERR_LAUNCH;
   FVGN_LAUNCH(kern, (unsigned)nchunks, TS_NT, SliceSmem<false>::bytes, stream, V, const_cast<float*>(sw), (const float*)nullptr,
               (const float*)nullptr, (const float*)nullptr, chunks, partial);
+  FVGN_CHECK_LAUNCH();
+  return FVGN_OK;
+}
+
+extern "C" int fvgn_ts_token_attention_forward(const float* rec, const float* wq, const float* wk, const float* wv, float scale,
+                                               int32_t nb, float* tok_out, void* stream) {
+  if (nb <= 0) return FVGN_OK;
+  if (!rec || !wq || !wk || !wv || !tok_out) return FVGN_ERR_NULL;
+  FVGN_LAUNCH(ts_token_attention_fwd_kernel, (unsigned)(nb * TS_HEADS), TS_G, 0, stream, rec, wq, wk, wv, scale, tok_out);
+  FVGN_CHECK_LAUNCH();
+  return FVGN_OK;
+}
+
+extern "C" int fvgn_ts_token_attention_backward(const float* rec, const float* wq, const float* wk, const float* wv, float scale,
+                                                int32_t nb, const float* d_tok_out, float* d_rec, float* w_partial, void* stream) {
+  if (nb <= 0) return FVGN_OK;
+  if (!rec || !wq || !wk || !wv || !d_tok_out || !d_rec || !w_partial) return FVGN_ERR_NULL;
+  FVGN_LAUNCH(ts_token_attention_bwd_kernel, (unsigned)(nb * TS_HEADS), TS_G, 0, stream, rec, wq, wk, wv, scale, d_tok_out, d_rec,
+              w_partial);
   FVGN_CHECK_LAUNCH();
   return FVGN_OK;
 }

@@ -938,15 +938,30 @@ def _ptr01(npart, device):
 
 
 def _token_attention(rec, wq, wk, wv, scale):
-    """GraphTransolver.py:72-81 on the [nb, 4352] token record (numerators | norms) -> attended tokens [nb, 4096].
-    [B,8,32,16]-sized glue: stays in PyTorch (also differentiated by PyTorch inside SliceAttentionFn.backward)."""
+    """GraphTransolver.py:72-81 on the [nb, 4352] token record (numerators | norms) -> attended tokens [nb, 4096]
+    (csrc/transolver.cu: ts_token_attention_fwd_kernel, one CTA per (graph, head))."""
+    rec = _c(rec)
     nb = rec.shape[0]
-    num = rec[:, :TS_TOK].reshape(nb, TS_HEADS, TS_G, TS_DH)
-    norm = rec[:, TS_TOK:].reshape(nb, TS_HEADS, TS_G)
-    tok = num / (norm.unsqueeze(-1) + 1e-5)
-    q, k, v = tok @ wq.t(), tok @ wk.t(), tok @ wv.t()
-    attn = torch.softmax(torch.matmul(q, k.transpose(-1, -2)) * scale, dim=-1)
-    return torch.matmul(attn, v).reshape(nb, TS_TOK)
+    out = _empty((nb, TS_TOK), rec)
+    _lib.call("fvgn_ts_token_attention_forward", fptr(rec), fptr(_c(wq.detach())), fptr(_c(wk.detach())), fptr(_c(wv.detach())),
+              float(scale), nb, fptr(out), _lib.stream_ptr(rec.device))
+    return out
+
+
+def _token_attention_backward(rec, wq, wk, wv, scale, d_tok_out):
+    """-> (d_rec [nb,4352], d_wq, d_wk, d_wv): the forward is recomputed from the token record; the weight gradients are
+    per-(graph, head) partials summed in fixed order."""
+    rec, d_tok_out = _c(rec), _c(d_tok_out)
+    nb = rec.shape[0]
+    d_rec = _empty((nb, _lib.FVGN_TS_TOKW), rec)
+    part = _empty((max(nb * TS_HEADS, 1), 3 * TS_DH * TS_DH), rec)
+    _lib.call("fvgn_ts_token_attention_backward", fptr(rec), fptr(_c(wq.detach())), fptr(_c(wk.detach())), fptr(_c(wv.detach())),
+              float(scale), nb, fptr(d_tok_out), fptr(d_rec), fptr(part), _lib.stream_ptr(rec.device))
+    if nb > 0:
+        g = _combine(part, 3 * TS_DH * TS_DH, _ptr01(nb * TS_HEADS, rec.device), 1).reshape(3, TS_DH, TS_DH)
+    else:
+        g = torch.zeros((3, TS_DH, TS_DH), device=rec.device)
+    return d_rec, g[0], g[1], g[2]
 
 
 def _attn_forward(x, wfx, bfx, wx, bx, ws, bs, temp, wq, wk, wv, wo, scale, tsp, halo, tc=False):
@@ -987,10 +1002,7 @@ def _attn_backward(saved, d_a, scale, tsp, halo, d_res=None, tc=False):
         extra = acc[tsp.nb:]
         d_tok_out = d_tok_out.clone()
         d_tok_out[:extra.shape[0]] += extra
-    with torch.enable_grad():
-        leaves = [t.detach().requires_grad_(True) for t in (rec, wq, wk, wv)]
-        ot = _token_attention(leaves[0], leaves[1], leaves[2], leaves[3], scale)
-        d_rec, d_wq, d_wk, d_wv = torch.autograd.grad(ot, leaves, d_tok_out)
+    d_rec, d_wq, d_wk, d_wv = _token_attention_backward(rec, wq, wk, wv, scale, d_tok_out)
     if halo is not None:
         from .parallel import allreduce_sum_
         d_rec = allreduce_sum_(d_rec.contiguous())
@@ -1056,8 +1068,8 @@ def _tail_backward(saved, d_out, tc=False):
 
 class SliceAttentionFn(torch.autograd.Function):
     """Graph_Physics_Attention_1D.graph_forward (GraphTransolver.py:48-95) without the to_out bias:
-    x[N,128] -> to_out.weight @ deslice(attention(slice(x))).  Projections are library GEMMs; slice softmax, token sums,
-    de-slice and their autograd are the ts_* kernels; the [B,8,32,16] token attention is PyTorch glue."""
+    x[N,128] -> to_out.weight @ deslice(attention(slice(x))).  Projections: fvgn_gemm_tf32 (tensor-core modes) or fp32 library
+    GEMMs (parity mode); slice softmax, token sums, token attention, de-slice and their autograd are the ts_* kernels."""
 
     @staticmethod
     def forward(ctx, x, wfx, bfx, wx, bx, ws, bs, temp, wq, wk, wv, wo, scale, tsp, halo, precision=None):
@@ -1076,7 +1088,8 @@ class TransolverBlockFn(torch.autograd.Function):
     """Transolver_block.forward with in_layernorm=False (GraphTransolver.py:163-169) as ONE autograd node:
         fx = xa (+ xb) ; y = graph_forward(fx) + fx ; out = mlp(ln_2(y)) + y      (+ bf16 shadow of out)
     xb is the node embedding the TransFVGN processors add before the block (TransFVGN_v1.py:70, TransFVGN_v2.py:49).
-    Library GEMMs for the five dense projections; everything else are the ts_* kernels; the residual gradient enters the
+    fvgn_gemm_tf32 (tensor-core modes) / fp32 library GEMMs (parity mode) for the five dense projections; everything else are
+    the ts_* kernels; the residual gradient enters the
     last backward GEMM as its accumulator, so no separate gradient-accumulation passes remain."""
 
     @staticmethod

@@ -267,6 +267,13 @@ int fvgn_ts_slice_forward(const float* P, const float* Ws, const float* bs, cons
                           int32_t nchunks, float* sw, float* partial, void* stream);
 /* partial[nchunks,4352] = per-chunk sums of sw (x) V | sw for V[N,128] (backward of the de-slice w.r.t. the tokens) */
 int fvgn_ts_accumulate(const float* sw, const float* V, const int32_t* chunks, int32_t nchunks, float* partial, void* stream);
+/* attention among the slice tokens (:72-81): rec[nb,4352] = token record (numerators | norms) -> tok_out[nb,4096]
+ * = softmax(q k^T * scale) v per (graph, head), q / k / v = tok W{q,k,v}^T with tok = num / (norm + 1e-5); wq / wk / wv [16,16] */
+int fvgn_ts_token_attention_forward(const float* rec, const float* wq, const float* wk, const float* wv, float scale, int32_t nb,
+                                    float* tok_out, void* stream);
+/* its autograd: d_rec[nb,4352]; w_partial[nb*8, 768] = per (graph, head) dWq | dWk | dWv, summed by fvgn_chunk_combine */
+int fvgn_ts_token_attention_backward(const float* rec, const float* wq, const float* wk, const float* wv, float scale, int32_t nb,
+                                     const float* d_tok_out, float* d_rec, float* w_partial, void* stream);
 /* out[n, h*16+d] = sum_g sw[n,h,g] tok[graph % tok_mod, h, g, d]  (:83-90); tok rows are tok_ld floats apart */
 int fvgn_ts_deslice(const float* sw, const float* tok, int64_t tok_ld, int32_t tok_mod, const int32_t* chunks, int32_t nchunks,
                     float* out, void* stream);

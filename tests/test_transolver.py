@@ -229,3 +229,35 @@ def test_ts_plan_chunk_table(sizes):
     if len(sizes) > 1 and sizes[0] > 0 and sizes[1] > 0:
         with pytest.raises(RuntimeError):
             ops.TsPlan(torch.flip(batch, [0]))
+
+
+@pytest.mark.parametrize("nb", [1, 3])
+def test_token_attention_kernels_match_autograd(nb):
+    """fvgn_ts_token_attention_forward / _backward (GraphTransolver.py:72-81: tok = num / (norm + 1e-5), q k v projections
+    shared by the heads, softmax(q k^T scale) v) through the CPU emulator against the same expression differentiated by
+    torch autograd in fp64."""
+    from tests import product_util as PU
+    from gen_fvgn_steady_b200 import ops
+    PU.use_emulated_kernels()
+    try:
+        g = torch.Generator().manual_seed(3)
+        num = torch.randn(nb, 4096, generator=g)
+        norm = torch.rand(nb, 256, generator=g) * 5 + 0.1
+        rec = torch.cat([num, norm], 1)
+        ws = [torch.randn(16, 16, generator=g) / 4 for _ in range(3)]
+        cot = torch.randn(nb, 4096, generator=g)
+        scale = 16 ** -0.5
+        out = ops._token_attention(rec, *ws, scale)
+        d_rec, d_wq, d_wk, d_wv = ops._token_attention_backward(rec, *ws, scale, cot)
+        leaves = [t.double().requires_grad_() for t in (rec, *ws)]
+        r, wq, wk, wv = leaves
+        tok = r[:, :4096].reshape(nb, 8, 32, 16) / (r[:, 4096:].reshape(nb, 8, 32, 1) + 1e-5)
+        q, k, v = tok @ wq.t(), tok @ wk.t(), tok @ wv.t()
+        ref = (torch.softmax(q @ k.transpose(-1, -2) * scale, -1) @ v).reshape(nb, 4096)
+        grads = torch.autograd.grad(ref, leaves, cot.double())
+    finally:
+        PU.use_real_kernels()
+    rel = lambda a, b: float((a.double() - b).norm() / b.norm())
+    assert rel(out, ref) < 1e-6
+    for a, b in zip((d_rec, d_wq, d_wk, d_wv), grads):
+        assert rel(a, b) < 1e-5, rel(a, b)
