@@ -10,7 +10,7 @@ mode = sys.argv[2] if len(sys.argv) > 2 else "EDGE"
 lib = ctypes.CDLL(_lib.LIB_PATH)
 buf = (ctypes.c_ulonglong * 16)()
 import runpy
-sys.argv = ["tc_profile.py", rows, mode, "bf16"]
+sys.argv = ["tc_profile.py", rows, mode, sys.argv[3] if len(sys.argv) > 3 else "f16"]
 runpy.run_path(os.path.join(os.path.dirname(os.path.abspath(__file__)), "tc_profile.py"), run_name="__main__")
 torch.cuda.synchronize()
 lib2 = _lib.load()

@@ -37,8 +37,10 @@ bf = ops.is_tc(prec)
 hdt = ops.HDTYPE.get(prec)
 in0h, in1h = (ops.shadow(in0, dtype=hdt), ops.shadow(in1, dtype=hdt)) if bf else (None, None)
 d_in0h = torch.empty((rows, 256), dtype=hdt, device=dev) if (bf and mode == "EDGE") else None
-fwd = lambda: ops.mlp_forward(code, prec, rows, params, in0, in1, s, r, want_out=not bf, want_res=True, z1=z1, in0h=in0h,
-                              in1h=in1h, want_outh=bf and mode == "EDGE", want_resh=bf)
+res16 = bf and os.environ.get("FVGN_TC_PROFILE_RES16", "1") != "0"   # 16-bit latent streams (the models' default)
+fwd = lambda: ops.mlp_forward(code, prec, rows, params, in0, None if res16 else in1, s, r, want_out=not bf, want_res=not res16,
+                              z1=z1, in0h=in0h, in1h=in1h, want_outh=bf and mode == "EDGE", want_resh=bf,
+                              flags=_lib.FVGN_MLP_RESIDUAL_FROM_SHADOW if res16 else 0)
 bwd = lambda: ops.mlp_backward(code, prec, rows, params, in0, in1, s, r, d_out, d_gather, None if d_in0h is not None else d_in0,
                                d_in1, z1=z1, in0h=in0h, in1h=in1h, d_in0h=d_in0h)
 for _ in range(2):
