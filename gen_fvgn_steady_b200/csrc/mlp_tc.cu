@@ -422,6 +422,16 @@ __global__ void __launch_bounds__(NTHREADS, 1) mlp_tc_fwd_kernel(const fvgn_mlp_
         }
         uint16_t* outh = reinterpret_cast<uint16_t*>(d.outh);
         uint16_t* out_resh = reinterpret_cast<uint16_t*>(d.out_resh);
+        // The normalisation is applied AFTER the transposition through the staging tile: in the write-out mapping a lane owns 4
+        // fixed columns of 8 rows, so gamma / beta / b3 are three 16-byte reads per 32-column group (instead of 24 in the
+        // thread-per-row mapping) and the accumulator chunk leaves its registers at once; the statistics of the 8 rows a lane
+        // serves are fetched once per tile.  Same operations in the same order per element: results unchanged.
+        float nmr[8], rsr[8];
+#pragma unroll
+        for (int ps = 0; ps < 8; ++ps) {
+          nmr[ps] = -__shfl_sync(0xffffffffu, mean, ps * 4 + orow);
+          rsr[ps] = __shfl_sync(0xffffffffu, rstd, ps * 4 + orow);
+        }
 #pragma unroll 1
         for (int c0 = 0; c0 < 128; c0 += 32) {
           uint32_t r[32];
@@ -442,37 +452,36 @@ __global__ void __launch_bounds__(NTHREADS, 1) mlp_tc_fwd_kernel(const fvgn_mlp_
               }
             }
           }
+          const float4 b = *reinterpret_cast<const float4*>(sb3 + c0 + oseg * 4);
+          const float4 gm = *reinterpret_cast<const float4*>(sg + c0 + oseg * 4);
+          const float4 bt = *reinterpret_cast<const float4*>(sbeta + c0 + oseg * 4);
           tmem_wait_ld();
 #pragma unroll
-          for (int j = 0; j < 32; j += 4) {
-            const float4 b = *reinterpret_cast<const float4*>(sb3 + c0 + j);
-            const float4 gm = *reinterpret_cast<const float4*>(sg + c0 + j);
-            const float4 bt = *reinterpret_cast<const float4*>(sbeta + c0 + j);
-            float4 y;
-#if FVGN_F32X2
-            {  // ((acc + b) - mean) * rstd * gamma + beta, same operation order as the scalar form
-              const float2 nm = splat2(-mean), rs = splat2(rstd);
-              const float2 ya = __ffma2_rn(__fmul2_rn(__fadd2_rn(__fadd2_rn(f2u(r[j], r[j + 1]), make_float2(b.x, b.y)), nm), rs),
-                                           make_float2(gm.x, gm.y), make_float2(bt.x, bt.y));
-              const float2 yb = __ffma2_rn(__fmul2_rn(__fadd2_rn(__fadd2_rn(f2u(r[j + 2], r[j + 3]), make_float2(b.z, b.w)), nm), rs),
-                                           make_float2(gm.z, gm.w), make_float2(bt.z, bt.w));
-              y = make_float4(ya.x, ya.y, yb.x, yb.y);
-            }
-#else
-            y.x = (__uint_as_float(r[j + 0]) + b.x - mean) * rstd * gm.x + bt.x;
-            y.y = (__uint_as_float(r[j + 1]) + b.y - mean) * rstd * gm.y + bt.y;
-            y.z = (__uint_as_float(r[j + 2]) + b.z - mean) * rstd * gm.z + bt.z;
-            y.w = (__uint_as_float(r[j + 3]) + b.w - mean) * rstd * gm.w + bt.w;
-#endif
-            *reinterpret_cast<float4*>(wstg_at(mystg, lane, j >> 2)) = y;
-          }
+          for (int j = 0; j < 32; j += 4)
+            *reinterpret_cast<uint4*>(wstg_at(mystg, lane, j >> 2)) = make_uint4(r[j], r[j + 1], r[j + 2], r[j + 3]);
           __syncwarp();
 #pragma unroll
           for (int ps = 0; ps < 8; ++ps) {
             const int rr = ps * 4 + orow;
             const int64_t row = wrow0 + rr;
             if (row < d.rows) {
-              const float4 y = *reinterpret_cast<const float4*>(wstg_at(mystg, rr, oseg));
+              const float4 a = *reinterpret_cast<const float4*>(wstg_at(mystg, rr, oseg));
+              float4 y;
+#if FVGN_F32X2
+              {  // ((acc + b) - mean) * rstd * gamma + beta, same operation order as the scalar form
+                const float2 nm = splat2(nmr[ps]), rs = splat2(rsr[ps]);
+                const float2 ya = __ffma2_rn(__fmul2_rn(__fadd2_rn(__fadd2_rn(make_float2(a.x, a.y), make_float2(b.x, b.y)), nm), rs),
+                                             make_float2(gm.x, gm.y), make_float2(bt.x, bt.y));
+                const float2 yb = __ffma2_rn(__fmul2_rn(__fadd2_rn(__fadd2_rn(make_float2(a.z, a.w), make_float2(b.z, b.w)), nm), rs),
+                                             make_float2(gm.z, gm.w), make_float2(bt.z, bt.w));
+                y = make_float4(ya.x, ya.y, yb.x, yb.y);
+              }
+#else
+              y.x = (a.x + b.x + nmr[ps]) * rsr[ps] * gm.x + bt.x;
+              y.y = (a.y + b.y + nmr[ps]) * rsr[ps] * gm.y + bt.y;
+              y.z = (a.z + b.z + nmr[ps]) * rsr[ps] * gm.z + bt.z;
+              y.w = (a.w + b.w + nmr[ps]) * rsr[ps] * gm.w + bt.w;
+#endif
               const size_t o = (size_t)row * 128 + c0 + oseg * 4;
               if (d.out) *reinterpret_cast<float4*>(d.out + o) = y;
               if (outh) *reinterpret_cast<uint2*>(outh + o) = make_uint2(pack16<P>(y.x, y.y), pack16<P>(y.z, y.w));
