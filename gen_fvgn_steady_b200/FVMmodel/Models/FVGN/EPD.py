@@ -64,10 +64,11 @@ class Encoder(nn.Module):
         latents_16bit / x_fp32: as GnBlock.forward (passed by the models; tensor-core modes only)."""
         plan = GraphPlan.of(graph_node)
         opts = (ops.GN_LATENTS16 if latents_16bit and ops.LATENTS16 else 0) | (ops.GN_X_FP32 if x_fp32 else 0)
+        ch = ops.GradChannel()   # 16-bit gradient rows of the placeholder latents come back through it (f16 mode)
         node_, edge_, nh, eh = ops.apply(ops.EncoderFn, graph_node.x.contiguous(), graph_node.pos.float().contiguous(), plan,
-                                         _precision(self), opts, *mlp_params(self.nb_encoder), *mlp_params(self.eb_encoder))
+                                         _precision(self), opts, ch, *mlp_params(self.nb_encoder), *mlp_params(self.eb_encoder))
         # bf16 mode: the kernels also emit bf16 shadows of the latents; they travel with the graph as (master, shadow)
-        return _carry(graph_node, x=node_, edge_attr=edge_, _fvgn_plan=plan, _xh=(node_, nh), _eh=(edge_, eh)), node_
+        return _carry(graph_node, x=node_, edge_attr=edge_, _fvgn_plan=plan, _xh=(node_, nh), _eh=(edge_, eh), _gch=ch), node_
 
 
 class GnBlock(nn.Module):
@@ -89,9 +90,10 @@ class GnBlock(nn.Module):
         xh, eh = _shadow_of(graph_node, "_xh", graph_node.x), _shadow_of(graph_node, "_eh", graph_node.edge_attr)
         opts = (ops.GN_KEEP_E if keep_edge_latent else 0) | (ops.GN_LATENTS16 if latents_16bit and ops.LATENTS16 else 0) | \
                (ops.GN_X_FP32 if x_fp32 else 0)
+        ch_in, ch_out = getattr(graph_node, "_gch", None), ops.GradChannel()
         x, e, xh, eh = ops.apply(ops.GnBlockFn, graph_node.x, graph_node.edge_attr, xh, eh, plan, _precision(self),
-                                 opts, *mlp_params(self.eb_module.net), *mlp_params(self.nb_module.net))
-        return _carry(graph_node, x=x, edge_attr=e, _fvgn_plan=plan, _xh=(x, xh), _eh=(e, eh))
+                                 opts, ch_in, ch_out, *mlp_params(self.eb_module.net), *mlp_params(self.nb_module.net))
+        return _carry(graph_node, x=x, edge_attr=e, _fvgn_plan=plan, _xh=(x, xh), _eh=(e, eh), _gch=ch_out)
 
 
 class Decoder(nn.Module):

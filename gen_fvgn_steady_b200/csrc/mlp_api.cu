@@ -143,8 +143,12 @@ extern "C" int fvgn_mlp_backward(const fvgn_mlp_desc* d, void* stream) {
   if (rc) return rc;
   // d_out == NULL: EDGE, tensor-core modes only -- the block's outputs e' / e + e' have no consumer but the node block
   // (last GnBlock of a processor): the upstream gradient is the gathered d_a1 alone
-  const bool dead_out = !d->d_out && d->mode == FVGN_MLP_EDGE && is_tc(d->precision) && (d->d_gather || d->d_gatherh);
-  if ((!d->d_out && !dead_out) || !d->partials || !d->d_params || d->n_partials < 1) return FVGN_ERR_NULL;
+  const bool grad16 = d->d_outh || d->d_in1h;   // 16-bit gradient streams: tensor-core modes, blocks with LayerNorm
+  if (grad16 && (!is_tc(d->precision) || d->mode == FVGN_MLP_DEC)) return FVGN_ERR_UNSUPPORTED;
+  if (d->d_in1h && d->mode != FVGN_MLP_EDGE && d->mode != FVGN_MLP_NODE) return FVGN_ERR_UNSUPPORTED;
+  if (!fvgn_aligned16(d->d_outh) || !fvgn_aligned16(d->d_in1h)) return FVGN_ERR_ALIGN;
+  const bool dead_out = !d->d_out && !d->d_outh && d->mode == FVGN_MLP_EDGE && is_tc(d->precision) && (d->d_gather || d->d_gatherh);
+  if ((!d->d_out && !d->d_outh && !dead_out) || !d->partials || !d->d_params || d->n_partials < 1) return FVGN_ERR_NULL;
   const bool node_path = d->d_aggh != nullptr;   // EDGE, tensor-core modes: node-level layer-1 backward
   if (node_path) {
     if (d->mode != FVGN_MLP_EDGE || !is_tc(d->precision)) return FVGN_ERR_UNSUPPORTED;
@@ -152,7 +156,8 @@ extern "C" int fvgn_mlp_backward(const fvgn_mlp_desc* d, void* stream) {
     if (d->n_nodes < 1 || d->n_node_partials != fvgn_mlp_bwd_node_partials(d->n_nodes)) return FVGN_ERR_SHAPE;
     if (!fvgn_aligned16(d->d_aggh) || ((uintptr_t)d->node_ws & 1023)) return FVGN_ERR_ALIGN;
   }
-  if ((d->mode == FVGN_MLP_EDGE || d->mode == FVGN_MLP_NODE) && ((!d->d_in0 && !d->d_in0h && !node_path) || !d->d_in1)) return FVGN_ERR_NULL;
+  if ((d->mode == FVGN_MLP_EDGE || d->mode == FVGN_MLP_NODE) && ((!d->d_in0 && !d->d_in0h && !node_path) || (!d->d_in1 && !d->d_in1h)))
+    return FVGN_ERR_NULL;
   if ((d->d_in0h || d->d_gatherh) && !is_tc(d->precision)) return FVGN_ERR_UNSUPPORTED;
   if (d->d_in0h && d->mode != FVGN_MLP_EDGE && d->mode != FVGN_MLP_NODE) return FVGN_ERR_UNSUPPORTED;
   if (!fvgn_aligned16(d->d_gatherh)) return FVGN_ERR_ALIGN;

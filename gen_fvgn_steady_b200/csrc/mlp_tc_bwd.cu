@@ -264,13 +264,46 @@ __global__ void __launch_bounds__(A_THREADS, 1) mlp_tc_bwd_a_kernel(const fvgn_m
         // rows i0 .. i0+NR-1 of this thread's 8 (tile rows i*16 + pw*4 + lane/8), 64-column block kb -> packed bf16
         auto load_pack = [&](int kb, int i0, auto nr_tag, uint4* out) {
           constexpr int NR = decltype(nr_tag)::value;
+          if (d.d_outh && (!gath || d.d_gatherh)) {
+            // 16-bit gradient stream: the rows are the operand format already -- no conversion at all; the gathered d_a1 rows
+            // are added as packed pairs (one rounding: both addends are 16-bit values)
+#pragma unroll
+            for (int j = 0; j < NR; ++j) {
+              const int64_t row = row0 + (i0 + j) * 16 + pw * 4 + (lane >> 3);
+              out[j] = make_uint4(0u, 0u, 0u, 0u);
+              if (row < d.rows)
+                out[j] = __ldg(reinterpret_cast<const uint4*>(reinterpret_cast<const uint8_t*>(d.d_outh) + (size_t)row * 256 + kb * 128 +
+                                                              seg * 16));
+            }
+            if (gath) {
+              uint4 gv[NR];
+#pragma unroll
+              for (int j = 0; j < NR; ++j) {
+                const int64_t row = row0 + (i0 + j) * 16 + pw * 4 + (lane >> 3);
+                const int gi = kb == 0 ? idx.sender(i0 + j, lane) : idx.receiver(i0 + j, lane);
+                gv[j] = make_uint4(0u, 0u, 0u, 0u);
+                if (row < d.rows)
+                  gv[j] = __ldg(reinterpret_cast<const uint4*>(reinterpret_cast<const uint8_t*>(d.d_gatherh) + (size_t)gi * 128 + seg * 16));
+              }
+#pragma unroll
+              for (int j = 0; j < NR; ++j)
+                out[j] = make_uint4(P::add2(out[j].x, gv[j].x), P::add2(out[j].y, gv[j].y), P::add2(out[j].z, gv[j].z),
+                                    P::add2(out[j].w, gv[j].w));
+            }
+            return;
+          }
           float4 lo[NR], hi[NR];
 #pragma unroll
           for (int j = 0; j < NR; ++j) {
             const int64_t row = row0 + (i0 + j) * 16 + pw * 4 + (lane >> 3);
             lo[j] = make_float4(0.f, 0.f, 0.f, 0.f);
             hi[j] = lo[j];
-            if (row < d.rows && d.d_out) {   // d_out == NULL (EDGE): no upstream gradient but the gathered d_a1
+            if (row < d.rows && d.d_outh) {   // 16-bit gradient stream with an fp32 d_gather (stand-alone use)
+              const uint4 w = __ldg(reinterpret_cast<const uint4*>(reinterpret_cast<const uint8_t*>(d.d_outh) + (size_t)row * 256 +
+                                                                   kb * 128 + seg * 16));
+              lo[j] = make_float4(P::lo(w.x), P::hi(w.x), P::lo(w.y), P::hi(w.y));
+              hi[j] = make_float4(P::lo(w.z), P::hi(w.z), P::lo(w.w), P::hi(w.w));
+            } else if (row < d.rows && d.d_out) {   // neither (EDGE): no upstream gradient but the gathered d_a1
               const float* p = d.d_out + (size_t)row * 128 + kb * 64 + seg * 8;
               lo[j] = __ldg(reinterpret_cast<const float4*>(p));
               hi[j] = __ldg(reinterpret_cast<const float4*>(p + 4));
@@ -687,7 +720,10 @@ constexpr int STG_BYTES = 4 * WSTG_BYTES;  // one wide staging tile per epilogue
 // mlp_tc_bwd_node.cu): only the e columns 256..383 -- dW1[:, 256:384] += dZ1^T e, d_e = dZ1 W1[:, 256:384] (+ residual
 // gradient); the agg[s] | agg[r] columns are differentiated per node by mlp_tc_bwd_node_kernel, so no gathered operand
 // chunks, no [E,256] gradient stream.
-template <int MODE, class P, int KB0>
+// GS: gradient streams of the residual path.  0 = fp32 in (d_out), fp32 out (d_in1); 1 = 16-bit in (d_outh), 16-bit out
+// (d_in1h); 2 = decided at run time (mixed: the first / last block of a 16-bit chain).  Compile-time for the two pure cases so
+// that the residual-row loads of the write-out keep their single predicated form (batched ahead of the accumulator wait).
+template <int MODE, class P, int KB0, int GS = 0>
 __global__ void __launch_bounds__(NTHREADS, 1) mlp_tc_bwd_b_kernel(const fvgn_mlp_desc d) {
   using C = BCfg<MODE>;
   constexpr uint32_t IDESC_MM64 = make_idesc(P::FMT, 64, 1, 1), IDESC_KM64 = make_idesc(P::FMT, 64, 0, 1);
@@ -711,7 +747,9 @@ __global__ void __launch_bounds__(NTHREADS, 1) mlp_tc_bwd_b_kernel(const fvgn_ml
   float* Pw1 = d.partials + (size_t)blockIdx.x * PC;
   const uint8_t* dz_img = reinterpret_cast<const uint8_t*>(d.workspace);
   const uint8_t* w_img = reinterpret_cast<const uint8_t*>(d.w_bf16);
-  const bool resid = !(d.flags & FVGN_MLP_NO_RESIDUAL) && d.d_out != nullptr;
+  const bool in16 = GS == 2 ? d.d_outh != nullptr : GS == 1, out16 = GS == 2 ? d.d_in1h != nullptr : GS == 1;
+  const bool resid = !(d.flags & FVGN_MLP_NO_RESIDUAL) && (in16 ? d.d_outh != nullptr : d.d_out != nullptr);
+  const uint8_t* resid_h = in16 ? reinterpret_cast<const uint8_t*>(d.d_outh) : nullptr;   // 16-bit gradient stream (else fp32 d_out)
 
   if (tid == 0) {
     mbar_init(BAR(B_W), 1);
@@ -830,9 +868,14 @@ __global__ void __launch_bounds__(NTHREADS, 1) mlp_tc_bwd_b_kernel(const fvgn_ml
         const int64_t wrow0 = tile * TILE_M + warp * 32;
         if (resid && (MODE == FVGN_MLP_EDGE || MODE == FVGN_MLP_NODE) && wrow0 + lane < d.rows) {
           // the residual-gradient rows are read at the END of this tile (last two blocks): pull them into L2 now
-          const float* rp = d.d_out + (size_t)(wrow0 + lane) * 128;
+          if (resid_h) {
+            prefetch_l2(resid_h + (size_t)(wrow0 + lane) * 256);
+            prefetch_l2(resid_h + (size_t)(wrow0 + lane) * 256 + 128);
+          } else {
+            const float* rp = d.d_out + (size_t)(wrow0 + lane) * 128;
 #pragma unroll
-          for (int k = 0; k < 4; ++k) prefetch_l2(rp + 32 * k);
+            for (int k = 0; k < 4; ++k) prefetch_l2(rp + 32 * k);
+          }
         }
         for (int j = KB0; j < NKB1; ++j, ++blk) {
           const int ab = blk & 1;
@@ -841,13 +884,13 @@ __global__ void __launch_bounds__(NTHREADS, 1) mlp_tc_bwd_b_kernel(const fvgn_ml
           // destination of the block (uniform: boundaries are multiples of 64)
           float* dst;
           int ld, colo;
-          bool add_res = false, to_bf16 = false;
+          bool add_res = false, to_bf16 = false, in1_blk = false;
           if (MODE == FVGN_MLP_EDGE) {
             if (col0 < 256) { dst = d.d_in0; ld = 256; colo = col0; to_bf16 = d.d_in0h != nullptr; }
-            else { dst = d.d_in1; ld = 128; colo = col0 - 256; add_res = resid; }
+            else { dst = d.d_in1; ld = 128; colo = col0 - 256; add_res = resid; to_bf16 = out16; in1_blk = true; }
           } else if (MODE == FVGN_MLP_NODE) {
             if (col0 < 64) { dst = d.d_in0; ld = 64; colo = col0; to_bf16 = d.d_in0h != nullptr; }
-            else { dst = d.d_in1; ld = 128; colo = col0 - 64; add_res = resid; }
+            else { dst = d.d_in1; ld = 128; colo = col0 - 64; add_res = resid; to_bf16 = out16; in1_blk = true; }
           } else {
             dst = d.d_in0; ld = 128; colo = col0;
           }
@@ -859,9 +902,27 @@ __global__ void __launch_bounds__(NTHREADS, 1) mlp_tc_bwd_b_kernel(const fvgn_ml
             g[ps] = make_float4(0.f, 0.f, 0.f, 0.f);
             g1[ps] = g[ps];
             if (add_res && row < d.rows) {
-              const float* gp = d.d_out + (size_t)row * 128 + colo + oseg * 4;
-              g[ps] = __ldg(reinterpret_cast<const float4*>(gp));
-              g1[ps] = __ldg(reinterpret_cast<const float4*>(gp + 32));
+              // (16-bit residual rows are kept as raw bits and unpacked where they are used, so that these loads stay in
+              //  flight behind the accumulator wait)
+              if (to_bf16) {   // 16-bit destination: this lane's 8 columns of the 64-column block; residual from either stream
+                if (resid_h) {
+                  const uint4 w = __ldg(reinterpret_cast<const uint4*>(resid_h + (size_t)row * 256 + colo * 2 + oseg * 16));
+                  g[ps] = make_float4(__uint_as_float(w.x), __uint_as_float(w.y), __uint_as_float(w.z), __uint_as_float(w.w));
+                } else {
+                  const float* gp = d.d_out + (size_t)row * 128 + colo + oseg * 8;
+                  g[ps] = __ldg(reinterpret_cast<const float4*>(gp));
+                  g1[ps] = __ldg(reinterpret_cast<const float4*>(gp + 4));
+                }
+              } else if (resid_h) {   // fp32 destination, 16-bit residual: columns colo + oseg*4 .. +3 and + 32
+                const uint2 w0 = __ldg(reinterpret_cast<const uint2*>(resid_h + (size_t)row * 256 + (colo + oseg * 4) * 2));
+                const uint2 w1 = __ldg(reinterpret_cast<const uint2*>(resid_h + (size_t)row * 256 + (colo + 32 + oseg * 4) * 2));
+                g[ps].x = __uint_as_float(w0.x); g[ps].y = __uint_as_float(w0.y);
+                g1[ps].x = __uint_as_float(w1.x); g1[ps].y = __uint_as_float(w1.y);
+              } else {
+                const float* gp = d.d_out + (size_t)row * 128 + colo + oseg * 4;
+                g[ps] = __ldg(reinterpret_cast<const float4*>(gp));
+                g1[ps] = __ldg(reinterpret_cast<const float4*>(gp + 32));
+              }
             }
           }
           mbar_wait(BAR(B_AFULL + ab), (blk >> 1) & 1);
@@ -870,13 +931,13 @@ __global__ void __launch_bounds__(NTHREADS, 1) mlp_tc_bwd_b_kernel(const fvgn_ml
             // 64 columns -> 128 B of bf16 per row: one staging tile, one coalesced pass
             uint32_t r[32];
             float rs = 1.f;  // NODE: D^-1 of the transposed scatter_mean applied to this thread's row of d_a2
-            if (MODE == FVGN_MLP_NODE && d.d_in0_row_ptr != nullptr && wrow0 + lane < d.rows)
+            if (MODE == FVGN_MLP_NODE && !in1_blk && d.d_in0_row_ptr != nullptr && wrow0 + lane < d.rows)
               rs = 1.f / (float)max(__ldg(d.d_in0_row_ptr + wrow0 + lane + 1) - __ldg(d.d_in0_row_ptr + wrow0 + lane), 1);
 #pragma unroll
             for (int half = 0; half < 2; ++half) {
               tmem_ld32(tacc + 32 * half, r);
               tmem_wait_ld();
-              if (MODE == FVGN_MLP_NODE) {
+              if (MODE == FVGN_MLP_NODE && !in1_blk) {
 #pragma unroll
                 for (int k = 0; k < 32; ++k) r[k] = __float_as_uint(__uint_as_float(r[k]) * rs);
               }
@@ -891,14 +952,24 @@ __global__ void __launch_bounds__(NTHREADS, 1) mlp_tc_bwd_b_kernel(const fvgn_ml
             tc_fence_before();
             mbar_arrive(BAR(B_AFREE + ab));
             __syncwarp();
-            uint8_t* dh = reinterpret_cast<uint8_t*>(d.d_in0h);
+            uint8_t* dh = reinterpret_cast<uint8_t*>(in1_blk ? d.d_in1h : d.d_in0h);
 #pragma unroll
             for (int ps = 0; ps < 8; ++ps) {
               const int rr = ps * 4 + orow;
               const int64_t row = wrow0 + rr;
-              if (row < d.rows)
-                *reinterpret_cast<uint4*>(dh + (size_t)row * (ld * 2) + colo * 2 + oseg * 16) =
-                    *reinterpret_cast<const uint4*>(wstg_at(mystg, rr, oseg));
+              if (row < d.rows) {
+                uint4 v = *reinterpret_cast<const uint4*>(wstg_at(mystg, rr, oseg));
+                if (add_res && resid_h) {   // d_e / d_x = dX + residual gradient: both 16-bit rows, packed adds (no conversions)
+                  const float4 ga = g[ps];
+                  v = make_uint4(P::add2(v.x, __float_as_uint(ga.x)), P::add2(v.y, __float_as_uint(ga.y)),
+                                 P::add2(v.z, __float_as_uint(ga.z)), P::add2(v.w, __float_as_uint(ga.w)));
+                } else if (add_res) {       // fp32 residual gradient
+                  const float4 ga = g[ps], gb = g1[ps];
+                  v = make_uint4(pack16<P>(P::lo(v.x) + ga.x, P::hi(v.x) + ga.y), pack16<P>(P::lo(v.y) + ga.z, P::hi(v.y) + ga.w),
+                                 pack16<P>(P::lo(v.z) + gb.x, P::hi(v.z) + gb.y), pack16<P>(P::lo(v.w) + gb.z, P::hi(v.w) + gb.w));
+                }
+                *reinterpret_cast<uint4*>(dh + (size_t)row * (ld * 2) + colo * 2 + oseg * 16) = v;
+              }
             }
             __syncwarp();
           } else {
@@ -927,7 +998,12 @@ __global__ void __launch_bounds__(NTHREADS, 1) mlp_tc_bwd_b_kernel(const fvgn_ml
                 const int64_t row = wrow0 + rr;
                 if (row < d.rows) {
                   float4 v = *reinterpret_cast<const float4*>(wstg_at(mystg, rr, oseg));
-                  v = make_float4(v.x + g[ps].x, v.y + g[ps].y, v.z + g[ps].z, v.w + g[ps].w);
+                  float4 ga = g[ps];
+                  if (add_res && resid_h) {
+                    const uint32_t w0 = __float_as_uint(ga.x), w1 = __float_as_uint(ga.y);
+                    ga = make_float4(P::lo(w0), P::hi(w0), P::lo(w1), P::hi(w1));
+                  }
+                  v = make_float4(v.x + ga.x, v.y + ga.y, v.z + ga.z, v.w + ga.w);
                   *reinterpret_cast<float4*>(dst + (size_t)row * ld + colo + 32 * half + oseg * 4) = v;
                 }
               }
@@ -987,17 +1063,21 @@ template <int MODE, class P>
 int launch_tc_bwd(const fvgn_mlp_desc& d, void* stream) {
   using C = BCfg<MODE>;
   auto ka = mlp_tc_bwd_a_kernel<MODE, P>;
-  auto kb = mlp_tc_bwd_b_kernel<MODE, P, 0>;
-  constexpr int KBN = (MODE == FVGN_MLP_EDGE) ? 4 : 0;
-  auto kbn = mlp_tc_bwd_b_kernel<MODE, P, KBN>;   // EDGE with the node-level layer-1 path: e columns only
+  constexpr int KBN = (MODE == FVGN_MLP_EDGE) ? 4 : 0;   // EDGE with the node-level layer-1 path: e columns only
+  constexpr bool GRAD = MODE == FVGN_MLP_EDGE || MODE == FVGN_MLP_NODE;   // modes with a residual gradient path
   const bool node_path = MODE == FVGN_MLP_EDGE && d.d_aggh != nullptr;
-  static bool attr_set[FVGN_MAX_DEV] = {false};  // the attribute is per device
+  const int gs = !GRAD ? 0 : (d.d_outh && d.d_in1h) ? 1 : (!d.d_outh && !d.d_in1h) ? 0 : 2;
+  void (*kb)(const fvgn_mlp_desc) = mlp_tc_bwd_b_kernel<MODE, P, 0, 0>;
+  void (*kbn)(const fvgn_mlp_desc) = mlp_tc_bwd_b_kernel<MODE, P, KBN, 0>;
+  if (GRAD && gs == 1) { kb = mlp_tc_bwd_b_kernel<MODE, P, 0, GRAD ? 1 : 0>; kbn = mlp_tc_bwd_b_kernel<MODE, P, KBN, GRAD ? 1 : 0>; }
+  if (GRAD && gs == 2) { kb = mlp_tc_bwd_b_kernel<MODE, P, 0, GRAD ? 2 : 0>; kbn = mlp_tc_bwd_b_kernel<MODE, P, KBN, GRAD ? 2 : 0>; }
+  static bool attr_set[FVGN_MAX_DEV][3] = {{false}};  // the attribute is per device (and per kernel variant)
   const int dev = fvgn_cur_device();
-  if (!attr_set[dev]) {
+  if (!attr_set[dev][gs]) {
     if (cudaFuncSetAttribute(ka, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_a<MODE>()) != cudaSuccess) return FVGN_ERR_LAUNCH;
     if (cudaFuncSetAttribute(kb, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_b<MODE>()) != cudaSuccess) return FVGN_ERR_LAUNCH;
     if (cudaFuncSetAttribute(kbn, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_b<MODE>()) != cudaSuccess) return FVGN_ERR_LAUNCH;
-    attr_set[dev] = true;
+    attr_set[dev][gs] = true;
   }
   const unsigned grid = (unsigned)d.n_partials;
   ka<<<grid, A_THREADS, smem_a<MODE>(), (cudaStream_t)stream>>>(d);

@@ -220,12 +220,13 @@ def _z1_for(ctx, mode, precision, rows, like):
 
 def mlp_backward(mode, precision, rows, params, in0, in1, idx_s, idx_r, d_out, d_gather=None, d_in0=None, d_in1=None,
                  flags=0, packed=None, z1=None, in0h=None, in1h=None, d_in0h=None, d_gatherh=None, d_in0_row_ptr=None,
-                 node_path=None):
+                 node_path=None, d_outh=None, d_in1h=None):
     """Runs the fused backward; returns the list of parameter gradients (views of one flat buffer).
     packed: the bf16 weight image used by the matching forward (bf16 mode); repacked from `params` when None.
     z1: the Z1Image the matching bf16 forward filled; when None (stand-alone use) the forward is re-run to make it.
     d_in0h: EDGE, bf16 mode: [E,256] bf16 destination of d(agg[s])|d(agg[r]) (instead of the fp32 d_in0)."""
-    like = d_out if d_out is not None else d_in1   # d_out None: EDGE block whose outputs only feed the node block
+    # d_out None: EDGE block whose outputs only feed the node block, or the upstream gradient arrives as 16-bit rows (d_outh)
+    like = next(t for t in (d_out, d_outh, d_in1, d_in1h) if t is not None)
     if is_tc(precision) and z1 is None and rows > 0:
         z1 = new_z1(mode, precision, rows, like)
         mlp_forward(mode, precision, rows, params, in0, in1, idx_s, idx_r, want_out=True, want_res=False, flags=flags,
@@ -238,6 +239,10 @@ def mlp_backward(mode, precision, rows, params, in0, in1, idx_s, idx_r, d_out, d
     flat = _empty((pc,), like)
     d.d_out, d.d_gather = fptr(d_out, True), fptr(d_gather, True)
     d.d_in0, d.d_in1 = fptr(d_in0, True), fptr(d_in1, True)
+    if d_outh is not None:      # 16-bit gradient streams (f16 mode: they carry the power-of-two pre-scaling)
+        d.d_outh = hptr(d_outh)
+    if d_in1h is not None:
+        d.d_in1h = hptr(d_in1h)
     if d_in0h is not None:
         d.d_in0h = hptr(d_in0h)
     if d_gatherh is not None:
@@ -286,6 +291,34 @@ def placeholder(rows, like):
 
 def is_placeholder(t):
     return t is not None and t.dim() == 2 and t.shape[0] > 1 and t.stride() == (0, 0)
+
+
+# f16 mode with 16-bit latent streams: the GRADIENTS of those streams also travel as 16-bit rows between the blocks of a
+# model (they carry the power-of-two pre-scaling of GradScaleFn, like every other half-precision gradient tensor).  autograd
+# still sees fp32 placeholders; the rows go through a GradChannel shared by the producer and the (single) consumer of a
+# placeholder latent.  FVGN_GRAD16=0 keeps fp32 gradient streams.
+GRAD16 = os.environ.get("FVGN_GRAD16", "1") != "0"
+
+
+class GradChannel:
+    """Side channel for the 16-bit gradient rows of one (x, e) placeholder pair: the consumer's backward put()s them, the
+    producer's backward take()s them when the gradient autograd hands it is a placeholder."""
+
+    def __init__(self):
+        self.x_ref = self.e_ref = None   # the placeholder tensors this channel belongs to (identity-checked by the consumer)
+        self._g = {}
+
+    def serves(self, key, tensor):
+        return tensor is not None and (self.x_ref if key == "x" else self.e_ref) is tensor
+
+    def put(self, key, rows):
+        self._g[key] = rows
+
+    def take(self, key):
+        rows = self._g.pop(key, None)
+        if rows is None:
+            raise RuntimeError("fvgn_b200: a placeholder gradient arrived without its 16-bit rows")
+        return rows
 
 
 def _packed(mode, precision, params):
@@ -348,8 +381,9 @@ class EncoderFn(torch.autograd.Function):
     -> (node, edge, node_h, edge_h); the last two are the bf16 shadows (None in fp32 mode)."""
 
     @staticmethod
-    def forward(ctx, xn, pos, plan, precision, opts, *params):
+    def forward(ctx, xn, pos, plan, precision, opts, chan_out, *params):
         nb, eb = params[:8], params[8:]
+        ctx.chan_out = chan_out
         ctx.set_materialize_grads(False)  # no zero tensors for the (non-differentiable) bf16 shadow outputs
         ctx.pk = (_packed(_lib.FVGN_MLP_ENC_NODE, precision, nb), _packed(_lib.FVGN_MLP_ENC_EDGE, precision, eb))
         ctx.z1 = (_z1_for(ctx, _lib.FVGN_MLP_ENC_NODE, precision, plan.N, xn), _z1_for(ctx, _lib.FVGN_MLP_ENC_EDGE, precision, plan.E, xn))
@@ -366,6 +400,8 @@ class EncoderFn(torch.autograd.Function):
         ctx.save_for_backward(xn, pos, *params)
         node = rn[0] if x32 else placeholder(plan.N, xn)
         edge = re[0] if not lat16 else placeholder(plan.E, xn)
+        if chan_out is not None:
+            chan_out.x_ref, chan_out.e_ref = (None if x32 else node), (edge if lat16 else None)
         nodeh, edgeh = (rn[2], re[2]) if bf else (None, None)
         if bf:
             ctx.mark_non_differentiable(nodeh, edgeh)
@@ -375,16 +411,21 @@ class EncoderFn(torch.autograd.Function):
     def backward(ctx, d_node, d_edge, _dnh=None, _deh=None):
         xn, pos, *params = ctx.saved_tensors
         plan, precision = ctx.plan, ctx.precision
-        if d_node is None:
+        d_nodeh = d_edgeh = None
+        if is_placeholder(d_node):      # the gradient rows came through the channel (16-bit gradient streams)
+            d_nodeh, d_node = ctx.chan_out.take("x"), None
+        elif d_node is None:
             d_node = torch.zeros((plan.N, 128), device=xn.device)
-        if d_edge is None:
+        if is_placeholder(d_edge):
+            d_edgeh, d_edge = ctx.chan_out.take("e"), None
+        elif d_edge is None:
             d_edge = torch.zeros((plan.E, 128), device=xn.device)
-        gn = mlp_backward(_lib.FVGN_MLP_ENC_NODE, precision, plan.N, params[:8], xn, None, None, None, _c(d_node),
-                          packed=ctx.pk[0], z1=ctx.z1[0])
+        gn = mlp_backward(_lib.FVGN_MLP_ENC_NODE, precision, plan.N, params[:8], xn, None, None, None,
+                          None if d_node is None else _c(d_node), packed=ctx.pk[0], z1=ctx.z1[0], d_outh=d_nodeh)
         ge = mlp_backward(_lib.FVGN_MLP_ENC_EDGE, precision, plan.E, params[8:], xn, pos, plan.edge_s, plan.edge_r,
-                          _c(d_edge), packed=ctx.pk[1], z1=ctx.z1[1])
+                          None if d_edge is None else _c(d_edge), packed=ctx.pk[1], z1=ctx.z1[1], d_outh=d_edgeh)
         ctx.z1 = None
-        return (None, None, None, None, None, *gn, *ge)
+        return (None, None, None, None, None, None, *gn, *ge)
 
 
 # ------------------------------------------------------------------ GnBlock
@@ -401,9 +442,15 @@ class GnBlockFn(torch.autograd.Function):
               the bf16 shadows xh, eh, aggh, a2h and the two Z1 tile images."""
 
     @staticmethod
-    def forward(ctx, x, e, xh, eh, plan, precision, opts, *params):
+    def forward(ctx, x, e, xh, eh, plan, precision, opts, chan_in, chan_out, *params):
         eb, nb = params[:8], params[8:]
         opts = int(opts) if is_tc(precision) else GN_KEEP_E
+        # 16-bit gradient streams (f16 mode): for an input that is a placeholder served by the producer's channel, the gradient
+        # leaves through that channel as 16-bit rows; chan_out is where the consumer of this block's placeholders puts theirs
+        g16 = GRAD16 and precision == "f16" and chan_in is not None
+        ctx.chan_in, ctx.chan_out = chan_in, chan_out
+        ctx.g16_x = g16 and is_placeholder(x) and chan_in.serves("x", x)
+        ctx.g16_e = g16 and is_placeholder(e) and chan_in.serves("e", e)
         ctx.keep_e = keep_e = bool(opts & GN_KEEP_E)
         # 16-bit latent streams (tensor-core modes, set by the models for their inner blocks): the residual rows are read from
         # the 16-bit shadows the MLPs consume anyway, e + e' / x + x' leave as 16-bit rows only -- the fp32 rows of both
@@ -439,10 +486,13 @@ class GnBlockFn(torch.autograd.Function):
                                               want_out=False, want_res=(not lat16) or bool(opts & GN_X_FP32), flags=fl,
                                               packed=ctx.pk[1], z1=ctx.z1[1], in0h=a2h, in1h=xh, want_resh=True)
             if lat16:
-                if x_out is None:
+                x_ph = x_out is None
+                if x_ph:
                     x_out = placeholder(plan.N, xh)
                 if keep_e:
                     e_out = placeholder(plan.E, xh)
+                if chan_out is not None:
+                    chan_out.x_ref, chan_out.e_ref = (x_out if x_ph else None), e_out
             ctx.save_for_backward(xh, eh, aggh, a2h, *params)
             ctx.mark_non_differentiable(*(t for t in (x_outh, e_outh) if t is not None))
             return x_out, e_out, x_outh, e_outh
@@ -463,21 +513,31 @@ class GnBlockFn(torch.autograd.Function):
         plan, precision = ctx.plan, ctx.precision
         eb, nb = params[:8], params[8:]
         dev = x.device
-        d_x_out = _c(d_x_out) if d_x_out is not None else torch.zeros((plan.N, 128), device=dev)
-        if d_e_out is not None:
+        d_x_outh = d_e_outh = None   # upstream gradients that came through the channel as 16-bit rows
+        if is_placeholder(d_x_out):
+            d_x_outh, d_x_out = ctx.chan_out.take("x"), None
+        else:
+            d_x_out = _c(d_x_out) if d_x_out is not None else torch.zeros((plan.N, 128), device=dev)
+        if is_placeholder(d_e_out):
+            d_e_outh, d_e_out = ctx.chan_out.take("e"), None
+        elif d_e_out is not None:
             d_e_out = _c(d_e_out)
         elif ctx.keep_e:
             d_e_out = torch.zeros((plan.E, 128), device=dev)
-        d_a2 = _empty((plan.N, 64), d_x_out) if not is_tc(precision) else None
-        d_x = _empty((plan.N, 128), d_x_out)
-        d_e = _empty((plan.E, 128), d_x_out)
+        d_a2 = _empty((plan.N, 64), x) if not is_tc(precision) else None
+        # gradients of the inputs: fp32, or 16-bit rows handed to the producer through its channel (+ a placeholder for autograd)
+        d_x = None if ctx.g16_x else _empty((plan.N, 128), x)
+        d_e = None if ctx.g16_e else _empty((plan.E, 128), x)
+        d_xh = torch.empty((plan.N, 128), dtype=x.dtype, device=dev) if ctx.g16_x else None
+        d_eh = torch.empty((plan.E, 128), dtype=x.dtype, device=dev) if ctx.g16_e else None
         if is_tc(precision):
             BF16 = HDTYPE[precision]
             xh, eh, aggh, a2h = x, e, agg, a2
             d_a2h = torch.empty((plan.N, 64), dtype=BF16, device=dev)
             # transposed scatter_mean: d_a1 = Adj (D^-1 d_a2); the D^-1 is applied by the producing kernel's epilogue
             g_nb = mlp_backward(_lib.FVGN_MLP_NODE, precision, plan.N, nb, None, None, None, None, d_x_out, None, None, d_x,
-                                packed=ctx.pk[1], z1=ctx.z1[1], in0h=a2h, in1h=xh, d_in0h=d_a2h, d_in0_row_ptr=plan.inc_ptr)
+                                packed=ctx.pk[1], z1=ctx.z1[1], in0h=a2h, in1h=xh, d_in0h=d_a2h, d_in0_row_ptr=plan.inc_ptr,
+                                d_outh=d_x_outh, d_in1h=d_xh)
             d_a1h = adj_reduce(d_a2h, plan, 64, out_dtype=BF16)
             del d_a2h
             if NODE_LEVEL_LAYER1:
@@ -486,13 +546,13 @@ class GnBlockFn(torch.autograd.Function):
                 d_agg = torch.empty((plan.N, 128), dtype=BF16, device=dev)
                 g_eb = mlp_backward(_lib.FVGN_MLP_EDGE, precision, plan.E, eb, None, None, plan.edge_s, plan.edge_r, d_e_out,
                                     None, None, d_e, packed=ctx.pk[0], z1=ctx.z1[0], in0h=aggh, in1h=eh, d_gatherh=d_a1h,
-                                    node_path=(plan, d_agg))
+                                    node_path=(plan, d_agg), d_outh=d_e_outh, d_in1h=d_eh)
                 ctx.z1 = None
             else:
                 d_srh = torch.empty((plan.E, 256), dtype=BF16, device=dev)
                 g_eb = mlp_backward(_lib.FVGN_MLP_EDGE, precision, plan.E, eb, None, None, plan.edge_s, plan.edge_r, d_e_out,
                                     None, None, d_e, packed=ctx.pk[0], z1=ctx.z1[0], in0h=aggh, in1h=eh, d_in0h=d_srh,
-                                    d_gatherh=d_a1h)
+                                    d_gatherh=d_a1h, d_outh=d_e_outh, d_in1h=d_eh)
                 ctx.z1 = None
                 d_agg = inc_reduce(d_srh, plan, 128, out_dtype=BF16)
                 del d_srh
@@ -505,8 +565,14 @@ class GnBlockFn(torch.autograd.Function):
                                 d_sr, d_e)
             d_agg = inc_reduce(d_sr, plan, 128)
             del d_sr
-        adj_reduce(d_agg, plan, 128, _lib.FVGN_ADJ_ACCUMULATE, out=d_x)
-        return (d_x, d_e, None, None, None, None, None, *g_eb, *g_nb)
+        adj_reduce(d_agg, plan, 128, _lib.FVGN_ADJ_ACCUMULATE, out=d_xh if ctx.g16_x else d_x)
+        if ctx.g16_x:
+            ctx.chan_in.put("x", d_xh)
+            d_x = placeholder(plan.N, x)
+        if ctx.g16_e:
+            ctx.chan_in.put("e", d_eh)
+            d_e = placeholder(plan.E, x)
+        return (d_x, d_e, None, None, None, None, None, None, None, *g_eb, *g_nb)
 
 
 class EdgeBlockFn(torch.autograd.Function):

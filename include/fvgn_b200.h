@@ -161,6 +161,11 @@ typedef struct fvgn_mlp_desc {
   int32_t reserved1;
   void* node_ws;       /* optional, fvgn_mlp_bwd_node_workspace_bytes(n_nodes) bytes, 1024-B aligned: when given, the incidence sums
                         * U_s / U_r are formed by a separate memory-bound kernel as operand tile images (two kernels) */
+  /* backward, tensor-core modes, EDGE / NODE / ENC_*, optional "16-bit gradient streams" (FVGN_PREC_F16: the streams carry the
+   * power-of-two gradient pre-scaling): d_outh replaces d_out as the upstream gradient [rows,128] (16-bit rows), d_in1h
+   * replaces d_in1 as the destination of d_e / d_x = d_out + dX (EDGE / NODE).  Either side may stay fp32. */
+  const void* d_outh;
+  void* d_in1h;
 } fvgn_mlp_desc;
 
 int64_t fvgn_mlp_param_count(int32_t mode);

@@ -377,7 +377,7 @@ def test_last_block_without_edge_latent_is_identical(prec):
     res = []
     for keep in (True, False):
         x, e = x0.clone().requires_grad_(), e0.clone().requires_grad_()
-        x_out, e_out, _, _ = ops.apply(ops.GnBlockFn, x, e, None, None, plan, prec, keep, *params)
+        x_out, e_out, _, _ = ops.apply(ops.GnBlockFn, x, e, None, None, plan, prec, keep, None, None, *params)
         assert (e_out is None) == (not keep)
         grads = torch.autograd.grad(x_out, [x, e] + params, dx)
         res.append((x_out.detach(), grads))
@@ -412,11 +412,12 @@ def test_16bit_latent_streams_track_fp32_streams(prec, tol):
     x0, e0, cot = rn(plan.N, 128), rn(plan.E, 128), rn(plan.N, 3)
     res = []
     for lat in (0, ops.GN_LATENTS16):
+        ch = ops.GradChannel()   # f16: the gradients of the placeholders between the two blocks travel as 16-bit rows
         x, e = x0.clone().requires_grad_(), e0.clone().requires_grad_()
-        xa, ea, xh, eh = ops.apply(ops.GnBlockFn, x, e, None, None, plan, prec, ops.GN_KEEP_E | lat, *blocks[0])
+        xa, ea, xh, eh = ops.apply(ops.GnBlockFn, x, e, None, None, plan, prec, ops.GN_KEEP_E | lat, None, ch, *blocks[0])
         if lat:
             assert ops.is_placeholder(xa) and ops.is_placeholder(ea) and xh is not None and eh is not None
-        xb, eb, xh2, _ = ops.apply(ops.GnBlockFn, xa, ea, xh, eh, plan, prec, lat | ops.GN_X_FP32, *blocks[1])
+        xb, eb, xh2, _ = ops.apply(ops.GnBlockFn, xa, ea, xh, eh, plan, prec, lat | ops.GN_X_FP32, ch, None, *blocks[1])
         assert eb is None and not ops.is_placeholder(xb)
         assert float((xb - xh2.float()).abs().max()) <= (2e-3 if prec == "f16" else 2e-2) * float(xb.abs().max())
         out = ops.apply(ops.DecoderFn, xb, xh2, prec, *dec)
