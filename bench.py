@@ -196,9 +196,10 @@ def workload_config(args):
 
 DTYPE_TEXT = {"fp32": "f32 (SIMT FMA)",
               "bf16": "bf16 tcgen05 operands and latent streams between the GnBlocks; f32 accumulators, LayerNorm, residual adds and "
-                      "every gradient stream",
-              "f16": "f16 tcgen05 operands and latent streams between the GnBlocks (11-bit significand = the reference's TF32 GPU "
-                     "arithmetic); f32 accumulators, LayerNorm, residual adds and every gradient stream"}
+                      "gradient streams",
+              "f16": "f16 tcgen05 operands, latent streams and (power-of-two pre-scaled) gradient streams between the GnBlocks "
+                     "(11-bit significand = the reference's TF32 GPU arithmetic); f32 accumulators, LayerNorm, residual adds, "
+                     "reductions and parameter gradients"}
 
 
 # ----------------------------------------------------------------------------------------------- our arm
