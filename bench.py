@@ -658,6 +658,9 @@ NCU_TRAFFIC_BYTES_PER_EDGE = {
     # node GEMM 3.075269 + 1.008122 GB = 29.635132 GB / 8.004e6 edges (this call ends in d(agg) [N,128]; the edge-level call
     # above is followed by a separate 5 GB incidence reduction)
     "tc_node_level": (29.635132e9 / 8.004e6, "profiles/r2y_ncu_edge_bwd_node_level_8Medges.csv, per edge x E"),
+    # the same with 16-bit gradient streams in and out (f16 mode, inner blocks): A 4.739270 + 2.028844, B<KB0=4,GS=1> 6.147607 +
+    # 2.035387, dz_incidence 2.304062 + 2.010787, node GEMM 3.075331 + 1.008751 GB = 23.350039 GB
+    "tc_node_level_grad16": (23.350039e9 / 8.004e6, "profiles/r2ao_ncu_edge_bwd_grad16_8Medges.csv, per edge x E"),
     "fp32": None,
 }
 
@@ -688,6 +691,14 @@ def edge_backward_runner(plan, dev, prec, params):
     d_a1h = d_a1.to(hdt)
     if ops.NODE_LEVEL_LAYER1:
         d_agg = torch.empty((N, 128), device=dev, dtype=hdt)
+        if prec == "f16" and ops.GRAD16 and ops.LATENTS16:   # the inner blocks of a model: 16-bit gradient streams in and out
+            d_outh, d_eh = d_out.to(hdt), torch.empty((E, 128), device=dev, dtype=hdt)
+            del d_out, d_e
+            return (lambda: ops.mlp_backward(code, prec, E, params, None, None, plan.edge_s, plan.edge_r, None, None, None, None,
+                                             z1=z1, in0h=aggh, in1h=eh, d_gatherh=d_a1h, node_path=(plan, d_agg), d_outh=d_outh,
+                                             d_in1h=d_eh),
+                    "fvgn_mlp_backward<EDGE>, node-level layer 1, 16-bit gradient streams = mlp_tc_bwd_a_kernel<0> + "
+                    "mlp_tc_bwd_b_kernel<0,KB0=4,GS=1> + dz_incidence_kernel + mlp_tc_bwd_node_kernel (tcgen05)")
         return (lambda: ops.mlp_backward(code, prec, E, params, None, None, plan.edge_s, plan.edge_r, d_out, None, None, d_e,
                                          z1=z1, in0h=aggh, in1h=eh, d_gatherh=d_a1h, node_path=(plan, d_agg)),
                 "fvgn_mlp_backward<EDGE>, node-level layer 1 = mlp_tc_bwd_a_kernel<0> + mlp_tc_bwd_b_kernel<0,KB0=4> + "
@@ -729,7 +740,8 @@ def dominant_kernel_roofline(model, plan, dev, args, p):
             times.append(ev0.elapsed_time(ev1))
     ms = float(np.mean(times))
     alg = E * (3 * 512) + N * (512 + 256 + 512)
-    key = "fp32" if not bf else ("tc_node_level" if ops.NODE_LEVEL_LAYER1 else "tc_edge_level")
+    key = "fp32" if not bf else ("tc_edge_level" if not ops.NODE_LEVEL_LAYER1 else
+                                 "tc_node_level_grad16" if "16-bit gradient" in label else "tc_node_level")
     tpe = NCU_TRAFFIC_BYTES_PER_EDGE.get(key)
     return {"kernel": label, "bound": "hbm",
             "achieved": alg / (ms / 1e3) / 1e9, "unit": "GB/s", "ms_per_launch": ms, "alg_bytes_per_launch": alg,

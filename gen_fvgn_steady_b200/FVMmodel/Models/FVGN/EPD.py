@@ -106,7 +106,8 @@ class Decoder(nn.Module):
 
     def forward(self, latent_graph_node=None):
         xh = _shadow_of(latent_graph_node, "_xh", latent_graph_node.x)
-        return ops.apply(ops.DecoderFn, latent_graph_node.x, xh, _precision(self), *mlp_params(self.node_decode_module))
+        return ops.apply(ops.DecoderFn, latent_graph_node.x, xh, _precision(self), getattr(latent_graph_node, "_gch", None),
+                         *mlp_params(self.node_decode_module))
 
 
 class EncoderProcesserDecoder(nn.Module):

@@ -159,9 +159,9 @@ extern "C" int fvgn_mlp_backward(const fvgn_mlp_desc* d, void* stream) {
   if ((d->mode == FVGN_MLP_EDGE || d->mode == FVGN_MLP_NODE) && ((!d->d_in0 && !d->d_in0h && !node_path) || (!d->d_in1 && !d->d_in1h)))
     return FVGN_ERR_NULL;
   if ((d->d_in0h || d->d_gatherh) && !is_tc(d->precision)) return FVGN_ERR_UNSUPPORTED;
-  if (d->d_in0h && d->mode != FVGN_MLP_EDGE && d->mode != FVGN_MLP_NODE) return FVGN_ERR_UNSUPPORTED;
+  if (d->d_in0h && d->mode != FVGN_MLP_EDGE && d->mode != FVGN_MLP_NODE && d->mode != FVGN_MLP_DEC) return FVGN_ERR_UNSUPPORTED;
   if (!fvgn_aligned16(d->d_gatherh)) return FVGN_ERR_ALIGN;
-  if (d->mode == FVGN_MLP_DEC && !d->d_in0) return FVGN_ERR_NULL;
+  if (d->mode == FVGN_MLP_DEC && !d->d_in0 && !d->d_in0h) return FVGN_ERR_NULL;
   if (d->precision == FVGN_PREC_FP32) {
     if (d->n_partials != fvgn_mlp_simt_partials(d->rows)) return FVGN_ERR_SHAPE;
     return fvgn_mlp_backward_simt(d, stream);

@@ -892,7 +892,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) mlp_tc_bwd_b_kernel(const fvgn_ml
             if (col0 < 64) { dst = d.d_in0; ld = 64; colo = col0; to_bf16 = d.d_in0h != nullptr; }
             else { dst = d.d_in1; ld = 128; colo = col0 - 64; add_res = resid; to_bf16 = out16; in1_blk = true; }
           } else {
-            dst = d.d_in0; ld = 128; colo = col0;
+            dst = d.d_in0; ld = 128; colo = col0; to_bf16 = d.d_in0h != nullptr;   // DEC: d_x, optionally as 16-bit rows
           }
           // residual gradient of this block: both 32-column halves are requested before waiting for the accumulator
           float4 g[8], g1[8];
@@ -1066,7 +1066,9 @@ int launch_tc_bwd(const fvgn_mlp_desc& d, void* stream) {
   constexpr int KBN = (MODE == FVGN_MLP_EDGE) ? 4 : 0;   // EDGE with the node-level layer-1 path: e columns only
   constexpr bool GRAD = MODE == FVGN_MLP_EDGE || MODE == FVGN_MLP_NODE;   // modes with a residual gradient path
   const bool node_path = MODE == FVGN_MLP_EDGE && d.d_aggh != nullptr;
-  const int gs = !GRAD ? 0 : (d.d_outh && d.d_in1h) ? 1 : (!d.d_outh && !d.d_in1h) ? 0 : 2;
+  // pure 16-bit: 16-bit destination and a 16-bit (or no) upstream gradient; pure fp32 likewise; anything else is mixed
+  const bool out16 = d.d_in1h != nullptr;
+  const int gs = !GRAD ? 0 : (out16 && (d.d_outh || !d.d_out)) ? 1 : (!out16 && (d.d_out || !d.d_outh)) ? 0 : 2;
   void (*kb)(const fvgn_mlp_desc) = mlp_tc_bwd_b_kernel<MODE, P, 0, 0>;
   void (*kbn)(const fvgn_mlp_desc) = mlp_tc_bwd_b_kernel<MODE, P, KBN, 0>;
   if (GRAD && gs == 1) { kb = mlp_tc_bwd_b_kernel<MODE, P, 0, GRAD ? 1 : 0>; kbn = mlp_tc_bwd_b_kernel<MODE, P, KBN, GRAD ? 1 : 0>; }

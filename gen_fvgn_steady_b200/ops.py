@@ -638,9 +638,12 @@ class DecoderFn(torch.autograd.Function):
     """Decoder.forward (EPD.py:215-219): Linear-GELU-Linear-GELU-Linear(128->3), no LayerNorm."""
 
     @staticmethod
-    def forward(ctx, x, xh, precision, *params):
+    def forward(ctx, x, xh, precision, chan_in, *params):
         if not (is_tc(precision) and xh is not None and xh.dtype == HDTYPE[precision]):
             x = _c(x)   # (a 16-bit latent stream arrives as placeholder + shadow: only the shadow is read)
+        # f16 mode: the gradient of a placeholder latent goes back to its producer as 16-bit rows (GradChannel)
+        ctx.chan_in = chan_in if (GRAD16 and precision == "f16" and chan_in is not None and is_placeholder(x)
+                                  and chan_in.serves("x", x)) else None
         ctx.pk = _packed(_lib.FVGN_MLP_DEC, precision, params)
         ctx.z1 = _z1_for(ctx, _lib.FVGN_MLP_DEC, precision, x.shape[0], x)
         ctx.precision = precision
@@ -657,14 +660,22 @@ class DecoderFn(torch.autograd.Function):
     def backward(ctx, d_out):
         x, *params = ctx.saved_tensors
         d_out = _c(d_out)
-        d_x = _empty((x.shape[0], 128), d_out)
+        n = x.shape[0]
+        if ctx.chan_in is not None:
+            d_xh = torch.empty((n, 128), dtype=x.dtype, device=x.device)
+            g = mlp_backward(_lib.FVGN_MLP_DEC, ctx.precision, n, params, None, None, None, None, d_out, None, None,
+                             packed=ctx.pk, z1=ctx.z1, in0h=x, d_in0h=d_xh)
+            ctx.z1 = None
+            ctx.chan_in.put("x", d_xh)
+            return (placeholder(n, x), None, None, None, *g)
+        d_x = _empty((n, 128), d_out)
         if is_tc(ctx.precision):
-            g = mlp_backward(_lib.FVGN_MLP_DEC, ctx.precision, x.shape[0], params, None, None, None, None, d_out, None, d_x,
+            g = mlp_backward(_lib.FVGN_MLP_DEC, ctx.precision, n, params, None, None, None, None, d_out, None, d_x,
                              packed=ctx.pk, z1=ctx.z1, in0h=x)
             ctx.z1 = None
         else:
-            g = mlp_backward(_lib.FVGN_MLP_DEC, ctx.precision, x.shape[0], params, x, None, None, None, d_out, None, d_x)
-        return (d_x, None, None, *g)
+            g = mlp_backward(_lib.FVGN_MLP_DEC, ctx.precision, n, params, x, None, None, None, d_out, None, d_x)
+        return (d_x, None, None, None, *g)
 
 
 INTEGRATORS = {"explicit": 0, "implicit": 1, "imex": 2}

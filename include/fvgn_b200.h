@@ -133,7 +133,8 @@ typedef struct fvgn_mlp_desc {
   const void* in0h; const void* in1h;
   void* outh;      /* bf16 copy of `out` (EDGE: e' for the node aggregation; ENC_*: shadow of the encoded latent); optional */
   void* out_resh;  /* bf16 shadow of out_res; optional */
-  void* d_in0h;    /* backward, bf16 destination instead of the fp32 d_in0: EDGE [E,256] = d(agg[s]) | d(agg[r]); NODE d_a2[N,64] */
+  void* d_in0h;    /* backward, 16-bit destination instead of the fp32 d_in0: EDGE [E,256] = d(agg[s]) | d(agg[r]); NODE d_a2[N,64];
+                    * DEC d_x[N,128] */
   const void* d_gatherh; /* EDGE backward: bf16 d_a1[N,64] gathered instead of the fp32 d_gather */
   /* backward, optional device scalar: every parameter gradient is multiplied by *grad_unscale when it leaves the
    * deterministic partial reduction (1 / S of the power-of-two gradient pre-scaling the FVGN_PREC_F16 mode applies at the

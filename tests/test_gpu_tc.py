@@ -420,7 +420,7 @@ def test_16bit_latent_streams_track_fp32_streams(prec, tol):
         xb, eb, xh2, _ = ops.apply(ops.GnBlockFn, xa, ea, xh, eh, plan, prec, lat | ops.GN_X_FP32, ch, None, *blocks[1])
         assert eb is None and not ops.is_placeholder(xb)
         assert float((xb - xh2.float()).abs().max()) <= (2e-3 if prec == "f16" else 2e-2) * float(xb.abs().max())
-        out = ops.apply(ops.DecoderFn, xb, xh2, prec, *dec)
+        out = ops.apply(ops.DecoderFn, xb, xh2, prec, None, *dec)
         grads = torch.autograd.grad(out, [x, e] + blocks[0] + blocks[1] + dec, cot)
         res.append((out.detach(), xh2.float(), grads))
     torch.cuda.synchronize()
