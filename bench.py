@@ -492,7 +492,9 @@ def run_ours(args):
     N, E, C, K, X = job.sizes
     cells_total = C_global if cells_mode else world * C
 
-    for _ in range(max(args.warmup, 3)):
+    # untimed warm-up: at least 6 steps whatever --warmup says (allocator growth and lazy NCCL channel set-up take more than 3 steps
+    # to settle on 8 GPUs: with 3, the first timed region of an 8-GPU run came out 4-15 % slower than the one after it)
+    for _ in range(max(args.warmup, 6)):
         job.step(False)
     launches_per_replay = None
     if job.gstep is not None:  # count the kernels of one step with the eager path (the graph replays exactly those)
