@@ -108,8 +108,9 @@ def make_grid_mesh(n, kind="quad", jitter=0.2, seed=0, bc="cavity", lx=1.0, ly=1
 
 
 def extract_mesh_state(raw):
-    """parse_to_h5.extract_mesh_state (:257-496) on torch tensors; requires cells grouped by type with equal vertex counts
-    inside a group (what the reference's COMSOL path and make_grid_mesh produce)."""
+    """parse_to_h5.extract_mesh_state (:257-496) on torch tensors.  Cells may have any vertex count in any order (the polygon
+    meshes of the Tecplot path included: tests/test_synthetic_torch.py); the slots of a cell must be contiguous.  Like the
+    reference's sort_vertices_ccw the per-slot arrays come back regrouped by vertex count (one pass per distinct count)."""
     m = dict(raw)
     pos, node_type, face_node = m["node|pos"], m["node|node_type"], m["face|face_node"]
     cells_node, cells_index, cells_face = m["cells_node"], m["cells_index"], m["cells_face"]
