@@ -63,3 +63,37 @@ def test_placeholder_gradient_flows_through_autograd():
     Consumer.apply(Producer.apply(w)).sum().backward()
     assert seen == {"consumer_input_is_placeholder": True, "producer_got_placeholder": True}
     assert float(w.grad) == 1.0
+
+
+def test_grad_channel_closes_no_reference_cycle():
+    """ctx -> channel -> placeholder -> grad_fn (= ctx) would be a cycle only the garbage collector frees (it slowed the
+    small-mesh eager step down by 2x before the channel held its tensors weakly): with the collector off, dropping the last
+    reference to the producer's output must free it at once."""
+    import gc
+    import weakref
+    from gen_fvgn_steady_b200 import ops
+
+    class Producer(torch.autograd.Function):
+        @staticmethod
+        def forward(ctx, w, ch):
+            ctx.chan_out = ch
+            out = ops.placeholder(6, w)
+            ch.x_ref = out
+            return out
+
+        @staticmethod
+        def backward(ctx, g):
+            return torch.ones(1), None
+
+    gc.collect()
+    gc.disable()
+    try:
+        w = torch.zeros(1, requires_grad=True)
+        ch = ops.GradChannel()
+        out = Producer.apply(w, ch)
+        assert ch.serves("x", out)
+        probe = weakref.ref(out)
+        del out, ch
+        assert probe() is None
+    finally:
+        gc.enable()
